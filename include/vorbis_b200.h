@@ -1,0 +1,218 @@
+/* vorbis_b200.h — C ABI of the B200-native per-block DSP path of libvorbis.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the xiph/vorbis tree, libvorbis 1.3.7).  The reference-side binding a
+ * libvorbis maintainer would add (a replacement `mapping0_exportbundle`) is
+ * shown in INTEGRATION.md and implemented in vorbis_b200/host/.
+ *
+ * Conventions
+ *   - return 0 on success, a negative OV_* style code on failure (never abort;
+ *     lib/mapping0.c:498 returns -1, include/vorbis/codec.h:217-233 OV_*);
+ *     vb200_last_error() gives a thread-local message.
+ *   - N  = block size in samples (vorbis_block.pcmend), n = N/2 spectral lines.
+ *   - W  = block-size flag (0 short, 1 long), as vorbis_block.W.
+ *   - batches are homogeneous in W; vectors are laid out [block][channel][...]
+ *     contiguous fp32 (the reference's vb->pcm[ch][N] stacked block-major).
+ *   - functions ending in _dev take DEVICE pointers and a cudaStream_t passed
+ *     as void* (NULL = legacy default stream) and are asynchronous;
+ *     the others take HOST pointers, copy in/out and synchronise.
+ */
+#ifndef VORBIS_B200_H
+#define VORBIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_OK        0
+#define VB200_EFAULT  (-129)   /* OV_EFAULT: CUDA/runtime failure            */
+#define VB200_EIMPL   (-130)   /* OV_EIMPL : configuration not supported      */
+#define VB200_EINVAL  (-131)   /* OV_EINVAL: bad argument                     */
+
+#define VB200_P_BANDS        17   /* lib/psy.h:28  */
+#define VB200_P_LEVELS        8   /* lib/psy.h:29  */
+#define VB200_P_NOISECURVES   3   /* lib/psy.h:31  */
+#define VB200_EHMER_MAX      56   /* lib/masking.h:43 */
+#define VB200_COMPAND_LEVELS 40   /* lib/psy.h:33  */
+#define VB200_PACKETBLOBS    15   /* lib/codec_internal.h:28 */
+#define VB200_MAX_CHANNELS  255
+#define VB200_MAX_COUPLING  256
+
+/* One psychoacoustic lookup == vorbis_look_psy + the vorbis_info_psy scalars
+ * the per-block code reads (lib/psy.h:35-65, 96-114).  Built by the
+ * reference's _vp_psy_init (lib/psy.c:266); we only consume it.            */
+typedef struct vb200_psy_setup {
+  int32_t n;                      /* vorbis_look_psy.n  (= blocksize/2)      */
+  int32_t blockflag;              /* vorbis_info_psy.blockflag               */
+  float   ath_adjatt;
+  float   ath_maxatt;
+  float   tone_masteratt[VB200_P_NOISECURVES];
+  float   tone_abs_limit;
+  float   noisemaxsupp;
+  int32_t noisewindowfixed;
+  float   noisecompand[VB200_COMPAND_LEVELS];
+  float   max_curve_dB;
+  int32_t normal_p;
+  int32_t normal_start;
+  int32_t normal_partition;
+  double  normal_thresh;
+  int32_t firstoc;
+  int32_t shiftoc;
+  int32_t eighth_octave_lines;
+  int32_t total_octave_lines;
+  float   m_val;
+  const float   *ath;             /* [n]                                      */
+  const int32_t *octave;          /* [n]   (reference: long)                  */
+  const int32_t *bark;            /* [n]   packed ((lo-1)<<16)+(hi-1)         */
+  const float   *tonecurves;      /* [P_BANDS][P_LEVELS][EHMER_MAX+2]         */
+  const float   *noiseoffset;     /* [P_NOISECURVES][n]                       */
+} vb200_psy_setup;
+
+/* Everything the kernels need from codec_setup_info / private_state
+ * (lib/codec_internal.h:59-133) for one (channels, rate, quality) setup.    */
+typedef struct vb200_setup {
+  int32_t channels;
+  int32_t rate;
+  int32_t blocksizes[2];          /* codec_setup_info.blocksizes              */
+  int32_t n_psy;                  /* 0 (decode/transform only) or 4           */
+  vb200_psy_setup psy[4];         /* private_state.psy[blocktype+2*W]         */
+  /* vorbis_info_psy_global (lib/psy.h:67-85) */
+  float   ampmax_att_per_sec;
+  int32_t coupling_pointlimit[2][VB200_PACKETBLOBS];
+  int32_t coupling_prepointamp[VB200_PACKETBLOBS];
+  int32_t coupling_postpointamp[VB200_PACKETBLOBS];
+  int32_t sliding_lowpass[2][VB200_PACKETBLOBS];
+  /* vorbis_info_mapping0 coupling (lib/backends.h:127-141), per W           */
+  int32_t coupling_steps[2];
+  int32_t coupling_mag[2][VB200_MAX_COUPLING];
+  int32_t coupling_ang[2][VB200_MAX_COUPLING];
+  /* optional half-window tables, vwin[] of lib/window.c:23-2096 for
+   * blocksizes[0] and [1] (blocksize/2 floats each); NULL = compute from the
+   * closed form of doc/04-codec.tex:320                                     */
+  const float *window[2];
+} vb200_setup;
+
+/* Per-block inputs of mapping0_forward that are not PCM (lib/mapping0.c:230-252) */
+typedef struct vb200_block_desc {
+  int32_t lW;                     /* vorbis_block.lW                          */
+  int32_t nW;                     /* vorbis_block.nW                          */
+  int32_t blocktype;              /* vorbis_block_internal.blocktype (0/1)    */
+  float   ampmax;                 /* vorbis_block_internal.ampmax on entry    */
+} vb200_block_desc;
+
+typedef struct vb200_ctx vb200_ctx;
+
+/* ---- context ---------------------------------------------------------- */
+/* replaces the lookup building of _vds_shared_init (lib/block.c:170-294):
+ * mdct_init, drft_init are recomputed here from the block sizes; the psy
+ * lookups and windows are uploaded as given.                                */
+int  vb200_ctx_create(const vb200_setup *setup, int device, vb200_ctx **out);
+void vb200_ctx_destroy(vb200_ctx *ctx);
+int  vb200_device_count(void);
+const char *vb200_last_error(void);
+/* host copies of the tables the context derived itself (for parity tests):
+ * which: 0 mdct trig (N+N/4), 1 mdct bitrev (N/4 int32), 2 window (N/2),
+ * 3 fft twiddles (N).  Returns element count or <0.                         */
+int  vb200_ctx_table(vb200_ctx *ctx, int W, int which, void *dst, int cap);
+/* kernels launched through this context since creation (bench evidence)     */
+uint64_t vb200_launch_count(vb200_ctx *ctx);
+
+/* ---- transforms ------------------------------------- */
+/* mdct_forward, lib/mdct.c:492: in [nvec][N] -> out [nvec][N/2]            */
+int vb200_mdct_forward_dev (vb200_ctx*, int W, int nvec, const float *d_in, float *d_out, void *stream);
+int vb200_mdct_forward     (vb200_ctx*, int W, int nvec, const float *in,   float *out);
+/* mdct_backward, lib/mdct.c:396: in [nvec][N/2] -> out [nvec][N]           */
+int vb200_mdct_backward_dev(vb200_ctx*, int W, int nvec, const float *d_in, float *d_out, void *stream);
+int vb200_mdct_backward    (vb200_ctx*, int W, int nvec, const float *in,   float *out);
+/* _vorbis_apply_window, lib/window.c:2102: in place on [nvec][N];
+ * lW/nW are per-vector int32 arrays (host) or NULL for W=0                  */
+int vb200_apply_window     (vb200_ctx*, int W, int nvec, const int32_t *lW, const int32_t *nW, float *data);
+/* drft_forward, lib/smallft.c:1231: in place on [nvec][N], FFTPACK layout   */
+int vb200_drft_forward     (vb200_ctx*, int W, int nvec, float *data);
+
+/* ---- psychoacoustic stages, stage-isolated --------- */
+/* look = blocktype + 2*W selects vb200_setup.psy[look]                      */
+/* _vp_noisemask, lib/psy.c:706: logmdct [nvec][n] -> noise [nvec][n]       */
+int vb200_noisemask        (vb200_ctx*, int look, int nvec, const float *logmdct, float *noise);
+/* _vp_tonemask, lib/psy.c:754: logfft [nvec][n], specmax per vector         */
+int vb200_tonemask         (vb200_ctx*, int look, int nvec, const float *logfft,
+                            const float *global_specmax, const float *local_specmax, float *tone);
+/* _vp_offset_and_mix, lib/psy.c:779: writes logmask, scales mdct in place   */
+int vb200_offset_and_mix   (vb200_ctx*, int look, int nvec, int offset_select,
+                            const float *noise, const float *tone,
+                            float *mdct, const float *logmdct, float *logmask);
+
+/* ---- encode Phase A: the per-channel loops of mapping0_forward
+ *      (lib/mapping0.c:254-470): window, MDCT, FFT, log spectra, ampmax,
+ *      noise mask, tone mask, offset_and_mix(select 1).
+ * pcm     [nblocks][ch][N]   un-windowed block PCM (vb->pcm), read-only
+ * desc    [nblocks]
+ * mdct    [nblocks][ch][n]   gmdct after the AoTuV-M1 scaling (mapping0.c:463)
+ * logmdct [nblocks][ch][n]   input of floor1_fit (mapping0.c:500)
+ * logmask [nblocks][ch][n]   input of floor1_fit
+ * ampmax_out [nblocks]       vorbis_block_internal.ampmax on exit (mapping0.c:576)
+ * Optional taps (may be NULL): noise, tone, logfft [nblocks][ch][n], raw mdct. */
+typedef struct vb200_phaseA_io {
+  const float *pcm;
+  const vb200_block_desc *desc;
+  float *mdct;
+  float *logmdct;
+  float *logmask;
+  float *ampmax_out;
+  float *tap_noise;
+  float *tap_tone;
+  float *tap_logfft;
+  float *tap_mdct_raw;
+} vb200_phaseA_io;
+int vb200_analysis_phaseA_dev(vb200_ctx*, int W, int nblocks, const vb200_phaseA_io *d_io, void *stream);
+int vb200_analysis_phaseA    (vb200_ctx*, int W, int nblocks, const vb200_phaseA_io *io);
+
+/* Stream mode: `nstreams` streams of `blocks_per_stream` consecutive blocks
+ * (block index = stream*blocks_per_stream + k).  desc[].ampmax is ignored;
+ * the ampmax chain of vorbis_analysis_blockout (lib/block.c:626-628,
+ * lib/psy.c:837-848) is evaluated on the device between the transform and
+ * the psy kernel, starting from `ampmax0[stream]` (NULL = -9999).           */
+int vb200_analysis_phaseA_streams_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream,
+                                      const vb200_phaseA_io *d_io, const float *d_ampmax0, void *stream);
+
+/* ---- encode Phase B: _vp_couple_quantize_normalize, lib/psy.c:1014 ----
+ * mdct  [nblocks][ch][n]  (Phase A output)
+ * iwork [nblocks][ch][n]  in: ilogmask from floor1_encode (0..1023 dB index,
+ *                         mapping0.c:617), out: quantised residue ints
+ * nonzero [nblocks][ch]   in/out                                            */
+int vb200_couple_quantize_normalize_dev(vb200_ctx*, int W, int blocktype, int blobno, int nblocks,
+                                        const float *d_mdct, int32_t *d_iwork, int32_t *d_nonzero, void *stream);
+int vb200_couple_quantize_normalize    (vb200_ctx*, int W, int blocktype, int blobno, int nblocks,
+                                        const float *mdct, int32_t *iwork, int32_t *nonzero);
+
+/* ---- decode: mdct_backward (lib/mapping0.c:792-795) fused with the windowed
+ *      overlap-add of vorbis_synthesis_blockin (lib/block.c:767-823).
+ * `nstreams` independent streams x `ch` channels, each `nblk` blocks long.
+ * Wseq  [nstreams][nblk] int32 block-size flags
+ * coef_off [nstreams][nblk] int64 offset (floats) of block k's spectra inside
+ *       `coef`; channel c of that block is at coef_off + c*n_k
+ * pcm_off  [nstreams][nblk] int64 offset (floats) into each channel's output
+ *       where the samples finished by block k go (k=0 finishes nothing)
+ * pcm   [nstreams][ch][pcm_stride]                                          */
+int vb200_synthesis_dev(vb200_ctx*, int nstreams, int nblk, const int32_t *d_Wseq,
+                        const int64_t *d_coef_off, const float *d_coef,
+                        const int64_t *d_pcm_off, float *d_pcm, int64_t pcm_stride, void *stream);
+int vb200_synthesis    (vb200_ctx*, int nstreams, int nblk, const int32_t *Wseq,
+                        const int64_t *coef_off, const float *coef, int64_t coef_len,
+                        const int64_t *pcm_off, float *pcm, int64_t pcm_stride);
+
+/* ---- device memory helpers for non-CUDA hosts (C callers) -------------- */
+int  vb200_malloc_device(vb200_ctx*, size_t bytes, void **dptr);
+int  vb200_free_device  (vb200_ctx*, void *dptr);
+int  vb200_memcpy_h2d   (vb200_ctx*, void *dptr, const void *src, size_t bytes);
+int  vb200_memcpy_d2h   (vb200_ctx*, void *dst, const void *dptr, size_t bytes);
+int  vb200_synchronize  (vb200_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VORBIS_B200_H */

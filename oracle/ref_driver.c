@@ -1,0 +1,635 @@
+/* ref_driver.c — thin driver around the UNMODIFIED reference sources.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is compiled together with the
+ * reference's own lib/*.c (read in place from /root/reference, never copied)
+ * into oracle/_ref/libvorbis_ref.so by oracle/Makefile.  It
+ *   (1) exposes the reference's hot-path functions (mdct_forward, drft_forward,
+ *       _vorbis_apply_window, _vp_noisemask, _vp_tonemask, _vp_offset_and_mix,
+ *       _vp_couple_quantize_normalize, mdct_backward, vorbis_synthesis_blockin)
+ *       behind flat C entry points that ctypes can call;
+ *   (2) dumps the lookup tables the reference builds in _vds_shared_init
+ *       (lib/block.c:170) into the vb200_setup layout of include/vorbis_b200.h;
+ *   (3) runs the real encoder / decoder API loop (as in
+ *       examples/encoder_example.c:210-235) and records every intermediate
+ *       vector of mapping0_forward / mapping0_inverse.  The recording works by
+ *       compiling lib/mapping0.c with -D<callee>=spy_<callee> (see Makefile):
+ *       the reference source is unchanged, its calls just land in the spy_*
+ *       functions below, which copy the arguments and forward to the real
+ *       callee.
+ * Nothing here is on the product path.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include "vorbis/codec.h"
+#include "vorbis/vorbisenc.h"
+#include "codec_internal.h"
+#include "registry.h"
+#include "mdct.h"
+#include "smallft.h"
+#include "window.h"
+#include "psy.h"
+#include "scales.h"
+
+#include "vorbis_b200.h"
+
+/* ------------------------------------------------------------------------ */
+typedef struct ref_handle {
+  vorbis_info      vi;
+  vorbis_comment   vc;
+  vorbis_dsp_state vd;
+  vorbis_block     vb;
+  int              channels;
+  long             rate;
+  /* converted copies of tables for vb200_setup */
+  int32_t *octave[4];
+  int32_t *bark[4];
+  float   *tonecurves[4];
+  float   *noiseoffset[4];
+  /* encoded packets kept for the decode capture */
+  unsigned char **pkt;
+  long  *pktbytes;
+  int    npkt, pktcap;
+  ogg_packet hdr[3];
+  unsigned char *hdrcopy[3];
+} ref_handle;
+
+void *ref_open(int channels, long rate, float quality){
+  ref_handle *h = (ref_handle*)calloc(1, sizeof(*h));
+  vorbis_info_init(&h->vi);
+  if(vorbis_encode_init_vbr(&h->vi, channels, rate, quality)){
+    vorbis_info_clear(&h->vi);
+    free(h);
+    return NULL;
+  }
+  vorbis_comment_init(&h->vc);
+  vorbis_analysis_init(&h->vd, &h->vi);
+  vorbis_block_init(&h->vd, &h->vb);
+  h->channels = channels;
+  h->rate = rate;
+  return h;
+}
+
+void ref_close(void *hv){
+  ref_handle *h = (ref_handle*)hv;
+  int i;
+  if(!h) return;
+  for(i=0;i<4;i++){
+    free(h->octave[i]); free(h->bark[i]); free(h->tonecurves[i]); free(h->noiseoffset[i]);
+  }
+  for(i=0;i<h->npkt;i++) free(h->pkt[i]);
+  free(h->pkt); free(h->pktbytes);
+  for(i=0;i<3;i++) free(h->hdrcopy[i]);
+  vorbis_block_clear(&h->vb);
+  vorbis_dsp_clear(&h->vd);
+  vorbis_comment_clear(&h->vc);
+  vorbis_info_clear(&h->vi);
+  free(h);
+}
+
+int ref_blocksize(void *hv, int W){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  return (int)ci->blocksizes[W];
+}
+
+/* fill a vb200_setup from the reference's own lookups */
+int ref_get_setup(void *hv, vb200_setup *s){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_info_psy_global *g = &ci->psy_g_param;
+  int i,j,k,w;
+  memset(s,0,sizeof(*s));
+  s->channels = h->vi.channels;
+  s->rate = (int32_t)h->vi.rate;
+  s->blocksizes[0] = (int32_t)ci->blocksizes[0];
+  s->blocksizes[1] = (int32_t)ci->blocksizes[1];
+  s->n_psy = ci->psys;
+  if(ci->psys != 4) return -1;
+  for(i=0;i<4;i++){
+    vorbis_look_psy *p = b->psy+i;
+    vorbis_info_psy *pi = p->vi;
+    vb200_psy_setup *o = &s->psy[i];
+    int n = p->n;
+    o->n = n;
+    o->blockflag = pi->blockflag;
+    o->ath_adjatt = pi->ath_adjatt;
+    o->ath_maxatt = pi->ath_maxatt;
+    for(j=0;j<P_NOISECURVES;j++) o->tone_masteratt[j] = pi->tone_masteratt[j];
+    o->tone_abs_limit = pi->tone_abs_limit;
+    o->noisemaxsupp = pi->noisemaxsupp;
+    o->noisewindowfixed = pi->noisewindowfixed;
+    for(j=0;j<NOISE_COMPAND_LEVELS;j++) o->noisecompand[j] = pi->noisecompand[j];
+    o->max_curve_dB = pi->max_curve_dB;
+    o->normal_p = pi->normal_p;
+    o->normal_start = pi->normal_start;
+    o->normal_partition = pi->normal_partition;
+    o->normal_thresh = pi->normal_thresh;
+    o->firstoc = (int32_t)p->firstoc;
+    o->shiftoc = (int32_t)p->shiftoc;
+    o->eighth_octave_lines = p->eighth_octave_lines;
+    o->total_octave_lines = p->total_octave_lines;
+    o->m_val = p->m_val;
+    o->ath = p->ath;
+    if(!h->octave[i]){
+      h->octave[i] = (int32_t*)malloc(sizeof(int32_t)*n);
+      h->bark[i]   = (int32_t*)malloc(sizeof(int32_t)*n);
+      h->tonecurves[i] = (float*)malloc(sizeof(float)*P_BANDS*P_LEVELS*(EHMER_MAX+2));
+      h->noiseoffset[i] = (float*)malloc(sizeof(float)*P_NOISECURVES*n);
+      for(j=0;j<n;j++){ h->octave[i][j]=(int32_t)p->octave[j]; h->bark[i][j]=(int32_t)p->bark[j]; }
+      for(j=0;j<P_BANDS;j++)for(k=0;k<P_LEVELS;k++)
+        memcpy(h->tonecurves[i]+(j*P_LEVELS+k)*(EHMER_MAX+2), p->tonecurves[j][k], sizeof(float)*(EHMER_MAX+2));
+      for(j=0;j<P_NOISECURVES;j++)
+        memcpy(h->noiseoffset[i]+j*n, p->noiseoffset[j], sizeof(float)*n);
+    }
+    o->octave = h->octave[i];
+    o->bark = h->bark[i];
+    o->tonecurves = h->tonecurves[i];
+    o->noiseoffset = h->noiseoffset[i];
+  }
+  s->ampmax_att_per_sec = g->ampmax_att_per_sec;
+  for(k=0;k<PACKETBLOBS;k++){
+    s->coupling_pointlimit[0][k]=g->coupling_pointlimit[0][k];
+    s->coupling_pointlimit[1][k]=g->coupling_pointlimit[1][k];
+    s->coupling_prepointamp[k]=g->coupling_prepointamp[k];
+    s->coupling_postpointamp[k]=g->coupling_postpointamp[k];
+    s->sliding_lowpass[0][k]=g->sliding_lowpass[0][k];
+    s->sliding_lowpass[1][k]=g->sliding_lowpass[1][k];
+  }
+  for(w=0;w<2;w++){
+    /* mode w uses map_param[mode_param[w]->mapping]; vorbisenc sets modes==maps */
+    vorbis_info_mapping0 *m = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[w]->mapping];
+    s->coupling_steps[w]=m->coupling_steps;
+    for(k=0;k<m->coupling_steps;k++){
+      s->coupling_mag[w][k]=m->coupling_mag[k];
+      s->coupling_ang[w][k]=m->coupling_ang[k];
+    }
+  }
+  s->window[0] = _vorbis_window_get(b->window[0]);
+  s->window[1] = _vorbis_window_get(b->window[1]);
+  return 0;
+}
+
+/* copies of the reference's derived transform tables (for table parity tests):
+ * which: 0 mdct trig (N+N/4), 1 bitrev (N/4), 2 window (N/2), 3 fft wa (N) */
+int ref_get_table(void *hv, int W, int which, void *dst, int cap){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  int N = (int)ci->blocksizes[W];
+  mdct_lookup *m = (mdct_lookup*)b->transform[W][0];
+  switch(which){
+  case 0: if(cap<N+N/4) return -1; memcpy(dst,m->trig,sizeof(float)*(N+N/4)); return N+N/4;
+  case 1: if(cap<N/4) return -1; memcpy(dst,m->bitrev,sizeof(int)*(N/4)); return N/4;
+  case 2: if(cap<N/2) return -1; memcpy(dst,_vorbis_window_get(b->window[W]),sizeof(float)*(N/2)); return N/2;
+  case 3: if(cap<N) return -1; memcpy(dst,b->fft_look[W].trigcache+N,sizeof(float)*N); return N;
+  }
+  return -1;
+}
+
+/* ---- stage-level calls into the reference ------------------------------ */
+void ref_mdct_forward(void *hv, int W, int nvec, const float *in, float *out){
+  ref_handle *h = (ref_handle*)hv;
+  private_state *b = (private_state*)h->vd.backend_state;
+  int N = ref_blocksize(hv,W), v;
+  float *tmp = (float*)malloc(sizeof(float)*N);
+  for(v=0;v<nvec;v++){
+    memcpy(tmp,in+(size_t)v*N,sizeof(float)*N);
+    mdct_forward((mdct_lookup*)b->transform[W][0],tmp,out+(size_t)v*(N/2));
+  }
+  free(tmp);
+}
+
+void ref_mdct_backward(void *hv, int W, int nvec, const float *in, float *out){
+  ref_handle *h = (ref_handle*)hv;
+  private_state *b = (private_state*)h->vd.backend_state;
+  int N = ref_blocksize(hv,W), v;
+  for(v=0;v<nvec;v++){
+    float *o = out+(size_t)v*N;
+    memcpy(o,in+(size_t)v*(N/2),sizeof(float)*(N/2));
+    mdct_backward((mdct_lookup*)b->transform[W][0],o,o); /* in place, as lib/mapping0.c:794 */
+  }
+}
+
+void ref_apply_window(void *hv, int W, int nvec, const int32_t *lW, const int32_t *nW, float *data){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  int N = ref_blocksize(hv,W), v;
+  for(v=0;v<nvec;v++)
+    _vorbis_apply_window(data+(size_t)v*N,b->window,ci->blocksizes,lW?lW[v]:0,W,nW?nW[v]:0);
+}
+
+void ref_drft_forward(void *hv, int W, int nvec, float *data){
+  ref_handle *h = (ref_handle*)hv;
+  private_state *b = (private_state*)h->vd.backend_state;
+  int N = ref_blocksize(hv,W), v;
+  for(v=0;v<nvec;v++) drft_forward(&b->fft_look[W],data+(size_t)v*N);
+}
+
+void ref_noisemask(void *hv, int look, int nvec, const float *logmdct, float *noise){
+  ref_handle *h = (ref_handle*)hv;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_look_psy *p = b->psy+look;
+  int n = p->n, v;
+  float *tmp = (float*)malloc(sizeof(float)*n);
+  for(v=0;v<nvec;v++){
+    memcpy(tmp,logmdct+(size_t)v*n,sizeof(float)*n);
+    _vp_noisemask(p,tmp,noise+(size_t)v*n);
+  }
+  free(tmp);
+}
+
+void ref_tonemask(void *hv, int look, int nvec, const float *logfft,
+                  const float *gmax, const float *lmax, float *tone){
+  ref_handle *h = (ref_handle*)hv;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_look_psy *p = b->psy+look;
+  int n = p->n, v;
+  float *tmp = (float*)malloc(sizeof(float)*n);
+  for(v=0;v<nvec;v++){
+    memcpy(tmp,logfft+(size_t)v*n,sizeof(float)*n);
+    _vp_tonemask(p,tmp,tone+(size_t)v*n,gmax[v],lmax[v]);
+  }
+  free(tmp);
+}
+
+void ref_offset_and_mix(void *hv, int look, int nvec, int offset_select,
+                        const float *noise, const float *tone,
+                        float *mdct, const float *logmdct, float *logmask){
+  ref_handle *h = (ref_handle*)hv;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_look_psy *p = b->psy+look;
+  int n = p->n, v;
+  for(v=0;v<nvec;v++){
+    size_t o=(size_t)v*n;
+    _vp_offset_and_mix(p,(float*)noise+o,(float*)tone+o,offset_select,logmask+o,mdct+o,(float*)logmdct+o);
+  }
+}
+
+/* _vp_couple_quantize_normalize over a batch; layouts [block][ch][n] */
+void ref_couple_quantize_normalize(void *hv, int W, int blocktype, int blobno, int nblocks,
+                                   float *mdct, int32_t *iwork, int32_t *nonzero){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_look_psy *p = b->psy+blocktype+(W?2:0);
+  vorbis_info_mapping0 *info = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[W]->mapping];
+  int ch = h->vi.channels, n = p->n, blk, c;
+  float **m = (float**)malloc(sizeof(*m)*ch);
+  int   **iw = (int**)malloc(sizeof(*iw)*ch);
+  int    *nz = (int*)malloc(sizeof(int)*ch);
+  for(blk=0;blk<nblocks;blk++){
+    for(c=0;c<ch;c++){
+      m[c] = mdct+((size_t)blk*ch+c)*n;
+      iw[c] = (int*)(iwork+((size_t)blk*ch+c)*n);
+      nz[c] = nonzero[(size_t)blk*ch+c];
+    }
+    _vp_couple_quantize_normalize(blobno,&ci->psy_g_param,p,info,m,iw,nz,
+                                  ci->psy_g_param.sliding_lowpass[W][blobno],ch);
+    for(c=0;c<ch;c++) nonzero[(size_t)blk*ch+c]=nz[c];
+  }
+  free(m); free(iw); free(nz);
+}
+
+float ref_ampmax_decay(void *hv, float amp, int W){
+  ref_handle *h = (ref_handle*)hv;
+  long save = h->vd.W;
+  float r;
+  h->vd.W = W;
+  r = _vp_ampmax_decay(amp,&h->vd);
+  h->vd.W = save;
+  return r;
+}
+
+/* ---- capture of the real API loop --------------------------------------- */
+typedef struct ref_capture {
+  int   maxblocks;
+  int   Nmax;            /* row stride for N-long vectors; n-long use Nmax/2 */
+  int   nblocks;         /* out: blocks seen */
+  /* per block */
+  int32_t *W, *lW, *nW, *blocktype;
+  float   *ampmax_in, *ampmax_out;
+  /* per block x channel; NULL = don't capture */
+  float *pcm;        /* [blk][ch][Nmax]  vb->pcm before windowing */
+  float *windowed;   /* [blk][ch][Nmax] */
+  float *fft;        /* [blk][ch][Nmax]  drft_forward output */
+  float *mdct_raw;   /* [blk][ch][Nmax/2] */
+  float *logfft;     /* tonemask input */
+  float *logmdct;    /* noisemask input */
+  float *noise;
+  float *tone;
+  float *logmask;    /* after offset_and_mix(select 1) */
+  float *mdct_m1;    /* gmdct after offset_and_mix(select 1) */
+  float *local_ampmax;   /* [blk][ch] */
+  float *global_ampmax;  /* [blk] value passed to _vp_tonemask */
+  int32_t *ilogmask;     /* [blk][ch][Nmax/2] iwork entering CQN (blob 7) */
+  int32_t *iwork_out;    /* [blk][ch][Nmax/2] iwork leaving CQN */
+  int32_t *nonzero_in;   /* [blk][ch] */
+  int32_t *nonzero_out;  /* [blk][ch] */
+  /* decode side */
+  float *dec_coef;   /* [blk][ch][Nmax/2] input of mdct_backward */
+  float *dec_imdct;  /* [blk][ch][Nmax]   output of mdct_backward */
+} ref_capture;
+
+static ref_capture *g_cap = NULL;
+static int g_blk = -1;
+static int g_ch_total = 0;
+static int g_cnt_window, g_cnt_mdct, g_cnt_fft, g_cnt_noise, g_cnt_tone, g_cnt_mix, g_cnt_imdct;
+
+static int cap_on(void){ return g_cap && g_blk>=0 && g_blk<g_cap->maxblocks; }
+static float *rowN(float *base,int c){ return base+((size_t)g_blk*g_ch_total+c)*g_cap->Nmax; }
+static float *rown(float *base,int c){ return base+((size_t)g_blk*g_ch_total+c)*(g_cap->Nmax/2); }
+static int32_t *irown(int32_t *base,int c){ return base+((size_t)g_blk*g_ch_total+c)*(g_cap->Nmax/2); }
+
+/* spies: lib/mapping0.c is compiled with -D<name>=spy_<name> (oracle/Makefile) */
+void spy__vorbis_apply_window(float *d,int *winno,long *blocksizes,int lW,int W,int nW){
+  int N = (int)blocksizes[W];
+  int c = g_cnt_window++;
+  if(cap_on() && g_cap->pcm) memcpy(rowN(g_cap->pcm,c),d,sizeof(float)*N);
+  _vorbis_apply_window(d,winno,blocksizes,lW,W,nW);
+  if(cap_on() && g_cap->windowed) memcpy(rowN(g_cap->windowed,c),d,sizeof(float)*N);
+}
+
+void spy_mdct_forward(mdct_lookup *init, float *in, float *out){
+  int c = g_cnt_mdct++;
+  mdct_forward(init,in,out);
+  if(cap_on() && g_cap->mdct_raw) memcpy(rown(g_cap->mdct_raw,c),out,sizeof(float)*(init->n/2));
+}
+
+void spy_drft_forward(drft_lookup *l,float *data){
+  int c = g_cnt_fft++;
+  drft_forward(l,data);
+  if(cap_on() && g_cap->fft) memcpy(rowN(g_cap->fft,c),data,sizeof(float)*l->n);
+}
+
+void spy__vp_noisemask(vorbis_look_psy *p,float *logmdct,float *logmask){
+  int c = g_cnt_noise++;
+  if(cap_on() && g_cap->logmdct) memcpy(rown(g_cap->logmdct,c),logmdct,sizeof(float)*p->n);
+  _vp_noisemask(p,logmdct,logmask);
+  if(cap_on() && g_cap->noise) memcpy(rown(g_cap->noise,c),logmask,sizeof(float)*p->n);
+}
+
+void spy__vp_tonemask(vorbis_look_psy *p,float *logfft,float *logmask,float gmax,float lmax){
+  int c = g_cnt_tone++;
+  if(cap_on()){
+    if(g_cap->logfft) memcpy(rown(g_cap->logfft,c),logfft,sizeof(float)*p->n);
+    if(g_cap->local_ampmax) g_cap->local_ampmax[(size_t)g_blk*g_ch_total+c]=lmax;
+    if(g_cap->global_ampmax) g_cap->global_ampmax[g_blk]=gmax;
+  }
+  _vp_tonemask(p,logfft,logmask,gmax,lmax);
+  if(cap_on() && g_cap->tone) memcpy(rown(g_cap->tone,c),logmask,sizeof(float)*p->n);
+}
+
+void spy__vp_offset_and_mix(vorbis_look_psy *p,float *noise,float *tone,int offset_select,
+                            float *logmask,float *mdct,float *logmdct){
+  _vp_offset_and_mix(p,noise,tone,offset_select,logmask,mdct,logmdct);
+  if(offset_select==1){
+    int c = g_cnt_mix++;
+    if(cap_on()){
+      if(g_cap->logmask) memcpy(rown(g_cap->logmask,c),logmask,sizeof(float)*p->n);
+      if(g_cap->mdct_m1) memcpy(rown(g_cap->mdct_m1,c),mdct,sizeof(float)*p->n);
+    }
+  }
+}
+
+void spy__vp_couple_quantize_normalize(int blobno,vorbis_info_psy_global *g,vorbis_look_psy *p,
+                                       vorbis_info_mapping0 *vi,float **mdct,int **iwork,
+                                       int *nonzero,int sliding_lowpass,int ch){
+  int c, on = cap_on() && blobno==PACKETBLOBS/2;
+  if(on){
+    for(c=0;c<ch;c++){
+      if(g_cap->ilogmask) memcpy(irown(g_cap->ilogmask,c),iwork[c],sizeof(int)*p->n);
+      if(g_cap->nonzero_in) g_cap->nonzero_in[(size_t)g_blk*g_ch_total+c]=nonzero[c];
+    }
+  }
+  _vp_couple_quantize_normalize(blobno,g,p,vi,mdct,iwork,nonzero,sliding_lowpass,ch);
+  if(on){
+    for(c=0;c<ch;c++){
+      if(g_cap->iwork_out) memcpy(irown(g_cap->iwork_out,c),iwork[c],sizeof(int)*p->n);
+      if(g_cap->nonzero_out) g_cap->nonzero_out[(size_t)g_blk*g_ch_total+c]=nonzero[c];
+    }
+  }
+}
+
+void spy_mdct_backward(mdct_lookup *init, float *in, float *out){
+  int c = g_cnt_imdct++;
+  if(cap_on() && g_cap->dec_coef) memcpy(rown(g_cap->dec_coef,c),in,sizeof(float)*(init->n/2));
+  mdct_backward(init,in,out);
+  if(cap_on() && g_cap->dec_imdct) memcpy(rowN(g_cap->dec_imdct,c),out,sizeof(float)*init->n);
+}
+
+static void keep_packet(ref_handle *h, ogg_packet *op){
+  if(h->npkt==h->pktcap){
+    h->pktcap = h->pktcap? h->pktcap*2 : 64;
+    h->pkt = (unsigned char**)realloc(h->pkt,sizeof(*h->pkt)*h->pktcap);
+    h->pktbytes = (long*)realloc(h->pktbytes,sizeof(*h->pktbytes)*h->pktcap);
+  }
+  h->pkt[h->npkt] = (unsigned char*)malloc(op->bytes? op->bytes:1);
+  memcpy(h->pkt[h->npkt],op->packet,op->bytes);
+  h->pktbytes[h->npkt] = op->bytes;
+  h->npkt++;
+}
+
+/* Encode `nsamples` samples per channel (pcm = [ch][nsamples]) through the
+ * reference API, capturing into *cap.  Returns number of blocks, and the
+ * total packet bytes in *bytes_out.  The handle must be fresh (one use).   */
+int ref_encode_capture(void *hv, const float *pcm, long nsamples, ref_capture *cap, long *bytes_out){
+  ref_handle *h = (ref_handle*)hv;
+  long pos = 0, total = 0;
+  int blocks = 0, i, eos = 0;
+  ogg_packet op;
+  const long chunk = 1024;
+
+  vorbis_analysis_headerout(&h->vd,&h->vc,&h->hdr[0],&h->hdr[1],&h->hdr[2]);
+  for(i=0;i<3;i++){
+    h->hdrcopy[i] = (unsigned char*)malloc(h->hdr[i].bytes);
+    memcpy(h->hdrcopy[i],h->hdr[i].packet,h->hdr[i].bytes);
+    h->hdr[i].packet = h->hdrcopy[i];
+  }
+
+  g_cap = cap; g_ch_total = h->channels;
+  if(cap) cap->nblocks = 0;
+  while(!eos){
+    long todo = nsamples-pos < chunk ? nsamples-pos : chunk;
+    if(todo>0){
+      float **buf = vorbis_analysis_buffer(&h->vd,(int)todo);
+      for(i=0;i<h->channels;i++) memcpy(buf[i],pcm+(size_t)i*nsamples+pos,sizeof(float)*todo);
+      vorbis_analysis_wrote(&h->vd,(int)todo);
+      pos += todo;
+    }else{
+      vorbis_analysis_wrote(&h->vd,0);
+    }
+    while(vorbis_analysis_blockout(&h->vd,&h->vb)==1){
+      vorbis_block_internal *vbi = (vorbis_block_internal*)h->vb.internal;
+      g_blk = blocks;
+      g_cnt_window=g_cnt_mdct=g_cnt_fft=g_cnt_noise=g_cnt_tone=g_cnt_mix=0;
+      if(cap_on()){
+        cap->W[blocks]=(int32_t)h->vb.W; cap->lW[blocks]=(int32_t)h->vb.lW; cap->nW[blocks]=(int32_t)h->vb.nW;
+        cap->blocktype[blocks]=vbi->blocktype;
+        cap->ampmax_in[blocks]=vbi->ampmax;
+      }
+      vorbis_analysis(&h->vb,NULL);
+      if(cap_on()) cap->ampmax_out[blocks]=vbi->ampmax;
+      vorbis_bitrate_addblock(&h->vb);
+      while(vorbis_bitrate_flushpacket(&h->vd,&op)){
+        total += op.bytes;
+        keep_packet(h,&op);
+        if(op.e_o_s) eos = 1;
+      }
+      blocks++;
+    }
+    if(todo<=0 && !eos) { /* blockout returned 0 after EOF without e_o_s: done */ eos = 1; }
+  }
+  if(cap) cap->nblocks = blocks < cap->maxblocks ? blocks : cap->maxblocks;
+  g_cap = NULL; g_blk = -1;
+  if(bytes_out) *bytes_out = total;
+  return blocks;
+}
+
+/* Decode the packets kept by ref_encode_capture through the reference API
+ * (vorbis_synthesis + vorbis_synthesis_blockin + pcmout), capturing the
+ * mdct_backward input/output per block and the finished PCM.
+ * pcm_out = [ch][pcm_cap]; returns samples produced (per channel).          */
+long ref_decode_capture(void *hv, ref_capture *cap, float *pcm_out, long pcm_cap, int32_t *Wseq){
+  ref_handle *h = (ref_handle*)hv;
+  vorbis_info vi; vorbis_comment vc; vorbis_dsp_state vd; vorbis_block vb;
+  long produced = 0;
+  int i, k, blocks = 0;
+  vorbis_info_init(&vi); vorbis_comment_init(&vc);
+  for(i=0;i<3;i++){
+    ogg_packet hp = h->hdr[i];
+    hp.b_o_s = (i==0);
+    if(vorbis_synthesis_headerin(&vi,&vc,&hp)<0){ vorbis_comment_clear(&vc); vorbis_info_clear(&vi); return -1; }
+  }
+  vorbis_synthesis_init(&vd,&vi);
+  vorbis_block_init(&vd,&vb);
+  g_cap = cap; g_ch_total = vi.channels;
+  for(k=0;k<h->npkt;k++){
+    ogg_packet op; float **pcm; int got;
+    memset(&op,0,sizeof(op));
+    op.packet = h->pkt[k]; op.bytes = h->pktbytes[k]; op.packetno = k+3; op.granulepos = -1;
+    g_blk = blocks; g_cnt_imdct = 0;
+    if(vorbis_synthesis(&vb,&op)==0){
+      if(Wseq && cap && blocks<cap->maxblocks) Wseq[blocks]=(int32_t)vb.W;
+      vorbis_synthesis_blockin(&vd,&vb);
+      blocks++;
+    }
+    while((got=vorbis_synthesis_pcmout(&vd,&pcm))>0){
+      int take = got;
+      if(produced+take>pcm_cap) take = (int)(pcm_cap-produced);
+      for(i=0;i<vi.channels;i++)
+        if(take>0) memcpy(pcm_out+(size_t)i*pcm_cap+produced,pcm[i],sizeof(float)*take);
+      produced += take;
+      vorbis_synthesis_read(&vd,got);
+    }
+  }
+  if(cap) cap->nblocks = blocks < cap->maxblocks ? blocks : cap->maxblocks;
+  g_cap = NULL; g_blk = -1;
+  vorbis_block_clear(&vb); vorbis_dsp_clear(&vd); vorbis_comment_clear(&vc); vorbis_info_clear(&vi);
+  return produced;
+}
+
+/* Pure overlap-add check: feed IMDCT outputs through vorbis_synthesis_blockin.
+ * Used to pin the oracle's overlap-add independent of the bitstream.
+ * imdct = [nblk][ch][Nmax]; Wseq[nblk]; pcm_out [ch][pcm_cap]               */
+long ref_blockin_sequence(void *hv, int nblk, const int32_t *Wseq, const float *imdct, int Nmax,
+                          float *pcm_out, long pcm_cap){
+  ref_handle *h = (ref_handle*)hv;
+  vorbis_info vi; vorbis_comment vc; vorbis_dsp_state vd; vorbis_block vb;
+  long produced = 0; int i,k;
+  vorbis_info_init(&vi); vorbis_comment_init(&vc);
+  if(!h->hdrcopy[0]){
+    vorbis_analysis_headerout(&h->vd,&h->vc,&h->hdr[0],&h->hdr[1],&h->hdr[2]);
+    for(i=0;i<3;i++){
+      h->hdrcopy[i] = (unsigned char*)malloc(h->hdr[i].bytes);
+      memcpy(h->hdrcopy[i],h->hdr[i].packet,h->hdr[i].bytes);
+      h->hdr[i].packet = h->hdrcopy[i];
+    }
+  }
+  for(i=0;i<3;i++){
+    ogg_packet hp = h->hdr[i]; hp.b_o_s=(i==0);
+    if(vorbis_synthesis_headerin(&vi,&vc,&hp)<0) return -1;
+  }
+  vorbis_synthesis_init(&vd,&vi);
+  vorbis_block_init(&vd,&vb);
+  {
+    codec_setup_info *ci=(codec_setup_info*)vi.codec_setup;
+    float **rows=(float**)malloc(sizeof(float*)*vi.channels);
+    for(k=0;k<nblk;k++){
+      float **pcm; int got;
+      vb.W = Wseq[k];
+      vb.pcmend = (int)ci->blocksizes[vb.W];
+      vb.sequence = k;
+      vb.granulepos = -1;
+      vb.eofflag = 0;
+      for(i=0;i<vi.channels;i++) rows[i]=(float*)imdct+((size_t)k*vi.channels+i)*Nmax;
+      vb.pcm = rows;
+      vorbis_synthesis_blockin(&vd,&vb);
+      while((got=vorbis_synthesis_pcmout(&vd,&pcm))>0){
+        int take=got;
+        if(produced+take>pcm_cap) take=(int)(pcm_cap-produced);
+        for(i=0;i<vi.channels;i++)
+          if(take>0) memcpy(pcm_out+(size_t)i*pcm_cap+produced,pcm[i],sizeof(float)*take);
+        produced+=take;
+        vorbis_synthesis_read(&vd,got);
+      }
+    }
+    vb.pcm=NULL;
+    free(rows);
+  }
+  vorbis_block_clear(&vb); vorbis_dsp_clear(&vd); vorbis_comment_clear(&vc); vorbis_info_clear(&vi);
+  return produced;
+}
+
+/* ---- CPU baseline helper: the reference's Phase-A calls, in order, on a
+ * batch of blocks (what mapping0_forward does at lib/mapping0.c:254-470 up to
+ * floor1_fit, using only the reference's functions).  Used by bench.py's
+ * cpu_baseline / --impl reference leg.                                      */
+void ref_phaseA_batch(void *hv, int W, int nblocks, const float *pcm, const vb200_block_desc *desc,
+                      float *mdct, float *logmdct_out, float *logmask_out, float *ampmax_out){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  int ch = h->vi.channels, N = (int)ci->blocksizes[W], n = N/2, blk, i, j;
+  float *work = (float*)malloc(sizeof(float)*N*ch);
+  float *noise = (float*)malloc(sizeof(float)*n);
+  float *tone = (float*)malloc(sizeof(float)*n);
+  float *lmax = (float*)malloc(sizeof(float)*ch);
+  for(blk=0;blk<nblocks;blk++){
+    vorbis_look_psy *psy_look = b->psy+desc[blk].blocktype+(W?2:0);
+    float gmax = desc[blk].ampmax;
+    for(i=0;i<ch;i++){
+      float scale=4.f/N, scale_dB, *p = work+(size_t)i*N, *gm = mdct+((size_t)blk*ch+i)*n;
+      memcpy(p,pcm+((size_t)blk*ch+i)*N,sizeof(float)*N);
+      scale_dB=todB(&scale)+.345;
+      _vorbis_apply_window(p,b->window,ci->blocksizes,desc[blk].lW,W,desc[blk].nW);
+      mdct_forward((mdct_lookup*)b->transform[W][0],p,gm);
+      drft_forward(&b->fft_look[W],p);
+      p[0]=scale_dB+todB(p)+.345;
+      lmax[i]=p[0];
+      for(j=1;j<N-1;j+=2){
+        float t=p[j]*p[j]+p[j+1]*p[j+1];
+        t=p[(j+1)>>1]=scale_dB+.5f*todB(&t)+.345;
+        if(t>lmax[i])lmax[i]=t;
+      }
+      if(lmax[i]>0.f)lmax[i]=0.f;
+      if(lmax[i]>gmax)gmax=lmax[i];
+    }
+    for(i=0;i<ch;i++){
+      float *p = work+(size_t)i*N, *gm = mdct+((size_t)blk*ch+i)*n;
+      float *logmdct = p+n, *logmask = p;
+      for(j=0;j<n;j++) logmdct[j]=todB(gm+j)+.345;
+      _vp_noisemask(psy_look,logmdct,noise);
+      _vp_tonemask(psy_look,p,tone,gmax,lmax[i]);
+      _vp_offset_and_mix(psy_look,noise,tone,1,logmask,gm,logmdct);
+      memcpy(logmdct_out+((size_t)blk*ch+i)*n,logmdct,sizeof(float)*n);
+      memcpy(logmask_out+((size_t)blk*ch+i)*n,logmask,sizeof(float)*n);
+    }
+    ampmax_out[blk]=gmax;
+  }
+  free(work); free(noise); free(tone); free(lmax);
+}

@@ -1,0 +1,221 @@
+"""ctypes mirrors of the plain-C structs in include/vorbis_b200.h.
+
+These are shared by the loader of the product library (libvorbis_b200.so), by the
+test-only loaders of the CPU oracle (oracle/libvb_oracle.so) and of the compiled
+reference (oracle/_ref/libvorbis_ref.so), and by the golden-fixture reader.
+Field order and types must match the header exactly.
+"""
+import ctypes as C
+import numpy as np
+
+P_BANDS = 17
+P_LEVELS = 8
+P_NOISECURVES = 3
+EHMER_MAX = 56
+COMPAND_LEVELS = 40
+PACKETBLOBS = 15
+MAX_COUPLING = 256
+
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+
+
+class PsySetup(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("blockflag", C.c_int32),
+        ("ath_adjatt", C.c_float),
+        ("ath_maxatt", C.c_float),
+        ("tone_masteratt", C.c_float * P_NOISECURVES),
+        ("tone_abs_limit", C.c_float),
+        ("noisemaxsupp", C.c_float),
+        ("noisewindowfixed", C.c_int32),
+        ("noisecompand", C.c_float * COMPAND_LEVELS),
+        ("max_curve_dB", C.c_float),
+        ("normal_p", C.c_int32),
+        ("normal_start", C.c_int32),
+        ("normal_partition", C.c_int32),
+        ("normal_thresh", C.c_double),
+        ("firstoc", C.c_int32),
+        ("shiftoc", C.c_int32),
+        ("eighth_octave_lines", C.c_int32),
+        ("total_octave_lines", C.c_int32),
+        ("m_val", C.c_float),
+        ("ath", c_float_p),
+        ("octave", c_int32_p),
+        ("bark", c_int32_p),
+        ("tonecurves", c_float_p),
+        ("noiseoffset", c_float_p),
+    ]
+
+
+class Setup(C.Structure):
+    _fields_ = [
+        ("channels", C.c_int32),
+        ("rate", C.c_int32),
+        ("blocksizes", C.c_int32 * 2),
+        ("n_psy", C.c_int32),
+        ("psy", PsySetup * 4),
+        ("ampmax_att_per_sec", C.c_float),
+        ("coupling_pointlimit", (C.c_int32 * PACKETBLOBS) * 2),
+        ("coupling_prepointamp", C.c_int32 * PACKETBLOBS),
+        ("coupling_postpointamp", C.c_int32 * PACKETBLOBS),
+        ("sliding_lowpass", (C.c_int32 * PACKETBLOBS) * 2),
+        ("coupling_steps", C.c_int32 * 2),
+        ("coupling_mag", (C.c_int32 * MAX_COUPLING) * 2),
+        ("coupling_ang", (C.c_int32 * MAX_COUPLING) * 2),
+        ("window", c_float_p * 2),
+    ]
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [
+        ("lW", C.c_int32),
+        ("nW", C.c_int32),
+        ("blocktype", C.c_int32),
+        ("ampmax", C.c_float),
+    ]
+
+
+BLOCKDESC_DTYPE = np.dtype(
+    [("lW", np.int32), ("nW", np.int32), ("blocktype", np.int32), ("ampmax", np.float32)]
+)
+assert BLOCKDESC_DTYPE.itemsize == C.sizeof(BlockDesc)
+
+
+class PhaseAIO(C.Structure):
+    _fields_ = [
+        ("pcm", C.c_void_p),
+        ("desc", C.c_void_p),
+        ("mdct", C.c_void_p),
+        ("logmdct", C.c_void_p),
+        ("logmask", C.c_void_p),
+        ("ampmax_out", C.c_void_p),
+        ("tap_noise", C.c_void_p),
+        ("tap_tone", C.c_void_p),
+        ("tap_logfft", C.c_void_p),
+        ("tap_mdct_raw", C.c_void_p),
+    ]
+
+
+_PSY_SCALARS = [
+    "n", "blockflag", "ath_adjatt", "ath_maxatt", "tone_abs_limit", "noisemaxsupp",
+    "noisewindowfixed", "max_curve_dB", "normal_p", "normal_start", "normal_partition",
+    "normal_thresh", "firstoc", "shiftoc", "eighth_octave_lines", "total_octave_lines", "m_val",
+]
+
+
+def _np_ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class SetupHolder:
+    """Owns numpy copies of every table a `Setup` points to (so the ctypes struct
+    stays valid), and converts to / from a flat dict of arrays (npz fixtures)."""
+
+    def __init__(self, arrays):
+        self.arrays = {k: np.ascontiguousarray(v) for k, v in arrays.items()}
+        self.c = Setup()
+        a = self.arrays
+        s = self.c
+        s.channels = int(a["channels"])
+        s.rate = int(a["rate"])
+        s.blocksizes[0], s.blocksizes[1] = [int(x) for x in a["blocksizes"]]
+        s.n_psy = int(a["n_psy"])
+        s.ampmax_att_per_sec = float(a["ampmax_att_per_sec"])
+        for w in range(2):
+            for k in range(PACKETBLOBS):
+                s.coupling_pointlimit[w][k] = int(a["coupling_pointlimit"][w][k])
+                s.sliding_lowpass[w][k] = int(a["sliding_lowpass"][w][k])
+            s.coupling_steps[w] = int(a["coupling_steps"][w])
+            for k in range(int(a["coupling_steps"][w])):
+                s.coupling_mag[w][k] = int(a["coupling_mag"][w][k])
+                s.coupling_ang[w][k] = int(a["coupling_ang"][w][k])
+        for k in range(PACKETBLOBS):
+            s.coupling_prepointamp[k] = int(a["coupling_prepointamp"][k])
+            s.coupling_postpointamp[k] = int(a["coupling_postpointamp"][k])
+        for w in range(2):
+            key = "window%d" % w
+            if key in a and a[key].size:
+                a[key] = np.ascontiguousarray(a[key], dtype=np.float32)
+                s.window[w] = _np_ptr(a[key], C.c_float)
+        for i in range(s.n_psy):
+            p = s.psy[i]
+            pre = "psy%d_" % i
+            for name in _PSY_SCALARS:
+                v = a[pre + name]
+                setattr(p, name, float(v) if name in ("ath_adjatt", "ath_maxatt", "tone_abs_limit",
+                                                      "noisemaxsupp", "max_curve_dB", "normal_thresh",
+                                                      "m_val") else int(v))
+            for j in range(P_NOISECURVES):
+                p.tone_masteratt[j] = float(a[pre + "tone_masteratt"][j])
+            for j in range(COMPAND_LEVELS):
+                p.noisecompand[j] = float(a[pre + "noisecompand"][j])
+            for name, ct, dt in (("ath", C.c_float, np.float32), ("octave", C.c_int32, np.int32),
+                                 ("bark", C.c_int32, np.int32), ("tonecurves", C.c_float, np.float32),
+                                 ("noiseoffset", C.c_float, np.float32)):
+                a[pre + name] = np.ascontiguousarray(a[pre + name], dtype=dt)
+                setattr(p, name, _np_ptr(a[pre + name], ct))
+
+    # ---- conveniences -------------------------------------------------------
+    @property
+    def channels(self):
+        return int(self.c.channels)
+
+    @property
+    def rate(self):
+        return int(self.c.rate)
+
+    def blocksize(self, W):
+        return int(self.c.blocksizes[W])
+
+    def psy_n(self, look):
+        return int(self.c.psy[look].n)
+
+    def save(self, path):
+        np.savez_compressed(path, **self.arrays)
+
+    @classmethod
+    def load(cls, path):
+        with np.load(path) as z:
+            return cls({k: z[k] for k in z.files})
+
+    @classmethod
+    def from_struct(cls, s):
+        """Deep-copy a C `Setup` (e.g. filled by ref_get_setup) into numpy arrays."""
+        a = {
+            "channels": np.int32(s.channels), "rate": np.int32(s.rate),
+            "blocksizes": np.array([s.blocksizes[0], s.blocksizes[1]], np.int32),
+            "n_psy": np.int32(s.n_psy),
+            "ampmax_att_per_sec": np.float32(s.ampmax_att_per_sec),
+            "coupling_pointlimit": np.array([[s.coupling_pointlimit[w][k] for k in range(PACKETBLOBS)]
+                                             for w in range(2)], np.int32),
+            "coupling_prepointamp": np.array(list(s.coupling_prepointamp), np.int32),
+            "coupling_postpointamp": np.array(list(s.coupling_postpointamp), np.int32),
+            "sliding_lowpass": np.array([[s.sliding_lowpass[w][k] for k in range(PACKETBLOBS)]
+                                         for w in range(2)], np.int32),
+            "coupling_steps": np.array(list(s.coupling_steps), np.int32),
+        }
+        ms = max(1, max(s.coupling_steps))
+        a["coupling_mag"] = np.array([[s.coupling_mag[w][k] for k in range(ms)] for w in range(2)], np.int32)
+        a["coupling_ang"] = np.array([[s.coupling_ang[w][k] for k in range(ms)] for w in range(2)], np.int32)
+        for w in range(2):
+            if s.window[w]:
+                a["window%d" % w] = np.ctypeslib.as_array(s.window[w], shape=(s.blocksizes[w] // 2,)).copy()
+        for i in range(s.n_psy):
+            p = s.psy[i]
+            pre = "psy%d_" % i
+            n = p.n
+            for name in _PSY_SCALARS:
+                v = getattr(p, name)
+                a[pre + name] = np.float64(v) if isinstance(v, float) else np.int32(v)
+            a[pre + "tone_masteratt"] = np.array(list(p.tone_masteratt), np.float32)
+            a[pre + "noisecompand"] = np.array(list(p.noisecompand), np.float32)
+            a[pre + "ath"] = np.ctypeslib.as_array(p.ath, shape=(n,)).copy()
+            a[pre + "octave"] = np.ctypeslib.as_array(p.octave, shape=(n,)).copy()
+            a[pre + "bark"] = np.ctypeslib.as_array(p.bark, shape=(n,)).copy()
+            a[pre + "tonecurves"] = np.ctypeslib.as_array(
+                p.tonecurves, shape=(P_BANDS * P_LEVELS * (EHMER_MAX + 2),)).copy()
+            a[pre + "noiseoffset"] = np.ctypeslib.as_array(p.noiseoffset, shape=(P_NOISECURVES * n,)).copy()
+        return cls(a)
