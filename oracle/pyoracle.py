@@ -1,0 +1,182 @@
+"""ctypes loader for oracle/libvb_oracle.so — our own plain-C restatement of the path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline leg; never by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from vorbis_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvb_oracle.so")
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    src = [os.path.join(HERE, f) for f in ("vb_oracle.c", "vb_oracle.h", "vb_oracle_b.inc")]
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return
+    subprocess.check_call(["make", "-s", "-C", HERE, "libvb_oracle.so", "CC=gcc"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.vbo_create.restype = C.c_void_p
+        L.vbo_create.argtypes = [C.POINTER(abi.Setup)]
+        L.vbo_destroy.argtypes = [C.c_void_p]
+        L.vbo_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.vbo_mdct_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, f32p]
+        L.vbo_mdct_backward.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, f32p]
+        L.vbo_apply_window.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, f32p]
+        L.vbo_drft_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p]
+        L.vbo_noisemask.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, f32p]
+        L.vbo_tonemask.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, f32p, f32p, f32p]
+        L.vbo_offset_and_mix.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p]
+        L.vbo_phaseA.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.PhaseAIO)]
+        L.vbo_phaseA_streams.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(abi.PhaseAIO), C.c_void_p]
+        L.vbo_ampmax_decay.restype = C.c_float
+        L.vbo_ampmax_decay.argtypes = [C.c_void_p, C.c_float, C.c_int]
+        L.vbo_couple_quantize_normalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                    f32p, i32p, i32p]
+        L.vbo_synthesis.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i64p, f32p, i64p, f32p, C.c_int64]
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    def __init__(self, setup):
+        """setup: abi.SetupHolder"""
+        self.L = lib()
+        self.setup = setup
+        self.h = self.L.vbo_create(C.byref(setup.c))
+        self.channels = setup.channels
+        self.bs = [setup.blocksize(0), setup.blocksize(1)]
+
+    def close(self):
+        if self.h:
+            self.L.vbo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def table(self, W, which):
+        N = self.bs[W]
+        out = np.zeros(N // 4, np.int32) if which == 1 else np.zeros(2 * N, np.float32)
+        k = self.L.vbo_table(self.h, W, which, out.ctypes.data, out.size)
+        assert k > 0
+        return out[:k].copy()
+
+    def mdct_forward(self, W, x):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.bs[W])
+        out = np.empty((x.shape[0], self.bs[W] // 2), np.float32)
+        self.L.vbo_mdct_forward(self.h, W, x.shape[0], x, out)
+        return out
+
+    def mdct_backward(self, W, x):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.bs[W] // 2)
+        out = np.empty((x.shape[0], self.bs[W]), np.float32)
+        self.L.vbo_mdct_backward(self.h, W, x.shape[0], x, out)
+        return out
+
+    def apply_window(self, W, x, lW=None, nW=None):
+        x = np.array(x, np.float32).reshape(-1, self.bs[W])
+        lWa = None if lW is None else np.ascontiguousarray(lW, np.int32)
+        nWa = None if nW is None else np.ascontiguousarray(nW, np.int32)
+        self.L.vbo_apply_window(self.h, W, x.shape[0],
+                                None if lWa is None else lWa.ctypes.data,
+                                None if nWa is None else nWa.ctypes.data, x)
+        return x
+
+    def drft_forward(self, W, x):
+        x = np.array(x, np.float32).reshape(-1, self.bs[W])
+        self.L.vbo_drft_forward(self.h, W, x.shape[0], x)
+        return x
+
+    def noisemask(self, look, logmdct):
+        x = np.ascontiguousarray(logmdct, np.float32)
+        x = x.reshape(-1, x.shape[-1])
+        out = np.empty_like(x)
+        self.L.vbo_noisemask(self.h, look, x.shape[0], x, out)
+        return out
+
+    def tonemask(self, look, logfft, gmax, lmax):
+        x = np.ascontiguousarray(logfft, np.float32)
+        x = x.reshape(-1, x.shape[-1])
+        out = np.empty_like(x)
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(gmax, np.float32), (x.shape[0],)))
+        l = np.ascontiguousarray(np.broadcast_to(np.asarray(lmax, np.float32), (x.shape[0],)))
+        self.L.vbo_tonemask(self.h, look, x.shape[0], x, g, l, out)
+        return out
+
+    def offset_and_mix(self, look, sel, noise, tone, mdct, logmdct):
+        noise = np.ascontiguousarray(noise, np.float32)
+        noise = noise.reshape(-1, noise.shape[-1])
+        tone = np.ascontiguousarray(tone, np.float32).reshape(noise.shape)
+        mdct = np.array(mdct, np.float32).reshape(noise.shape)
+        logmdct = np.ascontiguousarray(logmdct, np.float32).reshape(noise.shape)
+        logmask = np.empty_like(noise)
+        self.L.vbo_offset_and_mix(self.h, look, noise.shape[0], sel, noise, tone, mdct, logmdct, logmask)
+        return logmask, mdct
+
+    def phaseA(self, W, pcm, desc, taps=False, streams=None, ampmax0=None):
+        """pcm [nb][ch][N]; desc structured array (abi.BLOCKDESC_DTYPE).
+        streams=(nstreams, blocks_per_stream) selects the ampmax-chain mode."""
+        ch, N = self.channels, self.bs[W]
+        pcm = np.ascontiguousarray(pcm, np.float32).reshape(-1, ch, N)
+        nb = pcm.shape[0]
+        desc = np.ascontiguousarray(desc, abi.BLOCKDESC_DTYPE)
+        out = {k: np.empty((nb, ch, N // 2), np.float32) for k in ("mdct", "logmdct", "logmask")}
+        out["ampmax_out"] = np.empty(nb, np.float32)
+        io = abi.PhaseAIO()
+        io.pcm, io.desc = pcm.ctypes.data, desc.ctypes.data
+        io.mdct, io.logmdct, io.logmask = (out[k].ctypes.data for k in ("mdct", "logmdct", "logmask"))
+        io.ampmax_out = out["ampmax_out"].ctypes.data
+        if taps:
+            for k in ("noise", "tone", "logfft", "mdct_raw"):
+                out[k] = np.empty((nb, ch, N // 2), np.float32)
+                setattr(io, "tap_" + k, out[k].ctypes.data)
+        if streams is None:
+            self.L.vbo_phaseA(self.h, W, nb, C.byref(io))
+        else:
+            a0 = None if ampmax0 is None else np.ascontiguousarray(ampmax0, np.float32)
+            self.L.vbo_phaseA_streams(self.h, W, streams[0], streams[1], C.byref(io),
+                                      None if a0 is None else a0.ctypes.data)
+        return out
+
+    def ampmax_decay(self, amp, W):
+        return float(self.L.vbo_ampmax_decay(self.h, float(amp), W))
+
+    def couple_quantize_normalize(self, W, blocktype, blobno, mdct, iwork, nonzero):
+        mdct = np.ascontiguousarray(mdct, np.float32)
+        iwork = np.array(iwork, np.int32)
+        nonzero = np.array(nonzero, np.int32)
+        self.L.vbo_couple_quantize_normalize(self.h, W, blocktype, blobno, mdct.shape[0], mdct, iwork, nonzero)
+        return iwork, nonzero
+
+    def synthesis(self, Wseq, coef_off, coef, pcm_off, pcm_stride):
+        Wseq = np.ascontiguousarray(Wseq, np.int32)
+        ns, nblk = Wseq.shape
+        coef_off = np.ascontiguousarray(coef_off, np.int64)
+        pcm_off = np.ascontiguousarray(pcm_off, np.int64)
+        coef = np.ascontiguousarray(coef, np.float32)
+        pcm = np.zeros((ns, self.channels, pcm_stride), np.float32)
+        self.L.vbo_synthesis(self.h, ns, nblk, Wseq, coef_off, coef, pcm_off, pcm, pcm_stride)
+        return pcm
