@@ -120,6 +120,11 @@ const char *vb200_last_error(void);
 int  vb200_ctx_table(vb200_ctx *ctx, int W, int which, void *dst, int cap);
 /* kernels launched through this context since creation (bench evidence)     */
 uint64_t vb200_launch_count(vb200_ctx *ctx);
+/* measurement aid: when on, the Phase-A entry points bracket each of their three
+ * kernels (transform, ampmax, psy) with CUDA events on the launching stream;
+ * vb200_phaseA_kernel_ms returns the durations of the last call (ms3[3]).       */
+int  vb200_set_profiling(vb200_ctx *ctx, int on);
+int  vb200_phaseA_kernel_ms(vb200_ctx *ctx, float *ms3);
 
 /* ---- transforms ------------------------------------- */
 /* mdct_forward, lib/mdct.c:492: in [nvec][N] -> out [nvec][N/2]            */

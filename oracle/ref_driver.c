@@ -1,7 +1,7 @@
 /* ref_driver.c — thin driver around the UNMODIFIED reference sources.
  *
  * TEST INFRASTRUCTURE ONLY.  This file is compiled together with the
- * reference's own lib/*.c (read in place from /root/reference, never copied)
+ * reference C sources under lib/ (read in place from /root/reference, never copied)
  * into oracle/_ref/libvorbis_ref.so by oracle/Makefile.  It
  *   (1) exposes the reference's hot-path functions (mdct_forward, drft_forward,
  *       _vorbis_apply_window, _vp_noisemask, _vp_tonemask, _vp_offset_and_mix,

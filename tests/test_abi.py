@@ -1,0 +1,45 @@
+"""The C-ABI library loads and exports every symbol include/vorbis_b200.h declares
+(no compute calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+from vorbis_b200 import abi, lib
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "vorbis_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vb200_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib.load()
+    names = header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), "libvorbis_b200.so does not export %s" % n
+    assert sorted(lib.EXPORTS) == names, "vorbis_b200/lib.py EXPORTS out of sync with the header"
+
+
+def test_struct_sizes_match_header():
+    # compile-time layout check through the oracle library, which is built from the same header
+    from oracle import pyoracle
+    pyoracle.build()
+    assert ctypes.sizeof(abi.BlockDesc) == 16
+    assert ctypes.sizeof(abi.PhaseAIO) == 10 * ctypes.sizeof(ctypes.c_void_p)
+    # vb200_psy_setup: 2 ints, 7 floats(2+3+1+1), int, 40 floats, float, 3 ints, pad, double, 4 ints, float, pad, 5 ptrs
+    assert ctypes.sizeof(abi.PsySetup) % 8 == 0
+
+
+def test_bad_arguments_return_error_codes_not_aborts():
+    L = lib.load()
+    s = abi.Setup()
+    s.blocksizes[0], s.blocksizes[1] = 100, 2048       # not a power of two
+    s.channels = 2
+    h = ctypes.c_void_p()
+    rc = L.vb200_ctx_create(ctypes.byref(s), 0, ctypes.byref(h))
+    assert rc == -131, rc                                # OV_EINVAL
+    assert b"power" in L.vb200_last_error()
+    assert L.vb200_mdct_forward(None, 0, 1, None, None) == -131

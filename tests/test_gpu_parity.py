@@ -1,0 +1,154 @@
+"""CUDA path (through the C ABI of libvorbis_b200.so) against
+  (a) the golden vectors recorded from the reference, and
+  (b) the CPU oracle on seeded inputs.
+Bit-exact for every stage: the kernels execute the reference's arithmetic DAG with
+FMA contraction off (tolerance stated by north_star is 1e-4 relative; we hold 0)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import CONFIG_NAMES, assert_bits_equal, load_npz, load_setup, make_desc
+from vorbis_b200 import abi, lib as vlib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=CONFIG_NAMES)
+def cfg(request, oracle_lib, cuda_ok):
+    name = request.param
+    setup = load_setup(name)
+    return name, setup, vlib.Context(setup), oracle_lib.Oracle(setup), load_npz("encode", name), load_npz("decode", name)
+
+
+def test_tables_match_oracle(cfg):
+    name, setup, ctx, o, enc, _ = cfg
+    for W in (0, 1):
+        for which in (0, 1, 2, 3):
+            assert_bits_equal(ctx.table(W, which), o.table(W, which), "table W%d #%d" % (W, which))
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_transforms_golden(cfg, tag):
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    N = setup.blocksize(W)
+    pcm = enc[tag + "_pcm"].reshape(-1, N)
+    lW = np.repeat(enc[tag + "_lW"], setup.channels)
+    nW = np.repeat(enc[tag + "_nW"], setup.channels)
+    win = ctx.apply_window(W, pcm, lW, nW)
+    assert_bits_equal(win, enc[tag + "_windowed"].reshape(-1, N), "window")
+    assert_bits_equal(ctx.mdct_forward(W, win), enc[tag + "_mdct_raw"].reshape(-1, N // 2), "mdct_forward")
+    assert_bits_equal(ctx.drft_forward(W, win), enc[tag + "_fft"].reshape(-1, N), "drft_forward")
+
+
+@pytest.mark.parametrize("W", [0, 1])
+def test_transforms_vs_oracle_random(cfg, W):
+    name, setup, ctx, o, enc, _ = cfg
+    N = setup.blocksize(W)
+    rng = np.random.default_rng(12345 + W)
+    x = rng.uniform(-1, 1, (300, N)).astype(np.float32)
+    x[0] = 0.0                      # silence
+    x[1, :] = 1.0                   # DC at full scale
+    x[2, ::2] = 1.0; x[2, 1::2] = -1.0
+    x[3] *= 1e-30                   # denormal-range products
+    assert_bits_equal(ctx.mdct_forward(W, x), o.mdct_forward(W, x), "mdct_forward")
+    y = rng.uniform(-1, 1, (300, N // 2)).astype(np.float32)
+    y[0] = 0.0
+    assert_bits_equal(ctx.mdct_backward(W, y), o.mdct_backward(W, y), "mdct_backward")
+    assert_bits_equal(ctx.drft_forward(W, x), o.drft_forward(W, x), "drft_forward")
+    lW = rng.integers(0, 2, 300).astype(np.int32)
+    nW = rng.integers(0, 2, 300).astype(np.int32)
+    assert_bits_equal(ctx.apply_window(W, x, lW, nW), o.apply_window(W, x, lW, nW), "window")
+    # empty batch is a no-op
+    assert ctx.mdct_forward(W, np.zeros((0, N), np.float32)).shape == (0, N // 2)
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_psy_stages_isolated_golden(cfg, tag):
+    """each stage fed the REFERENCE's upstream vectors (SURVEY §8d parity metric)"""
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    n = setup.blocksize(W) // 2
+    ch = setup.channels
+    for bt in (0, 1):
+        sel = np.where(enc[tag + "_blocktype"] == bt)[0]
+        if not len(sel):
+            continue
+        look = bt + 2 * W
+        assert_bits_equal(ctx.noisemask(look, enc[tag + "_logmdct"][sel].reshape(-1, n)),
+                          enc[tag + "_noise"][sel].reshape(-1, n), "noise look %d" % look)
+        g = np.repeat(enc[tag + "_global_ampmax"][sel], ch)
+        l = enc[tag + "_local_ampmax"][sel].reshape(-1)
+        assert_bits_equal(ctx.tonemask(look, enc[tag + "_logfft"][sel].reshape(-1, n), g, l),
+                          enc[tag + "_tone"][sel].reshape(-1, n), "tone look %d" % look)
+        lm, m1 = ctx.offset_and_mix(look, 1, enc[tag + "_noise"][sel].reshape(-1, n),
+                                    enc[tag + "_tone"][sel].reshape(-1, n),
+                                    enc[tag + "_mdct_raw"][sel].reshape(-1, n),
+                                    enc[tag + "_logmdct"][sel].reshape(-1, n))
+        assert_bits_equal(lm, enc[tag + "_logmask"][sel].reshape(-1, n), "logmask")
+        assert_bits_equal(m1, enc[tag + "_mdct_m1"][sel].reshape(-1, n), "mdct after M1")
+
+
+@pytest.mark.parametrize("look", [0, 1, 2, 3])
+def test_psy_stages_vs_oracle_random(cfg, look):
+    name, setup, ctx, o, enc, _ = cfg
+    n = setup.psy_n(look)
+    rng = np.random.default_rng(99 + look)
+    nv = 200
+    logmdct = (rng.uniform(-140, 0, (nv, n)) + 20 * np.sin(np.arange(n) / 37.0)).astype(np.float32)
+    logmdct[0] = -764.6          # todB(0): digital silence
+    logmdct[1] = -3.0            # flat loud
+    assert_bits_equal(ctx.noisemask(look, logmdct), o.noisemask(look, logmdct), "noise")
+    logfft = (rng.uniform(-120, -10, (nv, n))).astype(np.float32)
+    logfft[2, n // 3] = 0.0      # one strong tone
+    logfft[3] = -200.0
+    lmax = np.minimum(logfft.max(axis=1), 0).astype(np.float32)
+    gmax = np.maximum(lmax, rng.uniform(-60, 0, nv)).astype(np.float32)
+    assert_bits_equal(ctx.tonemask(look, logfft, gmax, lmax), o.tonemask(look, logfft, gmax, lmax), "tone")
+    noise = rng.uniform(-120, -10, (nv, n)).astype(np.float32)
+    tone = rng.uniform(-120, -10, (nv, n)).astype(np.float32)
+    mdct = rng.uniform(-1, 1, (nv, n)).astype(np.float32)
+    for sel in (0, 1, 2):
+        a = ctx.offset_and_mix(look, sel, noise, tone, mdct, logmdct)
+        b = o.offset_and_mix(look, sel, noise, tone, mdct, logmdct)
+        assert_bits_equal(a[0], b[0], "logmask sel %d" % sel)
+        assert_bits_equal(a[1], b[1], "mdct sel %d" % sel)
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_phaseA_golden(cfg, tag):
+    """the fused chain against the real mapping0_forward; bit-exact, so no statistical caveat"""
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    out = ctx.phaseA(W, enc[tag + "_pcm"], make_desc(enc, tag), taps=True)
+    for k, g in (("mdct_raw", "mdct_raw"), ("logfft", "logfft"), ("noise", "noise"), ("tone", "tone"),
+                 ("logmdct", "logmdct"), ("logmask", "logmask"), ("mdct", "mdct_m1")):
+        assert_bits_equal(out[k], enc[tag + "_" + g], "phaseA " + k)
+    assert_bits_equal(out["ampmax_out"], enc[tag + "_ampmax_out"], "ampmax_out")
+    # and without taps (the in-place mdct path)
+    out2 = ctx.phaseA(W, enc[tag + "_pcm"], make_desc(enc, tag), taps=False)
+    for k in ("mdct", "logmdct", "logmask", "ampmax_out"):
+        assert_bits_equal(out2[k], out[k], "phaseA(no taps) " + k)
+
+
+@pytest.mark.parametrize("W", [0, 1])
+def test_phaseA_vs_oracle_random(cfg, W):
+    name, setup, ctx, o, enc, _ = cfg
+    N, ch = setup.blocksize(W), setup.channels
+    rng = np.random.default_rng(4242 + W)
+    nb = 64
+    t = np.arange(N)
+    pcm = (0.25 * rng.uniform(-1, 1, (nb, ch, N)) +
+           0.5 * np.sin(2 * np.pi * rng.uniform(50, 8000, (nb, ch, 1)) * t / setup.rate)).astype(np.float32)
+    pcm[0] = 0.0
+    pcm[1] *= 1e-4
+    desc = np.zeros(nb, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = rng.integers(0, 2, nb) if W else 0
+    desc["nW"] = rng.integers(0, 2, nb) if W else 0
+    desc["blocktype"] = rng.integers(0, 2, nb)
+    desc["ampmax"] = rng.choice([-9999.0, -30.0, -3.0, 0.0], nb).astype(np.float32)
+    a = ctx.phaseA(W, pcm, desc, taps=True)
+    b = o.phaseA(W, pcm, desc, taps=True)
+    for k in ("mdct_raw", "logfft", "noise", "tone", "logmdct", "logmask", "mdct", "ampmax_out"):
+        assert_bits_equal(a[k], b[k], "phaseA " + k)

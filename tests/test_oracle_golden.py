@@ -1,0 +1,104 @@
+"""CPU oracle (oracle/vb_oracle.c) against the golden vectors recorded from the reference.
+Bit-exact.  Runs anywhere gcc exists."""
+import numpy as np
+import pytest
+
+from conftest import CONFIG_NAMES, assert_bits_equal, load_npz, load_setup, make_desc
+from vorbis_b200 import lib as vlib
+
+
+@pytest.fixture(scope="module", params=CONFIG_NAMES)
+def cfg(request, oracle_lib):
+    name = request.param
+    setup = load_setup(name)
+    return name, setup, oracle_lib.Oracle(setup), load_npz("encode", name), load_npz("decode", name)
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_transforms(cfg, tag):
+    name, setup, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    N = setup.blocksize(W)
+    pcm = enc[tag + "_pcm"].reshape(-1, N)
+    lW = np.repeat(enc[tag + "_lW"], setup.channels)
+    nW = np.repeat(enc[tag + "_nW"], setup.channels)
+    win = o.apply_window(W, pcm, lW, nW)
+    assert_bits_equal(win, enc[tag + "_windowed"].reshape(-1, N), "window")
+    assert_bits_equal(o.mdct_forward(W, win), enc[tag + "_mdct_raw"].reshape(-1, N // 2), "mdct_forward")
+    assert_bits_equal(o.drft_forward(W, win), enc[tag + "_fft"].reshape(-1, N), "drft_forward")
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_psy_stages_isolated(cfg, tag):
+    name, setup, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    n = setup.blocksize(W) // 2
+    ch = setup.channels
+    for bt in (0, 1):
+        sel = np.where(enc[tag + "_blocktype"] == bt)[0]
+        if not len(sel):
+            continue
+        look = bt + 2 * W
+        assert_bits_equal(o.noisemask(look, enc[tag + "_logmdct"][sel].reshape(-1, n)),
+                          enc[tag + "_noise"][sel].reshape(-1, n), "noise look %d" % look)
+        g = np.repeat(enc[tag + "_global_ampmax"][sel], ch)
+        l = enc[tag + "_local_ampmax"][sel].reshape(-1)
+        assert_bits_equal(o.tonemask(look, enc[tag + "_logfft"][sel].reshape(-1, n), g, l),
+                          enc[tag + "_tone"][sel].reshape(-1, n), "tone look %d" % look)
+        lm, m1 = o.offset_and_mix(look, 1, enc[tag + "_noise"][sel].reshape(-1, n),
+                                  enc[tag + "_tone"][sel].reshape(-1, n),
+                                  enc[tag + "_mdct_raw"][sel].reshape(-1, n),
+                                  enc[tag + "_logmdct"][sel].reshape(-1, n))
+        assert_bits_equal(lm, enc[tag + "_logmask"][sel].reshape(-1, n), "logmask")
+        assert_bits_equal(m1, enc[tag + "_mdct_m1"][sel].reshape(-1, n), "mdct after M1")
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_phaseA_end_to_end(cfg, tag):
+    name, setup, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    out = o.phaseA(W, enc[tag + "_pcm"], make_desc(enc, tag), taps=True)
+    for k, g in (("mdct_raw", "mdct_raw"), ("logfft", "logfft"), ("noise", "noise"), ("tone", "tone"),
+                 ("logmdct", "logmdct"), ("logmask", "logmask"), ("mdct", "mdct_m1")):
+        assert_bits_equal(out[k], enc[tag + "_" + g], "phaseA " + k)
+    assert_bits_equal(out["ampmax_out"], enc[tag + "_ampmax_out"], "ampmax_out")
+
+
+def test_ampmax_chain(cfg):
+    """in[k] = decay(max(in[k-1], out[k-1])) reproduces the recorded chain (lib/block.c:626-628)."""
+    name, setup, o, enc, _ = cfg
+    W, ain, aout = enc["chain_W"], enc["chain_ampmax_in"], enc["chain_ampmax_out"]
+    g = np.float32(-9999.0)
+    prev = g
+    for k in range(len(W)):
+        g = max(g, prev)
+        g = np.float32(o.ampmax_decay(g, int(W[k])))
+        assert g == ain[k], (k, g, ain[k])
+        prev = aout[k]
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_couple_quantize_normalize(cfg, tag):
+    name, setup, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    for bt in (0, 1):
+        sel = np.where(enc[tag + "_blocktype"] == bt)[0]
+        if not len(sel):
+            continue
+        iw, nz = o.couple_quantize_normalize(W, bt, 7, enc[tag + "_mdct_m1"][sel], enc[tag + "_ilogmask"][sel],
+                                             enc[tag + "_nonzero_in"][sel])
+        assert np.array_equal(iw, enc[tag + "_iwork_out"][sel])
+        assert np.array_equal(nz, enc[tag + "_nonzero_out"][sel])
+
+
+def test_decode(cfg):
+    name, setup, o, _, dec = cfg
+    bs = [setup.blocksize(0), setup.blocksize(1)]
+    Wseq = dec["W"][None, :]
+    coef_off, pcm_off, coef_len, pcm_len = vlib.synthesis_layout(Wseq, bs, setup.channels)
+    assert coef_len == dec["coef"].size
+    pcm = o.synthesis(Wseq, coef_off, dec["coef"], pcm_off, pcm_len)
+    assert_bits_equal(pcm[0], dec["pcm"], "decoded pcm")
+    W0 = int(dec["W"][0])
+    first = o.mdct_backward(W0, dec["coef"][:setup.channels * bs[W0] // 2])
+    assert_bits_equal(first, dec["imdct_first"], "mdct_backward")

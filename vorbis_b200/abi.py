@@ -106,6 +106,11 @@ _PSY_SCALARS = [
 ]
 
 
+def _sc(v):
+    """scalar out of a 0-d / 1-element numpy array (npz round trip)"""
+    return np.asarray(v).reshape(-1)[0].item()
+
+
 def _np_ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 
@@ -119,11 +124,11 @@ class SetupHolder:
         self.c = Setup()
         a = self.arrays
         s = self.c
-        s.channels = int(a["channels"])
-        s.rate = int(a["rate"])
+        s.channels = int(_sc(a["channels"]))
+        s.rate = int(_sc(a["rate"]))
         s.blocksizes[0], s.blocksizes[1] = [int(x) for x in a["blocksizes"]]
-        s.n_psy = int(a["n_psy"])
-        s.ampmax_att_per_sec = float(a["ampmax_att_per_sec"])
+        s.n_psy = int(_sc(a["n_psy"]))
+        s.ampmax_att_per_sec = float(_sc(a["ampmax_att_per_sec"]))
         for w in range(2):
             for k in range(PACKETBLOBS):
                 s.coupling_pointlimit[w][k] = int(a["coupling_pointlimit"][w][k])
@@ -144,7 +149,7 @@ class SetupHolder:
             p = s.psy[i]
             pre = "psy%d_" % i
             for name in _PSY_SCALARS:
-                v = a[pre + name]
+                v = _sc(a[pre + name])
                 setattr(p, name, float(v) if name in ("ath_adjatt", "ath_maxatt", "tone_abs_limit",
                                                       "noisemaxsupp", "max_curve_dB", "normal_thresh",
                                                       "m_val") else int(v))

@@ -1,0 +1,806 @@
+// vb200.cu — kernels (__global__) and the C ABI of include/vorbis_b200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -Xcompiler -fPIC -shared   (see __graft_entry__.build()).
+// No torch, no oracle/ dependency: this is the product library.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "vorbis_b200.h"
+#include "vb200_tables.h"
+#include "vb200_kernels.cuh"
+#include "floor1_db_table.h"
+
+using namespace vb200;
+
+// ======================================================================== //
+// error plumbing
+static thread_local std::string g_err;
+static int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+  g_err = what;
+  if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+  return code;
+}
+#define CU(call)                                                         \
+  do {                                                                   \
+    cudaError_t e_ = (call);                                             \
+    if (e_ != cudaSuccess) return fail(VB200_EFAULT, #call, e_);         \
+  } while (0)
+
+extern "C" const char *vb200_last_error(void) { return g_err.c_str(); }
+
+// ======================================================================== //
+// context
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct vb200_ctx {
+  int device = 0;
+  int sm_count = 148;
+  vb200_setup setup;                 // scalar copy (pointers not used after create)
+  HostXform hx[2];
+  XformDev dx[2];
+  WinDev dwin;
+  int n_psy = 0;
+  HostPsyFlow hflow[4];
+  PsyDev dpsy[4];
+  std::vector<void *> owned;         // device allocations freed at destroy
+  std::atomic<uint64_t> launches{0};
+  // grow-only scratch for the host-buffer entry points and phase A intermediates
+  DevBuf scratch[16];
+  cudaStream_t s_main = nullptr;
+  std::mutex mu;
+  // optional per-kernel timing of the last Phase-A call (bench roofline evidence)
+  bool profiling = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+template <class T>
+static int upload(vb200_ctx *c, const T *src, size_t count, const T **dst) {
+  void *d = nullptr;
+  size_t bytes = sizeof(T) * (count ? count : 1);
+  CU(cudaMalloc(&d, bytes));
+  c->owned.push_back(d);
+  if (count) CU(cudaMemcpy(d, src, sizeof(T) * count, cudaMemcpyHostToDevice));
+  *dst = reinterpret_cast<const T *>(d);
+  return 0;
+}
+
+static int ensure(vb200_ctx *c, int slot, size_t bytes, void **out) {
+  DevBuf &b = c->scratch[slot];
+  if (b.cap < bytes) {
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    CU(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+  }
+  *out = b.p;
+  return 0;
+}
+
+extern "C" int vb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **out) {
+  if (!s || !out) return fail(VB200_EINVAL, "null argument");
+  for (int w = 0; w < 2; w++)
+    if (!pow2(s->blocksizes[w]) || s->blocksizes[w] < 64 || s->blocksizes[w] > 8192)
+      return fail(VB200_EINVAL, "block sizes must be powers of two in [64,8192] (lib/info.c:227-228)");
+  if (s->blocksizes[0] > s->blocksizes[1]) return fail(VB200_EINVAL, "blocksizes[0] > blocksizes[1]");
+  if (s->n_psy != 0 && s->n_psy != 4) return fail(VB200_EIMPL, "n_psy must be 0 or 4");
+  if (s->channels < 1 || s->channels > VB200_MAX_CHANNELS) return fail(VB200_EINVAL, "channels");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(VB200_EINVAL, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  vb200_ctx *c = new vb200_ctx();
+  c->device = device;
+  c->setup = *s;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+
+  for (int w = 0; w < 2; w++) {
+    HostXform &h = c->hx[w];
+    build_xform(h, s->blocksizes[w], s->window[w]);
+    XformDev &d = c->dx[w];
+    memset(&d, 0, sizeof(d));
+    d.N = h.N; d.log2n = h.log2n; d.nst = h.log2n - 6; d.nf = h.nf; d.scale = h.scale;
+    for (int i = 0; i < h.nf && i < 8; i++) d.fac[i] = h.fac[i];
+    for (size_t i = 0; i < h.stage_off.size() && i < 8; i++) d.stage_off[i] = h.stage_off[i];
+    int rc;
+    if ((rc = upload(c, h.trig.data(), h.trig.size(), &d.trig))) return rc;
+    if ((rc = upload(c, h.bitrev.data(), h.bitrev.size(), &d.bitrev))) return rc;
+    const float *tw = nullptr;
+    if ((rc = upload(c, h.stage_tw.data(), h.stage_tw.size(), &tw))) return rc;
+    d.stage_tw = reinterpret_cast<const float2 *>(tw);
+    if ((rc = upload(c, h.win.data(), h.win.size(), &d.win))) return rc;
+    if ((rc = upload(c, h.wa.data(), h.wa.size(), &d.wa))) return rc;
+    c->dwin.N[w] = h.N;
+    c->dwin.win[w] = d.win;
+  }
+  c->n_psy = s->n_psy;
+  for (int i = 0; i < s->n_psy; i++) {
+    const vb200_psy_setup &p = s->psy[i];
+    if (!p.ath || !p.octave || !p.bark || !p.tonecurves || !p.noiseoffset)
+      return fail(VB200_EINVAL, "psy lookup tables missing");
+    if (p.n != s->blocksizes[i >> 1] / 2) return fail(VB200_EINVAL, "psy n != blocksize/2");
+    HostPsyFlow &f = c->hflow[i];
+    build_psy_flow(f, p);
+    PsyDev &d = c->dpsy[i];
+    memset(&d, 0, sizeof(d));
+    d.n = p.n; d.total = p.total_octave_lines; d.linesper = p.eighth_octave_lines;
+    d.firstoc = p.firstoc; d.shiftoc = p.shiftoc;
+    d.noisewindowfixed = p.noisewindowfixed;
+    d.bark_first_extra = f.bark_first_extra; d.fixed_first_extra = f.fixed_first_extra;
+    d.nruns = (int)f.run_lo.size(); d.ngrp = (int)f.grp.size() / 4; d.tail_lin0 = f.tail_lin0;
+    d.ath_adjatt = p.ath_adjatt; d.ath_maxatt = p.ath_maxatt; d.tone_abs_limit = p.tone_abs_limit;
+    d.noisemaxsupp = p.noisemaxsupp; d.max_curve_dB = p.max_curve_dB; d.m_val = p.m_val;
+    for (int j = 0; j < 3; j++) d.tone_masteratt[j] = p.tone_masteratt[j];
+    int rc;
+    if ((rc = upload(c, p.ath, p.n, &d.ath))) return rc;
+    if ((rc = upload(c, p.octave, p.n, &d.octave))) return rc;
+    if ((rc = upload(c, p.bark, p.n, &d.bark))) return rc;
+    if ((rc = upload(c, p.tonecurves, (size_t)VB200_P_BANDS * VB200_P_LEVELS * (VB200_EHMER_MAX + 2),
+                     &d.tonecurves))) return rc;
+    if ((rc = upload(c, p.noiseoffset, (size_t)VB200_P_NOISECURVES * p.n, &d.noiseoffset))) return rc;
+    if ((rc = upload(c, p.noisecompand, (size_t)VB200_COMPAND_LEVELS, &d.noisecompand))) return rc;
+    std::vector<int> runs;
+    for (size_t r = 0; r < f.run_lo.size(); r++) { runs.push_back(f.run_lo[r]); runs.push_back(f.run_hi[r]); }
+    const int *dr = nullptr, *dg = nullptr;
+    if ((rc = upload(c, runs.data(), runs.size(), &dr))) return rc;
+    if ((rc = upload(c, f.grp.data(), f.grp.size(), &dg))) return rc;
+    d.runs = reinterpret_cast<const int2 *>(dr);
+    d.grps = reinterpret_cast<const int4 *>(dg);
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" void vb200_ctx_destroy(vb200_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (void *p : c->owned) cudaFree(p);
+  for (auto &b : c->scratch) if (b.p) cudaFree(b.p);
+  if (c->s_main) cudaStreamDestroy(c->s_main);
+  for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  delete c;
+}
+
+extern "C" int vb200_ctx_table(vb200_ctx *c, int W, int which, void *dst, int cap) {
+  if (!c || W < 0 || W > 1 || !dst) return VB200_EINVAL;
+  const HostXform &h = c->hx[W];
+  const void *src = nullptr; size_t cnt = 0, el = 4;
+  switch (which) {
+    case 0: src = h.trig.data(); cnt = h.trig.size(); break;
+    case 1: src = h.bitrev.data(); cnt = h.bitrev.size(); break;
+    case 2: src = h.win.data(); cnt = h.win.size(); break;
+    case 3: src = h.wa.data(); cnt = h.wa.size(); break;
+    default: return VB200_EINVAL;
+  }
+  if ((size_t)cap < cnt) return VB200_EINVAL;
+  memcpy(dst, src, cnt * el);
+  return (int)cnt;
+}
+
+extern "C" uint64_t vb200_launch_count(vb200_ctx *c) { return c ? c->launches.load() : 0; }
+
+extern "C" int vb200_set_profiling(vb200_ctx *c, int on) {
+  if (!c) return fail(VB200_EINVAL, "null context");
+  CU(cudaSetDevice(c->device));
+  if (on) for (auto &e : c->ev) if (!e) CU(cudaEventCreate(&e));
+  c->profiling = on != 0;
+  return 0;
+}
+
+extern "C" int vb200_phaseA_kernel_ms(vb200_ctx *c, float *ms3) {
+  if (!c || !ms3 || !c->ev[0]) return fail(VB200_EINVAL, "profiling not enabled");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ev[3]));
+  for (int i = 0; i < 3; i++) CU(cudaEventElapsedTime(ms3 + i, c->ev[i], c->ev[i + 1]));
+  return 0;
+}
+
+// ======================================================================== //
+// kernels
+
+// config 2: batched mdct_forward.  One CTA per vector (grid-stride), the vector
+// staged in shared memory with 128-bit coalesced loads.
+__global__ void __launch_bounds__(256)
+k_mdct_forward(XformDev X, int nvec, const float *__restrict__ in, float *__restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  const int N = X.N, tid = threadIdx.x, nt = blockDim.x;
+  float *sx = sm, *sw = sm + N;
+  for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
+    const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)v * N);
+    for (int i = tid; i < (N >> 2); i += nt) reinterpret_cast<float4 *>(sx)[i] = __ldg(src + i);
+    __syncthreads();
+    dev_mdct_forward(X, sx, sw, out + (size_t)v * (N >> 1), tid, nt);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_mdct_backward(XformDev X, int nvec, const float *__restrict__ in, float *__restrict__ out) {
+  extern __shared__ __align__(16) float sm[];
+  const int N = X.N, n2 = N >> 1, tid = threadIdx.x, nt = blockDim.x;
+  float *sin_ = sm, *so = sm + n2;         // n2 coefficients, N outputs
+  for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
+    const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)v * n2);
+    for (int i = tid; i < (n2 >> 2); i += nt) reinterpret_cast<float4 *>(sin_)[i] = __ldg(src + i);
+    __syncthreads();
+    dev_mdct_backward(X, sin_, so, tid, nt);
+    float4 *dst = reinterpret_cast<float4 *>(out + (size_t)v * N);
+    for (int i = tid; i < (N >> 2); i += nt) dst[i] = reinterpret_cast<float4 *>(so)[i];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_apply_window(WinDev Wd, int W, int nvec, const int *__restrict__ lW, const int *__restrict__ nW,
+               float *__restrict__ data) {
+  const int N = Wd.N[W];
+  for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
+    const int l = lW ? lW[v] : 0, r = nW ? nW[v] : 0;
+    float *d = data + (size_t)v * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      bool z;
+      const float g = dev_window_gain(Wd, W, l, r, i, z);
+      d[i] = z ? 0.f : d[i] * g;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_drft_forward(XformDev X, int nvec, float *__restrict__ data) {
+  extern __shared__ __align__(16) float sm[];
+  const int N = X.N, tid = threadIdx.x, nt = blockDim.x;
+  float *sa = sm, *sb = sm + N;
+  for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
+    float4 *g = reinterpret_cast<float4 *>(data + (size_t)v * N);
+    for (int i = tid; i < (N >> 2); i += nt) reinterpret_cast<float4 *>(sa)[i] = g[i];
+    __syncthreads();
+    const float *r = dev_drft_forward(X, sa, sb, tid, nt);
+    for (int i = tid; i < (N >> 2); i += nt) g[i] = reinterpret_cast<const float4 *>(r)[i];
+    __syncthreads();
+  }
+}
+
+// ---- Phase A, kernel 1: per (block, channel) window + MDCT + FFT + log spectrum.
+// Reads 4N bytes of PCM, writes mdct (2N), logfft (2N) and one local_ampmax.
+// (first per-channel loop of mapping0_forward, lib/mapping0.c:254-360)
+__global__ void __launch_bounds__(256)
+k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
+                   const float *__restrict__ pcm, const vb200_block_desc *__restrict__ desc,
+                   float *__restrict__ mdct, float *__restrict__ logfft, float *__restrict__ lmax) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ float s_red[8];
+  const int N = X.N, n = N >> 1, tid = threadIdx.x, nt = blockDim.x;
+  float *sx = sm, *sw = sm + N, *sf = sm + 2 * N;
+  const float scale = 4.f / (float)N;
+  const float scale_dB = add345(todB_dev(scale));
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int blk = row / ch;
+    const int lW = desc[blk].lW, nW = desc[blk].nW;
+    dev_load_windowed(Wd, W, lW, nW, pcm + (size_t)row * N, sx, tid, nt);
+    __syncthreads();
+    dev_mdct_forward(X, sx, sw, mdct + (size_t)row * n, tid, nt);
+    const float *f = dev_drft_forward(X, sx, sf, tid, nt);
+    // log spectrum + local maximum (lib/mapping0.c:310-345)
+    float mx = -1e30f;
+    float *lf = logfft + (size_t)row * n;
+    for (int k = tid; k < n; k += nt) {
+      float v;
+      if (k == 0) {
+        v = add345(scale_dB + todB_dev(f[0]));
+      } else {
+        const float re = f[2 * k - 1], im = f[2 * k];
+        const float t = re * re + im * im;
+        v = add345(scale_dB + .5f * todB_dev(t));
+      }
+      lf[k] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      float m = s_red[0];
+      for (int w = 1; w < (nt >> 5); w++) m = fmaxf(m, s_red[w]);
+      if (m > 0.f) m = 0.f;
+      lmax[row] = m;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- ampmax: per-block global_ampmax.
+// mode 0 (independent blocks): g[blk] = max(desc[blk].ampmax, locals)   (lib/mapping0.c:244,346)
+// mode 1 (streams): the decay chain of vorbis_analysis_blockout (lib/block.c:626-628,
+//   lib/psy.c:837-848), sequential per stream: one thread per stream.
+__global__ void k_ampmax(int mode, int nstreams, int bps, int ch, const vb200_block_desc *__restrict__ desc,
+                         const float *__restrict__ lmax, const float *__restrict__ amp0,
+                         float secs_att, float *__restrict__ gmax) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nstreams) return;
+  if (mode == 0) {
+    float g = desc[s].ampmax;
+    for (int c = 0; c < ch; c++) g = fmaxf(g, lmax[(size_t)s * ch + c]);
+    gmax[s] = g;
+    return;
+  }
+  float g = amp0 ? amp0[s] : -9999.f;
+  float prev = g;
+  for (int k = 0; k < bps; k++) {
+    const size_t blk = (size_t)s * bps + k;
+    if (prev > g) g = prev;
+    g = g + secs_att;                      // amp += secs*ampmax_att_per_sec
+    if (g < -9999.f) g = -9999.f;
+    float o = g;
+    for (int c = 0; c < ch; c++) o = fmaxf(o, lmax[blk * ch + c]);
+    gmax[blk] = o;
+    prev = o;
+  }
+}
+
+// ---- Phase A, kernel 2: per (block, channel) logmdct, noise mask, tone mask, mix.
+// (second per-channel loop of mapping0_forward, lib/mapping0.c:366-470)
+struct PhaseA2Args {
+  const float *mdct_in;   // [rows][n] raw mdct
+  const float *logfft;    // [rows][n]
+  const float *lmax;      // [rows]
+  const float *gmax;      // [blocks]
+  const vb200_block_desc *desc;
+  float *mdct_out;        // [rows][n] (may alias mdct_in)
+  float *logmdct;         // [rows][n]
+  float *logmask;         // [rows][n]
+  float *ampmax_out;      // [blocks]
+  float *tap_noise, *tap_tone;
+};
+
+__global__ void __launch_bounds__(256)
+k_phaseA_psy(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
+  extern __shared__ __align__(16) float sm[];
+  const int n = P0.n, ns = n + 4, tid = threadIdx.x, nt = blockDim.x;
+  const int total = P0.total > P1.total ? P0.total : P1.total;
+  float *s_logmdct = sm;
+  float *s_work = s_logmdct + n;
+  float *s_noise = s_work + n;
+  float *s_scan = s_noise + n;             // 5*ns
+  float *s_fft = s_scan + 5 * ns;          // logfft
+  float *s_tone = s_fft + n;
+  int   *s_seed = reinterpret_cast<int *>(s_tone + n);
+  int   *s_pstk = s_seed + total;
+  float *s_astk = reinterpret_cast<float *>(s_pstk + total);
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int blk = row / ch;
+    const PsyDev &P = A.desc[blk].blocktype ? P1 : P0;
+    const float *gm = A.mdct_in + (size_t)row * n;
+    const float *lf = A.logfft + (size_t)row * n;
+    for (int i = tid; i < n; i += nt) {
+      const float l = add345(todB_dev(gm[i]));          // lib/mapping0.c:384-385
+      s_logmdct[i] = l;
+      A.logmdct[(size_t)row * n + i] = l;
+      s_fft[i] = lf[i];
+    }
+    __syncthreads();
+    dev_noisemask(P, s_logmdct, s_noise, s_work, s_scan, ns, tid, nt);
+    const float g = A.gmax[blk];
+    dev_tonemask(P, s_fft, s_tone, g, A.lmax[row], s_seed, s_pstk, s_astk, tid, nt);
+    const float *noff = P.noiseoffset + n;               // offset_select 1
+    for (int i = tid; i < n; i += nt) {
+      float m = gm[i];
+      const float nz = s_noise[i], tn = s_tone[i];
+      const float lm = dev_mix_bin(P, 1, nz, tn, __ldg(noff + i), s_logmdct[i], m);
+      A.logmask[(size_t)row * n + i] = lm;
+      A.mdct_out[(size_t)row * n + i] = m;
+      if (A.tap_noise) A.tap_noise[(size_t)row * n + i] = nz;
+      if (A.tap_tone) A.tap_tone[(size_t)row * n + i] = tn;
+    }
+    if (tid == 0 && (row % ch) == 0) A.ampmax_out[blk] = g;   // lib/mapping0.c:576
+    __syncthreads();
+  }
+}
+
+// ---- stage-isolated psy kernels (parity tests feed them the oracle's upstream vectors)
+__global__ void __launch_bounds__(256)
+k_noisemask(PsyDev P, int nvec, const float *__restrict__ logmdct, float *__restrict__ noise) {
+  extern __shared__ __align__(16) float sm[];
+  const int n = P.n, ns = n + 4, tid = threadIdx.x, nt = blockDim.x;
+  float *s_l = sm, *s_w = sm + n, *s_n = sm + 2 * n, *s_s = sm + 3 * n;
+  for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
+    for (int i = tid; i < n; i += nt) s_l[i] = logmdct[(size_t)v * n + i];
+    __syncthreads();
+    dev_noisemask(P, s_l, s_n, s_w, s_s, ns, tid, nt);
+    for (int i = tid; i < n; i += nt) noise[(size_t)v * n + i] = s_n[i];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_tonemask(PsyDev P, int nvec, const float *__restrict__ logfft, const float *__restrict__ gmax,
+           const float *__restrict__ lmax, float *__restrict__ tone) {
+  extern __shared__ __align__(16) float sm[];
+  const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
+  float *s_f = sm, *s_t = sm + n;
+  int *s_seed = reinterpret_cast<int *>(sm + 2 * n);
+  int *s_p = s_seed + P.total;
+  float *s_a = reinterpret_cast<float *>(s_p + P.total);
+  for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
+    for (int i = tid; i < n; i += nt) s_f[i] = logfft[(size_t)v * n + i];
+    __syncthreads();
+    dev_tonemask(P, s_f, s_t, gmax[v], lmax[v], s_seed, s_p, s_a, tid, nt);
+    for (int i = tid; i < n; i += nt) tone[(size_t)v * n + i] = s_t[i];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_offset_and_mix(PsyDev P, int nvec, int sel, const float *__restrict__ noise,
+                 const float *__restrict__ tone, float *__restrict__ mdct,
+                 const float *__restrict__ logmdct, float *__restrict__ logmask) {
+  const int n = P.n;
+  const size_t tot = (size_t)nvec * n;
+  const float *noff = P.noiseoffset + (size_t)sel * n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e % n);
+    float m = mdct[e];
+    logmask[e] = dev_mix_bin(P, sel, noise[e], tone[e], __ldg(noff + i), logmdct[e], m);
+    if (sel == 1) mdct[e] = m;
+  }
+}
+
+// ======================================================================== //
+// launch helpers
+static int threads_for(int N) {
+  int t = N / 8;
+  if (t < 64) t = 64;
+  if (t > 256) t = 256;
+  return t;
+}
+
+static int grid_for(vb200_ctx *c, int items, int ctas_per_sm) {
+  long g = (long)c->sm_count * ctas_per_sm;
+  if (g > items) g = items;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024)
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+#define CHECK_CTX(c) do { if (!(c)) return fail(VB200_EINVAL, "null context"); CU(cudaSetDevice((c)->device)); } while (0)
+#define CHECK_W(W)   do { if ((W) < 0 || (W) > 1) return fail(VB200_EINVAL, "W must be 0 or 1"); } while (0)
+
+static int post_launch(vb200_ctx *c, int n = 1) {
+  c->launches += n;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// ======================================================================== //
+// transforms
+extern "C" int vb200_mdct_forward_dev(vb200_ctx *c, int W, int nvec, const float *d_in, float *d_out, void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nvec <= 0) return 0;
+  const XformDev &X = c->dx[W];
+  const size_t smem = sizeof(float) * 2 * X.N;
+  int rc = set_smem(k_mdct_forward, smem); if (rc) return rc;
+  const int nt = threads_for(X.N);
+  k_mdct_forward<<<grid_for(c, nvec, 8), nt, smem, (cudaStream_t)stream>>>(X, nvec, d_in, d_out);
+  return post_launch(c);
+}
+
+extern "C" int vb200_mdct_backward_dev(vb200_ctx *c, int W, int nvec, const float *d_in, float *d_out, void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nvec <= 0) return 0;
+  const XformDev &X = c->dx[W];
+  const size_t smem = sizeof(float) * (X.N + X.N / 2);
+  int rc = set_smem(k_mdct_backward, smem); if (rc) return rc;
+  k_mdct_backward<<<grid_for(c, nvec, 8), threads_for(X.N), smem, (cudaStream_t)stream>>>(X, nvec, d_in, d_out);
+  return post_launch(c);
+}
+
+// generic "copy in, run, copy out" for the host-buffer variants
+struct HostIO {
+  vb200_ctx *c;
+  int slot = 0;
+  int h2d(const void *src, size_t bytes, void **d) {
+    int rc = ensure(c, slot++, bytes, d); if (rc) return rc;
+    if (src) CU(cudaMemcpyAsync(*d, src, bytes, cudaMemcpyHostToDevice, c->s_main));
+    return 0;
+  }
+  int d2h(void *dst, const void *d, size_t bytes) {
+    CU(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, c->s_main));
+    return 0;
+  }
+  int sync() { CU(cudaStreamSynchronize(c->s_main)); return 0; }
+};
+
+extern "C" int vb200_mdct_forward(vb200_ctx *c, int W, int nvec, const float *in, float *out) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nvec <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int N = c->dx[W].N;
+  HostIO io{c};
+  void *di, *dout; int rc;
+  if ((rc = io.h2d(in, sizeof(float) * (size_t)nvec * N, &di))) return rc;
+  if ((rc = io.h2d(nullptr, sizeof(float) * (size_t)nvec * N / 2, &dout))) return rc;
+  if ((rc = vb200_mdct_forward_dev(c, W, nvec, (const float *)di, (float *)dout, c->s_main))) return rc;
+  if ((rc = io.d2h(out, dout, sizeof(float) * (size_t)nvec * N / 2))) return rc;
+  return io.sync();
+}
+
+extern "C" int vb200_mdct_backward(vb200_ctx *c, int W, int nvec, const float *in, float *out) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nvec <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int N = c->dx[W].N;
+  HostIO io{c};
+  void *di, *dout; int rc;
+  if ((rc = io.h2d(in, sizeof(float) * (size_t)nvec * N / 2, &di))) return rc;
+  if ((rc = io.h2d(nullptr, sizeof(float) * (size_t)nvec * N, &dout))) return rc;
+  if ((rc = vb200_mdct_backward_dev(c, W, nvec, (const float *)di, (float *)dout, c->s_main))) return rc;
+  if ((rc = io.d2h(out, dout, sizeof(float) * (size_t)nvec * N))) return rc;
+  return io.sync();
+}
+
+extern "C" int vb200_apply_window(vb200_ctx *c, int W, int nvec, const int32_t *lW, const int32_t *nW, float *data) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nvec <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int N = c->dx[W].N;
+  HostIO io{c};
+  void *dd, *dl = nullptr, *dn = nullptr; int rc;
+  if ((rc = io.h2d(data, sizeof(float) * (size_t)nvec * N, &dd))) return rc;
+  if (lW && (rc = io.h2d(lW, sizeof(int32_t) * nvec, &dl))) return rc;
+  if (nW && (rc = io.h2d(nW, sizeof(int32_t) * nvec, &dn))) return rc;
+  k_apply_window<<<grid_for(c, nvec, 8), 256, 0, c->s_main>>>(c->dwin, W, nvec, (const int *)dl, (const int *)dn, (float *)dd);
+  if ((rc = post_launch(c))) return rc;
+  if ((rc = io.d2h(data, dd, sizeof(float) * (size_t)nvec * N))) return rc;
+  return io.sync();
+}
+
+extern "C" int vb200_drft_forward(vb200_ctx *c, int W, int nvec, float *data) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nvec <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const XformDev &X = c->dx[W];
+  HostIO io{c};
+  void *dd; int rc;
+  if ((rc = io.h2d(data, sizeof(float) * (size_t)nvec * X.N, &dd))) return rc;
+  const size_t smem = sizeof(float) * 2 * X.N;
+  if ((rc = set_smem(k_drft_forward, smem))) return rc;
+  k_drft_forward<<<grid_for(c, nvec, 8), threads_for(X.N), smem, c->s_main>>>(X, nvec, (float *)dd);
+  if ((rc = post_launch(c))) return rc;
+  if ((rc = io.d2h(data, dd, sizeof(float) * (size_t)nvec * X.N))) return rc;
+  return io.sync();
+}
+
+// ======================================================================== //
+// stage-isolated psy entry points
+static size_t psy2_smem(const PsyDev &a, const PsyDev &b) {
+  const int n = a.n, total = a.total > b.total ? a.total : b.total;
+  return sizeof(float) * ((size_t)5 * n + 5 * (n + 4) + 3 * (size_t)total) + 64;
+}
+
+#define CHECK_LOOK(c, look) do { if ((look) < 0 || (look) >= (c)->n_psy) return fail(VB200_EINVAL, "no such psy look"); } while (0)
+
+extern "C" int vb200_noisemask(vb200_ctx *c, int look, int nvec, const float *logmdct, float *noise) {
+  CHECK_CTX(c); CHECK_LOOK(c, look);
+  if (nvec <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const PsyDev &P = c->dpsy[look];
+  HostIO io{c};
+  void *di, *dout; int rc;
+  const size_t bytes = sizeof(float) * (size_t)nvec * P.n;
+  if ((rc = io.h2d(logmdct, bytes, &di))) return rc;
+  if ((rc = io.h2d(nullptr, bytes, &dout))) return rc;
+  const size_t smem = sizeof(float) * ((size_t)3 * P.n + 5 * (P.n + 4));
+  if ((rc = set_smem(k_noisemask, smem))) return rc;
+  k_noisemask<<<grid_for(c, nvec, 4), 256, smem, c->s_main>>>(P, nvec, (const float *)di, (float *)dout);
+  if ((rc = post_launch(c))) return rc;
+  if ((rc = io.d2h(noise, dout, bytes))) return rc;
+  return io.sync();
+}
+
+extern "C" int vb200_tonemask(vb200_ctx *c, int look, int nvec, const float *logfft,
+                              const float *gmax, const float *lmax, float *tone) {
+  CHECK_CTX(c); CHECK_LOOK(c, look);
+  if (nvec <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const PsyDev &P = c->dpsy[look];
+  HostIO io{c};
+  void *di, *dg, *dl, *dout; int rc;
+  const size_t bytes = sizeof(float) * (size_t)nvec * P.n;
+  if ((rc = io.h2d(logfft, bytes, &di))) return rc;
+  if ((rc = io.h2d(gmax, sizeof(float) * nvec, &dg))) return rc;
+  if ((rc = io.h2d(lmax, sizeof(float) * nvec, &dl))) return rc;
+  if ((rc = io.h2d(nullptr, bytes, &dout))) return rc;
+  const size_t smem = sizeof(float) * ((size_t)2 * P.n + 3 * (size_t)P.total);
+  if ((rc = set_smem(k_tonemask, smem))) return rc;
+  k_tonemask<<<grid_for(c, nvec, 4), 256, smem, c->s_main>>>(P, nvec, (const float *)di, (const float *)dg,
+                                                             (const float *)dl, (float *)dout);
+  if ((rc = post_launch(c))) return rc;
+  if ((rc = io.d2h(tone, dout, bytes))) return rc;
+  return io.sync();
+}
+
+extern "C" int vb200_offset_and_mix(vb200_ctx *c, int look, int nvec, int sel, const float *noise,
+                                    const float *tone, float *mdct, const float *logmdct, float *logmask) {
+  CHECK_CTX(c); CHECK_LOOK(c, look);
+  if (sel < 0 || sel > 2) return fail(VB200_EINVAL, "offset_select");
+  if (nvec <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const PsyDev &P = c->dpsy[look];
+  HostIO io{c};
+  void *dn, *dt, *dm, *dl, *dk; int rc;
+  const size_t bytes = sizeof(float) * (size_t)nvec * P.n;
+  if ((rc = io.h2d(noise, bytes, &dn))) return rc;
+  if ((rc = io.h2d(tone, bytes, &dt))) return rc;
+  if ((rc = io.h2d(mdct, bytes, &dm))) return rc;
+  if ((rc = io.h2d(logmdct, bytes, &dl))) return rc;
+  if ((rc = io.h2d(nullptr, bytes, &dk))) return rc;
+  k_offset_and_mix<<<grid_for(c, (int)(((size_t)nvec * P.n + 255) / 256), 8), 256, 0, c->s_main>>>(
+      P, nvec, sel, (const float *)dn, (const float *)dt, (float *)dm, (const float *)dl, (float *)dk);
+  if ((rc = post_launch(c))) return rc;
+  if ((rc = io.d2h(logmask, dk, bytes))) return rc;
+  if ((rc = io.d2h(mdct, dm, bytes))) return rc;
+  return io.sync();
+}
+
+// ======================================================================== //
+// Phase A
+static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io,
+                         int nstreams, int bps, const float *d_amp0, cudaStream_t st,
+                         float *d_logfft, float *d_lmax, float *d_gmax) {
+  const XformDev &X = c->dx[W];
+  const int ch = c->setup.channels, N = X.N;
+  const int rows = nblocks * ch;
+  if (c->profiling) CU(cudaEventRecord(c->ev[0], st));
+  {
+    const size_t smem = sizeof(float) * 3 * N;
+    int rc = set_smem(k_phaseA_transform, smem); if (rc) return rc;
+    float *mdct_raw = io->tap_mdct_raw ? io->tap_mdct_raw : io->mdct;
+    k_phaseA_transform<<<grid_for(c, rows, 8), threads_for(N), smem, st>>>(
+        X, c->dwin, W, ch, rows, io->pcm, io->desc, mdct_raw, d_logfft, d_lmax);
+    rc = post_launch(c); if (rc) return rc;
+  }
+  if (c->profiling) CU(cudaEventRecord(c->ev[1], st));
+  {
+    const int n = N / 2;
+    const float secs = (float)n / (float)c->setup.rate;           // lib/psy.c:843
+    const float secs_att = secs * c->setup.ampmax_att_per_sec;
+    if (nstreams > 0)
+      k_ampmax<<<(nstreams + 127) / 128, 128, 0, st>>>(1, nstreams, bps, ch, io->desc, d_lmax, d_amp0, secs_att, d_gmax);
+    else
+      k_ampmax<<<(nblocks + 127) / 128, 128, 0, st>>>(0, nblocks, 0, ch, io->desc, d_lmax, nullptr, secs_att, d_gmax);
+    int rc = post_launch(c); if (rc) return rc;
+  }
+  if (c->profiling) CU(cudaEventRecord(c->ev[2], st));
+  {
+    const PsyDev &P0 = c->dpsy[2 * W], &P1 = c->dpsy[2 * W + 1];
+    const size_t smem = psy2_smem(P0, P1);
+    int rc = set_smem(k_phaseA_psy, smem); if (rc) return rc;
+    PhaseA2Args A;
+    A.mdct_in = io->tap_mdct_raw ? io->tap_mdct_raw : io->mdct;
+    A.logfft = d_logfft; A.lmax = d_lmax; A.gmax = d_gmax; A.desc = io->desc;
+    A.mdct_out = io->mdct; A.logmdct = io->logmdct; A.logmask = io->logmask; A.ampmax_out = io->ampmax_out;
+    A.tap_noise = io->tap_noise; A.tap_tone = io->tap_tone;
+    k_phaseA_psy<<<grid_for(c, rows, 4), 256, smem, st>>>(P0, P1, ch, rows, A);
+    rc = post_launch(c); if (rc) return rc;
+  }
+  if (c->profiling) CU(cudaEventRecord(c->ev[3], st));
+  return 0;
+}
+
+static int phaseA_dev_common(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io,
+                             int nstreams, int bps, const float *d_amp0, void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (c->n_psy != 4) return fail(VB200_EIMPL, "context has no psy lookups");
+  if (!io || !io->pcm || !io->desc || !io->mdct || !io->logmdct || !io->logmask || !io->ampmax_out)
+    return fail(VB200_EINVAL, "phase A io pointers");
+  if (nblocks <= 0) return 0;
+  const int ch = c->setup.channels, n = c->dx[W].N / 2;
+  void *d_logfft = io->tap_logfft, *d_lmax, *d_gmax; int rc;
+  if (!d_logfft && (rc = ensure(c, 13, sizeof(float) * (size_t)nblocks * ch * n, &d_logfft))) return rc;
+  if ((rc = ensure(c, 14, sizeof(float) * (size_t)nblocks * ch, &d_lmax))) return rc;
+  if ((rc = ensure(c, 15, sizeof(float) * (size_t)nblocks, &d_gmax))) return rc;
+  return phaseA_launch(c, W, nblocks, io, nstreams, bps, d_amp0, (cudaStream_t)stream,
+                       (float *)d_logfft, (float *)d_lmax, (float *)d_gmax);
+}
+
+extern "C" int vb200_analysis_phaseA_dev(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io, void *stream) {
+  return phaseA_dev_common(c, W, nblocks, io, 0, 0, nullptr, stream);
+}
+
+extern "C" int vb200_analysis_phaseA_streams_dev(vb200_ctx *c, int W, int nstreams, int bps,
+                                                 const vb200_phaseA_io *io, const float *d_amp0, void *stream) {
+  if (nstreams <= 0 || bps <= 0) return fail(VB200_EINVAL, "nstreams/blocks_per_stream");
+  return phaseA_dev_common(c, W, nstreams * bps, io, nstreams, bps, d_amp0, stream);
+}
+
+extern "C" int vb200_analysis_phaseA(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *h) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (!h) return fail(VB200_EINVAL, "null io");
+  if (nblocks <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int ch = c->setup.channels, N = c->dx[W].N, n = N / 2;
+  const size_t rows = (size_t)nblocks * ch;
+  HostIO io{c};
+  vb200_phaseA_io d;
+  memset(&d, 0, sizeof(d));
+  void *p; int rc;
+  if ((rc = io.h2d(h->pcm, sizeof(float) * rows * N, &p))) return rc; d.pcm = (const float *)p;
+  if ((rc = io.h2d(h->desc, sizeof(vb200_block_desc) * nblocks, &p))) return rc; d.desc = (const vb200_block_desc *)p;
+  if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.mdct = (float *)p;
+  if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.logmdct = (float *)p;
+  if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.logmask = (float *)p;
+  if ((rc = io.h2d(nullptr, sizeof(float) * nblocks, &p))) return rc; d.ampmax_out = (float *)p;
+  // optional taps share one extra slot each
+  if (h->tap_noise) { if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.tap_noise = (float *)p; }
+  if (h->tap_tone) { if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.tap_tone = (float *)p; }
+  if (h->tap_logfft) { if ((rc = ensure(c, 11, sizeof(float) * rows * n, &p))) return rc; d.tap_logfft = (float *)p; }
+  if (h->tap_mdct_raw) { if ((rc = ensure(c, 12, sizeof(float) * rows * n, &p))) return rc; d.tap_mdct_raw = (float *)p; }
+  if ((rc = phaseA_dev_common(c, W, nblocks, &d, 0, 0, nullptr, c->s_main))) return rc;
+  if ((rc = io.d2h(h->mdct, d.mdct, sizeof(float) * rows * n))) return rc;
+  if ((rc = io.d2h(h->logmdct, d.logmdct, sizeof(float) * rows * n))) return rc;
+  if ((rc = io.d2h(h->logmask, d.logmask, sizeof(float) * rows * n))) return rc;
+  if ((rc = io.d2h(h->ampmax_out, d.ampmax_out, sizeof(float) * nblocks))) return rc;
+  if (h->tap_noise && (rc = io.d2h(h->tap_noise, d.tap_noise, sizeof(float) * rows * n))) return rc;
+  if (h->tap_tone && (rc = io.d2h(h->tap_tone, d.tap_tone, sizeof(float) * rows * n))) return rc;
+  if (h->tap_logfft && (rc = io.d2h(h->tap_logfft, d.tap_logfft, sizeof(float) * rows * n))) return rc;
+  if (h->tap_mdct_raw && (rc = io.d2h(h->tap_mdct_raw, d.tap_mdct_raw, sizeof(float) * rows * n))) return rc;
+  return io.sync();
+}
+
+// ======================================================================== //
+// not yet implemented in this build
+extern "C" int vb200_couple_quantize_normalize_dev(vb200_ctx *, int, int, int, int, const float *, int32_t *, int32_t *, void *) {
+  return fail(VB200_EIMPL, "couple_quantize_normalize: not built yet");
+}
+extern "C" int vb200_couple_quantize_normalize(vb200_ctx *, int, int, int, int, const float *, int32_t *, int32_t *) {
+  return fail(VB200_EIMPL, "couple_quantize_normalize: not built yet");
+}
+extern "C" int vb200_synthesis_dev(vb200_ctx *, int, int, const int32_t *, const int64_t *, const float *,
+                                   const int64_t *, float *, int64_t, void *) {
+  return fail(VB200_EIMPL, "synthesis: not built yet");
+}
+extern "C" int vb200_synthesis(vb200_ctx *, int, int, const int32_t *, const int64_t *, const float *, int64_t,
+                               const int64_t *, float *, int64_t) {
+  return fail(VB200_EIMPL, "synthesis: not built yet");
+}
+
+// ======================================================================== //
+// device memory helpers
+extern "C" int vb200_malloc_device(vb200_ctx *c, size_t bytes, void **dptr) {
+  CHECK_CTX(c);
+  CU(cudaMalloc(dptr, bytes ? bytes : 1));
+  return 0;
+}
+extern "C" int vb200_free_device(vb200_ctx *c, void *dptr) { CHECK_CTX(c); CU(cudaFree(dptr)); return 0; }
+extern "C" int vb200_memcpy_h2d(vb200_ctx *c, void *dptr, const void *src, size_t bytes) {
+  CHECK_CTX(c); CU(cudaMemcpy(dptr, src, bytes, cudaMemcpyHostToDevice)); return 0;
+}
+extern "C" int vb200_memcpy_d2h(vb200_ctx *c, void *dst, const void *dptr, size_t bytes) {
+  CHECK_CTX(c); CU(cudaMemcpy(dst, dptr, bytes, cudaMemcpyDeviceToHost)); return 0;
+}
+extern "C" int vb200_synchronize(vb200_ctx *c) { CHECK_CTX(c); CU(cudaDeviceSynchronize()); return 0; }

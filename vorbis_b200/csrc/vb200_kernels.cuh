@@ -1,0 +1,687 @@
+// vb200_kernels.cuh — hand-written sm_100a kernels for the libvorbis per-block
+// DSP path (window, MDCT, real FFT, log spectra, noise/tone masks, mix).
+//
+// Numerics contract: every output value is produced by the same sequence of
+// IEEE-754 fp32 (and, where the reference promotes, fp64) operations as the
+// reference C code, only scheduled in parallel.  The TU is compiled with
+// -fmad=false (no FMA contraction), default -prec-div/-prec-sqrt, no fast-math,
+// so results are bit-identical to the reference built with -ffp-contract=off.
+// Each stage is a set of independent work items; items are
+// distributed over the threads of one CTA, data lives in shared memory.
+//
+// Reference citations are to the xiph/vorbis tree (libvorbis 1.3.7).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vorbis_b200.h"
+
+namespace vb200 {
+
+#define VB_C1 .92387953251128675613F   /* cos(pi/8),  lib/mdct.h:47 */
+#define VB_C2 .70710678118654752441F   /* cos(2pi/8), lib/mdct.h:46 */
+#define VB_C3 .38268343236508977175F   /* cos(3pi/8), lib/mdct.h:45 */
+#define VB_NEGINF (-9999.f)            /* lib/psy.c:31 */
+
+struct XformDev {
+  int N, log2n, nst, nf;
+  int fac[8];           // factors in drfti1 order (lib/smallft.c:37)
+  int stage_off[8];     // float2 offsets into stage_tw
+  float scale;          // 4/N
+  const float  *trig;   // N + N/4
+  const int    *bitrev; // N/4
+  const float2 *stage_tw;
+  const float  *win;    // N/2
+  const float  *wa;     // N
+};
+
+struct WinDev {         // both half windows, for lW/nW selection (lib/window.c:2102)
+  int N[2];
+  const float *win[2];
+};
+
+struct PsyDev {
+  int n, total, linesper, firstoc, shiftoc;
+  int noisewindowfixed, bark_first_extra, fixed_first_extra;
+  int nruns, ngrp, tail_lin0;
+  float ath_adjatt, ath_maxatt, tone_abs_limit, noisemaxsupp, max_curve_dB, m_val;
+  float tone_masteratt[3];
+  const float *ath;          // [n]
+  const int   *octave;       // [n]
+  const int   *bark;         // [n]
+  const float *tonecurves;   // [17][8][58]
+  const float *noiseoffset;  // [3][n]
+  const float *noisecompand; // [40]
+  const int2  *runs;         // [nruns] (lo,hi)
+  const int4  *grps;         // [ngrp]  (pos0,pos1,lin0,lin1)
+};
+
+// ------------------------------------------------------------------------
+__device__ __forceinline__ float todB_dev(float x) {           // lib/scales.h:43-51
+  const unsigned int u = __float_as_uint(x) & 0x7fffffffu;
+  return __uint2float_rn(u) * 7.17711438e-7f - 764.6161886f;
+}
+__device__ __forceinline__ float add345(float x) {             // "+ .345" is a double add
+  return (float)((double)x + .345);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------
+// MDCT pieces.  x points at n2 = N/2 floats in shared memory.
+
+// mdct_butterflies (lib/mdct.c:316-336): radix-2 stages (butterfly_first /
+// butterfly_generic, :216-314) then the fixed 32/16/8-point flies (:93-214),
+// each level spread over all threads: level L has N/8 independent items.
+__device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int tid, int nt) {
+  const int n2 = X.N >> 1;
+  const int items = n2 >> 2;
+  for (int s = 0; s < X.nst; s++) {
+    const int P = n2 >> s;
+    const int lq = P >> 2;                       // items per sub-block (power of two)
+    const int sh = X.log2n - 3 - s;              // log2(lq)
+    const float2 *tw = X.stage_tw + X.stage_off[s];
+    for (int u = tid; u < items; u += nt) {
+      const int blk = u >> sh, q = u & (lq - 1);
+      float *xb = x + P * blk;
+      const int a = P - 2 - 2 * q, b = (P >> 1) - 2 - 2 * q;
+      const float2 t = __ldg(tw + q);
+      const float2 hi = *reinterpret_cast<float2 *>(xb + a);
+      const float2 lo = *reinterpret_cast<float2 *>(xb + b);
+      const float r0 = hi.x - lo.x, r1 = hi.y - lo.y;
+      *reinterpret_cast<float2 *>(xb + a) = make_float2(hi.x + lo.x, hi.y + lo.y);
+      *reinterpret_cast<float2 *>(xb + b) = make_float2(r1 * t.y + r0 * t.x, r1 * t.x - r0 * t.y);
+    }
+    __syncthreads();
+  }
+  // 32-point fly, first level (lib/mdct.c:152-209): item q pairs (30-2q) with (14-2q)
+  for (int u = tid; u < items; u += nt) {
+    float *xc = x + 32 * (u >> 3);
+    const int q = u & 7;
+    const int a = 30 - 2 * q, b = 14 - 2 * q;
+    const float2 hi = *reinterpret_cast<float2 *>(xc + a);
+    const float2 lo = *reinterpret_cast<float2 *>(xc + b);
+    float r0, r1, o0, o1;
+    switch (q) {
+      case 0: r0 = hi.x - lo.x; r1 = hi.y - lo.y; o0 = r0;                       o1 = r1;                       break;
+      case 1: r0 = hi.x - lo.x; r1 = hi.y - lo.y; o0 = r0 * VB_C1 - r1 * VB_C3;  o1 = r0 * VB_C3 + r1 * VB_C1;  break;
+      case 2: r0 = hi.x - lo.x; r1 = hi.y - lo.y; o0 = (r0 - r1) * VB_C2;        o1 = (r0 + r1) * VB_C2;        break;
+      case 3: r0 = hi.x - lo.x; r1 = hi.y - lo.y; o0 = r0 * VB_C3 - r1 * VB_C1;  o1 = r1 * VB_C3 + r0 * VB_C1;  break;
+      case 4: r0 = hi.x - lo.x; r1 = lo.y - hi.y; o0 = r1;                       o1 = r0;                       break;
+      case 5: r0 = lo.x - hi.x; r1 = lo.y - hi.y; o0 = r1 * VB_C1 + r0 * VB_C3;  o1 = r1 * VB_C3 - r0 * VB_C1;  break;
+      case 6: r0 = lo.x - hi.x; r1 = lo.y - hi.y; o0 = (r1 + r0) * VB_C2;        o1 = (r1 - r0) * VB_C2;        break;
+      default: r0 = lo.x - hi.x; r1 = lo.y - hi.y; o0 = r1 * VB_C3 + r0 * VB_C1; o1 = r1 * VB_C1 - r0 * VB_C3;  break;
+    }
+    *reinterpret_cast<float2 *>(xc + a) = make_float2(hi.x + lo.x, hi.y + lo.y);
+    *reinterpret_cast<float2 *>(xc + b) = make_float2(o0, o1);
+  }
+  __syncthreads();
+  // 16-point fly, first level (lib/mdct.c:117-147): item j pairs (2j) with (2j+8)
+  for (int u = tid; u < items; u += nt) {
+    float *xc = x + 16 * (u >> 2);
+    const int j = u & 3;
+    const float2 lo = *reinterpret_cast<float2 *>(xc + 2 * j);
+    const float2 hi = *reinterpret_cast<float2 *>(xc + 2 * j + 8);
+    float o0, o1;
+    if (j == 0) {
+      const float a = lo.y - hi.y, b = lo.x - hi.x;
+      o0 = (a + b) * VB_C2; o1 = (a - b) * VB_C2;
+    } else if (j == 1) {
+      o0 = lo.y - hi.y; o1 = hi.x - lo.x;
+    } else if (j == 2) {
+      const float a = hi.x - lo.x, b = hi.y - lo.y;
+      o0 = (a - b) * VB_C2; o1 = (a + b) * VB_C2;
+    } else {
+      o0 = hi.x - lo.x; o1 = hi.y - lo.y;
+    }
+    *reinterpret_cast<float2 *>(xc + 2 * j + 8) = make_float2(hi.x + lo.x, hi.y + lo.y);
+    *reinterpret_cast<float2 *>(xc + 2 * j) = make_float2(o0, o1);
+  }
+  __syncthreads();
+  // 8-point fly (lib/mdct.c:93-115): one item per 8 values, in registers
+  for (int u = tid; u < (n2 >> 3); u += nt) {
+    float4 *p = reinterpret_cast<float4 *>(x + 8 * u);
+    const float4 v0 = p[0], v1 = p[1];           // x0..x3, x4..x7
+    const float s62 = v1.z + v0.z, d62 = v1.z - v0.z;
+    const float s40 = v1.x + v0.x, d40 = v1.x - v0.x;
+    const float d51 = v1.y - v0.y, d73 = v1.w - v0.w;
+    const float s51 = v1.y + v0.y, s73 = v1.w + v0.w;
+    float4 o0, o1;
+    o1.z = s62 + s40;  o1.x = s62 - s40;
+    o0.x = d62 + d51;  o0.z = d62 - d51;
+    o0.w = d73 + d40;  o0.y = d73 - d40;
+    o1.w = s73 + s51;  o1.y = s73 - s51;
+    p[0] = o0; p[1] = o1;
+  }
+  __syncthreads();
+}
+
+// mdct_bitreverse (lib/mdct.c:346-394): item m reads two complex values of the
+// upper half w[n2..N) through bitrev[] and writes four values of w[0..n2).
+__device__ __forceinline__ void dev_bitreverse(const XformDev &X, float *w, int tid, int nt) {
+  const int N = X.N, n2 = N >> 1;
+  const float2 *T = reinterpret_cast<const float2 *>(X.trig + N);
+  const int2 *br = reinterpret_cast<const int2 *>(X.bitrev);
+  const float *x = w + n2;
+  for (int m = tid; m < (N >> 3); m += nt) {
+    const int2 b = __ldg(br + m);
+    const float2 t = __ldg(T + m);
+    const float2 x0 = *reinterpret_cast<const float2 *>(x + b.x);
+    const float2 x1 = *reinterpret_cast<const float2 *>(x + b.y);
+    const float r0 = x0.y - x1.y;
+    const float r1 = x0.x + x1.x;
+    const float r2 = r1 * t.x + r0 * t.y;
+    const float r3 = r1 * t.y - r0 * t.x;
+    const float h0 = (x0.y + x1.y) * .5f;
+    const float h1 = (x0.x - x1.x) * .5f;
+    *reinterpret_cast<float2 *>(w + 2 * m) = make_float2(h0 + r2, h1 + r3);
+    *reinterpret_cast<float2 *>(w + n2 - 2 * m - 2) = make_float2(h0 - r2, r3 - h1);
+  }
+  __syncthreads();
+}
+
+// Forward MDCT of the N samples at `in` (shared memory, read-only) using the N
+// floats of scratch at `w`; writes N/2 coefficients to `out` (global or shared).
+// mdct_forward, lib/mdct.c:492-562.
+__device__ __forceinline__ void dev_mdct_forward(const XformDev &X, const float *in, float *w,
+                                                 float *out, int tid, int nt) {
+  const int N = X.N, n2 = N >> 1, n4 = N >> 2, n16 = N >> 4;
+  float *w2 = w + n2;
+  const float2 *Tf = reinterpret_cast<const float2 *>(X.trig);
+  for (int p = tid; p < n4; p += nt) {
+    const float2 t = __ldg(Tf + (n4 - 1 - p));     // trig[n2-2p-2], trig[n2-2p-1]
+    float r0, r1;
+    // x0[0],x0[2] and x1[0],x1[2] via two aligned 128-bit loads (x1 sits at an odd offset)
+    if (p < n16) {
+      const float4 a = *reinterpret_cast<const float4 *>(in + n2 + n4 - 4 * (p + 1));
+      const float4 b = *reinterpret_cast<const float4 *>(in + n2 + n4 + 4 * p);
+      r0 = a.z + b.y;
+      r1 = a.x + b.w;
+    } else if (p < n4 - n16) {
+      const float4 a = *reinterpret_cast<const float4 *>(in + n2 + n4 - 4 * (p + 1));
+      const float4 b = *reinterpret_cast<const float4 *>(in + 4 * (p - n16));
+      r0 = a.z - b.y;
+      r1 = a.x - b.w;
+    } else {
+      const float4 a = *reinterpret_cast<const float4 *>(in + N - 4 * (p - (n4 - n16) + 1));
+      const float4 b = *reinterpret_cast<const float4 *>(in + 4 * (p - n16));
+      r0 = -a.z - b.y;
+      r1 = -a.x - b.w;
+    }
+    *reinterpret_cast<float2 *>(w2 + 2 * p) = make_float2(r1 * t.y + r0 * t.x, r1 * t.x - r0 * t.y);
+  }
+  __syncthreads();
+  dev_butterflies(X, w2, tid, nt);
+  dev_bitreverse(X, w, tid, nt);
+  const float2 *Tp = reinterpret_cast<const float2 *>(X.trig + n2);
+  const float scale = X.scale;
+  for (int i = tid; i < n4; i += nt) {
+    const float2 v = *reinterpret_cast<const float2 *>(w + 2 * i);
+    const float2 t = __ldg(Tp + i);
+    out[i]          = (v.x * t.x + v.y * t.y) * scale;
+    out[n2 - 1 - i] = (v.x * t.y - v.y * t.x) * scale;
+  }
+}
+
+// Inverse MDCT: N/2 coefficients at `in` (shared or global, read-only) -> N
+// samples in the shared buffer `out` (N floats).  mdct_backward, lib/mdct.c:396-490.
+// The result layout is [A | -rev(A) | rev(B) | B].
+__device__ __forceinline__ void dev_mdct_backward(const XformDev &X, const float *in, float *out,
+                                                  int tid, int nt) {
+  const int N = X.N, n2 = N >> 1, n4 = N >> 2, n16 = N >> 4;
+  const float *T = X.trig;
+  for (int u = tid; u < 2 * n16; u += nt) {
+    if (u < n16) {
+      const int j = u;
+      const float *iX = in + n2 - 7 - 8 * j;
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(T + n4 + 4 * j));
+      float4 o;
+      o.x = -iX[2] * t.w - iX[0] * t.z;
+      o.y =  iX[0] * t.w - iX[2] * t.z;
+      o.z = -iX[6] * t.y - iX[4] * t.x;
+      o.w =  iX[4] * t.y - iX[6] * t.x;
+      *reinterpret_cast<float4 *>(out + n2 + n4 - 4 * (j + 1)) = o;
+    } else {
+      const int j = u - n16;
+      const float *iX = in + n2 - 8 - 8 * j;
+      const float4 t = __ldg(reinterpret_cast<const float4 *>(T + n4 - 4 * (j + 1)));
+      float4 o;
+      o.x = iX[4] * t.w + iX[6] * t.z;
+      o.y = iX[4] * t.z - iX[6] * t.w;
+      o.z = iX[0] * t.y + iX[2] * t.x;
+      o.w = iX[0] * t.x - iX[2] * t.y;
+      *reinterpret_cast<float4 *>(out + n2 + n4 + 4 * j) = o;
+    }
+  }
+  __syncthreads();
+  dev_butterflies(X, out + n2, tid, nt);
+  dev_bitreverse(X, out, tid, nt);
+  const float2 *Tp = reinterpret_cast<const float2 *>(X.trig + n2);
+  // item k: A[n4-1-k] = re*T1 - im*T0, B[k] = -(re*T0 + im*T1)
+  for (int k = tid; k < n4; k += nt) {
+    const float2 v = *reinterpret_cast<const float2 *>(out + 2 * k);
+    const float2 t = __ldg(Tp + k);
+    out[n2 + n4 - 1 - k] = v.x * t.y - v.y * t.x;
+    out[n2 + n4 + k]     = -(v.x * t.x + v.y * t.y);
+  }
+  __syncthreads();
+  for (int k = tid; k < n4; k += nt) {
+    const float a = out[n2 + n4 - 1 - k];
+    out[n4 - 1 - k] = a;
+    out[n4 + k] = -a;
+  }
+  __syncthreads();
+  for (int k = tid; k < n4; k += nt) out[n2 + n4 - 1 - k] = out[n2 + n4 + k];
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------
+// Real FFT forward (drftf1 + dradf4 + dradf2, lib/smallft.c:572-631, 168-268,
+// 113-166).  One pass per factor, last factor first; each pass reads cc and
+// writes ch (both N floats of shared memory).  Items: for every k<l1, the i=0
+// column, the twiddled interior pairs i=2,4,.., and the i=ido-1 column.
+__device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, float *ch,
+                                              const float *w1, const float *w2, const float *w3,
+                                              int tid, int nt) {
+  const float hsqt2 = .70710678118654752f;
+  const int t0 = l1 * ido;
+  if (ido == 1) {
+    for (int k = tid; k < l1; k += nt) {
+      const float c0 = cc[k], c1 = cc[k + t0], c2 = cc[k + 2 * t0], c3 = cc[k + 3 * t0];
+      const float tr1 = c1 + c3, tr2 = c0 + c2;
+      float4 o;
+      o.x = tr1 + tr2;       // o[0]
+      o.y = c0 - c2;         // o[2*ido-1] = o[1]
+      o.z = c3 - c1;         // o[2*ido]   = o[2]
+      o.w = tr2 - tr1;       // o[4*ido-1] = o[3]
+      *reinterpret_cast<float4 *>(ch + 4 * k) = o;
+    }
+    return;
+  }
+  const int half = ido >> 1;                         // power of two
+  const int items = l1 * half;
+  for (int v = tid; v < items + l1; v += nt) {
+    if (v < items) {
+      const int k = v / half, ii = v - k * half;
+      const float *c0 = cc + k * ido, *c1 = c0 + t0, *c2 = c1 + t0, *c3 = c2 + t0;
+      float *o = ch + 4 * k * ido;
+      if (ii == 0) {
+        const float tr1 = c1[0] + c3[0];
+        const float tr2 = c0[0] + c2[0];
+        o[0]           = tr1 + tr2;
+        o[4 * ido - 1] = tr2 - tr1;
+        o[2 * ido - 1] = c0[0] - c2[0];
+        o[2 * ido]     = c3[0] - c1[0];
+      } else {
+        const int i = 2 * ii;
+        const float wa1r = __ldg(w1 + i - 2), wa1i = __ldg(w1 + i - 1);
+        const float wa2r = __ldg(w2 + i - 2), wa2i = __ldg(w2 + i - 1);
+        const float wa3r = __ldg(w3 + i - 2), wa3i = __ldg(w3 + i - 1);
+        const float cr2 = wa1r * c1[i - 1] + wa1i * c1[i];
+        const float ci2 = wa1r * c1[i]     - wa1i * c1[i - 1];
+        const float cr3 = wa2r * c2[i - 1] + wa2i * c2[i];
+        const float ci3 = wa2r * c2[i]     - wa2i * c2[i - 1];
+        const float cr4 = wa3r * c3[i - 1] + wa3i * c3[i];
+        const float ci4 = wa3r * c3[i]     - wa3i * c3[i - 1];
+        const float tr1 = cr2 + cr4, tr4 = cr4 - cr2;
+        const float ti1 = ci2 + ci4, ti4 = ci2 - ci4;
+        const float ti2 = c0[i] + ci3,     ti3 = c0[i] - ci3;
+        const float tr2 = c0[i - 1] + cr3, tr3 = c0[i - 1] - cr3;
+        const int ic = 2 * ido - i;
+        o[i - 1]            = tr1 + tr2;   o[i]            = ti1 + ti2;
+        o[ic - 1]           = tr3 - ti4;   o[ic]           = tr4 - ti3;
+        o[2 * ido + i - 1]  = ti4 + tr3;   o[2 * ido + i]  = tr4 + ti3;
+        o[2 * ido + ic - 1] = tr2 - tr1;   o[2 * ido + ic] = ti1 - ti2;
+      }
+    } else {
+      const int k = v - items;
+      const float *c0 = cc + k * ido, *c1 = c0 + t0, *c2 = c1 + t0, *c3 = c2 + t0;
+      float *o = ch + 4 * k * ido;
+      const float ti1 = -hsqt2 * (c1[ido - 1] + c3[ido - 1]);
+      const float tr1 =  hsqt2 * (c1[ido - 1] - c3[ido - 1]);
+      o[ido - 1]     = tr1 + c0[ido - 1];
+      o[3 * ido - 1] = c0[ido - 1] - tr1;
+      o[ido]         = ti1 - c2[ido - 1];
+      o[3 * ido]     = ti1 + c2[ido - 1];
+    }
+  }
+}
+
+__device__ __forceinline__ void dev_fft_pass2(int ido, int l1, const float *cc, float *ch,
+                                              const float *w1, int tid, int nt) {
+  const int t0 = l1 * ido;
+  if (ido == 1) {
+    for (int k = tid; k < l1; k += nt) {
+      const float a = cc[k], b = cc[k + t0];
+      ch[2 * k] = a + b;
+      ch[2 * k + 1] = a - b;
+    }
+    return;
+  }
+  const int half = ido >> 1;
+  const int items = l1 * half;
+  for (int v = tid; v < items + l1; v += nt) {
+    if (v < items) {
+      const int k = v / half, ii = v - k * half;
+      const float *c0 = cc + k * ido, *c1 = c0 + t0;
+      float *o = ch + 2 * k * ido;
+      if (ii == 0) {
+        o[0]           = c0[0] + c1[0];
+        o[2 * ido - 1] = c0[0] - c1[0];
+      } else {
+        const int i = 2 * ii;
+        const float wr = __ldg(w1 + i - 2), wi = __ldg(w1 + i - 1);
+        const float tr2 = wr * c1[i - 1] + wi * c1[i];
+        const float ti2 = wr * c1[i]     - wi * c1[i - 1];
+        const int ic = 2 * ido - i;
+        o[i]      = c0[i] + ti2;       o[ic]     = ti2 - c0[i];
+        o[i - 1]  = c0[i - 1] + tr2;   o[ic - 1] = c0[i - 1] - tr2;
+      }
+    } else {
+      const int k = v - items;
+      const float *c0 = cc + k * ido, *c1 = c0 + t0;
+      float *o = ch + 2 * k * ido;
+      o[ido]     = -c1[ido - 1];
+      o[ido - 1] = c0[ido - 1];
+    }
+  }
+}
+
+// Returns the buffer (a or b) that holds the transform of the data in `a`.
+__device__ __forceinline__ float *dev_drft_forward(const XformDev &X, float *a, float *b,
+                                                   int tid, int nt) {
+  const int N = X.N, nf = X.nf;
+  int l2 = N, iw = N;
+  float *src = a, *dst = b;
+  for (int k1 = 0; k1 < nf; k1++) {
+    const int ip = X.fac[nf - 1 - k1];
+    const int l1 = l2 / ip, ido = N / l2;
+    iw -= (ip - 1) * ido;
+    if (ip == 4)
+      dev_fft_pass4(ido, l1, src, dst, X.wa + iw - 1, X.wa + iw + ido - 1, X.wa + iw + 2 * ido - 1, tid, nt);
+    else
+      dev_fft_pass2(ido, l1, src, dst, X.wa + iw - 1, tid, nt);
+    __syncthreads();
+    float *t = src; src = dst; dst = t;
+    l2 = l1;
+  }
+  return src;
+}
+
+// _vorbis_apply_window (lib/window.c:2102-2135) fused into the load of one
+// block from global memory: dst[i] = windowed src[i].
+__device__ __forceinline__ float dev_window_gain(const WinDev &Wd, int W, int lW, int nW, int i,
+                                                 bool &zero) {
+  if (!W) { lW = 0; nW = 0; }
+  const int n = Wd.N[W], ln = Wd.N[lW], rn = Wd.N[nW];
+  const int leftbegin = n / 4 - ln / 4, leftend = leftbegin + ln / 2;
+  const int rightbegin = n / 2 + n / 4 - rn / 4, rightend = rightbegin + rn / 2;
+  zero = false;
+  if (i < leftbegin || i >= rightend) { zero = true; return 0.f; }
+  if (i < leftend) return __ldg(Wd.win[lW] + (i - leftbegin));
+  if (i >= rightbegin) return __ldg(Wd.win[nW] + (rn / 2 - 1 - (i - rightbegin)));
+  return 1.f;   // flat middle: sample is left untouched (x*1.0f is exact)
+}
+
+__device__ __forceinline__ void dev_load_windowed(const WinDev &Wd, int W, int lW, int nW,
+                                                  const float *__restrict__ src, float *dst,
+                                                  int tid, int nt) {
+  const int N = Wd.N[W];
+  const float4 *s4 = reinterpret_cast<const float4 *>(src);
+  for (int v = tid; v < (N >> 2); v += nt) {
+    const float4 x = __ldg(s4 + v);
+    float4 o;
+    bool z;
+    float g;
+    g = dev_window_gain(Wd, W, lW, nW, 4 * v + 0, z); o.x = z ? 0.f : x.x * g;
+    g = dev_window_gain(Wd, W, lW, nW, 4 * v + 1, z); o.y = z ? 0.f : x.y * g;
+    g = dev_window_gain(Wd, W, lW, nW, 4 * v + 2, z); o.z = z ? 0.f : x.z * g;
+    g = dev_window_gain(Wd, W, lW, nW, 4 * v + 3, z); o.w = z ? 0.f : x.w * g;
+    *reinterpret_cast<float4 *>(dst + 4 * v) = o;
+  }
+}
+
+// ------------------------------------------------------------------------
+// Noise mask: bark_noise_hybridmp (lib/psy.c:547-704).
+// S = 5 prefix arrays with row stride ns (ns = n+4 keeps the five sequential
+// lanes on different banks for 128-bit accesses).
+
+struct Abd { float A, B, D; };
+
+__device__ __forceinline__ Abd dev_window_abd(int lo, int hi, const float *S, int ns) {
+  const float *N = S, *X = S + ns, *XX = S + 2 * ns, *Y = S + 3 * ns, *XY = S + 4 * ns;
+  float tN, tX, tXX, tY, tXY;
+  if (lo < 0) {
+    tN = N[hi] + N[-lo];   tX = X[hi] - X[-lo];   tXX = XX[hi] + XX[-lo];
+    tY = Y[hi] + Y[-lo];   tXY = XY[hi] - XY[-lo];
+  } else {
+    tN = N[hi] - N[lo];    tX = X[hi] - X[lo];    tXX = XX[hi] - XX[lo];
+    tY = Y[hi] - Y[lo];    tXY = XY[hi] - XY[lo];
+  }
+  Abd r;
+  r.A = tY * tXX - tX * tXY;
+  r.B = tN * tXY - tX * tY;
+  r.D = tN * tXX - tX * tX;
+  return r;
+}
+
+// One pass: f (n values in smem) -> noise (n values in smem).  pass2 == false:
+// offset 140, no fixed window, result clamped at 0 (lib/psy.c:715).  pass2 ==
+// true: offset 0 and the fixed window minimum (lib/psy.c:720).
+__device__ __forceinline__ void dev_noise_pass(const PsyDev &P, const float *f, float *noise,
+                                               float offset, int fixed, float *S, int ns,
+                                               int tid, int nt) {
+  const int n = P.n;
+  float *aN = S, *aX = S + ns, *aXX = S + 2 * ns, *aY = S + 3 * ns, *aXY = S + 4 * ns;
+  // per-bin terms of the five sums (lib/psy.c:565-596)
+  for (int i = tid; i < n; i += nt) {
+    float y = f[i] + offset;
+    if (y < 1.f) y = 1.f;
+    float w = y * y;
+    if (i == 0) {
+      w = w * .5f;
+      aN[0] = w; aX[0] = w; aXX[0] = 0.f; aY[0] = w * y; aXY[0] = 0.f;
+    } else {
+      const float x = (float)i;
+      const float wx = w * x;
+      aN[i] = w; aX[i] = wx; aXX[i] = wx * x; aY[i] = w * y; aXY[i] = wx * y;
+    }
+  }
+  __syncthreads();
+  // the running sums are strictly sequential fp32 (order matters):
+  // five lanes, one array each
+  if (tid < 5) {
+    float4 *a = reinterpret_cast<float4 *>(S + tid * ns);
+    float t = 0.f;
+    float4 v = a[0];
+    for (int i = 0; i < (n >> 2); i++) {
+      float4 nx = v;
+      if (i + 1 < (n >> 2)) nx = a[i + 1];
+      t += v.x; v.x = t;
+      t += v.y; v.y = t;
+      t += v.z; v.z = t;
+      t += v.w; v.w = t;
+      a[i] = v;
+      v = nx;
+    }
+  }
+  __syncthreads();
+  // regression per bin (lib/psy.c:604-703); bins past first_extra reuse the last A,B,D
+  const int bfe = P.bark_first_extra;
+  const int ffe = P.fixed_first_extra;
+  for (int i = tid; i < n; i += nt) {
+    Abd cur; cur.A = 0.f; cur.B = 0.f; cur.D = 1.f;
+    if (bfe > 0) {
+      const int wb = i < bfe ? i : bfe - 1;
+      const int bk = __ldg(P.bark + wb);
+      cur = dev_window_abd(bk >> 16, bk & 0xffff, S, ns);
+    }
+    const float x = (float)i;
+    float R = (cur.A + x * cur.B) / cur.D;
+    if (R < 0.f) R = 0.f;
+    float v = R - offset;
+    if (fixed > 0) {
+      if (ffe > 0) {
+        const int wb = i < ffe ? i : ffe - 1;
+        const int hi = wb + fixed / 2, lo = hi - fixed;
+        cur = dev_window_abd(lo, hi, S, ns);
+      } else if (bfe > 0 && i < bfe) {
+        // no fixed window qualifies: A,B,D left by the bark loops' last bin
+        const int bk = __ldg(P.bark + (bfe - 1));
+        cur = dev_window_abd(bk >> 16, bk & 0xffff, S, ns);
+      }
+      const float R2 = (cur.A + x * cur.B) / cur.D;
+      if (R2 - offset < v) v = R2 - offset;
+    }
+    noise[i] = v;
+  }
+  __syncthreads();
+}
+
+// _vp_noisemask (lib/psy.c:706-752): logmdct (smem) -> noise (smem).
+// work: n floats smem scratch.
+__device__ __forceinline__ void dev_noisemask(const PsyDev &P, const float *logmdct, float *noise,
+                                              float *work, float *S, int ns, int tid, int nt) {
+  const int n = P.n;
+  dev_noise_pass(P, logmdct, noise, 140.f, -1, S, ns, tid, nt);
+  for (int i = tid; i < n; i += nt) work[i] = logmdct[i] - noise[i];
+  __syncthreads();
+  dev_noise_pass(P, work, noise, 0.f, P.noisewindowfixed, S, ns, tid, nt);
+  for (int i = tid; i < n; i += nt) {
+    const float base = logmdct[i] - work[i];
+    int dB = (int)((double)noise[i] + .5);
+    if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
+    if (dB < 0) dB = 0;
+    noise[i] = base + __ldg(P.noisecompand + dB);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------
+// Tone mask: _vp_tonemask (lib/psy.c:754-777) with seed_loop/seed_curve
+// (:417-452, :390-415), seed_chase (:454-508) and max_seeds (:512-545).
+
+__device__ __forceinline__ int f2key(float f) {       // order-preserving float -> int
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key2f(int k) {
+  return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
+}
+
+// logfft: n floats smem (read), tone: n floats smem (written; may alias nothing),
+// seed: total ints/floats smem, pstk: total ints smem, astk: total floats smem.
+__device__ __forceinline__ void dev_tonemask(const PsyDev &P, const float *logfft, float *tone,
+                                             float gmax, float lmax, int *seedk, int *pstk,
+                                             float *astk, int tid, int nt) {
+  const int n = P.n, total = P.total, linesper = P.linesper;
+  float att = lmax + P.ath_adjatt;
+  if (att < P.ath_maxatt) att = P.ath_maxatt;
+  const float dBoffset = P.max_curve_dB - gmax;
+  const int negk = f2key(VB_NEGINF);
+  for (int i = tid; i < total; i += nt) seedk[i] = negk;
+  for (int i = tid; i < n; i += nt) tone[i] = __ldg(P.ath + i) + att;
+  __syncthreads();
+  // one item per run of equal octave[]: peak, gate, scatter-max of the chosen curve
+  for (int r = tid; r < P.nruns; r += nt) {
+    const int2 rr = __ldg(P.runs + r);
+    float mx = logfft[rr.x];
+    for (int i = rr.x + 1; i <= rr.y; i++) { const float v = logfft[i]; if (v > mx) mx = v; }
+    if (mx + 6.f > tone[rr.y]) {
+      const int ocv = __ldg(P.octave + rr.y);
+      int oc = ocv >> P.shiftoc;
+      if (oc >= VB200_P_BANDS) oc = VB200_P_BANDS - 1;
+      if (oc < 0) oc = 0;
+      int choice = (int)((((double)(mx + dBoffset)) - 30.) * (double).1f);
+      if (choice < 0) choice = 0;
+      if (choice > VB200_P_LEVELS - 1) choice = VB200_P_LEVELS - 1;
+      const float *posts = P.tonecurves + (oc * VB200_P_LEVELS + choice) * (VB200_EHMER_MAX + 2);
+      const float *curve = posts + 2;
+      const int post0 = (int)__ldg(posts), post1 = (int)__ldg(posts + 1);
+      int seedptr = (ocv - P.firstoc) + (post0 - 16) * linesper - (linesper >> 1);
+      for (int i = post0; i < post1; i++) {
+        if (seedptr > 0) {
+          const float lin = mx + __ldg(curve + i);
+          atomicMax(seedk + seedptr, f2key(lin));
+        }
+        seedptr += linesper;
+        if (seedptr >= total) break;
+      }
+    }
+  }
+  __syncthreads();
+  float *seed = reinterpret_cast<float *>(seedk);
+  for (int i = tid; i < total; i += nt) seed[i] = key2f(seedk[i]);
+  __syncthreads();
+  // seed_chase: literal emulation of the stack algorithm, one lane
+  if (tid == 0) {
+    int stack = 0;
+    for (int i = 0; i < total; i++) {
+      const float s = seed[i];
+      if (stack >= 2) {
+        while (!(s < astk[stack - 1]) && i < pstk[stack - 1] + linesper && stack > 1 &&
+               astk[stack - 1] <= astk[stack - 2] && i < pstk[stack - 2] + linesper)
+          stack--;
+      }
+      pstk[stack] = i;
+      astk[stack++] = s;
+    }
+    int pos = 0;
+    for (int i = 0; i < stack; i++) {
+      int endpos;
+      if (i < stack - 1 && astk[i + 1] > astk[i]) endpos = pstk[i + 1];
+      else endpos = pstk[i] + linesper + 1;
+      if (endpos > total) endpos = total;
+      const float a = astk[i];
+      for (; pos < endpos; pos++) seed[pos] = a;
+    }
+  }
+  __syncthreads();
+  // max_seeds gather: one item per (static) group
+  for (int g = tid; g < P.ngrp; g += nt) {
+    const int4 gg = __ldg(P.grps + g);
+    int pos = gg.x;
+    float minV = seed[pos];
+    if (minV > P.tone_abs_limit) minV = P.tone_abs_limit;
+    while (pos < gg.y) {
+      pos++;
+      const float s = seed[pos];
+      if ((s > VB_NEGINF && s < minV) || minV == VB_NEGINF) minV = s;
+    }
+    for (int i = gg.z; i < gg.w; i++)
+      if (tone[i] < minV) tone[i] = minV;
+  }
+  {
+    const float minV = seed[total - 1];
+    for (int i = P.tail_lin0 + tid; i < n; i += nt)
+      if (tone[i] < minV) tone[i] = minV;
+  }
+  __syncthreads();
+}
+
+// _vp_offset_and_mix for one bin (lib/psy.c:779-835); returns logmask, scales m.
+__device__ __forceinline__ float dev_mix_bin(const PsyDev &P, int sel, float noise, float tone,
+                                             float noff, float logmdct, float &m) {
+  float val = noise + noff;
+  if (val > P.noisemaxsupp) val = P.noisemaxsupp;
+  const float t = tone + P.tone_masteratt[sel];
+  const float logmask = val < t ? t : val;
+  if (sel == 1) {
+    const float coeffi = -17.2f;
+    float de;
+    val = val - logmdct;
+    if (val > coeffi) {
+      de = (float)(1.0 - ((double)(val - coeffi) * 0.005 * (double)P.m_val));
+      if (de < 0.f) de = 0.0001f;
+    } else {
+      de = (float)(1.0 - ((double)(val - coeffi) * 0.0003 * (double)P.m_val));
+    }
+    m *= de;
+  }
+  return logmask;
+}
+
+}  // namespace vb200

@@ -1,0 +1,273 @@
+"""ctypes binding of the product library libvorbis_b200.so (C ABI: include/vorbis_b200.h).
+
+This module is plumbing for tests and bench.py: it only marshals numpy arrays / raw
+device pointers into the C entry points.  There is NO CPU fallback: if the CUDA
+library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvorbis_b200.so")
+
+EXPORTS = [
+    "vb200_ctx_create", "vb200_ctx_destroy", "vb200_device_count", "vb200_last_error",
+    "vb200_ctx_table", "vb200_launch_count", "vb200_set_profiling", "vb200_phaseA_kernel_ms",
+    "vb200_mdct_forward_dev", "vb200_mdct_forward", "vb200_mdct_backward_dev", "vb200_mdct_backward",
+    "vb200_apply_window", "vb200_drft_forward",
+    "vb200_noisemask", "vb200_tonemask", "vb200_offset_and_mix",
+    "vb200_analysis_phaseA_dev", "vb200_analysis_phaseA", "vb200_analysis_phaseA_streams_dev",
+    "vb200_couple_quantize_normalize_dev", "vb200_couple_quantize_normalize",
+    "vb200_synthesis_dev", "vb200_synthesis",
+    "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
+]
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+vp = C.c_void_p
+
+
+class VB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libvorbis_b200.so; raises if it has not been built (run __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VB200Error("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                         % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.vb200_last_error.restype = C.c_char_p
+    L.vb200_launch_count.restype = C.c_uint64
+    L.vb200_launch_count.argtypes = [vp]
+    L.vb200_set_profiling.argtypes = [vp, C.c_int]
+    L.vb200_phaseA_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    L.vb200_ctx_create.argtypes = [C.POINTER(abi.Setup), C.c_int, C.POINTER(vp)]
+    L.vb200_ctx_destroy.argtypes = [vp]
+    L.vb200_ctx_table.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
+    L.vb200_mdct_forward_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.vb200_mdct_backward_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.vb200_mdct_forward.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.vb200_mdct_backward.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.vb200_apply_window.argtypes = [vp, C.c_int, C.c_int, vp, vp, f32p]
+    L.vb200_drft_forward.argtypes = [vp, C.c_int, C.c_int, f32p]
+    L.vb200_noisemask.argtypes = [vp, C.c_int, C.c_int, f32p, f32p]
+    L.vb200_tonemask.argtypes = [vp, C.c_int, C.c_int, f32p, f32p, f32p, f32p]
+    L.vb200_offset_and_mix.argtypes = [vp, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p]
+    L.vb200_analysis_phaseA_dev.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.PhaseAIO), vp]
+    L.vb200_analysis_phaseA.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.PhaseAIO)]
+    L.vb200_analysis_phaseA_streams_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(abi.PhaseAIO), vp, vp]
+    L.vb200_couple_quantize_normalize_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.vb200_couple_quantize_normalize.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.vb200_synthesis_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int64, vp]
+    L.vb200_synthesis.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, C.c_int64]
+    L.vb200_malloc_device.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.vb200_free_device.argtypes = [vp, vp]
+    L.vb200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.vb200_memcpy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.vb200_synchronize.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """numpy array / int (device pointer) / None -> c_void_p value"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)
+
+
+class Context:
+    """One vb200_ctx: device tables for a (channels, rate, quality) setup on one GPU."""
+
+    def __init__(self, setup, device=0):
+        self.L = load()
+        self.setup = setup
+        self.channels = setup.channels
+        self.bs = [setup.blocksize(0), setup.blocksize(1)]
+        h = vp()
+        self._chk(self.L.vb200_ctx_create(C.byref(setup.c), device, C.byref(h)))
+        self.h = h
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise VB200Error("vb200 error %d: %s" % (rc, (self.L.vb200_last_error() or b"").decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.vb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return int(self.L.vb200_launch_count(self.h))
+
+    def set_profiling(self, on=True):
+        self._chk(self.L.vb200_set_profiling(self.h, 1 if on else 0))
+
+    def phaseA_kernel_ms(self):
+        ms = (C.c_float * 3)()
+        self._chk(self.L.vb200_phaseA_kernel_ms(self.h, C.byref(ms)))
+        return [float(x) for x in ms]
+
+    def table(self, W, which):
+        N = self.bs[W]
+        out = np.zeros(N // 4, np.int32) if which == 1 else np.zeros(2 * N, np.float32)
+        k = self.L.vb200_ctx_table(self.h, W, which, out.ctypes.data, out.size)
+        if k <= 0:
+            raise VB200Error("vb200_ctx_table failed")
+        return out[:k].copy()
+
+    # ---- transforms: host buffers -------------------------------------------
+    def mdct_forward(self, W, x):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.bs[W])
+        out = np.empty((x.shape[0], self.bs[W] // 2), np.float32)
+        self._chk(self.L.vb200_mdct_forward(self.h, W, x.shape[0], _ptr(x), _ptr(out)))
+        return out
+
+    def mdct_backward(self, W, x):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.bs[W] // 2)
+        out = np.empty((x.shape[0], self.bs[W]), np.float32)
+        self._chk(self.L.vb200_mdct_backward(self.h, W, x.shape[0], _ptr(x), _ptr(out)))
+        return out
+
+    def apply_window(self, W, x, lW=None, nW=None):
+        x = np.array(x, np.float32).reshape(-1, self.bs[W])
+        lWa = None if lW is None else np.ascontiguousarray(lW, np.int32)
+        nWa = None if nW is None else np.ascontiguousarray(nW, np.int32)
+        self._chk(self.L.vb200_apply_window(self.h, W, x.shape[0], _ptr(lWa), _ptr(nWa), x))
+        return x
+
+    def drft_forward(self, W, x):
+        x = np.array(x, np.float32).reshape(-1, self.bs[W])
+        self._chk(self.L.vb200_drft_forward(self.h, W, x.shape[0], x))
+        return x
+
+    # ---- transforms: device pointers ----------------------------------------
+    def mdct_forward_dev(self, W, nvec, d_in, d_out, stream=None):
+        self._chk(self.L.vb200_mdct_forward_dev(self.h, W, nvec, _ptr(d_in), _ptr(d_out), _ptr(stream)))
+
+    def mdct_backward_dev(self, W, nvec, d_in, d_out, stream=None):
+        self._chk(self.L.vb200_mdct_backward_dev(self.h, W, nvec, _ptr(d_in), _ptr(d_out), _ptr(stream)))
+
+    # ---- psy stages -----------------------------------------------------------
+    def noisemask(self, look, logmdct):
+        x = np.ascontiguousarray(logmdct, np.float32)
+        x = x.reshape(-1, x.shape[-1])
+        out = np.empty_like(x)
+        self._chk(self.L.vb200_noisemask(self.h, look, x.shape[0], x, out))
+        return out
+
+    def tonemask(self, look, logfft, gmax, lmax):
+        x = np.ascontiguousarray(logfft, np.float32)
+        x = x.reshape(-1, x.shape[-1])
+        out = np.empty_like(x)
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(gmax, np.float32), (x.shape[0],)))
+        l = np.ascontiguousarray(np.broadcast_to(np.asarray(lmax, np.float32), (x.shape[0],)))
+        self._chk(self.L.vb200_tonemask(self.h, look, x.shape[0], x, g, l, out))
+        return out
+
+    def offset_and_mix(self, look, sel, noise, tone, mdct, logmdct):
+        noise = np.ascontiguousarray(noise, np.float32)
+        noise = noise.reshape(-1, noise.shape[-1])
+        tone = np.ascontiguousarray(tone, np.float32).reshape(noise.shape)
+        mdct = np.array(mdct, np.float32).reshape(noise.shape)
+        logmdct = np.ascontiguousarray(logmdct, np.float32).reshape(noise.shape)
+        logmask = np.empty_like(noise)
+        self._chk(self.L.vb200_offset_and_mix(self.h, look, noise.shape[0], sel, noise, tone, mdct,
+                                              logmdct, logmask))
+        return logmask, mdct
+
+    # ---- Phase A ---------------------------------------------------------------
+    def phaseA(self, W, pcm, desc, taps=False):
+        ch, N = self.channels, self.bs[W]
+        pcm = np.ascontiguousarray(pcm, np.float32).reshape(-1, ch, N)
+        nb = pcm.shape[0]
+        desc = np.ascontiguousarray(desc, abi.BLOCKDESC_DTYPE)
+        out = {k: np.empty((nb, ch, N // 2), np.float32) for k in ("mdct", "logmdct", "logmask")}
+        out["ampmax_out"] = np.empty(nb, np.float32)
+        io = abi.PhaseAIO()
+        io.pcm, io.desc = pcm.ctypes.data, desc.ctypes.data
+        io.mdct, io.logmdct, io.logmask = (out[k].ctypes.data for k in ("mdct", "logmdct", "logmask"))
+        io.ampmax_out = out["ampmax_out"].ctypes.data
+        if taps:
+            for k in ("noise", "tone", "logfft", "mdct_raw"):
+                out[k] = np.empty((nb, ch, N // 2), np.float32)
+                setattr(io, "tap_" + k, out[k].ctypes.data)
+        self._chk(self.L.vb200_analysis_phaseA(self.h, W, nb, C.byref(io)))
+        return out
+
+    def phaseA_dev(self, W, nblocks, io, stream=None, streams=None, d_ampmax0=None):
+        """io: abi.PhaseAIO holding DEVICE pointers."""
+        if streams is None:
+            self._chk(self.L.vb200_analysis_phaseA_dev(self.h, W, nblocks, C.byref(io), _ptr(stream)))
+        else:
+            self._chk(self.L.vb200_analysis_phaseA_streams_dev(self.h, W, streams[0], streams[1], C.byref(io),
+                                                               _ptr(d_ampmax0), _ptr(stream)))
+
+    # ---- Phase B ---------------------------------------------------------------
+    def couple_quantize_normalize(self, W, blocktype, blobno, mdct, iwork, nonzero):
+        mdct = np.ascontiguousarray(mdct, np.float32)
+        iwork = np.array(iwork, np.int32)
+        nonzero = np.array(nonzero, np.int32)
+        self._chk(self.L.vb200_couple_quantize_normalize(self.h, W, blocktype, blobno, mdct.shape[0],
+                                                         _ptr(mdct), _ptr(iwork), _ptr(nonzero)))
+        return iwork, nonzero
+
+    def couple_quantize_normalize_dev(self, W, blocktype, blobno, nblocks, d_mdct, d_iwork, d_nonzero, stream=None):
+        self._chk(self.L.vb200_couple_quantize_normalize_dev(self.h, W, blocktype, blobno, nblocks,
+                                                             _ptr(d_mdct), _ptr(d_iwork), _ptr(d_nonzero),
+                                                             _ptr(stream)))
+
+    # ---- decode ------------------------------------------------------------------
+    def synthesis(self, Wseq, coef_off, coef, pcm_off, pcm_stride):
+        Wseq = np.ascontiguousarray(Wseq, np.int32)
+        ns, nblk = Wseq.shape
+        coef_off = np.ascontiguousarray(coef_off, np.int64)
+        pcm_off = np.ascontiguousarray(pcm_off, np.int64)
+        coef = np.ascontiguousarray(coef, np.float32)
+        pcm = np.zeros((ns, self.channels, pcm_stride), np.float32)
+        self._chk(self.L.vb200_synthesis(self.h, ns, nblk, _ptr(Wseq), _ptr(coef_off), _ptr(coef), coef.size,
+                                         _ptr(pcm_off), _ptr(pcm), pcm_stride))
+        return pcm
+
+    def synthesis_dev(self, nstreams, nblk, d_Wseq, d_coef_off, d_coef, d_pcm_off, d_pcm, pcm_stride, stream=None):
+        self._chk(self.L.vb200_synthesis_dev(self.h, nstreams, nblk, _ptr(d_Wseq), _ptr(d_coef_off), _ptr(d_coef),
+                                             _ptr(d_pcm_off), _ptr(d_pcm), pcm_stride, _ptr(stream)))
+
+
+def synthesis_layout(Wseq, bs, channels):
+    """Offsets for vb200_synthesis: Wseq [nstreams][nblk] -> (coef_off, pcm_off, coef_len, pcm_len)
+    with every stream's spectra packed back to back (block-major, channel-minor)."""
+    Wseq = np.asarray(Wseq, np.int32)
+    ns, nblk = Wseq.shape
+    N = np.where(Wseq == 1, bs[1], bs[0]).astype(np.int64)
+    per_block = channels * (N // 2)
+    coef_off = np.zeros((ns, nblk), np.int64)
+    flat = per_block.reshape(-1)
+    coef_off.reshape(-1)[1:] = np.cumsum(flat)[:-1]
+    fin = np.zeros((ns, nblk), np.int64)
+    fin[:, 1:] = N[:, :-1] // 4 + N[:, 1:] // 4
+    pcm_off = np.cumsum(fin, axis=1) - fin      # finished samples before block k's contribution
+    # block k's finished samples start where block k-1's ended
+    pcm_off = np.concatenate([np.zeros((ns, 1), np.int64), np.cumsum(fin, axis=1)[:, :-1]], axis=1)
+    pcm_len = int(np.cumsum(fin, axis=1)[:, -1].max())
+    return coef_off, pcm_off, int(flat.sum()), pcm_len
