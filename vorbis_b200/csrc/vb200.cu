@@ -56,6 +56,7 @@ struct vb200_ctx {
   std::atomic<uint64_t> launches{0};
   // grow-only scratch for the host-buffer entry points and phase A intermediates
   DevBuf scratch[16];
+  int psy_ctas_per_sm = 4;
   cudaStream_t s_main = nullptr;
   std::mutex mu;
   // optional per-kernel timing of the last Phase-A call (bench roofline evidence)
@@ -159,13 +160,18 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
                      &d.tonecurves))) return rc;
     if ((rc = upload(c, p.noiseoffset, (size_t)VB200_P_NOISECURVES * p.n, &d.noiseoffset))) return rc;
     if ((rc = upload(c, p.noisecompand, (size_t)VB200_COMPAND_LEVELS, &d.noisecompand))) return rc;
-    std::vector<int> runs;
-    for (size_t r = 0; r < f.run_lo.size(); r++) { runs.push_back(f.run_lo[r]); runs.push_back(f.run_hi[r]); }
-    const int *dr = nullptr, *dg = nullptr;
-    if ((rc = upload(c, runs.data(), runs.size(), &dr))) return rc;
+    if ((1 << f.linesper_log2) != p.eighth_octave_lines)
+      return fail(VB200_EIMPL, "eighth_octave_lines must be a power of two (lib/psy.h:108)");
+    const int *dr = nullptr, *dg = nullptr, *dc = nullptr, *ds = nullptr;
+    if ((rc = upload(c, f.runinfo.data(), f.runinfo.size(), &dr))) return rc;
     if ((rc = upload(c, f.grp.data(), f.grp.size(), &dg))) return rc;
-    d.runs = reinterpret_cast<const int2 *>(dr);
+    if ((rc = upload(c, f.cls_run.data(), f.cls_run.size(), &dc))) return rc;
+    if ((rc = upload(c, f.slot_rng.data(), f.slot_rng.size(), &ds))) return rc;
+    d.runinfo = reinterpret_cast<const int4 *>(dr);
     d.grps = reinterpret_cast<const int4 *>(dg);
+    d.cls_run = reinterpret_cast<const int2 *>(dc);
+    d.slot_rng = reinterpret_cast<const int2 *>(ds);
+    d.linesper_log2 = f.linesper_log2;
   }
   *out = c;
   return 0;
@@ -372,40 +378,67 @@ struct PhaseA2Args {
   float *tap_noise, *tap_tone;
 };
 
-__global__ void __launch_bounds__(256)
+// shared-memory carve-up for the psy kernels (floats)
+struct PsySmem {
+  float *logmdct, *work, *noise, *scan, *fft;
+  ToneSmem T;
+};
+__host__ __device__ inline size_t psy_smem_floats(int n, int total, int nruns) {
+  const int tp = (total + 3) & ~3, rp = (nruns + 3) & ~3;
+  return (size_t)4 * n + 5 * (size_t)(n + 4) + 3 * (size_t)tp + 3 * (size_t)rp;
+}
+__device__ __forceinline__ PsySmem psy_carve(float *sm, int n, int total, int nruns) {
+  const int tp = (total + 3) & ~3, rp = (nruns + 3) & ~3;
+  PsySmem s;
+  s.logmdct = sm; s.work = s.logmdct + n; s.noise = s.work + n; s.scan = s.noise + n;
+  s.fft = s.scan + 5 * (n + 4);
+  s.T.seed = s.fft + n;
+  s.T.pstk = reinterpret_cast<int *>(s.T.seed + tp);
+  s.T.astk = reinterpret_cast<float *>(s.T.pstk + tp);
+  s.T.run_mx = s.T.astk + tp;
+  s.T.run_cofs = reinterpret_cast<int *>(s.T.run_mx + rp);
+  s.T.run_p01 = s.T.run_cofs + rp;
+  return s;
+}
+
+#define PSY_THREADS 128
+__global__ void __launch_bounds__(PSY_THREADS)
 k_phaseA_psy(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
   extern __shared__ __align__(16) float sm[];
-  const int n = P0.n, ns = n + 4, tid = threadIdx.x, nt = blockDim.x;
+  const int n = P0.n, ns = n + 4, tid = threadIdx.x, nt = PSY_THREADS;
   const int total = P0.total > P1.total ? P0.total : P1.total;
-  float *s_logmdct = sm;
-  float *s_work = s_logmdct + n;
-  float *s_noise = s_work + n;
-  float *s_scan = s_noise + n;             // 5*ns
-  float *s_fft = s_scan + 5 * ns;          // logfft
-  float *s_tone = s_fft + n;
-  int   *s_seed = reinterpret_cast<int *>(s_tone + n);
-  int   *s_pstk = s_seed + total;
-  float *s_astk = reinterpret_cast<float *>(s_pstk + total);
+  const int nruns = P0.nruns > P1.nruns ? P0.nruns : P1.nruns;
+  const PsySmem S = psy_carve(sm, n, total, nruns);
+  const int warp = tid >> 5, lane = tid & 31;
   for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
     const int blk = row / ch;
     const PsyDev &P = A.desc[blk].blocktype ? P1 : P0;
     const float *gm = A.mdct_in + (size_t)row * n;
     const float *lf = A.logfft + (size_t)row * n;
+    const float g = A.gmax[blk], lmax = A.lmax[row];
     for (int i = tid; i < n; i += nt) {
       const float l = add345(todB_dev(gm[i]));          // lib/mapping0.c:384-385
-      s_logmdct[i] = l;
+      S.logmdct[i] = l;
       A.logmdct[(size_t)row * n + i] = l;
-      s_fft[i] = lf[i];
+      S.fft[i] = lf[i];
     }
     __syncthreads();
-    dev_noisemask(P, s_logmdct, s_noise, s_work, s_scan, ns, tid, nt);
-    const float g = A.gmax[blk];
-    dev_tonemask(P, s_fft, s_tone, g, A.lmax[row], s_seed, s_pstk, s_astk, tid, nt);
+    // all warps: run peaks / curve choice, and the first pass' per-bin sum terms
+    dev_tone_runs(P, S.fft, g, lmax, S.T, tid, nt);
+    dev_noise_terms(n, S.logmdct, 140.f, S.scan, ns, tid, nt);
+    __syncthreads();
+    dev_tone_slots(P, S.T, tid, nt);
+    __syncthreads();
+    // warp 0: the sequential seed_chase + gather; warps 1-3: the noise mask (two sequential
+    // prefix-sum passes on five lanes + regressions).  The two chains are independent.
+    if (warp == 0) dev_tone_chase_gather(P, S.fft, lmax, S.T, lane);
+    else dev_noisemask(P, S.logmdct, S.noise, S.work, S.scan, ns, tid - 32, nt - 32, 1, true);
+    __syncthreads();
     const float *noff = P.noiseoffset + n;               // offset_select 1
     for (int i = tid; i < n; i += nt) {
       float m = gm[i];
-      const float nz = s_noise[i], tn = s_tone[i];
-      const float lm = dev_mix_bin(P, 1, nz, tn, __ldg(noff + i), s_logmdct[i], m);
+      const float nz = S.noise[i], tn = S.fft[i];
+      const float lm = dev_mix_bin(P, 1, nz, tn, __ldg(noff + i), S.logmdct[i], m);
       A.logmask[(size_t)row * n + i] = lm;
       A.mdct_out[(size_t)row * n + i] = m;
       if (A.tap_noise) A.tap_noise[(size_t)row * n + i] = nz;
@@ -417,34 +450,36 @@ k_phaseA_psy(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
 }
 
 // ---- stage-isolated psy kernels (parity tests feed them the oracle's upstream vectors)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PSY_THREADS)
 k_noisemask(PsyDev P, int nvec, const float *__restrict__ logmdct, float *__restrict__ noise) {
   extern __shared__ __align__(16) float sm[];
-  const int n = P.n, ns = n + 4, tid = threadIdx.x, nt = blockDim.x;
-  float *s_l = sm, *s_w = sm + n, *s_n = sm + 2 * n, *s_s = sm + 3 * n;
+  const int n = P.n, ns = n + 4, tid = threadIdx.x, nt = PSY_THREADS;
+  const PsySmem S = psy_carve(sm, n, P.total, P.nruns);
   for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
-    for (int i = tid; i < n; i += nt) s_l[i] = logmdct[(size_t)v * n + i];
+    for (int i = tid; i < n; i += nt) S.logmdct[i] = logmdct[(size_t)v * n + i];
     __syncthreads();
-    dev_noisemask(P, s_l, s_n, s_w, s_s, ns, tid, nt);
-    for (int i = tid; i < n; i += nt) noise[(size_t)v * n + i] = s_n[i];
+    dev_noisemask(P, S.logmdct, S.noise, S.work, S.scan, ns, tid, nt, 0, false);
+    for (int i = tid; i < n; i += nt) noise[(size_t)v * n + i] = S.noise[i];
     __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PSY_THREADS)
 k_tonemask(PsyDev P, int nvec, const float *__restrict__ logfft, const float *__restrict__ gmax,
            const float *__restrict__ lmax, float *__restrict__ tone) {
   extern __shared__ __align__(16) float sm[];
-  const int n = P.n, tid = threadIdx.x, nt = blockDim.x;
-  float *s_f = sm, *s_t = sm + n;
-  int *s_seed = reinterpret_cast<int *>(sm + 2 * n);
-  int *s_p = s_seed + P.total;
-  float *s_a = reinterpret_cast<float *>(s_p + P.total);
+  const int n = P.n, tid = threadIdx.x, nt = PSY_THREADS;
+  const PsySmem S = psy_carve(sm, n, P.total, P.nruns);
   for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
-    for (int i = tid; i < n; i += nt) s_f[i] = logfft[(size_t)v * n + i];
+    for (int i = tid; i < n; i += nt) S.fft[i] = logfft[(size_t)v * n + i];
     __syncthreads();
-    dev_tonemask(P, s_f, s_t, gmax[v], lmax[v], s_seed, s_p, s_a, tid, nt);
-    for (int i = tid; i < n; i += nt) tone[(size_t)v * n + i] = s_t[i];
+    dev_tone_runs(P, S.fft, gmax[v], lmax[v], S.T, tid, nt);
+    __syncthreads();
+    dev_tone_slots(P, S.T, tid, nt);
+    __syncthreads();
+    if (tid < 32) dev_tone_chase_gather(P, S.fft, lmax[v], S.T, tid);
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) tone[(size_t)v * n + i] = S.fft[i];
     __syncthreads();
   }
 }
@@ -598,8 +633,9 @@ extern "C" int vb200_drft_forward(vb200_ctx *c, int W, int nvec, float *data) {
 // ======================================================================== //
 // stage-isolated psy entry points
 static size_t psy2_smem(const PsyDev &a, const PsyDev &b) {
-  const int n = a.n, total = a.total > b.total ? a.total : b.total;
-  return sizeof(float) * ((size_t)5 * n + 5 * (n + 4) + 3 * (size_t)total) + 64;
+  const int total = a.total > b.total ? a.total : b.total;
+  const int nruns = a.nruns > b.nruns ? a.nruns : b.nruns;
+  return sizeof(float) * psy_smem_floats(a.n, total, nruns);
 }
 
 #define CHECK_LOOK(c, look) do { if ((look) < 0 || (look) >= (c)->n_psy) return fail(VB200_EINVAL, "no such psy look"); } while (0)
@@ -614,9 +650,9 @@ extern "C" int vb200_noisemask(vb200_ctx *c, int look, int nvec, const float *lo
   const size_t bytes = sizeof(float) * (size_t)nvec * P.n;
   if ((rc = io.h2d(logmdct, bytes, &di))) return rc;
   if ((rc = io.h2d(nullptr, bytes, &dout))) return rc;
-  const size_t smem = sizeof(float) * ((size_t)3 * P.n + 5 * (P.n + 4));
+  const size_t smem = psy2_smem(P, P);
   if ((rc = set_smem(k_noisemask, smem))) return rc;
-  k_noisemask<<<grid_for(c, nvec, 4), 256, smem, c->s_main>>>(P, nvec, (const float *)di, (float *)dout);
+  k_noisemask<<<grid_for(c, nvec, 4), PSY_THREADS, smem, c->s_main>>>(P, nvec, (const float *)di, (float *)dout);
   if ((rc = post_launch(c))) return rc;
   if ((rc = io.d2h(noise, dout, bytes))) return rc;
   return io.sync();
@@ -635,9 +671,9 @@ extern "C" int vb200_tonemask(vb200_ctx *c, int look, int nvec, const float *log
   if ((rc = io.h2d(gmax, sizeof(float) * nvec, &dg))) return rc;
   if ((rc = io.h2d(lmax, sizeof(float) * nvec, &dl))) return rc;
   if ((rc = io.h2d(nullptr, bytes, &dout))) return rc;
-  const size_t smem = sizeof(float) * ((size_t)2 * P.n + 3 * (size_t)P.total);
+  const size_t smem = psy2_smem(P, P);
   if ((rc = set_smem(k_tonemask, smem))) return rc;
-  k_tonemask<<<grid_for(c, nvec, 4), 256, smem, c->s_main>>>(P, nvec, (const float *)di, (const float *)dg,
+  k_tonemask<<<grid_for(c, nvec, 4), PSY_THREADS, smem, c->s_main>>>(P, nvec, (const float *)di, (const float *)dg,
                                                              (const float *)dl, (float *)dout);
   if ((rc = post_launch(c))) return rc;
   if ((rc = io.d2h(tone, dout, bytes))) return rc;
@@ -705,7 +741,7 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
     A.logfft = d_logfft; A.lmax = d_lmax; A.gmax = d_gmax; A.desc = io->desc;
     A.mdct_out = io->mdct; A.logmdct = io->logmdct; A.logmask = io->logmask; A.ampmax_out = io->ampmax_out;
     A.tap_noise = io->tap_noise; A.tap_tone = io->tap_tone;
-    k_phaseA_psy<<<grid_for(c, rows, 4), 256, smem, st>>>(P0, P1, ch, rows, A);
+    k_phaseA_psy<<<grid_for(c, rows, c->psy_ctas_per_sm), PSY_THREADS, smem, st>>>(P0, P1, ch, rows, A);
     rc = post_launch(c); if (rc) return rc;
   }
   if (c->profiling) CU(cudaEventRecord(c->ev[3], st));

@@ -51,8 +51,11 @@ struct PsyDev {
   const float *tonecurves;   // [17][8][58]
   const float *noiseoffset;  // [3][n]
   const float *noisecompand; // [40]
-  const int2  *runs;         // [nruns] (lo,hi)
+  const int4  *runinfo;      // [nruns] (lo, hi, octave[hi]-firstoc, band)
   const int4  *grps;         // [ngrp]  (pos0,pos1,lin0,lin1)
+  const int2  *cls_run;      // runs grouped by residue class, (run id, oc-firstoc), sorted by oc
+  const int2  *slot_rng;     // [total] candidate range in cls_run for every seed slot
+  int linesper_log2;
 };
 
 // ------------------------------------------------------------------------
@@ -448,6 +451,15 @@ __device__ __forceinline__ void dev_load_windowed(const WinDev &Wd, int W, int l
 // Noise mask: bark_noise_hybridmp (lib/psy.c:547-704).
 // S = 5 prefix arrays with row stride ns (ns = n+4 keeps the five sequential
 // lanes on different banks for 128-bit accesses).
+//
+// The psy device functions are written for a *group* of threads that may be a
+// subset of the CTA (warp specialisation): `tid`/`nt` are the rank and size of
+// the group and group_sync() is a named barrier over exactly those threads.
+
+__device__ __forceinline__ void group_sync(int barid, int nt) {
+  if (nt == 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" :: "r"(barid), "r"(nt) : "memory");
+}
 
 struct Abd { float A, B, D; };
 
@@ -468,15 +480,10 @@ __device__ __forceinline__ Abd dev_window_abd(int lo, int hi, const float *S, in
   return r;
 }
 
-// One pass: f (n values in smem) -> noise (n values in smem).  pass2 == false:
-// offset 140, no fixed window, result clamped at 0 (lib/psy.c:715).  pass2 ==
-// true: offset 0 and the fixed window minimum (lib/psy.c:720).
-__device__ __forceinline__ void dev_noise_pass(const PsyDev &P, const float *f, float *noise,
-                                               float offset, int fixed, float *S, int ns,
-                                               int tid, int nt) {
-  const int n = P.n;
+// per-bin terms of the five running sums (lib/psy.c:565-596)
+__device__ __forceinline__ void dev_noise_terms(int n, const float *f, float offset, float *S, int ns,
+                                                int tid, int nt) {
   float *aN = S, *aX = S + ns, *aXX = S + 2 * ns, *aY = S + 3 * ns, *aXY = S + 4 * ns;
-  // per-bin terms of the five sums (lib/psy.c:565-596)
   for (int i = tid; i < n; i += nt) {
     float y = f[i] + offset;
     if (y < 1.f) y = 1.f;
@@ -490,26 +497,32 @@ __device__ __forceinline__ void dev_noise_pass(const PsyDev &P, const float *f, 
       aN[i] = w; aX[i] = wx; aXX[i] = wx * x; aY[i] = w * y; aXY[i] = wx * y;
     }
   }
-  __syncthreads();
-  // the running sums are strictly sequential fp32 (order matters):
-  // five lanes, one array each
-  if (tid < 5) {
-    float4 *a = reinterpret_cast<float4 *>(S + tid * ns);
-    float t = 0.f;
-    float4 v = a[0];
-    for (int i = 0; i < (n >> 2); i++) {
-      float4 nx = v;
-      if (i + 1 < (n >> 2)) nx = a[i + 1];
-      t += v.x; v.x = t;
-      t += v.y; v.y = t;
-      t += v.z; v.z = t;
-      t += v.w; v.w = t;
-      a[i] = v;
-      v = nx;
-    }
+}
+
+// The running sums are strictly sequential fp32 (order matters):
+// five lanes, one array each, 16 values in flight per lane so that only the
+// 4-cycle add chain is on the critical path.
+__device__ __forceinline__ void dev_noise_scan(int n, float *S, int ns, int lane) {
+  if (lane >= 5) return;
+  float4 *a = reinterpret_cast<float4 *>(S + lane * ns);
+  const int q = n >> 2;                   // float4 count (n is a multiple of 32)
+  float t = 0.f;
+  float4 v0 = a[0], v1 = a[1], v2 = a[2], v3 = a[3];
+  for (int i = 0; i < q; i += 4) {
+    float4 w0 = v0, w1 = v1, w2 = v2, w3 = v3;
+    if (i + 4 < q) { v0 = a[i + 4]; v1 = a[i + 5]; v2 = a[i + 6]; v3 = a[i + 7]; }
+    t += w0.x; w0.x = t; t += w0.y; w0.y = t; t += w0.z; w0.z = t; t += w0.w; w0.w = t;
+    t += w1.x; w1.x = t; t += w1.y; w1.y = t; t += w1.z; w1.z = t; t += w1.w; w1.w = t;
+    t += w2.x; w2.x = t; t += w2.y; w2.y = t; t += w2.z; w2.z = t; t += w2.w; w2.w = t;
+    t += w3.x; w3.x = t; t += w3.y; w3.y = t; t += w3.z; w3.z = t; t += w3.w; w3.w = t;
+    a[i] = w0; a[i + 1] = w1; a[i + 2] = w2; a[i + 3] = w3;
   }
-  __syncthreads();
-  // regression per bin (lib/psy.c:604-703); bins past first_extra reuse the last A,B,D
+}
+
+// regression per bin (lib/psy.c:604-703); bins past first_extra reuse the last A,B,D
+__device__ __forceinline__ void dev_noise_regress(const PsyDev &P, float *noise, float offset, int fixed,
+                                                  const float *S, int ns, int tid, int nt) {
+  const int n = P.n;
   const int bfe = P.bark_first_extra;
   const int ffe = P.fixed_first_extra;
   for (int i = tid; i < n; i += nt) {
@@ -538,18 +551,27 @@ __device__ __forceinline__ void dev_noise_pass(const PsyDev &P, const float *f, 
     }
     noise[i] = v;
   }
-  __syncthreads();
 }
 
-// _vp_noisemask (lib/psy.c:706-752): logmdct (smem) -> noise (smem).
-// work: n floats smem scratch.
+// _vp_noisemask (lib/psy.c:706-752): logmdct (smem) -> noise (smem); work: n floats.
+// If terms_done, the pass-1 terms were already written to S by the caller.
 __device__ __forceinline__ void dev_noisemask(const PsyDev &P, const float *logmdct, float *noise,
-                                              float *work, float *S, int ns, int tid, int nt) {
+                                              float *work, float *S, int ns, int tid, int nt,
+                                              int barid, bool terms_done) {
   const int n = P.n;
-  dev_noise_pass(P, logmdct, noise, 140.f, -1, S, ns, tid, nt);
+  if (!terms_done) { dev_noise_terms(n, logmdct, 140.f, S, ns, tid, nt); group_sync(barid, nt); }
+  if (tid < 32) dev_noise_scan(n, S, ns, tid);
+  group_sync(barid, nt);
+  dev_noise_regress(P, noise, 140.f, -1, S, ns, tid, nt);
+  group_sync(barid, nt);
   for (int i = tid; i < n; i += nt) work[i] = logmdct[i] - noise[i];
-  __syncthreads();
-  dev_noise_pass(P, work, noise, 0.f, P.noisewindowfixed, S, ns, tid, nt);
+  group_sync(barid, nt);
+  dev_noise_terms(n, work, 0.f, S, ns, tid, nt);
+  group_sync(barid, nt);
+  if (tid < 32) dev_noise_scan(n, S, ns, tid);
+  group_sync(barid, nt);
+  dev_noise_regress(P, noise, 0.f, P.noisewindowfixed, S, ns, tid, nt);
+  group_sync(barid, nt);
   for (int i = tid; i < n; i += nt) {
     const float base = logmdct[i] - work[i];
     int dB = (int)((double)noise[i] + .5);
@@ -557,91 +579,133 @@ __device__ __forceinline__ void dev_noisemask(const PsyDev &P, const float *logm
     if (dB < 0) dB = 0;
     noise[i] = base + __ldg(P.noisecompand + dB);
   }
-  __syncthreads();
+  group_sync(barid, nt);
 }
 
 // ------------------------------------------------------------------------
 // Tone mask: _vp_tonemask (lib/psy.c:754-777) with seed_loop/seed_curve
 // (:417-452, :390-415), seed_chase (:454-508) and max_seeds (:512-545).
+//
+// seed_curve's scatter-max is evaluated owner-computes: a seed slot s can only
+// be written by runs r with (s - oc_r + linesper/2) divisible by linesper, and
+// only through curve point i = (s - oc_r + half)/linesper + 16.  The candidate
+// runs of every slot are a static contiguous range of a per-residue run list,
+// so each slot takes the max over its candidates: no atomics, and max is
+// order-independent so the result is bit-identical to the sequential scatter.
 
-__device__ __forceinline__ int f2key(float f) {       // order-preserving float -> int
-  const int i = __float_as_int(f);
-  return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float key2f(int k) {
-  return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff);
-}
+struct ToneSmem {
+  float *seed;      // [total]
+  int   *pstk;      // [total]
+  float *astk;      // [total]
+  float *run_mx;    // [nruns]
+  int   *run_cofs;  // [nruns] offset of the chosen curve in tonecurves
+  int   *run_p01;   // [nruns] post0 | post1<<16   (1000|1000<<16 = inactive)
+};
 
-// logfft: n floats smem (read), tone: n floats smem (written; may alias nothing),
-// seed: total ints/floats smem, pstk: total ints smem, astk: total floats smem.
-__device__ __forceinline__ void dev_tonemask(const PsyDev &P, const float *logfft, float *tone,
-                                             float gmax, float lmax, int *seedk, int *pstk,
-                                             float *astk, int tid, int nt) {
-  const int n = P.n, total = P.total, linesper = P.linesper;
+__device__ __forceinline__ float tone_att(const PsyDev &P, float lmax) {
   float att = lmax + P.ath_adjatt;
   if (att < P.ath_maxatt) att = P.ath_maxatt;
+  return att;
+}
+
+// seed_loop: one item per run of equal octave[] (peak, audibility gate, curve choice)
+__device__ __forceinline__ void dev_tone_runs(const PsyDev &P, const float *logfft, float gmax, float lmax,
+                                              const ToneSmem &T, int tid, int nt) {
+  const float att = tone_att(P, lmax);
   const float dBoffset = P.max_curve_dB - gmax;
-  const int negk = f2key(VB_NEGINF);
-  for (int i = tid; i < total; i += nt) seedk[i] = negk;
-  for (int i = tid; i < n; i += nt) tone[i] = __ldg(P.ath + i) + att;
-  __syncthreads();
-  // one item per run of equal octave[]: peak, gate, scatter-max of the chosen curve
   for (int r = tid; r < P.nruns; r += nt) {
-    const int2 rr = __ldg(P.runs + r);
-    float mx = logfft[rr.x];
-    for (int i = rr.x + 1; i <= rr.y; i++) { const float v = logfft[i]; if (v > mx) mx = v; }
-    if (mx + 6.f > tone[rr.y]) {
-      const int ocv = __ldg(P.octave + rr.y);
-      int oc = ocv >> P.shiftoc;
-      if (oc >= VB200_P_BANDS) oc = VB200_P_BANDS - 1;
-      if (oc < 0) oc = 0;
-      int choice = (int)((((double)(mx + dBoffset)) - 30.) * (double).1f);
+    const int4 ri = __ldg(P.runinfo + r);            // lo, hi, oc - firstoc, band
+    float mx = logfft[ri.x];
+    for (int i = ri.x + 1; i <= ri.y; i++) { const float v = logfft[i]; if (v > mx) mx = v; }
+    int p01 = 1000 | (1000 << 16), cofs = 0;
+    if (mx + 6.f > __ldg(P.ath + ri.y) + att) {
+      int choice = (int)((((double)(mx + dBoffset)) - 30.) * (double).1f);   // P_LEVEL_0 is a double
       if (choice < 0) choice = 0;
       if (choice > VB200_P_LEVELS - 1) choice = VB200_P_LEVELS - 1;
-      const float *posts = P.tonecurves + (oc * VB200_P_LEVELS + choice) * (VB200_EHMER_MAX + 2);
-      const float *curve = posts + 2;
-      const int post0 = (int)__ldg(posts), post1 = (int)__ldg(posts + 1);
-      int seedptr = (ocv - P.firstoc) + (post0 - 16) * linesper - (linesper >> 1);
-      for (int i = post0; i < post1; i++) {
-        if (seedptr > 0) {
-          const float lin = mx + __ldg(curve + i);
-          atomicMax(seedk + seedptr, f2key(lin));
-        }
-        seedptr += linesper;
-        if (seedptr >= total) break;
+      cofs = (ri.w * VB200_P_LEVELS + choice) * (VB200_EHMER_MAX + 2);
+      const int post0 = (int)__ldg(P.tonecurves + cofs), post1 = (int)__ldg(P.tonecurves + cofs + 1);
+      p01 = post0 | (post1 << 16);
+    }
+    T.run_mx[r] = mx; T.run_cofs[r] = cofs; T.run_p01[r] = p01;
+  }
+}
+
+// seed_curve, owner-computes: one item per seed slot
+__device__ __forceinline__ void dev_tone_slots(const PsyDev &P, const ToneSmem &T, int tid, int nt) {
+  const int half = P.linesper >> 1;
+  for (int s = tid; s < P.total; s += nt) {
+    float m = VB_NEGINF;
+    const int2 rg = __ldg(P.slot_rng + s);           // candidate range in cls_run (empty for s == 0)
+    for (int k = rg.x; k < rg.y; k++) {
+      const int2 cr = __ldg(P.cls_run + k);          // run id, oc - firstoc
+      const int i = ((s - cr.y + half) >> P.linesper_log2) + 16;
+      const int p01 = T.run_p01[cr.x];
+      if (i >= (p01 & 0xffff) && i < (p01 >> 16)) {
+        const float lin = T.run_mx[cr.x] + __ldg(P.tonecurves + T.run_cofs[cr.x] + 2 + i);
+        if (m < lin) m = lin;
       }
     }
+    T.seed[s] = m;
   }
-  __syncthreads();
-  float *seed = reinterpret_cast<float *>(seedk);
-  for (int i = tid; i < total; i += nt) seed[i] = key2f(seedk[i]);
-  __syncthreads();
-  // seed_chase: literal emulation of the stack algorithm, one lane
-  if (tid == 0) {
-    int stack = 0;
+}
+
+// seed_chase + max_seeds gather, executed by ONE warp (lane = 0..31).
+// tone: n floats (written).  The stack algorithm is emulated literally (its pop
+// rule is not a sliding maximum) by lane 0 with the two topmost
+// entries cached in registers; the fill and the gather are lane-parallel.
+__device__ __forceinline__ void dev_tone_chase_gather(const PsyDev &P, float *tone, float lmax,
+                                                      const ToneSmem &T, int lane) {
+  const int n = P.n, total = P.total, linesper = P.linesper;
+  float *seed = T.seed; int *pstk = T.pstk; float *astk = T.astk;
+  int stack = 0;
+  if (lane == 0) {
+    float a0 = 0.f, a1 = 0.f; int p0 = 0, p1 = 0;
     for (int i = 0; i < total; i++) {
       const float s = seed[i];
       if (stack >= 2) {
-        while (!(s < astk[stack - 1]) && i < pstk[stack - 1] + linesper && stack > 1 &&
-               astk[stack - 1] <= astk[stack - 2] && i < pstk[stack - 2] + linesper)
+        while (!(s < a0) && i < p0 + linesper && a0 <= a1 && i < p1 + linesper) {
           stack--;
+          a0 = a1; p0 = p1;
+          if (stack < 2) break;
+          a1 = astk[stack - 2]; p1 = pstk[stack - 2];
+        }
       }
-      pstk[stack] = i;
-      astk[stack++] = s;
-    }
-    int pos = 0;
-    for (int i = 0; i < stack; i++) {
-      int endpos;
-      if (i < stack - 1 && astk[i + 1] > astk[i]) endpos = pstk[i + 1];
-      else endpos = pstk[i] + linesper + 1;
-      if (endpos > total) endpos = total;
-      const float a = astk[i];
-      for (; pos < endpos; pos++) seed[pos] = a;
+      pstk[stack] = i; astk[stack] = s;
+      a1 = a0; p1 = p0; a0 = s; p0 = i;
+      stack++;
     }
   }
-  __syncthreads();
-  // max_seeds gather: one item per (static) group
-  for (int g = tid; g < P.ngrp; g += nt) {
+  stack = __shfl_sync(0xffffffffu, stack, 0);
+  __syncwarp();
+  // fill: entry k covers [start_k, end_k) with start_k = max(end_j, j<k) (running cursor)
+  int carry = 0;
+  for (int base = 0; base < stack; base += 32) {
+    const int k = base + lane;
+    int endpos = 0; float a = 0.f;
+    if (k < stack) {
+      a = astk[k];
+      if (k < stack - 1 && astk[k + 1] > a) endpos = pstk[k + 1];
+      else endpos = pstk[k] + linesper + 1;
+      if (endpos > total) endpos = total;
+    }
+    int incl = endpos;                                   // inclusive prefix max over lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o && t > incl) incl = t;
+    }
+    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 0;
+    const int start = excl > carry ? excl : carry;
+    if (k < stack) for (int p = start; p < endpos; p++) seed[p] = a;
+    const int last = __shfl_sync(0xffffffffu, incl, 31);
+    if (last > carry) carry = last;
+    __syncwarp();
+  }
+  __syncwarp();
+  // gather (max_seeds second half): one item per static group; tone starts as ath+att
+  const float att = tone_att(P, lmax);
+  for (int g = lane; g < P.ngrp; g += 32) {
     const int4 gg = __ldg(P.grps + g);
     int pos = gg.x;
     float minV = seed[pos];
@@ -651,16 +715,23 @@ __device__ __forceinline__ void dev_tonemask(const PsyDev &P, const float *logff
       const float s = seed[pos];
       if ((s > VB_NEGINF && s < minV) || minV == VB_NEGINF) minV = s;
     }
-    for (int i = gg.z; i < gg.w; i++)
-      if (tone[i] < minV) tone[i] = minV;
+    for (int i = gg.z; i < gg.w; i++) {
+      float t = __ldg(P.ath + i) + att;
+      if (t < minV) t = minV;
+      tone[i] = t;
+    }
   }
   {
     const float minV = seed[total - 1];
-    for (int i = P.tail_lin0 + tid; i < n; i += nt)
-      if (tone[i] < minV) tone[i] = minV;
+    for (int i = P.tail_lin0 + lane; i < n; i += 32) {
+      float t = __ldg(P.ath + i) + att;
+      if (t < minV) t = minV;
+      tone[i] = t;
+    }
   }
-  __syncthreads();
+  __syncwarp();
 }
+
 
 // _vp_offset_and_mix for one bin (lib/psy.c:779-835); returns logmask, scales m.
 __device__ __forceinline__ float dev_mix_bin(const PsyDev &P, int sel, float noise, float tone,

@@ -28,7 +28,7 @@ struct HostXform {
 
 inline void build_xform(HostXform &x, int N, const float *given_window) {
   x.N = N;
-  x.log2n = (int)std::rint(std::log((float)N) / std::log(2.f));
+  x.log2n = (int)std::rint(std::log((double)(float)N) / std::log((double)2.f));
   const int n2 = N >> 1;
   x.trig.assign(N + N / 4, 0.f);
   x.bitrev.assign(N / 4, 0);
@@ -109,8 +109,8 @@ inline void build_xform(HostXform &x, int N, const float *given_window) {
         for (int ii = 2; ii < ido; ii += 2) {
           fi += 1.f;
           const float arg = fi * argld;
-          x.wa[i++] = (float)std::cos(arg);
-          x.wa[i++] = (float)std::sin(arg);
+          x.wa[i++] = (float)std::cos((double)arg);   // double libm call, as C's cos(float) promotes
+          x.wa[i++] = (float)std::sin((double)arg);
         }
         is += ido;
       }
@@ -122,6 +122,10 @@ inline void build_xform(HostXform &x, int N, const float *given_window) {
 // Data-independent control flow of the psy stages, derived once per look.
 struct HostPsyFlow {
   std::vector<int> run_lo, run_hi;             // seed_loop runs (lib/psy.c:430-436)
+  std::vector<int> runinfo;                    // per run: lo, hi, octave[hi]-firstoc, band
+  std::vector<int> cls_run;                    // (run id, oc) pairs grouped by residue class of the seed slots
+  std::vector<int> slot_rng;                   // per seed slot: [k0,k1) into cls_run (seed_curve, lib/psy.c:390-415)
+  int linesper_log2 = 0;
   std::vector<int> grp;                        // max_seeds groups: pos0,pos1,lin0,lin1 (lib/psy.c:522-538)
   int tail_lin0 = 0;
   int bark_first_extra = 0;                    // first bin that reuses the last A,B,D (lib/psy.c:604-658)
@@ -136,6 +140,41 @@ inline void build_psy_flow(HostPsyFlow &f, const vb200_psy_setup &s) {
     while (j + 1 < n && s.octave[j + 1] == s.octave[i]) j++;
     f.run_lo.push_back(i); f.run_hi.push_back(j);
     i = j + 1;
+  }
+  {
+    // owner-computes form of seed_curve's scatter: slot sp = oc + (i-16)*L - L/2, i in [post0,post1) within [0,56)
+    const int L = s.eighth_octave_lines, half = L >> 1, total = s.total_octave_lines;
+    f.linesper_log2 = 0;
+    while ((1 << f.linesper_log2) < L) f.linesper_log2++;
+    f.runinfo.clear(); f.cls_run.clear(); f.slot_rng.assign((size_t)2 * total, 0);
+    const int nr = (int)f.run_lo.size();
+    std::vector<int> oc(nr);
+    for (int r = 0; r < nr; r++) {
+      const int ov = s.octave[f.run_hi[r]];
+      int band = ov >> s.shiftoc;              // arithmetic shift, as the reference's long >> (lib/psy.c:438)
+      if (band >= VB200_P_BANDS) band = VB200_P_BANDS - 1;
+      if (band < 0) band = 0;
+      oc[r] = ov - s.firstoc;
+      f.runinfo.push_back(f.run_lo[r]); f.runinfo.push_back(f.run_hi[r]);
+      f.runinfo.push_back(oc[r]); f.runinfo.push_back(band);
+    }
+    std::vector<int> cls_off(L + 1, 0);
+    for (int c = 0; c < L; c++) {
+      cls_off[c] = (int)f.cls_run.size() / 2;
+      for (int r = 0; r < nr; r++)             // runs are already in increasing oc order
+        if ((((oc[r] - half) % L) + L) % L == c) { f.cls_run.push_back(r); f.cls_run.push_back(oc[r]); }
+    }
+    cls_off[L] = (int)f.cls_run.size() / 2;
+    for (int sp = 1; sp < total; sp++) {
+      const int c = sp % L;
+      int k0 = cls_off[c + 1], k1 = cls_off[c];
+      for (int k = cls_off[c]; k < cls_off[c + 1]; k++) {
+        const int o = f.cls_run[2 * k + 1];
+        if (o >= sp + half - 39 * L && o <= sp + half + 16 * L) { if (k < k0) k0 = k; if (k + 1 > k1) k1 = k + 1; }
+      }
+      if (k1 < k0) { k0 = 0; k1 = 0; }
+      f.slot_rng[2 * sp] = k0; f.slot_rng[2 * sp + 1] = k1;
+    }
   }
   {
     long linpos = 0;
