@@ -376,6 +376,7 @@ struct PhaseA2Args {
   float *logmask;         // [rows][n]
   float *ampmax_out;      // [blocks]
   float *tap_noise, *tap_tone;
+  int dbg_skip;           // timing experiments only (VB200_DEBUG_SKIP); 0 in production
 };
 
 // shared-memory carve-up for the psy kernels (floats)
@@ -385,7 +386,7 @@ struct PsySmem {
 };
 __host__ __device__ inline size_t psy_smem_floats(int n, int total, int nruns) {
   const int tp = (total + 3) & ~3, rp = (nruns + 3) & ~3;
-  return (size_t)4 * n + 5 * (size_t)(n + 4) + 3 * (size_t)tp + 3 * (size_t)rp;
+  return (size_t)4 * n + 5 * (size_t)(n + 4) + 4 * (size_t)tp + 3 * (size_t)rp;
 }
 __device__ __forceinline__ PsySmem psy_carve(float *sm, int n, int total, int nruns) {
   const int tp = (total + 3) & ~3, rp = (nruns + 3) & ~3;
@@ -398,6 +399,7 @@ __device__ __forceinline__ PsySmem psy_carve(float *sm, int n, int total, int nr
   s.T.run_mx = s.T.astk + tp;
   s.T.run_cofs = reinterpret_cast<int *>(s.T.run_mx + rp);
   s.T.run_p01 = s.T.run_cofs + rp;
+  s.T.rec = s.T.run_p01 + rp;
   return s;
 }
 
@@ -427,12 +429,12 @@ k_phaseA_psy(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     dev_tone_runs(P, S.fft, g, lmax, S.T, tid, nt);
     dev_noise_terms(n, S.logmdct, 140.f, S.scan, ns, tid, nt);
     __syncthreads();
-    dev_tone_slots(P, S.T, tid, nt);
+    if (!(A.dbg_skip & 4)) dev_tone_slots(P, S.T, tid, nt);
     __syncthreads();
     // warp 0: the sequential seed_chase + gather; warps 1-3: the noise mask (two sequential
     // prefix-sum passes on five lanes + regressions).  The two chains are independent.
-    if (warp == 0) dev_tone_chase_gather(P, S.fft, lmax, S.T, lane);
-    else dev_noisemask(P, S.logmdct, S.noise, S.work, S.scan, ns, tid - 32, nt - 32, 1, true);
+    if (warp == 0) { if (!(A.dbg_skip & 1)) dev_tone_chase_gather(P, S.fft, lmax, S.T, lane); }
+    else if (!(A.dbg_skip & 2)) dev_noisemask(P, S.logmdct, S.noise, S.work, S.scan, ns, tid - 32, nt - 32, 1, true);
     __syncthreads();
     const float *noff = P.noiseoffset + n;               // offset_select 1
     for (int i = tid; i < n; i += nt) {
@@ -741,6 +743,7 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
     A.logfft = d_logfft; A.lmax = d_lmax; A.gmax = d_gmax; A.desc = io->desc;
     A.mdct_out = io->mdct; A.logmdct = io->logmdct; A.logmask = io->logmask; A.ampmax_out = io->ampmax_out;
     A.tap_noise = io->tap_noise; A.tap_tone = io->tap_tone;
+    { const char *e = getenv("VB200_DEBUG_SKIP"); A.dbg_skip = e ? atoi(e) : 0; }
     k_phaseA_psy<<<grid_for(c, rows, c->psy_ctas_per_sm), PSY_THREADS, smem, st>>>(P0, P1, ch, rows, A);
     rc = post_launch(c); if (rc) return rc;
   }

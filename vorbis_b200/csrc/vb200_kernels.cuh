@@ -600,6 +600,7 @@ struct ToneSmem {
   float *run_mx;    // [nruns]
   int   *run_cofs;  // [nruns] offset of the chosen curve in tonecurves
   int   *run_p01;   // [nruns] post0 | post1<<16   (1000|1000<<16 = inactive)
+  int   *rec;       // [total] positions of the chase's restart points
 };
 
 __device__ __forceinline__ float tone_att(const PsyDev &P, float lmax) {
@@ -650,57 +651,110 @@ __device__ __forceinline__ void dev_tone_slots(const PsyDev &P, const ToneSmem &
 }
 
 // seed_chase + max_seeds gather, executed by ONE warp (lane = 0..31).
-// tone: n floats (written).  The stack algorithm is emulated literally (its pop
-// rule is not a sliding maximum) by lane 0 with the two topmost
-// entries cached in registers; the fill and the gather are lane-parallel.
+// tone: n floats (written).
+//
+// seed_chase (lib/psy.c:454-508) is a stack algorithm whose pop rule is not a
+// sliding maximum, so it is emulated literally -- but not by one lane.
+// Exact segmentation: at step i the entry left directly below the new entry i has
+// position >= i-L+1 (a pop needs `i < pos[below]+L`).  Hence if seeds[i] is strictly
+// greater than seeds[i-L+1..i-1] ("record"), entry i sits on a strictly smaller
+// entry, can never satisfy the pop test `amp[top] <= amp[top-1]`, and freezes
+// everything beneath it: the algorithm restarted at i with an empty stack evolves
+// identically from there on.  The warp finds all records, splits them evenly over
+// its 32 lanes, and every lane runs the unmodified stack algorithm on its own
+// segment (up to and including the pop phase of the next lane's first record).
+// The final stack is the concatenation of the lanes' stacks.  Worst case (no record,
+// e.g. an all-NEGINF seed vector) degenerates to one lane doing all the work.
 __device__ __forceinline__ void dev_tone_chase_gather(const PsyDev &P, float *tone, float lmax,
                                                       const ToneSmem &T, int lane) {
   const int n = P.n, total = P.total, linesper = P.linesper;
-  float *seed = T.seed; int *pstk = T.pstk; float *astk = T.astk;
-  int stack = 0;
-  if (lane == 0) {
-    float a0 = 0.f, a1 = 0.f; int p0 = 0, p1 = 0;
-    for (int i = 0; i < total; i++) {
-      const float s = seed[i];
-      if (stack >= 2) {
-        while (!(s < a0) && i < p0 + linesper && a0 <= a1 && i < p1 + linesper) {
-          stack--;
-          a0 = a1; p0 = p1;
-          if (stack < 2) break;
-          a1 = astk[stack - 2]; p1 = pstk[stack - 2];
+  float *seed = T.seed; int *pstk = T.pstk; float *astk = T.astk; int *rec = T.rec;
+  const unsigned full = 0xffffffffu;
+  // 1. records
+  int m = 0;
+  for (int base = 0; base < total; base += 32) {
+    const int i = base + lane;
+    bool r = false;
+    if (i < total) {
+      r = (i == 0);
+      if (!r) {
+        const float v = seed[i];
+        r = true;
+        for (int d = 1; d < linesper; d++) {
+          if (i - d < 0) break;
+          if (!(v > seed[i - d])) { r = false; break; }
         }
       }
-      pstk[stack] = i; astk[stack] = s;
-      a1 = a0; p1 = p0; a0 = s; p0 = i;
-      stack++;
     }
+    const unsigned b = __ballot_sync(full, r);
+    if (r) rec[m + __popc(b & ((1u << lane) - 1u))] = i;
+    m += __popc(b);
   }
-  stack = __shfl_sync(0xffffffffu, stack, 0);
   __syncwarp();
-  // fill: entry k covers [start_k, end_k) with start_k = max(end_j, j<k) (running cursor)
-  int carry = 0;
-  for (int base = 0; base < stack; base += 32) {
-    const int k = base + lane;
-    int endpos = 0; float a = 0.f;
-    if (k < stack) {
-      a = astk[k];
-      if (k < stack - 1 && astk[k + 1] > a) endpos = pstk[k + 1];
-      else endpos = pstk[k] + linesper + 1;
-      if (endpos > total) endpos = total;
+  // 2. this lane's segment [start, end]
+  const int r0 = (lane * m) >> 5, r1 = ((lane + 1) * m) >> 5;
+  int start = 0, end = 0, cnt = 0;
+  if (r0 < r1) {
+    start = rec[r0];
+    end = r1 < m ? rec[r1] : total;
+    // 3. the stack algorithm on seeds[start..end); entries stored at astk/pstk[start + depth].
+    // Top three entries are cached in registers (a0 = top, l = pos + linesper, c = #valid).
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    int l0 = 0, l1 = 0, l2 = 0, c = 0, stack = 0;
+    float s = seed[start];
+    for (int i = start; i <= end && i < total; i++) {
+      const float snext = i + 1 < total ? seed[i + 1] : 0.f;
+      if (stack >= 2 && !(s < a0)) {
+        for (;;) {
+          if (c < 2) { a1 = astk[start + stack - 2]; l1 = pstk[start + stack - 2] + linesper; c = 2; }
+          if (!(i < l0 && a0 <= a1 && i < l1)) break;
+          stack--;                           // top is completely overlapped: drop it
+          a0 = a1; l0 = l1; a1 = a2; l1 = l2; c--;
+          if (stack < 2 || s < a0) break;    // the reference re-tests seeds[i] < new top
+        }
+      }
+      if (i < end) {                         // i == end: only the pops belong to this lane
+        astk[start + stack] = s; pstk[start + stack] = i;
+        a2 = a1; l2 = l1; a1 = a0; l1 = l0; a0 = s; l0 = i + linesper;
+        stack++;
+        c = c < 3 ? c + 1 : 3;
+      }
+      s = snext;
     }
-    int incl = endpos;                                   // inclusive prefix max over lanes
+    cnt = stack;
+  }
+  __syncwarp();
+  // 4. fill (lib/psy.c:489-503): entry k is written from the running cursor to endpos_k
+  {
+    int M = 0;
+    for (int j = 0; j < cnt; j++) {
+      const float a = astk[start + j];
+      int endpos;
+      const int nx = j + 1 < cnt ? start + j + 1 : (end < total ? end : -1);
+      if (nx >= 0 && astk[nx] > a) endpos = pstk[nx];
+      else endpos = pstk[start + j] + linesper + 1;
+      if (endpos > total) endpos = total;
+      if (endpos > M) M = endpos;
+    }
+    int incl = M;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      const int t = __shfl_up_sync(full, incl, o);
       if (lane >= o && t > incl) incl = t;
     }
-    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) excl = 0;
-    const int start = excl > carry ? excl : carry;
-    if (k < stack) for (int p = start; p < endpos; p++) seed[p] = a;
-    const int last = __shfl_sync(0xffffffffu, incl, 31);
-    if (last > carry) carry = last;
+    int cursor = __shfl_up_sync(full, incl, 1);
+    if (lane == 0) cursor = 0;
     __syncwarp();
+    for (int j = 0; j < cnt; j++) {
+      const float a = astk[start + j];
+      int endpos;
+      const int nx = j + 1 < cnt ? start + j + 1 : (end < total ? end : -1);
+      if (nx >= 0 && astk[nx] > a) endpos = pstk[nx];
+      else endpos = pstk[start + j] + linesper + 1;
+      if (endpos > total) endpos = total;
+      for (int p = cursor; p < endpos; p++) seed[p] = a;
+      if (endpos > cursor) cursor = endpos;
+    }
   }
   __syncwarp();
   // gather (max_seeds second half): one item per static group; tone starts as ath+att
