@@ -172,6 +172,8 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     d.cls_run = reinterpret_cast<const int2 *>(dc);
     d.slot_rng = reinterpret_cast<const int2 *>(ds);
     d.linesper_log2 = f.linesper_log2;
+    if (p.eighth_octave_lines > 32) return fail(VB200_EIMPL, "eighth_octave_lines > 32");
+    for (size_t k = 0; k < f.cls_off.size() && k < 33; k++) d.cls_off[k] = f.cls_off[k];
   }
   *out = c;
   return 0;

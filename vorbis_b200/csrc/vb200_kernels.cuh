@@ -56,6 +56,7 @@ struct PsyDev {
   const int2  *cls_run;      // runs grouped by residue class, (run id, oc-firstoc), sorted by oc
   const int2  *slot_rng;     // [total] candidate range in cls_run for every seed slot
   int linesper_log2;
+  int cls_off[33];           // class c owns cls_run[cls_off[c] .. cls_off[c+1])
 };
 
 // ------------------------------------------------------------------------
@@ -631,8 +632,48 @@ __device__ __forceinline__ void dev_tone_runs(const PsyDev &P, const float *logf
   }
 }
 
-// seed_curve, owner-computes: one item per seed slot
-__device__ __forceinline__ void dev_tone_slots(const PsyDev &P, const ToneSmem &T, int tid, int nt) {
+// seed_curve (lib/psy.c:390-415) for all runs, without atomics: a run with octave
+// position oc only touches slots s = oc - L/2 (mod L), so runs of different residue
+// classes never collide.  Each class is owned by a group of G = nt/L lanes (inside one
+// warp) that walks the class' runs in order; within a run the G lanes update distinct
+// slots; __syncwarp() orders the runs.  `max` is order-independent, so the result is
+// bit-identical to the reference's sequential scatter.  Requires L in {4,8,16,32} and
+// nt == 128 (G = 32,16,8,4 lanes); other L use dev_tone_slots_gather below.
+__device__ __forceinline__ void dev_tone_slots_scatter(const PsyDev &P, const ToneSmem &T, int tid, int nt) {
+  const int L = P.linesper, half = L >> 1, total = P.total;
+  for (int s = tid; s < total; s += nt) T.seed[s] = VB_NEGINF;
+  __syncthreads();
+  const int G = nt >> P.linesper_log2;               // lanes per class (<= 32)
+  const int cls = tid / G, g = tid - cls * G;
+  const int k0 = P.cls_off[cls], k1 = P.cls_off[cls + 1];
+  // every warp loops to the longest class it hosts so that __syncwarp() is convergent
+  const int wfirst = (tid & ~31) / G, wlast = ((tid | 31)) / G;
+  int len = 0;
+  for (int c = wfirst; c <= wlast; c++) { const int l = P.cls_off[c + 1] - P.cls_off[c]; if (l > len) len = l; }
+  for (int q = 0; q < len; q++) {
+    const int k = k0 + q;
+    if (k < k1) {
+      const int2 cr = __ldg(P.cls_run + k);          // run id, oc - firstoc
+      const int p01 = T.run_p01[cr.x];
+      const int post0 = p01 & 0xffff, post1 = p01 >> 16;
+      if (post0 < post1) {                           // active run
+        const float mx = T.run_mx[cr.x];
+        const float *curve = P.tonecurves + T.run_cofs[cr.x] + 2;
+        for (int i = post0 + g; i < post1; i += G) {
+          const int sp = cr.y + (i - 16) * L - half;
+          if (sp > 0 && sp < total) {
+            const float lin = mx + __ldg(curve + i);
+            if (T.seed[sp] < lin) T.seed[sp] = lin;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// seed_curve, owner-computes (generic fallback): one item per seed slot
+__device__ __forceinline__ void dev_tone_slots_gather(const PsyDev &P, const ToneSmem &T, int tid, int nt) {
   const int half = P.linesper >> 1;
   for (int s = tid; s < P.total; s += nt) {
     float m = VB_NEGINF;
@@ -648,6 +689,11 @@ __device__ __forceinline__ void dev_tone_slots(const PsyDev &P, const ToneSmem &
     }
     T.seed[s] = m;
   }
+}
+
+__device__ __forceinline__ void dev_tone_slots(const PsyDev &P, const ToneSmem &T, int tid, int nt) {
+  if (nt == 128 && P.linesper >= 4 && P.linesper <= 32) dev_tone_slots_scatter(P, T, tid, nt);
+  else dev_tone_slots_gather(P, T, tid, nt);
 }
 
 // seed_chase + max_seeds gather, executed by ONE warp (lane = 0..31).

@@ -126,6 +126,7 @@ struct HostPsyFlow {
   std::vector<int> cls_run;                    // (run id, oc) pairs grouped by residue class of the seed slots
   std::vector<int> slot_rng;                   // per seed slot: [k0,k1) into cls_run (seed_curve, lib/psy.c:390-415)
   int linesper_log2 = 0;
+  std::vector<int> cls_off;                    // [L+1]
   std::vector<int> grp;                        // max_seeds groups: pos0,pos1,lin0,lin1 (lib/psy.c:522-538)
   int tail_lin0 = 0;
   int bark_first_extra = 0;                    // first bin that reuses the last A,B,D (lib/psy.c:604-658)
@@ -158,7 +159,8 @@ inline void build_psy_flow(HostPsyFlow &f, const vb200_psy_setup &s) {
       f.runinfo.push_back(f.run_lo[r]); f.runinfo.push_back(f.run_hi[r]);
       f.runinfo.push_back(oc[r]); f.runinfo.push_back(band);
     }
-    std::vector<int> cls_off(L + 1, 0);
+    std::vector<int> &cls_off = f.cls_off;
+    cls_off.assign(L + 1, 0);
     for (int c = 0; c < L; c++) {
       cls_off[c] = (int)f.cls_run.size() / 2;
       for (int r = 0; r < nr; r++)             // runs are already in increasing oc order
