@@ -152,3 +152,76 @@ def test_phaseA_vs_oracle_random(cfg, W):
     b = o.phaseA(W, pcm, desc, taps=True)
     for k in ("mdct_raw", "logfft", "noise", "tone", "logmdct", "logmask", "mdct", "ampmax_out"):
         assert_bits_equal(a[k], b[k], "phaseA " + k)
+
+
+# ---------------------------------------------------------------------------------------------
+# Phase B: _vp_couple_quantize_normalize (integer outputs: exact match required)
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_couple_quantize_normalize_golden(cfg, tag):
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    for bt in (0, 1):
+        sel = np.where(enc[tag + "_blocktype"] == bt)[0]
+        if not len(sel):
+            continue
+        iw, nz = ctx.couple_quantize_normalize(W, bt, 7, enc[tag + "_mdct_m1"][sel], enc[tag + "_ilogmask"][sel],
+                                               enc[tag + "_nonzero_in"][sel])
+        assert np.array_equal(iw, enc[tag + "_iwork_out"][sel]), "iwork"
+        assert np.array_equal(nz, enc[tag + "_nonzero_out"][sel]), "nonzero"
+
+
+@pytest.mark.parametrize("W", [0, 1])
+def test_couple_quantize_normalize_vs_oracle_random(cfg, W):
+    name, setup, ctx, o, enc, _ = cfg
+    n, ch = setup.blocksize(W) // 2, setup.channels
+    rng = np.random.default_rng(777 + W)
+    nb = 48
+    # spectra with a wide dynamic range around the floor so that all branches fire:
+    # quantise-to-zero pools (noise normalisation), lossless and point stereo, ties
+    ilog = rng.integers(40, 220, (nb, ch, n)).astype(np.int32)
+    amp = 10.0 ** ((ilog.astype(np.float64) * (140.0 / 255.0) - 140.0 + rng.normal(0, 9, ilog.shape)) / 20.0)
+    mdct = (amp * rng.choice([-1.0, 1.0], ilog.shape)).astype(np.float32)
+    mdct[0] = 0.0                                   # silence: every line ties
+    mdct[1] = np.float32(0.01)                      # constant: ties inside the sort
+    if ch == 2:
+        mdct[2, 1] = mdct[2, 0]                     # identical channels
+        mdct[3, 1] = -mdct[3, 0]
+    nz = rng.integers(0, 2, (nb, ch)).astype(np.int32)
+    nz[:8] = 1
+    for bt in (0, 1):
+        for blob in (0, 7, 14):
+            a = ctx.couple_quantize_normalize(W, bt, blob, mdct, ilog, nz)
+            b = o.couple_quantize_normalize(W, bt, blob, mdct, ilog, nz)
+            assert np.array_equal(a[0], b[0]), "iwork bt%d blob%d: %d diffs" % (bt, blob, (a[0] != b[0]).sum())
+            assert np.array_equal(a[1], b[1]), "nonzero"
+
+
+# ---------------------------------------------------------------------------------------------
+# decode: mdct_backward + overlap-add
+def test_decode_golden(cfg):
+    name, setup, ctx, o, _, dec = cfg
+    bs = [setup.blocksize(0), setup.blocksize(1)]
+    Wseq = dec["W"][None, :]
+    coef_off, pcm_off, coef_len, pcm_len = vlib.synthesis_layout(Wseq, bs, setup.channels)
+    pcm = ctx.synthesis(Wseq, coef_off, dec["coef"], pcm_off, pcm_len)
+    assert_bits_equal(pcm[0], dec["pcm"], "decoded pcm")
+
+
+def test_decode_vs_oracle_random_streams(cfg):
+    """many independent streams, random long/short sequences (all four overlap cases)"""
+    name, setup, ctx, o, _, _ = cfg
+    bs = [setup.blocksize(0), setup.blocksize(1)]
+    ch = setup.channels
+    rng = np.random.default_rng(31337)
+    ns, nblk = 37, 23
+    Wseq = rng.integers(0, 2, (ns, nblk)).astype(np.int32)
+    Wseq[0] = 1
+    Wseq[1] = 0
+    coef_off, pcm_off, coef_len, pcm_len = vlib.synthesis_layout(Wseq, bs, ch)
+    coef = (rng.uniform(-1, 1, coef_len) * 1e-2).astype(np.float32)
+    a = ctx.synthesis(Wseq, coef_off, coef, pcm_off, pcm_len)
+    b = o.synthesis(Wseq, coef_off, coef, pcm_off, pcm_len)
+    assert_bits_equal(a, b, "decoded streams")
+    # a single block finishes nothing
+    one = ctx.synthesis(Wseq[:, :1], coef_off[:, :1], coef, pcm_off[:, :1], 8)
+    assert not one.any()

@@ -15,6 +15,7 @@
 #include "vorbis_b200.h"
 #include "vb200_tables.h"
 #include "vb200_kernels.cuh"
+#include "vb200_cqn.cuh"
 #include "floor1_db_table.h"
 
 using namespace vb200;
@@ -57,6 +58,8 @@ struct vb200_ctx {
   // grow-only scratch for the host-buffer entry points and phase A intermediates
   DevBuf scratch[16];
   int psy_ctas_per_sm = 4;
+  const float *d_fromdB = nullptr;
+  const int *d_mag[2] = {nullptr, nullptr}, *d_ang[2] = {nullptr, nullptr};
   cudaStream_t s_main = nullptr;
   std::mutex mu;
   // optional per-kernel timing of the last Phase-A call (bench roofline evidence)
@@ -133,6 +136,15 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     if ((rc = upload(c, h.wa.data(), h.wa.size(), &d.wa))) return rc;
     c->dwin.N[w] = h.N;
     c->dwin.win[w] = d.win;
+  }
+  {
+    int rc;
+    if ((rc = upload(c, VB_FLOOR1_FROMDB, (size_t)256, &c->d_fromdB))) return rc;
+    for (int w = 0; w < 2; w++) {
+      if (s->coupling_steps[w] < 0 || s->coupling_steps[w] > VB200_MAX_COUPLING) return fail(VB200_EINVAL, "coupling_steps");
+      if ((rc = upload(c, (const int *)s->coupling_mag[w], (size_t)s->coupling_steps[w], &c->d_mag[w]))) return rc;
+      if ((rc = upload(c, (const int *)s->coupling_ang[w], (size_t)s->coupling_steps[w], &c->d_ang[w]))) return rc;
+    }
   }
   c->n_psy = s->n_psy;
   for (int i = 0; i < s->n_psy; i++) {
@@ -503,6 +515,56 @@ k_offset_and_mix(PsyDev P, int nvec, int sel, const float *__restrict__ noise,
   }
 }
 
+// ---- decode: mdct_backward (lib/mapping0.c:792-795) + the windowed overlap-add of
+// vorbis_synthesis_blockin (lib/block.c:767-823).  One CTA walks one (stream, channel)
+// block by block; the previous block's second half stays in shared memory, so the only
+// HBM traffic is the spectra in (2N) and the finished samples out (2N per channel-block).
+__global__ void __launch_bounds__(256)
+k_synthesis(XformDev X0, XformDev X1, WinDev Wd, int ch, int nstreams, int nblk,
+            const int *__restrict__ Wseq, const long long *__restrict__ coef_off,
+            const float *__restrict__ coef, const long long *__restrict__ pcm_off,
+            float *__restrict__ pcm, long long pcm_stride) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int n0 = X0.N >> 1, n1 = X1.N >> 1;
+  float *s_in = sm, *s_out = sm + n1, *s_prev = s_out + 2 * n1;
+  const float *w0 = Wd.win[0], *w1 = Wd.win[1];
+  const int off = n1 / 2 - n0 / 2;
+  for (int task = blockIdx.x; task < nstreams * ch; task += gridDim.x) {
+    const int st = task / ch, c = task - st * ch;
+    float *dst0 = pcm + ((size_t)st * ch + c) * pcm_stride;
+    int lW = 0;
+    for (int k = 0; k < nblk; k++) {
+      const int W = Wseq[(size_t)st * nblk + k];
+      const XformDev &X = W ? X1 : X0;
+      const int N = X.N, n2 = N >> 1;
+      const float4 *src = reinterpret_cast<const float4 *>(coef + coef_off[(size_t)st * nblk + k] + (size_t)c * n2);
+      for (int i = tid; i < (n2 >> 2); i += nt) reinterpret_cast<float4 *>(s_in)[i] = __ldg(src + i);
+      __syncthreads();
+      dev_mdct_backward(X, s_in, s_out, tid, nt);
+      if (k > 0) {
+        float *dst = dst0 + pcm_off[(size_t)st * nblk + k];
+        const float *R = s_prev, *Lh = s_out;
+        if (lW && W) {
+          for (int i = tid; i < n1; i += nt) dst[i] = R[i] * __ldg(w1 + n1 - i - 1) + Lh[i] * __ldg(w1 + i);
+        } else if (lW && !W) {
+          for (int i = tid; i < off; i += nt) dst[i] = R[i];
+          for (int i = tid; i < n0; i += nt) dst[off + i] = R[off + i] * __ldg(w0 + n0 - i - 1) + Lh[i] * __ldg(w0 + i);
+        } else if (!lW && W) {
+          for (int i = tid; i < n1 / 2 + n0 / 2; i += nt)
+            dst[i] = i < n0 ? R[i] * __ldg(w0 + n0 - i - 1) + Lh[off + i] * __ldg(w0 + i) : Lh[off + i];
+        } else {
+          for (int i = tid; i < n0; i += nt) dst[i] = R[i] * __ldg(w0 + n0 - i - 1) + Lh[i] * __ldg(w0 + i);
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < n2; i += nt) s_prev[i] = s_out[n2 + i];
+      lW = W;
+      __syncthreads();
+    }
+  }
+}
+
 // ======================================================================== //
 // launch helpers
 static int threads_for(int N) {
@@ -814,20 +876,108 @@ extern "C" int vb200_analysis_phaseA(vb200_ctx *c, int W, int nblocks, const vb2
 }
 
 // ======================================================================== //
-// not yet implemented in this build
-extern "C" int vb200_couple_quantize_normalize_dev(vb200_ctx *, int, int, int, int, const float *, int32_t *, int32_t *, void *) {
-  return fail(VB200_EIMPL, "couple_quantize_normalize: not built yet");
+// Phase B
+static int cqn_setup(vb200_ctx *c, int W, int blocktype, int blobno, CqnDev *Q) {
+  if (c->n_psy != 4) return fail(VB200_EIMPL, "context has no psy lookups");
+  if (blocktype < 0 || blocktype > 1) return fail(VB200_EINVAL, "blocktype");
+  if (blobno < 0 || blobno >= VB200_PACKETBLOBS) return fail(VB200_EINVAL, "blobno");
+  const vb200_psy_setup &p = c->setup.psy[blocktype + 2 * W];
+  static const double thr[] = {0.0, .5, 1.0, 1.5, 2.5, 4.5, 8.5, 16.5, 9e10};       // lib/psy.c:32
+  static const double thr_limited[] = {0.0, .5, 1.0, 1.5, 2.0, 2.5, 4.5, 8.5, 9e10}; // lib/psy.c:33
+  const int pre = c->setup.coupling_prepointamp[blobno], post = c->setup.coupling_postpointamp[blobno];
+  if (pre < 0 || pre > 8 || post < 0 || post > 8) return fail(VB200_EINVAL, "pointamp index");
+  Q->n = p.n; Q->ch = c->setup.channels;
+  Q->partition = p.normal_p ? p.normal_partition : 16;
+  if (Q->partition != 8 && Q->partition != 16 && Q->partition != 32)
+    return fail(VB200_EIMPL, "normal_partition must be 8, 16 or 32");
+  Q->limit = c->setup.coupling_pointlimit[p.blockflag][blobno];
+  Q->sliding_lowpass = c->setup.sliding_lowpass[W][blobno];
+  Q->steps = c->setup.coupling_steps[W];
+  Q->normal_p = p.normal_p; Q->normal_start = p.normal_start; Q->normal_thresh = p.normal_thresh;
+  Q->prepoint = (float)thr[pre];
+  Q->postpoint = (float)(p.n > 1000 ? thr_limited[post] : thr[post]);
+  Q->mag = c->d_mag[W]; Q->ang = c->d_ang[W]; Q->fromdB = c->d_fromdB;
+  return 0;
 }
-extern "C" int vb200_couple_quantize_normalize(vb200_ctx *, int, int, int, int, const float *, int32_t *, int32_t *) {
-  return fail(VB200_EIMPL, "couple_quantize_normalize: not built yet");
+
+extern "C" int vb200_couple_quantize_normalize_dev(vb200_ctx *c, int W, int blocktype, int blobno, int nblocks,
+                                                   const float *d_mdct, int32_t *d_iwork, int32_t *d_nonzero,
+                                                   void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nblocks <= 0) return 0;
+  CqnDev Q; int rc;
+  if ((rc = cqn_setup(c, W, blocktype, blobno, &Q))) return rc;
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * (4 * Q.ch * 32 * sizeof(float) + Q.ch * sizeof(int));
+  if (smem > 200 * 1024) return fail(VB200_EIMPL, "too many channels for the coupling kernel");
+  if ((rc = set_smem(k_cqn, smem))) return rc;
+  const long tasks = (long)nblocks * (Q.n / 32);
+  const int grid = grid_for(c, (int)((tasks + wpb - 1) / wpb), 8);
+  k_cqn<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, nblocks, d_mdct, d_iwork, d_nonzero);
+  if ((rc = post_launch(c))) return rc;
+  if (Q.steps > 0) {
+    k_cqn_nonzero<<<(nblocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nblocks, Q.ch, Q.steps, Q.mag, Q.ang, d_nonzero);
+    if ((rc = post_launch(c))) return rc;
+  }
+  return 0;
 }
-extern "C" int vb200_synthesis_dev(vb200_ctx *, int, int, const int32_t *, const int64_t *, const float *,
-                                   const int64_t *, float *, int64_t, void *) {
-  return fail(VB200_EIMPL, "synthesis: not built yet");
+
+extern "C" int vb200_couple_quantize_normalize(vb200_ctx *c, int W, int blocktype, int blobno, int nblocks,
+                                               const float *mdct, int32_t *iwork, int32_t *nonzero) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nblocks <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int ch = c->setup.channels, n = c->dx[W].N / 2;
+  HostIO io{c};
+  void *dm, *di, *dz; int rc;
+  if ((rc = io.h2d(mdct, sizeof(float) * (size_t)nblocks * ch * n, &dm))) return rc;
+  if ((rc = io.h2d(iwork, sizeof(int32_t) * (size_t)nblocks * ch * n, &di))) return rc;
+  if ((rc = io.h2d(nonzero, sizeof(int32_t) * (size_t)nblocks * ch, &dz))) return rc;
+  if ((rc = vb200_couple_quantize_normalize_dev(c, W, blocktype, blobno, nblocks, (const float *)dm,
+                                                (int32_t *)di, (int32_t *)dz, c->s_main))) return rc;
+  if ((rc = io.d2h(iwork, di, sizeof(int32_t) * (size_t)nblocks * ch * n))) return rc;
+  if ((rc = io.d2h(nonzero, dz, sizeof(int32_t) * (size_t)nblocks * ch))) return rc;
+  return io.sync();
 }
-extern "C" int vb200_synthesis(vb200_ctx *, int, int, const int32_t *, const int64_t *, const float *, int64_t,
-                               const int64_t *, float *, int64_t) {
-  return fail(VB200_EIMPL, "synthesis: not built yet");
+
+// ======================================================================== //
+// decode
+extern "C" int vb200_synthesis_dev(vb200_ctx *c, int nstreams, int nblk, const int32_t *d_Wseq,
+                                   const int64_t *d_coef_off, const float *d_coef,
+                                   const int64_t *d_pcm_off, float *d_pcm, int64_t pcm_stride, void *stream) {
+  CHECK_CTX(c);
+  if (nstreams <= 0 || nblk <= 0) return 0;
+  const int ch = c->setup.channels, N1 = c->dx[1].N;
+  const size_t smem = sizeof(float) * ((size_t)N1 / 2 + N1 + N1 / 2);
+  int rc = set_smem(k_synthesis, smem); if (rc) return rc;
+  k_synthesis<<<grid_for(c, nstreams * ch, 8), threads_for(N1), smem, (cudaStream_t)stream>>>(
+      c->dx[0], c->dx[1], c->dwin, ch, nstreams, nblk, d_Wseq, (const long long *)d_coef_off, d_coef,
+      (const long long *)d_pcm_off, d_pcm, (long long)pcm_stride);
+  return post_launch(c);
+}
+
+extern "C" int vb200_synthesis(vb200_ctx *c, int nstreams, int nblk, const int32_t *Wseq,
+                               const int64_t *coef_off, const float *coef, int64_t coef_len,
+                               const int64_t *pcm_off, float *pcm, int64_t pcm_stride) {
+  CHECK_CTX(c);
+  if (nstreams <= 0 || nblk <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int ch = c->setup.channels;
+  const size_t nb = (size_t)nstreams * nblk;
+  for (size_t i = 0; i < nb; i++) if (Wseq[i] < 0 || Wseq[i] > 1) return fail(VB200_EINVAL, "Wseq values must be 0/1");
+  HostIO io{c};
+  void *dW, *dco, *dc, *dpo, *dp; int rc;
+  if ((rc = io.h2d(Wseq, sizeof(int32_t) * nb, &dW))) return rc;
+  if ((rc = io.h2d(coef_off, sizeof(int64_t) * nb, &dco))) return rc;
+  if ((rc = io.h2d(coef, sizeof(float) * (size_t)coef_len, &dc))) return rc;
+  if ((rc = io.h2d(pcm_off, sizeof(int64_t) * nb, &dpo))) return rc;
+  const size_t pbytes = sizeof(float) * (size_t)nstreams * ch * (size_t)pcm_stride;
+  if ((rc = io.h2d(nullptr, pbytes, &dp))) return rc;
+  CU(cudaMemsetAsync(dp, 0, pbytes, c->s_main));
+  if ((rc = vb200_synthesis_dev(c, nstreams, nblk, (const int32_t *)dW, (const int64_t *)dco, (const float *)dc,
+                                (const int64_t *)dpo, (float *)dp, pcm_stride, c->s_main))) return rc;
+  if ((rc = io.d2h(pcm, dp, pbytes))) return rc;
+  return io.sync();
 }
 
 // ======================================================================== //

@@ -1,0 +1,179 @@
+// vb200_cqn.cuh — Phase B: _vp_couple_quantize_normalize (lib/psy.c:1014-1213) with
+// flag_lossless (:924-935) and noise_normalize (:941-1010).
+//
+// Partitions are independent (noise_normalize resets its accumulator, :951), and inside
+// a partition every line is independent except for (a) the fp32 sum of the pooled
+// energies, taken in line order, and (b) the descending sort of the pooled lines.
+// One warp owns 32 consecutive lines of one block for all channels: lane = line; a
+// partition (8, 16 or 32 lines) is a sub-group of the warp and (a),(b) use shuffles of
+// that width.  Per-channel working values live in shared memory columns owned by the lane.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vorbis_b200.h"
+
+namespace vb200 {
+
+struct CqnDev {
+  int n, ch, partition, limit, sliding_lowpass, steps;
+  int normal_p, normal_start;
+  float prepoint, postpoint;
+  double normal_thresh;
+  const int *mag, *ang;        // [steps]
+  const float *fromdB;         // [256] floor1_inverse_dB_table
+};
+
+__device__ __forceinline__ int cqn_quant(float sign_src, float ve) {   // lib/psy.c:959-963
+  const double q = rint(sqrt((double)ve));
+  return sign_src < 0.f ? (int)-q : (int)q;
+}
+
+// noise_normalize for the lane's line.  use_flags=false <=> flags==NULL in the reference.
+__device__ __forceinline__ void cqn_normalize(const CqnDev &Q, float r, float &q, float f, bool use_flags,
+                                              int flag, int i, int j, int &out, int width, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int jn = Q.partition;
+  int start = Q.normal_p ? Q.normal_start - i : jn;
+  if (start > jn) start = jn;
+  const bool skip = use_flags && flag;             // losslessly coupled: already quantised
+  bool pooled = false;
+  float ve = 0.f;
+  if (!skip) {
+    ve = q / f;
+    if (j >= start && ve < .25f && (!use_flags || j >= Q.limit - i)) pooled = true;
+    else {
+      out = cqn_quant(r, ve);
+      if (j >= start) q = out * out * f;
+    }
+  }
+  // (a) acc += ve over the pooled lines in increasing line order (fp32, sequential)
+  // (b) rank among pooled lines, descending by q, ties by line order (stable, as qsort here)
+  float acc = 0.f;
+  int rank = 0, any = 0;
+  const int g0 = lane & ~(width - 1);
+  for (int t = 0; t < width; t++) {
+    const float vt = __shfl_sync(full, ve, g0 + t);
+    const float qt = __shfl_sync(full, q, g0 + t);
+    const int pt = __shfl_sync(full, (int)pooled, g0 + t);
+    if (pt) {
+      acc += vt;
+      any = 1;
+      if (qt > q || (qt == q && t < j)) rank++;
+    }
+  }
+  if (any && pooled) {
+    // lines are visited in rank order; each promotion costs 1.0 of acc (lib/psy.c:993-1006)
+    float a = acc;
+    bool ok = true;
+    for (int u = 0; u < rank; u++) {
+      if (!((double)a >= Q.normal_thresh)) { ok = false; break; }
+      a -= 1.f;
+    }
+    if (ok && (double)a >= Q.normal_thresh) {
+      out = (int)__int_as_float((__float_as_int(r) & 0x80000000) | 0x3f800000);   // unitnorm
+      q = f;
+    } else {
+      out = 0;
+      q = 0.f;
+    }
+  }
+}
+
+// smem per warp: raw, quant, floor (float) and flag (int): 4 * ch * 32 words
+__global__ void __launch_bounds__(128)
+k_cqn(CqnDev Q, int nblocks, const float *__restrict__ mdct, int *__restrict__ iwork,
+      const int *__restrict__ nonzero) {
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int n = Q.n, ch = Q.ch, width = Q.partition;
+  float *raw = sm + (size_t)wid * 4 * ch * 32;
+  float *quant = raw + ch * 32, *flr = quant + ch * 32;
+  int *flag = reinterpret_cast<int *>(flr + ch * 32);
+  int *nz = reinterpret_cast<int *>(sm + (size_t)wpb * 4 * ch * 32) + wid * ch;   // [ch] per warp
+  const int chunks = n >> 5;
+  const long tasks = (long)nblocks * chunks;
+  for (long t = (long)blockIdx.x * wpb + wid; t < tasks; t += (long)gridDim.x * wpb) {
+    const int blk = (int)(t / chunks), line = (int)(t % chunks) * 32 + lane;
+    const int i = line & ~(width - 1), j = line - i;       // partition start, index inside it
+    const float *m = mdct + (size_t)blk * ch * n;
+    int *iw = iwork + (size_t)blk * ch * n;
+    for (int k = lane; k < ch; k += 32) nz[k] = nonzero[(size_t)blk * ch + k];
+    __syncwarp();
+    for (int k = 0; k < ch; k++) {
+      int out = 0;
+      float R = 0.f, Qe = 0.f, F = 1e-10f; int G = 0;
+      if (nz[k]) {
+        const float mv = m[(size_t)k * n + line];
+        const float fl = __ldg(Q.fromdB + iw[(size_t)k * n + line]);
+        const float point = j >= Q.limit - i ? Q.postpoint : Q.prepoint;      // flag_lossless
+        G = (fabsf(mv) / fl < point) ? 0 : 1;
+        Qe = R = mv * mv;
+        if (mv < 0.f) R *= -1.f;
+        F = fl * fl;
+        cqn_normalize(Q, R, Qe, F, false, 0, i, j, out, width, lane);
+      }
+      raw[k * 32 + lane] = R; quant[k * 32 + lane] = Qe; flr[k * 32 + lane] = F; flag[k * 32 + lane] = nz[k] ? G : 0;
+      iw[(size_t)k * n + line] = out;
+      // note: flag_lossless results are kept for the coupling below; a zero channel has flag 0
+    }
+    for (int step = 0; step < Q.steps; step++) {
+      const int Mi = Q.mag[step], Ai = Q.ang[step];
+      if (!(nz[Mi] || nz[Ai])) continue;
+      __syncwarp();
+      if (lane == 0) { nz[Mi] = 1; nz[Ai] = 1; }
+      __syncwarp();
+      float reM = raw[Mi * 32 + lane], reA = raw[Ai * 32 + lane];
+      float qeM = quant[Mi * 32 + lane], qeA = quant[Ai * 32 + lane];
+      float fM = flr[Mi * 32 + lane], fA = flr[Ai * 32 + lane];
+      int gM = flag[Mi * 32 + lane], gA = flag[Ai * 32 + lane];
+      int iM = iw[(size_t)Mi * n + line], iA = iw[(size_t)Ai * n + line];
+      if (j < Q.sliding_lowpass - i) {
+        if (gM || gA) {                                    // lossless: integer square-polar map
+          const int A = iM, B = iA;
+          reM = fabsf(reM) + fabsf(reA);
+          qeM = qeM + qeA;
+          gM = gA = 1;
+          if (abs(A) > abs(B)) {
+            iA = (A > 0 ? A - B : B - A);
+          } else {
+            iA = (B > 0 ? A - B : B - A);
+            iM = B;
+          }
+          if (iA >= abs(iM) * 2) { iA = -iA; iM = -iM; }
+        } else {                                           // point stereo
+          if (j < Q.limit - i) {
+            reM += reA;
+            qeM = fabsf(reM);
+          } else {
+            const float e = fabsf(reM) + fabsf(reA);
+            qeM = e;
+            reM = (reM + reA < 0.f) ? -e : e;
+          }
+          reA = qeA = 0.f;
+          gA = 1;
+          iA = 0;
+        }
+      }
+      fM = fA = fM + fA;
+      cqn_normalize(Q, reM, qeM, fM, true, gM, i, j, iM, width, lane);
+      raw[Mi * 32 + lane] = reM; raw[Ai * 32 + lane] = reA;
+      quant[Mi * 32 + lane] = qeM; quant[Ai * 32 + lane] = qeA;
+      flr[Mi * 32 + lane] = fM; flr[Ai * 32 + lane] = fA;
+      flag[Mi * 32 + lane] = gM; flag[Ai * 32 + lane] = gA;
+      iw[(size_t)Mi * n + line] = iM; iw[(size_t)Ai * n + line] = iA;
+    }
+    __syncwarp();
+  }
+}
+
+// nonzero[] propagation over coupling steps (lib/psy.c:1203-1212); runs after k_cqn
+__global__ void k_cqn_nonzero(int nblocks, int ch, int steps, const int *__restrict__ mag,
+                              const int *__restrict__ ang, int *__restrict__ nonzero) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  int *nz = nonzero + (size_t)b * ch;
+  for (int s = 0; s < steps; s++)
+    if (nz[mag[s]] || nz[ang[s]]) { nz[mag[s]] = 1; nz[ang[s]] = 1; }
+}
+
+}  // namespace vb200
