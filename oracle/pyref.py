@@ -14,6 +14,7 @@ from vorbis_b200 import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "libvorbis_ref.so")
+DROPIN_PATH = os.path.join(HERE, "_ref", "libvorbis_dropin.so")
 
 f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -38,12 +39,44 @@ class Capture(C.Structure):
 
 
 _lib = None
+_dropin = None
+
+
+def dropin_available():
+    return os.path.exists(DROPIN_PATH)
+
+
+def dropin_lib():
+    """The reference encoder/decoder whose mapping0 hot callees are redirected to the CUDA
+    shims (vorbis_b200/host/vb200_ref_shim.c); same driver entry points as lib()."""
+    global _dropin
+    if _dropin is None:
+        L = C.CDLL(DROPIN_PATH)
+        _declare(L)
+        L.vb200shim_attach.argtypes = [C.c_void_p, C.c_int]
+        L.vb200shim_launches.restype = C.c_ulonglong
+        _dropin = L
+    return _dropin
+
+
+def _declare(L):
+    L.ref_open.restype = C.c_void_p
+    L.ref_open.argtypes = [C.c_int, C.c_long, C.c_float]
+    L.ref_close.argtypes = [C.c_void_p]
+    L.ref_vd.restype = C.c_void_p
+    L.ref_vd.argtypes = [C.c_void_p]
+    L.ref_blocksize.argtypes = [C.c_void_p, C.c_int]
+    L.ref_get_packets.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_int]
+    L.ref_encode_capture.argtypes = [C.c_void_p, f32p, C.c_long, C.POINTER(Capture), C.POINTER(C.c_long)]
+    L.ref_decode_capture.restype = C.c_long
+    L.ref_decode_capture.argtypes = [C.c_void_p, C.POINTER(Capture), f32p, C.c_long, C.c_void_p]
 
 
 def lib():
     global _lib
     if _lib is None:
         L = C.CDLL(LIB_PATH)
+        _declare(L)
         L.ref_open.restype = C.c_void_p
         L.ref_open.argtypes = [C.c_int, C.c_long, C.c_float]
         L.ref_close.argtypes = [C.c_void_p]
@@ -77,17 +110,39 @@ _CAP_I_n = ["ilogmask", "iwork_out"]
 
 
 class Ref:
-    """One reference encoder instance: vorbis_encode_init_vbr(channels, rate, quality)."""
+    """One reference encoder instance: vorbis_encode_init_vbr(channels, rate, quality).
+    dropin=True uses the CUDA-shimmed build and attaches the device context."""
 
-    def __init__(self, channels=2, rate=44100, quality=0.5):
-        self.L = lib()
+    def __init__(self, channels=2, rate=44100, quality=0.5, dropin=False, device=0):
+        self.L = dropin_lib() if dropin else lib()
         self.h = self.L.ref_open(channels, rate, quality)
         if not self.h:
             raise RuntimeError("reference refused setup (ch=%d rate=%d q=%g)" % (channels, rate, quality))
         self.channels, self.rate, self.quality = channels, rate, quality
         self.bs = [self.L.ref_blocksize(self.h, 0), self.L.ref_blocksize(self.h, 1)]
+        self.dropin = dropin
+        if dropin:
+            rc = self.L.vb200shim_attach(self.L.ref_vd(self.h), device)
+            if rc:
+                raise RuntimeError("vb200shim_attach failed: %d" % rc)
+
+    def packets(self):
+        """bytes of every packet produced by encode_capture (list of bytes objects)"""
+        cap = 1 << 24
+        buf = (C.c_ubyte * cap)()
+        sizes = (C.c_long * 100000)()
+        n = self.L.ref_get_packets(self.h, buf, cap, sizes, 100000)
+        assert n >= 0
+        out, off = [], 0
+        raw = bytes(buf)
+        for i in range(n):
+            out.append(raw[off:off + sizes[i]])
+            off += sizes[i]
+        return out
 
     def close(self):
+        if self.h and getattr(self, "dropin", False):
+            self.L.vb200shim_detach()
         if self.h:
             self.L.ref_close(self.h)
             self.h = None

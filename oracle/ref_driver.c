@@ -89,6 +89,22 @@ void ref_close(void *hv){
   free(h);
 }
 
+/* accessors used by the drop-in integration test */
+void *ref_vd(void *hv){ return &((ref_handle*)hv)->vd; }
+
+/* concatenated packet bytes kept by ref_encode_capture; returns number of packets */
+int ref_get_packets(void *hv, unsigned char *buf, long cap, long *sizes, int maxn){
+  ref_handle *h = (ref_handle*)hv;
+  long off = 0; int i;
+  for(i = 0; i < h->npkt && i < maxn; i++){
+    if(off + h->pktbytes[i] > cap) return -1;
+    memcpy(buf + off, h->pkt[i], h->pktbytes[i]);
+    sizes[i] = h->pktbytes[i];
+    off += h->pktbytes[i];
+  }
+  return i;
+}
+
 int ref_blocksize(void *hv, int W){
   ref_handle *h = (ref_handle*)hv;
   codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;

@@ -1,0 +1,191 @@
+/* vb200_ref_shim.c — the reference-side binding: libvorbis' own hot-path functions,
+ * with libvorbis' own signatures, implemented by calls into the CUDA library.
+ *
+ * A libvorbis maintainer drops this file into lib/ and compiles lib/mapping0.c with
+ *   -Dmdct_forward=vb200shim_mdct_forward -Dmdct_backward=vb200shim_mdct_backward
+ *   -D_vorbis_apply_window=vb200shim_apply_window -Ddrft_forward=vb200shim_drft_forward
+ *   -D_vp_noisemask=vb200shim_noisemask -D_vp_tonemask=vb200shim_tonemask
+ *   -D_vp_offset_and_mix=vb200shim_offset_and_mix
+ *   -D_vp_couple_quantize_normalize=vb200shim_couple_quantize_normalize
+ * (or renames the callees in place); nothing else in libvorbis changes.  Every function
+ * below has exactly the prototype of the reference function it replaces (cited), and
+ * the same argument meaning, in-place behaviour and (absence of) error returns; a CUDA
+ * failure is reported on stderr and the block is left untouched rather than aborting.
+ *
+ * This is the per-function (stage-level) binding: one host<->device round trip per
+ * call, so it demonstrates bit-exact drop-in behaviour, not speed.  The batched
+ * entry points of include/vorbis_b200.h (vb200_analysis_phaseA etc.) are the fast path;
+ * INTEGRATION.md shows how mapping0_forward hands whole batches to them.
+ *
+ * Compiled against the reference's internal headers (codec_internal.h, psy.h, mdct.h,
+ * smallft.h) - like any libvorbis-internal backend - by oracle/Makefile target `dropin`.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "vorbis/codec.h"
+#include "codec_internal.h"
+#include "mdct.h"
+#include "smallft.h"
+#include "window.h"
+#include "psy.h"
+
+#include "vorbis_b200.h"
+
+/* one attached encoder/decoder state at a time (the reference itself is single threaded
+ * per vorbis_dsp_state); a production build would hang the context off
+ * private_state instead of a global. */
+static struct {
+  vb200_ctx *ctx;
+  vorbis_dsp_state *vd;
+  int32_t *octave[4], *bark[4];
+  float *tonecurves[4], *noiseoffset[4];
+} g;
+
+static void shim_warn(const char *what, int rc){
+  fprintf(stderr, "vb200 shim: %s failed (%d): %s\n", what, rc, vb200_last_error());
+}
+
+/* Build the device context from the lookups _vds_shared_init made (lib/block.c:170-294). */
+int vb200shim_attach(vorbis_dsp_state *vd, int device){
+  vorbis_info *vi = vd->vi;
+  codec_setup_info *ci = (codec_setup_info*)vi->codec_setup;
+  private_state *b = (private_state*)vd->backend_state;
+  vorbis_info_psy_global *gi = &ci->psy_g_param;
+  vb200_setup s;
+  int i, j, k, w, rc;
+  memset(&s, 0, sizeof(s));
+  s.channels = vi->channels;
+  s.rate = (int32_t)vi->rate;
+  s.blocksizes[0] = (int32_t)ci->blocksizes[0];
+  s.blocksizes[1] = (int32_t)ci->blocksizes[1];
+  s.n_psy = (vd->analysisp && ci->psys == 4) ? 4 : 0;
+  for(i = 0; i < s.n_psy; i++){
+    vorbis_look_psy *p = b->psy + i;
+    vorbis_info_psy *pi = p->vi;
+    vb200_psy_setup *o = &s.psy[i];
+    int n = p->n;
+    o->n = n; o->blockflag = pi->blockflag;
+    o->ath_adjatt = pi->ath_adjatt; o->ath_maxatt = pi->ath_maxatt;
+    for(j = 0; j < P_NOISECURVES; j++) o->tone_masteratt[j] = pi->tone_masteratt[j];
+    o->tone_abs_limit = pi->tone_abs_limit; o->noisemaxsupp = pi->noisemaxsupp;
+    o->noisewindowfixed = pi->noisewindowfixed;
+    for(j = 0; j < NOISE_COMPAND_LEVELS; j++) o->noisecompand[j] = pi->noisecompand[j];
+    o->max_curve_dB = pi->max_curve_dB;
+    o->normal_p = pi->normal_p; o->normal_start = pi->normal_start;
+    o->normal_partition = pi->normal_partition; o->normal_thresh = pi->normal_thresh;
+    o->firstoc = (int32_t)p->firstoc; o->shiftoc = (int32_t)p->shiftoc;
+    o->eighth_octave_lines = p->eighth_octave_lines; o->total_octave_lines = p->total_octave_lines;
+    o->m_val = p->m_val;
+    g.octave[i] = (int32_t*)malloc(sizeof(int32_t)*n);
+    g.bark[i] = (int32_t*)malloc(sizeof(int32_t)*n);
+    g.tonecurves[i] = (float*)malloc(sizeof(float)*P_BANDS*P_LEVELS*(EHMER_MAX+2));
+    g.noiseoffset[i] = (float*)malloc(sizeof(float)*P_NOISECURVES*n);
+    for(j = 0; j < n; j++){ g.octave[i][j] = (int32_t)p->octave[j]; g.bark[i][j] = (int32_t)p->bark[j]; }
+    for(j = 0; j < P_BANDS; j++) for(k = 0; k < P_LEVELS; k++)
+      memcpy(g.tonecurves[i] + (j*P_LEVELS+k)*(EHMER_MAX+2), p->tonecurves[j][k], sizeof(float)*(EHMER_MAX+2));
+    for(j = 0; j < P_NOISECURVES; j++) memcpy(g.noiseoffset[i] + j*n, p->noiseoffset[j], sizeof(float)*n);
+    o->ath = p->ath; o->octave = g.octave[i]; o->bark = g.bark[i];
+    o->tonecurves = g.tonecurves[i]; o->noiseoffset = g.noiseoffset[i];
+  }
+  s.ampmax_att_per_sec = gi->ampmax_att_per_sec;
+  for(k = 0; k < PACKETBLOBS; k++){
+    for(w = 0; w < 2; w++){
+      s.coupling_pointlimit[w][k] = gi->coupling_pointlimit[w][k];
+      s.sliding_lowpass[w][k] = gi->sliding_lowpass[w][k];
+    }
+    s.coupling_prepointamp[k] = gi->coupling_prepointamp[k];
+    s.coupling_postpointamp[k] = gi->coupling_postpointamp[k];
+  }
+  for(w = 0; w < 2 && w < ci->modes; w++){
+    vorbis_info_mapping0 *m = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[w]->mapping];
+    s.coupling_steps[w] = m->coupling_steps;
+    for(k = 0; k < m->coupling_steps; k++){ s.coupling_mag[w][k] = m->coupling_mag[k]; s.coupling_ang[w][k] = m->coupling_ang[k]; }
+  }
+  s.window[0] = _vorbis_window_get(b->window[0]);
+  s.window[1] = _vorbis_window_get(b->window[1]);
+  rc = vb200_ctx_create(&s, device, &g.ctx);
+  if(rc){ shim_warn("vb200_ctx_create", rc); return rc; }
+  g.vd = vd;
+  return 0;
+}
+
+void vb200shim_detach(void){
+  int i;
+  if(g.ctx) vb200_ctx_destroy(g.ctx);
+  for(i = 0; i < 4; i++){ free(g.octave[i]); free(g.bark[i]); free(g.tonecurves[i]); free(g.noiseoffset[i]); }
+  memset(&g, 0, sizeof(g));
+}
+
+unsigned long long vb200shim_launches(void){ return g.ctx ? vb200_launch_count(g.ctx) : 0; }
+
+static int W_of_n(int n){
+  codec_setup_info *ci = (codec_setup_info*)g.vd->vi->codec_setup;
+  return n == ci->blocksizes[1] ? 1 : 0;
+}
+static int look_of(vorbis_look_psy *p){
+  private_state *b = (private_state*)g.vd->backend_state;
+  return (int)(p - b->psy);
+}
+
+/* mdct_forward, lib/mdct.c:492 */
+void vb200shim_mdct_forward(mdct_lookup *init, DATA_TYPE *in, DATA_TYPE *out){
+  int rc = vb200_mdct_forward(g.ctx, W_of_n(init->n), 1, in, out);
+  if(rc) shim_warn("mdct_forward", rc);
+}
+/* mdct_backward, lib/mdct.c:396 (in == out allowed, as at lib/mapping0.c:794) */
+void vb200shim_mdct_backward(mdct_lookup *init, DATA_TYPE *in, DATA_TYPE *out){
+  int n = init->n;
+  float *tmp = (float*)malloc(sizeof(float)*n);
+  int rc = vb200_mdct_backward(g.ctx, W_of_n(n), 1, in, tmp);
+  if(rc) shim_warn("mdct_backward", rc); else memcpy(out, tmp, sizeof(float)*n);
+  free(tmp);
+}
+/* _vorbis_apply_window, lib/window.c:2102 */
+void vb200shim_apply_window(float *d, int *winno, long *blocksizes, int lW, int W, int nW){
+  int32_t l = lW, r = nW;
+  int rc = vb200_apply_window(g.ctx, W, 1, &l, &r, d);
+  (void)winno; (void)blocksizes;
+  if(rc) shim_warn("apply_window", rc);
+}
+/* drft_forward, lib/smallft.c:1231 */
+void vb200shim_drft_forward(drft_lookup *l, float *data){
+  int rc = vb200_drft_forward(g.ctx, W_of_n(l->n), 1, data);
+  if(rc) shim_warn("drft_forward", rc);
+}
+/* _vp_noisemask, lib/psy.c:706 */
+void vb200shim_noisemask(vorbis_look_psy *p, float *logmdct, float *logmask){
+  int rc = vb200_noisemask(g.ctx, look_of(p), 1, logmdct, logmask);
+  if(rc) shim_warn("noisemask", rc);
+}
+/* _vp_tonemask, lib/psy.c:754 */
+void vb200shim_tonemask(vorbis_look_psy *p, float *logfft, float *logmask, float global_specmax, float local_specmax){
+  int rc = vb200_tonemask(g.ctx, look_of(p), 1, logfft, &global_specmax, &local_specmax, logmask);
+  if(rc) shim_warn("tonemask", rc);
+}
+/* _vp_offset_and_mix, lib/psy.c:779 */
+void vb200shim_offset_and_mix(vorbis_look_psy *p, float *noise, float *tone, int offset_select,
+                              float *logmask, float *mdct, float *logmdct){
+  int rc = vb200_offset_and_mix(g.ctx, look_of(p), 1, offset_select, noise, tone, mdct, logmdct, logmask);
+  if(rc) shim_warn("offset_and_mix", rc);
+}
+/* _vp_couple_quantize_normalize, lib/psy.c:1014 */
+void vb200shim_couple_quantize_normalize(int blobno, vorbis_info_psy_global *gp, vorbis_look_psy *p,
+                                         vorbis_info_mapping0 *vi, float **mdct, int **iwork, int *nonzero,
+                                         int sliding_lowpass, int ch){
+  int look = look_of(p), W = look >> 1, blocktype = look & 1, n = p->n, c, rc;
+  float *m = (float*)malloc(sizeof(float)*ch*n);
+  int32_t *iw = (int32_t*)malloc(sizeof(int32_t)*ch*n);
+  int32_t *nz = (int32_t*)malloc(sizeof(int32_t)*ch);
+  (void)gp; (void)vi; (void)sliding_lowpass;
+  for(c = 0; c < ch; c++){
+    memcpy(m + (size_t)c*n, mdct[c], sizeof(float)*n);
+    memcpy(iw + (size_t)c*n, iwork[c], sizeof(int32_t)*n);
+    nz[c] = nonzero[c];
+  }
+  rc = vb200_couple_quantize_normalize(g.ctx, W, blocktype, blobno, 1, m, iw, nz);
+  if(rc) shim_warn("couple_quantize_normalize", rc);
+  else for(c = 0; c < ch; c++){ memcpy(iwork[c], iw + (size_t)c*n, sizeof(int32_t)*n); nonzero[c] = nz[c]; }
+  free(m); free(iw); free(nz);
+}
