@@ -1,0 +1,101 @@
+"""CPU oracle (our restatement) against the compiled reference itself on fresh signals, for a grid
+of (channels, rate, quality): every stage, the fused Phase-A chain recorded from the real
+mapping0_forward, Phase B, the ampmax chain and the decoded PCM.  Bit-exact.
+Needs oracle/_ref (only buildable where /root/reference exists) - skipped elsewhere; the same
+claims are pinned everywhere by tests/test_oracle_golden.py through the committed fixtures."""
+import numpy as np
+import pytest
+
+from conftest import assert_bits_equal, probe_signal
+from oracle import pyref
+from vorbis_b200 import abi, lib as vlib
+
+pytestmark = pytest.mark.skipif(not pyref.available(), reason="oracle/_ref not built")
+
+GRID = [(2, 44100, 0.5), (1, 44100, 0.4), (2, 44100, 0.1), (2, 44100, 0.3), (1, 44100, 0.2),
+        (2, 48000, 0.9), (2, 32000, 0.0), (1, 22050, 0.3)]
+
+
+@pytest.fixture(scope="module", params=GRID, ids=lambda g: "ch%d_%d_q%g" % g)
+def pair(request, oracle_lib):
+    ch, rate, q = request.param
+    r = pyref.Ref(ch, rate, q)
+    setup = r.setup()
+    o = oracle_lib.Oracle(setup)
+    pcm = probe_signal(ch, rate, 1.2, seed=11)
+    if ch == 2:
+        pcm[1] = (0.7 * pcm[0] + 0.3 * pcm[1]).astype(np.float32)
+    cap = r.encode_capture(pcm)
+    return r, setup, o, cap, pcm
+
+
+def test_tables(pair):
+    r, setup, o, cap, _ = pair
+    for W in (0, 1):
+        for which in (0, 1, 2, 3):
+            assert_bits_equal(r.table(W, which), o.table(W, which), "table W%d #%d" % (W, which))
+
+
+def test_transforms_random(pair):
+    r, setup, o, cap, _ = pair
+    rng = np.random.default_rng(7)
+    for W in (0, 1):
+        N = r.bs[W]
+        x = rng.uniform(-1, 1, (16, N)).astype(np.float32)
+        assert_bits_equal(r.mdct_forward(W, x), o.mdct_forward(W, x), "mdct_forward")
+        y = rng.uniform(-1, 1, (16, N // 2)).astype(np.float32)
+        assert_bits_equal(r.mdct_backward(W, y), o.mdct_backward(W, y), "mdct_backward")
+        assert_bits_equal(r.drft_forward(W, x), o.drft_forward(W, x), "drft_forward")
+        lW = rng.integers(0, 2, 16).astype(np.int32)
+        nW = rng.integers(0, 2, 16).astype(np.int32)
+        assert_bits_equal(r.apply_window(W, x, lW, nW), o.apply_window(W, x, lW, nW), "window")
+
+
+def test_phaseA_chain_of_the_real_encoder(pair):
+    r, setup, o, cap, _ = pair
+    ch = setup.channels
+    for W in (0, 1):
+        idx = np.where(cap["W"] == W)[0]
+        if not len(idx):
+            continue
+        N = r.bs[W]
+        n = N // 2
+        desc = np.zeros(len(idx), abi.BLOCKDESC_DTYPE)
+        for k in ("lW", "nW", "blocktype"):
+            desc[k] = cap[k][idx]
+        desc["ampmax"] = cap["ampmax_in"][idx]
+        out = o.phaseA(W, cap["pcm"][idx][:, :, :N], desc, taps=True)
+        for k, g in (("mdct_raw", "mdct_raw"), ("logfft", "logfft"), ("noise", "noise"), ("tone", "tone"),
+                     ("logmdct", "logmdct"), ("logmask", "logmask"), ("mdct", "mdct_m1")):
+            assert_bits_equal(out[k], cap[g][idx][:, :, :n], "W%d %s" % (W, k))
+        assert_bits_equal(out["ampmax_out"], cap["ampmax_out"][idx], "ampmax_out")
+        # the driver's batched reference helper (used by bench.py's CPU legs) agrees too
+        m, lmd, lmk, amp = r.phaseA_batch(W, cap["pcm"][idx][:, :, :N], desc)
+        assert_bits_equal(lmk, cap["logmask"][idx][:, :, :n], "ref_phaseA_batch logmask")
+        assert_bits_equal(m, cap["mdct_m1"][idx][:, :, :n], "ref_phaseA_batch mdct")
+
+
+def test_phaseB_of_the_real_encoder(pair):
+    r, setup, o, cap, _ = pair
+    for W in (0, 1):
+        for bt in (0, 1):
+            sel = np.where((cap["W"] == W) & (cap["blocktype"] == bt))[0]
+            if not len(sel):
+                continue
+            n = r.bs[W] // 2
+            iw, nz = o.couple_quantize_normalize(W, bt, 7, cap["mdct_m1"][sel][:, :, :n],
+                                                 cap["ilogmask"][sel][:, :, :n], cap["nonzero_in"][sel])
+            assert np.array_equal(iw, cap["iwork_out"][sel][:, :, :n])
+            assert np.array_equal(nz, cap["nonzero_out"][sel])
+
+
+def test_decode_of_the_real_stream(pair):
+    r, setup, o, cap, pcm = pair
+    d = r.decode_capture(cap["nblocks"] + 4, pcm.shape[1] + 8192)
+    Wseq = d["W"][None, :]
+    coef_off, pcm_off, coef_len, pcm_len = vlib.synthesis_layout(Wseq, r.bs, setup.channels)
+    coef = np.concatenate([d["dec_coef"][k][:, :r.bs[d["W"][k]] // 2].reshape(-1) for k in range(len(d["W"]))])
+    out = o.synthesis(Wseq, coef_off, coef, pcm_off, pcm_len)
+    m = min(d["pcm"].shape[1], pcm_len)
+    assert m > 0
+    assert_bits_equal(out[0][:, :m], d["pcm"][:, :m], "decoded pcm")
