@@ -57,7 +57,7 @@ struct vb200_ctx {
   std::atomic<uint64_t> launches{0};
   // grow-only scratch for the host-buffer entry points and phase A intermediates
   DevBuf scratch[16];
-  int psy_ctas_per_sm = 4;
+  int psy_ctas_per_sm = 5;
   const float *d_fromdB = nullptr;
   const int *d_mag[2] = {nullptr, nullptr}, *d_ang[2] = {nullptr, nullptr};
   cudaStream_t s_main = nullptr;
@@ -395,25 +395,26 @@ struct PhaseA2Args {
 
 // shared-memory carve-up for the psy kernels (floats)
 struct PsySmem {
-  float *logmdct, *work, *noise, *scan, *fft;
+  float *logmdct, *noise, *scan, *fft;
   ToneSmem T;
 };
 __host__ __device__ inline size_t psy_smem_floats(int n, int total, int nruns) {
-  const int tp = (total + 3) & ~3, rp = (nruns + 3) & ~3;
-  return (size_t)4 * n + 5 * (size_t)(n + 4) + 4 * (size_t)tp + 3 * (size_t)rp;
+  const int tp = (total + 7) & ~7, rp = (nruns + 3) & ~3;
+  size_t runs = 2 * (size_t)rp;                      // run_mx + run_info, also hosts rec (tp shorts)
+  if (runs < (size_t)tp / 2) runs = tp / 2;
+  return (size_t)3 * n + 5 * (size_t)(n + 4) + 2 * (size_t)tp + tp / 2 + runs;
 }
 __device__ __forceinline__ PsySmem psy_carve(float *sm, int n, int total, int nruns) {
-  const int tp = (total + 3) & ~3, rp = (nruns + 3) & ~3;
+  const int tp = (total + 7) & ~7, rp = (nruns + 3) & ~3;
   PsySmem s;
-  s.logmdct = sm; s.work = s.logmdct + n; s.noise = s.work + n; s.scan = s.noise + n;
+  s.logmdct = sm; s.noise = s.logmdct + n; s.scan = s.noise + n;
   s.fft = s.scan + 5 * (n + 4);
   s.T.seed = s.fft + n;
-  s.T.pstk = reinterpret_cast<int *>(s.T.seed + tp);
-  s.T.astk = reinterpret_cast<float *>(s.T.pstk + tp);
-  s.T.run_mx = s.T.astk + tp;
-  s.T.run_cofs = reinterpret_cast<int *>(s.T.run_mx + rp);
-  s.T.run_p01 = s.T.run_cofs + rp;
-  s.T.rec = s.T.run_p01 + rp;
+  s.T.astk = s.T.seed + tp;
+  s.T.pstk = reinterpret_cast<short *>(s.T.astk + tp);
+  s.T.run_mx = s.T.astk + tp + tp / 2;
+  s.T.run_info = reinterpret_cast<int *>(s.T.run_mx + rp);
+  s.T.rec = reinterpret_cast<short *>(s.T.run_mx);
   return s;
 }
 
@@ -441,14 +442,14 @@ k_phaseA_psy(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     __syncthreads();
     // all warps: run peaks / curve choice, and the first pass' per-bin sum terms
     dev_tone_runs(P, S.fft, g, lmax, S.T, tid, nt);
-    dev_noise_terms(n, S.logmdct, 140.f, S.scan, ns, tid, nt);
+    dev_noise_terms(n, S.logmdct, nullptr, 140.f, S.scan, ns, tid, nt);
     __syncthreads();
     if (!(A.dbg_skip & 4)) dev_tone_slots(P, S.T, tid, nt);
     __syncthreads();
     // warp 0: the sequential seed_chase + gather; warps 1-3: the noise mask (two sequential
     // prefix-sum passes on five lanes + regressions).  The two chains are independent.
     if (warp == 0) { if (!(A.dbg_skip & 1)) dev_tone_chase_gather(P, S.fft, lmax, S.T, lane); }
-    else if (!(A.dbg_skip & 2)) dev_noisemask(P, S.logmdct, S.noise, S.work, S.scan, ns, tid - 32, nt - 32, 1, true);
+    else if (!(A.dbg_skip & 2)) dev_noisemask(P, S.logmdct, S.noise, S.scan, ns, tid - 32, nt - 32, 1, true);
     __syncthreads();
     const float *noff = P.noiseoffset + n;               // offset_select 1
     for (int i = tid; i < n; i += nt) {
@@ -474,7 +475,7 @@ k_noisemask(PsyDev P, int nvec, const float *__restrict__ logmdct, float *__rest
   for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
     for (int i = tid; i < n; i += nt) S.logmdct[i] = logmdct[(size_t)v * n + i];
     __syncthreads();
-    dev_noisemask(P, S.logmdct, S.noise, S.work, S.scan, ns, tid, nt, 0, false);
+    dev_noisemask(P, S.logmdct, S.noise, S.scan, ns, tid, nt, 0, false);
     for (int i = tid; i < n; i += nt) noise[(size_t)v * n + i] = S.noise[i];
     __syncthreads();
   }

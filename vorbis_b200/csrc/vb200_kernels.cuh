@@ -482,11 +482,13 @@ __device__ __forceinline__ Abd dev_window_abd(int lo, int hi, const float *S, in
 }
 
 // per-bin terms of the five running sums (lib/psy.c:565-596)
-__device__ __forceinline__ void dev_noise_terms(int n, const float *f, float offset, float *S, int ns,
-                                                int tid, int nt) {
+// f = a[i] (b == nullptr) or a[i] - b[i] (second pass: logmdct - first-pass mask, lib/psy.c:717)
+__device__ __forceinline__ void dev_noise_terms(int n, const float *a, const float *b, float offset,
+                                                float *S, int ns, int tid, int nt) {
   float *aN = S, *aX = S + ns, *aXX = S + 2 * ns, *aY = S + 3 * ns, *aXY = S + 4 * ns;
   for (int i = tid; i < n; i += nt) {
-    float y = f[i] + offset;
+    const float f = b ? a[i] - b[i] : a[i];
+    float y = f + offset;
     if (y < 1.f) y = 1.f;
     float w = y * y;
     if (i == 0) {
@@ -521,8 +523,11 @@ __device__ __forceinline__ void dev_noise_scan(int n, float *S, int ns, int lane
 }
 
 // regression per bin (lib/psy.c:604-703); bins past first_extra reuse the last A,B,D
+// If logmdct != nullptr this is the second pass and the final step of _vp_noisemask
+// (lib/psy.c:722,745-750) is applied in place: noise[i] holds the first-pass mask p1 on entry.
 __device__ __forceinline__ void dev_noise_regress(const PsyDev &P, float *noise, float offset, int fixed,
-                                                  const float *S, int ns, int tid, int nt) {
+                                                  const float *S, int ns, int tid, int nt,
+                                                  const float *logmdct) {
   const int n = P.n;
   const int bfe = P.bark_first_extra;
   const int ffe = P.fixed_first_extra;
@@ -550,36 +555,35 @@ __device__ __forceinline__ void dev_noise_regress(const PsyDev &P, float *noise,
       const float R2 = (cur.A + x * cur.B) / cur.D;
       if (R2 - offset < v) v = R2 - offset;
     }
+    if (logmdct) {
+      const float l = logmdct[i];
+      const float work = l - noise[i];               // logmdct - p1   (lib/psy.c:717)
+      const float base = l - work;                   // logmdct - work (lib/psy.c:722)
+      int dB = (int)((double)v + .5);
+      if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
+      if (dB < 0) dB = 0;
+      v = base + __ldg(P.noisecompand + dB);
+    }
     noise[i] = v;
   }
 }
 
-// _vp_noisemask (lib/psy.c:706-752): logmdct (smem) -> noise (smem); work: n floats.
+// _vp_noisemask (lib/psy.c:706-752): logmdct (smem) -> noise (smem).
 // If terms_done, the pass-1 terms were already written to S by the caller.
 __device__ __forceinline__ void dev_noisemask(const PsyDev &P, const float *logmdct, float *noise,
-                                              float *work, float *S, int ns, int tid, int nt,
+                                              float *S, int ns, int tid, int nt,
                                               int barid, bool terms_done) {
   const int n = P.n;
-  if (!terms_done) { dev_noise_terms(n, logmdct, 140.f, S, ns, tid, nt); group_sync(barid, nt); }
+  if (!terms_done) { dev_noise_terms(n, logmdct, nullptr, 140.f, S, ns, tid, nt); group_sync(barid, nt); }
   if (tid < 32) dev_noise_scan(n, S, ns, tid);
   group_sync(barid, nt);
-  dev_noise_regress(P, noise, 140.f, -1, S, ns, tid, nt);
+  dev_noise_regress(P, noise, 140.f, -1, S, ns, tid, nt, nullptr);
   group_sync(barid, nt);
-  for (int i = tid; i < n; i += nt) work[i] = logmdct[i] - noise[i];
-  group_sync(barid, nt);
-  dev_noise_terms(n, work, 0.f, S, ns, tid, nt);
+  dev_noise_terms(n, logmdct, noise, 0.f, S, ns, tid, nt);
   group_sync(barid, nt);
   if (tid < 32) dev_noise_scan(n, S, ns, tid);
   group_sync(barid, nt);
-  dev_noise_regress(P, noise, 0.f, P.noisewindowfixed, S, ns, tid, nt);
-  group_sync(barid, nt);
-  for (int i = tid; i < n; i += nt) {
-    const float base = logmdct[i] - work[i];
-    int dB = (int)((double)noise[i] + .5);
-    if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
-    if (dB < 0) dB = 0;
-    noise[i] = base + __ldg(P.noisecompand + dB);
-  }
+  dev_noise_regress(P, noise, 0.f, P.noisewindowfixed, S, ns, tid, nt, logmdct);
   group_sync(barid, nt);
 }
 
@@ -596,12 +600,11 @@ __device__ __forceinline__ void dev_noisemask(const PsyDev &P, const float *logm
 
 struct ToneSmem {
   float *seed;      // [total]
-  int   *pstk;      // [total]
   float *astk;      // [total]
+  short *pstk;      // [total]
   float *run_mx;    // [nruns]
-  int   *run_cofs;  // [nruns] offset of the chosen curve in tonecurves
-  int   *run_p01;   // [nruns] post0 | post1<<16   (1000|1000<<16 = inactive)
-  int   *rec;       // [total] positions of the chase's restart points
+  int   *run_info;  // [nruns] curve offset | post0<<16 | post1<<24  (post0==post1: inactive)
+  short *rec;       // [total] chase restart points; aliases run_mx/run_info (dead by then)
 };
 
 __device__ __forceinline__ float tone_att(const PsyDev &P, float lmax) {
@@ -619,16 +622,16 @@ __device__ __forceinline__ void dev_tone_runs(const PsyDev &P, const float *logf
     const int4 ri = __ldg(P.runinfo + r);            // lo, hi, oc - firstoc, band
     float mx = logfft[ri.x];
     for (int i = ri.x + 1; i <= ri.y; i++) { const float v = logfft[i]; if (v > mx) mx = v; }
-    int p01 = 1000 | (1000 << 16), cofs = 0;
+    int info = 0;
     if (mx + 6.f > __ldg(P.ath + ri.y) + att) {
       int choice = (int)((((double)(mx + dBoffset)) - 30.) * (double).1f);   // P_LEVEL_0 is a double
       if (choice < 0) choice = 0;
       if (choice > VB200_P_LEVELS - 1) choice = VB200_P_LEVELS - 1;
-      cofs = (ri.w * VB200_P_LEVELS + choice) * (VB200_EHMER_MAX + 2);
+      const int cofs = (ri.w * VB200_P_LEVELS + choice) * (VB200_EHMER_MAX + 2);
       const int post0 = (int)__ldg(P.tonecurves + cofs), post1 = (int)__ldg(P.tonecurves + cofs + 1);
-      p01 = post0 | (post1 << 16);
+      info = cofs | (post0 << 16) | (post1 << 24);
     }
-    T.run_mx[r] = mx; T.run_cofs[r] = cofs; T.run_p01[r] = p01;
+    T.run_mx[r] = mx; T.run_info[r] = info;
   }
 }
 
@@ -654,11 +657,11 @@ __device__ __forceinline__ void dev_tone_slots_scatter(const PsyDev &P, const To
     const int k = k0 + q;
     if (k < k1) {
       const int2 cr = __ldg(P.cls_run + k);          // run id, oc - firstoc
-      const int p01 = T.run_p01[cr.x];
-      const int post0 = p01 & 0xffff, post1 = p01 >> 16;
+      const int info = T.run_info[cr.x];
+      const int post0 = (info >> 16) & 0xff, post1 = (info >> 24) & 0xff;
       if (post0 < post1) {                           // active run
         const float mx = T.run_mx[cr.x];
-        const float *curve = P.tonecurves + T.run_cofs[cr.x] + 2;
+        const float *curve = P.tonecurves + (info & 0xffff) + 2;
         for (int i = post0 + g; i < post1; i += G) {
           const int sp = cr.y + (i - 16) * L - half;
           if (sp > 0 && sp < total) {
@@ -681,9 +684,9 @@ __device__ __forceinline__ void dev_tone_slots_gather(const PsyDev &P, const Ton
     for (int k = rg.x; k < rg.y; k++) {
       const int2 cr = __ldg(P.cls_run + k);          // run id, oc - firstoc
       const int i = ((s - cr.y + half) >> P.linesper_log2) + 16;
-      const int p01 = T.run_p01[cr.x];
-      if (i >= (p01 & 0xffff) && i < (p01 >> 16)) {
-        const float lin = T.run_mx[cr.x] + __ldg(P.tonecurves + T.run_cofs[cr.x] + 2 + i);
+      const int info = T.run_info[cr.x];
+      if (i >= ((info >> 16) & 0xff) && i < ((info >> 24) & 0xff)) {
+        const float lin = T.run_mx[cr.x] + __ldg(P.tonecurves + (info & 0xffff) + 2 + i);
         if (m < lin) m = lin;
       }
     }
@@ -714,7 +717,7 @@ __device__ __forceinline__ void dev_tone_slots(const PsyDev &P, const ToneSmem &
 __device__ __forceinline__ void dev_tone_chase_gather(const PsyDev &P, float *tone, float lmax,
                                                       const ToneSmem &T, int lane) {
   const int n = P.n, total = P.total, linesper = P.linesper;
-  float *seed = T.seed; int *pstk = T.pstk; float *astk = T.astk; int *rec = T.rec;
+  float *seed = T.seed; short *pstk = T.pstk; float *astk = T.astk; short *rec = T.rec;
   const unsigned full = 0xffffffffu;
   // 1. records
   int m = 0;
@@ -733,7 +736,7 @@ __device__ __forceinline__ void dev_tone_chase_gather(const PsyDev &P, float *to
       }
     }
     const unsigned b = __ballot_sync(full, r);
-    if (r) rec[m + __popc(b & ((1u << lane) - 1u))] = i;
+    if (r) rec[m + __popc(b & ((1u << lane) - 1u))] = (short)i;
     m += __popc(b);
   }
   __syncwarp();
@@ -760,7 +763,7 @@ __device__ __forceinline__ void dev_tone_chase_gather(const PsyDev &P, float *to
         }
       }
       if (i < end) {                         // i == end: only the pops belong to this lane
-        astk[start + stack] = s; pstk[start + stack] = i;
+        astk[start + stack] = s; pstk[start + stack] = (short)i;
         a2 = a1; l2 = l1; a1 = a0; l1 = l0; a0 = s; l0 = i + linesper;
         stack++;
         c = c < 3 ? c + 1 : 3;
