@@ -16,6 +16,7 @@
 #include "vb200_tables.h"
 #include "vb200_kernels.cuh"
 #include "vb200_cqn.cuh"
+#include "vb200_psy2.cuh"
 #include "floor1_db_table.h"
 
 using namespace vb200;
@@ -184,7 +185,9 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     d.cls_run = reinterpret_cast<const int2 *>(dc);
     d.slot_rng = reinterpret_cast<const int2 *>(ds);
     d.linesper_log2 = f.linesper_log2;
+    { const short *db = nullptr; if ((rc = upload(c, f.bin_grp.data(), f.bin_grp.size(), &db))) return rc; d.bin_grp = db; }
     if (p.eighth_octave_lines > 32) return fail(VB200_EIMPL, "eighth_octave_lines > 32");
+    if (p.total_octave_lines >= 2048) return fail(VB200_EIMPL, "total_octave_lines >= 2048");
     for (size_t k = 0; k < f.cls_off.size() && k < 33; k++) d.cls_off[k] = f.cls_off[k];
   }
   *out = c;
@@ -379,19 +382,6 @@ __global__ void k_ampmax(int mode, int nstreams, int bps, int ch, const vb200_bl
 
 // ---- Phase A, kernel 2: per (block, channel) logmdct, noise mask, tone mask, mix.
 // (second per-channel loop of mapping0_forward, lib/mapping0.c:366-470)
-struct PhaseA2Args {
-  const float *mdct_in;   // [rows][n] raw mdct
-  const float *logfft;    // [rows][n]
-  const float *lmax;      // [rows]
-  const float *gmax;      // [blocks]
-  const vb200_block_desc *desc;
-  float *mdct_out;        // [rows][n] (may alias mdct_in)
-  float *logmdct;         // [rows][n]
-  float *logmask;         // [rows][n]
-  float *ampmax_out;      // [blocks]
-  float *tap_noise, *tap_tone;
-  int dbg_skip;           // timing experiments only (VB200_DEBUG_SKIP); 0 in production
-};
 
 // shared-memory carve-up for the psy kernels (floats)
 struct PsySmem {
@@ -803,13 +793,54 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
     const PsyDev &P0 = c->dpsy[2 * W], &P1 = c->dpsy[2 * W + 1];
     const size_t smem = psy2_smem(P0, P1);
     int rc = set_smem(k_phaseA_psy, smem); if (rc) return rc;
+    {
+      // leave the rest of the 256 KB unified array to L1: the static psy tables (~60 KB per look)
+      // are read through it on every row
+      static int tuned = -1;
+      const char *e = getenv("VB200_PSY_CTAS");
+      const int ctas = e ? atoi(e) : c->psy_ctas_per_sm;
+      if (tuned != ctas) {
+        int pct = (int)((ctas * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+        CU(cudaFuncSetAttribute(k_phaseA_psy, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        tuned = ctas;
+      }
+      c->psy_ctas_per_sm = ctas;
+    }
     PhaseA2Args A;
     A.mdct_in = io->tap_mdct_raw ? io->tap_mdct_raw : io->mdct;
     A.logfft = d_logfft; A.lmax = d_lmax; A.gmax = d_gmax; A.desc = io->desc;
     A.mdct_out = io->mdct; A.logmdct = io->logmdct; A.logmask = io->logmask; A.ampmax_out = io->ampmax_out;
     A.tap_noise = io->tap_noise; A.tap_tone = io->tap_tone;
     { const char *e = getenv("VB200_DEBUG_SKIP"); A.dbg_skip = e ? atoi(e) : 0; }
-    k_phaseA_psy<<<grid_for(c, rows, c->psy_ctas_per_sm), PSY_THREADS, smem, st>>>(P0, P1, ch, rows, A);
+    const int n = N / 2;
+    const char *ev = getenv("VB200_PSY_V1");
+    const bool v2ok = !(ev && atoi(ev)) && (n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048);
+    if (v2ok) {
+      const int total = P0.total > P1.total ? P0.total : P1.total;
+      const int nruns = P0.nruns > P1.nruns ? P0.nruns : P1.nruns;
+      const int ngrp = P0.ngrp > P1.ngrp ? P0.ngrp : P1.ngrp;
+      const size_t smem2 = sizeof(float) * psy2_floats(n, total, nruns, ngrp);
+      int ctas = (int)((227 * 1024) / (smem2 + 1024));
+      if (ctas > 8) ctas = 8;
+      if (ctas < 1) ctas = 1;
+      { const char *e = getenv("VB200_PSY_CTAS"); if (e) ctas = atoi(e); }
+#define LAUNCH_PSY2(KK)                                                                            \
+      do {                                                                                         \
+        if ((rc = set_smem(k_phaseA_psy2<KK>, smem2))) return rc;                                  \
+        k_phaseA_psy2<KK><<<grid_for(c, rows, ctas), PSY2_THREADS, smem2, st>>>(P0, P1, ch, rows, A); \
+      } while (0)
+      switch (n / 128) {
+        case 1: LAUNCH_PSY2(1); break;
+        case 2: LAUNCH_PSY2(2); break;
+        case 4: LAUNCH_PSY2(4); break;
+        case 8: LAUNCH_PSY2(8); break;
+        default: LAUNCH_PSY2(16); break;
+      }
+#undef LAUNCH_PSY2
+    } else {
+      k_phaseA_psy<<<grid_for(c, rows, c->psy_ctas_per_sm), PSY_THREADS, smem, st>>>(P0, P1, ch, rows, A);
+    }
     rc = post_launch(c); if (rc) return rc;
   }
   if (c->profiling) CU(cudaEventRecord(c->ev[3], st));

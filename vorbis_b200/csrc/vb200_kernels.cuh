@@ -56,6 +56,7 @@ struct PsyDev {
   const int2  *cls_run;      // runs grouped by residue class, (run id, oc-firstoc), sorted by oc
   const int2  *slot_rng;     // [total] candidate range in cls_run for every seed slot
   int linesper_log2;
+  const short *bin_grp;      // [n] group of every bin (ngrp = the tail bins)
   int cls_off[33];           // class c owns cls_run[cls_off[c] .. cls_off[c+1])
 };
 
@@ -568,6 +569,50 @@ __device__ __forceinline__ void dev_noise_regress(const PsyDev &P, float *noise,
   }
 }
 
+// single-bin forms used by the register-resident kernel (vb200_psy2.cuh)
+__device__ __forceinline__ void dev_noise_term1(int i, float f, float offset, float *S, int ns) {
+  float *aN = S, *aX = S + ns, *aXX = S + 2 * ns, *aY = S + 3 * ns, *aXY = S + 4 * ns;
+  float y = f + offset;
+  if (y < 1.f) y = 1.f;
+  float w = y * y;
+  if (i == 0) {
+    w = w * .5f;
+    aN[0] = w; aX[0] = w; aXX[0] = 0.f; aY[0] = w * y; aXY[0] = 0.f;
+  } else {
+    const float x = (float)i;
+    const float wx = w * x;
+    aN[i] = w; aX[i] = wx; aXX[i] = wx * x; aY[i] = w * y; aXY[i] = wx * y;
+  }
+}
+
+__device__ __forceinline__ float dev_noise_regress1(const PsyDev &P, int i, float offset, int fixed,
+                                                    const float *S, int ns) {
+  const int bfe = P.bark_first_extra, ffe = P.fixed_first_extra;
+  Abd cur; cur.A = 0.f; cur.B = 0.f; cur.D = 1.f;
+  if (bfe > 0) {
+    const int wb = i < bfe ? i : bfe - 1;
+    const int bk = __ldg(P.bark + wb);
+    cur = dev_window_abd(bk >> 16, bk & 0xffff, S, ns);
+  }
+  const float x = (float)i;
+  float R = (cur.A + x * cur.B) / cur.D;
+  if (R < 0.f) R = 0.f;
+  float v = R - offset;
+  if (fixed > 0) {
+    if (ffe > 0) {
+      const int wb = i < ffe ? i : ffe - 1;
+      const int hi = wb + fixed / 2, lo = hi - fixed;
+      cur = dev_window_abd(lo, hi, S, ns);
+    } else if (bfe > 0 && i < bfe) {
+      const int bk = __ldg(P.bark + (bfe - 1));
+      cur = dev_window_abd(bk >> 16, bk & 0xffff, S, ns);
+    }
+    const float R2 = (cur.A + x * cur.B) / cur.D;
+    if (R2 - offset < v) v = R2 - offset;
+  }
+  return v;
+}
+
 // _vp_noisemask (lib/psy.c:706-752): logmdct (smem) -> noise (smem).
 // If terms_done, the pass-1 terms were already written to S by the caller.
 __device__ __forceinline__ void dev_noisemask(const PsyDev &P, const float *logmdct, float *noise,
@@ -603,7 +648,7 @@ struct ToneSmem {
   float *astk;      // [total]
   short *pstk;      // [total]
   float *run_mx;    // [nruns]
-  int   *run_info;  // [nruns] curve offset | post0<<16 | post1<<24  (post0==post1: inactive)
+  int   *run_info;  // [nruns] in cls_run order: curve idx | post0<<8 | post1<<14 | oc<<20
   short *rec;       // [total] chase restart points; aliases run_mx/run_info (dead by then)
 };
 
@@ -613,25 +658,31 @@ __device__ __forceinline__ float tone_att(const PsyDev &P, float lmax) {
   return att;
 }
 
-// seed_loop: one item per run of equal octave[] (peak, audibility gate, curve choice)
+// seed_loop: one item per run of equal octave[] (peak, audibility gate, curve choice).
+// Items are visited in residue-class order (cls_run) and their dynamic result is stored at
+// that index, so the scatter below walks shared memory only:
+//   run_mx[k]   = peak of the run
+//   run_info[k] = curve index (8 bits) | post0<<8 | post1<<14 | (oc-firstoc)<<20 ; post0==post1: inactive
 __device__ __forceinline__ void dev_tone_runs(const PsyDev &P, const float *logfft, float gmax, float lmax,
                                               const ToneSmem &T, int tid, int nt) {
   const float att = tone_att(P, lmax);
   const float dBoffset = P.max_curve_dB - gmax;
-  for (int r = tid; r < P.nruns; r += nt) {
-    const int4 ri = __ldg(P.runinfo + r);            // lo, hi, oc - firstoc, band
+  for (int k = tid; k < P.nruns; k += nt) {
+    const int2 cr = __ldg(P.cls_run + k);            // run id, oc - firstoc
+    const int4 ri = __ldg(P.runinfo + cr.x);         // lo, hi, oc - firstoc, band
     float mx = logfft[ri.x];
     for (int i = ri.x + 1; i <= ri.y; i++) { const float v = logfft[i]; if (v > mx) mx = v; }
-    int info = 0;
+    int info = ri.z << 20;
     if (mx + 6.f > __ldg(P.ath + ri.y) + att) {
       int choice = (int)((((double)(mx + dBoffset)) - 30.) * (double).1f);   // P_LEVEL_0 is a double
       if (choice < 0) choice = 0;
       if (choice > VB200_P_LEVELS - 1) choice = VB200_P_LEVELS - 1;
-      const int cofs = (ri.w * VB200_P_LEVELS + choice) * (VB200_EHMER_MAX + 2);
-      const int post0 = (int)__ldg(P.tonecurves + cofs), post1 = (int)__ldg(P.tonecurves + cofs + 1);
-      info = cofs | (post0 << 16) | (post1 << 24);
+      const int cidx = ri.w * VB200_P_LEVELS + choice;
+      const float *posts = P.tonecurves + cidx * (VB200_EHMER_MAX + 2);
+      const int post0 = (int)__ldg(posts), post1 = (int)__ldg(posts + 1);
+      info |= cidx | (post0 << 8) | (post1 << 14);
     }
-    T.run_mx[r] = mx; T.run_info[r] = info;
+    T.run_mx[k] = mx; T.run_info[k] = info;
   }
 }
 
@@ -653,25 +704,47 @@ __device__ __forceinline__ void dev_tone_slots_scatter(const PsyDev &P, const To
   const int wfirst = (tid & ~31) / G, wlast = ((tid | 31)) / G;
   int len = 0;
   for (int c = wfirst; c <= wlast; c++) { const int l = P.cls_off[c + 1] - P.cls_off[c]; if (l > len) len = l; }
-  for (int q = 0; q < len; q++) {
-    const int k = k0 + q;
-    if (k < k1) {
-      const int2 cr = __ldg(P.cls_run + k);          // run id, oc - firstoc
-      const int info = T.run_info[cr.x];
-      const int post0 = (info >> 16) & 0xff, post1 = (info >> 24) & 0xff;
-      if (post0 < post1) {                           // active run
-        const float mx = T.run_mx[cr.x];
-        const float *curve = P.tonecurves + (info & 0xffff) + 2;
-        for (int i = post0 + g; i < post1; i += G) {
-          const int sp = cr.y + (i - 16) * L - half;
-          if (sp > 0 && sp < total) {
-            const float lin = mx + __ldg(curve + i);
+  // four runs per trip: their curve values (the only global reads, L2-resident) are fetched
+  // together, then the four read-modify-writes happen in run order
+  constexpr int U = 4, PTS = 3;                      // PTS*G covers 48 of the <=56 points at G=16; rest looped
+  for (int q = 0; q < len; q += U) {
+    float mxs[U]; int sp0[U], cnt[U]; float cv[U][PTS]; const float *cptr[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int k = k0 + q + u;
+      cnt[u] = 0; sp0[u] = 0; mxs[u] = 0.f; cptr[u] = P.tonecurves;
+      if (k < k1) {
+        const int info = T.run_info[k];
+        const int post0 = (info >> 8) & 0x3f, post1 = (info >> 14) & 0x3f, oc = info >> 20;
+        mxs[u] = T.run_mx[k];
+        cptr[u] = P.tonecurves + (info & 0xff) * (VB200_EHMER_MAX + 2) + 2 + post0 + g;
+        cnt[u] = post1 - post0 - g;                  // points left for this lane, stride G
+        sp0[u] = oc + (post0 + g - 16) * L - half;
+      }
+#pragma unroll
+      for (int t = 0; t < PTS; t++) cv[u][t] = cnt[u] > t * G ? __ldg(cptr[u] + t * G) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (q + u < len) {
+#pragma unroll
+        for (int t = 0; t < PTS; t++) {
+          const int sp = sp0[u] + t * G * L;
+          if (cnt[u] > t * G && sp > 0 && sp < total) {
+            const float lin = mxs[u] + cv[u][t];
             if (T.seed[sp] < lin) T.seed[sp] = lin;
           }
         }
+        for (int t = PTS; cnt[u] > t * G; t++) {     // only when G < 28 (L > 4 with few lanes)
+          const int sp = sp0[u] + t * G * L;
+          if (sp > 0 && sp < total) {
+            const float lin = mxs[u] + __ldg(cptr[u] + t * G);
+            if (T.seed[sp] < lin) T.seed[sp] = lin;
+          }
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   }
 }
 
@@ -682,11 +755,10 @@ __device__ __forceinline__ void dev_tone_slots_gather(const PsyDev &P, const Ton
     float m = VB_NEGINF;
     const int2 rg = __ldg(P.slot_rng + s);           // candidate range in cls_run (empty for s == 0)
     for (int k = rg.x; k < rg.y; k++) {
-      const int2 cr = __ldg(P.cls_run + k);          // run id, oc - firstoc
-      const int i = ((s - cr.y + half) >> P.linesper_log2) + 16;
-      const int info = T.run_info[cr.x];
-      if (i >= ((info >> 16) & 0xff) && i < ((info >> 24) & 0xff)) {
-        const float lin = T.run_mx[cr.x] + __ldg(P.tonecurves + (info & 0xffff) + 2 + i);
+      const int info = T.run_info[k];                // class-order slot: curve, post0, post1, oc
+      const int i = ((s - (info >> 20) + half) >> P.linesper_log2) + 16;
+      if (i >= ((info >> 8) & 0x3f) && i < ((info >> 14) & 0x3f)) {
+        const float lin = T.run_mx[k] + __ldg(P.tonecurves + (info & 0xff) * (VB200_EHMER_MAX + 2) + 2 + i);
         if (m < lin) m = lin;
       }
     }

@@ -1,0 +1,252 @@
+// vb200_psy2.cuh — k_phaseA_psy2: the fused noise/tone/mix kernel, occupancy-first layout.
+//
+// Measured on B200 the psy stage is latency bound and its throughput scales with resident
+// CTAs, so this version minimises shared memory per (block,channel) row:
+//   * every per-bin value a thread needs twice (logmdct, first-pass noise) stays in
+//     registers: thread t owns bins t, t+128, ... in every per-bin phase;
+//   * the tone scratch (logfft copy, seeds, chase stacks, run records) is dead before the
+//     noise prefix sums start, so it aliases the 5x(n+4) prefix-sum area;
+//   * the tone curve is never materialised: bins read their group's minimum (grp_min).
+// => 5(n+4)+ngrp+1 floats (22 KB at n=1024) instead of 54 KB: 8-9 CTAs/SM instead of 4.
+// All phases use all 128 threads; seed_chase runs block-wide with the same exact
+// segmentation as dev_tone_chase_gather (restart points = strict records).
+#pragma once
+#include "vb200_kernels.cuh"
+
+namespace vb200 {
+
+struct PhaseA2Args {
+  const float *mdct_in;   // [rows][n] raw mdct
+  const float *logfft;    // [rows][n]
+  const float *lmax;      // [rows]
+  const float *gmax;      // [blocks]
+  const vb200_block_desc *desc;
+  float *mdct_out;        // [rows][n] (may alias mdct_in)
+  float *logmdct;         // [rows][n]
+  float *logmask;         // [rows][n]
+  float *ampmax_out;      // [blocks]
+  float *tap_noise, *tap_tone;
+  int dbg_skip;           // timing experiments only (VB200_DEBUG_SKIP); 0 in production
+};
+
+constexpr int PSY2_THREADS = 128;
+
+__host__ __device__ inline size_t psy2_floats(int n, int total, int nruns, int ngrp) {
+  const int tp = (total + 7) & ~7, rp = (nruns + 3) & ~3;
+  size_t tone = (size_t)n + 2 * (size_t)tp + tp / 2 + 2 * (size_t)rp;       // fft, seed, astk, pstk, runs
+  const size_t recs = (size_t)((((total + 3) / 4 + 31) & ~31) * 4 + 1) / 2 + 8;   // 4 chunks of shorts
+  if (2 * (size_t)rp < recs) tone += recs - 2 * (size_t)rp;
+  const size_t scan = 5 * (size_t)(n + 4);
+  return (scan > tone ? scan : tone) + (size_t)((ngrp + 1 + 3) & ~3) + 16;
+}
+
+// block-wide seed_chase (see dev_tone_chase_gather for the exactness argument)
+__device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem &T, int *s_misc,
+                                                int tid) {
+  const int total = P.total, linesper = P.linesper;
+  const int lane = tid & 31, warp = tid >> 5;
+  float *seed = T.seed; short *pstk = T.pstk; float *astk = T.astk; short *rec = T.rec;
+  const unsigned full = 0xffffffffu;
+  const int C = (((total + 3) >> 2) + 31) & ~31;          // positions per warp (multiple of 32)
+  // 1. records, in position order per warp chunk
+  int m = 0;
+  for (int base = warp * C; base < (warp + 1) * C && base < total; base += 32) {
+    const int i = base + lane;
+    bool r = false;
+    if (i < total) {
+      r = (i == 0);
+      if (!r) {
+        const float v = seed[i];
+        r = true;
+        for (int d = 1; d < linesper; d++) {
+          if (i - d < 0) break;
+          if (!(v > seed[i - d])) { r = false; break; }
+        }
+      }
+    }
+    const unsigned b = __ballot_sync(full, r);
+    if (r) rec[warp * C + m + __popc(b & ((1u << lane) - 1u))] = (short)i;
+    m += __popc(b);
+  }
+  if (lane == 0) s_misc[warp] = m;
+  __syncthreads();
+  const int m0 = s_misc[0], m1 = s_misc[1], m2 = s_misc[2], m3 = s_misc[3];
+  const int M = m0 + m1 + m2 + m3;
+  auto REC = [&](int g) -> int {
+    if (g < m0) return rec[g];
+    g -= m0; if (g < m1) return rec[C + g];
+    g -= m1; if (g < m2) return rec[2 * C + g];
+    return rec[3 * C + g - m2];
+  };
+  // 2. this thread's segment [start, end]
+  const int r0 = (tid * M) >> 7, r1 = ((tid + 1) * M) >> 7;
+  int start = 0, end = 0, cnt = 0;
+  if (r0 < r1) {
+    start = REC(r0);
+    end = r1 < M ? REC(r1) : total;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    int l0 = 0, l1 = 0, l2 = 0, c = 0, stack = 0;
+    float s = seed[start];
+    for (int i = start; i <= end && i < total; i++) {
+      const float snext = i + 1 < total ? seed[i + 1] : 0.f;
+      if (stack >= 2 && !(s < a0)) {
+        for (;;) {
+          if (c < 2) { a1 = astk[start + stack - 2]; l1 = pstk[start + stack - 2] + linesper; c = 2; }
+          if (!(i < l0 && a0 <= a1 && i < l1)) break;
+          stack--;
+          a0 = a1; l0 = l1; a1 = a2; l1 = l2; c--;
+          if (stack < 2 || s < a0) break;
+        }
+      }
+      if (i < end) {
+        astk[start + stack] = s; pstk[start + stack] = (short)i;
+        a2 = a1; l2 = l1; a1 = a0; l1 = l0; a0 = s; l0 = i + linesper;
+        stack++;
+        c = c < 3 ? c + 1 : 3;
+      }
+      s = snext;
+    }
+    cnt = stack;
+  }
+  __syncthreads();
+  // 3. fill: exclusive prefix-max of every thread's furthest endpos = its starting cursor
+  int Mx = 0;
+  for (int j = 0; j < cnt; j++) {
+    const float a = astk[start + j];
+    int endpos;
+    const int nx = j + 1 < cnt ? start + j + 1 : (end < total ? end : -1);
+    if (nx >= 0 && astk[nx] > a) endpos = pstk[nx];
+    else endpos = pstk[start + j] + linesper + 1;
+    if (endpos > total) endpos = total;
+    if (endpos > Mx) Mx = endpos;
+  }
+  int incl = Mx;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(full, incl, o);
+    if (lane >= o && t > incl) incl = t;
+  }
+  if (lane == 31) s_misc[4 + warp] = incl;
+  int cursor = __shfl_up_sync(full, incl, 1);
+  if (lane == 0) cursor = 0;
+  __syncthreads();
+  for (int w = 0; w < warp; w++) { const int t = s_misc[4 + w]; if (t > cursor) cursor = t; }
+  for (int j = 0; j < cnt; j++) {
+    const float a = astk[start + j];
+    int endpos;
+    const int nx = j + 1 < cnt ? start + j + 1 : (end < total ? end : -1);
+    if (nx >= 0 && astk[nx] > a) endpos = pstk[nx];
+    else endpos = pstk[start + j] + linesper + 1;
+    if (endpos > total) endpos = total;
+    for (int p = cursor; p < endpos; p++) seed[p] = a;
+    if (endpos > cursor) cursor = endpos;
+  }
+  __syncthreads();
+}
+
+template <int K>   // K = n / 128 bins per thread
+__global__ void __launch_bounds__(PSY2_THREADS, 8)
+k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int nt = PSY2_THREADS;
+  const int n = K * nt, ns = n + 4, tid = threadIdx.x, lane = tid & 31;
+  const int total = P0.total > P1.total ? P0.total : P1.total;
+  const int nruns = P0.nruns > P1.nruns ? P0.nruns : P1.nruns;
+  const int ngrp = P0.ngrp > P1.ngrp ? P0.ngrp : P1.ngrp;
+  const int tp = (total + 7) & ~7, rp = (nruns + 3) & ~3;
+  // carve: [ scan area | tone scratch (aliased) ] [ grp_min ] [ misc ]
+  float *S = sm;
+  float *s_fft = sm;
+  ToneSmem T;
+  T.seed = s_fft + n; T.astk = T.seed + tp; T.pstk = reinterpret_cast<short *>(T.astk + tp);
+  T.run_mx = T.astk + tp + tp / 2; T.run_info = reinterpret_cast<int *>(T.run_mx + rp);
+  T.rec = reinterpret_cast<short *>(T.run_mx);
+  const size_t area = psy2_floats(n, total, nruns, ngrp) - (size_t)((ngrp + 1 + 3) & ~3) - 16;
+  float *grp_min = sm + area;
+  int *s_misc = reinterpret_cast<int *>(grp_min + ((ngrp + 1 + 3) & ~3));
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int blk = row / ch;
+    const PsyDev &P = A.desc[blk].blocktype ? P1 : P0;
+    const float *gm = A.mdct_in + (size_t)row * n;
+    const float *lf = A.logfft + (size_t)row * n;
+    const float g = A.gmax[blk], lmax = A.lmax[row];
+    float L[K], M[K], p1[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int i = tid + k * nt;
+      M[k] = gm[i];
+      s_fft[i] = lf[i];
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      L[k] = add345(todB_dev(M[k]));                    // lib/mapping0.c:384-385
+      A.logmdct[(size_t)row * n + tid + k * nt] = L[k];
+    }
+    __syncthreads();
+    dev_tone_runs(P, s_fft, g, lmax, T, tid, nt);
+    __syncthreads();
+    dev_tone_slots(P, T, tid, nt);
+    __syncthreads();
+    dev_chase_block(P, T, s_misc, tid);
+    // max_seeds gather, first half: one minimum per static group (lib/psy.c:522-533)
+    for (int q = tid; q <= P.ngrp; q += nt) {
+      float minV;
+      if (q < P.ngrp) {
+        const int4 gg = __ldg(P.grps + q);
+        int pos = gg.x;
+        minV = T.seed[pos];
+        if (minV > P.tone_abs_limit) minV = P.tone_abs_limit;
+        while (pos < gg.y) {
+          pos++;
+          const float s = T.seed[pos];
+          if ((s > VB_NEGINF && s < minV) || minV == VB_NEGINF) minV = s;
+        }
+      } else {
+        minV = T.seed[P.total - 1];                    // tail bins (lib/psy.c:540-544)
+      }
+      grp_min[q] = minV;
+    }
+    __syncthreads();                                   // tone scratch is dead from here on
+    // ---- noise mask, pass 1 (offset 140, bark windows)
+#pragma unroll
+    for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k], 140.f, S, ns);
+    __syncthreads();
+    if (tid < 32) dev_noise_scan(n, S, ns, lane);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) p1[k] = dev_noise_regress1(P, tid + k * nt, 140.f, -1, S, ns);
+    __syncthreads();
+    // ---- pass 2 on logmdct - p1 (offset 0, bark + fixed windows)
+#pragma unroll
+    for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k] - p1[k], 0.f, S, ns);
+    __syncthreads();
+    if (tid < 32) dev_noise_scan(n, S, ns, lane);
+    __syncthreads();
+    const float att = tone_att(P, lmax);
+    const float *noff = P.noiseoffset + n;             // offset_select 1
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int i = tid + k * nt;
+      const float p2 = dev_noise_regress1(P, i, 0.f, P.noisewindowfixed, S, ns);
+      const float work = L[k] - p1[k];                 // lib/psy.c:717
+      const float base = L[k] - work;                  // lib/psy.c:722
+      int dB = (int)((double)p2 + .5);
+      if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
+      if (dB < 0) dB = 0;
+      const float nz = base + __ldg(P.noisecompand + dB);
+      float tn = __ldg(P.ath + i) + att;               // lib/psy.c:771, then max_seeds' flr update
+      const float mv = grp_min[__ldg(P.bin_grp + i)];
+      if (tn < mv) tn = mv;
+      float m = M[k];
+      const float lm = dev_mix_bin(P, 1, nz, tn, __ldg(noff + i), L[k], m);
+      A.logmask[(size_t)row * n + i] = lm;
+      A.mdct_out[(size_t)row * n + i] = m;
+      if (A.tap_noise) A.tap_noise[(size_t)row * n + i] = nz;
+      if (A.tap_tone) A.tap_tone[(size_t)row * n + i] = tn;
+    }
+    if (tid == 0 && (row % ch) == 0) A.ampmax_out[blk] = g;   // lib/mapping0.c:576
+    __syncthreads();
+  }
+}
+
+}  // namespace vb200

@@ -129,6 +129,7 @@ struct HostPsyFlow {
   std::vector<int> cls_off;                    // [L+1]
   std::vector<int> grp;                        // max_seeds groups: pos0,pos1,lin0,lin1 (lib/psy.c:522-538)
   int tail_lin0 = 0;
+  std::vector<short> bin_grp;                  // per bin: its max_seeds group, ngrp for the tail bins
   int bark_first_extra = 0;                    // first bin that reuses the last A,B,D (lib/psy.c:604-658)
   int fixed_first_extra = 0;                   // same for the fixed window (lib/psy.c:660-703)
 };
@@ -192,6 +193,10 @@ inline void build_psy_flow(HostPsyFlow &f, const vb200_psy_setup &s) {
       f.grp.push_back((int)linpos);
     }
     f.tail_lin0 = (int)linpos;
+    const int ng = (int)f.grp.size() / 4;
+    f.bin_grp.assign(n, (short)ng);
+    for (int gi = 0; gi < ng; gi++)
+      for (int i = f.grp[4 * gi + 2]; i < f.grp[4 * gi + 3]; i++) f.bin_grp[i] = (short)gi;
   }
   {
     int i = 0;
