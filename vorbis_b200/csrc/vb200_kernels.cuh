@@ -704,47 +704,43 @@ __device__ __forceinline__ void dev_tone_slots_scatter(const PsyDev &P, const To
   const int wfirst = (tid & ~31) / G, wlast = ((tid | 31)) / G;
   int len = 0;
   for (int c = wfirst; c <= wlast; c++) { const int l = P.cls_off[c + 1] - P.cls_off[c]; if (l > len) len = l; }
-  // four runs per trip: their curve values (the only global reads, L2-resident) are fetched
-  // together, then the four read-modify-writes happen in run order
-  constexpr int U = 4, PTS = 3;                      // PTS*G covers 48 of the <=56 points at G=16; rest looped
-  for (int q = 0; q < len; q += U) {
-    float mxs[U]; int sp0[U], cnt[U]; float cv[U][PTS]; const float *cptr[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int k = k0 + q + u;
-      cnt[u] = 0; sp0[u] = 0; mxs[u] = 0.f; cptr[u] = P.tonecurves;
-      if (k < k1) {
-        const int info = T.run_info[k];
-        const int post0 = (info >> 8) & 0x3f, post1 = (info >> 14) & 0x3f, oc = info >> 20;
-        mxs[u] = T.run_mx[k];
-        cptr[u] = P.tonecurves + (info & 0xff) * (VB200_EHMER_MAX + 2) + 2 + post0 + g;
-        cnt[u] = post1 - post0 - g;                  // points left for this lane, stride G
-        sp0[u] = oc + (post0 + g - 16) * L - half;
-      }
-#pragma unroll
-      for (int t = 0; t < PTS; t++) cv[u][t] = cnt[u] > t * G ? __ldg(cptr[u] + t * G) : 0.f;
+  const int GL = G * L;
+  // software pipeline: the next run's record and its first two curve values (the only global
+  // reads, L2 resident) are fetched while the current run is applied
+  float mx = 0.f, c0 = 0.f, c1 = 0.f;
+  int ext = 0, sp = 0;
+  const float *cptr = P.tonecurves;
+  auto fetch = [&](int k) {
+    ext = 0;
+    if (k < k1) {
+      const int info = T.run_info[k];
+      const int i0 = ((info >> 8) & 0x3f) + g;       // this lane's first curve point
+      ext = ((info >> 14) & 0x3f) - i0;              // > 0: points i0, i0+G, ... < post1
+      mx = T.run_mx[k];
+      cptr = P.tonecurves + (info & 0xff) * (VB200_EHMER_MAX + 2) + 2 + i0;
+      sp = (info >> 20) + (i0 - 16) * L - half;
+      if (ext > 0) c0 = __ldg(cptr);
+      if (ext > G) c1 = __ldg(cptr + G);
     }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (q + u < len) {
-#pragma unroll
-        for (int t = 0; t < PTS; t++) {
-          const int sp = sp0[u] + t * G * L;
-          if (cnt[u] > t * G && sp > 0 && sp < total) {
-            const float lin = mxs[u] + cv[u][t];
-            if (T.seed[sp] < lin) T.seed[sp] = lin;
-          }
+  };
+  fetch(k0);
+  for (int q = 0; q < len; q++) {
+    const float cmx = mx, cc0 = c0, cc1 = c1;
+    const int cext = ext, csp = sp;
+    const float *ccp = cptr;
+    fetch(k0 + q + 1);
+    if (cext > 0) {
+      if (csp > 0 && csp < total) T.seed[csp] = fmaxf(T.seed[csp], cmx + cc0);
+      if (cext > G) {
+        const int s1 = csp + GL;
+        if (s1 > 0 && s1 < total) T.seed[s1] = fmaxf(T.seed[s1], cmx + cc1);
+        for (int t = 2; cext > t * G; t++) {
+          const int st = csp + t * GL;
+          if (st > 0 && st < total) T.seed[st] = fmaxf(T.seed[st], cmx + __ldg(ccp + t * G));
         }
-        for (int t = PTS; cnt[u] > t * G; t++) {     // only when G < 28 (L > 4 with few lanes)
-          const int sp = sp0[u] + t * G * L;
-          if (sp > 0 && sp < total) {
-            const float lin = mxs[u] + __ldg(cptr[u] + t * G);
-            if (T.seed[sp] < lin) T.seed[sp] = lin;
-          }
-        }
-        __syncwarp();
       }
     }
+    __syncwarp();
   }
 }
 
@@ -795,16 +791,14 @@ __device__ __forceinline__ void dev_tone_chase_gather(const PsyDev &P, float *to
   int m = 0;
   for (int base = 0; base < total; base += 32) {
     const int i = base + lane;
-    bool r = false;
-    if (i < total) {
-      r = (i == 0);
-      if (!r) {
-        const float v = seed[i];
-        r = true;
-        for (int d = 1; d < linesper; d++) {
-          if (i - d < 0) break;
-          if (!(v > seed[i - d])) { r = false; break; }
-        }
+    // record <=> strictly greater than each of the previous linesper-1 seeds (branch free)
+    bool r = i < total;
+    {
+      const float v = r ? seed[i] : 0.f;
+      for (int d = 1; d < linesper; d++) {
+        const int j = i - d;
+        const float u = (r && j >= 0) ? seed[j] : 0.f;
+        r = r && (j < 0 || v > u);
       }
     }
     const unsigned b = __ballot_sync(full, r);

@@ -52,16 +52,14 @@ __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem 
   int m = 0;
   for (int base = warp * C; base < (warp + 1) * C && base < total; base += 32) {
     const int i = base + lane;
-    bool r = false;
-    if (i < total) {
-      r = (i == 0);
-      if (!r) {
-        const float v = seed[i];
-        r = true;
-        for (int d = 1; d < linesper; d++) {
-          if (i - d < 0) break;
-          if (!(v > seed[i - d])) { r = false; break; }
-        }
+    // record <=> strictly greater than each of the previous linesper-1 seeds (branch free)
+    bool r = i < total;
+    {
+      const float v = r ? seed[i] : 0.f;
+      for (int d = 1; d < linesper; d++) {
+        const int j = i - d;
+        const float u = (r && j >= 0) ? seed[j] : 0.f;
+        r = r && (j < 0 || v > u);
       }
     }
     const unsigned b = __ballot_sync(full, r);
