@@ -243,30 +243,32 @@ extern "C" int vb200_phaseA_kernel_ms(vb200_ctx *c, float *ms3) {
 
 // config 2: batched mdct_forward.  One CTA per vector (grid-stride), the vector
 // staged in shared memory with 128-bit coalesced loads.
+template <int NC>
 __global__ void __launch_bounds__(256)
 k_mdct_forward(XformDev X, int nvec, const float *__restrict__ in, float *__restrict__ out) {
   extern __shared__ __align__(16) float sm[];
-  const int N = X.N, tid = threadIdx.x, nt = blockDim.x;
+  const int N = NC ? NC : X.N, tid = threadIdx.x, nt = blockDim.x;
   float *sx = sm, *sw = sm + N;
   for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
     const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)v * N);
     for (int i = tid; i < (N >> 2); i += nt) reinterpret_cast<float4 *>(sx)[i] = __ldg(src + i);
     __syncthreads();
-    dev_mdct_forward(X, sx, sw, out + (size_t)v * (N >> 1), tid, nt);
+    dev_mdct_forward<NC>(X, sx, sw, out + (size_t)v * (N >> 1), tid, nt);
     __syncthreads();
   }
 }
 
+template <int NC>
 __global__ void __launch_bounds__(256)
 k_mdct_backward(XformDev X, int nvec, const float *__restrict__ in, float *__restrict__ out) {
   extern __shared__ __align__(16) float sm[];
-  const int N = X.N, n2 = N >> 1, tid = threadIdx.x, nt = blockDim.x;
+  const int N = NC ? NC : X.N, n2 = N >> 1, tid = threadIdx.x, nt = blockDim.x;
   float *sin_ = sm, *so = sm + n2;         // n2 coefficients, N outputs
   for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
     const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)v * n2);
     for (int i = tid; i < (n2 >> 2); i += nt) reinterpret_cast<float4 *>(sin_)[i] = __ldg(src + i);
     __syncthreads();
-    dev_mdct_backward(X, sin_, so, tid, nt);
+    dev_mdct_backward<NC>(X, sin_, so, tid, nt);
     float4 *dst = reinterpret_cast<float4 *>(out + (size_t)v * N);
     for (int i = tid; i < (N >> 2); i += nt) dst[i] = reinterpret_cast<float4 *>(so)[i];
     __syncthreads();
@@ -297,7 +299,7 @@ k_drft_forward(XformDev X, int nvec, float *__restrict__ data) {
     float4 *g = reinterpret_cast<float4 *>(data + (size_t)v * N);
     for (int i = tid; i < (N >> 2); i += nt) reinterpret_cast<float4 *>(sa)[i] = g[i];
     __syncthreads();
-    const float *r = dev_drft_forward(X, sa, sb, tid, nt);
+    const float *r = dev_drft_forward<0>(X, sa, sb, tid, nt);
     for (int i = tid; i < (N >> 2); i += nt) g[i] = reinterpret_cast<const float4 *>(r)[i];
     __syncthreads();
   }
@@ -306,13 +308,14 @@ k_drft_forward(XformDev X, int nvec, float *__restrict__ data) {
 // ---- Phase A, kernel 1: per (block, channel) window + MDCT + FFT + log spectrum.
 // Reads 4N bytes of PCM, writes mdct (2N), logfft (2N) and one local_ampmax.
 // (first per-channel loop of mapping0_forward, lib/mapping0.c:254-360)
+template <int NC>
 __global__ void __launch_bounds__(256)
 k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
                    const float *__restrict__ pcm, const vb200_block_desc *__restrict__ desc,
                    float *__restrict__ mdct, float *__restrict__ logfft, float *__restrict__ lmax) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float s_red[8];
-  const int N = X.N, n = N >> 1, tid = threadIdx.x, nt = blockDim.x;
+  const int N = NC ? NC : X.N, n = N >> 1, tid = threadIdx.x, nt = blockDim.x;
   float *sx = sm, *sw = sm + N, *sf = sm + 2 * N;
   const float scale = 4.f / (float)N;
   const float scale_dB = add345(todB_dev(scale));
@@ -321,8 +324,8 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
     const int lW = desc[blk].lW, nW = desc[blk].nW;
     dev_load_windowed(Wd, W, lW, nW, pcm + (size_t)row * N, sx, tid, nt);
     __syncthreads();
-    dev_mdct_forward(X, sx, sw, mdct + (size_t)row * n, tid, nt);
-    const float *f = dev_drft_forward(X, sx, sf, tid, nt);
+    dev_mdct_forward<NC>(X, sx, sw, mdct + (size_t)row * n, tid, nt);
+    const float *f = dev_drft_forward<NC>(X, sx, sf, tid, nt);
     // log spectrum + local maximum (lib/mapping0.c:310-345)
     float mx = -1e30f;
     float *lf = logfft + (size_t)row * n;
@@ -532,7 +535,7 @@ k_synthesis(XformDev X0, XformDev X1, WinDev Wd, int ch, int nstreams, int nblk,
       const float4 *src = reinterpret_cast<const float4 *>(coef + coef_off[(size_t)st * nblk + k] + (size_t)c * n2);
       for (int i = tid; i < (n2 >> 2); i += nt) reinterpret_cast<float4 *>(s_in)[i] = __ldg(src + i);
       __syncthreads();
-      dev_mdct_backward(X, s_in, s_out, tid, nt);
+      dev_mdct_backward<0>(X, s_in, s_out, tid, nt);
       if (k > 0) {
         float *dst = dst0 + pcm_off[(size_t)st * nblk + k];
         const float *R = s_prev, *Lh = s_out;
@@ -595,9 +598,22 @@ extern "C" int vb200_mdct_forward_dev(vb200_ctx *c, int W, int nvec, const float
   if (nvec <= 0) return 0;
   const XformDev &X = c->dx[W];
   const size_t smem = sizeof(float) * 2 * X.N;
-  int rc = set_smem(k_mdct_forward, smem); if (rc) return rc;
   const int nt = threads_for(X.N);
-  k_mdct_forward<<<grid_for(c, nvec, 8), nt, smem, (cudaStream_t)stream>>>(X, nvec, d_in, d_out);
+  const int grid = grid_for(c, nvec, 8);
+  int rc;
+#define LAUNCH_MF(NN)                                                                   \
+  do {                                                                                  \
+    if ((rc = set_smem(k_mdct_forward<NN>, smem))) return rc;                           \
+    k_mdct_forward<NN><<<grid, nt, smem, (cudaStream_t)stream>>>(X, nvec, d_in, d_out); \
+  } while (0)
+  switch (X.N) {
+    case 256: LAUNCH_MF(256); break;
+    case 512: LAUNCH_MF(512); break;
+    case 1024: LAUNCH_MF(1024); break;
+    case 2048: LAUNCH_MF(2048); break;
+    default: LAUNCH_MF(0); break;
+  }
+#undef LAUNCH_MF
   return post_launch(c);
 }
 
@@ -606,8 +622,21 @@ extern "C" int vb200_mdct_backward_dev(vb200_ctx *c, int W, int nvec, const floa
   if (nvec <= 0) return 0;
   const XformDev &X = c->dx[W];
   const size_t smem = sizeof(float) * (X.N + X.N / 2);
-  int rc = set_smem(k_mdct_backward, smem); if (rc) return rc;
-  k_mdct_backward<<<grid_for(c, nvec, 8), threads_for(X.N), smem, (cudaStream_t)stream>>>(X, nvec, d_in, d_out);
+  const int nt = threads_for(X.N), grid = grid_for(c, nvec, 8);
+  int rc;
+#define LAUNCH_MB(NN)                                                                    \
+  do {                                                                                   \
+    if ((rc = set_smem(k_mdct_backward<NN>, smem))) return rc;                           \
+    k_mdct_backward<NN><<<grid, nt, smem, (cudaStream_t)stream>>>(X, nvec, d_in, d_out); \
+  } while (0)
+  switch (X.N) {
+    case 256: LAUNCH_MB(256); break;
+    case 512: LAUNCH_MB(512); break;
+    case 1024: LAUNCH_MB(1024); break;
+    case 2048: LAUNCH_MB(2048); break;
+    default: LAUNCH_MB(0); break;
+  }
+#undef LAUNCH_MB
   return post_launch(c);
 }
 
@@ -771,10 +800,23 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
   if (c->profiling) CU(cudaEventRecord(c->ev[0], st));
   {
     const size_t smem = sizeof(float) * 3 * N;
-    int rc = set_smem(k_phaseA_transform, smem); if (rc) return rc;
+    int rc;
     float *mdct_raw = io->tap_mdct_raw ? io->tap_mdct_raw : io->mdct;
-    k_phaseA_transform<<<grid_for(c, rows, 8), threads_for(N), smem, st>>>(
-        X, c->dwin, W, ch, rows, io->pcm, io->desc, mdct_raw, d_logfft, d_lmax);
+    const int grid = grid_for(c, rows, 8), nt = threads_for(N);
+#define LAUNCH_XF(NN)                                                                        \
+    do {                                                                                     \
+      if ((rc = set_smem(k_phaseA_transform<NN>, smem))) return rc;                          \
+      k_phaseA_transform<NN><<<grid, nt, smem, st>>>(X, c->dwin, W, ch, rows, io->pcm, io->desc, \
+                                                     mdct_raw, d_logfft, d_lmax);            \
+    } while (0)
+    switch (N) {
+      case 256: LAUNCH_XF(256); break;
+      case 512: LAUNCH_XF(512); break;
+      case 1024: LAUNCH_XF(1024); break;
+      case 2048: LAUNCH_XF(2048); break;
+      default: LAUNCH_XF(0); break;
+    }
+#undef LAUNCH_XF
     rc = post_launch(c); if (rc) return rc;
   }
   if (c->profiling) CU(cudaEventRecord(c->ev[1], st));

@@ -81,13 +81,24 @@ __device__ __forceinline__ float warp_max(float v) {
 // mdct_butterflies (lib/mdct.c:316-336): radix-2 stages (butterfly_first /
 // butterfly_generic, :216-314) then the fixed 32/16/8-point flies (:93-214),
 // each level spread over all threads: level L has N/8 independent items.
+// NC = block size as a compile-time constant (0: read it from X at run time).  With NC known
+// every loop bound, shift and FFT pass shape below folds to a constant and the stage loops unroll.
+template <int NC> struct XLog2 { static constexpr int v = 1 + XLog2<NC / 2>::v; };
+template <> struct XLog2<1> { static constexpr int v = 0; };
+template <> struct XLog2<0> { static constexpr int v = 0; };
+
+template <int NC>
 __device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int tid, int nt) {
-  const int n2 = X.N >> 1;
+  const int N = NC ? NC : X.N;
+  const int log2n = NC ? XLog2<NC>::v : X.log2n;
+  const int nst = log2n - 6;
+  const int n2 = N >> 1;
   const int items = n2 >> 2;
-  for (int s = 0; s < X.nst; s++) {
+#pragma unroll
+  for (int s = 0; s < nst; s++) {
     const int P = n2 >> s;
     const int lq = P >> 2;                       // items per sub-block (power of two)
-    const int sh = X.log2n - 3 - s;              // log2(lq)
+    const int sh = log2n - 3 - s;                // log2(lq)
     const float2 *tw = X.stage_tw + X.stage_off[s];
     for (int u = tid; u < items; u += nt) {
       const int blk = u >> sh, q = u & (lq - 1);
@@ -166,8 +177,9 @@ __device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int
 
 // mdct_bitreverse (lib/mdct.c:346-394): item m reads two complex values of the
 // upper half w[n2..N) through bitrev[] and writes four values of w[0..n2).
+template <int NC>
 __device__ __forceinline__ void dev_bitreverse(const XformDev &X, float *w, int tid, int nt) {
-  const int N = X.N, n2 = N >> 1;
+  const int N = NC ? NC : X.N, n2 = N >> 1;
   const float2 *T = reinterpret_cast<const float2 *>(X.trig + N);
   const int2 *br = reinterpret_cast<const int2 *>(X.bitrev);
   const float *x = w + n2;
@@ -191,9 +203,10 @@ __device__ __forceinline__ void dev_bitreverse(const XformDev &X, float *w, int 
 // Forward MDCT of the N samples at `in` (shared memory, read-only) using the N
 // floats of scratch at `w`; writes N/2 coefficients to `out` (global or shared).
 // mdct_forward, lib/mdct.c:492-562.
+template <int NC>
 __device__ __forceinline__ void dev_mdct_forward(const XformDev &X, const float *in, float *w,
                                                  float *out, int tid, int nt) {
-  const int N = X.N, n2 = N >> 1, n4 = N >> 2, n16 = N >> 4;
+  const int N = NC ? NC : X.N, n2 = N >> 1, n4 = N >> 2, n16 = N >> 4;
   float *w2 = w + n2;
   const float2 *Tf = reinterpret_cast<const float2 *>(X.trig);
   for (int p = tid; p < n4; p += nt) {
@@ -219,8 +232,8 @@ __device__ __forceinline__ void dev_mdct_forward(const XformDev &X, const float 
     *reinterpret_cast<float2 *>(w2 + 2 * p) = make_float2(r1 * t.y + r0 * t.x, r1 * t.x - r0 * t.y);
   }
   __syncthreads();
-  dev_butterflies(X, w2, tid, nt);
-  dev_bitreverse(X, w, tid, nt);
+  dev_butterflies<NC>(X, w2, tid, nt);
+  dev_bitreverse<NC>(X, w, tid, nt);
   const float2 *Tp = reinterpret_cast<const float2 *>(X.trig + n2);
   const float scale = X.scale;
   for (int i = tid; i < n4; i += nt) {
@@ -234,9 +247,10 @@ __device__ __forceinline__ void dev_mdct_forward(const XformDev &X, const float 
 // Inverse MDCT: N/2 coefficients at `in` (shared or global, read-only) -> N
 // samples in the shared buffer `out` (N floats).  mdct_backward, lib/mdct.c:396-490.
 // The result layout is [A | -rev(A) | rev(B) | B].
+template <int NC>
 __device__ __forceinline__ void dev_mdct_backward(const XformDev &X, const float *in, float *out,
                                                   int tid, int nt) {
-  const int N = X.N, n2 = N >> 1, n4 = N >> 2, n16 = N >> 4;
+  const int N = NC ? NC : X.N, n2 = N >> 1, n4 = N >> 2, n16 = N >> 4;
   const float *T = X.trig;
   for (int u = tid; u < 2 * n16; u += nt) {
     if (u < n16) {
@@ -262,8 +276,8 @@ __device__ __forceinline__ void dev_mdct_backward(const XformDev &X, const float
     }
   }
   __syncthreads();
-  dev_butterflies(X, out + n2, tid, nt);
-  dev_bitreverse(X, out, tid, nt);
+  dev_butterflies<NC>(X, out + n2, tid, nt);
+  dev_bitreverse<NC>(X, out, tid, nt);
   const float2 *Tp = reinterpret_cast<const float2 *>(X.trig + n2);
   // item k: A[n4-1-k] = re*T1 - im*T0, B[k] = -(re*T0 + im*T1)
   for (int k = tid; k < n4; k += nt) {
@@ -307,10 +321,11 @@ __device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, 
     return;
   }
   const int half = ido >> 1;                         // power of two
+  const int hsh = 31 - __clz(half);
   const int items = l1 * half;
   for (int v = tid; v < items + l1; v += nt) {
     if (v < items) {
-      const int k = v / half, ii = v - k * half;
+      const int k = v >> hsh, ii = v & (half - 1);
       const float *c0 = cc + k * ido, *c1 = c0 + t0, *c2 = c1 + t0, *c3 = c2 + t0;
       float *o = ch + 4 * k * ido;
       if (ii == 0) {
@@ -367,10 +382,11 @@ __device__ __forceinline__ void dev_fft_pass2(int ido, int l1, const float *cc, 
     return;
   }
   const int half = ido >> 1;
+  const int hsh = 31 - __clz(half);
   const int items = l1 * half;
   for (int v = tid; v < items + l1; v += nt) {
     if (v < items) {
-      const int k = v / half, ii = v - k * half;
+      const int k = v >> hsh, ii = v & (half - 1);
       const float *c0 = cc + k * ido, *c1 = c0 + t0;
       float *o = ch + 2 * k * ido;
       if (ii == 0) {
@@ -396,13 +412,19 @@ __device__ __forceinline__ void dev_fft_pass2(int ido, int l1, const float *cc, 
 }
 
 // Returns the buffer (a or b) that holds the transform of the data in `a`.
+template <int NC>
 __device__ __forceinline__ float *dev_drft_forward(const XformDev &X, float *a, float *b,
                                                    int tid, int nt) {
-  const int N = X.N, nf = X.nf;
+  const int N = NC ? NC : X.N;
+  // power-of-two N: drfti1 stores 4,..,4 with a single 2 (odd log2) moved to the front, and the
+  // passes run last factor first: radix 4 throughout, the radix-2 pass (if any) comes last
+  const int log2n = NC ? XLog2<NC>::v : X.log2n;
+  const int nf = (log2n + 1) >> 1;
   int l2 = N, iw = N;
   float *src = a, *dst = b;
+#pragma unroll
   for (int k1 = 0; k1 < nf; k1++) {
-    const int ip = X.fac[nf - 1 - k1];
+    const int ip = (k1 == nf - 1 && (log2n & 1)) ? 2 : 4;
     const int l1 = l2 / ip, ido = N / l2;
     iw -= (ip - 1) * ido;
     if (ip == 4)
