@@ -191,6 +191,58 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def extra_configs(torch, lib, abi, device, peak):
+    """BASELINE configs[1] (batched mdct_forward N=1024 x 65536) and configs[3] (decode: IMDCT +
+    overlap-add, mixed 256/2048 blocks), device resident, CUDA events.  Informational."""
+    out = {}
+    dev = torch.device("cuda", device)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # config 2: mdct_init(1024), 65536 vectors uniform(-1,1)
+    s22 = abi.SetupHolder.load(os.path.join(GOLD, "setup_22k_mono_q3.npz"))
+    c22 = lib.Context(s22, device=device)
+    N = s22.blocksize(1)
+    nv = 65536
+    g = torch.Generator(device=dev); g.manual_seed(12345)
+    x = torch.rand((nv, N), generator=g, device=dev) * 2 - 1
+    y = torch.empty((nv, N // 2), device=dev)
+    ms = timed(lambda: c22.mdct_forward_dev(1, nv, x.data_ptr(), y.data_ptr(), stream))
+    out["mdct_forward_N1024_x65536"] = {"ms": ms, "transforms_per_s": nv / ms * 1e3,
+                                         "algorithmic_GBps": 6 * N * nv / ms / 1e6,
+                                         "frac_of_hbm_peak": 6 * N * nv / ms / 1e6 / peak}
+    c22.close()
+    # config 4: decode, 4096 stereo streams x 33 blocks, one run of 8 short blocks per 24 long
+    s44 = abi.SetupHolder.load(os.path.join(GOLD, "setup_44k_stereo_q5.npz"))
+    c44 = lib.Context(s44, device=device)
+    bs = [s44.blocksize(0), s44.blocksize(1)]
+    ns, nblk = 4096, 33
+    Wrow = np.ones(nblk, np.int32); Wrow[12:20] = 0
+    Wseq = np.tile(Wrow, (ns, 1))
+    coef_off, pcm_off, coef_len, pcm_len = lib.synthesis_layout(Wseq, bs, s44.channels)
+    coef = (torch.rand(coef_len, generator=g, device=dev) * 2 - 1) * 1e-2
+    pcm = torch.zeros((ns, s44.channels, pcm_len), device=dev)
+    dW = torch.from_numpy(Wseq).to(dev); dco = torch.from_numpy(coef_off).to(dev); dpo = torch.from_numpy(pcm_off).to(dev)
+    ms = timed(lambda: c44.synthesis_dev(ns, nblk, dW.data_ptr(), dco.data_ptr(), coef.data_ptr(), dpo.data_ptr(),
+                                         pcm.data_ptr(), pcm_len, stream))
+    byts = 4 * (coef_len + ns * s44.channels * pcm_len)
+    out["decode_4096streams_x33blocks_mixed"] = {"ms": ms, "stereo_blocks_per_s": ns * nblk / ms * 1e3,
+                                                  "algorithmic_GBps": byts / ms / 1e6,
+                                                  "frac_of_hbm_peak": byts / ms / 1e6 / peak}
+    c44.close()
+    return out
+
+
 def run_ours(args):
     import torch
     from vorbis_b200 import abi, lib
@@ -273,8 +325,17 @@ def run_ours(args):
         alg = [8 * N, 0, 10 * N]
         dom = int(np.argmax(kms))
         achieved = alg[dom] * ch * nb / (kms[dom] * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per
+        # (block,channel) row, profiles/summary.json), scaled to this launch
+        traffic = None
+        try:
+            summ = json.load(open(os.path.join(ROOT, "profiles", "summary.json")))
+            per_row = summ["kernels"][names[dom]]["dram_bytes_per_row"]
+            traffic = per_row * ch * nb
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": {k: float(v) for k, v in zip(names, kms)},
                 "phaseA_algorithmic_GBps": 10 * N * ch * nb / (kms.sum() * 1e-3) / 1e9}
 
@@ -316,6 +377,13 @@ def run_ours(args):
         cpu = {"value": rate_c, "unit": UNIT, "cores": used, "kind": kind,
                "sample": "%d long stereo blocks (%d per thread)" % (nb_c, args.ref_blocks_per_core)}
 
+        extra = None
+        if not args.no_extra:
+            try:
+                extra = extra_configs(torch, lib, abi, local, peak)
+            except Exception as e:  # the headline line must still be printed
+                extra = {"error": repr(e)}
+
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -324,6 +392,7 @@ def run_ours(args):
                        "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (18 * N * ch * nb / 1e9),
                        "sharding": "independent blocks per rank, no collective"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:
@@ -338,7 +407,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks", type=int, default=100000, help="stereo blocks per GPU per step")
-    ap.add_argument("--e2e-blocks", type=int, default=20000)
+    ap.add_argument("--e2e-blocks", type=int, default=50000)
+    ap.add_argument("--no-extra", action="store_true", help="skip the informational configs 2/4")
     ap.add_argument("--ref-blocks-per-core", type=int, default=512)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -225,3 +225,22 @@ def test_decode_vs_oracle_random_streams(cfg):
     # a single block finishes nothing
     one = ctx.synthesis(Wseq[:, :1], coef_off[:, :1], coef, pcm_off[:, :1], 8)
     assert not one.any()
+
+
+def test_phaseA_host_path_multichunk(cfg, monkeypatch):
+    """the pipelined two-lane host path (chunks alternate between two streams) == single chunk"""
+    name, setup, ctx, o, enc, _ = cfg
+    W = 0
+    N, ch = setup.blocksize(W), setup.channels
+    rng = np.random.default_rng(5)
+    nb = 45
+    pcm = rng.uniform(-0.7, 0.7, (nb, ch, N)).astype(np.float32)
+    desc = np.zeros(nb, abi.BLOCKDESC_DTYPE)
+    desc["blocktype"] = rng.integers(0, 2, nb)
+    desc["ampmax"] = -12.0
+    monkeypatch.setenv("VB200_CHUNK_BLOCKS", "7")
+    a = ctx.phaseA(W, pcm, desc)
+    monkeypatch.delenv("VB200_CHUNK_BLOCKS")
+    b = o.phaseA(W, pcm, desc)
+    for k in ("mdct", "logmdct", "logmask", "ampmax_out"):
+        assert_bits_equal(a[k], b[k], "chunked " + k)

@@ -58,6 +58,8 @@ struct vb200_ctx {
   std::atomic<uint64_t> launches{0};
   // grow-only scratch for the host-buffer entry points and phase A intermediates
   DevBuf scratch[16];
+  DevBuf lane_buf[2][10];            // per-lane device buffers of the pipelined host Phase-A path
+  cudaStream_t s_lane[2] = {nullptr, nullptr};
   int psy_ctas_per_sm = 5;
   const float *d_fromdB = nullptr;
   const int *d_mag[2] = {nullptr, nullptr}, *d_ang[2] = {nullptr, nullptr};
@@ -118,6 +120,7 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
   CU(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
+  for (auto &st : c->s_lane) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
 
   for (int w = 0; w < 2; w++) {
     HostXform &h = c->hx[w];
@@ -199,6 +202,8 @@ extern "C" void vb200_ctx_destroy(vb200_ctx *c) {
   cudaSetDevice(c->device);
   for (void *p : c->owned) cudaFree(p);
   for (auto &b : c->scratch) if (b.p) cudaFree(b.p);
+  for (auto &l : c->lane_buf) for (auto &b : l) if (b.p) cudaFree(b.p);
+  for (auto &st : c->s_lane) if (st) cudaStreamDestroy(st);
   if (c->s_main) cudaStreamDestroy(c->s_main);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   delete c;
@@ -889,6 +894,17 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
   return 0;
 }
 
+static int ensure_buf(DevBuf &b, size_t bytes, void **out) {
+  if (b.cap < bytes) {
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    CU(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+  }
+  *out = b.p;
+  return 0;
+}
+
 static int phaseA_dev_common(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io,
                              int nstreams, int bps, const float *d_amp0, void *stream) {
   CHECK_CTX(c); CHECK_W(W);
@@ -915,11 +931,59 @@ extern "C" int vb200_analysis_phaseA_streams_dev(vb200_ctx *c, int W, int nstrea
   return phaseA_dev_common(c, W, nstreams * bps, io, nstreams, bps, d_amp0, stream);
 }
 
+// Host-buffer Phase A.  Without taps the batch is cut into chunks that alternate between two
+// lanes (stream + device buffers each): while one lane computes, the other lane's H2D / D2H
+// copies run on the copy engines.  Pinned host memory is needed for the copies to be truly
+// asynchronous (pageable memory still works, staged by the driver).
+static int phaseA_host_pipelined(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *h) {
+  const int ch = c->setup.channels, N = c->dx[W].N, n = N / 2;
+  int chunk = 4096;
+  { const char *e = getenv("VB200_CHUNK_BLOCKS"); if (e && atoi(e) > 0) chunk = atoi(e); }
+  if (chunk > nblocks) chunk = nblocks;
+  const size_t crow = (size_t)chunk * ch;
+  int rc;
+  for (int L = 0; L < 2; L++) {
+    void *p;
+    const size_t sz[9] = {sizeof(float) * crow * N, sizeof(vb200_block_desc) * (size_t)chunk,
+                          sizeof(float) * crow * n, sizeof(float) * crow * n, sizeof(float) * crow * n,
+                          sizeof(float) * (size_t)chunk, sizeof(float) * crow * n, sizeof(float) * crow,
+                          sizeof(float) * (size_t)chunk};
+    for (int k = 0; k < 9; k++) if ((rc = ensure_buf(c->lane_buf[L][k], sz[k], &p))) return rc;
+  }
+  for (int b0 = 0, it = 0; b0 < nblocks; b0 += chunk, it++) {
+    const int L = it & 1, nb = nblocks - b0 < chunk ? nblocks - b0 : chunk;
+    const size_t rows = (size_t)nb * ch, r0 = (size_t)b0 * ch;
+    cudaStream_t st = c->s_lane[L];
+    DevBuf *B = c->lane_buf[L];
+    CU(cudaMemcpyAsync(B[0].p, h->pcm + r0 * N, sizeof(float) * rows * N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B[1].p, h->desc + b0, sizeof(vb200_block_desc) * nb, cudaMemcpyHostToDevice, st));
+    vb200_phaseA_io d;
+    memset(&d, 0, sizeof(d));
+    d.pcm = (const float *)B[0].p; d.desc = (const vb200_block_desc *)B[1].p;
+    d.mdct = (float *)B[2].p; d.logmdct = (float *)B[3].p; d.logmask = (float *)B[4].p;
+    d.ampmax_out = (float *)B[5].p;
+    if ((rc = phaseA_launch(c, W, nb, &d, 0, 0, nullptr, st, (float *)B[6].p, (float *)B[7].p, (float *)B[8].p)))
+      return rc;
+    CU(cudaMemcpyAsync(h->mdct + r0 * n, d.mdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->logmdct + r0 * n, d.logmdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->logmask + r0 * n, d.logmask, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->ampmax_out + b0, d.ampmax_out, sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(c->s_lane[0]));
+  CU(cudaStreamSynchronize(c->s_lane[1]));
+  return 0;
+}
+
 extern "C" int vb200_analysis_phaseA(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *h) {
   CHECK_CTX(c); CHECK_W(W);
   if (!h) return fail(VB200_EINVAL, "null io");
+  if (c->n_psy != 4) return fail(VB200_EIMPL, "context has no psy lookups");
+  if (!h->pcm || !h->desc || !h->mdct || !h->logmdct || !h->logmask || !h->ampmax_out)
+    return fail(VB200_EINVAL, "phase A io pointers");
   if (nblocks <= 0) return 0;
   std::lock_guard<std::mutex> lk(c->mu);
+  if (!h->tap_noise && !h->tap_tone && !h->tap_logfft && !h->tap_mdct_raw && !c->profiling)
+    return phaseA_host_pipelined(c, W, nblocks, h);
   const int ch = c->setup.channels, N = c->dx[W].N, n = N / 2;
   const size_t rows = (size_t)nblocks * ch;
   HostIO io{c};
@@ -932,7 +996,6 @@ extern "C" int vb200_analysis_phaseA(vb200_ctx *c, int W, int nblocks, const vb2
   if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.logmdct = (float *)p;
   if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.logmask = (float *)p;
   if ((rc = io.h2d(nullptr, sizeof(float) * nblocks, &p))) return rc; d.ampmax_out = (float *)p;
-  // optional taps share one extra slot each
   if (h->tap_noise) { if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.tap_noise = (float *)p; }
   if (h->tap_tone) { if ((rc = io.h2d(nullptr, sizeof(float) * rows * n, &p))) return rc; d.tap_tone = (float *)p; }
   if (h->tap_logfft) { if ((rc = ensure(c, 11, sizeof(float) * rows * n, &p))) return rc; d.tap_logfft = (float *)p; }
