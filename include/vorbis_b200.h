@@ -125,6 +125,9 @@ uint64_t vb200_launch_count(vb200_ctx *ctx);
  * vb200_phaseA_kernel_ms returns the durations of the last call (ms3[3]).       */
 int  vb200_set_profiling(vb200_ctx *ctx, int on);
 int  vb200_phaseA_kernel_ms(vb200_ctx *ctx, float *ms3);
+/* development aid: with env VB200_PHASE_TIMING set, the psy kernel adds the SM cycles each of
+ * its 11 barrier-delimited phases took (thread 0 of every CTA) into a 16-slot counter array. */
+int  vb200_debug_phase_cycles(vb200_ctx *ctx, unsigned long long *out16, int reset);
 
 /* ---- transforms ------------------------------------- */
 /* mdct_forward, lib/mdct.c:492: in [nvec][N] -> out [nvec][N/2]            */

@@ -191,7 +191,7 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     { const short *db = nullptr; if ((rc = upload(c, f.bin_grp.data(), f.bin_grp.size(), &db))) return rc; d.bin_grp = db; }
     if (p.eighth_octave_lines > 32) return fail(VB200_EIMPL, "eighth_octave_lines > 32");
     if (p.total_octave_lines >= 2048) return fail(VB200_EIMPL, "total_octave_lines >= 2048");
-    for (size_t k = 0; k < f.cls_off.size() && k < 33; k++) d.cls_off[k] = f.cls_off[k];
+    { const int *dco = nullptr; if ((rc = upload(c, f.cls_off.data(), f.cls_off.size(), &dco))) return rc; d.cls_off = dco; }
   }
   *out = c;
   return 0;
@@ -232,6 +232,18 @@ extern "C" int vb200_set_profiling(vb200_ctx *c, int on) {
   CU(cudaSetDevice(c->device));
   if (on) for (auto &e : c->ev) if (!e) CU(cudaEventCreate(&e));
   c->profiling = on != 0;
+  return 0;
+}
+
+// dev aid: per-phase cycle sums of k_phaseA_psy2 accumulated while VB200_PHASE_TIMING is set
+extern "C" int vb200_debug_phase_cycles(vb200_ctx *c, unsigned long long *out16, int reset) {
+  if (!c || !out16) return fail(VB200_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  void *p; int rc;
+  if ((rc = ensure(c, 10, 16 * sizeof(unsigned long long), &p))) return rc;
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out16, p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CU(cudaMemset(p, 0, 16 * sizeof(unsigned long long)));
   return 0;
 }
 
@@ -398,7 +410,7 @@ struct PsySmem {
 };
 __host__ __device__ inline size_t psy_smem_floats(int n, int total, int nruns) {
   const int tp = (total + 7) & ~7, rp = (nruns + 3) & ~3;
-  size_t runs = 2 * (size_t)rp;                      // run_mx + run_info, also hosts rec (tp shorts)
+  size_t runs = 4 * (size_t)rp;                      // run_rec (int4), also hosts rec (tp shorts)
   if (runs < (size_t)tp / 2) runs = tp / 2;
   return (size_t)3 * n + 5 * (size_t)(n + 4) + 2 * (size_t)tp + tp / 2 + runs;
 }
@@ -410,9 +422,9 @@ __device__ __forceinline__ PsySmem psy_carve(float *sm, int n, int total, int nr
   s.T.seed = s.fft + n;
   s.T.astk = s.T.seed + tp;
   s.T.pstk = reinterpret_cast<short *>(s.T.astk + tp);
-  s.T.run_mx = s.T.astk + tp + tp / 2;
-  s.T.run_info = reinterpret_cast<int *>(s.T.run_mx + rp);
-  s.T.rec = reinterpret_cast<short *>(s.T.run_mx);
+  s.T.run_rec = reinterpret_cast<int4 *>(s.T.astk + tp + tp / 2);
+  s.T.rec = reinterpret_cast<short *>(s.T.run_rec);
+  (void)rp;
   return s;
 }
 
@@ -860,6 +872,11 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
     A.mdct_out = io->mdct; A.logmdct = io->logmdct; A.logmask = io->logmask; A.ampmax_out = io->ampmax_out;
     A.tap_noise = io->tap_noise; A.tap_tone = io->tap_tone;
     { const char *e = getenv("VB200_DEBUG_SKIP"); A.dbg_skip = e ? atoi(e) : 0; }
+    A.dbg_cycles = nullptr;
+    if (getenv("VB200_PHASE_TIMING")) {
+      void *p; if ((rc = ensure(c, 10, 16 * sizeof(unsigned long long), &p))) return rc;
+      A.dbg_cycles = (unsigned long long *)p;
+    }
     const int n = N / 2;
     const char *ev = getenv("VB200_PSY_V1");
     const bool v2ok = !(ev && atoi(ev)) && (n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048);

@@ -57,7 +57,7 @@ struct PsyDev {
   const int2  *slot_rng;     // [total] candidate range in cls_run for every seed slot
   int linesper_log2;
   const short *bin_grp;      // [n] group of every bin (ngrp = the tail bins)
-  int cls_off[33];           // class c owns cls_run[cls_off[c] .. cls_off[c+1])
+  const int *cls_off;        // [L+1] (device) class c owns cls_run[cls_off[c] .. cls_off[c+1])
 };
 
 // ------------------------------------------------------------------------
@@ -68,6 +68,15 @@ __device__ __forceinline__ float todB_dev(float x) {           // lib/scales.h:4
 __device__ __forceinline__ float add345(float x) {             // "+ .345" is a double add
   return (float)((double)x + .345);
 }
+
+// 32-bit shared-window addressing: one cvta per array, then ld/st.shared with register offsets
+// (keeps the compiler from re-deriving the shared base inside predicated hot loops)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s16(unsigned a) { short v; asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(a)); return (int)v; }
+__device__ __forceinline__ void sts_s16(unsigned a, int v) { asm volatile("st.shared.s16 [%0], %1;" :: "r"(a), "h"((short)v) : "memory"); }
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -669,9 +678,8 @@ struct ToneSmem {
   float *seed;      // [total]
   float *astk;      // [total]
   short *pstk;      // [total]
-  float *run_mx;    // [nruns]
-  int   *run_info;  // [nruns] in cls_run order: curve idx | post0<<8 | post1<<14 | oc<<20
-  short *rec;       // [total] chase restart points; aliases run_mx/run_info (dead by then)
+  int4  *run_rec;   // [nruns] in cls_run order: decoded run records (see dev_tone_runs)
+  short *rec;       // [total] chase restart points; aliases run_rec (dead by then)
 };
 
 __device__ __forceinline__ float tone_att(const PsyDev &P, float lmax) {
@@ -681,30 +689,42 @@ __device__ __forceinline__ float tone_att(const PsyDev &P, float lmax) {
 }
 
 // seed_loop: one item per run of equal octave[] (peak, audibility gate, curve choice).
-// Items are visited in residue-class order (cls_run) and their dynamic result is stored at
-// that index, so the scatter below walks shared memory only:
-//   run_mx[k]   = peak of the run
-//   run_info[k] = curve index (8 bits) | post0<<8 | post1<<14 | (oc-firstoc)<<20 ; post0==post1: inactive
+// Items are visited in residue-class order (cls_run) and everything seed_curve needs is
+// decoded here, once, into a 16-byte record at that index:
+//   rec.x = peak (float bits)          rec.y = index of the first usable curve value
+//   rec.z = seed slot of that value     rec.w = number of usable values (0: inactive)
+// "usable" = curve points post0..post1-1 whose slot lies in (0,total) (lib/psy.c:405-413).
 __device__ __forceinline__ void dev_tone_runs(const PsyDev &P, const float *logfft, float gmax, float lmax,
                                               const ToneSmem &T, int tid, int nt) {
   const float att = tone_att(P, lmax);
   const float dBoffset = P.max_curve_dB - gmax;
+  const int L = P.linesper, half = L >> 1, total = P.total;
   for (int k = tid; k < P.nruns; k += nt) {
     const int2 cr = __ldg(P.cls_run + k);            // run id, oc - firstoc
     const int4 ri = __ldg(P.runinfo + cr.x);         // lo, hi, oc - firstoc, band
     float mx = logfft[ri.x];
     for (int i = ri.x + 1; i <= ri.y; i++) { const float v = logfft[i]; if (v > mx) mx = v; }
-    int info = ri.z << 20;
+    int4 rec = make_int4(__float_as_int(mx), 0, 0, 0);
     if (mx + 6.f > __ldg(P.ath + ri.y) + att) {
       int choice = (int)((((double)(mx + dBoffset)) - 30.) * (double).1f);   // P_LEVEL_0 is a double
       if (choice < 0) choice = 0;
       if (choice > VB200_P_LEVELS - 1) choice = VB200_P_LEVELS - 1;
-      const int cidx = ri.w * VB200_P_LEVELS + choice;
-      const float *posts = P.tonecurves + cidx * (VB200_EHMER_MAX + 2);
-      const int post0 = (int)__ldg(posts), post1 = (int)__ldg(posts + 1);
-      info |= cidx | (post0 << 8) | (post1 << 14);
+      const int cbase = (ri.w * VB200_P_LEVELS + choice) * (VB200_EHMER_MAX + 2);
+      int post0 = (int)__ldg(P.tonecurves + cbase), post1 = (int)__ldg(P.tonecurves + cbase + 1);
+      // clip to slots 1..total-1:  sp(i) = oc + (i-16)*L - half
+      const int sp_at0 = ri.z - 16 * L - half;                   // slot of i = 0
+      // smallest i with sp(i) > 0  and  smallest i with sp(i) >= total
+      int ilo = sp_at0 > 0 ? 0 : (-sp_at0) / L + 1;
+      int ihi = total - sp_at0 <= 0 ? 0 : (total - sp_at0 + L - 1) / L;
+      if (post0 < ilo) post0 = ilo;
+      if (post1 > ihi) post1 = ihi;
+      if (post0 < post1) {
+        rec.y = cbase + 2 + post0;
+        rec.z = sp_at0 + post0 * L;
+        rec.w = post1 - post0;
+      }
     }
-    T.run_mx[k] = mx; T.run_info[k] = info;
+    T.run_rec[k] = rec;
   }
 }
 
@@ -721,48 +741,56 @@ __device__ __forceinline__ void dev_tone_slots_scatter(const PsyDev &P, const To
   __syncthreads();
   const int G = nt >> P.linesper_log2;               // lanes per class (<= 32)
   const int cls = tid / G, g = tid - cls * G;
-  const int k0 = P.cls_off[cls], k1 = P.cls_off[cls + 1];
+  const int k0 = __ldg(P.cls_off + cls), k1 = __ldg(P.cls_off + cls + 1);
   // every warp loops to the longest class it hosts so that __syncwarp() is convergent
   const int wfirst = (tid & ~31) / G, wlast = ((tid | 31)) / G;
   int len = 0;
-  for (int c = wfirst; c <= wlast; c++) { const int l = P.cls_off[c + 1] - P.cls_off[c]; if (l > len) len = l; }
-  const int GL = G * L;
-  // software pipeline: the next run's record and its first two curve values (the only global
-  // reads, L2 resident) are fetched while the current run is applied
-  float mx = 0.f, c0 = 0.f, c1 = 0.f;
-  int ext = 0, sp = 0;
-  const float *cptr = P.tonecurves;
-  auto fetch = [&](int k) {
-    ext = 0;
+  for (int c = wfirst; c <= wlast; c++) { const int l = __ldg(P.cls_off + c + 1) - __ldg(P.cls_off + c); if (l > len) len = l; }
+  const int GL = G * L, gL = g * L;
+  // software pipeline, two register sets: while run q is applied, run q+1's record and its first
+  // two curve values (the only global reads, L2/L1 resident) are already in flight
+  const unsigned a_seed = smem_u32(T.seed), a_rec = smem_u32(T.run_rec);
+  const float *__restrict__ curves = P.tonecurves;
+  struct Run { float mx, c0, c1; int ext, sp, ci; };
+  auto fetch = [&](int k, Run &r) {
+    r.ext = 0;
     if (k < k1) {
-      const int info = T.run_info[k];
-      const int i0 = ((info >> 8) & 0x3f) + g;       // this lane's first curve point
-      ext = ((info >> 14) & 0x3f) - i0;              // > 0: points i0, i0+G, ... < post1
-      mx = T.run_mx[k];
-      cptr = P.tonecurves + (info & 0xff) * (VB200_EHMER_MAX + 2) + 2 + i0;
-      sp = (info >> 20) + (i0 - 16) * L - half;
-      if (ext > 0) c0 = __ldg(cptr);
-      if (ext > G) c1 = __ldg(cptr + G);
+      int4 v;
+      asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a_rec + 16u * k));
+      r.mx = __int_as_float(v.x);
+      r.ci = v.y + g;
+      r.sp = v.z + gL;
+      r.ext = v.w - g;                               // > 0: values ci, ci+G, ... for this lane
+      if (r.ext > 0) r.c0 = __ldg(curves + r.ci);
+      if (r.ext > G) r.c1 = __ldg(curves + r.ci + G);
     }
   };
-  fetch(k0);
-  for (int q = 0; q < len; q++) {
-    const float cmx = mx, cc0 = c0, cc1 = c1;
-    const int cext = ext, csp = sp;
-    const float *ccp = cptr;
-    fetch(k0 + q + 1);
-    if (cext > 0) {
-      if (csp > 0 && csp < total) T.seed[csp] = fmaxf(T.seed[csp], cmx + cc0);
-      if (cext > G) {
-        const int s1 = csp + GL;
-        if (s1 > 0 && s1 < total) T.seed[s1] = fmaxf(T.seed[s1], cmx + cc1);
-        for (int t = 2; cext > t * G; t++) {
-          const int st = csp + t * GL;
-          if (st > 0 && st < total) T.seed[st] = fmaxf(T.seed[st], cmx + __ldg(ccp + t * G));
+  auto apply = [&](const Run &r) {
+    if (r.ext > 0) {
+      const unsigned a0 = a_seed + 4u * r.sp;
+      sts_f32(a0, fmaxf(lds_f32(a0), r.mx + r.c0));
+      if (r.ext > G) {
+        const unsigned a1 = a0 + 4u * GL;
+        sts_f32(a1, fmaxf(lds_f32(a1), r.mx + r.c1));
+        for (int t = 2; r.ext > t * G; t++) {
+          const unsigned at = a0 + 4u * t * GL;
+          sts_f32(at, fmaxf(lds_f32(at), r.mx + __ldg(curves + r.ci + t * G)));
         }
       }
     }
+  };
+  Run A, B;
+  A.mx = A.c0 = A.c1 = 0.f; A.ext = A.sp = A.ci = 0; B = A;
+  fetch(k0, A);
+  for (int q = 0; q < len; q += 2) {
+    fetch(k0 + q + 1, B);
+    apply(A);
     __syncwarp();
+    if (q + 1 < len) {
+      fetch(k0 + q + 2, A);
+      apply(B);
+      __syncwarp();
+    }
   }
 }
 
@@ -773,10 +801,11 @@ __device__ __forceinline__ void dev_tone_slots_gather(const PsyDev &P, const Ton
     float m = VB_NEGINF;
     const int2 rg = __ldg(P.slot_rng + s);           // candidate range in cls_run (empty for s == 0)
     for (int k = rg.x; k < rg.y; k++) {
-      const int info = T.run_info[k];                // class-order slot: curve, post0, post1, oc
-      const int i = ((s - (info >> 20) + half) >> P.linesper_log2) + 16;
-      if (i >= ((info >> 8) & 0x3f) && i < ((info >> 14) & 0x3f)) {
-        const float lin = T.run_mx[k] + __ldg(P.tonecurves + (info & 0xff) * (VB200_EHMER_MAX + 2) + 2 + i);
+      const int4 rec = T.run_rec[k];                 // peak, first curve index, first slot, count
+      const int d = s - rec.z;                       // multiple of L by construction of the class
+      const int j = d >> P.linesper_log2;
+      if (d >= 0 && j < rec.w) {
+        const float lin = __int_as_float(rec.x) + __ldg(P.tonecurves + rec.y + j);
         if (m < lin) m = lin;
       }
     }

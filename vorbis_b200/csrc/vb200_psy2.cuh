@@ -27,15 +27,16 @@ struct PhaseA2Args {
   float *ampmax_out;      // [blocks]
   float *tap_noise, *tap_tone;
   int dbg_skip;           // timing experiments only (VB200_DEBUG_SKIP); 0 in production
+  unsigned long long *dbg_cycles;   // optional [16]: per-phase SM cycles summed over rows (thread 0 of each CTA)
 };
 
 constexpr int PSY2_THREADS = 128;
 
 __host__ __device__ inline size_t psy2_floats(int n, int total, int nruns, int ngrp) {
   const int tp = (total + 7) & ~7, rp = (nruns + 3) & ~3;
-  size_t tone = (size_t)n + 2 * (size_t)tp + tp / 2 + 2 * (size_t)rp;       // fft, seed, astk, pstk, runs
+  size_t tone = (size_t)n + 2 * (size_t)tp + tp / 2 + 4 * (size_t)rp;       // fft, seed, astk, pstk, run records
   const size_t recs = (size_t)((((total + 3) / 4 + 31) & ~31) * 4 + 1) / 2 + 8;   // 4 chunks of shorts
-  if (2 * (size_t)rp < recs) tone += recs - 2 * (size_t)rp;
+  if (4 * (size_t)rp < recs) tone += recs - 4 * (size_t)rp;
   const size_t scan = 5 * (size_t)(n + 4);
   return (scan > tone ? scan : tone) + (size_t)((ngrp + 1 + 3) & ~3) + 16;
 }
@@ -52,15 +53,23 @@ __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem 
   int m = 0;
   for (int base = warp * C; base < (warp + 1) * C && base < total; base += 32) {
     const int i = base + lane;
-    // record <=> strictly greater than each of the previous linesper-1 seeds (branch free)
+    // restart point <=> seeds[i] is strictly greater than each of the previous linesper-1 seeds
+    // (rule A: the entry it lands on is smaller, so it can never satisfy the pop test), or
+    // strictly greater than each of the next linesper-1 seeds (rule C: a pop of entry i needs a
+    // step j < i+linesper with seeds[j] >= seeds[i]).  Either way entry i is permanent and
+    // freezes the stack below it.  Branch free.
     bool r = i < total;
     {
       const float v = r ? seed[i] : 0.f;
+      bool ra = r, rc = r;
       for (int d = 1; d < linesper; d++) {
-        const int j = i - d;
+        const int j = i - d, h = i + d;
         const float u = (r && j >= 0) ? seed[j] : 0.f;
-        r = r && (j < 0 || v > u);
+        const float w = (r && h < total) ? seed[h] : 0.f;
+        ra = ra && (j < 0 || v > u);
+        rc = rc && (h >= total || v > w);
       }
+      r = ra || rc;
     }
     const unsigned b = __ballot_sync(full, r);
     if (r) rec[warp * C + m + __popc(b & ((1u << lane) - 1u))] = (short)i;
@@ -84,12 +93,14 @@ __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem 
     end = r1 < M ? REC(r1) : total;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     int l0 = 0, l1 = 0, l2 = 0, c = 0, stack = 0;
-    float s = seed[start];
-    for (int i = start; i <= end && i < total; i++) {
-      const float snext = i + 1 < total ? seed[i + 1] : 0.f;
+    const unsigned as_ = smem_u32(seed), aa = smem_u32(astk) + 4u * start, ap = smem_u32(pstk) + 2u * start;
+    const int last = end < total ? end : total - 1;
+    float s = lds_f32(as_ + 4u * start);
+    for (int i = start; i <= last; i++) {
+      const float snext = lds_f32(as_ + 4u * (i + 1 < total ? i + 1 : i));
       if (stack >= 2 && !(s < a0)) {
         for (;;) {
-          if (c < 2) { a1 = astk[start + stack - 2]; l1 = pstk[start + stack - 2] + linesper; c = 2; }
+          if (c < 2) { a1 = lds_f32(aa + 4u * (stack - 2)); l1 = lds_s16(ap + 2u * (stack - 2)) + linesper; c = 2; }
           if (!(i < l0 && a0 <= a1 && i < l1)) break;
           stack--;
           a0 = a1; l0 = l1; a1 = a2; l1 = l2; c--;
@@ -97,7 +108,7 @@ __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem 
         }
       }
       if (i < end) {
-        astk[start + stack] = s; pstk[start + stack] = (short)i;
+        sts_f32(aa + 4u * stack, s); sts_s16(ap + 2u * stack, i);
         a2 = a1; l2 = l1; a1 = a0; l1 = l0; a0 = s; l0 = i + linesper;
         stack++;
         c = c < 3 ? c + 1 : 3;
@@ -157,8 +168,9 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
   float *s_fft = sm;
   ToneSmem T;
   T.seed = s_fft + n; T.astk = T.seed + tp; T.pstk = reinterpret_cast<short *>(T.astk + tp);
-  T.run_mx = T.astk + tp + tp / 2; T.run_info = reinterpret_cast<int *>(T.run_mx + rp);
-  T.rec = reinterpret_cast<short *>(T.run_mx);
+  T.run_rec = reinterpret_cast<int4 *>(T.astk + tp + tp / 2);
+  T.rec = reinterpret_cast<short *>(T.run_rec);
+  (void)rp;
   const size_t area = psy2_floats(n, total, nruns, ngrp) - (size_t)((ngrp + 1 + 3) & ~3) - 16;
   float *grp_min = sm + area;
   int *s_misc = reinterpret_cast<int *>(grp_min + ((ngrp + 1 + 3) & ~3));
@@ -169,23 +181,38 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     const float *lf = A.logfft + (size_t)row * n;
     const float g = A.gmax[blk], lmax = A.lmax[row];
     float L[K], M[K], p1[K];
+    long long tmark = A.dbg_cycles ? clock64() : 0;
+    int tph = 0;
+#define PHASE_MARK()                                                              \
+    do {                                                                          \
+      if (A.dbg_cycles && tid == 0) {                                             \
+        const long long tnow = clock64();                                         \
+        atomicAdd(A.dbg_cycles + tph, (unsigned long long)(tnow - tmark));        \
+        tmark = tnow;                                                             \
+      }                                                                           \
+      tph++;                                                                      \
+    } while (0)
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const int i = tid + k * nt;
-      M[k] = gm[i];
-      s_fft[i] = lf[i];
+      M[k] = __ldcs(gm + i);                            // streaming: keep L1 for the lookup tables
+      s_fft[i] = __ldcs(lf + i);
     }
 #pragma unroll
     for (int k = 0; k < K; k++) {
       L[k] = add345(todB_dev(M[k]));                    // lib/mapping0.c:384-385
-      A.logmdct[(size_t)row * n + tid + k * nt] = L[k];
+      __stcs(A.logmdct + (size_t)row * n + tid + k * nt, L[k]);
     }
     __syncthreads();
+    PHASE_MARK();   // 0 load
     dev_tone_runs(P, s_fft, g, lmax, T, tid, nt);
     __syncthreads();
+    PHASE_MARK();   // 1 runs
     dev_tone_slots(P, T, tid, nt);
     __syncthreads();
+    PHASE_MARK();   // 2 scatter
     dev_chase_block(P, T, s_misc, tid);
+    PHASE_MARK();   // 3 chase
     // max_seeds gather, first half: one minimum per static group (lib/psy.c:522-533)
     for (int q = tid; q <= P.ngrp; q += nt) {
       float minV;
@@ -205,21 +232,27 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
       grp_min[q] = minV;
     }
     __syncthreads();                                   // tone scratch is dead from here on
+    PHASE_MARK();   // 4 group minima
     // ---- noise mask, pass 1 (offset 140, bark windows)
 #pragma unroll
     for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k], 140.f, S, ns);
     __syncthreads();
+    PHASE_MARK();   // 5 terms 1
     if (tid < 32) dev_noise_scan(n, S, ns, lane);
     __syncthreads();
+    PHASE_MARK();   // 6 scan 1
 #pragma unroll
     for (int k = 0; k < K; k++) p1[k] = dev_noise_regress1(P, tid + k * nt, 140.f, -1, S, ns);
     __syncthreads();
+    PHASE_MARK();   // 7 regress 1
     // ---- pass 2 on logmdct - p1 (offset 0, bark + fixed windows)
 #pragma unroll
     for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k] - p1[k], 0.f, S, ns);
     __syncthreads();
+    PHASE_MARK();   // 8 terms 2
     if (tid < 32) dev_noise_scan(n, S, ns, lane);
     __syncthreads();
+    PHASE_MARK();   // 9 scan 2
     const float att = tone_att(P, lmax);
     const float *noff = P.noiseoffset + n;             // offset_select 1
 #pragma unroll
@@ -237,13 +270,15 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
       if (tn < mv) tn = mv;
       float m = M[k];
       const float lm = dev_mix_bin(P, 1, nz, tn, __ldg(noff + i), L[k], m);
-      A.logmask[(size_t)row * n + i] = lm;
-      A.mdct_out[(size_t)row * n + i] = m;
+      __stcs(A.logmask + (size_t)row * n + i, lm);
+      __stcs(A.mdct_out + (size_t)row * n + i, m);
       if (A.tap_noise) A.tap_noise[(size_t)row * n + i] = nz;
       if (A.tap_tone) A.tap_tone[(size_t)row * n + i] = tn;
     }
     if (tid == 0 && (row % ch) == 0) A.ampmax_out[blk] = g;   // lib/mapping0.c:576
     __syncthreads();
+    PHASE_MARK();   // 10 regress 2 + final + mix
+#undef PHASE_MARK
   }
 }
 

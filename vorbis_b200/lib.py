@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libvorbis_b200.so")
 
 EXPORTS = [
     "vb200_ctx_create", "vb200_ctx_destroy", "vb200_device_count", "vb200_last_error",
-    "vb200_ctx_table", "vb200_launch_count", "vb200_set_profiling", "vb200_phaseA_kernel_ms",
+    "vb200_ctx_table", "vb200_launch_count", "vb200_set_profiling", "vb200_phaseA_kernel_ms", "vb200_debug_phase_cycles",
     "vb200_mdct_forward_dev", "vb200_mdct_forward", "vb200_mdct_backward_dev", "vb200_mdct_backward",
     "vb200_apply_window", "vb200_drft_forward",
     "vb200_noisemask", "vb200_tonemask", "vb200_offset_and_mix",
@@ -53,6 +53,7 @@ def load():
     L.vb200_launch_count.argtypes = [vp]
     L.vb200_set_profiling.argtypes = [vp, C.c_int]
     L.vb200_phaseA_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    L.vb200_debug_phase_cycles.argtypes = [vp, C.POINTER(C.c_ulonglong * 16), C.c_int]
     L.vb200_ctx_create.argtypes = [C.POINTER(abi.Setup), C.c_int, C.POINTER(vp)]
     L.vb200_ctx_destroy.argtypes = [vp]
     L.vb200_ctx_table.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
@@ -127,6 +128,11 @@ class Context:
         ms = (C.c_float * 3)()
         self._chk(self.L.vb200_phaseA_kernel_ms(self.h, C.byref(ms)))
         return [float(x) for x in ms]
+
+    def debug_phase_cycles(self, reset=True):
+        out = (C.c_ulonglong * 16)()
+        self._chk(self.L.vb200_debug_phase_cycles(self.h, C.byref(out), 1 if reset else 0))
+        return [int(x) for x in out]
 
     def table(self, W, which):
         N = self.bs[W]
