@@ -213,6 +213,12 @@ int vb200_synthesis    (vb200_ctx*, int nstreams, int nblk, const int32_t *Wseq,
                         const int64_t *coef_off, const float *coef, int64_t coef_len,
                         const int64_t *pcm_off, float *pcm, int64_t pcm_stride);
 
+/* ---- decode: channel de-coupling of mapping0_inverse (lib/mapping0.c:754-779).
+ * res [nblocks][ch][n] residue vectors as left by the residue backend; every coupling step
+ * (magnitude, angle) -> (left, right) is undone in place, last step first.  Elementwise.  */
+int vb200_decouple_dev(vb200_ctx*, int W, int nblocks, float *d_res, void *stream);
+int vb200_decouple    (vb200_ctx*, int W, int nblocks, float *res);
+
 /* ---- device memory helpers for non-CUDA hosts (C callers) -------------- */
 int  vb200_malloc_device(vb200_ctx*, size_t bytes, void **dptr);
 int  vb200_free_device  (vb200_ctx*, void *dptr);

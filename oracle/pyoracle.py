@@ -53,6 +53,7 @@ def lib():
         L.vbo_couple_quantize_normalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                     f32p, i32p, i32p]
         L.vbo_synthesis.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i64p, f32p, i64p, f32p, C.c_int64]
+        L.vbo_decouple.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p]
         _lib = L
     return _lib
 
@@ -170,6 +171,11 @@ class Oracle:
         nonzero = np.array(nonzero, np.int32)
         self.L.vbo_couple_quantize_normalize(self.h, W, blocktype, blobno, mdct.shape[0], mdct, iwork, nonzero)
         return iwork, nonzero
+
+    def decouple(self, W, res):
+        res = np.array(res, np.float32)
+        self.L.vbo_decouple(self.h, W, res.shape[0], res)
+        return res
 
     def synthesis(self, Wseq, coef_off, coef, pcm_off, pcm_stride):
         Wseq = np.ascontiguousarray(Wseq, np.int32)

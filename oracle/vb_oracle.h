@@ -48,4 +48,5 @@ void vbo_couple_quantize_normalize(vbo_ctx *c, int W, int blocktype, int blobno,
 void vbo_synthesis(vbo_ctx *c, int nstreams, int nblk, const int32_t *Wseq,
                    const int64_t *coef_off, const float *coef,
                    const int64_t *pcm_off, float *pcm, int64_t pcm_stride);
+void vbo_decouple(vbo_ctx *c, int W, int nblocks, float *res);
 #endif

@@ -244,3 +244,48 @@ def test_phaseA_host_path_multichunk(cfg, monkeypatch):
     b = o.phaseA(W, pcm, desc)
     for k in ("mdct", "logmdct", "logmask", "ampmax_out"):
         assert_bits_equal(a[k], b[k], "chunked " + k)
+
+
+def test_decouple_vs_oracle(cfg):
+    name, setup, ctx, o, _, _ = cfg
+    ch = setup.channels
+    rng = np.random.default_rng(8)
+    for W in (0, 1):
+        n = setup.blocksize(W) // 2
+        res = rng.integers(-6, 7, (33, ch, n)).astype(np.float32)      # residue values are small ints,
+        res[0] = 0.0                                                   # zeros and sign ties included
+        assert_bits_equal(ctx.decouple(W, res), o.decouple(W, res), "decouple W%d" % W)
+
+
+def test_phaseA_stream_mode_device(cfg):
+    """device-resident stream mode: the ampmax chain of vorbis_analysis_blockout evaluated on the GPU"""
+    import torch
+    name, setup, ctx, o, _, _ = cfg
+    W = 1
+    N, ch = setup.blocksize(W), setup.channels
+    ns, bps = 7, 9
+    rng = np.random.default_rng(99)
+    t = np.arange(N)
+    amp = rng.choice([1e-3, 0.05, 0.5], (ns, bps, 1, 1))                # loud and quiet blocks: the chain matters
+    pcm = (amp * (0.3 * rng.uniform(-1, 1, (ns, bps, ch, N)) +
+                  0.6 * np.sin(2 * np.pi * 700 * t / setup.rate))).astype(np.float32).reshape(-1, ch, N)
+    desc = np.zeros(ns * bps, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = 1; desc["nW"] = 1; desc["blocktype"] = 1
+    amp0 = rng.choice([-9999.0, -20.0], ns).astype(np.float32)
+    want = o.phaseA(W, pcm, desc, streams=(ns, bps), ampmax0=amp0)
+    dev = torch.device("cuda", 0)
+    d_pcm = torch.from_numpy(pcm).to(dev)
+    d_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1, 16).copy()).to(dev)
+    outs = {k: torch.empty((ns * bps, ch, N // 2), device=dev) for k in ("mdct", "logmdct", "logmask")}
+    d_amp = torch.empty(ns * bps, device=dev)
+    d_amp0 = torch.from_numpy(amp0).to(dev)
+    io = abi.PhaseAIO()
+    io.pcm, io.desc = d_pcm.data_ptr(), d_desc.data_ptr()
+    io.mdct, io.logmdct, io.logmask = (outs[k].data_ptr() for k in ("mdct", "logmdct", "logmask"))
+    io.ampmax_out = d_amp.data_ptr()
+    ctx.phaseA_dev(W, ns * bps, io, stream=torch.cuda.current_stream().cuda_stream, streams=(ns, bps),
+                   d_ampmax0=d_amp0.data_ptr())
+    torch.cuda.synchronize()
+    for k in ("mdct", "logmdct", "logmask"):
+        assert_bits_equal(outs[k].cpu().numpy(), want[k], "stream mode " + k)
+    assert_bits_equal(d_amp.cpu().numpy(), want["ampmax_out"], "stream mode ampmax chain")

@@ -102,3 +102,29 @@ def test_decode(cfg):
     W0 = int(dec["W"][0])
     first = o.mdct_backward(W0, dec["coef"][:setup.channels * bs[W0] // 2])
     assert_bits_equal(first, dec["imdct_first"], "mdct_backward")
+
+
+def test_decouple_inverts_the_encoder_coupling(cfg):
+    """oracle's de-coupling (lib/mapping0.c:754-779) undoes the encoder's lossless square-polar
+    coupling (lib/psy.c:1128-1146): (A,B) -> (iM,iA) -> (A,B) for every integer pair."""
+    name, setup, o, _, _ = cfg
+    if setup.channels != 2 or int(setup.c.coupling_steps[1]) != 1:
+        pytest.skip("needs a single-step stereo coupling")
+    n = setup.blocksize(1) // 2
+    rng = np.random.default_rng(0)
+    A = rng.integers(-40, 41, n)
+    B = rng.integers(-40, 41, n)
+    A[:20] = 0; B[10:30] = 0
+    iM, iA = A.copy(), B.copy()
+    big = np.abs(A) > np.abs(B)
+    iA = np.where(big, np.where(A > 0, A - B, B - A), np.where(B > 0, A - B, B - A))
+    iM = np.where(big, A, B)
+    flip = iA >= np.abs(iM) * 2
+    iA = np.where(flip, -iA, iA)
+    iM = np.where(flip, -iM, iM)
+    res = np.zeros((1, 2, n), np.float32)
+    res[0, int(setup.c.coupling_mag[1][0])] = iM
+    res[0, int(setup.c.coupling_ang[1][0])] = iA
+    out = o.decouple(1, res)
+    assert np.array_equal(out[0, int(setup.c.coupling_mag[1][0])], A.astype(np.float32))
+    assert np.array_equal(out[0, int(setup.c.coupling_ang[1][0])], B.astype(np.float32))

@@ -576,6 +576,29 @@ k_synthesis(XformDev X0, XformDev X1, WinDev Wd, int ch, int nstreams, int nblk,
   }
 }
 
+// ---- decode: undo channel coupling, lib/mapping0.c:754-779 (square polar -> L/R), in place
+__global__ void __launch_bounds__(256)
+k_decouple(int n, int ch, int steps, const int *__restrict__ mag, const int *__restrict__ ang,
+           long long total, float *__restrict__ res) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long blk = e / n;
+    const int j = (int)(e - blk * n);
+    float *base = res + blk * (long long)ch * n + j;
+    for (int s = steps - 1; s >= 0; s--) {
+      float *pM = base + (long long)mag[s] * n, *pA = base + (long long)ang[s] * n;
+      const float m = *pM, a = *pA;
+      if (m > 0.f) {
+        if (a > 0.f) { *pM = m; *pA = m - a; }
+        else         { *pA = m; *pM = m + a; }
+      } else {
+        if (a > 0.f) { *pM = m; *pA = m + a; }
+        else         { *pA = m; *pM = m - a; }
+      }
+    }
+  }
+}
+
 // ======================================================================== //
 // launch helpers
 static int threads_for(int N) {
@@ -886,7 +909,7 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
       const int ngrp = P0.ngrp > P1.ngrp ? P0.ngrp : P1.ngrp;
       const size_t smem2 = sizeof(float) * psy2_floats(n, total, nruns, ngrp);
       int ctas = (int)((227 * 1024) / (smem2 + 1024));
-      if (ctas > 8) ctas = 8;
+      if (ctas > PSY2_MINB) ctas = PSY2_MINB;
       if (ctas < 1) ctas = 1;
       { const char *e = getenv("VB200_PSY_CTAS"); if (e) ctas = atoi(e); }
 #define LAUNCH_PSY2(KK)                                                                            \
@@ -1131,6 +1154,29 @@ extern "C" int vb200_synthesis(vb200_ctx *c, int nstreams, int nblk, const int32
   if ((rc = vb200_synthesis_dev(c, nstreams, nblk, (const int32_t *)dW, (const int64_t *)dco, (const float *)dc,
                                 (const int64_t *)dpo, (float *)dp, pcm_stride, c->s_main))) return rc;
   if ((rc = io.d2h(pcm, dp, pbytes))) return rc;
+  return io.sync();
+}
+
+extern "C" int vb200_decouple_dev(vb200_ctx *c, int W, int nblocks, float *d_res, void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nblocks <= 0 || c->setup.coupling_steps[W] <= 0) return 0;
+  const int n = c->dx[W].N / 2;
+  const long long total = (long long)nblocks * n;
+  k_decouple<<<grid_for(c, (int)((total + 255) / 256), 16), 256, 0, (cudaStream_t)stream>>>(
+      n, c->setup.channels, c->setup.coupling_steps[W], c->d_mag[W], c->d_ang[W], total, d_res);
+  return post_launch(c);
+}
+
+extern "C" int vb200_decouple(vb200_ctx *c, int W, int nblocks, float *res) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nblocks <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t bytes = sizeof(float) * (size_t)nblocks * c->setup.channels * (c->dx[W].N / 2);
+  HostIO io{c};
+  void *d; int rc;
+  if ((rc = io.h2d(res, bytes, &d))) return rc;
+  if ((rc = vb200_decouple_dev(c, W, nblocks, (float *)d, c->s_main))) return rc;
+  if ((rc = io.d2h(res, d, bytes))) return rc;
   return io.sync();
 }
 

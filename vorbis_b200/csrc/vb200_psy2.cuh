@@ -31,6 +31,9 @@ struct PhaseA2Args {
 };
 
 constexpr int PSY2_THREADS = 128;
+#ifndef PSY2_MINB
+#define PSY2_MINB 8
+#endif
 
 __host__ __device__ inline size_t psy2_floats(int n, int total, int nruns, int ngrp) {
   const int tp = (total + 7) & ~7, rp = (nruns + 3) & ~3;
@@ -154,7 +157,7 @@ __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem 
 }
 
 template <int K>   // K = n / 128 bins per thread
-__global__ void __launch_bounds__(PSY2_THREADS, 8)
+__global__ void __launch_bounds__(PSY2_THREADS, PSY2_MINB)
 k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
   extern __shared__ __align__(16) float sm[];
   constexpr int nt = PSY2_THREADS;

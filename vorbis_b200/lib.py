@@ -22,7 +22,7 @@ EXPORTS = [
     "vb200_noisemask", "vb200_tonemask", "vb200_offset_and_mix",
     "vb200_analysis_phaseA_dev", "vb200_analysis_phaseA", "vb200_analysis_phaseA_streams_dev",
     "vb200_couple_quantize_normalize_dev", "vb200_couple_quantize_normalize",
-    "vb200_synthesis_dev", "vb200_synthesis",
+    "vb200_synthesis_dev", "vb200_synthesis", "vb200_decouple_dev", "vb200_decouple",
     "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
 ]
 
@@ -73,6 +73,8 @@ def load():
     L.vb200_couple_quantize_normalize.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.vb200_synthesis_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int64, vp]
     L.vb200_synthesis.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, C.c_int64]
+    L.vb200_decouple_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.vb200_decouple.argtypes = [vp, C.c_int, C.c_int, vp]
     L.vb200_malloc_device.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.vb200_free_device.argtypes = [vp, vp]
     L.vb200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -244,6 +246,11 @@ class Context:
                                                              _ptr(stream)))
 
     # ---- decode ------------------------------------------------------------------
+    def decouple(self, W, res):
+        res = np.array(res, np.float32)
+        self._chk(self.L.vb200_decouple(self.h, W, res.shape[0], _ptr(res)))
+        return res
+
     def synthesis(self, Wseq, coef_off, coef, pcm_off, pcm_stride):
         Wseq = np.ascontiguousarray(Wseq, np.int32)
         ns, nblk = Wseq.shape
