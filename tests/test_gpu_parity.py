@@ -289,3 +289,15 @@ def test_phaseA_stream_mode_device(cfg):
     for k in ("mdct", "logmdct", "logmask"):
         assert_bits_equal(outs[k].cpu().numpy(), want[k], "stream mode " + k)
     assert_bits_equal(d_amp.cpu().numpy(), want["ampmax_out"], "stream mode ampmax chain")
+
+
+def test_phaseA_generic_kernel_path(cfg, monkeypatch):
+    """the generic psy kernel (k_phaseA_psy, any n) kept as fallback for block sizes the
+    register-resident kernel does not cover: same bits"""
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1
+    monkeypatch.setenv("VB200_PSY_V1", "1")
+    out = ctx.phaseA(W, enc["L_pcm"], make_desc(enc, "L"), taps=True)
+    monkeypatch.delenv("VB200_PSY_V1")
+    for k, g in (("noise", "noise"), ("tone", "tone"), ("logmask", "logmask"), ("mdct", "mdct_m1")):
+        assert_bits_equal(out[k], enc["L_" + g], "generic kernel " + k)

@@ -44,6 +44,69 @@ __host__ __device__ inline size_t psy2_floats(int n, int total, int nruns, int n
   return (scan > tone ? scan : tone) + (size_t)((ngrp + 1 + 3) & ~3) + 16;
 }
 
+// The per-bin regression and mix are called 8x (bins per thread) x 3 (windows); inlining them
+// made the kernel ~93 KB of SASS and 11 % of the stall samples were instruction-cache misses.
+// They are real functions here (scalars only in the signature, so nothing spills to local).
+template <int NS>
+__device__ __noinline__ float regress_core(const int *__restrict__ bark, int bfe, int ffe, const float *S,
+                                           int i, float offset, int fixed) {
+  Abd cur; cur.A = 0.f; cur.B = 0.f; cur.D = 1.f;
+  if (bfe > 0) {
+    const int wb = i < bfe ? i : bfe - 1;
+    const int bk = __ldg(bark + wb);
+    cur = dev_window_abd(bk >> 16, bk & 0xffff, S, NS);
+  }
+  const float x = (float)i;
+  float R = (cur.A + x * cur.B) / cur.D;
+  if (R < 0.f) R = 0.f;
+  float v = R - offset;
+  if (fixed > 0) {
+    if (ffe > 0) {
+      const int wb = i < ffe ? i : ffe - 1;
+      const int hi = wb + fixed / 2, lo = hi - fixed;
+      cur = dev_window_abd(lo, hi, S, NS);
+    } else if (bfe > 0 && i < bfe) {
+      const int bk = __ldg(bark + (bfe - 1));
+      cur = dev_window_abd(bk >> 16, bk & 0xffff, S, NS);
+    }
+    const float R2 = (cur.A + x * cur.B) / cur.D;
+    if (R2 - offset < v) v = R2 - offset;
+  }
+  return v;
+}
+
+// final step of _vp_noisemask for one bin + tone lookup + _vp_offset_and_mix(select 1);
+// returns logmask, updates m (the mdct value), writes the optional taps
+struct MixConst { float noisemaxsupp, toneatt, m_val, att; };
+__device__ __noinline__ float final_mix_core(float p2, float L, float p1, float noff, float ath, float gmin,
+                                             const float *__restrict__ compand, MixConst C, float &m,
+                                             float &nz_out, float &tn_out) {
+  const float work = L - p1;                       // lib/psy.c:717
+  const float base = L - work;                     // lib/psy.c:722
+  int dB = (int)((double)p2 + .5);
+  if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
+  if (dB < 0) dB = 0;
+  const float nz = base + __ldg(compand + dB);
+  float tn = ath + C.att;                          // lib/psy.c:771, then max_seeds' flr update
+  if (tn < gmin) tn = gmin;
+  nz_out = nz; tn_out = tn;
+  float val = nz + noff;                           // lib/psy.c:789-791
+  if (val > C.noisemaxsupp) val = C.noisemaxsupp;
+  const float t = tn + C.toneatt;
+  const float logmask = val < t ? t : val;
+  const float coeffi = -17.2f;
+  float de;
+  val = val - L;
+  if (val > coeffi) {
+    de = (float)(1.0 - ((double)(val - coeffi) * 0.005 * (double)C.m_val));
+    if (de < 0.f) de = 0.0001f;
+  } else {
+    de = (float)(1.0 - ((double)(val - coeffi) * 0.0003 * (double)C.m_val));
+  }
+  m *= de;
+  return logmask;
+}
+
 // block-wide seed_chase (see dev_tone_chase_gather for the exactness argument)
 __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem &T, int *s_misc,
                                                 int tid) {
@@ -245,7 +308,8 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     __syncthreads();
     PHASE_MARK();   // 6 scan 1
 #pragma unroll
-    for (int k = 0; k < K; k++) p1[k] = dev_noise_regress1(P, tid + k * nt, 140.f, -1, S, ns);
+    for (int k = 0; k < K; k++)
+      p1[k] = regress_core<K * PSY2_THREADS + 4>(P.bark, P.bark_first_extra, P.fixed_first_extra, S, tid + k * nt, 140.f, -1);
     __syncthreads();
     PHASE_MARK();   // 7 regress 1
     // ---- pass 2 on logmdct - p1 (offset 0, bark + fixed windows)
@@ -256,23 +320,20 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     if (tid < 32) dev_noise_scan(n, S, ns, lane);
     __syncthreads();
     PHASE_MARK();   // 9 scan 2
-    const float att = tone_att(P, lmax);
+    MixConst MC;
+    MC.noisemaxsupp = P.noisemaxsupp; MC.toneatt = P.tone_masteratt[1]; MC.m_val = P.m_val;
+    MC.att = tone_att(P, lmax);
     const float *noff = P.noiseoffset + n;             // offset_select 1
+    const int *bark = P.bark; const float *athp = P.ath, *compand = P.noisecompand;
+    const short *bin_grp = P.bin_grp;
+    const int bfe = P.bark_first_extra, ffe = P.fixed_first_extra, fixedw = P.noisewindowfixed;
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const int i = tid + k * nt;
-      const float p2 = dev_noise_regress1(P, i, 0.f, P.noisewindowfixed, S, ns);
-      const float work = L[k] - p1[k];                 // lib/psy.c:717
-      const float base = L[k] - work;                  // lib/psy.c:722
-      int dB = (int)((double)p2 + .5);
-      if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
-      if (dB < 0) dB = 0;
-      const float nz = base + __ldg(P.noisecompand + dB);
-      float tn = __ldg(P.ath + i) + att;               // lib/psy.c:771, then max_seeds' flr update
-      const float mv = grp_min[__ldg(P.bin_grp + i)];
-      if (tn < mv) tn = mv;
-      float m = M[k];
-      const float lm = dev_mix_bin(P, 1, nz, tn, __ldg(noff + i), L[k], m);
+      const float p2 = regress_core<K * PSY2_THREADS + 4>(bark, bfe, ffe, S, i, 0.f, fixedw);
+      float m = M[k], nz, tn;
+      const float lm = final_mix_core(p2, L[k], p1[k], __ldg(noff + i), __ldg(athp + i),
+                                      grp_min[__ldg(bin_grp + i)], compand, MC, m, nz, tn);
       __stcs(A.logmask + (size_t)row * n + i, lm);
       __stcs(A.mdct_out + (size_t)row * n + i, m);
       if (A.tap_noise) A.tap_noise[(size_t)row * n + i] = nz;
