@@ -38,7 +38,8 @@ constexpr int PSY2_THREADS = 128;
 __host__ __device__ inline size_t psy2_floats(int n, int total, int nruns, int ngrp) {
   const int tp = (total + 7) & ~7, rp = (nruns + 3) & ~3;
   size_t tone = (size_t)n + 2 * (size_t)tp + tp / 2 + 4 * (size_t)rp;       // fft, seed, astk, pstk, run records
-  const size_t recs = (size_t)((((total + 3) / 4 + 31) & ~31) * 4 + 1) / 2 + 8;   // 4 chunks of shorts
+  size_t recs = (size_t)((((total + 3) / 4 + 31) & ~31) * 4 + 1) / 2 + 8;   // 4 chunks of shorts
+  if (recs < 4 * 224 / 2 + 8) recs = 4 * 224 / 2 + 8;
   if (4 * (size_t)rp < recs) tone += recs - 4 * (size_t)rp;
   const size_t scan = 5 * (size_t)(n + 4);
   return (scan > tone ? scan : tone) + (size_t)((ngrp + 1 + 3) & ~3) + 16;
@@ -109,47 +110,81 @@ __device__ __noinline__ float final_mix_core(float p2, float L, float p1, float 
 
 // block-wide seed_chase (see dev_tone_chase_gather for the exactness argument)
 __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem &T, int *s_misc,
-                                                int tid) {
+                                                int tid, unsigned long long *dbg = nullptr) {
+  long long tc = dbg ? clock64() : 0;
+#define CHASE_MARK(slot) do { if (dbg && tid == 0) { const long long tn_ = clock64(); atomicAdd(dbg + (slot), (unsigned long long)(tn_ - tc)); tc = tn_; } } while (0)
   const int total = P.total, linesper = P.linesper;
   const int lane = tid & 31, warp = tid >> 5;
   float *seed = T.seed; short *pstk = T.pstk; float *astk = T.astk; short *rec = T.rec;
   const unsigned full = 0xffffffffu;
-  const int C = (((total + 3) >> 2) + 31) & ~31;          // positions per warp (multiple of 32)
-  // 1. records, in position order per warp chunk
+  // 1. restart points.  Thread t owns positions [t*RB, t*RB+RB); with L = linesper <= RB+1 the
+  // window maxima over the previous / next L-1 seeds come from the suffix maximum of the previous
+  // block, the prefix/suffix maxima inside the own block and the prefix maximum of the next block.
+  //   rule A: seeds[i] > max(seeds[i-L+1 .. i-1])   (strict; positions < 0 do not exist)
+  //   rule C: seeds[i] > max(seeds[i+1 .. i+L-1])   (strict; positions >= total do not exist)
+  constexpr int RB = 7;
+  const int C = 32 * RB;                                    // positions per warp
   int m = 0;
-  for (int base = warp * C; base < (warp + 1) * C && base < total; base += 32) {
-    const int i = base + lane;
-    // restart point <=> seeds[i] is strictly greater than each of the previous linesper-1 seeds
-    // (rule A: the entry it lands on is smaller, so it can never satisfy the pop test), or
-    // strictly greater than each of the next linesper-1 seeds (rule C: a pop of entry i needs a
-    // step j < i+linesper with seeds[j] >= seeds[i]).  Either way entry i is permanent and
-    // freezes the stack below it.  Branch free.
-    bool r = i < total;
-    {
-      const float v = r ? seed[i] : 0.f;
-      bool ra = r, rc = r;
-      for (int d = 1; d < linesper; d++) {
-        const int j = i - d, h = i + d;
-        const float u = (r && j >= 0) ? seed[j] : 0.f;
-        const float w = (r && h < total) ? seed[h] : 0.f;
-        ra = ra && (j < 0 || v > u);
-        rc = rc && (h >= total || v > w);
+  if (linesper - 1 <= RB && total <= PSY2_THREADS * RB) {
+    const float NINF = -3.0e38f;                            // below every seed (>= -9999)
+    float v[3 * RB];
+    const int p0 = tid * RB - RB;
+#pragma unroll
+    for (int j = 0; j < 3 * RB; j++) { const int p = p0 + j; v[j] = (p >= 0 && p < total) ? seed[p] : NINF; }
+    unsigned flags = 0;
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+      const int i = tid * RB + j;
+      float mb = NINF, mf = NINF;
+#pragma unroll
+      for (int d = 1; d <= RB; d++) {
+        if (d < linesper) { mb = fmaxf(mb, v[RB + j - d]); mf = fmaxf(mf, v[RB + j + d]); }
       }
-      r = ra || rc;
+      const bool r = i < total && (v[RB + j] > mb || v[RB + j] > mf);
+      flags |= (r ? 1u : 0u) << j;
     }
-    const unsigned b = __ballot_sync(full, r);
-    if (r) rec[warp * C + m + __popc(b & ((1u << lane) - 1u))] = (short)i;
-    m += __popc(b);
+    // ordered compaction: records are numbered by position = by (thread, j)
+    const int cnt = __popc(flags);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, incl, o); if (lane >= o) incl += t; }
+    int w = warp * C + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < RB; j++) if (flags & (1u << j)) rec[w++] = (short)(tid * RB + j);
+    m = __shfl_sync(full, incl, 31);
+  } else {
+    const int Cg = (((total + 3) >> 2) + 31) & ~31;
+    for (int base = warp * Cg; base < (warp + 1) * Cg && base < total; base += 32) {
+      const int i = base + lane;
+      bool r = i < total;
+      {
+        const float vv = r ? seed[i] : 0.f;
+        bool ra = r, rc = r;
+        for (int d = 1; d < linesper; d++) {
+          const int j = i - d, h = i + d;
+          const float u = (r && j >= 0) ? seed[j] : 0.f;
+          const float ww = (r && h < total) ? seed[h] : 0.f;
+          ra = ra && (j < 0 || vv > u);
+          rc = rc && (h >= total || vv > ww);
+        }
+        r = ra || rc;
+      }
+      const unsigned bb = __ballot_sync(full, r);
+      if (r) rec[warp * Cg + m + __popc(bb & ((1u << lane) - 1u))] = (short)i;
+      m += __popc(bb);
+    }
   }
+  const int Cw = (linesper - 1 <= RB && total <= PSY2_THREADS * RB) ? C : ((((total + 3) >> 2) + 31) & ~31);
   if (lane == 0) s_misc[warp] = m;
   __syncthreads();
+  CHASE_MARK(11);   // records
   const int m0 = s_misc[0], m1 = s_misc[1], m2 = s_misc[2], m3 = s_misc[3];
   const int M = m0 + m1 + m2 + m3;
   auto REC = [&](int g) -> int {
     if (g < m0) return rec[g];
-    g -= m0; if (g < m1) return rec[C + g];
-    g -= m1; if (g < m2) return rec[2 * C + g];
-    return rec[3 * C + g - m2];
+    g -= m0; if (g < m1) return rec[Cw + g];
+    g -= m1; if (g < m2) return rec[2 * Cw + g];
+    return rec[3 * Cw + g - m2];
   };
   // 2. this thread's segment [start, end]
   const int r0 = (tid * M) >> 7, r1 = ((tid + 1) * M) >> 7;
@@ -184,6 +219,7 @@ __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem 
     cnt = stack;
   }
   __syncthreads();
+  CHASE_MARK(12);   // simulate
   // 3. fill: exclusive prefix-max of every thread's furthest endpos = its starting cursor
   int Mx = 0;
   for (int j = 0; j < cnt; j++) {
@@ -217,6 +253,8 @@ __device__ __forceinline__ void dev_chase_block(const PsyDev &P, const ToneSmem 
     if (endpos > cursor) cursor = endpos;
   }
   __syncthreads();
+  CHASE_MARK(13);   // fill
+#undef CHASE_MARK
 }
 
 template <int K>   // K = n / 128 bins per thread
@@ -277,7 +315,7 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     dev_tone_slots(P, T, tid, nt);
     __syncthreads();
     PHASE_MARK();   // 2 scatter
-    dev_chase_block(P, T, s_misc, tid);
+    dev_chase_block(P, T, s_misc, tid, A.dbg_cycles);
     PHASE_MARK();   // 3 chase
     // max_seeds gather, first half: one minimum per static group (lib/psy.c:522-533)
     for (int q = tid; q <= P.ngrp; q += nt) {
