@@ -188,6 +188,10 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     d.cls_run = reinterpret_cast<const int2 *>(dc);
     d.slot_rng = reinterpret_cast<const int2 *>(ds);
     d.linesper_log2 = f.linesper_log2;
+    { const int *drr = nullptr, *dlg = nullptr;
+      if ((rc = upload(c, f.runrec.data(), f.runrec.size(), &drr))) return rc;
+      if ((rc = upload(c, f.long_grp.data(), f.long_grp.size(), &dlg))) return rc;
+      d.runrec = reinterpret_cast<const int4 *>(drr); d.long_grp = dlg; d.nlong = (int)f.long_grp.size(); }
     { const short *db = nullptr; if ((rc = upload(c, f.bin_grp.data(), f.bin_grp.size(), &db))) return rc; d.bin_grp = db; }
     if (p.eighth_octave_lines > 32) return fail(VB200_EIMPL, "eighth_octave_lines > 32");
     if (p.total_octave_lines >= 2048) return fail(VB200_EIMPL, "total_octave_lines >= 2048");

@@ -57,6 +57,9 @@ struct PsyDev {
   const int2  *slot_rng;     // [total] candidate range in cls_run for every seed slot
   int linesper_log2;
   const short *bin_grp;      // [n] group of every bin (ngrp = the tail bins)
+  const int4  *runrec;       // [nruns] class-ordered: lo|hi<<16, oc-firstoc, band, bits(ath[hi])
+  const int   *long_grp;     // [nlong] groups folded cooperatively
+  int nlong;
   const int *cls_off;        // [L+1] (device) class c owns cls_run[cls_off[c] .. cls_off[c+1])
 };
 
@@ -700,12 +703,12 @@ __device__ __forceinline__ void dev_tone_runs(const PsyDev &P, const float *logf
   const float dBoffset = P.max_curve_dB - gmax;
   const int L = P.linesper, half = L >> 1, total = P.total;
   for (int k = tid; k < P.nruns; k += nt) {
-    const int2 cr = __ldg(P.cls_run + k);            // run id, oc - firstoc
-    const int4 ri = __ldg(P.runinfo + cr.x);         // lo, hi, oc - firstoc, band
+    const int4 rr = __ldg(P.runrec + k);             // lo|hi<<16, oc - firstoc, band, ath[hi]
+    int4 ri; ri.x = rr.x & 0xffff; ri.y = rr.x >> 16; ri.z = rr.y; ri.w = rr.z;
     float mx = logfft[ri.x];
     for (int i = ri.x + 1; i <= ri.y; i++) { const float v = logfft[i]; if (v > mx) mx = v; }
     int4 rec = make_int4(__float_as_int(mx), 0, 0, 0);
-    if (mx + 6.f > __ldg(P.ath + ri.y) + att) {
+    if (mx + 6.f > __int_as_float(rr.w) + att) {
       int choice = (int)((((double)(mx + dBoffset)) - 30.) * (double).1f);   // P_LEVEL_0 is a double
       if (choice < 0) choice = 0;
       if (choice > VB200_P_LEVELS - 1) choice = VB200_P_LEVELS - 1;

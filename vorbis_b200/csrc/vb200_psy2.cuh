@@ -322,6 +322,7 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
       float minV;
       if (q < P.ngrp) {
         const int4 gg = __ldg(P.grps + q);
+        if (gg.y - gg.x > 16) continue;                // long fold: done by a whole warp below
         int pos = gg.x;
         minV = T.seed[pos];
         if (minV > P.tone_abs_limit) minV = P.tone_abs_limit;
@@ -334,6 +335,29 @@ k_phaseA_psy2(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
         minV = T.seed[P.total - 1];                    // tail bins (lib/psy.c:540-544)
       }
       grp_min[q] = minV;
+    }
+    // long groups (the first few bins span tens of seed slots): the fold equals the minimum over
+    // the non-NEGINF seeds of the range, joined by tone_abs_limit iff the first seed is not
+    // NEGINF, and NEGINF if there is none - associative, so a warp reduces it with shuffles
+    for (int li = tid >> 5; li < P.nlong; li += nt >> 5) {
+      const int q = __ldg(P.long_grp + li);
+      const int4 gg = __ldg(P.grps + q);
+      float mn = 3.0e38f;
+      int any = 0;
+      for (int pos = gg.x + lane; pos <= gg.y; pos += 32) {
+        const float s = T.seed[pos];
+        if (s > VB_NEGINF) {
+          any = 1;
+          if (s < mn) mn = s;
+          if (pos == gg.x && P.tone_abs_limit < mn) mn = P.tone_abs_limit;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        any |= __shfl_xor_sync(0xffffffffu, any, o);
+      }
+      if (lane == 0) grp_min[q] = any ? mn : VB_NEGINF;
     }
     __syncthreads();                                   // tone scratch is dead from here on
     PHASE_MARK();   // 4 group minima

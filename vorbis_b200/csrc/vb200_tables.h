@@ -129,6 +129,8 @@ struct HostPsyFlow {
   std::vector<int> cls_off;                    // [L+1]
   std::vector<int> grp;                        // max_seeds groups: pos0,pos1,lin0,lin1 (lib/psy.c:522-538)
   int tail_lin0 = 0;
+  std::vector<int> runrec;                     // per class-ordered run: lo|hi<<16, oc-firstoc, band, bits(ath[hi])
+  std::vector<int> long_grp;                   // groups whose seed range is longer than 16 (folded by a whole warp)
   std::vector<short> bin_grp;                  // per bin: its max_seeds group, ngrp for the tail bins
   int bark_first_extra = 0;                    // first bin that reuses the last A,B,D (lib/psy.c:604-658)
   int fixed_first_extra = 0;                   // same for the fixed window (lib/psy.c:660-703)
@@ -168,6 +170,13 @@ inline void build_psy_flow(HostPsyFlow &f, const vb200_psy_setup &s) {
         if ((((oc[r] - half) % L) + L) % L == c) { f.cls_run.push_back(r); f.cls_run.push_back(oc[r]); }
     }
     cls_off[L] = (int)f.cls_run.size() / 2;
+    f.runrec.clear();
+    for (size_t k = 0; k < f.cls_run.size() / 2; k++) {
+      const int r = f.cls_run[2 * k];
+      union { float fl; int i; } u; u.fl = s.ath[f.run_hi[r]];
+      f.runrec.push_back(f.run_lo[r] | (f.run_hi[r] << 16));
+      f.runrec.push_back(f.runinfo[4 * r + 2]); f.runrec.push_back(f.runinfo[4 * r + 3]); f.runrec.push_back(u.i);
+    }
     for (int sp = 1; sp < total; sp++) {
       const int c = sp % L;
       int k0 = cls_off[c + 1], k1 = cls_off[c];
@@ -194,6 +203,8 @@ inline void build_psy_flow(HostPsyFlow &f, const vb200_psy_setup &s) {
     }
     f.tail_lin0 = (int)linpos;
     const int ng = (int)f.grp.size() / 4;
+    f.long_grp.clear();
+    for (int gi = 0; gi < ng; gi++) if (f.grp[4 * gi + 1] - f.grp[4 * gi] > 16) f.long_grp.push_back(gi);
     f.bin_grp.assign(n, (short)ng);
     for (int gi = 0; gi < ng; gi++)
       for (int i = f.grp[4 * gi + 2]; i < f.grp[4 * gi + 3]; i++) f.bin_grp[i] = (short)gi;
