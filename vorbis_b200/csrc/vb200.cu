@@ -315,13 +315,14 @@ __global__ void __launch_bounds__(256)
 k_drft_forward(XformDev X, int nvec, float *__restrict__ data) {
   extern __shared__ __align__(16) float sm[];
   const int N = X.N, tid = threadIdx.x, nt = blockDim.x;
-  float *sa = sm, *sb = sm + N;
+  float *sa = sm, *sb = sm + N + 4;
   for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
     float4 *g = reinterpret_cast<float4 *>(data + (size_t)v * N);
     for (int i = tid; i < (N >> 2); i += nt) reinterpret_cast<float4 *>(sa)[i] = g[i];
     __syncthreads();
     const float *r = dev_drft_forward<0>(X, sa, sb, tid, nt);
-    for (int i = tid; i < (N >> 2); i += nt) g[i] = reinterpret_cast<const float4 *>(r)[i];
+    float *gs = data + (size_t)v * N;
+    for (int i = tid; i < N; i += nt) gs[i] = r[i];
     __syncthreads();
   }
 }
@@ -337,7 +338,7 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
   extern __shared__ __align__(16) float sm[];
   __shared__ float s_red[8];
   const int N = NC ? NC : X.N, n = N >> 1, tid = threadIdx.x, nt = blockDim.x;
-  float *sx = sm, *sw = sm + N, *sf = sm + 2 * N;
+  float *sx = sm, *sw = sm + N + 4, *sf = sm + 2 * N + 4;   // sx and sf hold N+2 (shifted FFT passes)
   const float scale = 4.f / (float)N;
   const float scale_dB = add345(todB_dev(scale));
   for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
@@ -355,7 +356,8 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
       if (k == 0) {
         v = add345(scale_dB + todB_dev(f[0]));
       } else {
-        const float re = f[2 * k - 1], im = f[2 * k];
+        const float2 c = *reinterpret_cast<const float2 *>(f + 2 * k - 1);   // aligned: f is shifted by one
+        const float re = c.x, im = c.y;
         const float t = re * re + im * im;
         v = add345(scale_dB + .5f * todB_dev(t));
       }
@@ -752,7 +754,7 @@ extern "C" int vb200_drft_forward(vb200_ctx *c, int W, int nvec, float *data) {
   HostIO io{c};
   void *dd; int rc;
   if ((rc = io.h2d(data, sizeof(float) * (size_t)nvec * X.N, &dd))) return rc;
-  const size_t smem = sizeof(float) * 2 * X.N;
+  const size_t smem = sizeof(float) * (2 * X.N + 8);
   if ((rc = set_smem(k_drft_forward, smem))) return rc;
   k_drft_forward<<<grid_for(c, nvec, 8), threads_for(X.N), smem, c->s_main>>>(X, nvec, (float *)dd);
   if ((rc = post_launch(c))) return rc;
@@ -843,7 +845,7 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
   const int rows = nblocks * ch;
   if (c->profiling) CU(cudaEventRecord(c->ev[0], st));
   {
-    const size_t smem = sizeof(float) * 3 * N;
+    const size_t smem = sizeof(float) * (3 * N + 8);
     int rc;
     float *mdct_raw = io->tap_mdct_raw ? io->tap_mdct_raw : io->mdct;
     const int grid = grid_for(c, rows, 8), nt = threads_for(N);

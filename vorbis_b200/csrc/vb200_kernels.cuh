@@ -323,12 +323,11 @@ __device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, 
     for (int k = tid; k < l1; k += nt) {
       const float c0 = cc[k], c1 = cc[k + t0], c2 = cc[k + 2 * t0], c3 = cc[k + 3 * t0];
       const float tr1 = c1 + c3, tr2 = c0 + c2;
-      float4 o;
-      o.x = tr1 + tr2;       // o[0]
-      o.y = c0 - c2;         // o[2*ido-1] = o[1]
-      o.z = c3 - c1;         // o[2*ido]   = o[2]
-      o.w = tr2 - tr1;       // o[4*ido-1] = o[3]
-      *reinterpret_cast<float4 *>(ch + 4 * k) = o;
+      // ch is shifted by one float (see dev_drft_forward): 4k+1,4k+2 form the aligned pair
+      float *o = ch + 4 * k;
+      o[0] = tr1 + tr2;                                                   // o[0]
+      *reinterpret_cast<float2 *>(o + 1) = make_float2(c0 - c2, c3 - c1); // o[2*ido-1], o[2*ido]
+      o[3] = tr2 - tr1;                                                   // o[4*ido-1]
     }
     return;
   }
@@ -352,21 +351,27 @@ __device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, 
         const float wa1r = __ldg(w1 + i - 2), wa1i = __ldg(w1 + i - 1);
         const float wa2r = __ldg(w2 + i - 2), wa2i = __ldg(w2 + i - 1);
         const float wa3r = __ldg(w3 + i - 2), wa3i = __ldg(w3 + i - 1);
-        const float cr2 = wa1r * c1[i - 1] + wa1i * c1[i];
-        const float ci2 = wa1r * c1[i]     - wa1i * c1[i - 1];
-        const float cr3 = wa2r * c2[i - 1] + wa2i * c2[i];
-        const float ci3 = wa2r * c2[i]     - wa2i * c2[i - 1];
-        const float cr4 = wa3r * c3[i - 1] + wa3i * c3[i];
-        const float ci4 = wa3r * c3[i]     - wa3i * c3[i - 1];
+        // (re,im) pairs sit at (i-1,i); the buffers are shifted by one float so that they are
+        // 8-byte aligned: one 64-bit access per pair, consecutive lanes on consecutive banks
+        const float2 a0 = *reinterpret_cast<const float2 *>(c0 + i - 1);
+        const float2 a1 = *reinterpret_cast<const float2 *>(c1 + i - 1);
+        const float2 a2 = *reinterpret_cast<const float2 *>(c2 + i - 1);
+        const float2 a3 = *reinterpret_cast<const float2 *>(c3 + i - 1);
+        const float cr2 = wa1r * a1.x + wa1i * a1.y;
+        const float ci2 = wa1r * a1.y - wa1i * a1.x;
+        const float cr3 = wa2r * a2.x + wa2i * a2.y;
+        const float ci3 = wa2r * a2.y - wa2i * a2.x;
+        const float cr4 = wa3r * a3.x + wa3i * a3.y;
+        const float ci4 = wa3r * a3.y - wa3i * a3.x;
         const float tr1 = cr2 + cr4, tr4 = cr4 - cr2;
         const float ti1 = ci2 + ci4, ti4 = ci2 - ci4;
-        const float ti2 = c0[i] + ci3,     ti3 = c0[i] - ci3;
-        const float tr2 = c0[i - 1] + cr3, tr3 = c0[i - 1] - cr3;
+        const float ti2 = a0.y + ci3, ti3 = a0.y - ci3;
+        const float tr2 = a0.x + cr3, tr3 = a0.x - cr3;
         const int ic = 2 * ido - i;
-        o[i - 1]            = tr1 + tr2;   o[i]            = ti1 + ti2;
-        o[ic - 1]           = tr3 - ti4;   o[ic]           = tr4 - ti3;
-        o[2 * ido + i - 1]  = ti4 + tr3;   o[2 * ido + i]  = tr4 + ti3;
-        o[2 * ido + ic - 1] = tr2 - tr1;   o[2 * ido + ic] = ti1 - ti2;
+        *reinterpret_cast<float2 *>(o + i - 1)            = make_float2(tr1 + tr2, ti1 + ti2);
+        *reinterpret_cast<float2 *>(o + ic - 1)           = make_float2(tr3 - ti4, tr4 - ti3);
+        *reinterpret_cast<float2 *>(o + 2 * ido + i - 1)  = make_float2(ti4 + tr3, tr4 + ti3);
+        *reinterpret_cast<float2 *>(o + 2 * ido + ic - 1) = make_float2(tr2 - tr1, ti1 - ti2);
       }
     } else {
       const int k = v - items;
@@ -407,11 +412,13 @@ __device__ __forceinline__ void dev_fft_pass2(int ido, int l1, const float *cc, 
       } else {
         const int i = 2 * ii;
         const float wr = __ldg(w1 + i - 2), wi = __ldg(w1 + i - 1);
-        const float tr2 = wr * c1[i - 1] + wi * c1[i];
-        const float ti2 = wr * c1[i]     - wi * c1[i - 1];
+        const float2 a0 = *reinterpret_cast<const float2 *>(c0 + i - 1);
+        const float2 a1 = *reinterpret_cast<const float2 *>(c1 + i - 1);
+        const float tr2 = wr * a1.x + wi * a1.y;
+        const float ti2 = wr * a1.y - wi * a1.x;
         const int ic = 2 * ido - i;
-        o[i]      = c0[i] + ti2;       o[ic]     = ti2 - c0[i];
-        o[i - 1]  = c0[i - 1] + tr2;   o[ic - 1] = c0[i - 1] - tr2;
+        *reinterpret_cast<float2 *>(o + i - 1)  = make_float2(a0.x + tr2, a0.y + ti2);
+        *reinterpret_cast<float2 *>(o + ic - 1) = make_float2(a0.x - tr2, ti2 - a0.y);
       }
     } else {
       const int k = v - items;
@@ -423,7 +430,10 @@ __device__ __forceinline__ void dev_fft_pass2(int ido, int l1, const float *cc, 
   }
 }
 
-// Returns the buffer (a or b) that holds the transform of the data in `a`.
+// a: N input floats (16-byte aligned, unshifted).  a and b must each have room for N+2 floats.
+// Every pass writes its output shifted by ONE float (logical element e at address e+1) so that
+// FFTPACK's (re,im) pairs at (2k-1,2k) are 8-byte aligned; the first pass (ido == 1, no pairs)
+// reads the unshifted input.  Returns a pointer to logical element 0 of the result.
 template <int NC>
 __device__ __forceinline__ float *dev_drft_forward(const XformDev &X, float *a, float *b,
                                                    int tid, int nt) {
@@ -433,7 +443,7 @@ __device__ __forceinline__ float *dev_drft_forward(const XformDev &X, float *a, 
   const int log2n = NC ? XLog2<NC>::v : X.log2n;
   const int nf = (log2n + 1) >> 1;
   int l2 = N, iw = N;
-  float *src = a, *dst = b;
+  float *src = a, *dst = b + 1;
 #pragma unroll
   for (int k1 = 0; k1 < nf; k1++) {
     const int ip = (k1 == nf - 1 && (log2n & 1)) ? 2 : 4;
@@ -444,7 +454,8 @@ __device__ __forceinline__ float *dev_drft_forward(const XformDev &X, float *a, 
     else
       dev_fft_pass2(ido, l1, src, dst, X.wa + iw - 1, tid, nt);
     __syncthreads();
-    float *t = src; src = dst; dst = t;
+    float *t = (k1 == 0) ? a + 1 : src;     // after the first pass `a` is reused shifted as well
+    src = dst; dst = t;
     l2 = l1;
   }
   return src;
