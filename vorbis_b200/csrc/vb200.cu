@@ -608,7 +608,9 @@ k_decouple(int n, int ch, int steps, const int *__restrict__ mag, const int *__r
 // ======================================================================== //
 // launch helpers
 static int threads_for(int N) {
-  int t = N / 8;
+  int div = 8;
+  { const char *e = getenv("VB200_XF_DIV"); if (e && atoi(e) > 0) div = atoi(e); }
+  int t = N / div;
   if (t < 64) t = 64;
   if (t > 256) t = 256;
   return t;
