@@ -9,12 +9,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CONFIG_NAMES = ["44k_stereo_q5", "44k_stereo_q1", "44k_mono_q4", "22k_mono_q3"]
+CONFIG_NAMES = ["44k_stereo_q5", "44k_stereo_q1", "44k_mono_q4", "22k_mono_q3", "48k_6ch_q2"]
 REF_ARGS = {  # the vorbis_encode_init_vbr arguments each fixture was generated with
     "44k_stereo_q5": (2, 44100, 0.5),
     "44k_stereo_q1": (2, 44100, 0.1),
     "44k_mono_q4": (1, 44100, 0.4),
     "22k_mono_q3": (1, 22050, 0.3),
+    "48k_6ch_q2": (6, 48000, 0.2),
 }
 
 

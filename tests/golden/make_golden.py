@@ -31,6 +31,7 @@ CONFIGS = {
     "44k_stereo_q1": (2, 44100, 0.1, 1.0, 3, 4),   # noise normalisation active
     "44k_mono_q4": (1, 44100, 0.4, 1.0, 3, 2),     # BASELINE config 1 shape (uncoupled)
     "22k_mono_q3": (1, 22050, 0.3, 1.0, 3, 2),     # 512/1024 blocks
+    "48k_6ch_q2": (6, 48000, 0.2, 0.5, 2, 2),      # 5.1: four coupling steps, noise norm active
 }
 
 
@@ -42,8 +43,8 @@ def signal(ch, rate, secs, seed):
     t = np.arange(ns)
     pcm = np.stack([0.25 * rng.uniform(-1, 1, ns) + 0.5 * np.sin(2 * np.pi * (440 + 110 * c) * t / rate)
                     for c in range(ch)]).astype(np.float32)
-    if ch == 2:
-        pcm[1] = (0.6 * pcm[0] + 0.4 * pcm[1]).astype(np.float32)
+    for c in range(1, ch):                        # correlated channels so that coupling has work to do
+        pcm[c] = (0.6 * pcm[0] + 0.4 * pcm[c]).astype(np.float32)
     a = ns // 2
     pcm[:, a:a + 300] *= 0.01
     pcm[:, a + 300:a + 400] = rng.uniform(-0.9, 0.9, (ch, 100)).astype(np.float32)

@@ -12,7 +12,7 @@ from oracle import pyref
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("ch,rate,q", [(2, 44100, 0.5), (1, 44100, 0.4), (2, 44100, 0.1)])
+@pytest.mark.parametrize("ch,rate,q", [(2, 44100, 0.5), (1, 44100, 0.4), (2, 44100, 0.1), (6, 48000, 0.2)])
 def test_encoder_packets_identical(cuda_ok, ch, rate, q):
     if not (pyref.available() and pyref.dropin_available()):
         pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
