@@ -187,6 +187,22 @@ int vb200_analysis_phaseA    (vb200_ctx*, int W, int nblocks, const vb200_phaseA
 int vb200_analysis_phaseA_streams_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream,
                                       const vb200_phaseA_io *d_io, const float *d_ampmax0, void *stream);
 
+/* ---- PCM ingest fused into Phase A -----------------------------------------
+ * Each stream's PCM is ONE contiguous buffer; block k of a stream is the N samples that start
+ * at sample k*hop - exactly what vorbis_analysis_blockout copies out of v->pcm (lib/block.c:630-643;
+ * hop = N/2 for a run of equal-size blocks), so the 50 % overlap is never duplicated in memory.
+ *   fmt VB200_PCM_F32_PLANAR : float [stream][ch][stream_stride]
+ *   fmt VB200_PCM_S16_INTERLEAVED : int16 [stream][stream_stride][ch], converted sample/32768.f
+ *       as examples/encoder_example.c:196-201 does
+ * io->pcm is ignored; everything else as vb200_analysis_phaseA_streams_dev (ampmax chain on device,
+ * d_ampmax0 may be NULL).  stream_stride counts samples per channel; it and hop must be multiples
+ * of 4 for the float format.                                                                 */
+#define VB200_PCM_F32_PLANAR       1
+#define VB200_PCM_S16_INTERLEAVED  2
+int vb200_analysis_phaseA_pcmstream_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream,
+                                        const void *d_pcm, int fmt, int64_t stream_stride, int hop,
+                                        const vb200_phaseA_io *d_io, const float *d_ampmax0, void *stream);
+
 /* ---- encode Phase B: _vp_couple_quantize_normalize, lib/psy.c:1014 ----
  * mdct  [nblocks][ch][n]  (Phase A output)
  * iwork [nblocks][ch][n]  in: ilogmask from floor1_encode (0..1023 dB index,
@@ -209,6 +225,11 @@ int vb200_couple_quantize_normalize    (vb200_ctx*, int W, int blocktype, int bl
 int vb200_synthesis_dev(vb200_ctx*, int nstreams, int nblk, const int32_t *d_Wseq,
                         const int64_t *d_coef_off, const float *d_coef,
                         const int64_t *d_pcm_off, float *d_pcm, int64_t pcm_stride, void *stream);
+/* same, but the finished samples leave as interleaved int16 [stream][pcm_stride][ch]:
+ * floor(x*32767.f+.5f) clipped to [-32768,32767] (examples/decoder_example.c:250-262)          */
+int vb200_synthesis_s16_dev(vb200_ctx*, int nstreams, int nblk, const int32_t *d_Wseq,
+                            const int64_t *d_coef_off, const float *d_coef,
+                            const int64_t *d_pcm_off, int16_t *d_pcm16, int64_t pcm_stride, void *stream);
 int vb200_synthesis    (vb200_ctx*, int nstreams, int nblk, const int32_t *Wseq,
                         const int64_t *coef_off, const float *coef, int64_t coef_len,
                         const int64_t *pcm_off, float *pcm, int64_t pcm_stride);

@@ -301,3 +301,105 @@ def test_phaseA_generic_kernel_path(cfg, monkeypatch):
     monkeypatch.delenv("VB200_PSY_V1")
     for k, g in (("noise", "noise"), ("tone", "tone"), ("logmask", "logmask"), ("mdct", "mdct_m1")):
         assert_bits_equal(out[k], enc["L_" + g], "generic kernel " + k)
+
+
+@pytest.mark.parametrize("W", [0, 1])
+def test_phaseA_adversarial_inputs(cfg, W):
+    """impulses, DC, full-scale square waves, denormals, huge and tiny amplitudes, exact zeros in one
+    channel only: the CUDA chain must follow the reference arithmetic (oracle) bit for bit"""
+    name, setup, ctx, o, enc, _ = cfg
+    N, ch = setup.blocksize(W), setup.channels
+    rng = np.random.default_rng(2718 + W)
+    t = np.arange(N)
+    cases = []
+    imp = np.zeros((ch, N), np.float32); imp[:, N // 2] = 1.0; cases.append(imp)
+    imp2 = np.zeros((ch, N), np.float32); imp2[0, 3] = -1.0; cases.append(imp2)
+    cases.append(np.full((ch, N), 0.999, np.float32))
+    sq = np.where((t // 16) % 2 == 0, 1.0, -1.0).astype(np.float32); cases.append(np.tile(sq, (ch, 1)))
+    cases.append(np.full((ch, N), 1e-40, np.float32))                     # denormal PCM
+    cases.append((rng.uniform(-1, 1, (ch, N)) * 1e-30).astype(np.float32))
+    cases.append((rng.uniform(-1, 1, (ch, N)) * 1e6).astype(np.float32))  # far beyond full scale
+    oz = rng.uniform(-0.5, 0.5, (ch, N)).astype(np.float32); oz[-1] = 0.0; cases.append(oz)
+    cases.append(np.tile(np.sin(2 * np.pi * 1000.0 * t / setup.rate).astype(np.float32), (ch, 1)))
+    cases.append(np.tile(np.float32(0.5) * np.sign(np.sin(2 * np.pi * 6000.0 * t / setup.rate)).astype(np.float32), (ch, 1)))
+    pcm = np.stack(cases)
+    nb = len(cases)
+    desc = np.zeros(nb, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = (np.arange(nb) % 2) if W else 0
+    desc["nW"] = ((np.arange(nb) // 2) % 2) if W else 0
+    desc["blocktype"] = np.arange(nb) % 2
+    desc["ampmax"] = np.where(np.arange(nb) % 3 == 0, -9999.0, -1.5).astype(np.float32)
+    a = ctx.phaseA(W, pcm, desc, taps=True)
+    b = o.phaseA(W, pcm, desc, taps=True)
+    for k in ("mdct_raw", "logfft", "noise", "tone", "logmdct", "logmask", "mdct", "ampmax_out"):
+        assert_bits_equal(a[k], b[k], "adversarial " + k)
+
+
+@pytest.mark.parametrize("fmt", ["f32", "s16"])
+def test_phaseA_pcm_ingest_from_stream_buffers(cfg, fmt):
+    """blocks cut on the device out of one contiguous buffer per stream (hop = N/2,
+    lib/block.c:630-643), float planar or interleaved int16 (/32768.f, examples/encoder_example.c:196-201);
+    must equal the block-layout path fed the same samples (checked against the oracle's stream mode)"""
+    import torch
+    name, setup, ctx, o, _, _ = cfg
+    W = 1
+    N, ch = setup.blocksize(W), setup.channels
+    hop, ns, bps = N // 2, 5, 6
+    stride = (bps - 1) * hop + N + 8
+    rng = np.random.default_rng(123)
+    t = np.arange(stride)
+    s16 = np.clip(6000 * rng.standard_normal((ns, stride, ch)) +
+                  12000 * np.sin(2 * np.pi * 523.0 * t / setup.rate)[None, :, None], -32768, 32767).astype(np.int16)
+    f32 = (s16.astype(np.float32) / np.float32(32768.0))            # [ns][stride][ch]
+    planar = np.ascontiguousarray(f32.transpose(0, 2, 1))           # [ns][ch][stride]
+    blocks = np.stack([planar[s, :, k * hop:k * hop + N] for s in range(ns) for k in range(bps)])
+    desc = np.zeros(ns * bps, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = 1; desc["nW"] = 1; desc["blocktype"] = 1
+    want = o.phaseA(W, blocks, desc, streams=(ns, bps))
+    dev = torch.device("cuda", 0)
+    d_desc = torch.from_numpy(desc.view(np.uint8).reshape(-1, 16).copy()).to(dev)
+    outs = {k: torch.empty((ns * bps, ch, N // 2), device=dev) for k in ("mdct", "logmdct", "logmask")}
+    d_amp = torch.empty(ns * bps, device=dev)
+    io = abi.PhaseAIO()
+    io.desc = d_desc.data_ptr()
+    io.mdct, io.logmdct, io.logmask = (outs[k].data_ptr() for k in ("mdct", "logmdct", "logmask"))
+    io.ampmax_out = d_amp.data_ptr()
+    if fmt == "s16":
+        d_pcm = torch.from_numpy(s16).to(dev)
+        ctx.phaseA_pcmstream_dev(W, ns, bps, d_pcm.data_ptr(), vlib.PCM_S16_INTERLEAVED, stride, hop, io,
+                                 stream=torch.cuda.current_stream().cuda_stream)
+    else:
+        d_pcm = torch.from_numpy(planar).to(dev)
+        ctx.phaseA_pcmstream_dev(W, ns, bps, d_pcm.data_ptr(), vlib.PCM_F32_PLANAR, stride, hop, io,
+                                 stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for k in ("mdct", "logmdct", "logmask"):
+        assert_bits_equal(outs[k].cpu().numpy(), want[k], "pcm ingest %s %s" % (fmt, k))
+    assert_bits_equal(d_amp.cpu().numpy(), want["ampmax_out"], "pcm ingest ampmax")
+
+
+def test_decode_int16_egress(cfg):
+    """finished samples as interleaved int16: floor(x*32767.f+.5f), clipped (examples/decoder_example.c:250-262)"""
+    import torch
+    name, setup, ctx, o, _, dec = cfg
+    bs = [setup.blocksize(0), setup.blocksize(1)]
+    ch = setup.channels
+    rng = np.random.default_rng(77)
+    ns, nblk = 6, 9
+    Wseq = rng.integers(0, 2, (ns, nblk)).astype(np.int32)
+    coef_off, pcm_off, coef_len, pcm_len = vlib.synthesis_layout(Wseq, bs, ch)
+    coef = (rng.uniform(-1, 1, coef_len) * 0.08).astype(np.float32)      # loud enough to clip sometimes
+    ref_f = o.synthesis(Wseq, coef_off, coef, pcm_off, pcm_len)          # [ns][ch][len] float
+    want = np.floor(ref_f * np.float32(32767.0) + np.float32(0.5))
+    want = np.clip(want, -32768, 32767).astype(np.int16).transpose(0, 2, 1)   # [ns][len][ch]
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(v).to(dev) for k, v in
+         (("W", Wseq), ("co", coef_off), ("c", coef), ("po", pcm_off))}
+    out = torch.zeros((ns, pcm_len, ch), dtype=torch.int16, device=dev)
+    ctx.synthesis_s16_dev(ns, nblk, d["W"].data_ptr(), d["co"].data_ptr(), d["c"].data_ptr(), d["po"].data_ptr(),
+                          out.data_ptr(), pcm_len, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert (np.abs(want.astype(np.int32)) == 32767).any() or (want == -32768).any(), "test signal should clip"
+    # only positions that blocks actually finish are written; the layout leaves no gaps
+    assert np.array_equal(got, want)

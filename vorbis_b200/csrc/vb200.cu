@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "vorbis_b200.h"
@@ -330,10 +331,20 @@ k_drft_forward(XformDev X, int nvec, float *__restrict__ data) {
 // ---- Phase A, kernel 1: per (block, channel) window + MDCT + FFT + log spectrum.
 // Reads 4N bytes of PCM, writes mdct (2N), logfft (2N) and one local_ampmax.
 // (first per-channel loop of mapping0_forward, lib/mapping0.c:254-360)
+// where a row's N samples come from: block layout (fmt 0), or a contiguous per-stream buffer
+// from which block k is the window starting at k*hop (lib/block.c:630-643), float planar or
+// interleaved int16 (examples/encoder_example.c:196-201)
+struct PcmSrc {
+  const void *base;
+  int fmt;                 // 0 blocks [row][N] f32, VB200_PCM_F32_PLANAR, VB200_PCM_S16_INTERLEAVED
+  int bps, hop;
+  long long stride;        // samples per channel per stream
+};
+
 template <int NC>
 __global__ void __launch_bounds__(256)
 k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
-                   const float *__restrict__ pcm, const vb200_block_desc *__restrict__ desc,
+                   PcmSrc src, const vb200_block_desc *__restrict__ desc,
                    float *__restrict__ mdct, float *__restrict__ logfft, float *__restrict__ lmax) {
   extern __shared__ __align__(16) float sm[];
   __shared__ float s_red[8];
@@ -344,7 +355,26 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
   for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
     const int blk = row / ch;
     const int lW = desc[blk].lW, nW = desc[blk].nW;
-    dev_load_windowed(Wd, W, lW, nW, pcm + (size_t)row * N, sx, tid, nt);
+    if (src.fmt == VB200_PCM_S16_INTERLEAVED) {
+      const int c = row - blk * ch, st = blk / src.bps, k = blk - st * src.bps;
+      const short *p16 = reinterpret_cast<const short *>(src.base) +
+                         ((long long)st * src.stride + (long long)k * src.hop) * ch + c;
+      for (int i = tid; i < N; i += nt) {
+        bool z;
+        const float g = dev_window_gain(Wd, W, lW, nW, i, z);
+        const float v = (float)__ldg(p16 + (long long)i * ch) / 32768.f;
+        sx[i] = z ? 0.f : v * g;
+      }
+    } else {
+      const float *pf = reinterpret_cast<const float *>(src.base);
+      if (src.fmt == VB200_PCM_F32_PLANAR) {
+        const int c = row - blk * ch, st = blk / src.bps, k = blk - st * src.bps;
+        pf += ((long long)st * ch + c) * src.stride + (long long)k * src.hop;
+      } else {
+        pf += (size_t)row * N;
+      }
+      dev_load_windowed(Wd, W, lW, nW, pf, sx, tid, nt);
+    }
     __syncthreads();
     dev_mdct_forward<NC>(X, sx, sw, mdct + (size_t)row * n, tid, nt);
     const float *f = dev_drft_forward<NC>(X, sx, sf, tid, nt);
@@ -536,11 +566,27 @@ k_offset_and_mix(PsyDev P, int nvec, int sel, const float *__restrict__ noise,
 // vorbis_synthesis_blockin (lib/block.c:767-823).  One CTA walks one (stream, channel)
 // block by block; the previous block's second half stays in shared memory, so the only
 // HBM traffic is the spectra in (2N) and the finished samples out (2N per channel-block).
+// finished-sample sinks: planar float, or interleaved int16 as examples/decoder_example.c:250-262
+struct SinkF32 {
+  float *p;
+  __device__ __forceinline__ void put(int i, float v) const { p[i] = v; }
+};
+struct SinkS16 {
+  short *p; int ch;
+  __device__ __forceinline__ void put(int i, float v) const {
+    int val = (int)floorf(v * 32767.f + .5f);
+    if (val > 32767) val = 32767;
+    if (val < -32768) val = -32768;
+    p[(long long)i * ch] = (short)val;
+  }
+};
+
+template <bool S16>
 __global__ void __launch_bounds__(256)
 k_synthesis(XformDev X0, XformDev X1, WinDev Wd, int ch, int nstreams, int nblk,
             const int *__restrict__ Wseq, const long long *__restrict__ coef_off,
             const float *__restrict__ coef, const long long *__restrict__ pcm_off,
-            float *__restrict__ pcm, long long pcm_stride) {
+            void *__restrict__ pcm_out, long long pcm_stride) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, nt = blockDim.x;
   const int n0 = X0.N >> 1, n1 = X1.N >> 1;
@@ -549,7 +595,6 @@ k_synthesis(XformDev X0, XformDev X1, WinDev Wd, int ch, int nstreams, int nblk,
   const int off = n1 / 2 - n0 / 2;
   for (int task = blockIdx.x; task < nstreams * ch; task += gridDim.x) {
     const int st = task / ch, c = task - st * ch;
-    float *dst0 = pcm + ((size_t)st * ch + c) * pcm_stride;
     int lW = 0;
     for (int k = 0; k < nblk; k++) {
       const int W = Wseq[(size_t)st * nblk + k];
@@ -560,18 +605,25 @@ k_synthesis(XformDev X0, XformDev X1, WinDev Wd, int ch, int nstreams, int nblk,
       __syncthreads();
       dev_mdct_backward<0>(X, s_in, s_out, tid, nt);
       if (k > 0) {
-        float *dst = dst0 + pcm_off[(size_t)st * nblk + k];
+        const long long o = pcm_off[(size_t)st * nblk + k];
+        typename std::conditional<S16, SinkS16, SinkF32>::type dst;
+        if constexpr (S16) {
+          dst.p = reinterpret_cast<short *>(pcm_out) + ((long long)st * pcm_stride + o) * ch + c;
+          dst.ch = ch;
+        } else {
+          dst.p = reinterpret_cast<float *>(pcm_out) + ((size_t)st * ch + c) * pcm_stride + o;
+        }
         const float *R = s_prev, *Lh = s_out;
         if (lW && W) {
-          for (int i = tid; i < n1; i += nt) dst[i] = R[i] * __ldg(w1 + n1 - i - 1) + Lh[i] * __ldg(w1 + i);
+          for (int i = tid; i < n1; i += nt) dst.put(i, R[i] * __ldg(w1 + n1 - i - 1) + Lh[i] * __ldg(w1 + i));
         } else if (lW && !W) {
-          for (int i = tid; i < off; i += nt) dst[i] = R[i];
-          for (int i = tid; i < n0; i += nt) dst[off + i] = R[off + i] * __ldg(w0 + n0 - i - 1) + Lh[i] * __ldg(w0 + i);
+          for (int i = tid; i < off; i += nt) dst.put(i, R[i]);
+          for (int i = tid; i < n0; i += nt) dst.put(off + i, R[off + i] * __ldg(w0 + n0 - i - 1) + Lh[i] * __ldg(w0 + i));
         } else if (!lW && W) {
           for (int i = tid; i < n1 / 2 + n0 / 2; i += nt)
-            dst[i] = i < n0 ? R[i] * __ldg(w0 + n0 - i - 1) + Lh[off + i] * __ldg(w0 + i) : Lh[off + i];
+            dst.put(i, i < n0 ? R[i] * __ldg(w0 + n0 - i - 1) + Lh[off + i] * __ldg(w0 + i) : Lh[off + i]);
         } else {
-          for (int i = tid; i < n0; i += nt) dst[i] = R[i] * __ldg(w0 + n0 - i - 1) + Lh[i] * __ldg(w0 + i);
+          for (int i = tid; i < n0; i += nt) dst.put(i, R[i] * __ldg(w0 + n0 - i - 1) + Lh[i] * __ldg(w0 + i));
         }
       }
       __syncthreads();
@@ -841,7 +893,10 @@ extern "C" int vb200_offset_and_mix(vb200_ctx *c, int look, int nvec, int sel, c
 // Phase A
 static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io,
                          int nstreams, int bps, const float *d_amp0, cudaStream_t st,
-                         float *d_logfft, float *d_lmax, float *d_gmax) {
+                         float *d_logfft, float *d_lmax, float *d_gmax, const PcmSrc *pcmsrc = nullptr) {
+  PcmSrc psrc;
+  if (pcmsrc) psrc = *pcmsrc;
+  else { psrc.base = io->pcm; psrc.fmt = 0; psrc.bps = 1; psrc.hop = 0; psrc.stride = 0; }
   const XformDev &X = c->dx[W];
   const int ch = c->setup.channels, N = X.N;
   const int rows = nblocks * ch;
@@ -854,7 +909,7 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
 #define LAUNCH_XF(NN)                                                                        \
     do {                                                                                     \
       if ((rc = set_smem(k_phaseA_transform<NN>, smem))) return rc;                          \
-      k_phaseA_transform<NN><<<grid, nt, smem, st>>>(X, c->dwin, W, ch, rows, io->pcm, io->desc, \
+      k_phaseA_transform<NN><<<grid, nt, smem, st>>>(X, c->dwin, W, ch, rows, psrc, io->desc,    \
                                                      mdct_raw, d_logfft, d_lmax);            \
     } while (0)
     switch (N) {
@@ -954,10 +1009,11 @@ static int ensure_buf(DevBuf &b, size_t bytes, void **out) {
 }
 
 static int phaseA_dev_common(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io,
-                             int nstreams, int bps, const float *d_amp0, void *stream) {
+                             int nstreams, int bps, const float *d_amp0, void *stream,
+                             const PcmSrc *pcmsrc = nullptr) {
   CHECK_CTX(c); CHECK_W(W);
   if (c->n_psy != 4) return fail(VB200_EIMPL, "context has no psy lookups");
-  if (!io || !io->pcm || !io->desc || !io->mdct || !io->logmdct || !io->logmask || !io->ampmax_out)
+  if (!io || (!io->pcm && !pcmsrc) || !io->desc || !io->mdct || !io->logmdct || !io->logmask || !io->ampmax_out)
     return fail(VB200_EINVAL, "phase A io pointers");
   if (nblocks <= 0) return 0;
   const int ch = c->setup.channels, n = c->dx[W].N / 2;
@@ -966,7 +1022,22 @@ static int phaseA_dev_common(vb200_ctx *c, int W, int nblocks, const vb200_phase
   if ((rc = ensure(c, 14, sizeof(float) * (size_t)nblocks * ch, &d_lmax))) return rc;
   if ((rc = ensure(c, 15, sizeof(float) * (size_t)nblocks, &d_gmax))) return rc;
   return phaseA_launch(c, W, nblocks, io, nstreams, bps, d_amp0, (cudaStream_t)stream,
-                       (float *)d_logfft, (float *)d_lmax, (float *)d_gmax);
+                       (float *)d_logfft, (float *)d_lmax, (float *)d_gmax, pcmsrc);
+}
+
+extern "C" int vb200_analysis_phaseA_pcmstream_dev(vb200_ctx *c, int W, int nstreams, int bps,
+                                                   const void *d_pcm, int fmt, int64_t stream_stride, int hop,
+                                                   const vb200_phaseA_io *io, const float *d_amp0, void *stream) {
+  if (nstreams <= 0 || bps <= 0) return fail(VB200_EINVAL, "nstreams/blocks_per_stream");
+  if (!d_pcm) return fail(VB200_EINVAL, "null pcm");
+  if (fmt != VB200_PCM_F32_PLANAR && fmt != VB200_PCM_S16_INTERLEAVED) return fail(VB200_EINVAL, "pcm format");
+  if (hop <= 0 || stream_stride <= 0) return fail(VB200_EINVAL, "hop/stream_stride");
+  if (fmt == VB200_PCM_F32_PLANAR && ((hop & 3) || (stream_stride & 3)))
+    return fail(VB200_EINVAL, "hop and stream_stride must be multiples of 4 for float PCM");
+  if (!c || W < 0 || W > 1) return fail(VB200_EINVAL, "ctx/W");
+  if ((int64_t)(bps - 1) * hop + c->dx[W].N > stream_stride) return fail(VB200_EINVAL, "blocks exceed the stream buffer");
+  PcmSrc ps; ps.base = d_pcm; ps.fmt = fmt; ps.bps = bps; ps.hop = hop; ps.stride = stream_stride;
+  return phaseA_dev_common(c, W, nstreams * bps, io, nstreams, bps, d_amp0, stream, &ps);
 }
 
 extern "C" int vb200_analysis_phaseA_dev(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io, void *stream) {
@@ -1134,10 +1205,24 @@ extern "C" int vb200_synthesis_dev(vb200_ctx *c, int nstreams, int nblk, const i
   if (nstreams <= 0 || nblk <= 0) return 0;
   const int ch = c->setup.channels, N1 = c->dx[1].N;
   const size_t smem = sizeof(float) * ((size_t)N1 / 2 + N1 + N1 / 2);
-  int rc = set_smem(k_synthesis, smem); if (rc) return rc;
-  k_synthesis<<<grid_for(c, nstreams * ch, 8), threads_for(N1), smem, (cudaStream_t)stream>>>(
+  int rc = set_smem(k_synthesis<false>, smem); if (rc) return rc;
+  k_synthesis<false><<<grid_for(c, nstreams * ch, 8), threads_for(N1), smem, (cudaStream_t)stream>>>(
       c->dx[0], c->dx[1], c->dwin, ch, nstreams, nblk, d_Wseq, (const long long *)d_coef_off, d_coef,
       (const long long *)d_pcm_off, d_pcm, (long long)pcm_stride);
+  return post_launch(c);
+}
+
+extern "C" int vb200_synthesis_s16_dev(vb200_ctx *c, int nstreams, int nblk, const int32_t *d_Wseq,
+                                       const int64_t *d_coef_off, const float *d_coef,
+                                       const int64_t *d_pcm_off, int16_t *d_pcm16, int64_t pcm_stride, void *stream) {
+  CHECK_CTX(c);
+  if (nstreams <= 0 || nblk <= 0) return 0;
+  const int ch = c->setup.channels, N1 = c->dx[1].N;
+  const size_t smem = sizeof(float) * ((size_t)N1 / 2 + N1 + N1 / 2);
+  int rc = set_smem(k_synthesis<true>, smem); if (rc) return rc;
+  k_synthesis<true><<<grid_for(c, nstreams * ch, 8), threads_for(N1), smem, (cudaStream_t)stream>>>(
+      c->dx[0], c->dx[1], c->dwin, ch, nstreams, nblk, d_Wseq, (const long long *)d_coef_off, d_coef,
+      (const long long *)d_pcm_off, d_pcm16, (long long)pcm_stride);
   return post_launch(c);
 }
 

@@ -14,6 +14,9 @@ from . import abi
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libvorbis_b200.so")
 
+PCM_F32_PLANAR = 1
+PCM_S16_INTERLEAVED = 2
+
 EXPORTS = [
     "vb200_ctx_create", "vb200_ctx_destroy", "vb200_device_count", "vb200_last_error",
     "vb200_ctx_table", "vb200_launch_count", "vb200_set_profiling", "vb200_phaseA_kernel_ms", "vb200_debug_phase_cycles",
@@ -21,6 +24,7 @@ EXPORTS = [
     "vb200_apply_window", "vb200_drft_forward",
     "vb200_noisemask", "vb200_tonemask", "vb200_offset_and_mix",
     "vb200_analysis_phaseA_dev", "vb200_analysis_phaseA", "vb200_analysis_phaseA_streams_dev",
+    "vb200_analysis_phaseA_pcmstream_dev", "vb200_synthesis_s16_dev",
     "vb200_couple_quantize_normalize_dev", "vb200_couple_quantize_normalize",
     "vb200_synthesis_dev", "vb200_synthesis", "vb200_decouple_dev", "vb200_decouple",
     "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
@@ -69,6 +73,9 @@ def load():
     L.vb200_analysis_phaseA_dev.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.PhaseAIO), vp]
     L.vb200_analysis_phaseA.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.PhaseAIO)]
     L.vb200_analysis_phaseA_streams_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(abi.PhaseAIO), vp, vp]
+    L.vb200_analysis_phaseA_pcmstream_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int64, C.c_int,
+                                                      C.POINTER(abi.PhaseAIO), vp, vp]
+    L.vb200_synthesis_s16_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int64, vp]
     L.vb200_couple_quantize_normalize_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.vb200_couple_quantize_normalize.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.vb200_synthesis_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int64, vp]
@@ -230,6 +237,14 @@ class Context:
         else:
             self._chk(self.L.vb200_analysis_phaseA_streams_dev(self.h, W, streams[0], streams[1], C.byref(io),
                                                                _ptr(d_ampmax0), _ptr(stream)))
+
+    def phaseA_pcmstream_dev(self, W, nstreams, bps, d_pcm, fmt, stream_stride, hop, io, d_ampmax0=None, stream=None):
+        self._chk(self.L.vb200_analysis_phaseA_pcmstream_dev(self.h, W, nstreams, bps, _ptr(d_pcm), fmt, stream_stride,
+                                                             hop, C.byref(io), _ptr(d_ampmax0), _ptr(stream)))
+
+    def synthesis_s16_dev(self, nstreams, nblk, d_Wseq, d_coef_off, d_coef, d_pcm_off, d_pcm16, pcm_stride, stream=None):
+        self._chk(self.L.vb200_synthesis_s16_dev(self.h, nstreams, nblk, _ptr(d_Wseq), _ptr(d_coef_off), _ptr(d_coef),
+                                                 _ptr(d_pcm_off), _ptr(d_pcm16), pcm_stride, _ptr(stream)))
 
     # ---- Phase B ---------------------------------------------------------------
     def couple_quantize_normalize(self, W, blocktype, blobno, mdct, iwork, nonzero):
