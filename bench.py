@@ -239,6 +239,53 @@ def extra_configs(torch, lib, abi, device, peak):
     out["decode_4096streams_x33blocks_mixed"] = {"ms": ms, "stereo_blocks_per_s": ns * nblk / ms * 1e3,
                                                   "algorithmic_GBps": byts / ms / 1e6,
                                                   "frac_of_hbm_peak": byts / ms / 1e6 / peak}
+    # the whole per-block encode DSP on the device - Phase A, floor1_fit, floor render,
+    # couple/quantise/normalise - 20000 long stereo blocks, buffers resident
+    nb, N, chn = 20000, bs[1], s44.channels
+    n = N // 2
+    pcm_e = synth_pcm_torch(torch, nb, chn, N, 44100, dev, 99)
+    d_desc = torch.from_numpy(make_desc(nb).view(np.uint8).reshape(-1, 16).copy()).to(dev)
+    o_m = torch.empty((nb, chn, n), device=dev); o_lm = torch.empty_like(o_m); o_mask = torch.empty_like(o_m)
+    o_amp = torch.empty(nb, device=dev)
+    posts = torch.empty((nb * chn, abi.FLOOR1_STRIDE), dtype=torch.int32, device=dev)
+    fnz = torch.empty(nb * chn, dtype=torch.int32, device=dev)
+    iwork = torch.empty((nb, chn, n), dtype=torch.int32, device=dev)
+    nz = torch.empty(nb * chn, dtype=torch.int32, device=dev)
+    io = abi.PhaseAIO()
+    io.pcm, io.desc = pcm_e.data_ptr(), d_desc.data_ptr()
+    io.mdct, io.logmdct, io.logmask, io.ampmax_out = o_m.data_ptr(), o_lm.data_ptr(), o_mask.data_ptr(), o_amp.data_ptr()
+    stages = {
+        "phaseA": lambda: c44.phaseA_dev(1, nb, io, stream=stream),
+        "floor1_fit": lambda: c44.floor1_fit_dev(1, nb * chn, o_lm.data_ptr(), o_mask.data_ptr(), posts.data_ptr(),
+                                                 fnz.data_ptr(), stream=stream),
+        "floor1_render": lambda: c44.floor1_render_dev(1, nb * chn, posts.data_ptr(), fnz.data_ptr(), iwork.data_ptr(),
+                                                       nz.data_ptr(), stream=stream),
+    }
+
+    def fit_render():                   # render rewrites posts in place: time it behind a fresh fit
+        stages["floor1_fit"]()
+        stages["floor1_render"]()
+
+    def render_cqn():                   # CQN rewrites iwork in place: time it behind a fresh fit + render
+        fit_render()
+        c44.couple_quantize_normalize_dev(1, 1, 7, nb, o_m.data_ptr(), iwork.data_ptr(), nz.data_ptr(), stream=stream)
+    chain = {}
+    chain["phaseA_ms"] = timed(stages["phaseA"], reps=3)
+    chain["floor1_fit_ms"] = timed(stages["floor1_fit"], reps=3)
+    fr = timed(fit_render, reps=3)
+    chain["floor1_render_ms"] = fr - chain["floor1_fit_ms"]
+    stages["couple_quantize_normalize"] = lambda: c44.couple_quantize_normalize_dev(
+        1, 1, 7, nb, o_m.data_ptr(), iwork.data_ptr(), nz.data_ptr(), stream=stream)
+    chain["couple_quantize_normalize_ms"] = timed(render_cqn, reps=3) - fr
+
+    def whole():
+        for fn in stages.values():
+            fn()
+    ms = timed(whole, reps=3)
+    chain["whole_chain_ms"] = ms
+    chain["stereo_blocks_per_s"] = nb / ms * 1e3
+    chain["blocks"] = nb
+    out["encode_chain_phaseA_floor1_cqn_20000_long_stereo"] = chain
     c44.close()
     return out
 

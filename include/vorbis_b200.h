@@ -72,6 +72,22 @@ typedef struct vb200_psy_setup {
   const float   *noiseoffset;     /* [P_NOISECURVES][n]                       */
 } vb200_psy_setup;
 
+/* Floor 1 configuration of one block size: vorbis_info_floor1 (lib/backends.h:64-91).  The sorted /
+ * forward / reverse indices and the decode neighbours of vorbis_look_floor1
+ * (lib/codec_internal.h:138-155, built by floor1_look lib/floor1.c:180-259) are re-derived from
+ * postlist by the context.                                                                    */
+#define VB200_VIF_POSIT 63
+#define VB200_FLOOR1_STRIDE (VB200_VIF_POSIT + 2)   /* ints per row in every posts array of this API */
+#define VB200_MAX_SUBMAPS 4                          /* libvorbis' encoder setups use 1 or 2 (5.1: LFE) */
+typedef struct vb200_floor1_setup {
+  int32_t posts;                          /* vorbis_look_floor1.posts (<= VIF_POSIT+2); 0 = absent */
+  int32_t postlist[VB200_VIF_POSIT + 2];
+  int32_t mult;                           /* 1..4 */
+  int32_t n;                              /* spectral lines this floor spans (postlist[1])  */
+  float   maxover, maxunder, maxerr;
+  float   twofitweight, twofitatten;
+} vb200_floor1_setup;
+
 /* Everything the kernels need from codec_setup_info / private_state
  * (lib/codec_internal.h:59-133) for one (channels, rate, quality) setup.    */
 typedef struct vb200_setup {
@@ -94,6 +110,12 @@ typedef struct vb200_setup {
    * blocksizes[0] and [1] (blocksize/2 floats each); NULL = compute from the
    * closed form of doc/04-codec.tex:320                                     */
   const float *window[2];
+  /* floors of mode W (lib/mapping0.c:499-506): channel i uses floor1[W][chmux[W][i]], i.e. the
+   * floor of its submap (vorbis_info_mapping0.chmuxlist / floorsubmap, lib/backends.h:127-141).
+   * posts == 0: not provided (the floor entry points then return -1)                          */
+  int32_t submaps[2];
+  uint8_t chmux[2][VB200_MAX_CHANNELS + 1];
+  vb200_floor1_setup floor1[2][VB200_MAX_SUBMAPS];
 } vb200_setup;
 
 /* Per-block inputs of mapping0_forward that are not PCM (lib/mapping0.c:230-252) */
@@ -202,6 +224,29 @@ int vb200_analysis_phaseA_streams_dev(vb200_ctx*, int W, int nstreams, int block
 int vb200_analysis_phaseA_pcmstream_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream,
                                         const void *d_pcm, int fmt, int64_t stream_stride, int hop,
                                         const vb200_phaseA_io *d_io, const float *d_ampmax0, void *stream);
+
+/* ---- floor 1 on the device ---------------------------------------------------
+ * Rows are (block, channel) pairs.  floor_sel = -1: rows are laid out [block][channel] like the
+ * Phase A outputs and row r uses the floor of channel r % channels; floor_sel >= 0: every row uses
+ * floor1[W][floor_sel] (what one reference call with one vorbis_look_floor1 does).
+ * All posts arrays are [rows][VB200_FLOOR1_STRIDE] int32; entries past the floor's posts are 0.
+ *
+ * floor1_fit (lib/floor1.c:576-729): logmdct, logmask [rows][n] -> posts exactly as the reference
+ * returns them (unused posts carry predicted|0x8000); fit_nonzero[rows] = 0 where the reference
+ * returns NULL (silent channel; the row of posts is then all 0).                               */
+int vb200_floor1_fit_dev(vb200_ctx*, int W, int floor_sel, int nrows, const float *d_logmdct,
+                         const float *d_logmask, int32_t *d_posts, int32_t *d_fit_nonzero, void *stream);
+int vb200_floor1_fit    (vb200_ctx*, int W, int floor_sel, int nrows, const float *logmdct,
+                         const float *logmask, int32_t *posts, int32_t *fit_nonzero);
+/* the part of floor1_encode that is not bit packing (lib/floor1.c:765-832, 919-945): quantise the
+ * posts to the multiplier, apply the prediction/flag pass, render the integer floor curve.
+ * posts is updated in place to what the reference leaves in post[]; ilogmask [rows][n] is the curve
+ * (all zero and nonzero = 0 where fit_nonzero is 0).                                            */
+int vb200_floor1_render_dev(vb200_ctx*, int W, int floor_sel, int nrows, int32_t *d_posts,
+                            const int32_t *d_fit_nonzero, int32_t *d_ilogmask, int32_t *d_nonzero,
+                            void *stream);
+int vb200_floor1_render    (vb200_ctx*, int W, int floor_sel, int nrows, int32_t *posts,
+                            const int32_t *fit_nonzero, int32_t *ilogmask, int32_t *nonzero);
 
 /* ---- encode Phase B: _vp_couple_quantize_normalize, lib/psy.c:1014 ----
  * mdct  [nblocks][ch][n]  (Phase A output)

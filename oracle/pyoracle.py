@@ -20,7 +20,7 @@ i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    src = [os.path.join(HERE, f) for f in ("vb_oracle.c", "vb_oracle.h", "vb_oracle_b.inc")]
+    src = [os.path.join(HERE, f) for f in ("vb_oracle.c", "vb_oracle.h", "vb_oracle_b.inc", "vb_oracle_floor.inc")]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return
@@ -54,6 +54,8 @@ def lib():
                                                     f32p, i32p, i32p]
         L.vbo_synthesis.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i64p, f32p, i64p, f32p, C.c_int64]
         L.vbo_decouple.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p]
+        L.vbo_floor1_fit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p, i32p, i32p]
+        L.vbo_floor1_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i32p]
         _lib = L
     return _lib
 
@@ -171,6 +173,25 @@ class Oracle:
         nonzero = np.array(nonzero, np.int32)
         self.L.vbo_couple_quantize_normalize(self.h, W, blocktype, blobno, mdct.shape[0], mdct, iwork, nonzero)
         return iwork, nonzero
+
+    def floor1_fit(self, W, logmdct, logmask, floor_sel=-1):
+        """[rows][n] x2 -> (posts [rows][FLOOR1_STRIDE], fit_nonzero [rows])"""
+        n = self.bs[W] // 2
+        a = np.ascontiguousarray(logmdct, np.float32).reshape(-1, n)
+        b = np.ascontiguousarray(logmask, np.float32).reshape(-1, n)
+        posts = np.zeros((a.shape[0], abi.FLOOR1_STRIDE), np.int32)
+        nz = np.zeros(a.shape[0], np.int32)
+        self.L.vbo_floor1_fit(self.h, W, floor_sel, a.shape[0], a, b, posts, nz)
+        return posts, nz
+
+    def floor1_render(self, W, posts, fit_nonzero, floor_sel=-1):
+        n = self.bs[W] // 2
+        posts = np.array(posts, np.int32).reshape(-1, abi.FLOOR1_STRIDE)
+        fz = np.ascontiguousarray(fit_nonzero, np.int32)
+        ilog = np.zeros((posts.shape[0], n), np.int32)
+        nz = np.zeros(posts.shape[0], np.int32)
+        self.L.vbo_floor1_render(self.h, W, floor_sel, posts.shape[0], posts, fz, ilog, nz)
+        return posts, ilog, nz
 
     def decouple(self, W, res):
         res = np.array(res, np.float32)

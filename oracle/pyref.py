@@ -34,6 +34,7 @@ class Capture(C.Structure):
         ("logmask", C.c_void_p), ("mdct_m1", C.c_void_p), ("local_ampmax", C.c_void_p),
         ("global_ampmax", C.c_void_p), ("ilogmask", C.c_void_p), ("iwork_out", C.c_void_p),
         ("nonzero_in", C.c_void_p), ("nonzero_out", C.c_void_p),
+        ("fit_posts", C.c_void_p), ("enc_posts", C.c_void_p),
         ("dec_coef", C.c_void_p), ("dec_imdct", C.c_void_p),
     ]
 
@@ -258,6 +259,8 @@ class Ref:
         arr["local_ampmax"] = np.zeros((maxblocks, ch), np.float32)
         arr["nonzero_in"] = np.zeros((maxblocks, ch), np.int32)
         arr["nonzero_out"] = np.zeros((maxblocks, ch), np.int32)
+        arr["fit_posts"] = np.zeros((maxblocks, ch, 65), np.int32)
+        arr["enc_posts"] = np.zeros((maxblocks, ch, 65), np.int32)
         for name in _CAP_F_N:
             if name in fields:
                 arr[name] = np.zeros((maxblocks, ch, Nmax), np.float32)

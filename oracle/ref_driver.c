@@ -186,6 +186,26 @@ int ref_get_setup(void *hv, vb200_setup *s){
   }
   s->window[0] = _vorbis_window_get(b->window[0]);
   s->window[1] = _vorbis_window_get(b->window[1]);
+  for(w=0;w<2;w++){
+    vorbis_info_mapping0 *m = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[w]->mapping];
+    int sm;
+    if(m->submaps > VB200_MAX_SUBMAPS) return -1;
+    s->submaps[w] = m->submaps;
+    for(k=0;k<h->vi.channels;k++) s->chmux[w][k] = (uint8_t)m->chmuxlist[k];
+    for(sm=0;sm<m->submaps;sm++){
+      int fl = m->floorsubmap[sm];
+      if(ci->floor_type[fl]==1){
+        vorbis_info_floor1 *fi = (vorbis_info_floor1*)ci->floor_param[fl];
+        vorbis_look_floor1 *lk = (vorbis_look_floor1*)b->flr[fl];
+        vb200_floor1_setup *o = &s->floor1[w][sm];
+        o->posts = lk->posts;
+        for(k=0;k<lk->posts;k++) o->postlist[k]=fi->postlist[k];
+        o->mult = fi->mult; o->n = lk->n;
+        o->maxover = fi->maxover; o->maxunder = fi->maxunder; o->maxerr = fi->maxerr;
+        o->twofitweight = fi->twofitweight; o->twofitatten = fi->twofitatten;
+      }
+    }
+  }
   return 0;
 }
 
@@ -346,6 +366,8 @@ typedef struct ref_capture {
   int32_t *iwork_out;    /* [blk][ch][Nmax/2] iwork leaving CQN */
   int32_t *nonzero_in;   /* [blk][ch] */
   int32_t *nonzero_out;  /* [blk][ch] */
+  int32_t *fit_posts;    /* [blk][ch][65] output of floor1_fit (blob 7); [0] = -1 when NULL */
+  int32_t *enc_posts;    /* [blk][ch][65] post[] after floor1_encode's quantise/predict pass */
   /* decode side */
   float *dec_coef;   /* [blk][ch][Nmax/2] input of mdct_backward */
   float *dec_imdct;  /* [blk][ch][Nmax]   output of mdct_backward */
@@ -354,7 +376,7 @@ typedef struct ref_capture {
 static ref_capture *g_cap = NULL;
 static int g_blk = -1;
 static int g_ch_total = 0;
-static int g_cnt_window, g_cnt_mdct, g_cnt_fft, g_cnt_noise, g_cnt_tone, g_cnt_mix, g_cnt_imdct;
+static int g_cnt_window, g_cnt_mdct, g_cnt_fft, g_cnt_noise, g_cnt_tone, g_cnt_mix, g_cnt_imdct, g_cnt_fit, g_cnt_enc;
 
 static int cap_on(void){ return g_cap && g_blk>=0 && g_blk<g_cap->maxblocks; }
 static float *rowN(float *base,int c){ return base+((size_t)g_blk*g_ch_total+c)*g_cap->Nmax; }
@@ -431,6 +453,31 @@ void spy__vp_couple_quantize_normalize(int blobno,vorbis_info_psy_global *g,vorb
   }
 }
 
+/* floor1_fit / floor1_encode (lib/floor1.c:576,753) as called from mapping0_forward (:500,:617).
+ * Only the first fit per channel is the PACKETBLOBS/2 one in non-managed mode. */
+int *spy_floor1_fit(vorbis_block *vb,vorbis_look_floor1 *look,const float *logmdct,const float *logmask){
+  int c = g_cnt_fit++;
+  int *r = floor1_fit(vb,look,logmdct,logmask);
+  if(cap_on() && g_cap->fit_posts && c < g_ch_total){
+    int32_t *dst = g_cap->fit_posts + ((size_t)g_blk*g_ch_total+c)*65;
+    int k;
+    for(k=0;k<65;k++) dst[k] = 0;
+    if(!r) dst[0] = -1; else for(k=0;k<look->posts;k++) dst[k]=r[k];
+  }
+  return r;
+}
+int spy_floor1_encode(oggpack_buffer *opb,vorbis_block *vb,vorbis_look_floor1 *look,int *post,int *ilogmask){
+  int c = g_cnt_enc++;
+  int r = floor1_encode(opb,vb,look,post,ilogmask);
+  if(cap_on() && g_cap->enc_posts && c < g_ch_total){
+    int32_t *dst = g_cap->enc_posts + ((size_t)g_blk*g_ch_total+c)*65;
+    int k;
+    for(k=0;k<65;k++) dst[k] = 0;
+    if(!post) dst[0] = -1; else for(k=0;k<look->posts;k++) dst[k]=post[k];
+  }
+  return r;
+}
+
 void spy_mdct_backward(mdct_lookup *init, float *in, float *out){
   int c = g_cnt_imdct++;
   if(cap_on() && g_cap->dec_coef) memcpy(rown(g_cap->dec_coef,c),in,sizeof(float)*(init->n/2));
@@ -482,7 +529,7 @@ int ref_encode_capture(void *hv, const float *pcm, long nsamples, ref_capture *c
     while(vorbis_analysis_blockout(&h->vd,&h->vb)==1){
       vorbis_block_internal *vbi = (vorbis_block_internal*)h->vb.internal;
       g_blk = blocks;
-      g_cnt_window=g_cnt_mdct=g_cnt_fft=g_cnt_noise=g_cnt_tone=g_cnt_mix=0;
+      g_cnt_window=g_cnt_mdct=g_cnt_fft=g_cnt_noise=g_cnt_tone=g_cnt_mix=g_cnt_fit=g_cnt_enc=0;
       if(cap_on()){
         cap->W[blocks]=(int32_t)h->vb.W; cap->lW[blocks]=(int32_t)h->vb.lW; cap->nW[blocks]=(int32_t)h->vb.nW;
         cap->blocktype[blocks]=vbi->blocktype;

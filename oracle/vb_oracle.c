@@ -38,10 +38,19 @@ typedef struct {
   int ngrp; int *grp_pos0, *grp_pos1, *grp_lin0, *grp_lin1; int tail_lin0;
 } vbo_psy;
 
+typedef struct {
+  vb200_floor1_setup s;
+  int quant_q;
+  int sorted_index[VB200_VIF_POSIT + 2], forward_index[VB200_VIF_POSIT + 2], reverse_index[VB200_VIF_POSIT + 2];
+  int hineighbor[VB200_VIF_POSIT], loneighbor[VB200_VIF_POSIT];
+} vbo_floor1;
+void vbo_floor1_init(vbo_floor1 *f, const vb200_floor1_setup *s);
+
 struct vbo_ctx {
   vb200_setup setup;
   vbo_xform x[2];
   vbo_psy   psy[4];
+  vbo_floor1 floor1[2][VB200_MAX_SUBMAPS];
 };
 
 /* ======================================================================= */
@@ -202,6 +211,8 @@ vbo_ctx *vbo_create(const vb200_setup *setup){
     xform_init_window(&c->x[w], setup->window[w]);
   }
   for(i = 0; i < setup->n_psy && i < 4; i++) psy_init(&c->psy[i], &setup->psy[i]);
+  for(w = 0; w < 2; w++)
+    for(i = 0; i < VB200_MAX_SUBMAPS; i++) vbo_floor1_init(&c->floor1[w][i], &setup->floor1[w][i]);
   return c;
 }
 
@@ -985,3 +996,4 @@ void vbo_phaseA_streams(vbo_ctx *c, int W, int nstreams, int bps, const vb200_ph
 /* ======================================================================= */
 /* Phase B and decode are in vb_oracle_b.c (included to keep one library)  */
 #include "vb_oracle_b.inc"
+#include "vb_oracle_floor.inc"

@@ -49,4 +49,8 @@ void vbo_synthesis(vbo_ctx *c, int nstreams, int nblk, const int32_t *Wseq,
                    const int64_t *coef_off, const float *coef,
                    const int64_t *pcm_off, float *pcm, int64_t pcm_stride);
 void vbo_decouple(vbo_ctx *c, int W, int nblocks, float *res);
+void vbo_floor1_fit(vbo_ctx *c, int W, int floor_sel, int nrows, const float *logmdct, const float *logmask,
+                    int32_t *posts, int32_t *fit_nonzero);
+void vbo_floor1_render(vbo_ctx *c, int W, int floor_sel, int nrows, int32_t *posts, const int32_t *fit_nonzero,
+                       int32_t *ilogmask, int32_t *nonzero);
 #endif

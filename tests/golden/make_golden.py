@@ -58,6 +58,8 @@ def main():
         setup.save(os.path.join(OUT, "setup_%s.npz" % name))
         bs = r.bs
         pcm = signal(ch, rate, secs, seed=1234)
+        if name == "44k_mono_q4":
+            pcm[:, :3000] = 0                     # digital silence: floor1_fit returns NULL there
         cap = r.encode_capture(pcm)
         W = cap["W"]
         longs = np.where(W == 1)[0]
@@ -78,6 +80,10 @@ def main():
             for k in ("mdct_raw", "logfft", "logmdct", "noise", "tone", "logmask", "mdct_m1",
                       "ilogmask", "iwork_out"):
                 enc[tag + "_" + k] = cap[k][idx][:, :, :n]
+            # floor 1: what floor1_fit returned ([0] = -1 where it returned NULL) and what
+            # floor1_encode left in post[] after its quantise / predict pass
+            enc[tag + "_fit_posts"] = cap["fit_posts"][idx]
+            enc[tag + "_enc_posts"] = cap["enc_posts"][idx]
         # the whole ampmax chain (cheap): lets the stream-mode test replay it
         enc["chain_W"] = W
         enc["chain_ampmax_in"] = cap["ampmax_in"]

@@ -403,3 +403,106 @@ def test_decode_int16_egress(cfg):
     assert (np.abs(want.astype(np.int32)) == 32767).any() or (want == -32768).any(), "test signal should clip"
     # only positions that blocks actually finish are written; the layout leaves no gaps
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------
+# floor 1
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_floor1_golden(cfg, tag):
+    from test_oracle_golden import floor_expect
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    n = setup.blocksize(W) // 2
+    fit, nz, encp = floor_expect(enc, tag)
+    posts, got_nz = ctx.floor1_fit(W, enc[tag + "_logmdct"], enc[tag + "_logmask"])
+    assert np.array_equal(got_nz, nz), "fit_nonzero"
+    assert np.array_equal(posts, fit), "fit posts: %d diffs" % (posts != fit).sum()
+    p2, ilog, nz2 = ctx.floor1_render(W, posts, got_nz)
+    assert np.array_equal(p2[nz == 1], encp[nz == 1]), "encode posts"
+    assert np.array_equal(ilog, enc[tag + "_ilogmask"].reshape(-1, n)), "ilogmask"
+    assert np.array_equal(nz2, enc[tag + "_nonzero_in"].reshape(-1)), "nonzero"
+
+
+@pytest.mark.parametrize("W", [0, 1])
+def test_floor1_vs_oracle_random(cfg, W):
+    """masks from the oracle's own Phase A on random PCM plus synthetic curves that force the
+    corner cases: silence (NULL), flat curves, cliffs, everything inaudible, everything clipped."""
+    name, setup, ctx, o, enc, _ = cfg
+    N, ch = setup.blocksize(W), setup.channels
+    n = N // 2
+    rng = np.random.default_rng(4242 + W)
+    nb = 24
+    scale = 10.0 ** rng.uniform(-4, 0, (nb, 1, 1))
+    pcm = (rng.uniform(-1, 1, (nb, ch, N)) * scale).astype(np.float32)
+    t = np.arange(N)
+    pcm[3] += (0.5 * np.sin(2 * np.pi * 0.013 * t)).astype(np.float32)
+    pcm[5] = 0
+    desc = np.zeros(nb, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = W; desc["nW"] = W; desc["blocktype"] = rng.integers(0, 2, nb); desc["ampmax"] = -9999.0
+    pa = o.phaseA(W, pcm, desc)
+    logmdct = [pa["logmdct"].reshape(-1, n)]
+    logmask = [pa["logmask"].reshape(-1, n)]
+    R = 12 * ch
+    x = np.arange(n)
+    syn_mask = rng.uniform(-140, 0, (R, n)).astype(np.float32)
+    syn_mdct = (syn_mask + rng.normal(0, 12, (R, n))).astype(np.float32)
+    syn_mask[0] = -60.0                                         # flat
+    syn_mask[1] = np.where(x < n // 3, -20.0, -120.0)           # cliff
+    syn_mdct[2] = -400.0                                        # nothing audible: every bin in the "b" sums
+    syn_mask[3] = 20.0                                          # dBquant clips at 1023
+    syn_mask[4] = -200.0                                        # dBquant clips at 0 -> NULL fit
+    syn_mask[5] = (-30.0 - 80.0 * x / n).astype(np.float32)     # a straight line: no splits needed
+    syn_mask[6] = np.where(rng.uniform(0, 1, n) < 0.1, -10.0, -139.9)  # sparse peaks
+    logmdct.append(syn_mdct); logmask.append(syn_mask)
+    logmdct = np.concatenate(logmdct); logmask = np.concatenate(logmask)
+    a = ctx.floor1_fit(W, logmdct, logmask)
+    b = o.floor1_fit(W, logmdct, logmask)
+    assert np.array_equal(a[1], b[1]), "fit_nonzero"
+    assert (b[1] == 0).any() and (b[1] == 1).any()
+    assert np.array_equal(a[0], b[0]), "posts: %d diffs in rows %s" % ((a[0] != b[0]).sum(), np.unique(np.argwhere(a[0] != b[0])[:, 0])[:8])
+    ra = ctx.floor1_render(W, a[0], a[1])
+    rb = o.floor1_render(W, b[0], b[1])
+    for k, what in enumerate(("posts", "ilogmask", "nonzero")):
+        assert np.array_equal(ra[k], rb[k]), what
+    # explicit floor selection (what one reference call does): rows of channel 0 only
+    sel = setup.floor_of(W, 0)
+    rows = np.arange(0, logmdct.shape[0], ch)
+    a0 = ctx.floor1_fit(W, logmdct[rows], logmask[rows], floor_sel=sel)
+    assert np.array_equal(a0[0], b[0][rows]) and np.array_equal(a0[1], b[1][rows])
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_encode_chain_on_device_golden(cfg, tag):
+    """PCM -> Phase A -> floor1_fit -> floor render -> couple/quantise/normalise, every buffer
+    resident on the device, equals what the reference's mapping0_forward produced."""
+    import torch
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    N, ch = setup.blocksize(W), setup.channels
+    n = N // 2
+    for bt in (0, 1):
+        sel = np.where(enc[tag + "_blocktype"] == bt)[0]
+        if not len(sel):
+            continue
+        nb = len(sel)
+        dev = torch.device("cuda")
+        pcm = torch.from_numpy(np.ascontiguousarray(enc[tag + "_pcm"][sel])).to(dev)
+        desc = torch.from_numpy(make_desc(enc, tag, sel).view(np.uint8).reshape(-1, 16).copy()).to(dev)
+        mdct = torch.empty((nb, ch, n), dtype=torch.float32, device=dev)
+        logmdct = torch.empty_like(mdct); logmask = torch.empty_like(mdct)
+        amp = torch.empty(nb, dtype=torch.float32, device=dev)
+        posts = torch.empty((nb * ch, abi.FLOOR1_STRIDE), dtype=torch.int32, device=dev)
+        fnz = torch.empty(nb * ch, dtype=torch.int32, device=dev)
+        iwork = torch.empty((nb, ch, n), dtype=torch.int32, device=dev)
+        nz = torch.empty(nb * ch, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        io = abi.PhaseAIO()
+        io.pcm, io.desc = pcm.data_ptr(), desc.data_ptr()
+        io.mdct, io.logmdct, io.logmask, io.ampmax_out = mdct.data_ptr(), logmdct.data_ptr(), logmask.data_ptr(), amp.data_ptr()
+        ctx.phaseA_dev(W, nb, io, stream=st)
+        ctx.floor1_fit_dev(W, nb * ch, logmdct.data_ptr(), logmask.data_ptr(), posts.data_ptr(), fnz.data_ptr(), stream=st)
+        ctx.floor1_render_dev(W, nb * ch, posts.data_ptr(), fnz.data_ptr(), iwork.data_ptr(), nz.data_ptr(), stream=st)
+        ctx.couple_quantize_normalize_dev(W, bt, 7, nb, mdct.data_ptr(), iwork.data_ptr(), nz.data_ptr(), stream=st)
+        torch.cuda.synchronize()
+        assert np.array_equal(iwork.cpu().numpy(), enc[tag + "_iwork_out"][sel]), "iwork"
+        assert np.array_equal(nz.cpu().numpy().reshape(nb, ch), enc[tag + "_nonzero_out"][sel]), "nonzero"

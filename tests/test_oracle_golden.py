@@ -128,3 +128,33 @@ def test_decouple_inverts_the_encoder_coupling(cfg):
     out = o.decouple(1, res)
     assert np.array_equal(out[0, int(setup.c.coupling_mag[1][0])], A.astype(np.float32))
     assert np.array_equal(out[0, int(setup.c.coupling_ang[1][0])], B.astype(np.float32))
+
+
+def floor_expect(enc, tag):
+    """golden floor vectors as the API lays them out: NULL fits -> zero rows, fit_nonzero 0"""
+    fit = enc[tag + "_fit_posts"].reshape(-1, enc[tag + "_fit_posts"].shape[-1]).astype(np.int32).copy()
+    nz = (fit[:, 0] != -1).astype(np.int32)
+    fit[nz == 0] = 0
+    encp = enc[tag + "_enc_posts"].reshape(fit.shape).astype(np.int32)
+    return fit, nz, encp
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_floor1_golden(cfg, tag):
+    """floor1_fit (lib/floor1.c:576) and floor1_encode's quantise/predict/render (:765-945)."""
+    name, setup, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    n = setup.blocksize(W) // 2
+    fit, nz, encp = floor_expect(enc, tag)
+    posts, got_nz = o.floor1_fit(W, enc[tag + "_logmdct"], enc[tag + "_logmask"])
+    assert np.array_equal(got_nz, nz), "fit_nonzero"
+    assert np.array_equal(posts, fit), "fit posts"
+    p2, ilog, nz2 = o.floor1_render(W, posts, got_nz)
+    assert np.array_equal(p2[nz == 1], encp[nz == 1]), "encode posts"
+    assert np.array_equal(ilog, enc[tag + "_ilogmask"].reshape(-1, n)), "ilogmask"
+    assert np.array_equal(nz2, enc[tag + "_nonzero_in"].reshape(-1)), "nonzero"
+
+
+def test_floor1_golden_has_null_fit():
+    enc = load_npz("encode", "44k_mono_q4")
+    assert (enc["L_fit_posts"][:, :, 0] == -1).any(), "fixture should hold a silent block (floor1_fit == NULL)"

@@ -99,3 +99,37 @@ def test_decode_of_the_real_stream(pair):
     m = min(d["pcm"].shape[1], pcm_len)
     assert m > 0
     assert_bits_equal(out[0][:, :m], d["pcm"][:, :m], "decoded pcm")
+
+
+@pytest.mark.parametrize("args", [(2, 44100, 0.5), (6, 48000, 0.2), (2, 32000, -0.1), (1, 16000, 0.5), (2, 96000, 0.7)],
+                         ids=lambda g: "ch%d_%d_q%g" % g)
+def test_floor1_vs_reference(args, oracle_lib):
+    """floor1_fit / floor1_encode recorded inside the reference's own mapping0_forward, incl. silent
+    blocks (NULL fit) and the 5.1 LFE submap with its own 2-post floor."""
+    ch, rate, q = args
+    r = pyref.Ref(ch, rate, q)
+    setup = r.setup()
+    o = oracle_lib.Oracle(setup)
+    pcm = probe_signal(ch, rate, 1.0, seed=5)
+    pcm[:, :3000] = 0
+    cap = r.encode_capture(pcm)
+    nulls = 0
+    for W in (0, 1):
+        idx = np.where(cap["W"] == W)[0]
+        if not len(idx):
+            continue
+        n = r.bs[W] // 2
+        posts, nz = o.floor1_fit(W, cap["logmdct"][idx][:, :, :n], cap["logmask"][idx][:, :, :n])
+        want = cap["fit_posts"][idx].reshape(-1, abi.FLOOR1_STRIDE).copy()
+        wnz = (want[:, 0] != -1).astype(np.int32)
+        want[wnz == 0] = 0
+        nulls += int((wnz == 0).sum())
+        assert np.array_equal(nz, wnz)
+        assert np.array_equal(posts, want)
+        p2, ilog, nz2 = o.floor1_render(W, posts, nz)
+        wenc = cap["enc_posts"][idx].reshape(-1, abi.FLOOR1_STRIDE)
+        assert np.array_equal(p2[wnz == 1], wenc[wnz == 1])
+        assert np.array_equal(ilog, cap["ilogmask"][idx][:, :, :n].reshape(-1, n))
+        assert np.array_equal(nz2, cap["nonzero_in"][idx].reshape(-1))
+    assert nulls > 0
+    r.close()

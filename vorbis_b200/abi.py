@@ -15,6 +15,9 @@ EHMER_MAX = 56
 COMPAND_LEVELS = 40
 PACKETBLOBS = 15
 MAX_COUPLING = 256
+MAX_CHANNELS = 255
+MAX_SUBMAPS = 4
+FLOOR1_STRIDE = 65
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
@@ -50,6 +53,20 @@ class PsySetup(C.Structure):
     ]
 
 
+VIF_POSIT = 63
+
+
+class Floor1Setup(C.Structure):
+    _fields_ = [
+        ("posts", C.c_int32),
+        ("postlist", C.c_int32 * (VIF_POSIT + 2)),
+        ("mult", C.c_int32),
+        ("n", C.c_int32),
+        ("maxover", C.c_float), ("maxunder", C.c_float), ("maxerr", C.c_float),
+        ("twofitweight", C.c_float), ("twofitatten", C.c_float),
+    ]
+
+
 class Setup(C.Structure):
     _fields_ = [
         ("channels", C.c_int32),
@@ -66,6 +83,9 @@ class Setup(C.Structure):
         ("coupling_mag", (C.c_int32 * MAX_COUPLING) * 2),
         ("coupling_ang", (C.c_int32 * MAX_COUPLING) * 2),
         ("window", c_float_p * 2),
+        ("submaps", C.c_int32 * 2),
+        ("chmux", (C.c_uint8 * (MAX_CHANNELS + 1)) * 2),
+        ("floor1", (Floor1Setup * MAX_SUBMAPS) * 2),
     ]
 
 
@@ -145,6 +165,27 @@ class SetupHolder:
             if key in a and a[key].size:
                 a[key] = np.ascontiguousarray(a[key], dtype=np.float32)
                 s.window[w] = _np_ptr(a[key], C.c_float)
+        if "chmux" in a:
+            cm = np.asarray(a["chmux"]).astype(np.int64)
+            for w in range(2):
+                s.submaps[w] = int(a["submaps"][w])
+                for k in range(cm.shape[1]):
+                    s.chmux[w][k] = int(cm[w][k])
+        for w in range(2):
+            for sm in range(MAX_SUBMAPS):
+                key = "floor1_%d_%d_postlist" % (w, sm)
+                if key not in a:
+                    continue
+                f = s.floor1[w][sm]
+                pl = np.asarray(a[key]).astype(np.int64)
+                f.posts = len(pl)
+                for k, v in enumerate(pl):
+                    f.postlist[k] = int(v)
+                pre = "floor1_%d_%d_" % (w, sm)
+                f.mult = int(_sc(a[pre + "mult"]))
+                f.n = int(_sc(a[pre + "n"]))
+                for nm in ("maxover", "maxunder", "maxerr", "twofitweight", "twofitatten"):
+                    setattr(f, nm, float(_sc(a[pre + nm])))
         for i in range(s.n_psy):
             p = s.psy[i]
             pre = "psy%d_" % i
@@ -178,6 +219,12 @@ class SetupHolder:
     def psy_n(self, look):
         return int(self.c.psy[look].n)
 
+    def floor_of(self, W, channel):
+        return int(self.c.chmux[W][channel])
+
+    def floor_posts(self, W, sel=0):
+        return int(self.c.floor1[W][sel].posts)
+
     def save(self, path):
         np.savez_compressed(path, **self.arrays)
 
@@ -208,6 +255,19 @@ class SetupHolder:
         for w in range(2):
             if s.window[w]:
                 a["window%d" % w] = np.ctypeslib.as_array(s.window[w], shape=(s.blocksizes[w] // 2,)).copy()
+        a["submaps"] = np.array(list(s.submaps), np.int32)
+        a["chmux"] = np.array([[s.chmux[w][k] for k in range(max(1, s.channels))] for w in range(2)], np.int32)
+        for w in range(2):
+            for sm in range(MAX_SUBMAPS):
+                f = s.floor1[w][sm]
+                if f.posts <= 0:
+                    continue
+                pre = "floor1_%d_%d_" % (w, sm)
+                a[pre + "postlist"] = np.array([f.postlist[k] for k in range(f.posts)], np.int32)
+                a[pre + "mult"] = np.int32(f.mult)
+                a[pre + "n"] = np.int32(f.n)
+                for nm in ("maxover", "maxunder", "maxerr", "twofitweight", "twofitatten"):
+                    a[pre + nm] = np.float64(getattr(f, nm))
         for i in range(s.n_psy):
             p = s.psy[i]
             pre = "psy%d_" % i

@@ -4,6 +4,7 @@
 //        -Xcompiler -fPIC -shared   (see __graft_entry__.build()).
 // No torch, no oracle/ dependency: this is the product library.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include "vb200_kernels.cuh"
 #include "vb200_cqn.cuh"
 #include "vb200_psy2.cuh"
+#include "vb200_floor1.cuh"
 #include "floor1_db_table.h"
 
 using namespace vb200;
@@ -64,6 +66,8 @@ struct vb200_ctx {
   int psy_ctas_per_sm = 5;
   const float *d_fromdB = nullptr;
   const int *d_mag[2] = {nullptr, nullptr}, *d_ang[2] = {nullptr, nullptr};
+  const Floor1Dev *d_floor[2] = {nullptr, nullptr};   // [VB200_MAX_SUBMAPS] per block size
+  const unsigned char *d_chmux[2] = {nullptr, nullptr};
   cudaStream_t s_main = nullptr;
   std::mutex mu;
   // optional per-kernel timing of the last Phase-A call (bench roofline evidence)
@@ -197,6 +201,56 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     if (p.eighth_octave_lines > 32) return fail(VB200_EIMPL, "eighth_octave_lines > 32");
     if (p.total_octave_lines >= 2048) return fail(VB200_EIMPL, "total_octave_lines >= 2048");
     { const int *dco = nullptr; if ((rc = upload(c, f.cls_off.data(), f.cls_off.size(), &dco))) return rc; d.cls_off = dco; }
+  }
+  // floor 1 lookups: what floor1_look (lib/floor1.c:205-253) derives from the post list
+  for (int w = 0; w < 2; w++) {
+    Floor1Dev hf[VB200_MAX_SUBMAPS];
+    memset(hf, 0, sizeof(hf));
+    if (s->submaps[w] < 0 || s->submaps[w] > VB200_MAX_SUBMAPS) return fail(VB200_EINVAL, "submaps");
+    for (int sm = 0; sm < VB200_MAX_SUBMAPS; sm++) {
+      const vb200_floor1_setup &f = s->floor1[w][sm];
+      Floor1Dev &d = hf[sm];
+      if (f.posts == 0) continue;
+      const int P = f.posts;
+      if (P < 2 || P > VB200_VIF_POSIT + 2) return fail(VB200_EINVAL, "floor1 posts");
+      if (f.mult < 1 || f.mult > 4) return fail(VB200_EINVAL, "floor1 mult");
+      if (f.n < 1 || f.n > s->blocksizes[w] / 2 || f.postlist[0] != 0 || f.postlist[1] != f.n)
+        return fail(VB200_EINVAL, "floor1 post list must start 0, n with n <= blocksize/2");
+      for (int i = 0; i < P; i++) {
+        if (f.postlist[i] < 0 || f.postlist[i] > f.n) return fail(VB200_EINVAL, "floor1 post out of range");
+        for (int j = 0; j < i; j++)
+          if (f.postlist[j] == f.postlist[i]) return fail(VB200_EINVAL, "floor1 posts must be distinct");
+      }
+      d.posts = P; d.n = f.n; d.mult = f.mult;
+      d.maxover = f.maxover; d.maxunder = f.maxunder; d.maxerr = f.maxerr;
+      d.twofitweight = f.twofitweight; d.twofitatten = f.twofitatten;
+      int order[VB200_VIF_POSIT + 2];
+      for (int i = 0; i < P; i++) order[i] = i;
+      std::sort(order, order + P, [&](int x, int y) { return f.postlist[x] < f.postlist[y]; });
+      for (int i = 0; i < P; i++) {
+        d.postlist[i] = (short)f.postlist[i];
+        d.fwd[i] = (short)order[i];
+        d.rev[order[i]] = (short)i;
+        d.sorted[i] = (short)f.postlist[order[i]];
+      }
+      for (int i = 0; i < P - 2; i++) {                 // nearest already-coded posts on both sides
+        int lo = 0, hi = 1, lx = 0, hx = f.n;
+        const int cur = f.postlist[i + 2];
+        for (int j = 0; j < i + 2; j++) {
+          const int x = f.postlist[j];
+          if (x > lx && x < cur) { lo = j; lx = x; }
+          if (x < hx && x > cur) { hi = j; hx = x; }
+        }
+        d.lo[i] = (short)lo; d.hi[i] = (short)hi;
+      }
+    }
+    for (int k = 0; k < s->channels; k++) {
+      const int sm = s->chmux[w][k];
+      if (sm >= VB200_MAX_SUBMAPS) return fail(VB200_EINVAL, "chmux");
+    }
+    int rc;
+    if ((rc = upload(c, hf, (size_t)VB200_MAX_SUBMAPS, &c->d_floor[w]))) return rc;
+    if ((rc = upload(c, (const unsigned char *)s->chmux[w], (size_t)VB200_MAX_CHANNELS + 1, &c->d_chmux[w]))) return rc;
   }
   *out = c;
   return 0;
@@ -1270,6 +1324,87 @@ extern "C" int vb200_decouple(vb200_ctx *c, int W, int nblocks, float *res) {
   if ((rc = io.h2d(res, bytes, &d))) return rc;
   if ((rc = vb200_decouple_dev(c, W, nblocks, (float *)d, c->s_main))) return rc;
   if ((rc = io.d2h(res, d, bytes))) return rc;
+  return io.sync();
+}
+
+// ======================================================================== //
+// floor 1
+static int floor1_args(vb200_ctx *c, int W, int floor_sel, int nrows, Floor1Args *a) {
+  if (floor_sel >= VB200_MAX_SUBMAPS) return fail(VB200_EINVAL, "floor_sel");
+  const int ch = c->setup.channels;
+  if (floor_sel >= 0) {
+    if (c->setup.floor1[W][floor_sel].posts <= 0) return fail(VB200_EINVAL, "no floor1 setup for this floor_sel");
+  } else {
+    for (int k = 0; k < ch; k++)
+      if (c->setup.floor1[W][c->setup.chmux[W][k]].posts <= 0)
+        return fail(VB200_EINVAL, "no floor1 setup for a channel's submap");
+  }
+  a->floors = c->d_floor[W]; a->chmux = c->d_chmux[W];
+  a->channels = ch; a->floor_sel = floor_sel; a->nrows = nrows; a->n = c->dx[W].N / 2;
+  return 0;
+}
+
+extern "C" int vb200_floor1_fit_dev(vb200_ctx *c, int W, int floor_sel, int nrows, const float *d_logmdct,
+                                    const float *d_logmask, int32_t *d_posts, int32_t *d_fit_nonzero, void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nrows <= 0) return 0;
+  Floor1Args a; int rc;
+  if ((rc = floor1_args(c, W, floor_sel, nrows, &a))) return rc;
+  const size_t smem = sizeof(Floor1Dev) * VB200_MAX_SUBMAPS + floor1_fit_smem_per_warp(a.n) * F1_WARPS;
+  if ((rc = set_smem(k_floor1_fit, smem))) return rc;
+  const int ctas = (nrows + F1_WARPS - 1) / F1_WARPS;
+  k_floor1_fit<<<grid_for(c, ctas, 8), 32 * F1_WARPS, smem, (cudaStream_t)stream>>>(a, d_logmdct, d_logmask, d_posts, d_fit_nonzero);
+  return post_launch(c);
+}
+
+extern "C" int vb200_floor1_render_dev(vb200_ctx *c, int W, int floor_sel, int nrows, int32_t *d_posts,
+                                       const int32_t *d_fit_nonzero, int32_t *d_ilogmask, int32_t *d_nonzero,
+                                       void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nrows <= 0) return 0;
+  Floor1Args a; int rc;
+  if ((rc = floor1_args(c, W, floor_sel, nrows, &a))) return rc;
+  const int ctas = (nrows + F1_WARPS - 1) / F1_WARPS;
+  k_floor1_render<<<grid_for(c, ctas, 8), 32 * F1_WARPS, 0, (cudaStream_t)stream>>>(a, d_posts, d_fit_nonzero, d_ilogmask, d_nonzero);
+  return post_launch(c);
+}
+
+extern "C" int vb200_floor1_fit(vb200_ctx *c, int W, int floor_sel, int nrows, const float *logmdct,
+                                const float *logmask, int32_t *posts, int32_t *fit_nonzero) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nrows <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t n = c->dx[W].N / 2;
+  HostIO io{c};
+  void *da, *db, *dp, *dz; int rc;
+  if ((rc = io.h2d(logmdct, sizeof(float) * nrows * n, &da))) return rc;
+  if ((rc = io.h2d(logmask, sizeof(float) * nrows * n, &db))) return rc;
+  if ((rc = io.h2d(nullptr, sizeof(int32_t) * (size_t)nrows * VB200_FLOOR1_STRIDE, &dp))) return rc;
+  if ((rc = io.h2d(nullptr, sizeof(int32_t) * (size_t)nrows, &dz))) return rc;
+  if ((rc = vb200_floor1_fit_dev(c, W, floor_sel, nrows, (const float *)da, (const float *)db, (int32_t *)dp,
+                                 (int32_t *)dz, c->s_main))) return rc;
+  if ((rc = io.d2h(posts, dp, sizeof(int32_t) * (size_t)nrows * VB200_FLOOR1_STRIDE))) return rc;
+  if ((rc = io.d2h(fit_nonzero, dz, sizeof(int32_t) * (size_t)nrows))) return rc;
+  return io.sync();
+}
+
+extern "C" int vb200_floor1_render(vb200_ctx *c, int W, int floor_sel, int nrows, int32_t *posts,
+                                   const int32_t *fit_nonzero, int32_t *ilogmask, int32_t *nonzero) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nrows <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t n = c->dx[W].N / 2;
+  HostIO io{c};
+  void *dp, *dz, *di, *dn; int rc;
+  if ((rc = io.h2d(posts, sizeof(int32_t) * (size_t)nrows * VB200_FLOOR1_STRIDE, &dp))) return rc;
+  if ((rc = io.h2d(fit_nonzero, sizeof(int32_t) * (size_t)nrows, &dz))) return rc;
+  if ((rc = io.h2d(nullptr, sizeof(int32_t) * nrows * n, &di))) return rc;
+  if ((rc = io.h2d(nullptr, sizeof(int32_t) * (size_t)nrows, &dn))) return rc;
+  if ((rc = vb200_floor1_render_dev(c, W, floor_sel, nrows, (int32_t *)dp, (const int32_t *)dz, (int32_t *)di,
+                                    (int32_t *)dn, c->s_main))) return rc;
+  if ((rc = io.d2h(posts, dp, sizeof(int32_t) * (size_t)nrows * VB200_FLOOR1_STRIDE))) return rc;
+  if ((rc = io.d2h(ilogmask, di, sizeof(int32_t) * nrows * n))) return rc;
+  if ((rc = io.d2h(nonzero, dn, sizeof(int32_t) * (size_t)nrows))) return rc;
   return io.sync();
 }
 

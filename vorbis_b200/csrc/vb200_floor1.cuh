@@ -1,0 +1,349 @@
+// vb200_floor1.cuh — floor 1 on the device.
+//
+// k_floor1_fit     floor1_fit            lib/floor1.c:576-729
+//                    accumulate_fit      :406-454   per-gap integer sums, all lanes per gap + redux
+//                    fit_line            :456-521   fp64 chains, one lane per chain (12 lanes for the
+//                                                   two fits of a split), summed in accumulator order
+//                    inspect_error       :523-566   lanes over x; the Bresenham line in closed form
+//                    greedy splitting    :627-700   warp-uniform control flow, state in shared memory
+// k_floor1_render  floor1_encode minus the bit packing  :765-832 (quantise, predict/flag), :919-945
+//                    (render_line0 :376-403 into ilogmask)
+//
+// One warp per (block, channel) row.  All values are integers except vorbis_dBquant (fp32,
+// :278-283) and the line fit (fp64); the library is built -fmad=false so every expression rounds
+// where the C source rounds.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/vorbis_b200.h"
+
+struct Floor1Dev {                     // vorbis_look_floor1 (lib/codec_internal.h:138-155) in 16-bit
+  int posts, n, mult, pad;
+  float maxover, maxunder, maxerr, twofitweight, twofitatten;
+  short postlist[VB200_VIF_POSIT + 3], sorted[VB200_VIF_POSIT + 3];
+  short fwd[VB200_VIF_POSIT + 3], rev[VB200_VIF_POSIT + 3];
+  short lo[VB200_VIF_POSIT + 1], hi[VB200_VIF_POSIT + 1];
+};
+static_assert(sizeof(Floor1Dev) % 4 == 0, "Floor1Dev is copied as words");
+
+struct Floor1Args {
+  const Floor1Dev *floors;             // [VB200_MAX_SUBMAPS] of this block size
+  const unsigned char *chmux;          // [channels]
+  int channels, floor_sel, nrows, n;   // n = spectral lines per row (row stride)
+};
+
+#define F1_WARPS 8
+#define F1_ACC 12                      // xa ya x2a y2a xya an | xb yb x2b y2b xyb bn
+#define F1_STATE (6 * (VB200_VIF_POSIT + 2))
+
+__host__ __device__ inline size_t floor1_fit_smem_per_warp(int n) {
+  return sizeof(unsigned short) * (size_t)n + sizeof(int) * ((VB200_VIF_POSIT + 1) * F1_ACC + F1_STATE);
+}
+
+__device__ __forceinline__ int f1_dBquant(float x) {               // lib/floor1.c:278-283
+  int i = (int)(x * 7.3142857f + 1023.5f);
+  return i > 1023 ? 1023 : (i < 0 ? 0 : i);
+}
+
+__device__ __forceinline__ int f1_point(int x0, int x1, int y0, int y1, int x) {   // render_point
+  y0 &= 0x7fff; y1 &= 0x7fff;
+  const int dy = y1 - y0, adx = x1 - x0, ady = abs(dy);
+  const int off = (ady * (x - x0)) / adx;
+  return dy < 0 ? y0 - off : y0 + off;
+}
+
+// the integer line of render_line0 / inspect_error: after k steps the error term has wrapped
+// floor(k*ady/adx) times, each wrap adding (sy - base)
+struct F1Line {
+  int x0, y0, adx, base, ady, step;
+  __device__ __forceinline__ F1Line(int x0_, int x1, int y0_, int y1) {
+    x0 = x0_; y0 = y0_;
+    const int dy = y1 - y0;
+    adx = x1 - x0;
+    base = dy / adx;
+    step = dy < 0 ? -1 : 1;
+    ady = abs(dy) - abs(base * adx);
+  }
+  __device__ __forceinline__ int at(int x) const {
+    const int k = x - x0;
+    return y0 + k * base + ((k * ady) / adx) * step;
+  }
+};
+
+__device__ __forceinline__ int f1_postY(const int *A, const int *B, int pos) {
+  const int a = A[pos], b = B[pos];
+  if (a < 0) return b;
+  if (b < 0) return a;
+  return (a + b) >> 1;
+}
+
+// inspect_error: 1 = this line is not good enough.  q[x] = dBquant(mask[x]) | (audible << 15)
+__device__ __forceinline__ int f1_inspect(const Floor1Dev &F, const unsigned short *q, int x0, int x1,
+                                          int y0, int y1, int lane) {
+  const F1Line L(x0, x1, y0, y1);
+  int mse = 0, viol = 0;
+  for (int x = x0 + lane; x < x1; x += 32) {
+    const int y = L.at(x);
+    const int v = q[x];
+    const int val = v & 0x7fff;
+    mse += (y - val) * (y - val);
+    if ((v & 0x8000) && (x == x0 || val)) {
+      if ((float)y + F.maxover < (float)val) viol = 1;
+      if ((float)y - F.maxunder > (float)val) viol = 1;
+    }
+  }
+  if (__any_sync(0xffffffffu, viol)) return 1;
+  mse = __reduce_add_sync(0xffffffffu, mse);
+  const int cnt = x1 - x0;
+  if (F.maxover * F.maxover / (float)cnt > F.maxerr) return 0;
+  if (F.maxunder * F.maxunder / (float)cnt > F.maxerr) return 0;
+  if ((float)(mse / cnt) > F.maxerr) return 1;
+  return 0;
+}
+
+// fit_line for up to two runs of accumulators at once.  Lane 6*s + f sums chain f of side s in
+// accumulator order (the order the reference adds in); every lane then finishes both fits.
+// y[2*s], y[2*s+1] receive the fitted ends, return bit s = fit s was degenerate (reference ret 1).
+// The reference's "*y0 >= 0" endpoint terms never fire on this path (every call passes -200).
+__device__ __forceinline__ int f1_fit_lines(const Floor1Dev &F, const int *acc, int start0, int cnt0,
+                                            int start1, int cnt1, int lane, int y[4]) {
+  const int side = lane >= 6 ? 1 : 0, f = lane - 6 * side;
+  const int start = side ? start1 : start0;
+  const int cnt = lane < 12 ? (side ? cnt1 : cnt0) : 0;
+  double sum = 0.0;
+  for (int t = 0; t < cnt; t++) {
+    const int *a = acc + (start + t) * F1_ACC;
+    const int an = a[5], bn = a[11];
+    const double w = (double)((float)(bn + an) * F.twofitweight / (float)(an + 1)) + 1.0;
+    sum += (double)a[6 + f] + (double)a[f] * w;
+  }
+  int ret = 0;
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const double xb = __shfl_sync(0xffffffffu, sum, 6 * s + 0), yb = __shfl_sync(0xffffffffu, sum, 6 * s + 1);
+    const double x2b = __shfl_sync(0xffffffffu, sum, 6 * s + 2);
+    const double xyb = __shfl_sync(0xffffffffu, sum, 6 * s + 4), bn = __shfl_sync(0xffffffffu, sum, 6 * s + 5);
+    const int st = s ? start1 : start0, ct = s ? cnt1 : cnt0;
+    const int x0 = F.sorted[st], x1 = F.sorted[st + ct];
+    const double denom = bn * x2b - xb * xb;
+    int a0 = 0, a1 = 0;
+    if (ct > 0 && denom > 0.) {
+      const double A = (yb * x2b - xyb * xb) / denom;
+      const double B = (bn * xyb - xb * yb) / denom;
+      a0 = (int)rint(A + B * (double)x0);
+      a1 = (int)rint(A + B * (double)x1);
+      a0 = a0 > 1023 ? 1023 : (a0 < 0 ? 0 : a0);
+      a1 = a1 > 1023 ? 1023 : (a1 < 0 ? 0 : a1);
+    } else {
+      ret |= 1 << s;
+    }
+    y[2 * s] = a0; y[2 * s + 1] = a1;
+  }
+  return ret;
+}
+
+__global__ void __launch_bounds__(32 * F1_WARPS)
+k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__restrict__ logmask,
+             int32_t *__restrict__ posts_out, int32_t *__restrict__ fit_nonzero) {
+  extern __shared__ __align__(16) unsigned char f1_smem[];
+  Floor1Dev *sF = reinterpret_cast<Floor1Dev *>(f1_smem);
+  {
+    const int words = (int)(sizeof(Floor1Dev) * VB200_MAX_SUBMAPS / 4);
+    const int *src = reinterpret_cast<const int *>(a.floors);
+    int *dst = reinterpret_cast<int *>(sF);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *wbase = f1_smem + sizeof(Floor1Dev) * VB200_MAX_SUBMAPS + floor1_fit_smem_per_warp(a.n) * warp;
+  int *acc = reinterpret_cast<int *>(wbase);
+  int *A = acc + (VB200_VIF_POSIT + 1) * F1_ACC;
+  int *B = A + (VB200_VIF_POSIT + 2), *lon = B + (VB200_VIF_POSIT + 2), *hin = lon + (VB200_VIF_POSIT + 2);
+  int *memo = hin + (VB200_VIF_POSIT + 2), *out = memo + (VB200_VIF_POSIT + 2);
+  unsigned short *q = reinterpret_cast<unsigned short *>(out + (VB200_VIF_POSIT + 2));
+
+  for (long row = (long)blockIdx.x * F1_WARPS + warp; row < a.nrows; row += (long)gridDim.x * F1_WARPS) {
+    const int sel = a.floor_sel >= 0 ? a.floor_sel : a.chmux[row % a.channels];
+    const Floor1Dev &F = sF[sel];
+    const int P = F.posts, n = F.n;
+    const float *md = logmdct + (size_t)row * a.n, *mk = logmask + (size_t)row * a.n;
+    int32_t *po = posts_out + (size_t)row * VB200_FLOOR1_STRIDE;
+    __syncwarp();
+    for (int x = lane; x < n; x += 32) {
+      const float m = mk[x];
+      const int v = f1_dBquant(m);
+      q[x] = (unsigned short)(v | ((md[x] + F.twofitatten >= m) ? 0x8000 : 0));
+    }
+    for (int i = lane; i < P; i += 32) { A[i] = -200; B[i] = -200; lon[i] = 0; hin[i] = 1; memo[i] = -1; }
+    __syncwarp();
+    // accumulate_fit: one accumulator per gap, both ends inclusive
+    int nonzero = 0;
+    for (int j = 0; j < P - 1; j++) {
+      const int x0 = F.sorted[j];
+      int x1 = F.sorted[j + 1];
+      if (x1 >= n) x1 = n - 1;
+      int s[F1_ACC];
+#pragma unroll
+      for (int k = 0; k < F1_ACC; k++) s[k] = 0;
+      for (int x = x0 + lane; x <= x1; x += 32) {
+        const int v = q[x], val = v & 0x7fff;
+        if (val) {
+          if (v & 0x8000) { s[0] += x; s[1] += val; s[2] += x * x; s[3] += val * val; s[4] += x * val; s[5]++; }
+          else            { s[6] += x; s[7] += val; s[8] += x * x; s[9] += val * val; s[10] += x * val; s[11]++; }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < F1_ACC; k++) s[k] = __reduce_add_sync(0xffffffffu, s[k]);
+      if (lane < F1_ACC) {
+        int v = s[0];
+#pragma unroll
+        for (int k = 1; k < F1_ACC; k++) if (lane == k) v = s[k];
+        acc[j * F1_ACC + lane] = v;
+      }
+      nonzero += s[5];
+    }
+    __syncwarp();
+    if (!nonzero) {                                      // the reference returns NULL
+      for (int i = lane; i < VB200_FLOOR1_STRIDE; i += 32) po[i] = 0;
+      if (lane == 0) fit_nonzero[row] = 0;
+      continue;
+    }
+    int y[4];
+    f1_fit_lines(F, acc, 0, P - 1, 0, 0, lane, y);
+    if (lane == 0) { A[0] = y[0]; B[0] = y[0]; A[1] = y[1]; B[1] = y[1]; }
+    __syncwarp();
+    for (int i = 2; i < P; i++) {
+      const int sortpos = F.rev[i];
+      const int ln = lon[sortpos], hn = hin[sortpos];
+      if (memo[ln] == hn) continue;                      // this span was already judged
+      const int lsortpos = F.rev[ln], hsortpos = F.rev[hn];
+      const int lx = F.postlist[ln], hx = F.postlist[hn];
+      const int ly = f1_postY(A, B, ln), hy = f1_postY(A, B, hn);
+      __syncwarp();
+      if (lane == 0) memo[ln] = hn;
+      if (f1_inspect(F, q, lx, hx, ly, hy, lane)) {
+        const int ret = f1_fit_lines(F, acc, lsortpos, sortpos - lsortpos, sortpos, hsortpos - sortpos, lane, y);
+        int ly0 = y[0], ly1 = y[1], hy0 = y[2], hy1 = y[3];
+        if (ret & 1) { ly0 = ly; ly1 = hy0; }
+        if (ret & 2) { hy0 = ly1; hy1 = hy; }
+        if (lane == 0) {
+          if (ret == 3) {
+            A[i] = -200; B[i] = -200;
+          } else {
+            B[ln] = ly0;
+            if (ln == 0) A[ln] = ly0;
+            A[i] = ly1; B[i] = hy0;
+            A[hn] = hy1;
+            if (hn == 1) B[hn] = hy1;
+            if (ly1 >= 0 || hy0 >= 0) {
+              for (int j = sortpos - 1; j >= 0; j--) { if (hin[j] == hn) hin[j] = i; else break; }
+              for (int j = sortpos + 1; j < P; j++) { if (lon[j] == ln) lon[j] = i; else break; }
+            }
+          }
+        }
+      } else if (lane == 0) {
+        A[i] = -200; B[i] = -200;
+      }
+      __syncwarp();
+    }
+    // posts as the reference returns them: fitted value, or predicted | 0x8000 when unused
+    if (lane == 0) {
+      out[0] = f1_postY(A, B, 0);
+      out[1] = f1_postY(A, B, 1);
+      for (int i = 2; i < P; i++) {
+        const int ln = F.lo[i - 2], hn = F.hi[i - 2];
+        const int predicted = f1_point(F.postlist[ln], F.postlist[hn], out[ln], out[hn], F.postlist[i]);
+        const int vx = f1_postY(A, B, i);
+        out[i] = (vx >= 0 && predicted != vx) ? vx : (predicted | 0x8000);
+      }
+      fit_nonzero[row] = 1;
+    }
+    __syncwarp();
+    for (int i = lane; i < VB200_FLOOR1_STRIDE; i += 32) po[i] = i < P ? out[i] : 0;
+  }
+}
+
+__global__ void __launch_bounds__(32 * F1_WARPS)
+k_floor1_render(Floor1Args a, int32_t *__restrict__ posts, const int32_t *__restrict__ fit_nonzero,
+                int32_t *__restrict__ ilogmask, int32_t *__restrict__ nonzero) {
+  __shared__ Floor1Dev sF[VB200_MAX_SUBMAPS];
+  __shared__ int s_post[F1_WARPS][VB200_VIF_POSIT + 2];
+  __shared__ short s_segx[F1_WARPS][VB200_VIF_POSIT + 3];
+  __shared__ short s_segy[F1_WARPS][VB200_VIF_POSIT + 3];
+  {
+    const int words = (int)(sizeof(Floor1Dev) * VB200_MAX_SUBMAPS / 4);
+    const int *src = reinterpret_cast<const int *>(a.floors);
+    int *dst = reinterpret_cast<int *>(sF);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int *post = s_post[warp];
+  short *segx = s_segx[warp], *segy = s_segy[warp];
+  for (long row = (long)blockIdx.x * F1_WARPS + warp; row < a.nrows; row += (long)gridDim.x * F1_WARPS) {
+    int32_t *il = ilogmask + (size_t)row * a.n;
+    if (!fit_nonzero[row]) {
+      for (int x = lane; x < a.n; x += 32) il[x] = 0;
+      if (lane == 0) nonzero[row] = 0;
+      continue;
+    }
+    const int sel = a.floor_sel >= 0 ? a.floor_sel : a.chmux[row % a.channels];
+    const Floor1Dev &F = sF[sel];
+    const int P = F.posts;
+    int32_t *pr = posts + (size_t)row * VB200_FLOOR1_STRIDE;
+    __syncwarp();
+    for (int i = lane; i < P; i += 32) {                 // quantise to the multiplier, :765-783
+      const int p = pr[i];
+      int val = p & 0x7fff;
+      switch (F.mult) {
+        case 1: val >>= 2; break;
+        case 2: val >>= 3; break;
+        case 3: val /= 12; break;
+        case 4: val >>= 4; break;
+      }
+      post[i] = val | (p & 0x8000);
+    }
+    __syncwarp();
+    if (lane == 0) {                                     // prediction / flag pass, :788-832
+      for (int i = 2; i < P; i++) {
+        const int ln = F.lo[i - 2], hn = F.hi[i - 2];
+        const int predicted = f1_point(F.postlist[ln], F.postlist[hn], post[ln], post[hn], F.postlist[i]);
+        if ((post[i] & 0x8000) || predicted == post[i]) {
+          post[i] = predicted | 0x8000;
+        } else {
+          post[ln] &= 0x7fff;
+          post[hn] &= 0x7fff;
+        }
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < P; i += 32) pr[i] = post[i];
+    // the posts that carry a value, in abscissa order
+    int nseg = 0;
+    if (lane == 0) { segx[0] = 0; segy[0] = (short)(post[0] * F.mult); }
+    for (int j0 = 1; j0 < P; j0 += 32) {
+      const int j = j0 + lane;
+      int used = 0, cur = 0;
+      if (j < P) { cur = F.fwd[j]; used = !(post[cur] & 0x8000); }
+      const unsigned m = __ballot_sync(0xffffffffu, used);
+      if (used) {
+        const int k = nseg + __popc(m & ((1u << lane) - 1)) + 1;
+        segx[k] = F.postlist[cur];
+        segy[k] = (short)(post[cur] * F.mult);
+      }
+      nseg += __popc(m);
+    }
+    __syncwarp();
+    for (int k = 0; k < nseg; k++) {                     // render_line0 clipped at the row length
+      const int lx = segx[k], hx = segx[k + 1];
+      const F1Line L(lx, hx, segy[k], segy[k + 1]);
+      const int lim = hx < a.n ? hx : a.n;
+      for (int x = lx + lane; x < lim; x += 32) il[x] = L.at(x);
+    }
+    {
+      const int hx = segx[nseg], ly = segy[nseg];
+      for (int x = hx + lane; x < a.n; x += 32) il[x] = ly;
+    }
+    if (lane == 0) nonzero[row] = 1;
+  }
+}

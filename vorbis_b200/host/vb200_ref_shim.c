@@ -7,6 +7,7 @@
  *   -D_vp_noisemask=vb200shim_noisemask -D_vp_tonemask=vb200shim_tonemask
  *   -D_vp_offset_and_mix=vb200shim_offset_and_mix
  *   -D_vp_couple_quantize_normalize=vb200shim_couple_quantize_normalize
+ *   -Dfloor1_fit=vb200shim_floor1_fit
  * (or renames the callees in place); nothing else in libvorbis changes.  Every function
  * below has exactly the prototype of the reference function it replaces (cited), and
  * the same argument meaning, in-place behaviour and (absence of) error returns; a CUDA
@@ -105,6 +106,26 @@ int vb200shim_attach(vorbis_dsp_state *vd, int device){
   }
   s.window[0] = _vorbis_window_get(b->window[0]);
   s.window[1] = _vorbis_window_get(b->window[1]);
+  /* floors per submap (lib/mapping0.c:499-506); only encode-side floor 1 is bound */
+  for(w = 0; w < 2 && w < ci->modes && vd->analysisp; w++){
+    vorbis_info_mapping0 *m = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[w]->mapping];
+    if(m->submaps > VB200_MAX_SUBMAPS) continue;
+    s.submaps[w] = m->submaps;
+    for(k = 0; k < vi->channels; k++) s.chmux[w][k] = (uint8_t)m->chmuxlist[k];
+    for(j = 0; j < m->submaps; j++){
+      int fl = m->floorsubmap[j];
+      if(ci->floor_type[fl] == 1){
+        vorbis_info_floor1 *fi = (vorbis_info_floor1*)ci->floor_param[fl];
+        vorbis_look_floor1 *lk = (vorbis_look_floor1*)b->flr[fl];
+        vb200_floor1_setup *o = &s.floor1[w][j];
+        o->posts = lk->posts;
+        for(i = 0; i < lk->posts; i++) o->postlist[i] = fi->postlist[i];
+        o->mult = fi->mult; o->n = lk->n;
+        o->maxover = fi->maxover; o->maxunder = fi->maxunder; o->maxerr = fi->maxerr;
+        o->twofitweight = fi->twofitweight; o->twofitatten = fi->twofitatten;
+      }
+    }
+  }
   rc = vb200_ctx_create(&s, device, &g.ctx);
   if(rc){ shim_warn("vb200_ctx_create", rc); return rc; }
   g.vd = vd;
@@ -188,4 +209,21 @@ void vb200shim_couple_quantize_normalize(int blobno, vorbis_info_psy_global *gp,
   if(rc) shim_warn("couple_quantize_normalize", rc);
   else for(c = 0; c < ch; c++){ memcpy(iwork[c], iw + (size_t)c*n, sizeof(int32_t)*n); nonzero[c] = nz[c]; }
   free(m); free(iw); free(nz);
+}
+
+/* floor1_fit, lib/floor1.c:576: returns posts in vorbis_block storage, or NULL for a silent channel */
+int *vb200shim_floor1_fit(vorbis_block *vb, vorbis_look_floor1 *look, const float *logmdct, const float *logmask){
+  codec_setup_info *ci = (codec_setup_info*)g.vd->vi->codec_setup;
+  private_state *b = (private_state*)g.vd->backend_state;
+  vorbis_info_mapping0 *m = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[vb->W]->mapping];
+  int32_t posts[VB200_FLOOR1_STRIDE], nz = 0;
+  int sel = -1, j, rc, *out;
+  for(j = 0; j < m->submaps; j++) if((void*)b->flr[m->floorsubmap[j]] == (void*)look) sel = j;
+  if(sel < 0){ fprintf(stderr, "vb200 shim: floor1_fit: unknown floor look\n"); return NULL; }
+  rc = vb200_floor1_fit(g.ctx, (int)vb->W, sel, 1, logmdct, logmask, posts, &nz);
+  if(rc){ shim_warn("floor1_fit", rc); return NULL; }
+  if(!nz) return NULL;
+  out = (int*)_vorbis_block_alloc(vb, sizeof(*out) * look->posts);
+  for(j = 0; j < look->posts; j++) out[j] = posts[j];
+  return out;
 }

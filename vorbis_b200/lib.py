@@ -27,6 +27,7 @@ EXPORTS = [
     "vb200_analysis_phaseA_pcmstream_dev", "vb200_synthesis_s16_dev",
     "vb200_couple_quantize_normalize_dev", "vb200_couple_quantize_normalize",
     "vb200_synthesis_dev", "vb200_synthesis", "vb200_decouple_dev", "vb200_decouple",
+    "vb200_floor1_fit_dev", "vb200_floor1_fit", "vb200_floor1_render_dev", "vb200_floor1_render",
     "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
 ]
 
@@ -82,6 +83,10 @@ def load():
     L.vb200_synthesis.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, C.c_int64]
     L.vb200_decouple_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.vb200_decouple.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.vb200_floor1_fit_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.vb200_floor1_fit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.vb200_floor1_render_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.vb200_floor1_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.vb200_malloc_device.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.vb200_free_device.argtypes = [vp, vp]
     L.vb200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -259,6 +264,36 @@ class Context:
         self._chk(self.L.vb200_couple_quantize_normalize_dev(self.h, W, blocktype, blobno, nblocks,
                                                              _ptr(d_mdct), _ptr(d_iwork), _ptr(d_nonzero),
                                                              _ptr(stream)))
+
+    # ---- floor 1 (lib/floor1.c:576 floor1_fit, :765 floor1_encode minus the bit packing) -------
+    def floor1_fit(self, W, logmdct, logmask, floor_sel=-1):
+        """logmdct, logmask [rows][n] -> (posts [rows][FLOOR1_STRIDE] int32, fit_nonzero [rows])"""
+        n = self.bs[W] // 2
+        a = np.ascontiguousarray(logmdct, np.float32).reshape(-1, n)
+        b = np.ascontiguousarray(logmask, np.float32).reshape(-1, n)
+        posts = np.zeros((a.shape[0], abi.FLOOR1_STRIDE), np.int32)
+        nz = np.zeros(a.shape[0], np.int32)
+        self._chk(self.L.vb200_floor1_fit(self.h, W, floor_sel, a.shape[0], _ptr(a), _ptr(b), _ptr(posts), _ptr(nz)))
+        return posts, nz
+
+    def floor1_render(self, W, posts, fit_nonzero, floor_sel=-1):
+        """posts from floor1_fit -> (posts as floor1_encode leaves them, ilogmask [rows][n], nonzero)"""
+        n = self.bs[W] // 2
+        posts = np.array(posts, np.int32).reshape(-1, abi.FLOOR1_STRIDE)
+        fz = np.ascontiguousarray(fit_nonzero, np.int32)
+        ilog = np.zeros((posts.shape[0], n), np.int32)
+        nz = np.zeros(posts.shape[0], np.int32)
+        self._chk(self.L.vb200_floor1_render(self.h, W, floor_sel, posts.shape[0], _ptr(posts), _ptr(fz),
+                                             _ptr(ilog), _ptr(nz)))
+        return posts, ilog, nz
+
+    def floor1_fit_dev(self, W, nrows, d_logmdct, d_logmask, d_posts, d_fit_nonzero, floor_sel=-1, stream=None):
+        self._chk(self.L.vb200_floor1_fit_dev(self.h, W, floor_sel, nrows, _ptr(d_logmdct), _ptr(d_logmask),
+                                              _ptr(d_posts), _ptr(d_fit_nonzero), _ptr(stream)))
+
+    def floor1_render_dev(self, W, nrows, d_posts, d_fit_nonzero, d_ilogmask, d_nonzero, floor_sel=-1, stream=None):
+        self._chk(self.L.vb200_floor1_render_dev(self.h, W, floor_sel, nrows, _ptr(d_posts), _ptr(d_fit_nonzero),
+                                                 _ptr(d_ilogmask), _ptr(d_nonzero), _ptr(stream)))
 
     # ---- decode ------------------------------------------------------------------
     def decouple(self, W, res):
