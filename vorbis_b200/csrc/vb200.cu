@@ -1218,7 +1218,7 @@ extern "C" int vb200_couple_quantize_normalize_dev(vb200_ctx *c, int W, int bloc
   CqnDev Q; int rc;
   if ((rc = cqn_setup(c, W, blocktype, blobno, &Q))) return rc;
   const int wpb = 4;
-  const size_t smem = (size_t)wpb * (4 * Q.ch * 32 * sizeof(float) + Q.ch * sizeof(int));
+  const size_t smem = (size_t)wpb * (CQN_COLS * Q.ch * 32 * sizeof(float) + Q.ch * sizeof(int));
   if (smem > 200 * 1024) return fail(VB200_EIMPL, "too many channels for the coupling kernel");
   if ((rc = set_smem(k_cqn, smem))) return rc;
   const long tasks = (long)nblocks * (Q.n / 32);

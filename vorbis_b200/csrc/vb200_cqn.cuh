@@ -48,16 +48,24 @@ __device__ __forceinline__ void cqn_normalize(const CqnDev &Q, float r, float &q
   }
   // (a) acc += ve over the pooled lines in increasing line order (fp32, sequential)
   // (b) rank among pooled lines, descending by q, ties by line order (stable, as qsort here)
-  float acc = 0.f;
-  int rank = 0, any = 0;
+  // Only pooled lines take part, so the walk visits the set bits of the ballot: `offs` is the
+  // union over the warp's partitions of the in-partition offsets that hold a pooled line.
+  const unsigned bal = __ballot_sync(full, pooled);
+  if (!bal) return;
   const int g0 = lane & ~(width - 1);
-  for (int t = 0; t < width; t++) {
+  const unsigned wmask = width == 32 ? full : ((1u << width) - 1u);
+  const unsigned mine = (bal >> g0) & wmask;
+  unsigned offs = 0;
+  for (int g = 0; g < 32; g += width) offs |= (bal >> g) & wmask;
+  float acc = 0.f;
+  int rank = 0;
+  const int any = mine != 0;
+  for (unsigned m = offs; m; m &= m - 1) {
+    const int t = __ffs(m) - 1;
     const float vt = __shfl_sync(full, ve, g0 + t);
     const float qt = __shfl_sync(full, q, g0 + t);
-    const int pt = __shfl_sync(full, (int)pooled, g0 + t);
-    if (pt) {
+    if ((mine >> t) & 1) {
       acc += vt;
-      any = 1;
       if (qt > q || (qt == q && t < j)) rank++;
     }
   }
@@ -79,17 +87,19 @@ __device__ __forceinline__ void cqn_normalize(const CqnDev &Q, float r, float &q
   }
 }
 
-// smem per warp: raw, quant, floor (float) and flag (int): 4 * ch * 32 words
+// smem per warp: raw, quant, floor (float), flag and quantised value (int): CQN_COLS * ch * 32 words
+#define CQN_COLS 5
 __global__ void __launch_bounds__(128)
 k_cqn(CqnDev Q, int nblocks, const float *__restrict__ mdct, int *__restrict__ iwork,
       const int *__restrict__ nonzero) {
   extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const int n = Q.n, ch = Q.ch, width = Q.partition;
-  float *raw = sm + (size_t)wid * 4 * ch * 32;
+  float *raw = sm + (size_t)wid * CQN_COLS * ch * 32;
   float *quant = raw + ch * 32, *flr = quant + ch * 32;
   int *flag = reinterpret_cast<int *>(flr + ch * 32);
-  int *nz = reinterpret_cast<int *>(sm + (size_t)wpb * 4 * ch * 32) + wid * ch;   // [ch] per warp
+  int *iq = flag + ch * 32;
+  int *nz = reinterpret_cast<int *>(sm + (size_t)wpb * CQN_COLS * ch * 32) + wid * ch;   // [ch] per warp
   const int chunks = n >> 5;
   const long tasks = (long)nblocks * chunks;
   for (long t = (long)blockIdx.x * wpb + wid; t < tasks; t += (long)gridDim.x * wpb) {
@@ -113,7 +123,7 @@ k_cqn(CqnDev Q, int nblocks, const float *__restrict__ mdct, int *__restrict__ i
         cqn_normalize(Q, R, Qe, F, false, 0, i, j, out, width, lane);
       }
       raw[k * 32 + lane] = R; quant[k * 32 + lane] = Qe; flr[k * 32 + lane] = F; flag[k * 32 + lane] = nz[k] ? G : 0;
-      iw[(size_t)k * n + line] = out;
+      iq[k * 32 + lane] = out;
       // note: flag_lossless results are kept for the coupling below; a zero channel has flag 0
     }
     for (int step = 0; step < Q.steps; step++) {
@@ -126,7 +136,7 @@ k_cqn(CqnDev Q, int nblocks, const float *__restrict__ mdct, int *__restrict__ i
       float qeM = quant[Mi * 32 + lane], qeA = quant[Ai * 32 + lane];
       float fM = flr[Mi * 32 + lane], fA = flr[Ai * 32 + lane];
       int gM = flag[Mi * 32 + lane], gA = flag[Ai * 32 + lane];
-      int iM = iw[(size_t)Mi * n + line], iA = iw[(size_t)Ai * n + line];
+      int iM = iq[Mi * 32 + lane], iA = iq[Ai * 32 + lane];
       if (j < Q.sliding_lowpass - i) {
         if (gM || gA) {                                    // lossless: integer square-polar map
           const int A = iM, B = iA;
@@ -160,8 +170,9 @@ k_cqn(CqnDev Q, int nblocks, const float *__restrict__ mdct, int *__restrict__ i
       quant[Mi * 32 + lane] = qeM; quant[Ai * 32 + lane] = qeA;
       flr[Mi * 32 + lane] = fM; flr[Ai * 32 + lane] = fA;
       flag[Mi * 32 + lane] = gM; flag[Ai * 32 + lane] = gA;
-      iw[(size_t)Mi * n + line] = iM; iw[(size_t)Ai * n + line] = iA;
+      iq[Mi * 32 + lane] = iM; iq[Ai * 32 + lane] = iA;
     }
+    for (int k = 0; k < ch; k++) iw[(size_t)k * n + line] = iq[k * 32 + lane];
     __syncwarp();
   }
 }
