@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""bench.py — encode Phase-A (window + MDCT + FFT + noise/tone masks + mix) throughput.
+"""bench.py — per-block encode DSP of mapping0_forward (window + MDCT + FFT + noise/tone masks + mix
++ floor1 fit/render + couple/quantise/normalise) throughput.
 
   python bench.py --gpus N --steps K --warmup W          our CUDA path (default N=1)
   python bench.py --impl reference ...                   the reference's CPU code on the host cores
@@ -7,7 +8,11 @@
 Workload (BASELINE.json configs[2]): 44.1 kHz stereo, vorbis_encode_init_vbr q=0.5, 100 000
 long blocks (N=2048 samples -> 1024 spectral lines per channel: the "N=1024" of the metric;
 SURVEY.md §8d) per GPU per step, synthetic PCM, independent blocks with ampmax given per block
-(drop-in semantics).  One step = one pass of the hot path over that batch.
+(drop-in semantics).  One step = one pass of the hot path over that batch: ONE vb200_encode_dsp_dev
+call = six kernels (transform, ampmax, psy, floor1_fit, floor1_render, couple_quantize_normalize).
+`e2e` is the same chain through vb200_encode_dsp with pinned HOST buffers: int16 interleaved stream
+PCM in (blocks cut on the device, hop N/2), floor posts + quantised residue out.  The reference arm
+and cpu_baseline run the same chain with the reference's own functions.
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
 """
@@ -33,7 +38,8 @@ W_LONG = 1
 
 
 def workload_name(nblocks, N, ch):
-    return ("mapping0_forward Phase A (window+MDCT+FFT+noise/tone mask+mix), 44.1kHz stereo q=0.5, "
+    return ("mapping0_forward per-block DSP (window+MDCT+FFT+noise/tone mask+mix, floor1 fit+render, "
+            "couple/quantise/normalise), 44.1kHz stereo q=0.5, "
             "%d long blocks x %d ch x N=%d samples (n=%d lines/ch)" % (nblocks, ch, N, N // 2))
 
 
@@ -121,7 +127,7 @@ def make_desc(nblocks):
 
 
 def cpu_reference_rate(setup_name, W, pcm_np, desc_np, threads):
-    """Reference CPU implementation of the same Phase A on `threads` host threads (the library is
+    """Reference CPU implementation of the same chain on `threads` host threads (the library is
     single threaded; blocks are independent, one reference instance per thread).  Returns
     (blocks/s, kind).  Uses oracle/_ref (the compiled reference) when present, else the oracle port."""
     from concurrent.futures import ThreadPoolExecutor
@@ -135,7 +141,7 @@ def cpu_reference_rate(setup_name, W, pcm_np, desc_np, threads):
         insts = [pyref.Ref(ch, 44100, 0.5) for _ in shards]
 
         def run(i):
-            insts[i].phaseA_batch(W, pcm_np[shards[i]], desc_np[shards[i]])
+            insts[i].encode_dsp_batch(W, pcm_np[shards[i]], desc_np[shards[i]])
     else:
         kind = "port"
         from oracle import pyoracle
@@ -143,7 +149,7 @@ def cpu_reference_rate(setup_name, W, pcm_np, desc_np, threads):
         insts = [pyoracle.Oracle(setup) for _ in shards]
 
         def run(i):
-            insts[i].phaseA(W, pcm_np[shards[i]], desc_np[shards[i]])
+            insts[i].encode_dsp(W, pcm_np[shards[i]], desc_np[shards[i]])
     with ThreadPoolExecutor(len(shards)) as ex:
         list(ex.map(run, range(len(shards))))           # warm caches / page in
         t0 = time.perf_counter()
@@ -239,55 +245,45 @@ def extra_configs(torch, lib, abi, device, peak):
     out["decode_4096streams_x33blocks_mixed"] = {"ms": ms, "stereo_blocks_per_s": ns * nblk / ms * 1e3,
                                                   "algorithmic_GBps": byts / ms / 1e6,
                                                   "frac_of_hbm_peak": byts / ms / 1e6 / peak}
-    # the whole per-block encode DSP on the device - Phase A, floor1_fit, floor render,
-    # couple/quantise/normalise - 20000 long stereo blocks, buffers resident
+    # Phase A alone through vb200_analysis_phaseA with float host buffers (the round-1 e2e figure, kept for
+    # continuity: 16 KB in + 24.6 KB out per block instead of 4 KB + 8.4 KB for the one-call chain)
     nb, N, chn = 20000, bs[1], s44.channels
     n = N // 2
-    pcm_e = synth_pcm_torch(torch, nb, chn, N, 44100, dev, 99)
-    d_desc = torch.from_numpy(make_desc(nb).view(np.uint8).reshape(-1, 16).copy()).to(dev)
-    o_m = torch.empty((nb, chn, n), device=dev); o_lm = torch.empty_like(o_m); o_mask = torch.empty_like(o_m)
-    o_amp = torch.empty(nb, device=dev)
-    posts = torch.empty((nb * chn, abi.FLOOR1_STRIDE), dtype=torch.int32, device=dev)
-    fnz = torch.empty(nb * chn, dtype=torch.int32, device=dev)
-    iwork = torch.empty((nb, chn, n), dtype=torch.int32, device=dev)
-    nz = torch.empty(nb * chn, dtype=torch.int32, device=dev)
-    io = abi.PhaseAIO()
-    io.pcm, io.desc = pcm_e.data_ptr(), d_desc.data_ptr()
-    io.mdct, io.logmdct, io.logmask, io.ampmax_out = o_m.data_ptr(), o_lm.data_ptr(), o_mask.data_ptr(), o_amp.data_ptr()
-    stages = {
-        "phaseA": lambda: c44.phaseA_dev(1, nb, io, stream=stream),
-        "floor1_fit": lambda: c44.floor1_fit_dev(1, nb * chn, o_lm.data_ptr(), o_mask.data_ptr(), posts.data_ptr(),
-                                                 fnz.data_ptr(), stream=stream),
-        "floor1_render": lambda: c44.floor1_render_dev(1, nb * chn, posts.data_ptr(), fnz.data_ptr(), iwork.data_ptr(),
-                                                       nz.data_ptr(), stream=stream),
-    }
-
-    def fit_render():                   # render rewrites posts in place: time it behind a fresh fit
-        stages["floor1_fit"]()
-        stages["floor1_render"]()
-
-    def render_cqn():                   # CQN rewrites iwork in place: time it behind a fresh fit + render
-        fit_render()
-        c44.couple_quantize_normalize_dev(1, 1, 7, nb, o_m.data_ptr(), iwork.data_ptr(), nz.data_ptr(), stream=stream)
-    chain = {}
-    chain["phaseA_ms"] = timed(stages["phaseA"], reps=3)
-    chain["floor1_fit_ms"] = timed(stages["floor1_fit"], reps=3)
-    fr = timed(fit_render, reps=3)
-    chain["floor1_render_ms"] = fr - chain["floor1_fit_ms"]
-    stages["couple_quantize_normalize"] = lambda: c44.couple_quantize_normalize_dev(
-        1, 1, 7, nb, o_m.data_ptr(), iwork.data_ptr(), nz.data_ptr(), stream=stream)
-    chain["couple_quantize_normalize_ms"] = timed(render_cqn, reps=3) - fr
-
-    def whole():
-        for fn in stages.values():
-            fn()
-    ms = timed(whole, reps=3)
-    chain["whole_chain_ms"] = ms
-    chain["stereo_blocks_per_s"] = nb / ms * 1e3
-    chain["blocks"] = nb
-    out["encode_chain_phaseA_floor1_cqn_20000_long_stereo"] = chain
+    hp = synth_pcm_torch(torch, nb, chn, N, 44100, dev, 99).cpu().pin_memory()
+    outs = [torch.empty((nb, chn, n), dtype=torch.float32).pin_memory() for _ in range(3)]
+    hamp = torch.empty(nb, dtype=torch.float32).pin_memory()
+    hdesc = make_desc(nb)
+    hio = abi.PhaseAIO()
+    hio.pcm, hio.desc = hp.data_ptr(), hdesc.ctypes.data
+    hio.mdct, hio.logmdct, hio.logmask = (o.data_ptr() for o in outs)
+    hio.ampmax_out = hamp.data_ptr()
+    L = lib.load()
+    for _ in range(2):
+        L.vb200_analysis_phaseA(c44.h, 1, nb, C.byref(hio))
+    t0 = time.perf_counter()
+    for _ in range(3):
+        L.vb200_analysis_phaseA(c44.h, 1, nb, C.byref(hio))
+    dt = (time.perf_counter() - t0) / 3
+    out["phaseA_only_f32_host_buffers_20000_long_stereo"] = {"stereo_blocks_per_s": nb / dt,
+                                                             "h2d_bytes": int(hp.numel() * 4), "d2h_bytes": int(3 * outs[0].numel() * 4)}
     c44.close()
     return out
+
+
+def synth_stream_s16(torch, ns, stride, ch, rate, device, seed):
+    """[streams][stride][ch] int16: the same noise+sine mix as synth_pcm_torch, as a contiguous stream"""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    t = torch.arange(stride, device=device, dtype=torch.float32).view(1, stride, 1)
+    x = torch.rand((ns, stride, ch), generator=g, device=device, dtype=torch.float32)
+    x.mul_(0.5).sub_(0.25)
+    f = 440.0 + 110.0 * torch.arange(ch, device=device, dtype=torch.float32).view(1, 1, ch)
+    ph = torch.rand((ns, 1, 1), generator=g, device=device) * 6.2831853
+    x.add_(0.5 * torch.sin(2 * np.pi * f * t / rate + ph))
+    return (x * 32767.0).round_().clamp_(-32768, 32767).to(torch.int16)
+
+
+KERNELS = ["k_phaseA_transform", "k_ampmax", "k_phaseA_psy", "k_floor1_fit", "k_floor1_render", "k_cqn"]
 
 
 def run_ours(args):
@@ -313,16 +309,16 @@ def run_ours(args):
     pcm = synth_pcm_torch(torch, nb, ch, N, setup.rate, dev, seed=1000 + rank)
     desc_np = make_desc(nb)
     desc = torch.from_numpy(desc_np.view(np.uint8).reshape(nb, 16).copy()).to(dev)
-    mdct = torch.empty((nb, ch, n), device=dev, dtype=torch.float32)
-    logmdct = torch.empty_like(mdct)
-    logmask = torch.empty_like(mdct)
+    posts = torch.empty((nb, ch, abi.FLOOR1_STRIDE), device=dev, dtype=torch.int32)
+    nonzero = torch.empty((nb, ch), device=dev, dtype=torch.int32)
+    iwork = torch.empty((nb, ch, n), device=dev, dtype=torch.int32)
     amp = torch.empty(nb, device=dev, dtype=torch.float32)
-    io = abi.PhaseAIO()
-    io.pcm, io.desc = pcm.data_ptr(), desc.data_ptr()
-    io.mdct, io.logmdct, io.logmask, io.ampmax_out = mdct.data_ptr(), logmdct.data_ptr(), logmask.data_ptr(), amp.data_ptr()
+    io = abi.EncodeIO()
+    io.pcm, io.pcm_fmt, io.desc, io.independent = pcm.data_ptr(), 0, desc.data_ptr(), 1
+    io.posts, io.nonzero, io.iwork, io.ampmax_out = posts.data_ptr(), nonzero.data_ptr(), iwork.data_ptr(), amp.data_ptr()
 
     def step():
-        ctx.phaseA_dev(W_LONG, nb, io, stream=sptr)
+        ctx.encode_dsp_dev(W_LONG, nb, 1, io, blobno=7, stream=sptr)
 
     def barrier():
         torch.cuda.synchronize()
@@ -354,22 +350,71 @@ def run_ours(args):
 
     # per-kernel durations (CUDA events on the launching stream, inside the library) for the roofline
     ctx.set_profiling(True)
-    kms = np.zeros(3)
+    kms = np.zeros(6)
     reps = max(3, args.steps)
     for _ in range(reps):
         step()
         torch.cuda.synchronize()
-        kms += np.array(ctx.phaseA_kernel_ms())
+        kms += np.array(ctx.encode_dsp_kernel_ms())
     kms /= reps
     ctx.set_profiling(False)
+
+    # ---- end to end through the host-buffer C-ABI call: int16 stream PCM in (pinned), posts + residue out.
+    # Every rank runs it on its own shard at the same time (streams are independent: no collective).
+    bps = args.e2e_blocks_per_stream
+    ns_e = max(1, min(nb, args.e2e_blocks) // bps)
+    nb_e = ns_e * bps
+    hop = N // 2
+    stride = (bps - 1) * hop + N
+    s16 = synth_stream_s16(torch, ns_e, stride, ch, setup.rate, dev, seed=2000 + rank)
+    hp = torch.empty((ns_e, stride, ch), dtype=torch.int16).pin_memory()
+    hp.copy_(s16)
+    del s16
+    hdesc = make_desc(nb_e)
+    h_posts = torch.empty((nb_e, ch, abi.FLOOR1_STRIDE), dtype=torch.int32).pin_memory()
+    h_nz = torch.empty((nb_e, ch), dtype=torch.int32).pin_memory()
+    h_iw = torch.empty((nb_e, ch, n), dtype=torch.int32).pin_memory()
+    h_amp = torch.empty(nb_e, dtype=torch.float32).pin_memory()
+    hio = abi.EncodeIO()
+    hio.pcm, hio.pcm_fmt, hio.hop, hio.stream_stride = hp.data_ptr(), lib.PCM_S16_INTERLEAVED, hop, stride
+    hio.desc, hio.independent = hdesc.ctypes.data, 0
+    hio.posts, hio.nonzero, hio.iwork, hio.ampmax_out = h_posts.data_ptr(), h_nz.data_ptr(), h_iw.data_ptr(), h_amp.data_ptr()
+    L = lib.load()
+
+    def e2e_step():
+        rc = L.vb200_encode_dsp(ctx.h, W_LONG, ns_e, bps, 7, C.byref(hio))
+        if rc:
+            raise RuntimeError("vb200_encode_dsp failed: %d" % rc)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    l1 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    e2e_launches = ctx.launch_count() - l1
+    td = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    dt_max = float(td.item())
+    h2d = int(hp.numel() * 2 + hdesc.nbytes)
+    d2h = int((h_posts.numel() + h_nz.numel() + h_iw.numel() + h_amp.numel()) * 4)
+    e2e = {"value": world * nb_e * args.steps / dt_max, "unit": UNIT,
+           "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+           "blocks_per_step": nb_e * world, "gpu_launches": int(e2e_launches),
+           "call": "vb200_encode_dsp: %d streams x %d blocks per GPU, int16 interleaved stream PCM in (hop N/2, "
+                   "blocks cut on the device), posts+nonzero+quantised residue out; pinned host memory; "
+                   "three-lane chunk pipeline; wall clock, max over ranks" % (ns_e, bps)}
 
     line = None
     if rank == 0:
         peak, peak_src = load_peaks()
-        names = ["k_phaseA_transform", "k_ampmax", "k_phaseA_psy"]
-        # algorithmic bytes per channel-block: transform reads 4N, writes mdct 2N + logfft 2N;
-        # psy reads mdct 2N + logfft 2N, writes mdct' 2N + logmdct 2N + logmask 2N.  Phase A fused: 10N.
-        alg = [8 * N, 0, 10 * N]
+        # algorithmic bytes per (block,channel) row: transform reads 4N, writes mdct 2N + logfft 2N;
+        # psy reads mdct 2N + logfft 2N, writes mdct' + logmdct + logmask 6N; floor1_fit reads logmdct + logmask 4N;
+        # render writes ilogmask 2N; cqn reads mdct' 2N + ilogmask 2N, writes residue 2N
+        alg = [8 * N, 0, 10 * N, 4 * N, 2 * N, 6 * N]
         dom = int(np.argmax(kms))
         achieved = alg[dom] * ch * nb / (kms[dom] * 1e-3) / 1e9
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per
@@ -377,44 +422,18 @@ def run_ours(args):
         traffic = None
         try:
             summ = json.load(open(os.path.join(ROOT, "profiles", "summary.json")))
-            per_row = summ["kernels"][names[dom]]["dram_bytes_per_row"]
+            per_row = summ["kernels"][KERNELS[dom]]["dram_bytes_per_row"]
             traffic = per_row * ch * nb
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"bound": "hbm", "kernel": KERNELS[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel_ms": {k: float(v) for k, v in zip(names, kms)},
-                "phaseA_algorithmic_GBps": 10 * N * ch * nb / (kms.sum() * 1e-3) / 1e9}
+                "kernel_ms": {k: float(v) for k, v in zip(KERNELS, kms)},
+                "kernel_algorithmic_GBps": {k: (float(a * ch * nb / (v * 1e-3) / 1e9) if v > 0 else None)
+                                            for k, a, v in zip(KERNELS, alg, kms)},
+                "phaseA_only_blocks_per_s": float(nb / (kms[:3].sum() * 1e-3))}
 
-        # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside)
-        nb_e = min(nb, args.e2e_blocks)
-        hp = torch.empty((nb_e, ch, N), dtype=torch.float32).pin_memory()
-        hp.copy_(pcm[:nb_e].cpu())
-        outs = [torch.empty((nb_e, ch, n), dtype=torch.float32).pin_memory() for _ in range(3)]
-        hamp = torch.empty(nb_e, dtype=torch.float32).pin_memory()
-        hdesc = desc_np[:nb_e].copy()
-        hio = abi.PhaseAIO()
-        hio.pcm, hio.desc = hp.data_ptr(), hdesc.ctypes.data
-        hio.mdct, hio.logmdct, hio.logmask = (o.data_ptr() for o in outs)
-        hio.ampmax_out = hamp.data_ptr()
-        L = lib.load()
-
-        def e2e_step():
-            rc = L.vb200_analysis_phaseA(ctx.h, W_LONG, nb_e, C.byref(hio))
-            if rc:
-                raise RuntimeError("vb200_analysis_phaseA failed: %d" % rc)
-        for _ in range(2):
-            e2e_step()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        dt = time.perf_counter() - t0
-        e2e = {"value": nb_e * args.steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(hp.numel() * 4 + hdesc.nbytes),
-               "d2h_bytes_per_step": int(sum(o.numel() for o in outs) * 4 + hamp.numel() * 4),
-               "blocks_per_step": nb_e}
-
-        # ---- CPU baseline on a bounded sample of the same workload
+        # ---- CPU baseline on a bounded sample of the same workload (same chain, reference functions)
         cores = os.cpu_count() or 1
         nb_c = args.ref_blocks_per_core * cores
         pcm_c = pcm[:min(nb, nb_c)].cpu().numpy()
@@ -436,7 +455,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(nb, N, ch), "blocks_per_gpu": nb,
-                       "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (18 * N * ch * nb / 1e9),
+                       "l2": "inputs+intermediates+outputs per step (%.1f GB) exceed the 126 MB L2" % (30 * N * ch * nb / 1e9),
                        "sharding": "independent blocks per rank, no collective"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "extra": extra,
@@ -454,7 +473,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks", type=int, default=100000, help="stereo blocks per GPU per step")
-    ap.add_argument("--e2e-blocks", type=int, default=50000)
+    ap.add_argument("--e2e-blocks", type=int, default=50000, help="stereo blocks per GPU per e2e step")
+    ap.add_argument("--e2e-blocks-per-stream", type=int, default=50)
     ap.add_argument("--no-extra", action="store_true", help="skip the informational configs 2/4")
     ap.add_argument("--ref-blocks-per-core", type=int, default=512)
     args = ap.parse_args()

@@ -147,6 +147,9 @@ uint64_t vb200_launch_count(vb200_ctx *ctx);
  * vb200_phaseA_kernel_ms returns the durations of the last call (ms3[3]).       */
 int  vb200_set_profiling(vb200_ctx *ctx, int on);
 int  vb200_phaseA_kernel_ms(vb200_ctx *ctx, float *ms3);
+/* same for the last vb200_encode_dsp_dev call: transform, ampmax, psy, floor1_fit, floor1_render,
+ * couple_quantize_normalize (+ nonzero propagation)                                            */
+int  vb200_encode_dsp_kernel_ms(vb200_ctx *ctx, float *ms6);
 /* development aid: with env VB200_PHASE_TIMING set, the psy kernel adds the SM cycles each of
  * its 11 barrier-delimited phases took (thread 0 of every CTA) into a 16-slot counter array. */
 int  vb200_debug_phase_cycles(vb200_ctx *ctx, unsigned long long *out16, int reset);
@@ -257,6 +260,55 @@ int vb200_couple_quantize_normalize_dev(vb200_ctx*, int W, int blocktype, int bl
                                         const float *d_mdct, int32_t *d_iwork, int32_t *d_nonzero, void *stream);
 int vb200_couple_quantize_normalize    (vb200_ctx*, int W, int blocktype, int blobno, int nblocks,
                                         const float *mdct, int32_t *iwork, int32_t *nonzero);
+
+/* ---- the whole per-block encode DSP of mapping0_forward in ONE call ---------------------------
+ * lib/mapping0.c:230-646 with the bit packing and the residue backend left to the caller:
+ *   window, MDCT, FFT, log spectra, ampmax (:254-346)  ->  noise / tone masks, offset_and_mix(1)
+ *   (:366-470)  ->  floor1_fit (:500)  ->  the non-bit-packing part of floor1_encode (:617)
+ *   ->  _vp_couple_quantize_normalize (:631-646)
+ * for un-managed bitrate (only blob `blobno` = PACKETBLOBS/2 is produced, :592-594).  The float
+ * spectra never leave the device: per stereo long block 4 KB of int16 PCM go in and 8.4 KB come
+ * back (posts, nonzero, quantised residue) instead of 16 KB + 24.6 KB for Phase A alone.
+ *
+ * Blocks are `nstreams` x `blocks_per_stream`, block index = stream*blocks_per_stream + k.
+ *   pcm_fmt VB200_PCM_F32_BLOCKS      float [nblocks][ch][N]  (vb->pcm as blockout leaves it)
+ *           VB200_PCM_F32_PLANAR      float [stream][ch][stream_stride], block k starts at k*hop
+ *           VB200_PCM_S16_INTERLEAVED int16 [stream][stream_stride][ch], sample/32768.f
+ *   desc[nblocks]      lW, nW, blocktype of every block (psy look = blocktype + 2W, :250)
+ *   independent != 0   desc[].ampmax is each block's ampmax on entry (what one vorbis_analysis
+ *                      call sees); == 0: the decay chain of vorbis_analysis_blockout
+ *                      (lib/block.c:626-628) runs per stream from ampmax0[stream] (NULL = -9999)
+ * Outputs (what floor1_encode's bit packer and the residue backend consume):
+ *   posts   [nblocks][ch][VB200_FLOOR1_STRIDE]  post[] as floor1_encode leaves it (:765-832)
+ *   nonzero [nblocks][ch]                       after the coupling propagation (lib/psy.c:1203)
+ *   iwork   [nblocks][ch][n]                    quantised, coupled residue ints
+ *   ampmax_out [nblocks]                        vorbis_block_internal.ampmax on exit (:576)
+ *   mdct, logmdct, logmask [nblocks][ch][n]     optional (NULL = stay in device scratch)        */
+#define VB200_PCM_F32_BLOCKS       0
+typedef struct vb200_encode_io {
+  const void *pcm;
+  int32_t pcm_fmt;
+  int32_t hop;
+  int64_t stream_stride;
+  const vb200_block_desc *desc;
+  const float *ampmax0;
+  int32_t independent;
+  int32_t reserved;
+  int32_t *posts;
+  int32_t *nonzero;
+  int32_t *iwork;
+  float *ampmax_out;
+  float *mdct;
+  float *logmdct;
+  float *logmask;
+} vb200_encode_io;
+/* every pointer in *d_io is a device pointer; the struct itself is host memory */
+int vb200_encode_dsp_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream, int blobno,
+                         const vb200_encode_io *d_io, void *stream);
+/* host buffers (pinned memory makes the copies asynchronous); whole streams are cut into chunks
+ * that rotate over three lanes so H2D, the kernels and D2H of different chunks overlap         */
+int vb200_encode_dsp    (vb200_ctx*, int W, int nstreams, int blocks_per_stream, int blobno,
+                         const vb200_encode_io *io);
 
 /* ---- decode: mdct_backward (lib/mapping0.c:792-795) fused with the windowed
  *      overlap-add of vorbis_synthesis_blockin (lib/block.c:767-823).

@@ -193,6 +193,26 @@ class Oracle:
         self.L.vbo_floor1_render(self.h, W, floor_sel, posts.shape[0], posts, fz, ilog, nz)
         return posts, ilog, nz
 
+    def encode_dsp(self, W, pcm, desc, streams=None, ampmax0=None, blobno=7):
+        """The chain of mapping0_forward (lib/mapping0.c:230-646) composed from the stage oracles:
+        Phase A -> floor1_fit -> floor render -> couple/quantise/normalise with each block's own
+        psy look (blocktype).  pcm [nb][ch][N] block layout."""
+        ch, n = self.channels, self.bs[W] // 2
+        desc = np.ascontiguousarray(desc, abi.BLOCKDESC_DTYPE)
+        a = self.phaseA(W, pcm, desc, streams=streams, ampmax0=ampmax0)
+        nb = desc.shape[0]
+        posts, fz = self.floor1_fit(W, a["logmdct"], a["logmask"])
+        posts, ilog, nz = self.floor1_render(W, posts, fz)
+        iwork = ilog.reshape(nb, ch, n).copy()
+        nonzero = nz.reshape(nb, ch).copy()
+        for bt in (0, 1):
+            sel = np.where(desc["blocktype"] == bt)[0]
+            if len(sel):
+                iw, z = self.couple_quantize_normalize(W, bt, blobno, a["mdct"][sel], iwork[sel], nonzero[sel])
+                iwork[sel], nonzero[sel] = iw, z
+        a.update(posts=posts.reshape(nb, ch, -1), iwork=iwork, nonzero=nonzero)
+        return a
+
     def decouple(self, W, res):
         res = np.array(res, np.float32)
         self.L.vbo_decouple(self.h, W, res.shape[0], res)

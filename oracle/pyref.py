@@ -101,6 +101,7 @@ def lib():
         L.ref_blockin_sequence.restype = C.c_long
         L.ref_blockin_sequence.argtypes = [C.c_void_p, C.c_int, i32p, f32p, C.c_int, f32p, C.c_long]
         L.ref_phaseA_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, f32p, f32p, f32p, f32p]
+        L.ref_encode_dsp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, i32p, i32p, i32p, f32p]
         _lib = L
     return _lib
 
@@ -245,6 +246,19 @@ class Ref:
         amp = np.empty(nb, np.float32)
         self.L.ref_phaseA_batch(self.h, W, nb, pcm, desc.ctypes.data, mdct, logmdct, logmask, amp)
         return mdct, logmdct, logmask, amp
+
+    def encode_dsp_batch(self, W, pcm, desc):
+        """the reference's own functions in mapping0_forward's order: Phase A, floor1_fit, floor1_encode,
+        _vp_couple_quantize_normalize (blob PACKETBLOBS/2); independent blocks, desc[].ampmax on entry"""
+        ch, N = self.channels, self.bs[W]
+        pcm = np.ascontiguousarray(pcm, np.float32).reshape(-1, ch, N)
+        nb = pcm.shape[0]
+        desc = np.ascontiguousarray(desc, abi.BLOCKDESC_DTYPE)
+        out = {"posts": np.zeros((nb, ch, 65), np.int32), "nonzero": np.zeros((nb, ch), np.int32),
+               "iwork": np.zeros((nb, ch, N // 2), np.int32), "ampmax_out": np.zeros(nb, np.float32)}
+        self.L.ref_encode_dsp_batch(self.h, W, nb, pcm, desc.ctypes.data, out["posts"], out["nonzero"],
+                                    out["iwork"], out["ampmax_out"])
+        return out
 
     # ---- full API capture ----------------------------------------------------
     def _mkcap(self, maxblocks, fields):

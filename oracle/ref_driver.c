@@ -696,3 +696,54 @@ void ref_phaseA_batch(void *hv, int W, int nblocks, const float *pcm, const vb20
   }
   free(work); free(noise); free(tone); free(lmax);
 }
+
+/* ---- CPU baseline helper: the whole per-block DSP chain of mapping0_forward for un-managed
+ * bitrate (lib/mapping0.c:230-646): the Phase-A calls above, then floor1_fit (:500),
+ * floor1_encode (:617; its bits go to a scratch buffer) and _vp_couple_quantize_normalize
+ * (:631-646) for blob PACKETBLOBS/2, using only the reference's functions.  This is the same work
+ * vb200_encode_dsp does; used by bench.py's cpu_baseline / --impl reference leg.               */
+#include "misc.h"
+extern int *floor1_fit(vorbis_block *vb,vorbis_look_floor1 *look,const float *logmdct,const float *logmask);
+extern int floor1_encode(oggpack_buffer *opb,vorbis_block *vb,vorbis_look_floor1 *look,int *post,int *ilogmask);
+
+void ref_encode_dsp_batch(void *hv, int W, int nblocks, const float *pcm, const vb200_block_desc *desc,
+                          int32_t *posts_out, int32_t *nonzero_out, int32_t *iwork_out, float *ampmax_out){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_info_mapping0 *info = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[W]->mapping];
+  int ch = h->vi.channels, N = (int)ci->blocksizes[W], n = N/2, blk, i, k;
+  const int blob = PACKETBLOBS/2;
+  float *mdct = (float*)malloc(sizeof(float)*n*ch);
+  float *logmdct = (float*)malloc(sizeof(float)*n*ch);
+  float *logmask = (float*)malloc(sizeof(float)*n*ch);
+  float **m = (float**)malloc(sizeof(*m)*ch);
+  int   **iw = (int**)malloc(sizeof(*iw)*ch);
+  int    *nz = (int*)malloc(sizeof(int)*ch);
+  oggpack_buffer opb;
+  oggpack_writeinit(&opb);
+  h->vb.W = W;
+  h->vb.pcmend = N;               /* floor1_encode fills ilogmask up to vb->pcmend/2 (lib/floor1.c:941) */
+  for(blk=0;blk<nblocks;blk++){
+    vorbis_look_psy *p = b->psy+desc[blk].blocktype+(W?2:0);
+    ref_phaseA_batch(hv,W,1,pcm+(size_t)blk*ch*N,desc+blk,mdct,logmdct,logmask,ampmax_out+blk);
+    oggpack_reset(&opb);
+    for(i=0;i<ch;i++){
+      int submap = info->chmuxlist[i];
+      vorbis_look_floor1 *look = (vorbis_look_floor1*)b->flr[info->floorsubmap[submap]];
+      int32_t *po = posts_out+((size_t)blk*ch+i)*65;
+      int *post = floor1_fit(&h->vb,look,logmdct+(size_t)i*n,logmask+(size_t)i*n);
+      m[i] = mdct+(size_t)i*n;
+      iw[i] = (int*)(iwork_out+((size_t)blk*ch+i)*n);
+      nz[i] = floor1_encode(&opb,&h->vb,look,post,iw[i]);
+      for(k=0;k<65;k++) po[k]=0;
+      if(post) for(k=0;k<look->posts;k++) po[k]=post[k];
+    }
+    _vp_couple_quantize_normalize(blob,&ci->psy_g_param,p,info,m,iw,nz,
+                                  ci->psy_g_param.sliding_lowpass[W][blob],ch);
+    for(i=0;i<ch;i++) nonzero_out[(size_t)blk*ch+i]=nz[i];
+    _vorbis_block_ripcord(&h->vb);
+  }
+  oggpack_writeclear(&opb);
+  free(mdct); free(logmdct); free(logmask); free(m); free(iw); free(nz);
+}

@@ -506,3 +506,105 @@ def test_encode_chain_on_device_golden(cfg, tag):
         torch.cuda.synchronize()
         assert np.array_equal(iwork.cpu().numpy(), enc[tag + "_iwork_out"][sel]), "iwork"
         assert np.array_equal(nz.cpu().numpy().reshape(nb, ch), enc[tag + "_nonzero_out"][sel]), "nonzero"
+
+
+def _enc_compare(got, want, what):
+    for k in ("posts", "nonzero", "iwork"):
+        assert np.array_equal(got[k], want[k]), "%s: %s" % (what, k)
+    assert_bits_equal(got["ampmax_out"], want["ampmax_out"], what + ": ampmax_out")
+    for k in ("mdct", "logmdct", "logmask"):
+        if k in got:
+            assert_bits_equal(got[k], want[k], "%s: %s" % (what, k))
+
+
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_encode_dsp_one_call_golden(cfg, tag):
+    """vb200_encode_dsp (host buffers, one call for the whole chain of mapping0_forward) equals what
+    the reference's mapping0_forward produced: quantised residue, nonzero, and - through the oracle -
+    the floor posts; blocks of both blocktypes in ONE batch (per-block psy look)."""
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1 if tag == "L" else 0
+    nb = len(enc[tag + "_blocktype"])
+    if not nb:
+        pytest.skip("no such blocks in the fixture")
+    sel = np.arange(nb)
+    desc = make_desc(enc, tag, sel)
+    got = ctx.encode_dsp(W, enc[tag + "_pcm"], desc, floats=True)
+    assert np.array_equal(got["iwork"], enc[tag + "_iwork_out"]), "iwork vs reference"
+    assert np.array_equal(got["nonzero"], enc[tag + "_nonzero_out"]), "nonzero vs reference"
+    ep = enc[tag + "_enc_posts"].astype(np.int32).copy()
+    ep[enc[tag + "_fit_posts"][..., 0] == -1] = 0                       # NULL fit: the API returns a zero row
+    assert np.array_equal(got["posts"], ep), "posts vs reference (floor1_encode)"
+    assert_bits_equal(got["mdct"], enc[tag + "_mdct_m1"], "mdct vs reference")
+    assert_bits_equal(got["logmask"], enc[tag + "_logmask"], "logmask vs reference")
+    _enc_compare(got, o.encode_dsp(W, enc[tag + "_pcm"], desc), "golden " + tag)
+
+
+@pytest.mark.parametrize("fmt", ["blocks", "f32", "s16"])
+@pytest.mark.parametrize("W", [0, 1])
+def test_encode_dsp_streams_vs_oracle(cfg, W, fmt, monkeypatch):
+    """streams of consecutive blocks cut on the device from contiguous PCM (int16 interleaved or float
+    planar), ampmax chain per stream, mixed blocktypes, several pipeline chunks and a ragged last one"""
+    name, setup, ctx, o, _, _ = cfg
+    monkeypatch.setenv("VB200_CHUNK_BLOCKS", "12")
+    N, ch = setup.blocksize(W), setup.channels
+    hop, ns, bps = N // 2, 7, 5
+    stride = (bps - 1) * hop + N + 4
+    rng = np.random.default_rng(77 + W)
+    t = np.arange(stride)
+    s16 = np.clip(5000 * rng.standard_normal((ns, stride, ch)) * rng.uniform(0.02, 1.5, (ns, 1, 1)) +
+                  9000 * np.sin(2 * np.pi * 660.0 * t / setup.rate)[None, :, None], -32768, 32767).astype(np.int16)
+    s16[2] = 0                                                        # a silent stream: floor1_fit returns NULL
+    planar = np.ascontiguousarray((s16.astype(np.float32) / np.float32(32768.0)).transpose(0, 2, 1))
+    blocks = np.stack([planar[s, :, k * hop:k * hop + N] for s in range(ns) for k in range(bps)])
+    desc = np.zeros(ns * bps, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = W; desc["nW"] = W
+    desc["blocktype"] = rng.integers(0, 2, ns * bps)
+    amp0 = rng.uniform(-40, -3, ns).astype(np.float32)
+    want = o.encode_dsp(W, blocks, desc, streams=(ns, bps), ampmax0=amp0)
+    if fmt == "blocks":
+        got = ctx.encode_dsp(W, blocks, desc, nstreams=ns, ampmax0=amp0, independent=False, floats=True)
+    elif fmt == "f32":
+        got = ctx.encode_dsp(W, planar, desc, nstreams=ns, fmt=vlib.PCM_F32_PLANAR, hop=hop, ampmax0=amp0,
+                             independent=False, floats=True)
+    else:
+        got = ctx.encode_dsp(W, s16, desc, nstreams=ns, fmt=vlib.PCM_S16_INTERLEAVED, hop=hop, ampmax0=amp0,
+                             independent=False)
+    _enc_compare(got, want, "streams %s W=%d" % (fmt, W))
+    assert not got["nonzero"][2 * bps:3 * bps].any(), "silent stream must come back all-zero"
+
+
+def test_encode_dsp_device_pointers_and_errors(cfg):
+    import torch
+    name, setup, ctx, o, enc, _ = cfg
+    W = 1
+    N, ch = setup.blocksize(W), setup.channels
+    n = N // 2
+    nb = min(4, len(enc["L_blocktype"]))
+    desc = make_desc(enc, "L", np.arange(nb))
+    pcm = np.ascontiguousarray(enc["L_pcm"][:nb])
+    want = o.encode_dsp(W, pcm, desc)
+    dev = torch.device("cuda")
+    t = {"pcm": torch.from_numpy(pcm).to(dev),
+         "desc": torch.from_numpy(desc.view(np.uint8).reshape(-1, 16).copy()).to(dev),
+         "posts": torch.zeros((nb, ch, abi.FLOOR1_STRIDE), dtype=torch.int32, device=dev),
+         "nonzero": torch.zeros((nb, ch), dtype=torch.int32, device=dev),
+         "iwork": torch.zeros((nb, ch, n), dtype=torch.int32, device=dev),
+         "ampmax_out": torch.zeros(nb, device=dev)}
+    io = abi.EncodeIO()
+    for k, v in t.items():
+        setattr(io, k, v.data_ptr())
+    io.independent = 1
+    ctx.encode_dsp_dev(W, nb, 1, io, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = {k: t[k].cpu().numpy() for k in ("posts", "nonzero", "iwork", "ampmax_out")}
+    _enc_compare(got, want, "device pointers")
+    io.pcm_fmt = 9
+    with pytest.raises(vlib.VB200Error):
+        ctx.encode_dsp_dev(W, nb, 1, io)
+    io.pcm_fmt = vlib.PCM_S16_INTERLEAVED; io.hop = N // 2; io.stream_stride = N - 2
+    with pytest.raises(vlib.VB200Error):
+        ctx.encode_dsp_dev(W, nb, 1, io)
+    io.pcm_fmt = 0; io.posts = None
+    with pytest.raises(vlib.VB200Error):
+        ctx.encode_dsp_dev(W, nb, 1, io)

@@ -158,3 +158,21 @@ def test_floor1_golden(cfg, tag):
 def test_floor1_golden_has_null_fit():
     enc = load_npz("encode", "44k_mono_q4")
     assert (enc["L_fit_posts"][:, :, 0] == -1).any(), "fixture should hold a silent block (floor1_fit == NULL)"
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+@pytest.mark.parametrize("tag", ["L", "S"])
+def test_oracle_encode_chain_golden(name, tag, oracle_lib):
+    """the composed chain the one-call GPU entry point (vb200_encode_dsp) is checked against:
+    Phase A -> floor1_fit -> floor render -> couple/quantise/normalise with per-block psy look"""
+    setup = load_setup(name)
+    enc = load_npz("encode", name)
+    if not len(enc[tag + "_blocktype"]):
+        pytest.skip("no such blocks")
+    o = oracle_lib.Oracle(setup)
+    r = o.encode_dsp(1 if tag == "L" else 0, enc[tag + "_pcm"], make_desc(enc, tag))
+    assert np.array_equal(r["iwork"], enc[tag + "_iwork_out"])
+    assert np.array_equal(r["nonzero"], enc[tag + "_nonzero_out"])
+    ep = enc[tag + "_enc_posts"].astype(np.int32).copy()
+    ep[enc[tag + "_fit_posts"][..., 0] == -1] = 0                       # NULL fit: the API returns a zero row
+    assert np.array_equal(r["posts"], ep)

@@ -133,3 +133,34 @@ def test_floor1_vs_reference(args, oracle_lib):
         assert np.array_equal(nz2, cap["nonzero_in"][idx].reshape(-1))
     assert nulls > 0
     r.close()
+
+
+@pytest.mark.parametrize("args", [(2, 44100, 0.5), (2, 44100, 0.1), (1, 44100, 0.4), (6, 48000, 0.2)],
+                         ids=lambda g: "ch%d_%d_q%g" % g)
+def test_encode_chain_vs_reference(args, oracle_lib):
+    """the composed oracle chain (what vb200_encode_dsp is checked against) equals the reference's own
+    functions called in mapping0_forward's order (ref_encode_dsp_batch, also bench.py's CPU arm), on the
+    PCM blocks, block flags and ampmax the reference's own API loop handed to mapping0_forward"""
+    ch, rate, q = args
+    r = pyref.Ref(ch, rate, q)
+    o = oracle_lib.Oracle(r.setup())
+    pcm = probe_signal(ch, rate, 1.0, seed=9)
+    pcm[:, 5000:9000] = 0
+    cap = r.encode_capture(pcm)
+    for W in (0, 1):
+        idx = np.where(cap["W"] == W)[0]
+        if not len(idx):
+            continue
+        N = r.bs[W]
+        desc = np.zeros(len(idx), abi.BLOCKDESC_DTYPE)
+        for k in ("lW", "nW", "blocktype"):
+            desc[k] = cap[k][idx]
+        desc["ampmax"] = cap["ampmax_in"][idx]
+        blocks = np.ascontiguousarray(cap["pcm"][idx][:, :, :N])
+        a = o.encode_dsp(W, blocks, desc)
+        b = r.encode_dsp_batch(W, blocks, desc)
+        for k in ("posts", "nonzero", "iwork"):
+            assert np.array_equal(a[k], b[k]), k
+        assert_bits_equal(a["ampmax_out"], b["ampmax_out"], "ampmax_out")
+        assert np.array_equal(a["iwork"], cap["iwork_out"][idx][:, :, :N // 2]), "iwork vs the API loop's capture"
+    r.close()

@@ -118,6 +118,26 @@ class PhaseAIO(C.Structure):
         ("tap_mdct_raw", C.c_void_p),
     ]
 
+class EncodeIO(C.Structure):
+    """vb200_encode_io (include/vorbis_b200.h)"""
+    _fields_ = [
+        ("pcm", C.c_void_p),
+        ("pcm_fmt", C.c_int32),
+        ("hop", C.c_int32),
+        ("stream_stride", C.c_int64),
+        ("desc", C.c_void_p),
+        ("ampmax0", C.c_void_p),
+        ("independent", C.c_int32),
+        ("reserved", C.c_int32),
+        ("posts", C.c_void_p),
+        ("nonzero", C.c_void_p),
+        ("iwork", C.c_void_p),
+        ("ampmax_out", C.c_void_p),
+        ("mdct", C.c_void_p),
+        ("logmdct", C.c_void_p),
+        ("logmask", C.c_void_p),
+    ]
+
 
 _PSY_SCALARS = [
     "n", "blockflag", "ath_adjatt", "ath_maxatt", "tone_abs_limit", "noisemaxsupp",

@@ -63,6 +63,9 @@ struct vb200_ctx {
   DevBuf scratch[16];
   DevBuf lane_buf[2][10];            // per-lane device buffers of the pipelined host Phase-A path
   cudaStream_t s_lane[2] = {nullptr, nullptr};
+  DevBuf enc_buf[8];                 // scratch of vb200_encode_dsp_dev
+  DevBuf enc_lane[3][16];            // per-lane device buffers of the pipelined vb200_encode_dsp
+  cudaStream_t s_enc[3] = {nullptr, nullptr, nullptr};
   int psy_ctas_per_sm = 5;
   const float *d_fromdB = nullptr;
   const int *d_mag[2] = {nullptr, nullptr}, *d_ang[2] = {nullptr, nullptr};
@@ -72,7 +75,7 @@ struct vb200_ctx {
   std::mutex mu;
   // optional per-kernel timing of the last Phase-A call (bench roofline evidence)
   bool profiling = false;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 template <class T>
@@ -126,6 +129,7 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
   c->sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
   for (auto &st : c->s_lane) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto &st : c->s_enc) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
 
   for (int w = 0; w < 2; w++) {
     HostXform &h = c->hx[w];
@@ -263,6 +267,9 @@ extern "C" void vb200_ctx_destroy(vb200_ctx *c) {
   for (auto &b : c->scratch) if (b.p) cudaFree(b.p);
   for (auto &l : c->lane_buf) for (auto &b : l) if (b.p) cudaFree(b.p);
   for (auto &st : c->s_lane) if (st) cudaStreamDestroy(st);
+  for (auto &b : c->enc_buf) if (b.p) cudaFree(b.p);
+  for (auto &l : c->enc_lane) for (auto &b : l) if (b.p) cudaFree(b.p);
+  for (auto &st : c->s_enc) if (st) cudaStreamDestroy(st);
   if (c->s_main) cudaStreamDestroy(c->s_main);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   delete c;
@@ -311,6 +318,14 @@ extern "C" int vb200_phaseA_kernel_ms(vb200_ctx *c, float *ms3) {
   CU(cudaSetDevice(c->device));
   CU(cudaEventSynchronize(c->ev[3]));
   for (int i = 0; i < 3; i++) CU(cudaEventElapsedTime(ms3 + i, c->ev[i], c->ev[i + 1]));
+  return 0;
+}
+
+extern "C" int vb200_encode_dsp_kernel_ms(vb200_ctx *c, float *ms6) {
+  if (!c || !ms6 || !c->ev[0]) return fail(VB200_EINVAL, "profiling not enabled");
+  CU(cudaSetDevice(c->device));
+  CU(cudaEventSynchronize(c->ev[6]));
+  for (int i = 0; i < 6; i++) CU(cudaEventElapsedTime(ms6 + i, c->ev[i], c->ev[i + 1]));
   return 0;
 }
 
@@ -1223,7 +1238,7 @@ extern "C" int vb200_couple_quantize_normalize_dev(vb200_ctx *c, int W, int bloc
   if ((rc = set_smem(k_cqn, smem))) return rc;
   const long tasks = (long)nblocks * (Q.n / 32);
   const int grid = grid_for(c, (int)((tasks + wpb - 1) / wpb), 8);
-  k_cqn<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, nblocks, d_mdct, d_iwork, d_nonzero);
+  k_cqn<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, Q, nullptr, nblocks, d_mdct, d_iwork, d_nonzero);
   if ((rc = post_launch(c))) return rc;
   if (Q.steps > 0) {
     k_cqn_nonzero<<<(nblocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nblocks, Q.ch, Q.steps, Q.mag, Q.ang, d_nonzero);
@@ -1406,6 +1421,146 @@ extern "C" int vb200_floor1_render(vb200_ctx *c, int W, int floor_sel, int nrows
   if ((rc = io.d2h(ilogmask, di, sizeof(int32_t) * nrows * n))) return rc;
   if ((rc = io.d2h(nonzero, dn, sizeof(int32_t) * (size_t)nrows))) return rc;
   return io.sync();
+}
+
+// ======================================================================== //
+// the whole per-block encode DSP (Phase A -> floor1 fit -> floor render -> Phase B)
+static_assert(sizeof(vb200_encode_io) == 104, "vb200_encode_io layout (mirrored by vorbis_b200/abi.py)");
+struct EncScratch {
+  float *mdct, *logmdct, *logmask, *logfft, *lmax, *gmax;
+  int32_t *fitnz;
+};
+
+static size_t enc_pcm_bytes(const vb200_encode_io *io, int ch, int N, int nstreams, int bps) {
+  switch (io->pcm_fmt) {
+    case VB200_PCM_F32_BLOCKS: return sizeof(float) * (size_t)nstreams * bps * ch * N;
+    case VB200_PCM_F32_PLANAR: return sizeof(float) * (size_t)nstreams * ch * (size_t)io->stream_stride;
+    default: return sizeof(int16_t) * (size_t)nstreams * ch * (size_t)io->stream_stride;
+  }
+}
+
+static int enc_check(vb200_ctx *c, int W, int nstreams, int bps, int blobno, const vb200_encode_io *io) {
+  if (!io || !io->pcm || !io->desc || !io->posts || !io->nonzero || !io->iwork || !io->ampmax_out)
+    return fail(VB200_EINVAL, "encode io pointers");
+  if (nstreams <= 0 || bps <= 0) return fail(VB200_EINVAL, "nstreams/blocks_per_stream");
+  if (c->n_psy != 4) return fail(VB200_EIMPL, "context has no psy lookups");
+  if (blobno < 0 || blobno >= VB200_PACKETBLOBS) return fail(VB200_EINVAL, "blobno");
+  const int fmt = io->pcm_fmt;
+  if (fmt != VB200_PCM_F32_BLOCKS && fmt != VB200_PCM_F32_PLANAR && fmt != VB200_PCM_S16_INTERLEAVED)
+    return fail(VB200_EINVAL, "pcm format");
+  if (fmt != VB200_PCM_F32_BLOCKS) {
+    if (io->hop <= 0 || io->stream_stride <= 0) return fail(VB200_EINVAL, "hop/stream_stride");
+    if (fmt == VB200_PCM_F32_PLANAR && ((io->hop & 3) || (io->stream_stride & 3)))
+      return fail(VB200_EINVAL, "hop and stream_stride must be multiples of 4 for float PCM");
+    if ((int64_t)(bps - 1) * io->hop + c->dx[W].N > io->stream_stride)
+      return fail(VB200_EINVAL, "blocks exceed the stream buffer");
+  }
+  return 0;
+}
+
+// all pointers device; S holds the float intermediates
+static int encode_launch(vb200_ctx *c, int W, int nstreams, int bps, int blobno, const vb200_encode_io *d,
+                         const EncScratch &S, cudaStream_t st) {
+  const int ch = c->setup.channels, nblocks = nstreams * bps, rows = nblocks * ch;
+  vb200_phaseA_io a;
+  memset(&a, 0, sizeof(a));
+  a.desc = d->desc; a.mdct = S.mdct; a.logmdct = S.logmdct; a.logmask = S.logmask; a.ampmax_out = d->ampmax_out;
+  PcmSrc ps; const PcmSrc *pp = nullptr;
+  if (d->pcm_fmt == VB200_PCM_F32_BLOCKS) a.pcm = (const float *)d->pcm;
+  else { ps.base = d->pcm; ps.fmt = d->pcm_fmt; ps.bps = bps; ps.hop = d->hop; ps.stride = d->stream_stride; pp = &ps; }
+  int rc;
+  if ((rc = phaseA_launch(c, W, nblocks, &a, d->independent ? 0 : nstreams, bps, d->ampmax0, st,
+                          S.logfft, S.lmax, S.gmax, pp))) return rc;
+  if ((rc = vb200_floor1_fit_dev(c, W, -1, rows, S.logmdct, S.logmask, d->posts, S.fitnz, st))) return rc;
+  if (c->profiling) CU(cudaEventRecord(c->ev[4], st));
+  if ((rc = vb200_floor1_render_dev(c, W, -1, rows, d->posts, S.fitnz, d->iwork, d->nonzero, st))) return rc;
+  if (c->profiling) CU(cudaEventRecord(c->ev[5], st));
+  CqnDev Q0, Q1;
+  if ((rc = cqn_setup(c, W, 0, blobno, &Q0))) return rc;
+  if ((rc = cqn_setup(c, W, 1, blobno, &Q1))) return rc;
+  const int wpb = 4;
+  const size_t smem = (size_t)wpb * (CQN_COLS * Q0.ch * 32 * sizeof(float) + Q0.ch * sizeof(int));
+  if (smem > 200 * 1024) return fail(VB200_EIMPL, "too many channels for the coupling kernel");
+  if ((rc = set_smem(k_cqn, smem))) return rc;
+  const long tasks = (long)nblocks * (Q0.n / 32);
+  k_cqn<<<grid_for(c, (int)((tasks + wpb - 1) / wpb), 8), wpb * 32, smem, st>>>(Q0, Q1, d->desc, nblocks, S.mdct,
+                                                                            d->iwork, d->nonzero);
+  if ((rc = post_launch(c))) return rc;
+  if (Q0.steps > 0) {
+    k_cqn_nonzero<<<(nblocks + 127) / 128, 128, 0, st>>>(nblocks, Q0.ch, Q0.steps, Q0.mag, Q0.ang, d->nonzero);
+    if ((rc = post_launch(c))) return rc;
+  }
+  if (c->profiling) CU(cudaEventRecord(c->ev[6], st));
+  return 0;
+}
+
+static int enc_scratch(DevBuf *B, size_t rows, size_t nblocks, size_t n, const vb200_encode_io *d, EncScratch *S) {
+  void *p; int rc;
+  const size_t big = sizeof(float) * rows * n;
+  if (d && d->mdct) S->mdct = d->mdct; else { if ((rc = ensure_buf(B[0], big, &p))) return rc; S->mdct = (float *)p; }
+  if (d && d->logmdct) S->logmdct = d->logmdct; else { if ((rc = ensure_buf(B[1], big, &p))) return rc; S->logmdct = (float *)p; }
+  if (d && d->logmask) S->logmask = d->logmask; else { if ((rc = ensure_buf(B[2], big, &p))) return rc; S->logmask = (float *)p; }
+  if ((rc = ensure_buf(B[3], big, &p))) return rc; S->logfft = (float *)p;
+  if ((rc = ensure_buf(B[4], sizeof(float) * rows, &p))) return rc; S->lmax = (float *)p;
+  if ((rc = ensure_buf(B[5], sizeof(float) * nblocks, &p))) return rc; S->gmax = (float *)p;
+  if ((rc = ensure_buf(B[6], sizeof(int32_t) * rows, &p))) return rc; S->fitnz = (int32_t *)p;
+  return 0;
+}
+
+extern "C" int vb200_encode_dsp_dev(vb200_ctx *c, int W, int nstreams, int bps, int blobno,
+                                    const vb200_encode_io *d, void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  int rc;
+  if ((rc = enc_check(c, W, nstreams, bps, blobno, d))) return rc;
+  const size_t ch = c->setup.channels, n = c->dx[W].N / 2, nblocks = (size_t)nstreams * bps;
+  EncScratch S;
+  if ((rc = enc_scratch(c->enc_buf, nblocks * ch, nblocks, n, d, &S))) return rc;
+  return encode_launch(c, W, nstreams, bps, blobno, d, S, (cudaStream_t)stream);
+}
+
+extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int blobno, const vb200_encode_io *h) {
+  CHECK_CTX(c); CHECK_W(W);
+  int rc;
+  if ((rc = enc_check(c, W, nstreams, bps, blobno, h))) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int ch = c->setup.channels, N = c->dx[W].N, n = N / 2;
+  int chunk_blocks = 4096;
+  { const char *e = getenv("VB200_CHUNK_BLOCKS"); if (e && atoi(e) > 0) chunk_blocks = atoi(e); }
+  int cs = chunk_blocks / bps;                       // whole streams per chunk
+  if (cs < 1) cs = 1;
+  if (cs > nstreams) cs = nstreams;
+  const size_t pcm_per_stream = enc_pcm_bytes(h, ch, N, 1, bps);
+  for (int s0 = 0, it = 0; s0 < nstreams; s0 += cs, it++) {
+    const int L = it % 3, ns = nstreams - s0 < cs ? nstreams - s0 : cs;
+    const size_t nb = (size_t)ns * bps, b0 = (size_t)s0 * bps, rows = nb * ch, r0 = b0 * ch;
+    cudaStream_t st = c->s_enc[L];
+    DevBuf *B = c->enc_lane[L];
+    void *p;
+    vb200_encode_io d = *h;
+    d.mdct = d.logmdct = d.logmask = nullptr;
+    if ((rc = ensure_buf(B[8], pcm_per_stream * cs, &p))) return rc; d.pcm = p;
+    if ((rc = ensure_buf(B[9], sizeof(vb200_block_desc) * (size_t)cs * bps, &p))) return rc; d.desc = (const vb200_block_desc *)p;
+    if ((rc = ensure_buf(B[10], sizeof(float) * cs, &p))) return rc; d.ampmax0 = h->ampmax0 ? (const float *)p : nullptr;
+    if ((rc = ensure_buf(B[11], sizeof(int32_t) * (size_t)cs * bps * ch * VB200_FLOOR1_STRIDE, &p))) return rc; d.posts = (int32_t *)p;
+    if ((rc = ensure_buf(B[12], sizeof(int32_t) * (size_t)cs * bps * ch, &p))) return rc; d.nonzero = (int32_t *)p;
+    if ((rc = ensure_buf(B[13], sizeof(int32_t) * (size_t)cs * bps * ch * n, &p))) return rc; d.iwork = (int32_t *)p;
+    if ((rc = ensure_buf(B[14], sizeof(float) * (size_t)cs * bps, &p))) return rc; d.ampmax_out = (float *)p;
+    EncScratch S;
+    if ((rc = enc_scratch(B, (size_t)cs * bps * ch, (size_t)cs * bps, n, nullptr, &S))) return rc;
+    CU(cudaMemcpyAsync((void *)d.pcm, (const char *)h->pcm + pcm_per_stream * s0, pcm_per_stream * ns, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync((void *)d.desc, h->desc + b0, sizeof(vb200_block_desc) * nb, cudaMemcpyHostToDevice, st));
+    if (h->ampmax0) CU(cudaMemcpyAsync((void *)d.ampmax0, h->ampmax0 + s0, sizeof(float) * ns, cudaMemcpyHostToDevice, st));
+    if ((rc = encode_launch(c, W, ns, bps, blobno, &d, S, st))) return rc;
+    CU(cudaMemcpyAsync(h->posts + r0 * VB200_FLOOR1_STRIDE, d.posts, sizeof(int32_t) * rows * VB200_FLOOR1_STRIDE, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->nonzero + r0, d.nonzero, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->iwork + r0 * n, d.iwork, sizeof(int32_t) * rows * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->ampmax_out + b0, d.ampmax_out, sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
+    if (h->mdct) CU(cudaMemcpyAsync(h->mdct + r0 * n, S.mdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
+    if (h->logmdct) CU(cudaMemcpyAsync(h->logmdct + r0 * n, S.logmdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
+    if (h->logmask) CU(cudaMemcpyAsync(h->logmask + r0 * n, S.logmask, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
+  }
+  for (auto &st : c->s_enc) CU(cudaStreamSynchronize(st));
+  return 0;
 }
 
 // ======================================================================== //

@@ -90,11 +90,13 @@ __device__ __forceinline__ void cqn_normalize(const CqnDev &Q, float r, float &q
 // smem per warp: raw, quant, floor (float), flag and quantised value (int): CQN_COLS * ch * 32 words
 #define CQN_COLS 5
 __global__ void __launch_bounds__(128)
-k_cqn(CqnDev Q, int nblocks, const float *__restrict__ mdct, int *__restrict__ iwork,
-      const int *__restrict__ nonzero) {
+k_cqn(CqnDev Q0, CqnDev Q1, const vb200_block_desc *__restrict__ desc, int nblocks,
+      const float *__restrict__ mdct, int *__restrict__ iwork, const int *__restrict__ nonzero) {
+  // desc == NULL: every block uses Q0; else block b uses the psy look of its blocktype
+  // (b->psy + blocktype + (W?2:0), lib/mapping0.c:250), Q0 / Q1
   extern __shared__ __align__(16) float sm[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int n = Q.n, ch = Q.ch, width = Q.partition;
+  const int n = Q0.n, ch = Q0.ch;
   float *raw = sm + (size_t)wid * CQN_COLS * ch * 32;
   float *quant = raw + ch * 32, *flr = quant + ch * 32;
   int *flag = reinterpret_cast<int *>(flr + ch * 32);
@@ -104,6 +106,8 @@ k_cqn(CqnDev Q, int nblocks, const float *__restrict__ mdct, int *__restrict__ i
   const long tasks = (long)nblocks * chunks;
   for (long t = (long)blockIdx.x * wpb + wid; t < tasks; t += (long)gridDim.x * wpb) {
     const int blk = (int)(t / chunks), line = (int)(t % chunks) * 32 + lane;
+    const CqnDev &Q = (desc && desc[blk].blocktype) ? Q1 : Q0;
+    const int width = Q.partition;
     const int i = line & ~(width - 1), j = line - i;       // partition start, index inside it
     const float *m = mdct + (size_t)blk * ch * n;
     int *iw = iwork + (size_t)blk * ch * n;

@@ -20,6 +20,7 @@ PCM_S16_INTERLEAVED = 2
 EXPORTS = [
     "vb200_ctx_create", "vb200_ctx_destroy", "vb200_device_count", "vb200_last_error",
     "vb200_ctx_table", "vb200_launch_count", "vb200_set_profiling", "vb200_phaseA_kernel_ms", "vb200_debug_phase_cycles",
+    "vb200_encode_dsp_kernel_ms",
     "vb200_mdct_forward_dev", "vb200_mdct_forward", "vb200_mdct_backward_dev", "vb200_mdct_backward",
     "vb200_apply_window", "vb200_drft_forward",
     "vb200_noisemask", "vb200_tonemask", "vb200_offset_and_mix",
@@ -28,6 +29,7 @@ EXPORTS = [
     "vb200_couple_quantize_normalize_dev", "vb200_couple_quantize_normalize",
     "vb200_synthesis_dev", "vb200_synthesis", "vb200_decouple_dev", "vb200_decouple",
     "vb200_floor1_fit_dev", "vb200_floor1_fit", "vb200_floor1_render_dev", "vb200_floor1_render",
+    "vb200_encode_dsp_dev", "vb200_encode_dsp",
     "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
 ]
 
@@ -58,6 +60,7 @@ def load():
     L.vb200_launch_count.argtypes = [vp]
     L.vb200_set_profiling.argtypes = [vp, C.c_int]
     L.vb200_phaseA_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 3)]
+    L.vb200_encode_dsp_kernel_ms.argtypes = [vp, C.POINTER(C.c_float * 6)]
     L.vb200_debug_phase_cycles.argtypes = [vp, C.POINTER(C.c_ulonglong * 16), C.c_int]
     L.vb200_ctx_create.argtypes = [C.POINTER(abi.Setup), C.c_int, C.POINTER(vp)]
     L.vb200_ctx_destroy.argtypes = [vp]
@@ -87,6 +90,8 @@ def load():
     L.vb200_floor1_fit.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.vb200_floor1_render_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.vb200_floor1_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.vb200_encode_dsp_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO), vp]
+    L.vb200_encode_dsp.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO)]
     L.vb200_malloc_device.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.vb200_free_device.argtypes = [vp, vp]
     L.vb200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -142,6 +147,11 @@ class Context:
         ms = (C.c_float * 3)()
         self._chk(self.L.vb200_phaseA_kernel_ms(self.h, C.byref(ms)))
         return [float(x) for x in ms]
+
+    def encode_dsp_kernel_ms(self):
+        ms = (C.c_float * 6)()
+        self._chk(self.L.vb200_encode_dsp_kernel_ms(self.h, C.byref(ms)))
+        return list(ms)
 
     def debug_phase_cycles(self, reset=True):
         out = (C.c_ulonglong * 16)()
@@ -294,6 +304,53 @@ class Context:
     def floor1_render_dev(self, W, nrows, d_posts, d_fit_nonzero, d_ilogmask, d_nonzero, floor_sel=-1, stream=None):
         self._chk(self.L.vb200_floor1_render_dev(self.h, W, floor_sel, nrows, _ptr(d_posts), _ptr(d_fit_nonzero),
                                                  _ptr(d_ilogmask), _ptr(d_nonzero), _ptr(stream)))
+
+    # ---- whole per-block encode DSP (Phase A -> floor1 -> Phase B) in one call ---------------
+    def encode_dsp(self, W, pcm, desc, nstreams=None, fmt=0, hop=0, ampmax0=None, independent=None, blobno=7,
+                   floats=False):
+        """Host buffers.  fmt 0: pcm [nblocks][ch][N] float; PCM_F32_PLANAR: [streams][ch][stride] float;
+        PCM_S16_INTERLEAVED: [streams][stride][ch] int16.  nstreams None = every block its own stream.
+        independent None = True when the blocks are not grouped in streams."""
+        ch, N = self.channels, self.bs[W]
+        n = N // 2
+        desc = np.ascontiguousarray(desc, abi.BLOCKDESC_DTYPE)
+        nb = desc.shape[0]
+        if nstreams is None:
+            nstreams = nb
+            if independent is None:
+                independent = True
+        bps = nb // nstreams
+        assert bps * nstreams == nb
+        io = abi.EncodeIO()
+        if fmt == 0:
+            pcm = np.ascontiguousarray(pcm, np.float32).reshape(nb, ch, N)
+        elif fmt == PCM_F32_PLANAR:
+            pcm = np.ascontiguousarray(pcm, np.float32)
+            assert pcm.shape[:2] == (nstreams, ch)
+            io.stream_stride = pcm.shape[2]
+        else:
+            pcm = np.ascontiguousarray(pcm, np.int16)
+            assert pcm.shape[0] == nstreams and pcm.shape[2] == ch
+            io.stream_stride = pcm.shape[1]
+        io.pcm, io.pcm_fmt, io.hop = pcm.ctypes.data, fmt, hop
+        io.desc = desc.ctypes.data
+        io.independent = 1 if independent else 0
+        if ampmax0 is not None:
+            ampmax0 = np.ascontiguousarray(ampmax0, np.float32)
+            io.ampmax0 = ampmax0.ctypes.data
+        out = {"posts": np.zeros((nb, ch, abi.FLOOR1_STRIDE), np.int32), "nonzero": np.zeros((nb, ch), np.int32),
+               "iwork": np.zeros((nb, ch, n), np.int32), "ampmax_out": np.zeros(nb, np.float32)}
+        if floats:
+            for k in ("mdct", "logmdct", "logmask"):
+                out[k] = np.zeros((nb, ch, n), np.float32)
+        for k, v in out.items():
+            setattr(io, k, v.ctypes.data)
+        self._chk(self.L.vb200_encode_dsp(self.h, W, nstreams, bps, blobno, C.byref(io)))
+        return out
+
+    def encode_dsp_dev(self, W, nstreams, bps, io, blobno=7, stream=None):
+        """io: abi.EncodeIO holding DEVICE pointers."""
+        self._chk(self.L.vb200_encode_dsp_dev(self.h, W, nstreams, bps, blobno, C.byref(io), _ptr(stream)))
 
     # ---- decode ------------------------------------------------------------------
     def decouple(self, W, res):
