@@ -1225,6 +1225,32 @@ static int cqn_setup(vb200_ctx *c, int W, int blocktype, int blobno, CqnDev *Q) 
   return 0;
 }
 
+// one launcher for both entry points: desc == NULL -> every block uses Q0
+static int cqn_launch(vb200_ctx *c, const CqnDev &Q0, const CqnDev &Q1, const vb200_block_desc *d_desc, int nblocks,
+                      const float *d_mdct, int32_t *d_iwork, int32_t *d_nonzero, cudaStream_t st) {
+  int rc;
+  const int wpb = 4;
+  const long tasks = (long)nblocks * (Q0.n / 32);
+  const bool v1 = getenv("VB200_CQN_V1") && atoi(getenv("VB200_CQN_V1"));
+  if (!v1 && (Q0.ch == 1 || (Q0.ch == 2 && Q0.steps <= 1))) {
+    const int grid = grid_for(c, (int)((tasks + wpb - 1) / wpb), 16);
+    if (Q0.ch == 1) k_cqn_fast<1><<<grid, wpb * 32, 0, st>>>(Q0, Q1, d_desc, nblocks, d_mdct, d_iwork, d_nonzero);
+    else k_cqn_fast<2><<<grid, wpb * 32, 0, st>>>(Q0, Q1, d_desc, nblocks, d_mdct, d_iwork, d_nonzero);
+  } else {
+    const size_t smem = (size_t)wpb * (CQN_COLS * Q0.ch * 32 * sizeof(float) + Q0.ch * sizeof(int));
+    if (smem > 200 * 1024) return fail(VB200_EIMPL, "too many channels for the coupling kernel");
+    if ((rc = set_smem(k_cqn, smem))) return rc;
+    k_cqn<<<grid_for(c, (int)((tasks + wpb - 1) / wpb), 8), wpb * 32, smem, st>>>(Q0, Q1, d_desc, nblocks, d_mdct,
+                                                                              d_iwork, d_nonzero);
+  }
+  if ((rc = post_launch(c))) return rc;
+  if (Q0.steps > 0) {
+    k_cqn_nonzero<<<(nblocks + 127) / 128, 128, 0, st>>>(nblocks, Q0.ch, Q0.steps, Q0.mag, Q0.ang, d_nonzero);
+    if ((rc = post_launch(c))) return rc;
+  }
+  return 0;
+}
+
 extern "C" int vb200_couple_quantize_normalize_dev(vb200_ctx *c, int W, int blocktype, int blobno, int nblocks,
                                                    const float *d_mdct, int32_t *d_iwork, int32_t *d_nonzero,
                                                    void *stream) {
@@ -1232,19 +1258,7 @@ extern "C" int vb200_couple_quantize_normalize_dev(vb200_ctx *c, int W, int bloc
   if (nblocks <= 0) return 0;
   CqnDev Q; int rc;
   if ((rc = cqn_setup(c, W, blocktype, blobno, &Q))) return rc;
-  const int wpb = 4;
-  const size_t smem = (size_t)wpb * (CQN_COLS * Q.ch * 32 * sizeof(float) + Q.ch * sizeof(int));
-  if (smem > 200 * 1024) return fail(VB200_EIMPL, "too many channels for the coupling kernel");
-  if ((rc = set_smem(k_cqn, smem))) return rc;
-  const long tasks = (long)nblocks * (Q.n / 32);
-  const int grid = grid_for(c, (int)((tasks + wpb - 1) / wpb), 8);
-  k_cqn<<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(Q, Q, nullptr, nblocks, d_mdct, d_iwork, d_nonzero);
-  if ((rc = post_launch(c))) return rc;
-  if (Q.steps > 0) {
-    k_cqn_nonzero<<<(nblocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(nblocks, Q.ch, Q.steps, Q.mag, Q.ang, d_nonzero);
-    if ((rc = post_launch(c))) return rc;
-  }
-  return 0;
+  return cqn_launch(c, Q, Q, nullptr, nblocks, d_mdct, d_iwork, d_nonzero, (cudaStream_t)stream);
 }
 
 extern "C" int vb200_couple_quantize_normalize(vb200_ctx *c, int W, int blocktype, int blobno, int nblocks,
@@ -1478,18 +1492,7 @@ static int encode_launch(vb200_ctx *c, int W, int nstreams, int bps, int blobno,
   CqnDev Q0, Q1;
   if ((rc = cqn_setup(c, W, 0, blobno, &Q0))) return rc;
   if ((rc = cqn_setup(c, W, 1, blobno, &Q1))) return rc;
-  const int wpb = 4;
-  const size_t smem = (size_t)wpb * (CQN_COLS * Q0.ch * 32 * sizeof(float) + Q0.ch * sizeof(int));
-  if (smem > 200 * 1024) return fail(VB200_EIMPL, "too many channels for the coupling kernel");
-  if ((rc = set_smem(k_cqn, smem))) return rc;
-  const long tasks = (long)nblocks * (Q0.n / 32);
-  k_cqn<<<grid_for(c, (int)((tasks + wpb - 1) / wpb), 8), wpb * 32, smem, st>>>(Q0, Q1, d->desc, nblocks, S.mdct,
-                                                                            d->iwork, d->nonzero);
-  if ((rc = post_launch(c))) return rc;
-  if (Q0.steps > 0) {
-    k_cqn_nonzero<<<(nblocks + 127) / 128, 128, 0, st>>>(nblocks, Q0.ch, Q0.steps, Q0.mag, Q0.ang, d->nonzero);
-    if ((rc = post_launch(c))) return rc;
-  }
+  if ((rc = cqn_launch(c, Q0, Q1, d->desc, nblocks, S.mdct, d->iwork, d->nonzero, st))) return rc;
   if (c->profiling) CU(cudaEventRecord(c->ev[6], st));
   return 0;
 }

@@ -87,6 +87,120 @@ __device__ __forceinline__ void cqn_normalize(const CqnDev &Q, float r, float &q
   }
 }
 
+// field-wise select: a reference to one of two kernel-parameter structs would force both into
+// local memory (dynamic indexing of the parameter space)
+__device__ __forceinline__ CqnDev cqn_pick(const CqnDev &a, const CqnDev &b, bool second) {
+  CqnDev q;
+  q.n = a.n; q.ch = a.ch; q.steps = a.steps; q.mag = a.mag; q.ang = a.ang; q.fromdB = a.fromdB;
+  q.partition = second ? b.partition : a.partition;
+  q.limit = second ? b.limit : a.limit;
+  q.sliding_lowpass = second ? b.sliding_lowpass : a.sliding_lowpass;
+  q.normal_p = second ? b.normal_p : a.normal_p;
+  q.normal_start = second ? b.normal_start : a.normal_start;
+  q.prepoint = second ? b.prepoint : a.prepoint;
+  q.postpoint = second ? b.postpoint : a.postpoint;
+  q.normal_thresh = second ? b.normal_thresh : a.normal_thresh;
+  return q;
+}
+
+// ---- register-resident version for 1 channel, or 2 channels with at most one coupling step
+// (every stereo / mono setup of vorbisenc).  Lane = line as in k_cqn, but nothing goes through
+// shared memory except the 256-entry floor table, and the next task's four loads are in flight
+// while the current one is computed (the kernel is latency bound: two dependent global loads,
+// two IEEE divisions and an fp64 sqrt per channel on the critical path).
+template <int CH>
+__global__ void __launch_bounds__(128)
+k_cqn_fast(CqnDev Q0, CqnDev Q1, const vb200_block_desc *__restrict__ desc, int nblocks,
+           const float *__restrict__ mdct, int *__restrict__ iwork, const int *__restrict__ nonzero) {
+  __shared__ float s_fromdB[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_fromdB[i] = __ldg(Q0.fromdB + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int n = Q0.n, chunks = n >> 5;
+  const long tasks = (long)nblocks * chunks, stride = (long)gridDim.x * wpb;
+  const bool coupled = CH == 2 && Q0.steps > 0;
+  // slot 0 = magnitude channel, slot 1 = angle channel (channels are independent up to the coupling)
+  const int c0 = coupled ? __ldg(Q0.mag) : 0, c1 = coupled ? __ldg(Q0.ang) : 1;
+  float mv[CH], nmv[CH];
+  int il[CH], nil[CH], nzr[CH], nnz[CH];
+  auto fetch = [&](long t, float (&m_)[CH], int (&i_)[CH], int (&z_)[CH]) {
+    const int blk = (int)(t / chunks), line = (int)(t % chunks) * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      const int c = k == 0 ? c0 : c1;
+      const size_t row = (size_t)blk * CH + c;
+      z_[k] = __ldg(nonzero + row);
+      m_[k] = __ldcs(mdct + row * n + line);
+      i_[k] = __ldcs(iwork + row * n + line);
+    }
+  };
+  long t = (long)blockIdx.x * wpb + wid;
+  if (t < tasks) fetch(t, nmv, nil, nnz);
+  for (; t < tasks; t += stride) {
+#pragma unroll
+    for (int k = 0; k < CH; k++) { mv[k] = nmv[k]; il[k] = nil[k]; nzr[k] = nnz[k]; }
+    if (t + stride < tasks) fetch(t + stride, nmv, nil, nnz);
+    const int blk = (int)(t / chunks), line = (int)(t % chunks) * 32 + lane;
+    const CqnDev Q = cqn_pick(Q0, Q1, desc && desc[blk].blocktype);
+    const int width = Q.partition;
+    const int i = line & ~(width - 1), j = line - i;
+    float R[CH], Qe[CH], F[CH];
+    int G[CH], out[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      R[k] = 0.f; Qe[k] = 0.f; F[k] = 1e-10f; G[k] = 0; out[k] = 0;
+      if (nzr[k]) {
+        const float fl = s_fromdB[il[k] & 255];
+        const float point = j >= Q.limit - i ? Q.postpoint : Q.prepoint;      // flag_lossless
+        G[k] = (fabsf(mv[k]) / fl < point) ? 0 : 1;
+        Qe[k] = R[k] = mv[k] * mv[k];
+        if (mv[k] < 0.f) R[k] *= -1.f;
+        F[k] = fl * fl;
+        cqn_normalize(Q, R[k], Qe[k], F[k], false, 0, i, j, out[k], width, lane);
+      }
+    }
+    if (CH == 2 && coupled && (nzr[0] || nzr[1])) {
+      float reM = R[0], reA = R[1], qeM = Qe[0], qeA = Qe[1];
+      int gM = G[0], gA = G[1], iM = out[0], iA = out[1];
+      if (j < Q.sliding_lowpass - i) {
+        if (gM || gA) {                                    // lossless: integer square-polar map
+          const int A = iM, B = iA;
+          reM = fabsf(reM) + fabsf(reA);
+          qeM = qeM + qeA;
+          gM = gA = 1;
+          if (abs(A) > abs(B)) {
+            iA = (A > 0 ? A - B : B - A);
+          } else {
+            iA = (B > 0 ? A - B : B - A);
+            iM = B;
+          }
+          if (iA >= abs(iM) * 2) { iA = -iA; iM = -iM; }
+        } else {                                           // point stereo
+          if (j < Q.limit - i) {
+            reM += reA;
+            qeM = fabsf(reM);
+          } else {
+            const float e = fabsf(reM) + fabsf(reA);
+            qeM = e;
+            reM = (reM + reA < 0.f) ? -e : e;
+          }
+          reA = qeA = 0.f;
+          gA = 1;
+          iA = 0;
+        }
+      }
+      const float fM = F[0] + F[1];
+      cqn_normalize(Q, reM, qeM, fM, true, gM, i, j, iM, width, lane);
+      out[0] = iM; out[1] = iA;
+    }
+    {
+      int *iw = iwork + (size_t)blk * CH * n + line;
+      __stcs(iw + (size_t)c0 * n, out[0]);
+      if (CH == 2) __stcs(iw + (size_t)c1 * n, out[CH - 1]);
+    }
+  }
+}
+
 // smem per warp: raw, quant, floor (float), flag and quantised value (int): CQN_COLS * ch * 32 words
 #define CQN_COLS 5
 __global__ void __launch_bounds__(128)
@@ -106,7 +220,7 @@ k_cqn(CqnDev Q0, CqnDev Q1, const vb200_block_desc *__restrict__ desc, int nbloc
   const long tasks = (long)nblocks * chunks;
   for (long t = (long)blockIdx.x * wpb + wid; t < tasks; t += (long)gridDim.x * wpb) {
     const int blk = (int)(t / chunks), line = (int)(t % chunks) * 32 + lane;
-    const CqnDev &Q = (desc && desc[blk].blocktype) ? Q1 : Q0;
+    const CqnDev Q = cqn_pick(Q0, Q1, desc && desc[blk].blocktype);
     const int width = Q.partition;
     const int i = line & ~(width - 1), j = line - i;       // partition start, index inside it
     const float *m = mdct + (size_t)blk * ch * n;

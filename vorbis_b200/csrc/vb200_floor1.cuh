@@ -2,8 +2,9 @@
 //
 // k_floor1_fit     floor1_fit            lib/floor1.c:576-729
 //                    accumulate_fit      :406-454   per-gap integer sums, all lanes per gap + redux
-//                    fit_line            :456-521   fp64 chains, one lane per chain (12 lanes for the
-//                                                   two fits of a split), summed in accumulator order
+//                    fit_line            :456-521   fp64 chains over per-gap terms computed once per row,
+//                                                   one lane per chain (12 lanes for the two fits of a
+//                                                   split, one fit per half-warp), summed in gap order
 //                    inspect_error       :523-566   lanes over x; the Bresenham line in closed form
 //                    greedy splitting    :627-700   warp-uniform control flow, state in shared memory
 // k_floor1_render  floor1_encode minus the bit packing  :765-832 (quantise, predict/flag), :919-945
@@ -56,6 +57,7 @@ __device__ __forceinline__ int f1_point(int x0, int x1, int y0, int y1, int x) {
 // floor(k*ady/adx) times, each wrap adding (sy - base)
 struct F1Line {
   int x0, y0, adx, base, ady, step;
+  float rcp;
   __device__ __forceinline__ F1Line(int x0_, int x1, int y0_, int y1) {
     x0 = x0_; y0 = y0_;
     const int dy = y1 - y0;
@@ -63,10 +65,17 @@ struct F1Line {
     base = dy / adx;
     step = dy < 0 ? -1 : 1;
     ady = abs(dy) - abs(base * adx);
+    rcp = 1.f / (float)adx;
   }
+  // floor(k*ady/adx) without the integer-division sequence: k*ady < 2^22 is exact in fp32, the
+  // estimate is off by at most one, and the remainder test makes it exact
   __device__ __forceinline__ int at(int x) const {
-    const int k = x - x0;
-    return y0 + k * base + ((k * ady) / adx) * step;
+    const int k = x - x0, num = k * ady;
+    int q = __float2int_rz((float)num * rcp);
+    const int r = num - q * adx;
+    if (r < 0) q--;
+    else if (r >= adx) q++;
+    return y0 + k * base + q * step;
   }
 };
 
@@ -101,45 +110,43 @@ __device__ __forceinline__ int f1_inspect(const Floor1Dev &F, const unsigned sho
   return 0;
 }
 
-// fit_line for up to two runs of accumulators at once.  Lane 6*s + f sums chain f of side s in
-// accumulator order (the order the reference adds in); every lane then finishes both fits.
-// y[2*s], y[2*s+1] receive the fitted ends, return bit s = fit s was degenerate (reference ret 1).
-// The reference's "*y0 >= 0" endpoint terms never fire on this path (every call passes -200).
-__device__ __forceinline__ int f1_fit_lines(const Floor1Dev &F, const int *acc, int start0, int cnt0,
+// fit_line (lib/floor1.c:456-521) for up to two runs of gaps at once.  term[gap*6 + f] holds what
+// the reference adds to chain f (xb yb x2b y2b xyb bn) for that gap, a[i].Xb + a[i].Xa * weight, in
+// fp64 exactly as the C expression evaluates; it does not depend on the run, so it is computed once
+// per row.  Lane 16*s + f sums chain f of side s in gap order (the order the reference adds in),
+// then the lanes of a side finish that side's fit.  y[2*s], y[2*s+1] receive the fitted ends,
+// return bit s = fit s was degenerate (reference ret 1).  The reference's "*y0 >= 0" endpoint terms
+// never fire on this path (every call passes -200).
+__device__ __forceinline__ int f1_fit_lines(const Floor1Dev &F, const double *term, int start0, int cnt0,
                                             int start1, int cnt1, int lane, int y[4]) {
-  const int side = lane >= 6 ? 1 : 0, f = lane - 6 * side;
+  const unsigned full = 0xffffffffu;
+  const int side = lane >> 4, f = lane & 15;
   const int start = side ? start1 : start0;
-  const int cnt = lane < 12 ? (side ? cnt1 : cnt0) : 0;
+  const int ct = side ? cnt1 : cnt0;
   double sum = 0.0;
-  for (int t = 0; t < cnt; t++) {
-    const int *a = acc + (start + t) * F1_ACC;
-    const int an = a[5], bn = a[11];
-    const double w = (double)((float)(bn + an) * F.twofitweight / (float)(an + 1)) + 1.0;
-    sum += (double)a[6 + f] + (double)a[f] * w;
+  if (f < 6) {
+    const double *tp = term + start * 6 + f;
+    for (int t = 0; t < ct; t++) sum += tp[t * 6];
   }
-  int ret = 0;
-#pragma unroll
-  for (int s = 0; s < 2; s++) {
-    const double xb = __shfl_sync(0xffffffffu, sum, 6 * s + 0), yb = __shfl_sync(0xffffffffu, sum, 6 * s + 1);
-    const double x2b = __shfl_sync(0xffffffffu, sum, 6 * s + 2);
-    const double xyb = __shfl_sync(0xffffffffu, sum, 6 * s + 4), bn = __shfl_sync(0xffffffffu, sum, 6 * s + 5);
-    const int st = s ? start1 : start0, ct = s ? cnt1 : cnt0;
-    const int x0 = F.sorted[st], x1 = F.sorted[st + ct];
-    const double denom = bn * x2b - xb * xb;
-    int a0 = 0, a1 = 0;
-    if (ct > 0 && denom > 0.) {
-      const double A = (yb * x2b - xyb * xb) / denom;
-      const double B = (bn * xyb - xb * yb) / denom;
-      a0 = (int)rint(A + B * (double)x0);
-      a1 = (int)rint(A + B * (double)x1);
-      a0 = a0 > 1023 ? 1023 : (a0 < 0 ? 0 : a0);
-      a1 = a1 > 1023 ? 1023 : (a1 < 0 ? 0 : a1);
-    } else {
-      ret |= 1 << s;
-    }
-    y[2 * s] = a0; y[2 * s + 1] = a1;
+  const int sb = lane & 16;
+  const double xb = __shfl_sync(full, sum, sb + 0), yb = __shfl_sync(full, sum, sb + 1);
+  const double x2b = __shfl_sync(full, sum, sb + 2);
+  const double xyb = __shfl_sync(full, sum, sb + 4), bn = __shfl_sync(full, sum, sb + 5);
+  const int x0 = F.sorted[start], x1 = F.sorted[start + ct];
+  const double denom = bn * x2b - xb * xb;
+  int a0 = 0, a1 = 0, bad = 1;
+  if (ct > 0 && denom > 0.) {
+    const double A = (yb * x2b - xyb * xb) / denom;
+    const double B = (bn * xyb - xb * yb) / denom;
+    a0 = (int)rint(A + B * (double)x0);
+    a1 = (int)rint(A + B * (double)x1);
+    a0 = a0 > 1023 ? 1023 : (a0 < 0 ? 0 : a0);
+    a1 = a1 > 1023 ? 1023 : (a1 < 0 ? 0 : a1);
+    bad = 0;
   }
-  return ret;
+  y[0] = __shfl_sync(full, a0, 0); y[1] = __shfl_sync(full, a1, 0);
+  y[2] = __shfl_sync(full, a0, 16); y[3] = __shfl_sync(full, a1, 16);
+  return __shfl_sync(full, bad, 0) | (__shfl_sync(full, bad, 16) << 1);
 }
 
 __global__ void __launch_bounds__(32 * F1_WARPS)
@@ -156,8 +163,8 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char *wbase = f1_smem + sizeof(Floor1Dev) * VB200_MAX_SUBMAPS + floor1_fit_smem_per_warp(a.n) * warp;
-  int *acc = reinterpret_cast<int *>(wbase);
-  int *A = acc + (VB200_VIF_POSIT + 1) * F1_ACC;
+  double *term = reinterpret_cast<double *>(wbase);          // [gaps][6], same bytes as 12 ints per gap
+  int *A = reinterpret_cast<int *>(wbase) + (VB200_VIF_POSIT + 1) * F1_ACC;
   int *B = A + (VB200_VIF_POSIT + 2), *lon = B + (VB200_VIF_POSIT + 2), *hin = lon + (VB200_VIF_POSIT + 2);
   int *memo = hin + (VB200_VIF_POSIT + 2), *out = memo + (VB200_VIF_POSIT + 2);
   unsigned short *q = reinterpret_cast<unsigned short *>(out + (VB200_VIF_POSIT + 2));
@@ -194,11 +201,13 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
       }
 #pragma unroll
       for (int k = 0; k < F1_ACC; k++) s[k] = __reduce_add_sync(0xffffffffu, s[k]);
-      if (lane < F1_ACC) {
-        int v = s[0];
+      if (lane < 6) {                                    // what fit_line adds for this gap, chain = lane
+        int va = s[0], vb = s[6];
 #pragma unroll
-        for (int k = 1; k < F1_ACC; k++) if (lane == k) v = s[k];
-        acc[j * F1_ACC + lane] = v;
+        for (int k = 1; k < 6; k++) if (lane == k) { va = s[k]; vb = s[6 + k]; }
+        const int an = s[5], bn = s[11];
+        const double w = (double)((float)(bn + an) * F.twofitweight / (float)(an + 1)) + 1.0;
+        term[j * 6 + lane] = (double)vb + (double)va * w;
       }
       nonzero += s[5];
     }
@@ -209,7 +218,7 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
       continue;
     }
     int y[4];
-    f1_fit_lines(F, acc, 0, P - 1, 0, 0, lane, y);
+    f1_fit_lines(F, term, 0, P - 1, 0, 0, lane, y);
     if (lane == 0) { A[0] = y[0]; B[0] = y[0]; A[1] = y[1]; B[1] = y[1]; }
     __syncwarp();
     for (int i = 2; i < P; i++) {
@@ -222,7 +231,7 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
       __syncwarp();
       if (lane == 0) memo[ln] = hn;
       if (f1_inspect(F, q, lx, hx, ly, hy, lane)) {
-        const int ret = f1_fit_lines(F, acc, lsortpos, sortpos - lsortpos, sortpos, hsortpos - sortpos, lane, y);
+        const int ret = f1_fit_lines(F, term, lsortpos, sortpos - lsortpos, sortpos, hsortpos - sortpos, lane, y);
         int ly0 = y[0], ly1 = y[1], hy0 = y[2], hy1 = y[3];
         if (ret & 1) { ly0 = ly; ly1 = hy0; }
         if (ret & 2) { hy0 = ly1; hy1 = hy; }
