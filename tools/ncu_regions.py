@@ -23,7 +23,7 @@ for l in dis[start + 1:]:
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*)", l)
     if m:
         off2[int(m.group(1), 16)] = cur
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kname], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split("\n")))
 hdr = None
 data = []

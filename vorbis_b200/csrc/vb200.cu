@@ -246,6 +246,7 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
           if (x < hx && x > cur) { hi = j; hx = x; }
         }
         d.lo[i] = (short)lo; d.hi[i] = (short)hi;
+        d.prcp[i] = 1.f / (float)(hx - lx);             // render_point's divisor for post i+2 is static
       }
     }
     for (int k = 0; k < s->channels; k++) {
@@ -1232,7 +1233,7 @@ static int cqn_launch(vb200_ctx *c, const CqnDev &Q0, const CqnDev &Q1, const vb
   const int wpb = 4;
   const long tasks = (long)nblocks * (Q0.n / 32);
   const bool v1 = getenv("VB200_CQN_V1") && atoi(getenv("VB200_CQN_V1"));
-  if (!v1 && (Q0.ch == 1 || (Q0.ch == 2 && Q0.steps <= 1))) {
+  if (!v1 && tasks < (1L << 30) && (Q0.n & (Q0.n - 1)) == 0 && (Q0.ch == 1 || (Q0.ch == 2 && Q0.steps <= 1))) {
     const int grid = grid_for(c, (int)((tasks + wpb - 1) / wpb), 16);
     if (Q0.ch == 1) k_cqn_fast<1><<<grid, wpb * 32, 0, st>>>(Q0, Q1, d_desc, nblocks, d_mdct, d_iwork, d_nonzero);
     else k_cqn_fast<2><<<grid, wpb * 32, 0, st>>>(Q0, Q1, d_desc, nblocks, d_mdct, d_iwork, d_nonzero);

@@ -23,9 +23,22 @@ struct CqnDev {
   const float *fromdB;         // [256] floor1_inverse_dB_table
 };
 
-__device__ __forceinline__ int cqn_quant(float sign_src, float ve) {   // lib/psy.c:959-963
-  const double q = rint(sqrt((double)ve));
-  return sign_src < 0.f ? (int)-q : (int)q;
+// lib/psy.c:959-963: rint(sqrt(ve)) in double, then the sign.  For ve < 2^22 the result is computed
+// without the fp64 square root: q0 = trunc(sqrtf(ve)) is floor(sqrt(ve)) or one more (only when ve is
+// within an fp32 rounding of q0^2, where q0 is still the nearest integer), and the nearest integer
+// is q0+1 exactly when ve > (q0+.5)^2 = q0^2+q0+.25, a comparison that is exact in fp64.  The
+// correctly rounded double sqrt can only land on a tie k+.5 when ve == (k+.5)^2 exactly (ve has
+// 24 significant bits), where rint rounds to even.
+__device__ __forceinline__ int cqn_quant(float sign_src, float ve) {
+  int q;
+  if (ve < 4194304.f) {
+    const int q0 = (int)sqrtf(ve);
+    const double h = (double)(q0 * q0 + q0) + .25, vd = (double)ve;
+    q = q0 + ((vd > h || (vd == h && (q0 & 1))) ? 1 : 0);
+  } else {
+    q = (int)rint(sqrt((double)ve));
+  }
+  return sign_src < 0.f ? -q : q;
 }
 
 // noise_normalize for the lane's line.  use_flags=false <=> flags==NULL in the reference.
@@ -116,15 +129,15 @@ k_cqn_fast(CqnDev Q0, CqnDev Q1, const vb200_block_desc *__restrict__ desc, int 
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_fromdB[i] = __ldg(Q0.fromdB + i);
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const int n = Q0.n, chunks = n >> 5;
-  const long tasks = (long)nblocks * chunks, stride = (long)gridDim.x * wpb;
+  const int n = Q0.n, csh = 31 - __clz(n >> 5);          // n is a power of two: chunks = 1 << csh
+  const int tasks = nblocks << csh, stride = gridDim.x * wpb;   // the launcher keeps tasks < 2^31
   const bool coupled = CH == 2 && Q0.steps > 0;
   // slot 0 = magnitude channel, slot 1 = angle channel (channels are independent up to the coupling)
   const int c0 = coupled ? __ldg(Q0.mag) : 0, c1 = coupled ? __ldg(Q0.ang) : 1;
   float mv[CH], nmv[CH];
   int il[CH], nil[CH], nzr[CH], nnz[CH];
-  auto fetch = [&](long t, float (&m_)[CH], int (&i_)[CH], int (&z_)[CH]) {
-    const int blk = (int)(t / chunks), line = (int)(t % chunks) * 32 + lane;
+  auto fetch = [&](int t, float (&m_)[CH], int (&i_)[CH], int (&z_)[CH]) {
+    const int blk = t >> csh, line = ((t & ((1 << csh) - 1)) << 5) + lane;
 #pragma unroll
     for (int k = 0; k < CH; k++) {
       const int c = k == 0 ? c0 : c1;
@@ -134,13 +147,13 @@ k_cqn_fast(CqnDev Q0, CqnDev Q1, const vb200_block_desc *__restrict__ desc, int 
       i_[k] = __ldcs(iwork + row * n + line);
     }
   };
-  long t = (long)blockIdx.x * wpb + wid;
+  int t = blockIdx.x * wpb + wid;
   if (t < tasks) fetch(t, nmv, nil, nnz);
   for (; t < tasks; t += stride) {
 #pragma unroll
     for (int k = 0; k < CH; k++) { mv[k] = nmv[k]; il[k] = nil[k]; nzr[k] = nnz[k]; }
-    if (t + stride < tasks) fetch(t + stride, nmv, nil, nnz);
-    const int blk = (int)(t / chunks), line = (int)(t % chunks) * 32 + lane;
+    if (t < tasks - stride) fetch(t + stride, nmv, nil, nnz);
+    const int blk = t >> csh, line = ((t & ((1 << csh) - 1)) << 5) + lane;
     const CqnDev Q = cqn_pick(Q0, Q1, desc && desc[blk].blocktype);
     const int width = Q.partition;
     const int i = line & ~(width - 1), j = line - i;

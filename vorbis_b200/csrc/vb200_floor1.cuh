@@ -24,8 +24,10 @@ struct Floor1Dev {                     // vorbis_look_floor1 (lib/codec_internal
   short postlist[VB200_VIF_POSIT + 3], sorted[VB200_VIF_POSIT + 3];
   short fwd[VB200_VIF_POSIT + 3], rev[VB200_VIF_POSIT + 3];
   short lo[VB200_VIF_POSIT + 1], hi[VB200_VIF_POSIT + 1];
+  float prcp[VB200_VIF_POSIT + 1];     // 1 / (postlist[hi[i]] - postlist[lo[i]])
 };
 static_assert(sizeof(Floor1Dev) % 4 == 0, "Floor1Dev is copied as words");
+static_assert((sizeof(Floor1Dev) * VB200_MAX_SUBMAPS) % 8 == 0, "the per-warp fp64 terms follow the floor table in shared memory");
 
 struct Floor1Args {
   const Floor1Dev *floors;             // [VB200_MAX_SUBMAPS] of this block size
@@ -35,7 +37,7 @@ struct Floor1Args {
 
 #define F1_WARPS 8
 #define F1_ACC 12                      // xa ya x2a y2a xya an | xb yb x2b y2b xyb bn
-#define F1_STATE (6 * (VB200_VIF_POSIT + 2))
+#define F1_STATE (3 * (VB200_VIF_POSIT + 2) + 3 * ((VB200_VIF_POSIT + 2 + 1) / 2))   // A, B, out int; lon, hin, memo short
 
 __host__ __device__ inline size_t floor1_fit_smem_per_warp(int n) {
   return sizeof(unsigned short) * (size_t)n + sizeof(int) * ((VB200_VIF_POSIT + 1) * F1_ACC + F1_STATE);
@@ -46,10 +48,16 @@ __device__ __forceinline__ int f1_dBquant(float x) {               // lib/floor1
   return i > 1023 ? 1023 : (i < 0 ? 0 : i);
 }
 
-__device__ __forceinline__ int f1_point(int x0, int x1, int y0, int y1, int x) {   // render_point
+// render_point (lib/floor1.c:362-374).  rcp = 1/(x1-x0) as fp32: ady*(x-x0) < 2^22 is exact in
+// fp32, the quotient estimate is off by at most one and the remainder test makes it exact
+__device__ __forceinline__ int f1_point(int x0, int x1, int y0, int y1, int x, float rcp) {
   y0 &= 0x7fff; y1 &= 0x7fff;
   const int dy = y1 - y0, adx = x1 - x0, ady = abs(dy);
-  const int off = (ady * (x - x0)) / adx;
+  const int num = ady * (x - x0);
+  int off = __float2int_rz((float)num * rcp);
+  const int r = num - off * adx;
+  if (r < 0) off--;
+  else if (r >= adx) off++;
   return dy < 0 ? y0 - off : y0 + off;
 }
 
@@ -165,9 +173,10 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
   unsigned char *wbase = f1_smem + sizeof(Floor1Dev) * VB200_MAX_SUBMAPS + floor1_fit_smem_per_warp(a.n) * warp;
   double *term = reinterpret_cast<double *>(wbase);          // [gaps][6], same bytes as 12 ints per gap
   int *A = reinterpret_cast<int *>(wbase) + (VB200_VIF_POSIT + 1) * F1_ACC;
-  int *B = A + (VB200_VIF_POSIT + 2), *lon = B + (VB200_VIF_POSIT + 2), *hin = lon + (VB200_VIF_POSIT + 2);
-  int *memo = hin + (VB200_VIF_POSIT + 2), *out = memo + (VB200_VIF_POSIT + 2);
-  unsigned short *q = reinterpret_cast<unsigned short *>(out + (VB200_VIF_POSIT + 2));
+  int *B = A + (VB200_VIF_POSIT + 2), *out = B + (VB200_VIF_POSIT + 2);
+  short *lon = reinterpret_cast<short *>(out + (VB200_VIF_POSIT + 2));
+  short *hin = lon + 2 * ((VB200_VIF_POSIT + 2 + 1) / 2), *memo = hin + 2 * ((VB200_VIF_POSIT + 2 + 1) / 2);
+  unsigned short *q = reinterpret_cast<unsigned short *>(memo + 2 * ((VB200_VIF_POSIT + 2 + 1) / 2));
 
   for (long row = (long)blockIdx.x * F1_WARPS + warp; row < a.nrows; row += (long)gridDim.x * F1_WARPS) {
     const int sel = a.floor_sel >= 0 ? a.floor_sel : a.chmux[row % a.channels];
@@ -229,7 +238,7 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
       const int lx = F.postlist[ln], hx = F.postlist[hn];
       const int ly = f1_postY(A, B, ln), hy = f1_postY(A, B, hn);
       __syncwarp();
-      if (lane == 0) memo[ln] = hn;
+      if (lane == 0) memo[ln] = (short)hn;
       if (f1_inspect(F, q, lx, hx, ly, hy, lane)) {
         const int ret = f1_fit_lines(F, term, lsortpos, sortpos - lsortpos, sortpos, hsortpos - sortpos, lane, y);
         int ly0 = y[0], ly1 = y[1], hy0 = y[2], hy1 = y[3];
@@ -245,8 +254,8 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
             A[hn] = hy1;
             if (hn == 1) B[hn] = hy1;
             if (ly1 >= 0 || hy0 >= 0) {
-              for (int j = sortpos - 1; j >= 0; j--) { if (hin[j] == hn) hin[j] = i; else break; }
-              for (int j = sortpos + 1; j < P; j++) { if (lon[j] == ln) lon[j] = i; else break; }
+              for (int j = sortpos - 1; j >= 0; j--) { if (hin[j] == hn) hin[j] = (short)i; else break; }
+              for (int j = sortpos + 1; j < P; j++) { if (lon[j] == ln) lon[j] = (short)i; else break; }
             }
           }
         }
@@ -261,7 +270,7 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
       out[1] = f1_postY(A, B, 1);
       for (int i = 2; i < P; i++) {
         const int ln = F.lo[i - 2], hn = F.hi[i - 2];
-        const int predicted = f1_point(F.postlist[ln], F.postlist[hn], out[ln], out[hn], F.postlist[i]);
+        const int predicted = f1_point(F.postlist[ln], F.postlist[hn], out[ln], out[hn], F.postlist[i], F.prcp[i - 2]);
         const int vx = f1_postY(A, B, i);
         out[i] = (vx >= 0 && predicted != vx) ? vx : (predicted | 0x8000);
       }
@@ -316,7 +325,7 @@ k_floor1_render(Floor1Args a, int32_t *__restrict__ posts, const int32_t *__rest
     if (lane == 0) {                                     // prediction / flag pass, :788-832
       for (int i = 2; i < P; i++) {
         const int ln = F.lo[i - 2], hn = F.hi[i - 2];
-        const int predicted = f1_point(F.postlist[ln], F.postlist[hn], post[ln], post[hn], F.postlist[i]);
+        const int predicted = f1_point(F.postlist[ln], F.postlist[hn], post[ln], post[hn], F.postlist[i], F.prcp[i - 2]);
         if ((post[i] & 0x8000) || predicted == post[i]) {
           post[i] = predicted | 0x8000;
         } else {
