@@ -11,7 +11,7 @@ SURVEY.md §8d) per GPU per step, synthetic PCM, independent blocks with ampmax 
 (drop-in semantics).  One step = one pass of the hot path over that batch: ONE vb200_encode_dsp_dev
 call = six kernels (transform, ampmax, psy, floor1_fit, floor1_render, couple_quantize_normalize).
 `e2e` is the same chain through vb200_encode_dsp with pinned HOST buffers: int16 interleaved stream
-PCM in (blocks cut on the device, hop N/2), floor posts + quantised residue out.  The reference arm
+PCM in (blocks cut on the device, hop N/2), floor posts + quantised residue (int16) out.  The reference arm
 and cpu_baseline run the same chain with the reference's own functions.
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
@@ -373,11 +373,13 @@ def run_ours(args):
     hdesc = make_desc(nb_e)
     h_posts = torch.empty((nb_e, ch, abi.FLOOR1_STRIDE), dtype=torch.int32).pin_memory()
     h_nz = torch.empty((nb_e, ch), dtype=torch.int32).pin_memory()
-    h_iw = torch.empty((nb_e, ch, n), dtype=torch.int32).pin_memory()
+    h_iw = torch.empty((nb_e, ch, n), dtype=torch.int16).pin_memory()      # VB200_IWORK_S16: saturated, counted
+    h_ovf = torch.empty(nb_e, dtype=torch.int32).pin_memory()
     h_amp = torch.empty(nb_e, dtype=torch.float32).pin_memory()
     hio = abi.EncodeIO()
     hio.pcm, hio.pcm_fmt, hio.hop, hio.stream_stride = hp.data_ptr(), lib.PCM_S16_INTERLEAVED, hop, stride
     hio.desc, hio.independent = hdesc.ctypes.data, 0
+    hio.iwork_fmt, hio.overflow = lib.IWORK_S16, h_ovf.data_ptr()
     hio.posts, hio.nonzero, hio.iwork, hio.ampmax_out = h_posts.data_ptr(), h_nz.data_ptr(), h_iw.data_ptr(), h_amp.data_ptr()
     L = lib.load()
 
@@ -400,12 +402,14 @@ def run_ours(args):
         dist.all_reduce(td, op=dist.ReduceOp.MAX)
     dt_max = float(td.item())
     h2d = int(hp.numel() * 2 + hdesc.nbytes)
-    d2h = int((h_posts.numel() + h_nz.numel() + h_iw.numel() + h_amp.numel()) * 4)
+    d2h = int((h_posts.numel() + h_nz.numel() + h_amp.numel() + h_ovf.numel()) * 4 + h_iw.numel() * 2)
+    if int(h_ovf.sum()) != 0:
+        raise RuntimeError("int16 residue overflowed on the bench signal")
     e2e = {"value": world * nb_e * args.steps / dt_max, "unit": UNIT,
            "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
            "blocks_per_step": nb_e * world, "gpu_launches": int(e2e_launches),
            "call": "vb200_encode_dsp: %d streams x %d blocks per GPU, int16 interleaved stream PCM in (hop N/2, "
-                   "blocks cut on the device), posts+nonzero+quantised residue out; pinned host memory; "
+                   "blocks cut on the device), posts+nonzero+quantised residue (int16, overflow-counted) out; pinned host memory; "
                    "three-lane chunk pipeline; wall clock, max over ranks" % (ns_e, bps)}
 
     line = None

@@ -283,8 +283,14 @@ int vb200_couple_quantize_normalize    (vb200_ctx*, int W, int blocktype, int bl
  *   nonzero [nblocks][ch]                       after the coupling propagation (lib/psy.c:1203)
  *   iwork   [nblocks][ch][n]                    quantised, coupled residue ints
  *   ampmax_out [nblocks]                        vorbis_block_internal.ampmax on exit (:576)
- *   mdct, logmdct, logmask [nblocks][ch][n]     optional (NULL = stay in device scratch)        */
+ *   mdct, logmdct, logmask [nblocks][ch][n]     optional (NULL = stay in device scratch)
+ * iwork_fmt VB200_IWORK_S16 halves the largest output: the residue leaves as int16, saturated to
+ * [-32768,32767]; overflow[block] counts the values of that block that were clipped (0 for any
+ * realistic signal: |mdct|/floor would have to exceed 32767) - a caller that sees a non-zero
+ * count re-runs that block with VB200_IWORK_S32.                                                */
 #define VB200_PCM_F32_BLOCKS       0
+#define VB200_IWORK_S32            0
+#define VB200_IWORK_S16            1
 typedef struct vb200_encode_io {
   const void *pcm;
   int32_t pcm_fmt;
@@ -293,14 +299,15 @@ typedef struct vb200_encode_io {
   const vb200_block_desc *desc;
   const float *ampmax0;
   int32_t independent;
-  int32_t reserved;
+  int32_t iwork_fmt;              /* VB200_IWORK_S32 (0) or VB200_IWORK_S16 */
   int32_t *posts;
   int32_t *nonzero;
-  int32_t *iwork;
+  void    *iwork;                 /* int32 or int16 [nblocks][ch][n], see iwork_fmt */
   float *ampmax_out;
   float *mdct;
   float *logmdct;
   float *logmask;
+  int32_t *overflow;              /* VB200_IWORK_S16 only: [nblocks] values that did not fit */
 } vb200_encode_io;
 /* every pointer in *d_io is a device pointer; the struct itself is host memory */
 int vb200_encode_dsp_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream, int blobno,

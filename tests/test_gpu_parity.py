@@ -608,3 +608,33 @@ def test_encode_dsp_device_pointers_and_errors(cfg):
     io.pcm_fmt = 0; io.posts = None
     with pytest.raises(vlib.VB200Error):
         ctx.encode_dsp_dev(W, nb, 1, io)
+
+
+@pytest.mark.parametrize("W", [0, 1])
+def test_encode_dsp_int16_residue(cfg, W, monkeypatch):
+    """VB200_IWORK_S16: the residue leaves as int16; equal to the int32 result where it fits, saturated and
+    counted per block where it does not (PCM far outside [-1,1] makes |mdct|/floor exceed 32767)"""
+    name, setup, ctx, o, _, _ = cfg
+    if setup.channels & (setup.channels - 1):
+        with pytest.raises(vlib.VB200Error):
+            ctx.encode_dsp(W, np.zeros((1, setup.channels, setup.blocksize(W)), np.float32),
+                           np.zeros(1, abi.BLOCKDESC_DTYPE), iwork_s16=True)
+        return
+    monkeypatch.setenv("VB200_CHUNK_BLOCKS", "5")
+    N, ch = setup.blocksize(W), setup.channels
+    rng = np.random.default_rng(5 + W)
+    nb = 12
+    pcm = (0.3 * rng.standard_normal((nb, ch, N))).astype(np.float32)
+    pcm[3] *= 3e6                                                      # overflowing block
+    pcm[8, 0] *= 1e6
+    desc = np.zeros(nb, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = W; desc["nW"] = W; desc["blocktype"] = np.arange(nb) % 2; desc["ampmax"] = -10.0
+    want = o.encode_dsp(W, pcm, desc)
+    got = ctx.encode_dsp(W, pcm, desc, iwork_s16=True)
+    assert got["iwork"].dtype == np.int16
+    assert np.array_equal(got["iwork"], np.clip(want["iwork"], -32768, 32767).astype(np.int16))
+    clipped = ((want["iwork"] > 32767) | (want["iwork"] < -32768)).reshape(nb, -1).sum(1)
+    assert np.array_equal(got["overflow"], clipped)
+    assert clipped[3] > 0 and clipped[0] == 0
+    for k in ("posts", "nonzero"):
+        assert np.array_equal(got[k], want[k]), k

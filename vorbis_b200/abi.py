@@ -128,7 +128,7 @@ class EncodeIO(C.Structure):
         ("desc", C.c_void_p),
         ("ampmax0", C.c_void_p),
         ("independent", C.c_int32),
-        ("reserved", C.c_int32),
+        ("iwork_fmt", C.c_int32),
         ("posts", C.c_void_p),
         ("nonzero", C.c_void_p),
         ("iwork", C.c_void_p),
@@ -136,6 +136,7 @@ class EncodeIO(C.Structure):
         ("mdct", C.c_void_p),
         ("logmdct", C.c_void_p),
         ("logmask", C.c_void_p),
+        ("overflow", C.c_void_p),
     ]
 
 

@@ -1440,11 +1440,27 @@ extern "C" int vb200_floor1_render(vb200_ctx *c, int W, int floor_sel, int nrows
 
 // ======================================================================== //
 // the whole per-block encode DSP (Phase A -> floor1 fit -> floor render -> Phase B)
-static_assert(sizeof(vb200_encode_io) == 104, "vb200_encode_io layout (mirrored by vorbis_b200/abi.py)");
+static_assert(sizeof(vb200_encode_io) == 112, "vb200_encode_io layout (mirrored by vorbis_b200/abi.py)");
 struct EncScratch {
   float *mdct, *logmdct, *logmask, *logfft, *lmax, *gmax;
   int32_t *fitnz;
+  int32_t *iw32;                     // residue as int32 when the caller wants int16 out
 };
+
+// int32 residue -> saturated int16, counting per block what did not fit (VB200_IWORK_S16)
+__global__ void __launch_bounds__(256)
+k_pack_s16(const int4 *__restrict__ src, short4 *__restrict__ dst, long nvec, int vec_per_block_log2,
+           int32_t *__restrict__ overflow) {
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
+    const int4 a = __ldcs(src + v);
+    int bad = 0;
+    auto sat = [&](int x) { if (x > 32767) { bad++; return (short)32767; } if (x < -32768) { bad++; return (short)-32768; } return (short)x; };
+    short4 o;
+    o.x = sat(a.x); o.y = sat(a.y); o.z = sat(a.z); o.w = sat(a.w);
+    __stcs(dst + v, o);
+    if (bad) atomicAdd(overflow + (v >> vec_per_block_log2), bad);
+  }
+}
 
 static size_t enc_pcm_bytes(const vb200_encode_io *io, int ch, int N, int nstreams, int bps) {
   switch (io->pcm_fmt) {
@@ -1457,6 +1473,8 @@ static size_t enc_pcm_bytes(const vb200_encode_io *io, int ch, int N, int nstrea
 static int enc_check(vb200_ctx *c, int W, int nstreams, int bps, int blobno, const vb200_encode_io *io) {
   if (!io || !io->pcm || !io->desc || !io->posts || !io->nonzero || !io->iwork || !io->ampmax_out)
     return fail(VB200_EINVAL, "encode io pointers");
+  if (io->iwork_fmt != VB200_IWORK_S32 && io->iwork_fmt != VB200_IWORK_S16) return fail(VB200_EINVAL, "iwork format");
+  if (io->iwork_fmt == VB200_IWORK_S16 && !io->overflow) return fail(VB200_EINVAL, "int16 residue needs the overflow array");
   if (nstreams <= 0 || bps <= 0) return fail(VB200_EINVAL, "nstreams/blocks_per_stream");
   if (c->n_psy != 4) return fail(VB200_EIMPL, "context has no psy lookups");
   if (blobno < 0 || blobno >= VB200_PACKETBLOBS) return fail(VB200_EINVAL, "blobno");
@@ -1488,17 +1506,31 @@ static int encode_launch(vb200_ctx *c, int W, int nstreams, int bps, int blobno,
                           S.logfft, S.lmax, S.gmax, pp))) return rc;
   if ((rc = vb200_floor1_fit_dev(c, W, -1, rows, S.logmdct, S.logmask, d->posts, S.fitnz, st))) return rc;
   if (c->profiling) CU(cudaEventRecord(c->ev[4], st));
-  if ((rc = vb200_floor1_render_dev(c, W, -1, rows, d->posts, S.fitnz, d->iwork, d->nonzero, st))) return rc;
+  const bool s16 = d->iwork_fmt == VB200_IWORK_S16;
+  int32_t *iw = s16 ? S.iw32 : (int32_t *)d->iwork;
+  if ((rc = vb200_floor1_render_dev(c, W, -1, rows, d->posts, S.fitnz, iw, d->nonzero, st))) return rc;
   if (c->profiling) CU(cudaEventRecord(c->ev[5], st));
   CqnDev Q0, Q1;
   if ((rc = cqn_setup(c, W, 0, blobno, &Q0))) return rc;
   if ((rc = cqn_setup(c, W, 1, blobno, &Q1))) return rc;
-  if ((rc = cqn_launch(c, Q0, Q1, d->desc, nblocks, S.mdct, d->iwork, d->nonzero, st))) return rc;
+  if ((rc = cqn_launch(c, Q0, Q1, d->desc, nblocks, S.mdct, iw, d->nonzero, st))) return rc;
+  if (s16) {
+    const int n = c->dx[W].N / 2;
+    const long nvec = (long)rows * n / 4;
+    int lg = 0;
+    while ((1L << lg) < (long)ch * n / 4) lg++;
+    if ((1L << lg) != (long)ch * n / 4) {             // channels not a power of two: per-block counts need a division
+      return fail(VB200_EIMPL, "int16 residue needs a power-of-two channel count");
+    }
+    CU(cudaMemsetAsync(d->overflow, 0, sizeof(int32_t) * (size_t)nblocks, st));
+    k_pack_s16<<<grid_for(c, (int)((nvec + 255) / 256), 8), 256, 0, st>>>((const int4 *)iw, (short4 *)d->iwork, nvec, lg, d->overflow);
+    if ((rc = post_launch(c))) return rc;
+  }
   if (c->profiling) CU(cudaEventRecord(c->ev[6], st));
   return 0;
 }
 
-static int enc_scratch(DevBuf *B, size_t rows, size_t nblocks, size_t n, const vb200_encode_io *d, EncScratch *S) {
+static int enc_scratch(DevBuf *B, size_t rows, size_t nblocks, size_t n, const vb200_encode_io *d, bool s16, EncScratch *S) {
   void *p; int rc;
   const size_t big = sizeof(float) * rows * n;
   if (d && d->mdct) S->mdct = d->mdct; else { if ((rc = ensure_buf(B[0], big, &p))) return rc; S->mdct = (float *)p; }
@@ -1508,6 +1540,8 @@ static int enc_scratch(DevBuf *B, size_t rows, size_t nblocks, size_t n, const v
   if ((rc = ensure_buf(B[4], sizeof(float) * rows, &p))) return rc; S->lmax = (float *)p;
   if ((rc = ensure_buf(B[5], sizeof(float) * nblocks, &p))) return rc; S->gmax = (float *)p;
   if ((rc = ensure_buf(B[6], sizeof(int32_t) * rows, &p))) return rc; S->fitnz = (int32_t *)p;
+  S->iw32 = nullptr;
+  if (s16) { if ((rc = ensure_buf(B[7], sizeof(int32_t) * rows * n, &p))) return rc; S->iw32 = (int32_t *)p; }
   return 0;
 }
 
@@ -1518,7 +1552,7 @@ extern "C" int vb200_encode_dsp_dev(vb200_ctx *c, int W, int nstreams, int bps, 
   if ((rc = enc_check(c, W, nstreams, bps, blobno, d))) return rc;
   const size_t ch = c->setup.channels, n = c->dx[W].N / 2, nblocks = (size_t)nstreams * bps;
   EncScratch S;
-  if ((rc = enc_scratch(c->enc_buf, nblocks * ch, nblocks, n, d, &S))) return rc;
+  if ((rc = enc_scratch(c->enc_buf, nblocks * ch, nblocks, n, d, d->iwork_fmt == VB200_IWORK_S16, &S))) return rc;
   return encode_launch(c, W, nstreams, bps, blobno, d, S, (cudaStream_t)stream);
 }
 
@@ -1547,17 +1581,21 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
     if ((rc = ensure_buf(B[10], sizeof(float) * cs, &p))) return rc; d.ampmax0 = h->ampmax0 ? (const float *)p : nullptr;
     if ((rc = ensure_buf(B[11], sizeof(int32_t) * (size_t)cs * bps * ch * VB200_FLOOR1_STRIDE, &p))) return rc; d.posts = (int32_t *)p;
     if ((rc = ensure_buf(B[12], sizeof(int32_t) * (size_t)cs * bps * ch, &p))) return rc; d.nonzero = (int32_t *)p;
-    if ((rc = ensure_buf(B[13], sizeof(int32_t) * (size_t)cs * bps * ch * n, &p))) return rc; d.iwork = (int32_t *)p;
+    const bool s16 = h->iwork_fmt == VB200_IWORK_S16;
+    const size_t isz = s16 ? sizeof(int16_t) : sizeof(int32_t);
+    if ((rc = ensure_buf(B[13], isz * (size_t)cs * bps * ch * n, &p))) return rc; d.iwork = p;
+    if (s16) { if ((rc = ensure_buf(B[15], sizeof(int32_t) * (size_t)cs * bps, &p))) return rc; d.overflow = (int32_t *)p; }
     if ((rc = ensure_buf(B[14], sizeof(float) * (size_t)cs * bps, &p))) return rc; d.ampmax_out = (float *)p;
     EncScratch S;
-    if ((rc = enc_scratch(B, (size_t)cs * bps * ch, (size_t)cs * bps, n, nullptr, &S))) return rc;
+    if ((rc = enc_scratch(B, (size_t)cs * bps * ch, (size_t)cs * bps, n, nullptr, s16, &S))) return rc;
     CU(cudaMemcpyAsync((void *)d.pcm, (const char *)h->pcm + pcm_per_stream * s0, pcm_per_stream * ns, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync((void *)d.desc, h->desc + b0, sizeof(vb200_block_desc) * nb, cudaMemcpyHostToDevice, st));
     if (h->ampmax0) CU(cudaMemcpyAsync((void *)d.ampmax0, h->ampmax0 + s0, sizeof(float) * ns, cudaMemcpyHostToDevice, st));
     if ((rc = encode_launch(c, W, ns, bps, blobno, &d, S, st))) return rc;
     CU(cudaMemcpyAsync(h->posts + r0 * VB200_FLOOR1_STRIDE, d.posts, sizeof(int32_t) * rows * VB200_FLOOR1_STRIDE, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->nonzero + r0, d.nonzero, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(h->iwork + r0 * n, d.iwork, sizeof(int32_t) * rows * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync((char *)h->iwork + isz * r0 * n, d.iwork, isz * rows * n, cudaMemcpyDeviceToHost, st));
+    if (s16) CU(cudaMemcpyAsync(h->overflow + b0, d.overflow, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->ampmax_out + b0, d.ampmax_out, sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
     if (h->mdct) CU(cudaMemcpyAsync(h->mdct + r0 * n, S.mdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
     if (h->logmdct) CU(cudaMemcpyAsync(h->logmdct + r0 * n, S.logmdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));

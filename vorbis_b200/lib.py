@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(HERE, "libvorbis_b200.so")
 
 PCM_F32_PLANAR = 1
 PCM_S16_INTERLEAVED = 2
+IWORK_S32 = 0
+IWORK_S16 = 1
 
 EXPORTS = [
     "vb200_ctx_create", "vb200_ctx_destroy", "vb200_device_count", "vb200_last_error",
@@ -307,7 +309,7 @@ class Context:
 
     # ---- whole per-block encode DSP (Phase A -> floor1 -> Phase B) in one call ---------------
     def encode_dsp(self, W, pcm, desc, nstreams=None, fmt=0, hop=0, ampmax0=None, independent=None, blobno=7,
-                   floats=False):
+                   floats=False, iwork_s16=False):
         """Host buffers.  fmt 0: pcm [nblocks][ch][N] float; PCM_F32_PLANAR: [streams][ch][stride] float;
         PCM_S16_INTERLEAVED: [streams][stride][ch] int16.  nstreams None = every block its own stream.
         independent None = True when the blocks are not grouped in streams."""
@@ -339,7 +341,11 @@ class Context:
             ampmax0 = np.ascontiguousarray(ampmax0, np.float32)
             io.ampmax0 = ampmax0.ctypes.data
         out = {"posts": np.zeros((nb, ch, abi.FLOOR1_STRIDE), np.int32), "nonzero": np.zeros((nb, ch), np.int32),
-               "iwork": np.zeros((nb, ch, n), np.int32), "ampmax_out": np.zeros(nb, np.float32)}
+               "iwork": np.zeros((nb, ch, n), np.int16 if iwork_s16 else np.int32),
+               "ampmax_out": np.zeros(nb, np.float32)}
+        if iwork_s16:
+            io.iwork_fmt = IWORK_S16
+            out["overflow"] = np.full(nb, -1, np.int32)
         if floats:
             for k in ("mdct", "logmdct", "logmask"):
                 out[k] = np.zeros((nb, ch, n), np.float32)
