@@ -40,6 +40,7 @@ extern "C" {
 #define VB200_COMPAND_LEVELS 40   /* lib/psy.h:33  */
 #define VB200_PACKETBLOBS    15   /* lib/codec_internal.h:28 */
 #define VB200_MAX_CHANNELS  255
+#define VB200_VE_BANDS        7   /* lib/envelope.h:29 */
 #define VB200_MAX_COUPLING  256
 
 /* One psychoacoustic lookup == vorbis_look_psy + the vorbis_info_psy scalars
@@ -116,6 +117,12 @@ typedef struct vb200_setup {
   int32_t submaps[2];
   uint8_t chmux[2][VB200_MAX_CHANNELS + 1];
   vb200_floor1_setup floor1[2][VB200_MAX_SUBMAPS];
+  /* envelope / block-switch detector: vorbis_info_psy_global.preecho_thresh, postecho_thresh,
+   * stretch_penalty, preecho_minenergy (lib/psy.h:67-85), read by _ve_amp (lib/envelope.c:88-213) */
+  float   preecho_thresh[VB200_VE_BANDS];
+  float   postecho_thresh[VB200_VE_BANDS];
+  float   stretch_penalty;
+  float   preecho_minenergy;
 } vb200_setup;
 
 /* Per-block inputs of mapping0_forward that are not PCM (lib/mapping0.c:230-252) */
@@ -316,6 +323,30 @@ int vb200_encode_dsp_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream,
  * that rotate over three lanes so H2D, the kernels and D2H of different chunks overlap         */
 int vb200_encode_dsp    (vb200_ctx*, int W, int nstreams, int blocks_per_stream, int blobno,
                          const vb200_encode_io *io);
+
+/* ---- envelope / block-switch detector -----------------------------------------
+ * The analysis loop of _ve_envelope_search (lib/envelope.c:232-267): for steps j = first_step ..
+ * first_step+nsteps-1 of every stream and every channel, _ve_amp (:88-213) on the 128 samples that
+ * start at sample 64*j - squared-sine window, mdct_forward(128), near-DC spreading, the seven band
+ * amplitudes, their pre-/post-echo deltas against the 17-deep amplitude history - and the stretch
+ * logic that couples the channels.  Everything that vorbis_analysis_blockout then does with the
+ * result (cursor / curmark walk, :269-327) only reads the marks and stays on the host.
+ *
+ * pcm     stream PCM, VB200_PCM_F32_PLANAR [stream][ch][stream_stride] or VB200_PCM_S16_INTERLEAVED
+ *         [stream][stream_stride][ch]; 64*(first_step+nsteps-1)+128 <= stream_stride
+ * state   [nstreams][VB200_VE_STATE_WORDS(ch)] 32-bit words, in/out: word 0 = envelope_lookup.stretch,
+ *         then envelope_filter_state[ch*VE_BANDS] with the reference's own layout (lib/envelope.h:32-42:
+ *         ampbuf[17], ampptr, nearDC[15], nearDC_acc, nearDC_partialacc, nearptr) so that a binding
+ *         can copy ve->filter in and out verbatim; all zero = a fresh vorbis_dsp_state
+ * ret     [nstreams][nsteps] the loop's `ret` per step: bit 0 (and 2) pre-echo, bit 1 post-echo
+ * vb200_envelope_apply_marks (plain C, no CUDA) replays lib/envelope.c:254-264 on a mark array.   */
+#define VB200_VE_FILTER_WORDS 36
+#define VB200_VE_STATE_WORDS(ch) (1 + VB200_VE_FILTER_WORDS * VB200_VE_BANDS * (ch))
+int vb200_envelope_search_dev(vb200_ctx*, int nstreams, const void *d_pcm, int pcm_fmt, int64_t stream_stride,
+                              int first_step, int nsteps, int32_t *d_state, uint8_t *d_ret, void *stream);
+int vb200_envelope_search    (vb200_ctx*, int nstreams, const void *pcm, int pcm_fmt, int64_t stream_stride,
+                              int first_step, int nsteps, int32_t *state, uint8_t *ret);
+void vb200_envelope_apply_marks(const uint8_t *ret, int first_step, int nsteps, int32_t *mark);
 
 /* ---- decode: mdct_backward (lib/mapping0.c:792-795) fused with the windowed
  *      overlap-add of vorbis_synthesis_blockin (lib/block.c:767-823).

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libvb_oracle.so")
 f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
@@ -56,6 +57,8 @@ def lib():
         L.vbo_decouple.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p]
         L.vbo_floor1_fit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p, i32p, i32p]
         L.vbo_floor1_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i32p]
+        L.vbo_envelope_search.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int64, C.c_int, C.c_int, i32p, u8p]
+        L.vbo_envelope_apply_marks.argtypes = [u8p, C.c_int, C.c_int, i32p]
         _lib = L
     return _lib
 
@@ -212,6 +215,25 @@ class Oracle:
                 iwork[sel], nonzero[sel] = iw, z
         a.update(posts=posts.reshape(nb, ch, -1), iwork=iwork, nonzero=nonzero)
         return a
+
+    def envelope_search(self, pcm, first_step, nsteps, state=None):
+        """pcm planar float [streams][ch][stride]; returns (ret uint8 [streams][nsteps], state words)"""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        ns, ch, stride = pcm.shape
+        assert ch == self.channels and 64 * (first_step + nsteps - 1) + 128 <= stride
+        state = (np.zeros((ns, abi.ve_state_words(ch)), np.int32) if state is None
+                 else np.array(state, np.int32).reshape(ns, abi.ve_state_words(ch)))
+        ret = np.zeros((ns, nsteps), np.uint8)
+        self.L.vbo_envelope_search(self.h, ns, pcm, stride, first_step, nsteps, state, ret)
+        return ret, state
+
+    def envelope_marks(self, ret, first_step=0, mark=None):
+        """replay lib/envelope.c:254-264 for one stream's ret codes"""
+        ret = np.ascontiguousarray(ret, np.uint8)
+        if mark is None:
+            mark = np.zeros(first_step + len(ret) + 2, np.int32)
+        self.L.vbo_envelope_apply_marks(ret, first_step, len(ret), mark)
+        return mark
 
     def decouple(self, W, res):
         res = np.array(res, np.float32)

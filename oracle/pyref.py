@@ -101,6 +101,8 @@ def lib():
         L.ref_blockin_sequence.restype = C.c_long
         L.ref_blockin_sequence.argtypes = [C.c_void_p, C.c_int, i32p, f32p, C.c_int, f32p, C.c_long]
         L.ref_phaseA_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, f32p, f32p, f32p, f32p]
+        L.ref_envelope_marks.restype = C.c_long
+        L.ref_envelope_marks.argtypes = [C.c_void_p, f32p, C.c_long, i32p, C.c_long, C.c_void_p, f32p]
         L.ref_encode_dsp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, i32p, i32p, i32p, f32p]
         _lib = L
     return _lib
@@ -246,6 +248,21 @@ class Ref:
         amp = np.empty(nb, np.float32)
         self.L.ref_phaseA_batch(self.h, W, nb, pcm, desc.ctypes.data, mdct, logmdct, logmask, amp)
         return mdct, logmdct, logmask, amp
+
+    def envelope_marks(self, pcm):
+        """pcm [ch][S] float -> (marks int32 [steps+2], steps, state words, stream [ch][bs1/2+S]) from the
+        reference's own _ve_envelope_search on a fresh dsp state (lib/envelope.c:216).  The reference's
+        stream buffer starts with blocksizes[1]/2 samples of preamble (v->pcm_current = v->centerW at
+        init, lib/block.c:283-284; zeros, later overwritten by _preextrapolate_helper's reverse LPC
+        extrapolation): step j covers samples 64j.. of the returned stream."""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        ch, S = pcm.shape
+        cap = (S + self.bs[1] // 2) // 64 + 8
+        marks = np.zeros(cap, np.int32)
+        state = np.zeros(abi.ve_state_words(ch), np.int32)
+        stream = np.zeros((ch, self.bs[1] // 2 + S), np.float32)
+        steps = int(self.L.ref_envelope_marks(self.h, pcm, S, marks, cap, state.ctypes.data, stream))
+        return marks[:steps + 2], steps, state, stream
 
     def encode_dsp_batch(self, W, pcm, desc):
         """the reference's own functions in mapping0_forward's order: Phase A, floor1_fit, floor1_encode,

@@ -186,6 +186,12 @@ int ref_get_setup(void *hv, vb200_setup *s){
   }
   s->window[0] = _vorbis_window_get(b->window[0]);
   s->window[1] = _vorbis_window_get(b->window[1]);
+  for(k=0;k<VE_BANDS;k++){
+    s->preecho_thresh[k] = g->preecho_thresh[k];
+    s->postecho_thresh[k] = g->postecho_thresh[k];
+  }
+  s->stretch_penalty = g->stretch_penalty;
+  s->preecho_minenergy = g->preecho_minenergy;
   for(w=0;w<2;w++){
     vorbis_info_mapping0 *m = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[w]->mapping];
     int sm;
@@ -746,4 +752,42 @@ void ref_encode_dsp_batch(void *hv, int W, int nblocks, const float *pcm, const 
   }
   oggpack_writeclear(&opb);
   free(mdct); free(logmdct); free(logmask); free(m); free(iw); free(nz);
+}
+
+
+/* ---- envelope detector: the reference's own _ve_envelope_search (lib/envelope.c:216) on a fresh
+ * vorbis_dsp_state holding `nsamples` samples per channel (planar pcm [ch][nsamples]); no blockout
+ * happens, so the one call analyses every step the buffer allows.  Copies out ve->mark[0..steps+VE_POST),
+ * the filter states and stretch afterwards, and the stream buffer itself ([ch][bs1/2+nsamples]);
+ * returns the number of steps analysed (`last`).                                                 */
+#include "envelope.h"
+long ref_envelope_marks(void *hv, const float *pcm, long nsamples, int32_t *marks, long markcap,
+                        int32_t *state_out, float *stream_out){
+  ref_handle *h = (ref_handle*)hv;
+  vorbis_dsp_state vd;
+  private_state *b;
+  envelope_lookup *ve;
+  float **buf;
+  long steps, k;
+  int c, ch = h->vi.channels;
+  if(vorbis_analysis_init(&vd,&h->vi)) return -1;
+  buf = vorbis_analysis_buffer(&vd,(int)nsamples);
+  for(c=0;c<ch;c++) memcpy(buf[c],pcm+(size_t)c*nsamples,sizeof(float)*nsamples);
+  vorbis_analysis_wrote(&vd,(int)nsamples);
+  _ve_envelope_search(&vd);
+  b = (private_state*)vd.backend_state;
+  ve = b->ve;
+  /* the stream buffer the detector saw: blocksizes[1]/2 samples of preamble (zeros, or the reverse
+   * LPC extrapolation of _preextrapolate_helper, lib/block.c:415-456) followed by the input */
+  if(stream_out)
+    for(c=0;c<ch;c++) memcpy(stream_out+(size_t)c*vd.pcm_current,vd.pcm[c],sizeof(float)*vd.pcm_current);
+  steps = vd.pcm_current/ve->searchstep-VE_WIN;
+  if(steps<0) steps=0;
+  for(k=0;k<markcap;k++) marks[k] = (k<steps+VE_POST && k<ve->storage) ? ve->mark[k] : 0;
+  if(state_out){
+    state_out[0] = ve->stretch;
+    memcpy(state_out+1, ve->filter, sizeof(envelope_filter_state)*VE_BANDS*ch);
+  }
+  vorbis_dsp_clear(&vd);
+  return steps;
 }

@@ -997,3 +997,4 @@ void vbo_phaseA_streams(vbo_ctx *c, int W, int nstreams, int bps, const vb200_ph
 /* Phase B and decode are in vb_oracle_b.c (included to keep one library)  */
 #include "vb_oracle_b.inc"
 #include "vb_oracle_floor.inc"
+#include "vb_oracle_env.inc"

@@ -53,4 +53,7 @@ void vbo_floor1_fit(vbo_ctx *c, int W, int floor_sel, int nrows, const float *lo
                     int32_t *posts, int32_t *fit_nonzero);
 void vbo_floor1_render(vbo_ctx *c, int W, int floor_sel, int nrows, int32_t *posts, const int32_t *fit_nonzero,
                        int32_t *ilogmask, int32_t *nonzero);
+void vbo_envelope_search(vbo_ctx *c, int nstreams, const float *pcm, int64_t stride, int first_step,
+                         int nsteps, int32_t *state, uint8_t *ret);
+void vbo_envelope_apply_marks(const uint8_t *ret, int first_step, int nsteps, int32_t *mark);
 #endif

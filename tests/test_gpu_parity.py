@@ -638,3 +638,55 @@ def test_encode_dsp_int16_residue(cfg, W, monkeypatch):
     assert clipped[3] > 0 and clipped[0] == 0
     for k in ("posts", "nonzero"):
         assert np.array_equal(got[k], want[k]), k
+
+
+def test_envelope_search_golden(cfg):
+    """the envelope / block-switch detector on the device equals the reference's
+    _ve_envelope_search: marks and the carried filter state (lib/envelope.c:88-267)"""
+    name, setup, ctx, o, _, _ = cfg
+    env = load_npz("envelope", name)
+    steps = int(env["steps"])
+    ret, state = ctx.envelope_search(env["stream"][None], 0, steps)
+    assert np.array_equal(ctx.envelope_marks(ret[0])[:steps + 2], env["marks"]), "marks vs reference"
+    assert np.array_equal(state[0], env["state"]), "filter state vs reference"
+    want_ret, want_state = o.envelope_search(env["stream"][None], 0, steps)
+    assert np.array_equal(ret, want_ret)
+
+
+@pytest.mark.parametrize("fmt", ["f32", "s16"])
+def test_envelope_search_streams_vs_oracle(cfg, fmt):
+    """many streams at once, int16 or float PCM, the search cut into two calls with the state carried"""
+    import torch
+    name, setup, ctx, o, _, _ = cfg
+    ch = setup.channels
+    ns, stride = 9, 64 * 90 + 128
+    rng = np.random.default_rng(21)
+    t = np.arange(stride)
+    s16 = np.clip(4000 * rng.standard_normal((ns, stride, ch)) * rng.uniform(0.01, 2.0, (ns, 1, 1)) +
+                  9000 * np.sin(2 * np.pi * 500.0 * t / setup.rate)[None, :, None], -32768, 32767).astype(np.int16)
+    for s in range(ns):                                  # bursts and drop-outs at different places
+        a = 300 + 517 * s
+        s16[s, a:a + 400] //= 64
+        s16[s, a + 400:a + 520] = rng.integers(-30000, 30000, (120, ch))
+    s16[4] = 0                                           # digital silence
+    planar = np.ascontiguousarray((s16.astype(np.float32) / np.float32(32768.0)).transpose(0, 2, 1))
+    nsteps = 90
+    want_ret, want_state = o.envelope_search(planar, 0, nsteps)
+    src = planar if fmt == "f32" else s16
+    f = vlib.PCM_F32_PLANAR if fmt == "f32" else vlib.PCM_S16_INTERLEAVED
+    r1, s1 = ctx.envelope_search(src, 0, 37, fmt=f)
+    r2, s2 = ctx.envelope_search(src, 37, nsteps - 37, state=s1, fmt=f)
+    assert np.array_equal(np.concatenate([r1, r2], 1), want_ret), "trigger bits"
+    assert np.array_equal(s2, want_state), "state"
+    assert (want_ret != 0).any()
+    # device pointers
+    dev = torch.device("cuda")
+    d_pcm = torch.from_numpy(src).to(dev)
+    d_state = torch.zeros((ns, abi.ve_state_words(ch)), dtype=torch.int32, device=dev)
+    d_ret = torch.zeros((ns, nsteps), dtype=torch.uint8, device=dev)
+    ctx.envelope_search_dev(ns, d_pcm.data_ptr(), f, stride, 0, nsteps, d_state.data_ptr(), d_ret.data_ptr(),
+                            stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_ret.cpu().numpy(), want_ret) and np.array_equal(d_state.cpu().numpy(), want_state)
+    with pytest.raises(vlib.VB200Error):
+        ctx.envelope_search(src, 80, 20, fmt=f)          # runs past the stream buffer

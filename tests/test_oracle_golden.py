@@ -176,3 +176,22 @@ def test_oracle_encode_chain_golden(name, tag, oracle_lib):
     ep = enc[tag + "_enc_posts"].astype(np.int32).copy()
     ep[enc[tag + "_fit_posts"][..., 0] == -1] = 0                       # NULL fit: the API returns a zero row
     assert np.array_equal(r["posts"], ep)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_oracle_envelope_golden(name, oracle_lib):
+    """envelope / block-switch detector (lib/envelope.c): the oracle's trigger bits, replayed into marks,
+    and its final filter state equal what the reference's _ve_envelope_search left behind"""
+    setup = load_setup(name)
+    env = load_npz("envelope", name)
+    o = oracle_lib.Oracle(setup)
+    steps = int(env["steps"])
+    ret, state = o.envelope_search(env["stream"][None], 0, steps)
+    assert np.array_equal(o.envelope_marks(ret[0])[:steps + 2], env["marks"])
+    assert np.array_equal(state[0], env["state"])
+    assert env["marks"].sum() > 0 and (ret & 2).any() and (ret & 1).any()
+    # the search may be cut anywhere: state carries over
+    a = steps // 2 + 1
+    r1, s1 = o.envelope_search(env["stream"][None], 0, a)
+    r2, s2 = o.envelope_search(env["stream"][None], a, steps - a, state=s1)
+    assert np.array_equal(np.concatenate([r1, r2], 1), ret) and np.array_equal(s2, state)

@@ -164,3 +164,25 @@ def test_encode_chain_vs_reference(args, oracle_lib):
         assert_bits_equal(a["ampmax_out"], b["ampmax_out"], "ampmax_out")
         assert np.array_equal(a["iwork"], cap["iwork_out"][idx][:, :, :N // 2]), "iwork vs the API loop's capture"
     r.close()
+
+
+@pytest.mark.parametrize("args", [(2, 44100, 0.5), (1, 44100, 0.4), (6, 48000, 0.2), (1, 22050, 0.3), (2, 32000, 0.0),
+                                  (2, 96000, 0.7)], ids=lambda g: "ch%d_%d_q%g" % g)
+def test_envelope_vs_reference(args, oracle_lib):
+    """the reference's own _ve_envelope_search on a fresh dsp state vs the restatement: marks, filter
+    states and stretch bit-identical (the stream buffer, incl. the pre-extrapolated preamble, is taken
+    from the reference)"""
+    ch, rate, q = args
+    r = pyref.Ref(ch, rate, q)
+    o = oracle_lib.Oracle(r.setup())
+    rng = np.random.default_rng(3)
+    pcm = probe_signal(ch, rate, 44100 / rate, seed=5)[:, :44100].copy()
+    pcm[:, 8000:12000] *= 0.001
+    pcm[:, 20000:20300] = rng.uniform(-.9, .9, (ch, 300))
+    pcm[:, 30000:33000] = 0
+    marks, steps, st, stream = r.envelope_marks(pcm)
+    ret, state = o.envelope_search(stream[None], 0, steps)
+    assert np.array_equal(o.envelope_marks(ret[0])[:steps + 2], marks)
+    assert np.array_equal(state[0], st)
+    assert marks.sum() > 0
+    r.close()

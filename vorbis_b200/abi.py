@@ -17,6 +17,13 @@ PACKETBLOBS = 15
 MAX_COUPLING = 256
 MAX_CHANNELS = 255
 MAX_SUBMAPS = 4
+VE_BANDS = 7
+VE_FILTER_WORDS = 36
+
+
+def ve_state_words(ch):
+    return 1 + VE_FILTER_WORDS * VE_BANDS * ch
+
 FLOOR1_STRIDE = 65
 
 c_float_p = C.POINTER(C.c_float)
@@ -86,6 +93,10 @@ class Setup(C.Structure):
         ("submaps", C.c_int32 * 2),
         ("chmux", (C.c_uint8 * (MAX_CHANNELS + 1)) * 2),
         ("floor1", (Floor1Setup * MAX_SUBMAPS) * 2),
+        ("preecho_thresh", C.c_float * VE_BANDS),
+        ("postecho_thresh", C.c_float * VE_BANDS),
+        ("stretch_penalty", C.c_float),
+        ("preecho_minenergy", C.c_float),
     ]
 
 
@@ -192,6 +203,12 @@ class SetupHolder:
                 s.submaps[w] = int(a["submaps"][w])
                 for k in range(cm.shape[1]):
                     s.chmux[w][k] = int(cm[w][k])
+        if "env_preecho_thresh" in a:
+            for k in range(VE_BANDS):
+                s.preecho_thresh[k] = float(a["env_preecho_thresh"][k])
+                s.postecho_thresh[k] = float(a["env_postecho_thresh"][k])
+            s.stretch_penalty = float(_sc(a["env_stretch_penalty"]))
+            s.preecho_minenergy = float(_sc(a["env_preecho_minenergy"]))
         for w in range(2):
             for sm in range(MAX_SUBMAPS):
                 key = "floor1_%d_%d_postlist" % (w, sm)
@@ -276,6 +293,10 @@ class SetupHolder:
         for w in range(2):
             if s.window[w]:
                 a["window%d" % w] = np.ctypeslib.as_array(s.window[w], shape=(s.blocksizes[w] // 2,)).copy()
+        a["env_preecho_thresh"] = np.array(list(s.preecho_thresh), np.float32)
+        a["env_postecho_thresh"] = np.array(list(s.postecho_thresh), np.float32)
+        a["env_stretch_penalty"] = np.float32(s.stretch_penalty)
+        a["env_preecho_minenergy"] = np.float32(s.preecho_minenergy)
         a["submaps"] = np.array(list(s.submaps), np.int32)
         a["chmux"] = np.array([[s.chmux[w][k] for k in range(max(1, s.channels))] for w in range(2)], np.int32)
         for w in range(2):

@@ -20,6 +20,7 @@
 #include "vb200_cqn.cuh"
 #include "vb200_psy2.cuh"
 #include "vb200_floor1.cuh"
+#include "vb200_env.cuh"
 #include "floor1_db_table.h"
 
 using namespace vb200;
@@ -63,6 +64,8 @@ struct vb200_ctx {
   DevBuf scratch[16];
   DevBuf lane_buf[2][10];            // per-lane device buffers of the pipelined host Phase-A path
   cudaStream_t s_lane[2] = {nullptr, nullptr};
+  EnvDev env;                        // envelope detector tables (N = 128 transform, windows, thresholds)
+  DevBuf env_buf[4];                 // scratch of vb200_envelope_search[_dev]
   DevBuf enc_buf[8];                 // scratch of vb200_encode_dsp_dev
   DevBuf enc_lane[3][16];            // per-lane device buffers of the pipelined vb200_encode_dsp
   cudaStream_t s_enc[3] = {nullptr, nullptr, nullptr};
@@ -149,6 +152,42 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     if ((rc = upload(c, h.wa.data(), h.wa.size(), &d.wa))) return rc;
     c->dwin.N[w] = h.N;
     c->dwin.win[w] = d.win;
+  }
+  {
+    // envelope detector lookups, _ve_envelope_init (lib/envelope.c:31-74)
+    HostXform h;
+    build_xform(h, ENV_N, nullptr);
+    EnvDev &E = c->env;
+    memset(&E, 0, sizeof(E));
+    XformDev &d = E.X;
+    d.N = h.N; d.log2n = h.log2n; d.nst = h.log2n - 6; d.nf = h.nf; d.scale = h.scale;
+    for (size_t i = 0; i < h.stage_off.size() && i < 8; i++) d.stage_off[i] = h.stage_off[i];
+    int rc;
+    if ((rc = upload(c, h.trig.data(), h.trig.size(), &d.trig))) return rc;
+    if ((rc = upload(c, h.bitrev.data(), h.bitrev.size(), &d.bitrev))) return rc;
+    const float *tw = nullptr;
+    if ((rc = upload(c, h.stage_tw.data(), h.stage_tw.size(), &tw))) return rc;
+    d.stage_tw = reinterpret_cast<const float2 *>(tw);
+    float win[ENV_N];
+    for (int i = 0; i < ENV_N; i++) {
+      win[i] = (float)std::sin(i / (ENV_N - 1.) * M_PI);
+      win[i] = win[i] * win[i];
+    }
+    if ((rc = upload(c, win, (size_t)ENV_N, &E.win))) return rc;
+    static const int B[VB200_VE_BANDS] = {2, 4, 6, 9, 13, 17, 22}, En[VB200_VE_BANDS] = {4, 5, 6, 8, 8, 8, 8};
+    float bwin[VB200_VE_BANDS * 8] = {0};
+    for (int j = 0; j < VB200_VE_BANDS; j++) {
+      float total = 0.f;
+      for (int i = 0; i < En[j]; i++) {
+        bwin[j * 8 + i] = (float)std::sin((i + .5) / En[j] * M_PI);
+        total = total + bwin[j * 8 + i];
+      }
+      E.total[j] = (float)(1. / (double)total);
+      E.begin[j] = B[j]; E.end[j] = En[j];
+      E.preecho[j] = s->preecho_thresh[j]; E.postecho[j] = s->postecho_thresh[j];
+    }
+    if ((rc = upload(c, bwin, (size_t)VB200_VE_BANDS * 8, &E.bwin))) return rc;
+    E.stretch_penalty = s->stretch_penalty; E.minenergy = s->preecho_minenergy;
   }
   {
     int rc;
@@ -269,6 +308,7 @@ extern "C" void vb200_ctx_destroy(vb200_ctx *c) {
   for (auto &l : c->lane_buf) for (auto &b : l) if (b.p) cudaFree(b.p);
   for (auto &st : c->s_lane) if (st) cudaStreamDestroy(st);
   for (auto &b : c->enc_buf) if (b.p) cudaFree(b.p);
+  for (auto &b : c->env_buf) if (b.p) cudaFree(b.p);
   for (auto &l : c->enc_lane) for (auto &b : l) if (b.p) cudaFree(b.p);
   for (auto &st : c->s_enc) if (st) cudaStreamDestroy(st);
   if (c->s_main) cudaStreamDestroy(c->s_main);
@@ -1603,6 +1643,82 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
   }
   for (auto &st : c->s_enc) CU(cudaStreamSynchronize(st));
   return 0;
+}
+
+// ======================================================================== //
+// envelope / block-switch detector
+static int env_check(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64_t stride, int first, int nsteps,
+                     const void *state, const void *ret) {
+  if (!pcm || !state || !ret) return fail(VB200_EINVAL, "envelope pointers");
+  if (nstreams <= 0 || nsteps < 0 || first < 0) return fail(VB200_EINVAL, "nstreams/steps");
+  if (fmt != VB200_PCM_F32_PLANAR && fmt != VB200_PCM_S16_INTERLEAVED) return fail(VB200_EINVAL, "pcm format");
+  if ((int64_t)ENV_STEP * ((int64_t)first + nsteps - 1) + ENV_N > stride && nsteps > 0)
+    return fail(VB200_EINVAL, "steps exceed the stream buffer");
+  (void)c;
+  return 0;
+}
+
+extern "C" int vb200_envelope_search_dev(vb200_ctx *c, int nstreams, const void *d_pcm, int fmt, int64_t stride,
+                                         int first_step, int nsteps, int32_t *d_state, uint8_t *d_ret, void *stream) {
+  CHECK_CTX(c);
+  int rc;
+  if ((rc = env_check(c, nstreams, d_pcm, fmt, stride, first_step, nsteps, d_state, d_ret))) return rc;
+  if (nsteps == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ch = c->setup.channels;
+  // bounded scratch: the spectra of at most ~4M (stream, channel, step) items at a time
+  long per_step = (long)nstreams * ch;
+  int chunk = (int)((1L << 22) / per_step);
+  if (chunk < 1) chunk = 1;
+  if (chunk > nsteps) chunk = nsteps;
+  void *p_t, *p_v;
+  if ((rc = ensure_buf(c->env_buf[0], sizeof(float) * (size_t)per_step * chunk, &p_t))) return rc;
+  if ((rc = ensure_buf(c->env_buf[1], sizeof(float) * (size_t)per_step * chunk * 32, &p_v))) return rc;
+  EnvSrc src; src.base = d_pcm; src.fmt = fmt; src.stride = stride; src.ch = ch;
+  for (int j0 = 0; j0 < nsteps; j0 += chunk) {
+    const int ns = nsteps - j0 < chunk ? nsteps - j0 : chunk;
+    const long items = per_step * ns;
+    const int grid = grid_for(c, (int)((items + ENV_WARPS - 1) / ENV_WARPS), 16);
+    k_env_spectrum<<<grid, 32 * ENV_WARPS, 0, st>>>(c->env, src, nstreams, first_step + j0, ns, (float *)p_t, (float *)p_v);
+    if ((rc = post_launch(c))) return rc;
+    k_env_filter<<<(nstreams + ENV_WARPS - 1) / ENV_WARPS, 32 * ENV_WARPS, 0, st>>>(
+        c->env, nstreams, ch, ns, nsteps, j0, (const float *)p_t, (const float *)p_v, d_state, d_ret);
+    if ((rc = post_launch(c))) return rc;
+  }
+  return 0;
+}
+
+extern "C" int vb200_envelope_search(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64_t stride,
+                                     int first_step, int nsteps, int32_t *state, uint8_t *ret) {
+  CHECK_CTX(c);
+  int rc;
+  if ((rc = env_check(c, nstreams, pcm, fmt, stride, first_step, nsteps, state, ret))) return rc;
+  if (nsteps == 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int ch = c->setup.channels;
+  const size_t pcm_bytes = (fmt == VB200_PCM_S16_INTERLEAVED ? sizeof(int16_t) : sizeof(float)) * (size_t)nstreams * ch * (size_t)stride;
+  const size_t st_bytes = sizeof(int32_t) * (size_t)nstreams * VB200_VE_STATE_WORDS(ch);
+  void *dp, *ds, *dr;
+  if ((rc = ensure_buf(c->env_buf[2], pcm_bytes, &dp))) return rc;
+  if ((rc = ensure_buf(c->env_buf[3], st_bytes + (size_t)nstreams * nsteps, &ds))) return rc;
+  dr = (char *)ds + st_bytes;
+  CU(cudaMemcpyAsync(dp, pcm, pcm_bytes, cudaMemcpyHostToDevice, c->s_main));
+  CU(cudaMemcpyAsync(ds, state, st_bytes, cudaMemcpyHostToDevice, c->s_main));
+  if ((rc = vb200_envelope_search_dev(c, nstreams, dp, fmt, stride, first_step, nsteps, (int32_t *)ds, (uint8_t *)dr, c->s_main))) return rc;
+  CU(cudaMemcpyAsync(state, ds, st_bytes, cudaMemcpyDeviceToHost, c->s_main));
+  CU(cudaMemcpyAsync(ret, dr, (size_t)nstreams * nsteps, cudaMemcpyDeviceToHost, c->s_main));
+  CU(cudaStreamSynchronize(c->s_main));
+  return 0;
+}
+
+// lib/envelope.c:254-264, replayed on the host from the per-step trigger bits (plain C, no CUDA)
+extern "C" void vb200_envelope_apply_marks(const uint8_t *ret, int first_step, int nsteps, int32_t *mark) {
+  for (int k = 0; k < nsteps; k++) {
+    const int j = first_step + k;
+    mark[j + 2] = 0;                                    // VE_POST
+    if (ret[k] & 1) { mark[j] = 1; mark[j + 1] = 1; }
+    if (ret[k] & 2) { mark[j] = 1; if (j > 0) mark[j - 1] = 1; }
+  }
 }
 
 // ======================================================================== //

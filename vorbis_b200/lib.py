@@ -32,6 +32,7 @@ EXPORTS = [
     "vb200_synthesis_dev", "vb200_synthesis", "vb200_decouple_dev", "vb200_decouple",
     "vb200_floor1_fit_dev", "vb200_floor1_fit", "vb200_floor1_render_dev", "vb200_floor1_render",
     "vb200_encode_dsp_dev", "vb200_encode_dsp",
+    "vb200_envelope_search_dev", "vb200_envelope_search", "vb200_envelope_apply_marks",
     "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
 ]
 
@@ -94,6 +95,10 @@ def load():
     L.vb200_floor1_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.vb200_encode_dsp_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO), vp]
     L.vb200_encode_dsp.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO)]
+    L.vb200_envelope_search_dev.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
+    L.vb200_envelope_search.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp]
+    L.vb200_envelope_apply_marks.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.vb200_envelope_apply_marks.restype = None
     L.vb200_malloc_device.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.vb200_free_device.argtypes = [vp, vp]
     L.vb200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -357,6 +362,38 @@ class Context:
     def encode_dsp_dev(self, W, nstreams, bps, io, blobno=7, stream=None):
         """io: abi.EncodeIO holding DEVICE pointers."""
         self._chk(self.L.vb200_encode_dsp_dev(self.h, W, nstreams, bps, blobno, C.byref(io), _ptr(stream)))
+
+    # ---- envelope / block-switch detector (lib/envelope.c) --------------------------------------
+    def envelope_search(self, pcm, first_step, nsteps, state=None, fmt=PCM_F32_PLANAR):
+        """Host buffers.  pcm: float [streams][ch][stride] (PCM_F32_PLANAR) or int16 [streams][stride][ch].
+        Returns (ret uint8 [streams][nsteps], state int32 [streams][ve_state_words])."""
+        ch = self.channels
+        if fmt == PCM_F32_PLANAR:
+            pcm = np.ascontiguousarray(pcm, np.float32)
+            ns, stride = pcm.shape[0], pcm.shape[2]
+            assert pcm.shape[1] == ch
+        else:
+            pcm = np.ascontiguousarray(pcm, np.int16)
+            ns, stride = pcm.shape[0], pcm.shape[1]
+            assert pcm.shape[2] == ch
+        state = (np.zeros((ns, abi.ve_state_words(ch)), np.int32) if state is None
+                 else np.array(state, np.int32).reshape(ns, abi.ve_state_words(ch)))
+        ret = np.zeros((ns, nsteps), np.uint8)
+        self._chk(self.L.vb200_envelope_search(self.h, ns, _ptr(pcm), fmt, stride, first_step, nsteps,
+                                               _ptr(state), _ptr(ret)))
+        return ret, state
+
+    def envelope_search_dev(self, nstreams, d_pcm, fmt, stride, first_step, nsteps, d_state, d_ret, stream=None):
+        self._chk(self.L.vb200_envelope_search_dev(self.h, nstreams, _ptr(d_pcm), fmt, stride, first_step, nsteps,
+                                                   _ptr(d_state), _ptr(d_ret), _ptr(stream)))
+
+    def envelope_marks(self, ret, first_step=0, mark=None):
+        """replay lib/envelope.c:254-264 for one stream's trigger bits (plain C helper, no GPU)"""
+        ret = np.ascontiguousarray(ret, np.uint8)
+        if mark is None:
+            mark = np.zeros(first_step + len(ret) + 2, np.int32)
+        self.L.vb200_envelope_apply_marks(_ptr(ret), first_step, len(ret), _ptr(mark))
+        return mark
 
     # ---- decode ------------------------------------------------------------------
     def decouple(self, W, res):
