@@ -1,7 +1,7 @@
 """Drop-in proof: the reference's own encoder and decoder (unmodified sources, real API loop)
-with lib/mapping0.c's hot callees bound to the CUDA library through the reference-signature
-shims (vorbis_b200/host/vb200_ref_shim.c) must produce byte-identical packets and bit-identical
-decoded PCM.  Needs oracle/_ref/*.so (built in the container where /root/reference exists;
+with lib/mapping0.c's hot callees AND lib/block.c's envelope search (the block-size decisions of
+vorbis_analysis_blockout) bound to the CUDA library through the reference-signature shims
+(vorbis_b200/host/vb200_ref_shim.c) must produce byte-identical packets and bit-identical decoded PCM.  Needs oracle/_ref/*.so (built in the container where /root/reference exists;
 the .so files travel to the GPU box)."""
 import numpy as np
 import pytest

@@ -8,6 +8,8 @@
  *   -D_vp_offset_and_mix=vb200shim_offset_and_mix
  *   -D_vp_couple_quantize_normalize=vb200shim_couple_quantize_normalize
  *   -Dfloor1_fit=vb200shim_floor1_fit
+ * and lib/block.c with
+ *   -D_ve_envelope_search=vb200shim_envelope_search
  * (or renames the callees in place); nothing else in libvorbis changes.  Every function
  * below has exactly the prototype of the reference function it replaces (cited), and
  * the same argument meaning, in-place behaviour and (absence of) error returns; a CUDA
@@ -31,6 +33,7 @@
 #include "smallft.h"
 #include "window.h"
 #include "psy.h"
+#include "envelope.h"
 
 #include "vorbis_b200.h"
 
@@ -106,6 +109,9 @@ int vb200shim_attach(vorbis_dsp_state *vd, int device){
   }
   s.window[0] = _vorbis_window_get(b->window[0]);
   s.window[1] = _vorbis_window_get(b->window[1]);
+  for(k = 0; k < VE_BANDS; k++){ s.preecho_thresh[k] = gi->preecho_thresh[k]; s.postecho_thresh[k] = gi->postecho_thresh[k]; }
+  s.stretch_penalty = gi->stretch_penalty;
+  s.preecho_minenergy = gi->preecho_minenergy;
   /* floors per submap (lib/mapping0.c:499-506); only encode-side floor 1 is bound */
   for(w = 0; w < 2 && w < ci->modes && vd->analysisp; w++){
     vorbis_info_mapping0 *m = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[w]->mapping];
@@ -226,4 +232,59 @@ int *vb200shim_floor1_fit(vorbis_block *vb, vorbis_look_floor1 *look, const floa
   out = (int*)_vorbis_block_alloc(vb, sizeof(*out) * look->posts);
   for(j = 0; j < look->posts; j++) out[j] = posts[j];
   return out;
+}
+
+/* _ve_envelope_search, lib/envelope.c:216-327.  The analysis loop (:232-267: _ve_amp on every new
+ * 64-sample step of every channel, the stretch logic, the marks) runs on the device; the walk of
+ * the cursor over the marks that picks the next block size (:269-327) is host control flow over a
+ * handful of ints and is restated here.  The filter state is handed over in the reference's own
+ * envelope_filter_state layout, so ve->filter / ve->stretch stay authoritative between calls.  */
+long vb200shim_envelope_search(vorbis_dsp_state *v){
+  vorbis_info *vi = v->vi;
+  codec_setup_info *ci = (codec_setup_info*)vi->codec_setup;
+  envelope_lookup *ve = ((private_state*)(v->backend_state))->ve;
+  long j;
+  int first = ve->current/ve->searchstep;
+  int last = v->pcm_current/ve->searchstep - VE_WIN;
+  if(first < 0) first = 0;
+  if(last + VE_WIN + VE_POST > ve->storage){                   /* :227-230 */
+    ve->storage = last + VE_WIN + VE_POST;
+    ve->mark = (int*)realloc(ve->mark, ve->storage*sizeof(*ve->mark));
+  }
+  if(last > first){
+    const int nsteps = last - first, ch = ve->ch;
+    const long len = (long)ve->searchstep*(nsteps - 1) + ve->winlength;
+    float *tmp = (float*)malloc(sizeof(float)*(size_t)ch*len);
+    int32_t *state = (int32_t*)malloc(sizeof(int32_t)*VB200_VE_STATE_WORDS(ch));
+    uint8_t *ret = (uint8_t*)malloc((size_t)nsteps);
+    int32_t *mark = (int32_t*)ve->mark;                        /* int == int32_t on every libvorbis target */
+    int c, rc;
+    for(c = 0; c < ch; c++) memcpy(tmp + (size_t)c*len, v->pcm[c] + (long)ve->searchstep*first, sizeof(float)*len);
+    state[0] = ve->stretch;
+    memcpy(state + 1, ve->filter, sizeof(envelope_filter_state)*VE_BANDS*ch);
+    rc = vb200_envelope_search(g.ctx, 1, tmp, VB200_PCM_F32_PLANAR, len, 0, nsteps, state, ret);
+    if(rc) shim_warn("envelope_search", rc);
+    else{
+      ve->stretch = state[0];
+      memcpy(ve->filter, state + 1, sizeof(envelope_filter_state)*VE_BANDS*ch);
+      vb200_envelope_apply_marks(ret, first, nsteps, mark);
+    }
+    free(tmp); free(state); free(ret);
+  }
+  ve->current = last*ve->searchstep;
+  {                                                            /* :269-327 */
+    long centerW = v->centerW;
+    long testW = centerW + ci->blocksizes[v->W]/4 + ci->blocksizes[1]/2 + ci->blocksizes[0]/4;
+    j = ve->cursor;
+    while(j < ve->current - ve->searchstep){
+      if(j >= testW) return 1;
+      ve->cursor = j;
+      if(ve->mark[j/ve->searchstep] && j > centerW){
+        ve->curmark = j;
+        return j >= testW ? 1 : 0;
+      }
+      j += ve->searchstep;
+    }
+  }
+  return -1;
 }
