@@ -375,6 +375,28 @@ int vb200_synthesis    (vb200_ctx*, int nstreams, int nblk, const int32_t *Wseq,
 int vb200_decouple_dev(vb200_ctx*, int W, int nblocks, float *d_res, void *stream);
 int vb200_decouple    (vb200_ctx*, int W, int nblocks, float *res);
 
+/* ---- decode: floor1_inverse2 (lib/floor1.c:1041-1086), the floor curve multiplied into the spectrum.
+ * data [rows][n] in place; posts [rows][VB200_FLOOR1_STRIDE] = fit_value[] as floor1_inverse1 returns it
+ * (:962-1039; unused posts carry bit 15); present[rows] = 0 where floor1_inverse1 returned NULL (the row
+ * is zeroed, :1084).  Rows and floor_sel as for vb200_floor1_fit.                                        */
+int vb200_floor1_inverse2_dev(vb200_ctx*, int W, int floor_sel, int nrows, const int32_t *d_posts,
+                              const int32_t *d_present, float *d_data, void *stream);
+int vb200_floor1_inverse2    (vb200_ctx*, int W, int floor_sel, int nrows, const int32_t *posts,
+                              const int32_t *present, float *data);
+
+/* ---- decode: everything of mapping0_inverse after the entropy decoders (lib/mapping0.c:754-795) plus
+ * the overlap-add of vorbis_synthesis_blockin, in one call: channel de-coupling, floor multiply,
+ * mdct_backward, windowed overlap-add.  Layout as vb200_synthesis; `res` holds the residue vectors as
+ * the residue backend leaves them and is modified in place; posts / present are
+ * [nstreams][nblk][ch][VB200_FLOOR1_STRIDE] and [nstreams][nblk][ch].  pcm_s16 != 0: the finished
+ * samples leave as interleaved int16 (as vb200_synthesis_s16_dev), else planar float.                   */
+int vb200_decode_dsp_dev(vb200_ctx*, int nstreams, int nblk, const int32_t *d_Wseq, const int64_t *d_coef_off,
+                         float *d_res, const int32_t *d_posts, const int32_t *d_present,
+                         const int64_t *d_pcm_off, void *d_pcm, int pcm_s16, int64_t pcm_stride, void *stream);
+int vb200_decode_dsp    (vb200_ctx*, int nstreams, int nblk, const int32_t *Wseq, const int64_t *coef_off,
+                         float *res, int64_t res_len, const int32_t *posts, const int32_t *present,
+                         const int64_t *pcm_off, void *pcm, int pcm_s16, int64_t pcm_stride);
+
 /* ---- device memory helpers for non-CUDA hosts (C callers) -------------- */
 int  vb200_malloc_device(vb200_ctx*, size_t bytes, void **dptr);
 int  vb200_free_device  (vb200_ctx*, void *dptr);

@@ -57,6 +57,8 @@ def lib():
         L.vbo_decouple.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p]
         L.vbo_floor1_fit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p, i32p, i32p]
         L.vbo_floor1_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i32p]
+        L.vbo_floor1_inverse2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, f32p]
+        L.vbo_decode_dsp.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i64p, f32p, i32p, i32p, i64p, f32p, C.c_int64]
         L.vbo_envelope_search.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int64, C.c_int, C.c_int, i32p, u8p]
         L.vbo_envelope_apply_marks.argtypes = [u8p, C.c_int, C.c_int, i32p]
         _lib = L
@@ -215,6 +217,27 @@ class Oracle:
                 iwork[sel], nonzero[sel] = iw, z
         a.update(posts=posts.reshape(nb, ch, -1), iwork=iwork, nonzero=nonzero)
         return a
+
+    def floor1_inverse2(self, W, posts, present, data, floor_sel=-1):
+        n = self.bs[W] // 2
+        posts = np.ascontiguousarray(posts, np.int32).reshape(-1, abi.FLOOR1_STRIDE)
+        present = np.ascontiguousarray(present, np.int32).reshape(-1)
+        data = np.array(data, np.float32).reshape(posts.shape[0], n)
+        self.L.vbo_floor1_inverse2(self.h, W, floor_sel, posts.shape[0], posts, present, data)
+        return data
+
+    def decode_dsp(self, Wseq, coef_off, res, posts, present, pcm_off, pcm_stride):
+        """de-couple + floor multiply + IMDCT + overlap-add (lib/mapping0.c:754-795, lib/block.c:767-823)"""
+        Wseq = np.ascontiguousarray(Wseq, np.int32)
+        ns, nblk = Wseq.shape
+        res = np.array(res, np.float32)
+        posts = np.ascontiguousarray(posts, np.int32)
+        present = np.ascontiguousarray(present, np.int32)
+        pcm = np.zeros((ns, self.channels, pcm_stride), np.float32)
+        self.L.vbo_decode_dsp(self.h, ns, nblk, Wseq, np.ascontiguousarray(coef_off, np.int64), res,
+                              posts.reshape(-1), present.reshape(-1), np.ascontiguousarray(pcm_off, np.int64),
+                              pcm, pcm_stride)
+        return pcm
 
     def envelope_search(self, pcm, first_step, nsteps, state=None):
         """pcm planar float [streams][ch][stride]; returns (ret uint8 [streams][nsteps], state words)"""

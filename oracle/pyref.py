@@ -101,6 +101,7 @@ def lib():
         L.ref_blockin_sequence.restype = C.c_long
         L.ref_blockin_sequence.argtypes = [C.c_void_p, C.c_int, i32p, f32p, C.c_int, f32p, C.c_long]
         L.ref_phaseA_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, f32p, f32p, f32p, f32p]
+        L.ref_floor1_inverse2.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i32p, f32p]
         L.ref_envelope_marks.restype = C.c_long
         L.ref_envelope_marks.argtypes = [C.c_void_p, f32p, C.c_long, i32p, C.c_long, C.c_void_p, f32p]
         L.ref_encode_dsp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, i32p, i32p, i32p, f32p]
@@ -248,6 +249,14 @@ class Ref:
         amp = np.empty(nb, np.float32)
         self.L.ref_phaseA_batch(self.h, W, nb, pcm, desc.ctypes.data, mdct, logmdct, logmask, amp)
         return mdct, logmdct, logmask, amp
+
+    def floor1_inverse2(self, W, posts, present, data):
+        """the reference's floor1_inverse2 (lib/floor1.c:1041) on rows [block][channel]"""
+        posts = np.ascontiguousarray(posts, np.int32).reshape(-1, 65)
+        present = np.ascontiguousarray(present, np.int32).reshape(-1)
+        data = np.array(data, np.float32).reshape(posts.shape[0], self.bs[W] // 2)
+        self.L.ref_floor1_inverse2(self.h, W, posts.shape[0], posts, present, data)
+        return data
 
     def envelope_marks(self, pcm):
         """pcm [ch][S] float -> (marks int32 [steps+2], steps, state words, stream [ch][bs1/2+S]) from the

@@ -791,3 +791,26 @@ long ref_envelope_marks(void *hv, const float *pcm, long nsamples, int32_t *mark
   vorbis_dsp_clear(&vd);
   return steps;
 }
+
+
+/* ---- decode floor: the reference's own floor1_inverse2 (static, lib/floor1.c:1041) through its
+ * export bundle, on a batch of rows laid out [block][channel]: row r uses the floor of channel
+ * r % channels of mode W.  fit [rows][65] = fit_value[] as floor1_inverse1 would return it,
+ * present[r] == 0 <=> memo NULL.                                                              */
+#include "backends.h"
+extern const vorbis_func_floor floor1_exportbundle;
+void ref_floor1_inverse2(void *hv, int W, int nrows, const int32_t *fit, const int32_t *present, float *data){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_info_mapping0 *info = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[W]->mapping];
+  int ch = h->vi.channels, n = (int)ci->blocksizes[W]/2, r, k;
+  int memo[65];
+  h->vb.W = W;
+  for(r=0;r<nrows;r++){
+    int c = r % ch;
+    vorbis_look_floor *look = b->flr[info->floorsubmap[info->chmuxlist[c]]];
+    for(k=0;k<65;k++) memo[k] = fit[(size_t)r*65+k];
+    floor1_exportbundle.inverse2(&h->vb, look, present[r] ? (void*)memo : NULL, data+(size_t)r*n);
+  }
+}

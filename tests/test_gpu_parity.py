@@ -690,3 +690,83 @@ def test_envelope_search_streams_vs_oracle(cfg, fmt):
     assert np.array_equal(d_ret.cpu().numpy(), want_ret) and np.array_equal(d_state.cpu().numpy(), want_state)
     with pytest.raises(vlib.VB200Error):
         ctx.envelope_search(src, 80, 20, fmt=f)          # runs past the stream buffer
+
+
+def _random_fit(rng, rows):
+    posts = rng.integers(0, 140, (rows, abi.FLOOR1_STRIDE)).astype(np.int32)
+    flag = rng.random(posts.shape) < 0.4
+    flag[:, :2] = False
+    posts[flag] |= 0x8000
+    return posts
+
+
+@pytest.mark.parametrize("W", [0, 1])
+def test_floor1_inverse2_vs_oracle(cfg, W):
+    """the decode-side floor multiply (lib/floor1.c:1041-1086)"""
+    name, setup, ctx, o, _, _ = cfg
+    rng = np.random.default_rng(40 + W)
+    n, rows = setup.blocksize(W) // 2, setup.channels * 9
+    posts = _random_fit(rng, rows)
+    posts[2, 7] = 400
+    posts[5, 0] = 999
+    present = (rng.random(rows) < 0.85).astype(np.int32)
+    data = (rng.standard_normal((rows, n)) * 5).astype(np.float32)
+    assert_bits_equal(ctx.floor1_inverse2(W, posts, present, data), o.floor1_inverse2(W, posts, present, data),
+                      "floor1_inverse2")
+
+
+@pytest.mark.parametrize("s16", [False, True])
+def test_decode_dsp_one_call_vs_oracle(cfg, s16):
+    """de-coupling + floor multiply + IMDCT + overlap-add in one call on packed mixed-size streams"""
+    name, setup, ctx, o, _, _ = cfg
+    ch = setup.channels
+    bs = [setup.blocksize(0), setup.blocksize(1)]
+    rng = np.random.default_rng(11)
+    ns, nblk = 5, 9
+    Wseq = rng.integers(0, 2, (ns, nblk)).astype(np.int32)
+    Wseq[0] = 1
+    Wseq[1] = 0
+    coef_off, pcm_off, coef_len, pcm_len = vlib.synthesis_layout(Wseq, bs, ch)
+    res = np.rint(rng.standard_normal(coef_len) * 3).astype(np.float32)        # residue backends leave integers
+    posts = _random_fit(rng, ns * nblk * ch).reshape(ns, nblk, ch, -1)
+    present = (rng.random((ns, nblk, ch)) < 0.9).astype(np.int32)
+    want = o.decode_dsp(Wseq, coef_off, res, posts, present, pcm_off, pcm_len)
+    got = ctx.decode_dsp(Wseq, coef_off, res, posts, present, pcm_off, pcm_len, s16=s16)
+    if s16:
+        w16 = np.clip(np.floor(want * np.float32(32767.0) + np.float32(0.5)), -32768, 32767).astype(np.int16)
+        assert np.array_equal(got, w16.transpose(0, 2, 1))
+    else:
+        assert_bits_equal(got, want, "decode_dsp pcm")
+
+
+def test_encode_then_decode_round_trip(cfg):
+    """size-independent property: what vb200_encode_dsp hands to the entropy coder (posts + quantised,
+    coupled residue), fed to vb200_decode_dsp as the entropy decoder would deliver it, reconstructs the
+    PCM (lossy codec: the reconstruction must track the input closely, and equal the oracle's)"""
+    name, setup, ctx, o, _, _ = cfg
+    W = 1
+    N, ch = setup.blocksize(W), setup.channels
+    hop, ns, bps = N // 2, 3, 8
+    stride = (bps - 1) * hop + N
+    rng = np.random.default_rng(8)
+    t = np.arange(stride)
+    pcm = np.stack([[0.05 * rng.standard_normal(stride) + 0.4 * np.sin(2 * np.pi * (300 + 90 * c + 40 * s) * t / setup.rate)
+                     for c in range(ch)] for s in range(ns)]).astype(np.float32)
+    desc = np.zeros(ns * bps, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = 1; desc["nW"] = 1; desc["blocktype"] = 1
+    enc = ctx.encode_dsp(W, pcm, desc, nstreams=ns, fmt=vlib.PCM_F32_PLANAR, hop=hop, independent=False)
+    Wseq = np.ones((ns, bps), np.int32)
+    coef_off, pcm_off, coef_len, pcm_len = vlib.synthesis_layout(Wseq, [setup.blocksize(0), N], ch)
+    res = enc["iwork"].astype(np.float32).reshape(-1)
+    assert res.size == coef_len
+    present = (enc["posts"][..., 0] != 0) | (enc["posts"][..., 1] != 0) | (enc["nonzero"] != 0)
+    got = ctx.decode_dsp(Wseq, coef_off, res, enc["posts"], present.astype(np.int32), pcm_off, pcm_len)
+    want = o.decode_dsp(Wseq, coef_off, res, enc["posts"], present.astype(np.int32), pcm_off, pcm_len)
+    assert_bits_equal(got, want, "round trip pcm")
+    # block k (k >= 1) finishes the samples between the centres of blocks k-1 and k: output sample i
+    # is stream sample N/2 + i (lib/block.c:767-823)
+    m = pcm_len
+    ref = pcm[:, :, N // 2:N // 2 + m]
+    err = got[:, :, :ref.shape[2]] - ref
+    snr = 10 * np.log10((ref ** 2).sum() / (err ** 2).sum())
+    assert snr > 10.0, "reconstruction SNR %.1f dB" % snr

@@ -195,3 +195,30 @@ def test_oracle_envelope_golden(name, oracle_lib):
     r1, s1 = o.envelope_search(env["stream"][None], 0, a)
     r2, s2 = o.envelope_search(env["stream"][None], a, steps - a, state=s1)
     assert np.array_equal(np.concatenate([r1, r2], 1), ret) and np.array_equal(s2, state)
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_oracle_encode_decode_round_trip(name, oracle_lib):
+    """the encode chain's posts + quantised residue, decoded by the decode chain (de-couple, floor multiply,
+    IMDCT, overlap-add), reconstruct the PCM: a whole-codec property no single stage test covers"""
+    from vorbis_b200 import abi
+    setup = load_setup(name)
+    o = oracle_lib.Oracle(setup)
+    N, ch = setup.blocksize(1), setup.channels
+    hop, ns, bps = N // 2, 2, 6
+    stride = (bps - 1) * hop + N
+    rng = np.random.default_rng(8)
+    t = np.arange(stride)
+    pcm = np.stack([[0.05 * rng.standard_normal(stride) + 0.4 * np.sin(2 * np.pi * (300 + 90 * c + 40 * s) * t / setup.rate)
+                     for c in range(ch)] for s in range(ns)]).astype(np.float32)
+    desc = np.zeros(ns * bps, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = 1; desc["nW"] = 1; desc["blocktype"] = 1
+    blocks = np.stack([pcm[s, :, k * hop:k * hop + N] for s in range(ns) for k in range(bps)])
+    enc = o.encode_dsp(1, blocks, desc, streams=(ns, bps))
+    Wseq = np.ones((ns, bps), np.int32)
+    coef_off, pcm_off, coef_len, pcm_len = vlib.synthesis_layout(Wseq, [setup.blocksize(0), N], ch)
+    present = ((enc["posts"][..., 0] != 0) | (enc["posts"][..., 1] != 0) | (enc["nonzero"] != 0)).astype(np.int32)
+    got = o.decode_dsp(Wseq, coef_off, enc["iwork"].astype(np.float32).reshape(-1), enc["posts"], present, pcm_off, pcm_len)
+    ref = pcm[:, :, N // 2:N // 2 + pcm_len]
+    err = got - ref
+    assert 10 * np.log10((ref ** 2).sum() / (err ** 2).sum()) > 10.0

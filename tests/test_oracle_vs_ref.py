@@ -186,3 +186,27 @@ def test_envelope_vs_reference(args, oracle_lib):
     assert np.array_equal(state[0], st)
     assert marks.sum() > 0
     r.close()
+
+
+@pytest.mark.parametrize("args", [(2, 44100, 0.5), (6, 48000, 0.2), (1, 22050, 0.3)], ids=lambda g: "ch%d_%d_q%g" % g)
+def test_floor1_inverse2_vs_reference(args, oracle_lib):
+    """decode-side floor: the reference's own floor1_inverse2 (through floor1_exportbundle) vs the
+    restatement, on random fit_value[] incl. unused posts (bit 15), out-of-range values (clamped,
+    lib/floor1.c:1056-1064) and absent floors (row zeroed)"""
+    ch, rate, q = args
+    r = pyref.Ref(ch, rate, q)
+    o = oracle_lib.Oracle(r.setup())
+    rng = np.random.default_rng(4)
+    for W in (0, 1):
+        n, rows = r.bs[W] // 2, ch * 7
+        posts = rng.integers(0, 140, (rows, abi.FLOOR1_STRIDE)).astype(np.int32)
+        flag = rng.random(posts.shape) < 0.4
+        flag[:, :2] = False
+        posts[flag] |= 0x8000
+        posts[3, 5] = 400
+        posts[4, 0] = 999
+        present = (rng.random(rows) < 0.85).astype(np.int32)
+        data = (rng.standard_normal((rows, n)) * 5).astype(np.float32)
+        assert_bits_equal(o.floor1_inverse2(W, posts, present, data), r.floor1_inverse2(W, posts, present, data),
+                          "floor1_inverse2 W=%d" % W)
+    r.close()

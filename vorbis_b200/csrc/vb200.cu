@@ -1646,6 +1646,90 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
 }
 
 // ======================================================================== //
+// decode: floor multiply and the fused decode chain
+extern "C" int vb200_floor1_inverse2_dev(vb200_ctx *c, int W, int floor_sel, int nrows, const int32_t *d_posts,
+                                         const int32_t *d_present, float *d_data, void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nrows <= 0) return 0;
+  if (!d_posts || !d_present || !d_data) return fail(VB200_EINVAL, "floor1_inverse2 pointers");
+  Floor1Args a; int rc;
+  if ((rc = floor1_args(c, W, floor_sel, nrows, &a))) return rc;
+  const int ctas = (nrows + F1_WARPS - 1) / F1_WARPS;
+  k_floor1_inverse2<<<grid_for(c, ctas, 8), 32 * F1_WARPS, 0, (cudaStream_t)stream>>>(a, d_posts, d_present, d_data, c->d_fromdB);
+  return post_launch(c);
+}
+
+extern "C" int vb200_floor1_inverse2(vb200_ctx *c, int W, int floor_sel, int nrows, const int32_t *posts,
+                                     const int32_t *present, float *data) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nrows <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t n = c->dx[W].N / 2;
+  HostIO io{c};
+  void *dp, *dz, *dd; int rc;
+  if ((rc = io.h2d(posts, sizeof(int32_t) * (size_t)nrows * VB200_FLOOR1_STRIDE, &dp))) return rc;
+  if ((rc = io.h2d(present, sizeof(int32_t) * (size_t)nrows, &dz))) return rc;
+  if ((rc = io.h2d(data, sizeof(float) * nrows * n, &dd))) return rc;
+  if ((rc = vb200_floor1_inverse2_dev(c, W, floor_sel, nrows, (const int32_t *)dp, (const int32_t *)dz, (float *)dd, c->s_main))) return rc;
+  if ((rc = io.d2h(data, dd, sizeof(float) * nrows * n))) return rc;
+  return io.sync();
+}
+
+extern "C" int vb200_decode_dsp_dev(vb200_ctx *c, int nstreams, int nblk, const int32_t *d_Wseq, const int64_t *d_coef_off,
+                                    float *d_res, const int32_t *d_posts, const int32_t *d_present,
+                                    const int64_t *d_pcm_off, void *d_pcm, int pcm_s16, int64_t pcm_stride, void *stream) {
+  CHECK_CTX(c);
+  if (nstreams <= 0 || nblk <= 0) return 0;
+  if (!d_Wseq || !d_coef_off || !d_res || !d_posts || !d_present || !d_pcm_off || !d_pcm)
+    return fail(VB200_EINVAL, "decode pointers");
+  const int ch = c->setup.channels;
+  DecodePrepArgs A;
+  for (int w = 0; w < 2; w++) {
+    for (int k = 0; k < ch; k++)
+      if (c->setup.floor1[w][c->setup.chmux[w][k]].posts <= 0)
+        return fail(VB200_EINVAL, "no floor1 setup for a channel's submap");
+    A.floors[w] = c->d_floor[w]; A.chmux[w] = c->d_chmux[w];
+    A.mag[w] = c->d_mag[w]; A.ang[w] = c->d_ang[w];
+    A.steps[w] = c->setup.coupling_steps[w]; A.n[w] = c->dx[w].N / 2;
+  }
+  A.ch = ch; A.nblk = nblk; A.nitems = (long)nstreams * nblk;
+  int rc;
+  k_decode_prepare<<<grid_for(c, (int)A.nitems, 8), 128, 0, (cudaStream_t)stream>>>(
+      A, d_Wseq, (const long long *)d_coef_off, d_res, d_posts, d_present, c->d_fromdB);
+  if ((rc = post_launch(c))) return rc;
+  if (pcm_s16) return vb200_synthesis_s16_dev(c, nstreams, nblk, d_Wseq, d_coef_off, d_res, d_pcm_off, (int16_t *)d_pcm, pcm_stride, stream);
+  return vb200_synthesis_dev(c, nstreams, nblk, d_Wseq, d_coef_off, d_res, d_pcm_off, (float *)d_pcm, pcm_stride, stream);
+}
+
+extern "C" int vb200_decode_dsp(vb200_ctx *c, int nstreams, int nblk, const int32_t *Wseq, const int64_t *coef_off,
+                                float *res, int64_t res_len, const int32_t *posts, const int32_t *present,
+                                const int64_t *pcm_off, void *pcm, int pcm_s16, int64_t pcm_stride) {
+  CHECK_CTX(c);
+  if (nstreams <= 0 || nblk <= 0) return 0;
+  if (!Wseq || !coef_off || !res || !posts || !present || !pcm_off || !pcm) return fail(VB200_EINVAL, "decode pointers");
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int ch = c->setup.channels;
+  const size_t nb = (size_t)nstreams * nblk;
+  for (size_t i = 0; i < nb; i++) if (Wseq[i] < 0 || Wseq[i] > 1) return fail(VB200_EINVAL, "Wseq values must be 0/1");
+  HostIO io{c};
+  void *dW, *dco, *dc, *dpo, *dp, *dps, *dpr; int rc;
+  if ((rc = io.h2d(Wseq, sizeof(int32_t) * nb, &dW))) return rc;
+  if ((rc = io.h2d(coef_off, sizeof(int64_t) * nb, &dco))) return rc;
+  if ((rc = io.h2d(res, sizeof(float) * (size_t)res_len, &dc))) return rc;
+  if ((rc = io.h2d(pcm_off, sizeof(int64_t) * nb, &dpo))) return rc;
+  const size_t pbytes = (pcm_s16 ? sizeof(int16_t) : sizeof(float)) * (size_t)nstreams * ch * (size_t)pcm_stride;
+  if ((rc = io.h2d(nullptr, pbytes, &dp))) return rc;
+  if ((rc = io.h2d(posts, sizeof(int32_t) * nb * ch * VB200_FLOOR1_STRIDE, &dps))) return rc;
+  if ((rc = io.h2d(present, sizeof(int32_t) * nb * ch, &dpr))) return rc;
+  CU(cudaMemsetAsync(dp, 0, pbytes, c->s_main));
+  if ((rc = vb200_decode_dsp_dev(c, nstreams, nblk, (const int32_t *)dW, (const int64_t *)dco, (float *)dc,
+                                 (const int32_t *)dps, (const int32_t *)dpr, (const int64_t *)dpo, dp, pcm_s16,
+                                 pcm_stride, c->s_main))) return rc;
+  if ((rc = io.d2h(pcm, dp, pbytes))) return rc;
+  return io.sync();
+}
+
+// ======================================================================== //
 // envelope / block-switch detector
 static int env_check(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64_t stride, int first, int nsteps,
                      const void *state, const void *ret) {

@@ -365,3 +365,131 @@ k_floor1_render(Floor1Args a, int32_t *__restrict__ posts, const int32_t *__rest
     if (lane == 0) nonzero[row] = 1;
   }
 }
+
+// ---- decode side: floor1_inverse2 (lib/floor1.c:1041-1086): the curve through the posts that
+// carry a value (fit_value[] as floor1_inverse1 leaves it: unused posts have bit 15 set), rendered
+// with render_line (:337-360, the same integer line as the encoder's render_line0) and multiplied
+// into the spectrum through FLOOR1_fromdB_LOOKUP; out-of-range values are clamped to 0..255 as
+// the reference guards them (:1056-1064).  One warp per (block, channel) row, in place.
+__device__ __forceinline__ void dev_floor1_inverse2_row(const Floor1Dev &F, const int32_t *__restrict__ fit,
+                                                        bool present, float *__restrict__ d, int n,
+                                                        const float *__restrict__ fromdB,
+                                                        short *segx, short *segy, int lane) {
+  if (!present) {                                        // memo == NULL: the channel is silent, :1084
+    for (int x = lane; x < n; x += 32) d[x] = 0.f;
+    return;
+  }
+  const int P = F.posts;
+  int nseg = 0;
+  __syncwarp();
+  if (lane == 0) {
+    int ly = fit[0] * F.mult;
+    ly = ly < 0 ? 0 : (ly > 255 ? 255 : ly);
+    segx[0] = 0; segy[0] = (short)ly;
+  }
+  for (int j0 = 1; j0 < P; j0 += 32) {
+    const int j = j0 + lane;
+    int used = 0, cur = 0, hy = 0;
+    if (j < P) {
+      cur = F.fwd[j];
+      const int fv = fit[cur];
+      hy = fv & 0x7fff;
+      used = hy == fv;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, used);
+    if (used) {
+      const int k = nseg + __popc(m & ((1u << lane) - 1)) + 1;
+      hy *= F.mult;
+      hy = hy < 0 ? 0 : (hy > 255 ? 255 : hy);
+      segx[k] = F.postlist[cur];
+      segy[k] = (short)hy;
+    }
+    nseg += __popc(m);
+  }
+  __syncwarp();
+  for (int k = 0; k < nseg; k++) {
+    const int lx = segx[k], hx = segx[k + 1];
+    const F1Line L(lx, hx, segy[k], segy[k + 1]);
+    const int lim = hx < n ? hx : n;
+    for (int x = lx + lane; x < lim; x += 32) d[x] = d[x] * __ldg(fromdB + L.at(x));
+  }
+  {
+    const int hx = segx[nseg];
+    const float f = __ldg(fromdB + segy[nseg]);
+    for (int x = hx + lane; x < n; x += 32) d[x] = d[x] * f;
+  }
+}
+
+__global__ void __launch_bounds__(32 * F1_WARPS)
+k_floor1_inverse2(Floor1Args a, const int32_t *__restrict__ posts, const int32_t *__restrict__ present,
+                  float *__restrict__ data, const float *__restrict__ fromdB) {
+  __shared__ Floor1Dev sF[VB200_MAX_SUBMAPS];
+  __shared__ short s_segx[F1_WARPS][VB200_VIF_POSIT + 3];
+  __shared__ short s_segy[F1_WARPS][VB200_VIF_POSIT + 3];
+  {
+    const int words = (int)(sizeof(Floor1Dev) * VB200_MAX_SUBMAPS / 4);
+    const int *src = reinterpret_cast<const int *>(a.floors);
+    int *dst = reinterpret_cast<int *>(sF);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long row = (long)blockIdx.x * F1_WARPS + warp; row < a.nrows; row += (long)gridDim.x * F1_WARPS) {
+    const int sel = a.floor_sel >= 0 ? a.floor_sel : a.chmux[row % a.channels];
+    dev_floor1_inverse2_row(sF[sel], posts + (size_t)row * VB200_FLOOR1_STRIDE, present[row] != 0,
+                            data + (size_t)row * a.n, a.n, fromdB, s_segx[warp], s_segy[warp], lane);
+  }
+}
+
+// ---- decode, fused front half of mapping0_inverse for packed mixed-size streams: one CTA per
+// (stream, block): channel de-coupling (lib/mapping0.c:754-779, last step first) then the floor
+// multiply of every channel (:781-790), in place on the residue vectors; k_synthesis follows.
+struct DecodePrepArgs {
+  const Floor1Dev *floors[2];          // per block size
+  const unsigned char *chmux[2];
+  const int *mag[2], *ang[2];
+  int steps[2], n[2];
+  int ch, nblk;
+  long nitems;                         // nstreams * nblk
+};
+
+__global__ void __launch_bounds__(128)
+k_decode_prepare(DecodePrepArgs A, const int *__restrict__ Wseq, const long long *__restrict__ coef_off,
+                 float *__restrict__ res, const int32_t *__restrict__ posts, const int32_t *__restrict__ present,
+                 const float *__restrict__ fromdB) {
+  __shared__ Floor1Dev sF[2][VB200_MAX_SUBMAPS];
+  __shared__ short s_segx[4][VB200_VIF_POSIT + 3];
+  __shared__ short s_segy[4][VB200_VIF_POSIT + 3];
+  for (int w = 0; w < 2; w++) {
+    const int words = (int)(sizeof(Floor1Dev) * VB200_MAX_SUBMAPS / 4);
+    const int *src = reinterpret_cast<const int *>(A.floors[w]);
+    int *dst = reinterpret_cast<int *>(sF[w]);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long it = blockIdx.x; it < A.nitems; it += gridDim.x) {
+    const int W = Wseq[it] ? 1 : 0, n = A.n[W];
+    float *base = res + coef_off[it];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      for (int s = A.steps[W] - 1; s >= 0; s--) {
+        float *pM = base + (size_t)A.mag[W][s] * n + j, *pA = base + (size_t)A.ang[W][s] * n + j;
+        const float m = *pM, a = *pA;
+        if (m > 0.f) {
+          if (a > 0.f) { *pM = m; *pA = m - a; }
+          else         { *pA = m; *pM = m + a; }
+        } else {
+          if (a > 0.f) { *pM = m; *pA = m + a; }
+          else         { *pA = m; *pM = m - a; }
+        }
+      }
+    }
+    __syncthreads();
+    for (int c = warp; c < A.ch; c += 4) {
+      const size_t row = (size_t)it * A.ch + c;
+      dev_floor1_inverse2_row(sF[W][A.chmux[W][c]], posts + row * VB200_FLOOR1_STRIDE, present[row] != 0,
+                              base + (size_t)c * n, n, fromdB, s_segx[warp], s_segy[warp], lane);
+    }
+    __syncthreads();
+  }
+}

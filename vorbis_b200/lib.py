@@ -33,6 +33,7 @@ EXPORTS = [
     "vb200_floor1_fit_dev", "vb200_floor1_fit", "vb200_floor1_render_dev", "vb200_floor1_render",
     "vb200_encode_dsp_dev", "vb200_encode_dsp",
     "vb200_envelope_search_dev", "vb200_envelope_search", "vb200_envelope_apply_marks",
+    "vb200_floor1_inverse2_dev", "vb200_floor1_inverse2", "vb200_decode_dsp_dev", "vb200_decode_dsp",
     "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
 ]
 
@@ -95,6 +96,10 @@ def load():
     L.vb200_floor1_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.vb200_encode_dsp_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO), vp]
     L.vb200_encode_dsp.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO)]
+    L.vb200_floor1_inverse2_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    L.vb200_floor1_inverse2.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.vb200_decode_dsp_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int64, vp]
+    L.vb200_decode_dsp.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int, C.c_int64]
     L.vb200_envelope_search_dev.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp, vp]
     L.vb200_envelope_search.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp]
     L.vb200_envelope_apply_marks.argtypes = [vp, C.c_int, C.c_int, vp]
@@ -362,6 +367,33 @@ class Context:
     def encode_dsp_dev(self, W, nstreams, bps, io, blobno=7, stream=None):
         """io: abi.EncodeIO holding DEVICE pointers."""
         self._chk(self.L.vb200_encode_dsp_dev(self.h, W, nstreams, bps, blobno, C.byref(io), _ptr(stream)))
+
+    # ---- decode: floor multiply and the whole decode DSP in one call ----------------------------
+    def floor1_inverse2(self, W, posts, present, data, floor_sel=-1):
+        """floor1_inverse2 (lib/floor1.c:1041): rows [block][channel] of n floats, multiplied in place"""
+        n = self.bs[W] // 2
+        posts = np.ascontiguousarray(posts, np.int32).reshape(-1, abi.FLOOR1_STRIDE)
+        present = np.ascontiguousarray(present, np.int32).reshape(-1)
+        data = np.array(data, np.float32).reshape(posts.shape[0], n)
+        self._chk(self.L.vb200_floor1_inverse2(self.h, W, floor_sel, posts.shape[0], _ptr(posts), _ptr(present),
+                                               _ptr(data)))
+        return data
+
+    def decode_dsp(self, Wseq, coef_off, res, posts, present, pcm_off, pcm_stride, s16=False):
+        """de-couple + floor multiply + IMDCT + overlap-add in one call; layout as synthesis()"""
+        Wseq = np.ascontiguousarray(Wseq, np.int32)
+        ns, nblk = Wseq.shape
+        res = np.array(res, np.float32)
+        posts = np.ascontiguousarray(posts, np.int32)
+        present = np.ascontiguousarray(present, np.int32)
+        coef_off = np.ascontiguousarray(coef_off, np.int64)
+        pcm_off = np.ascontiguousarray(pcm_off, np.int64)
+        pcm = (np.zeros((ns, pcm_stride, self.channels), np.int16) if s16
+               else np.zeros((ns, self.channels, pcm_stride), np.float32))
+        self._chk(self.L.vb200_decode_dsp(self.h, ns, nblk, _ptr(Wseq), _ptr(coef_off), _ptr(res), res.size,
+                                          _ptr(posts), _ptr(present), _ptr(pcm_off), _ptr(pcm), 1 if s16 else 0,
+                                          pcm_stride))
+        return pcm
 
     # ---- envelope / block-switch detector (lib/envelope.c) --------------------------------------
     def envelope_search(self, pcm, first_step, nsteps, state=None, fmt=PCM_F32_PLANAR):
