@@ -245,6 +245,27 @@ def extra_configs(torch, lib, abi, device, peak):
     out["decode_4096streams_x33blocks_mixed"] = {"ms": ms, "stereo_blocks_per_s": ns * nblk / ms * 1e3,
                                                   "algorithmic_GBps": byts / ms / 1e6,
                                                   "frac_of_hbm_peak": byts / ms / 1e6 / peak}
+    # the whole decode DSP in one call (de-couple + floor multiply + IMDCT + overlap-add, int16 out)
+    posts = torch.randint(0, 120, (ns * nblk * s44.channels, abi.FLOOR1_STRIDE), generator=g, device=dev, dtype=torch.int32)
+    present = torch.ones(ns * nblk * s44.channels, dtype=torch.int32, device=dev)
+    pcm16 = torch.zeros((ns, pcm_len, s44.channels), dtype=torch.int16, device=dev)
+    res0 = coef.clone()
+
+    def dec():
+        coef.copy_(res0)                              # the chain works in place on the residue
+        c44.L.vb200_decode_dsp_dev(c44.h, ns, nblk, dW.data_ptr(), dco.data_ptr(), coef.data_ptr(), posts.data_ptr(),
+                                   present.data_ptr(), dpo.data_ptr(), pcm16.data_ptr(), 1, pcm_len, stream)
+    ms_d = timed(dec) - timed(lambda: coef.copy_(res0))
+    out["decode_dsp_4096streams_x33blocks_mixed_s16"] = {"ms": ms_d, "stereo_blocks_per_s": ns * nblk / ms_d * 1e3}
+    # envelope / block-switch detector, 1000 stereo streams x 800 steps (= 50 long blocks each), int16 PCM
+    nse, steps = 1000, 800
+    stride_e = 64 * (steps - 1) + 128
+    pe = torch.randint(-8000, 8000, (nse, stride_e, s44.channels), generator=g, device=dev, dtype=torch.int16)
+    st_e = torch.zeros((nse, abi.ve_state_words(s44.channels)), dtype=torch.int32, device=dev)
+    ret_e = torch.zeros((nse, steps), dtype=torch.uint8, device=dev)
+    ms_e = timed(lambda: c44.envelope_search_dev(nse, pe.data_ptr(), lib.PCM_S16_INTERLEAVED, stride_e, 0, steps,
+                                                 st_e.data_ptr(), ret_e.data_ptr(), stream=stream))
+    out["envelope_search_1000streams_x800steps_s16"] = {"ms": ms_e, "long_block_equivalents_per_s": nse * steps / 16 / ms_e * 1e3}
     # Phase A alone through vb200_analysis_phaseA with float host buffers (the round-1 e2e figure, kept for
     # continuity: 16 KB in + 24.6 KB out per block instead of 4 KB + 8.4 KB for the one-call chain)
     nb, N, chn = 20000, bs[1], s44.channels

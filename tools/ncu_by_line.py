@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an ncu report's per-SASS-instruction counters by CUDA source line.
 
-usage: tools/ncu_by_line.py <report.ncu-rep> <kernel-name-substring> [lib.so] [top]
+usage: tools/ncu_by_line.py <report.ncu-rep> <kernel-name-substring> [lib.so] [top] [cubin-symbol-substring]
 Needs -lineinfo at compile time.  Joins `ncu --page source --csv` (SASS rows) with the
 line table printed by `nvdisasm -g` for the same cubin (the built .so must match the report).
 """
@@ -16,6 +16,7 @@ from collections import defaultdict
 rep, kname = sys.argv[1], sys.argv[2]
 so = sys.argv[3] if len(sys.argv) > 3 else os.path.join(os.path.dirname(__file__), "..", "vorbis_b200", "libvorbis_b200.so")
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+cname = sys.argv[5] if len(sys.argv) > 5 else kname   # mangled-name substring in the cubin (template instances)
 
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
@@ -24,7 +25,7 @@ dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture
 lines = dis.split("\n")
 start = None
 for i, l in enumerate(lines):
-    if l.startswith(".text.") and kname in l:
+    if l.startswith(".text.") and cname in l:
         start = i
         break
 assert start is not None, "kernel not found in cubin"
