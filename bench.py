@@ -79,6 +79,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def count(self):
+        return len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -347,12 +350,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                  # nvidia-smi needs ~0.1 s before its first line: start it ahead of the warm-up
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.lines.clear()            # keep only samples taken from here on (timed region + same-load tail)
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -362,7 +367,14 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
+    if rank == 0:
+        # the timed region is ~0.1 s: keep the same load running (untimed) until a few clock samples exist
+        t_end = time.time() + 2.0
+        while sampler.count() < 4 and time.time() < t_end:
+            step()
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    barrier()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

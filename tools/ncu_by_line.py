@@ -47,11 +47,13 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-n
 rows = list(csv.reader(out.split("\n")))
 hdr = None
 data = []
+seen = set()
 for r in rows:
     if r and r[0] == "Address":
         hdr = r
         continue
-    if hdr and len(r) == len(hdr):
+    if hdr and len(r) == len(hdr) and r[0] not in seen:
+        seen.add(r[0])
         data.append(r)
 ci = {h: i for i, h in enumerate(hdr)}
 base = int(data[0][ci["Address"]], 16)

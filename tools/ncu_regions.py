@@ -1,16 +1,17 @@
 #!/usr/bin/env python
 """List the hot SASS regions of a kernel in an ncu report with the CUDA source lines they come from.
-usage: tools/ncu_regions.py <report.ncu-rep> <kernel-substring-in-cubin-symbol> <matching lib.so> [rows] [min_exec]
+usage: tools/ncu_regions.py <report.ncu-rep> <kernel-substring-in-cubin-symbol> <matching lib.so> [rows] [min_exec] [cubin-symbol-substring]
 The .so MUST be the build the report was captured from."""
 import csv, os, re, subprocess, sys, tempfile
 rep, kname, so = sys.argv[1:4]
 rows_n = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
 thr = float(sys.argv[5]) if len(sys.argv) > 5 else 2e5
+cname = sys.argv[6] if len(sys.argv) > 6 else kname   # mangled-name substring in the cubin (template instances)
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(dis) if l.startswith(".text.") and kname in l][0]
+start = [i for i, l in enumerate(dis) if l.startswith(".text.") and cname in l][0]
 off2 = {}
 cur = None
 for l in dis[start + 1:]:
@@ -27,11 +28,13 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "rege
 rows = list(csv.reader(out.split("\n")))
 hdr = None
 data = []
+seen = set()
 for r in rows:
     if r and r[0] == "Address":
         hdr = r
         continue
-    if hdr and len(r) == len(hdr):
+    if hdr and len(r) == len(hdr) and r[0] not in seen:
+        seen.add(r[0])
         data.append(r)
 ci = {h: i for i, h in enumerate(hdr)}
 base = int(data[0][ci["Address"]], 16)
