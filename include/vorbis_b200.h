@@ -89,6 +89,17 @@ typedef struct vb200_floor1_setup {
   float   twofitweight, twofitatten;
 } vb200_floor1_setup;
 
+/* Residue partition classification parameters of one submap: vorbis_info_residue0 (lib/backends.h:103-118)
+ * + the residue type (codec_setup_info.residue_type).  Only what res{0,1,2}_class read.              */
+typedef struct vb200_residue_setup {
+  int32_t type;                           /* 0, 1 or 2; -1 = not provided                          */
+  int32_t begin, end;                     /* in samples (type 2: interleaved samples of the bundle) */
+  int32_t grouping;                       /* samples per partition                                  */
+  int32_t partitions;                     /* number of partition classes                            */
+  int32_t classmetric1[64];
+  int32_t classmetric2[64];
+} vb200_residue_setup;
+
 /* Everything the kernels need from codec_setup_info / private_state
  * (lib/codec_internal.h:59-133) for one (channels, rate, quality) setup.    */
 typedef struct vb200_setup {
@@ -123,6 +134,8 @@ typedef struct vb200_setup {
   float   postecho_thresh[VB200_VE_BANDS];
   float   stretch_penalty;
   float   preecho_minenergy;
+  /* residue of submap sm of mode W: residue_param[ mapping.residuesubmap[sm] ] (lib/mapping0.c:663) */
+  vb200_residue_setup residue[2][VB200_MAX_SUBMAPS];
 } vb200_setup;
 
 /* Per-block inputs of mapping0_forward that are not PCM (lib/mapping0.c:230-252) */
@@ -268,6 +281,23 @@ int vb200_couple_quantize_normalize_dev(vb200_ctx*, int W, int blocktype, int bl
 int vb200_couple_quantize_normalize    (vb200_ctx*, int W, int blocktype, int blobno, int nblocks,
                                         const float *mdct, int32_t *iwork, int32_t *nonzero);
 
+/* ---- residue partition classification: res1_class / res2_class (lib/res0.c:745-778)
+ * -> _01class (:412-474) / _2class (:479-532), called per submap as mapping0_forward does (:660-672).
+ * iwork   [nblocks][ch][n] quantised residue (what vb200_couple_quantize_normalize leaves)
+ * nonzero [nblocks][ch]
+ * classes [nblocks][ch][class_stride] int32 partition classes (the reference's partword):
+ *   residue type 0/1: row of channel c holds partword of that channel, valid where nonzero[c] (the
+ *     reference compacts the used channels of a submap: partword[u] = row of the u-th used channel);
+ *   residue type 2: ONE vector per submap, stored in the row of the submap's first channel, valid if any
+ *     channel of the submap is nonzero (the reference then classifies the whole bundle, :769-778).
+ *   Rows that are not valid and entries past partvals = (end-begin)/grouping are 0.
+ * class_stride >= vb200_residue_partvals(ctx, W) (the largest partvals over the mode's submaps).    */
+int vb200_residue_partvals(vb200_ctx*, int W);
+int vb200_residue_classify_dev(vb200_ctx*, int W, int nblocks, const int32_t *d_iwork, const int32_t *d_nonzero,
+                               int32_t *d_classes, int class_stride, void *stream);
+int vb200_residue_classify    (vb200_ctx*, int W, int nblocks, const int32_t *iwork, const int32_t *nonzero,
+                               int32_t *classes, int class_stride);
+
 /* ---- the whole per-block encode DSP of mapping0_forward in ONE call ---------------------------
  * lib/mapping0.c:230-646 with the bit packing and the residue backend left to the caller:
  *   window, MDCT, FFT, log spectra, ampmax (:254-346)  ->  noise / tone masks, offset_and_mix(1)
@@ -315,6 +345,8 @@ typedef struct vb200_encode_io {
   float *logmdct;
   float *logmask;
   int32_t *overflow;              /* VB200_IWORK_S16 only: [nblocks] values that did not fit */
+  int32_t *classes;               /* optional [nblocks][ch][class_stride]: vb200_residue_classify of the residue */
+  int64_t class_stride;
 } vb200_encode_io;
 /* every pointer in *d_io is a device pointer; the struct itself is host memory */
 int vb200_encode_dsp_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream, int blobno,

@@ -59,6 +59,8 @@ def lib():
         L.vbo_floor1_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p, i32p]
         L.vbo_floor1_inverse2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, i32p, i32p, f32p]
         L.vbo_decode_dsp.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i64p, f32p, i32p, i32p, i64p, f32p, C.c_int64]
+        L.vbo_residue_partvals.argtypes = [C.c_void_p, C.c_int]
+        L.vbo_residue_classify.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int]
         L.vbo_envelope_search.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int64, C.c_int, C.c_int, i32p, u8p]
         L.vbo_envelope_apply_marks.argtypes = [u8p, C.c_int, C.c_int, i32p]
         _lib = L
@@ -217,6 +219,18 @@ class Oracle:
                 iwork[sel], nonzero[sel] = iw, z
         a.update(posts=posts.reshape(nb, ch, -1), iwork=iwork, nonzero=nonzero)
         return a
+
+    def residue_partvals(self, W):
+        return int(self.L.vbo_residue_partvals(self.h, W))
+
+    def residue_classify(self, W, iwork, nonzero, stride=None):
+        ch, n = self.channels, self.bs[W] // 2
+        iwork = np.ascontiguousarray(iwork, np.int32).reshape(-1, ch, n)
+        nonzero = np.ascontiguousarray(nonzero, np.int32).reshape(-1, ch)
+        stride = self.residue_partvals(W) if stride is None else stride
+        classes = np.zeros((iwork.shape[0], ch, stride), np.int32)
+        self.L.vbo_residue_classify(self.h, W, iwork.shape[0], iwork, nonzero, classes, stride)
+        return classes
 
     def floor1_inverse2(self, W, posts, present, data, floor_sel=-1):
         n = self.bs[W] // 2

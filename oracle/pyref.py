@@ -101,6 +101,7 @@ def lib():
         L.ref_blockin_sequence.restype = C.c_long
         L.ref_blockin_sequence.argtypes = [C.c_void_p, C.c_int, i32p, f32p, C.c_int, f32p, C.c_long]
         L.ref_phaseA_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, f32p, f32p, f32p, f32p]
+        L.ref_residue_classify.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int]
         L.ref_floor1_inverse2.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i32p, f32p]
         L.ref_envelope_marks.restype = C.c_long
         L.ref_envelope_marks.argtypes = [C.c_void_p, f32p, C.c_long, i32p, C.c_long, C.c_void_p, f32p]
@@ -249,6 +250,15 @@ class Ref:
         amp = np.empty(nb, np.float32)
         self.L.ref_phaseA_batch(self.h, W, nb, pcm, desc.ctypes.data, mdct, logmdct, logmask, amp)
         return mdct, logmdct, logmask, amp
+
+    def residue_classify(self, W, iwork, nonzero, stride):
+        """the reference's res{0,1,2}_class per submap (lib/mapping0.c:660-672) on [block][ch][n] ints"""
+        ch, n = self.channels, self.bs[W] // 2
+        iwork = np.ascontiguousarray(iwork, np.int32).reshape(-1, ch, n)
+        nonzero = np.ascontiguousarray(nonzero, np.int32).reshape(-1, ch)
+        classes = np.zeros((iwork.shape[0], ch, stride), np.int32)
+        self.L.ref_residue_classify(self.h, W, iwork.shape[0], iwork, nonzero, classes, stride)
+        return classes
 
     def floor1_inverse2(self, W, posts, present, data):
         """the reference's floor1_inverse2 (lib/floor1.c:1041) on rows [block][channel]"""

@@ -198,8 +198,18 @@ int ref_get_setup(void *hv, vb200_setup *s){
     if(m->submaps > VB200_MAX_SUBMAPS) return -1;
     s->submaps[w] = m->submaps;
     for(k=0;k<h->vi.channels;k++) s->chmux[w][k] = (uint8_t)m->chmuxlist[k];
+    for(sm=0;sm<VB200_MAX_SUBMAPS;sm++) s->residue[w][sm].type = -1;
     for(sm=0;sm<m->submaps;sm++){
       int fl = m->floorsubmap[sm];
+      {
+        int rn = m->residuesubmap[sm];
+        vorbis_info_residue0 *ri = (vorbis_info_residue0*)ci->residue_param[rn];
+        vb200_residue_setup *o = &s->residue[w][sm];
+        o->type = ci->residue_type[rn];
+        o->begin = (int32_t)ri->begin; o->end = (int32_t)ri->end;
+        o->grouping = ri->grouping; o->partitions = ri->partitions;
+        for(k=0;k<64;k++){ o->classmetric1[k] = ri->classmetric1[k]; o->classmetric2[k] = ri->classmetric2[k]; }
+      }
       if(ci->floor_type[fl]==1){
         vorbis_info_floor1 *fi = (vorbis_info_floor1*)ci->floor_param[fl];
         vorbis_look_floor1 *lk = (vorbis_look_floor1*)b->flr[fl];
@@ -813,4 +823,50 @@ void ref_floor1_inverse2(void *hv, int W, int nrows, const int32_t *fit, const i
     for(k=0;k<65;k++) memo[k] = fit[(size_t)r*65+k];
     floor1_exportbundle.inverse2(&h->vb, look, present[r] ? (void*)memo : NULL, data+(size_t)r*n);
   }
+}
+
+
+/* ---- residue classification: the reference's own res{0,1,2}_class through _residue_P[] exactly as
+ * mapping0_forward calls it per submap (lib/mapping0.c:660-672), on a batch laid out [block][ch][n].
+ * classes [block][ch][stride], written in the layout documented for vb200_residue_classify.      */
+void ref_residue_classify(void *hv, int W, int nblocks, const int32_t *iwork, const int32_t *nonzero,
+                          int32_t *classes, int stride){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_info_mapping0 *info = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[W]->mapping];
+  int ch = h->vi.channels, n = (int)ci->blocksizes[W]/2, blk, i, j, k;
+  int **bundle = (int**)malloc(sizeof(*bundle)*ch);
+  int *zb = (int*)malloc(sizeof(int)*ch), *chan = (int*)malloc(sizeof(int)*ch);
+  int *copy = (int*)malloc(sizeof(int)*(size_t)ch*n);
+  h->vb.W = W; h->vb.pcmend = 2*n;
+  memset(classes,0,sizeof(int32_t)*(size_t)nblocks*ch*stride);
+  for(blk=0;blk<nblocks;blk++){
+    memcpy(copy,iwork+(size_t)blk*ch*n,sizeof(int)*(size_t)ch*n);
+    for(i=0;i<info->submaps;i++){
+      int cib=0, resnum=info->residuesubmap[i], type=ci->residue_type[resnum];
+      vorbis_info_residue0 *ri=(vorbis_info_residue0*)ci->residue_param[resnum];
+      int partvals=(int)((ri->end-ri->begin)/ri->grouping);
+      long **pw;
+      for(j=0;j<ch;j++) if(info->chmuxlist[j]==i){
+        zb[cib]=nonzero[(size_t)blk*ch+j]?1:0; chan[cib]=j; bundle[cib++]=copy+(size_t)j*n;
+      }
+      pw=_residue_P[type]->class(&h->vb,b->residue[resnum],bundle,zb,cib);
+      if(pw){
+        if(type==2){
+          int32_t *dst=classes+((size_t)blk*ch+chan[0])*stride;
+          for(k=0;k<partvals;k++) dst[k]=(int32_t)pw[0][k];
+        }else{
+          int u=0;
+          for(j=0;j<cib;j++) if(zb[j]){
+            int32_t *dst=classes+((size_t)blk*ch+chan[j])*stride;
+            for(k=0;k<partvals;k++) dst[k]=(int32_t)pw[u][k];
+            u++;
+          }
+        }
+      }
+    }
+    _vorbis_block_ripcord(&h->vb);
+  }
+  free(bundle); free(zb); free(chan); free(copy);
 }

@@ -58,6 +58,9 @@ void vbo_floor1_inverse2(vbo_ctx *c, int W, int floor_sel, int nrows, const int3
 void vbo_decode_dsp(vbo_ctx *c, int nstreams, int nblk, const int32_t *Wseq, const int64_t *coef_off,
                     float *res, const int32_t *posts, const int32_t *present,
                     const int64_t *pcm_off, float *pcm, int64_t pcm_stride);
+int  vbo_residue_partvals(vbo_ctx *c, int W);
+void vbo_residue_classify(vbo_ctx *c, int W, int nblocks, const int32_t *iwork, const int32_t *nonzero,
+                          int32_t *classes, int stride);
 void vbo_envelope_search(vbo_ctx *c, int nstreams, const float *pcm, int64_t stride, int first_step,
                          int nsteps, int32_t *state, uint8_t *ret);
 void vbo_envelope_apply_marks(const uint8_t *ret, int first_step, int nsteps, int32_t *mark);

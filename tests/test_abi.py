@@ -29,7 +29,7 @@ def test_struct_sizes_match_header():
     pyoracle.build()
     assert ctypes.sizeof(abi.BlockDesc) == 16
     assert ctypes.sizeof(abi.PhaseAIO) == 10 * ctypes.sizeof(ctypes.c_void_p)
-    assert ctypes.sizeof(abi.EncodeIO) == 112          # static_assert in vorbis_b200/csrc/vb200.cu
+    assert ctypes.sizeof(abi.EncodeIO) == 128          # static_assert in vorbis_b200/csrc/vb200.cu
     # vb200_psy_setup: 2 ints, 7 floats(2+3+1+1), int, 40 floats, float, 3 ints, pad, double, 4 ints, float, pad, 5 ptrs
     assert ctypes.sizeof(abi.PsySetup) % 8 == 0
 

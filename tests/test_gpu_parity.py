@@ -770,3 +770,42 @@ def test_encode_then_decode_round_trip(cfg):
     err = got[:, :, :ref.shape[2]] - ref
     snr = 10 * np.log10((ref ** 2).sum() / (err ** 2).sum())
     assert snr > 10.0, "reconstruction SNR %.1f dB" % snr
+
+
+@pytest.mark.parametrize("W", [0, 1])
+def test_residue_classify_vs_oracle(cfg, W):
+    """residue partition classification (lib/res0.c:412-532) per submap"""
+    name, setup, ctx, o, enc, _ = cfg
+    ch, n = setup.channels, setup.blocksize(W) // 2
+    rng = np.random.default_rng(14 + W)
+    nb = 40
+    mag = np.exp(rng.uniform(-2, 3, (nb, ch, 1))) * np.exp(-np.arange(n) / (n / 4.0))[None, None, :]
+    iwork = np.rint(rng.standard_normal((nb, ch, n)) * mag).astype(np.int32)
+    nonzero = (rng.random((nb, ch)) < 0.8).astype(np.int32)
+    nonzero[3] = 0
+    assert ctx.residue_partvals(W) == o.residue_partvals(W) > 0
+    got = ctx.residue_classify(W, iwork, nonzero)
+    assert np.array_equal(got, o.residue_classify(W, iwork, nonzero))
+    wide = ctx.residue_classify(W, iwork, nonzero, stride=ctx.residue_partvals(W) + 5)
+    assert np.array_equal(wide[:, :, :got.shape[2]], got) and not wide[:, :, got.shape[2]:].any()
+    with pytest.raises(vlib.VB200Error):
+        ctx.residue_classify(W, iwork, nonzero, stride=ctx.residue_partvals(W) - 1)
+    # on the reference's own residue vectors
+    tag = "L" if W else "S"
+    if len(enc[tag + "_blocktype"]):
+        iw, nz = enc[tag + "_iwork_out"], enc[tag + "_nonzero_out"]
+        assert np.array_equal(ctx.residue_classify(W, iw, nz), o.residue_classify(W, iw, nz))
+
+
+def test_encode_dsp_with_classes(cfg, monkeypatch):
+    """the one-call chain can hand back the partition classes too (int32 or int16 residue)"""
+    name, setup, ctx, o, enc, _ = cfg
+    monkeypatch.setenv("VB200_CHUNK_BLOCKS", "2")
+    desc = make_desc(enc, "L")
+    want = o.encode_dsp(1, enc["L_pcm"], desc)
+    wcls = o.residue_classify(1, want["iwork"], want["nonzero"])
+    got = ctx.encode_dsp(1, enc["L_pcm"], desc, classes=True)
+    assert np.array_equal(got["classes"], wcls) and np.array_equal(got["iwork"], want["iwork"])
+    if not (setup.channels & (setup.channels - 1)):
+        got = ctx.encode_dsp(1, enc["L_pcm"], desc, classes=True, iwork_s16=True)
+        assert np.array_equal(got["classes"], wcls)

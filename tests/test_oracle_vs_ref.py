@@ -210,3 +210,28 @@ def test_floor1_inverse2_vs_reference(args, oracle_lib):
         assert_bits_equal(o.floor1_inverse2(W, posts, present, data), r.floor1_inverse2(W, posts, present, data),
                           "floor1_inverse2 W=%d" % W)
     r.close()
+
+
+@pytest.mark.parametrize("args", [(2, 44100, 0.5), (1, 44100, 0.4), (6, 48000, 0.2), (1, 22050, 0.3), (2, 44100, 0.1)],
+                         ids=lambda g: "ch%d_%d_q%g" % g)
+def test_residue_classify_vs_reference(args, oracle_lib):
+    """res1_class / res2_class through the reference's own _residue_P[] (per submap, as mapping0_forward
+    calls them) vs the restatement; residue types 1 and 2, the 5.1 setup's two submaps and 30-sample
+    partitions, silent channels and silent bundles"""
+    ch, rate, q = args
+    r = pyref.Ref(ch, rate, q)
+    o = oracle_lib.Oracle(r.setup())
+    rng = np.random.default_rng(13)
+    for W in (0, 1):
+        n, nb = r.bs[W] // 2, 6
+        mag = np.exp(rng.uniform(-2, 3, (nb, ch, 1))) * np.exp(-np.arange(n) / (n / 4.0))[None, None, :]
+        iwork = np.rint(rng.standard_normal((nb, ch, n)) * mag).astype(np.int32)
+        nonzero = (rng.random((nb, ch)) < 0.8).astype(np.int32)
+        nonzero[1] = 0
+        st = o.residue_partvals(W)
+        assert st > 0
+        a = o.residue_classify(W, iwork, nonzero)
+        b = r.residue_classify(W, iwork, nonzero, st)
+        assert np.array_equal(a, b)
+        assert a.max() > 0 and not a[1].any()
+    r.close()

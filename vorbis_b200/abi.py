@@ -74,6 +74,13 @@ class Floor1Setup(C.Structure):
     ]
 
 
+class ResidueSetup(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32), ("begin", C.c_int32), ("end", C.c_int32), ("grouping", C.c_int32),
+        ("partitions", C.c_int32), ("classmetric1", C.c_int32 * 64), ("classmetric2", C.c_int32 * 64),
+    ]
+
+
 class Setup(C.Structure):
     _fields_ = [
         ("channels", C.c_int32),
@@ -97,6 +104,7 @@ class Setup(C.Structure):
         ("postecho_thresh", C.c_float * VE_BANDS),
         ("stretch_penalty", C.c_float),
         ("preecho_minenergy", C.c_float),
+        ("residue", (ResidueSetup * MAX_SUBMAPS) * 2),
     ]
 
 
@@ -148,6 +156,8 @@ class EncodeIO(C.Structure):
         ("logmdct", C.c_void_p),
         ("logmask", C.c_void_p),
         ("overflow", C.c_void_p),
+        ("classes", C.c_void_p),
+        ("class_stride", C.c_int64),
     ]
 
 
@@ -203,6 +213,18 @@ class SetupHolder:
                 s.submaps[w] = int(a["submaps"][w])
                 for k in range(cm.shape[1]):
                     s.chmux[w][k] = int(cm[w][k])
+        for w in range(2):
+            for sm in range(MAX_SUBMAPS):
+                s.residue[w][sm].type = -1
+                pre = "residue_%d_%d_" % (w, sm)
+                if pre + "type" not in a:
+                    continue
+                rs = s.residue[w][sm]
+                for nm in ("type", "begin", "end", "grouping", "partitions"):
+                    setattr(rs, nm, int(_sc(a[pre + nm])))
+                for k in range(64):
+                    rs.classmetric1[k] = int(a[pre + "classmetric1"][k])
+                    rs.classmetric2[k] = int(a[pre + "classmetric2"][k])
         if "env_preecho_thresh" in a:
             for k in range(VE_BANDS):
                 s.preecho_thresh[k] = float(a["env_preecho_thresh"][k])
@@ -293,6 +315,16 @@ class SetupHolder:
         for w in range(2):
             if s.window[w]:
                 a["window%d" % w] = np.ctypeslib.as_array(s.window[w], shape=(s.blocksizes[w] // 2,)).copy()
+        for w in range(2):
+            for sm in range(MAX_SUBMAPS):
+                rs = s.residue[w][sm]
+                if rs.type < 0 or rs.grouping <= 0:
+                    continue
+                pre = "residue_%d_%d_" % (w, sm)
+                for nm in ("type", "begin", "end", "grouping", "partitions"):
+                    a[pre + nm] = np.int32(getattr(rs, nm))
+                a[pre + "classmetric1"] = np.array(list(rs.classmetric1), np.int32)
+                a[pre + "classmetric2"] = np.array(list(rs.classmetric2), np.int32)
         a["env_preecho_thresh"] = np.array(list(s.preecho_thresh), np.float32)
         a["env_postecho_thresh"] = np.array(list(s.postecho_thresh), np.float32)
         a["env_stretch_penalty"] = np.float32(s.stretch_penalty)

@@ -21,6 +21,7 @@
 #include "vb200_psy2.cuh"
 #include "vb200_floor1.cuh"
 #include "vb200_env.cuh"
+#include "vb200_res.cuh"
 #include "floor1_db_table.h"
 
 using namespace vb200;
@@ -64,10 +65,12 @@ struct vb200_ctx {
   DevBuf scratch[16];
   DevBuf lane_buf[2][10];            // per-lane device buffers of the pipelined host Phase-A path
   cudaStream_t s_lane[2] = {nullptr, nullptr};
+  const ResDev *d_res[2] = {nullptr, nullptr};        // [VB200_MAX_SUBMAPS] residue class parameters per block size
+  int res_partvals[2] = {0, 0};
   EnvDev env;                        // envelope detector tables (N = 128 transform, windows, thresholds)
   DevBuf env_buf[4];                 // scratch of vb200_envelope_search[_dev]
   DevBuf enc_buf[8];                 // scratch of vb200_encode_dsp_dev
-  DevBuf enc_lane[3][16];            // per-lane device buffers of the pipelined vb200_encode_dsp
+  DevBuf enc_lane[3][17];            // per-lane device buffers of the pipelined vb200_encode_dsp
   cudaStream_t s_enc[3] = {nullptr, nullptr, nullptr};
   int psy_ctas_per_sm = 5;
   const float *d_fromdB = nullptr;
@@ -152,6 +155,25 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     if ((rc = upload(c, h.wa.data(), h.wa.size(), &d.wa))) return rc;
     c->dwin.N[w] = h.N;
     c->dwin.win[w] = d.win;
+  }
+  for (int w = 0; w < 2; w++) {      // residue classification parameters (lib/backends.h:103-118)
+    ResDev hr[VB200_MAX_SUBMAPS];
+    memset(hr, 0, sizeof(hr));
+    for (int sm = 0; sm < VB200_MAX_SUBMAPS; sm++) {
+      const vb200_residue_setup &r = s->residue[w][sm];
+      ResDev &d = hr[sm];
+      d.type = -1;
+      if (r.type < 0 || r.grouping <= 0) continue;         // not provided (zero-initialised setups: grouping 0)
+      if (r.type > 2 || r.begin < 0 || r.end < r.begin || r.partitions < 1 || r.partitions > 64)
+        return fail(VB200_EINVAL, "residue setup");
+      d.type = r.type; d.begin = r.begin; d.end = r.end; d.grouping = r.grouping; d.partitions = r.partitions;
+      d.partvals = (r.end - r.begin) / r.grouping;
+      d.scale = (float)(100. / r.grouping);
+      for (int k = 0; k < 64; k++) { d.cm1[k] = r.classmetric1[k]; d.cm2[k] = r.classmetric2[k]; }
+      if (d.partvals > c->res_partvals[w]) c->res_partvals[w] = d.partvals;
+    }
+    int rc;
+    if ((rc = upload(c, hr, (size_t)VB200_MAX_SUBMAPS, &c->d_res[w]))) return rc;
   }
   {
     // envelope detector lookups, _ve_envelope_init (lib/envelope.c:31-74)
@@ -1480,7 +1502,7 @@ extern "C" int vb200_floor1_render(vb200_ctx *c, int W, int floor_sel, int nrows
 
 // ======================================================================== //
 // the whole per-block encode DSP (Phase A -> floor1 fit -> floor render -> Phase B)
-static_assert(sizeof(vb200_encode_io) == 112, "vb200_encode_io layout (mirrored by vorbis_b200/abi.py)");
+static_assert(sizeof(vb200_encode_io) == 128, "vb200_encode_io layout (mirrored by vorbis_b200/abi.py)");
 struct EncScratch {
   float *mdct, *logmdct, *logmask, *logfft, *lmax, *gmax;
   int32_t *fitnz;
@@ -1554,6 +1576,8 @@ static int encode_launch(vb200_ctx *c, int W, int nstreams, int bps, int blobno,
   if ((rc = cqn_setup(c, W, 0, blobno, &Q0))) return rc;
   if ((rc = cqn_setup(c, W, 1, blobno, &Q1))) return rc;
   if ((rc = cqn_launch(c, Q0, Q1, d->desc, nblocks, S.mdct, iw, d->nonzero, st))) return rc;
+  if (d->classes &&
+      (rc = vb200_residue_classify_dev(c, W, nblocks, iw, d->nonzero, d->classes, (int)d->class_stride, st))) return rc;
   if (s16) {
     const int n = c->dx[W].N / 2;
     const long nvec = (long)rows * n / 4;
@@ -1625,6 +1649,10 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
     const size_t isz = s16 ? sizeof(int16_t) : sizeof(int32_t);
     if ((rc = ensure_buf(B[13], isz * (size_t)cs * bps * ch * n, &p))) return rc; d.iwork = p;
     if (s16) { if ((rc = ensure_buf(B[15], sizeof(int32_t) * (size_t)cs * bps, &p))) return rc; d.overflow = (int32_t *)p; }
+    if (h->classes) {
+      if ((rc = ensure_buf(B[16], sizeof(int32_t) * (size_t)cs * bps * ch * (size_t)h->class_stride, &p))) return rc;
+      d.classes = (int32_t *)p;
+    }
     if ((rc = ensure_buf(B[14], sizeof(float) * (size_t)cs * bps, &p))) return rc; d.ampmax_out = (float *)p;
     EncScratch S;
     if ((rc = enc_scratch(B, (size_t)cs * bps * ch, (size_t)cs * bps, n, nullptr, s16, &S))) return rc;
@@ -1636,6 +1664,8 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
     CU(cudaMemcpyAsync(h->nonzero + r0, d.nonzero, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync((char *)h->iwork + isz * r0 * n, d.iwork, isz * rows * n, cudaMemcpyDeviceToHost, st));
     if (s16) CU(cudaMemcpyAsync(h->overflow + b0, d.overflow, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, st));
+    if (h->classes) CU(cudaMemcpyAsync(h->classes + r0 * (size_t)h->class_stride, d.classes,
+                                       sizeof(int32_t) * rows * (size_t)h->class_stride, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->ampmax_out + b0, d.ampmax_out, sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
     if (h->mdct) CU(cudaMemcpyAsync(h->mdct + r0 * n, S.mdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
     if (h->logmdct) CU(cudaMemcpyAsync(h->logmdct + r0 * n, S.logmdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
@@ -1643,6 +1673,58 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
   }
   for (auto &st : c->s_enc) CU(cudaStreamSynchronize(st));
   return 0;
+}
+
+// ======================================================================== //
+// residue partition classification
+extern "C" int vb200_residue_partvals(vb200_ctx *c, int W) {
+  if (!c || W < 0 || W > 1) return VB200_EINVAL;
+  return c->res_partvals[W];
+}
+
+extern "C" int vb200_residue_classify_dev(vb200_ctx *c, int W, int nblocks, const int32_t *d_iwork,
+                                          const int32_t *d_nonzero, int32_t *d_classes, int class_stride, void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nblocks <= 0) return 0;
+  if (!d_iwork || !d_nonzero || !d_classes) return fail(VB200_EINVAL, "residue_classify pointers");
+  if (c->res_partvals[W] <= 0) return fail(VB200_EINVAL, "no residue setup for this block size");
+  if (class_stride < c->res_partvals[W]) return fail(VB200_EINVAL, "class_stride < partvals");
+  const int ch = c->setup.channels, n = c->dx[W].N / 2, submaps = c->setup.submaps[W] > 0 ? c->setup.submaps[W] : 1;
+  for (int sm = 0; sm < submaps; sm++) {                   // the reads must stay inside the rows
+    const vb200_residue_setup &r = c->setup.residue[W][sm];
+    if (r.type < 0 || r.grouping <= 0) continue;
+    int cib = 0;
+    for (int k = 0; k < ch; k++) if (c->setup.chmux[W][k] == sm) cib++;
+    const long reach = r.type == 2 ? (cib ? r.begin / cib + (long)((r.end - r.begin) / r.grouping) * ((r.grouping + cib - 1) / cib) : 0)
+                                   : (long)r.begin + (long)((r.end - r.begin) / r.grouping) * r.grouping;
+    if (reach > n) return fail(VB200_EINVAL, "residue range exceeds the block");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(d_classes, 0, sizeof(int32_t) * (size_t)nblocks * ch * class_stride, st));
+  ResArgs A;
+  A.res = c->d_res[W]; A.chmux = c->d_chmux[W]; A.ch = ch; A.n = n; A.submaps = submaps; A.nblocks = nblocks;
+  A.stride = class_stride;
+  const long tasks = (long)nblocks * submaps;
+  k_residue_classify<<<grid_for(c, (int)((tasks + RES_WARPS - 1) / RES_WARPS), 16), 32 * RES_WARPS, 0, st>>>(
+      A, d_iwork, d_nonzero, d_classes);
+  return post_launch(c);
+}
+
+extern "C" int vb200_residue_classify(vb200_ctx *c, int W, int nblocks, const int32_t *iwork, const int32_t *nonzero,
+                                      int32_t *classes, int class_stride) {
+  CHECK_CTX(c); CHECK_W(W);
+  if (nblocks <= 0) return 0;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const size_t ch = c->setup.channels, n = c->dx[W].N / 2;
+  HostIO io{c};
+  void *di, *dz, *dc; int rc;
+  if ((rc = io.h2d(iwork, sizeof(int32_t) * nblocks * ch * n, &di))) return rc;
+  if ((rc = io.h2d(nonzero, sizeof(int32_t) * nblocks * ch, &dz))) return rc;
+  if ((rc = io.h2d(nullptr, sizeof(int32_t) * nblocks * ch * (size_t)(class_stride > 0 ? class_stride : 1), &dc))) return rc;
+  if ((rc = vb200_residue_classify_dev(c, W, nblocks, (const int32_t *)di, (const int32_t *)dz, (int32_t *)dc,
+                                       class_stride, c->s_main))) return rc;
+  if ((rc = io.d2h(classes, dc, sizeof(int32_t) * nblocks * ch * (size_t)class_stride))) return rc;
+  return io.sync();
 }
 
 // ======================================================================== //

@@ -118,8 +118,18 @@ int vb200shim_attach(vorbis_dsp_state *vd, int device){
     if(m->submaps > VB200_MAX_SUBMAPS) continue;
     s.submaps[w] = m->submaps;
     for(k = 0; k < vi->channels; k++) s.chmux[w][k] = (uint8_t)m->chmuxlist[k];
+    for(j = 0; j < VB200_MAX_SUBMAPS; j++) s.residue[w][j].type = -1;
     for(j = 0; j < m->submaps; j++){
       int fl = m->floorsubmap[j];
+      {                                               /* residue class parameters of the submap, lib/mapping0.c:663 */
+        int rn = m->residuesubmap[j];
+        vorbis_info_residue0 *ri = (vorbis_info_residue0*)ci->residue_param[rn];
+        vb200_residue_setup *o = &s.residue[w][j];
+        o->type = ci->residue_type[rn];
+        o->begin = (int32_t)ri->begin; o->end = (int32_t)ri->end;
+        o->grouping = ri->grouping; o->partitions = ri->partitions;
+        for(i = 0; i < 64; i++){ o->classmetric1[i] = ri->classmetric1[i]; o->classmetric2[i] = ri->classmetric2[i]; }
+      }
       if(ci->floor_type[fl] == 1){
         vorbis_info_floor1 *fi = (vorbis_info_floor1*)ci->floor_param[fl];
         vorbis_look_floor1 *lk = (vorbis_look_floor1*)b->flr[fl];

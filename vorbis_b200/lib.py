@@ -34,6 +34,7 @@ EXPORTS = [
     "vb200_encode_dsp_dev", "vb200_encode_dsp",
     "vb200_envelope_search_dev", "vb200_envelope_search", "vb200_envelope_apply_marks",
     "vb200_floor1_inverse2_dev", "vb200_floor1_inverse2", "vb200_decode_dsp_dev", "vb200_decode_dsp",
+    "vb200_residue_partvals", "vb200_residue_classify_dev", "vb200_residue_classify",
     "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
 ]
 
@@ -96,6 +97,9 @@ def load():
     L.vb200_floor1_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.vb200_encode_dsp_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO), vp]
     L.vb200_encode_dsp.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO)]
+    L.vb200_residue_partvals.argtypes = [vp, C.c_int]
+    L.vb200_residue_classify_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
+    L.vb200_residue_classify.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int]
     L.vb200_floor1_inverse2_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.vb200_floor1_inverse2.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.vb200_decode_dsp_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int64, vp]
@@ -319,7 +323,7 @@ class Context:
 
     # ---- whole per-block encode DSP (Phase A -> floor1 -> Phase B) in one call ---------------
     def encode_dsp(self, W, pcm, desc, nstreams=None, fmt=0, hop=0, ampmax0=None, independent=None, blobno=7,
-                   floats=False, iwork_s16=False):
+                   floats=False, iwork_s16=False, classes=False):
         """Host buffers.  fmt 0: pcm [nblocks][ch][N] float; PCM_F32_PLANAR: [streams][ch][stride] float;
         PCM_S16_INTERLEAVED: [streams][stride][ch] int16.  nstreams None = every block its own stream.
         independent None = True when the blocks are not grouped in streams."""
@@ -356,6 +360,9 @@ class Context:
         if iwork_s16:
             io.iwork_fmt = IWORK_S16
             out["overflow"] = np.full(nb, -1, np.int32)
+        if classes:
+            io.class_stride = self.residue_partvals(W)
+            out["classes"] = np.full((nb, ch, int(io.class_stride)), -1, np.int32)
         if floats:
             for k in ("mdct", "logmdct", "logmask"):
                 out[k] = np.zeros((nb, ch, n), np.float32)
@@ -367,6 +374,24 @@ class Context:
     def encode_dsp_dev(self, W, nstreams, bps, io, blobno=7, stream=None):
         """io: abi.EncodeIO holding DEVICE pointers."""
         self._chk(self.L.vb200_encode_dsp_dev(self.h, W, nstreams, bps, blobno, C.byref(io), _ptr(stream)))
+
+    # ---- residue partition classification (lib/res0.c:412-532) --------------------------------
+    def residue_partvals(self, W):
+        return int(self.L.vb200_residue_partvals(self.h, W))
+
+    def residue_classify(self, W, iwork, nonzero, stride=None):
+        ch, n = self.channels, self.bs[W] // 2
+        iwork = np.ascontiguousarray(iwork, np.int32).reshape(-1, ch, n)
+        nonzero = np.ascontiguousarray(nonzero, np.int32).reshape(-1, ch)
+        stride = self.residue_partvals(W) if stride is None else stride
+        classes = np.full((iwork.shape[0], ch, stride), -1, np.int32)
+        self._chk(self.L.vb200_residue_classify(self.h, W, iwork.shape[0], _ptr(iwork), _ptr(nonzero), _ptr(classes),
+                                                stride))
+        return classes
+
+    def residue_classify_dev(self, W, nblocks, d_iwork, d_nonzero, d_classes, stride, stream=None):
+        self._chk(self.L.vb200_residue_classify_dev(self.h, W, nblocks, _ptr(d_iwork), _ptr(d_nonzero), _ptr(d_classes),
+                                                    stride, _ptr(stream)))
 
     # ---- decode: floor multiply and the whole decode DSP in one call ----------------------------
     def floor1_inverse2(self, W, posts, present, data, floor_sel=-1):
