@@ -4,6 +4,7 @@
 Bit-exact for every stage: the kernels execute the reference's arithmetic DAG with
 FMA contraction off (tolerance stated by north_star is 1e-4 relative; we hold 0)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -809,3 +810,43 @@ def test_encode_dsp_with_classes(cfg, monkeypatch):
     if not (setup.channels & (setup.channels - 1)):
         got = ctx.encode_dsp(1, enc["L_pcm"], desc, classes=True, iwork_s16=True)
         assert np.array_equal(got["classes"], wcls)
+
+
+def test_encode_dsp_dev_split_half_batches(cfg, monkeypatch):
+    """vb200_encode_dsp_dev run as two concurrent half-batches (VB200_SPLIT=2): same results"""
+    import torch
+    name, setup, ctx, o, _, _ = cfg
+    monkeypatch.setenv("VB200_SPLIT", os.environ.get("VB200_TEST_SPLIT", "2"))
+    monkeypatch.setenv("VB200_SPLIT_MIN", "1")
+    W = 1
+    N, ch = setup.blocksize(W), setup.channels
+    n, hop, ns, bps = N // 2, N // 2, 5, 3
+    stride = (bps - 1) * hop + N
+    rng = np.random.default_rng(31)
+    s16 = np.clip(7000 * rng.standard_normal((ns, stride, ch)), -32768, 32767).astype(np.int16)
+    planar = np.ascontiguousarray((s16.astype(np.float32) / np.float32(32768.0)).transpose(0, 2, 1))
+    blocks = np.stack([planar[s, :, k * hop:k * hop + N] for s in range(ns) for k in range(bps)])
+    desc = np.zeros(ns * bps, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = 1; desc["nW"] = 1; desc["blocktype"] = rng.integers(0, 2, ns * bps)
+    amp0 = rng.uniform(-30, -3, ns).astype(np.float32)
+    want = o.encode_dsp(W, blocks, desc, streams=(ns, bps), ampmax0=amp0)
+    wcls = o.residue_classify(W, want["iwork"], want["nonzero"])
+    dev = torch.device("cuda")
+    nb = ns * bps
+    t = {"pcm": torch.from_numpy(s16).to(dev),
+         "desc": torch.from_numpy(desc.view(np.uint8).reshape(-1, 16).copy()).to(dev),
+         "ampmax0": torch.from_numpy(amp0).to(dev),
+         "posts": torch.zeros((nb, ch, abi.FLOOR1_STRIDE), dtype=torch.int32, device=dev),
+         "nonzero": torch.zeros((nb, ch), dtype=torch.int32, device=dev),
+         "iwork": torch.zeros((nb, ch, n), dtype=torch.int32, device=dev),
+         "ampmax_out": torch.zeros(nb, device=dev),
+         "classes": torch.zeros((nb, ch, ctx.residue_partvals(W)), dtype=torch.int32, device=dev)}
+    io = abi.EncodeIO()
+    for k, v in t.items():
+        setattr(io, k, v.data_ptr())
+    io.pcm_fmt, io.hop, io.stream_stride, io.class_stride = vlib.PCM_S16_INTERLEAVED, hop, stride, ctx.residue_partvals(W)
+    ctx.encode_dsp_dev(W, ns, bps, io, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = {k: t[k].cpu().numpy() for k in ("posts", "nonzero", "iwork", "ampmax_out")}
+    _enc_compare(got, want, "split halves")
+    assert np.array_equal(t["classes"].cpu().numpy(), wcls)
