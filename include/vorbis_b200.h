@@ -17,6 +17,9 @@
  *   - functions ending in _dev take DEVICE pointers and a cudaStream_t passed
  *     as void* (NULL = legacy default stream) and are asynchronous;
  *     the others take HOST pointers, copy in/out and synchronise.
+ *   - a context keeps grow-only device scratch: use one context per host thread
+ *     (the reference is single threaded per vorbis_dsp_state as well);
+ *     the host-pointer entry points serialise on a per-context mutex.
  */
 #ifndef VORBIS_B200_H
 #define VORBIS_B200_H
