@@ -482,6 +482,15 @@ struct PcmSrc {
   long long stride;        // samples per channel per stream
 };
 
+// the FFT ping-pong buffer is idle during the MDCT: it takes the padded fly output
+__device__ __forceinline__ float *getenv_free_pad(float *sf) {
+#ifdef VB200_NO_FLY_PAD
+  (void)sf; return nullptr;
+#else
+  return sf;
+#endif
+}
+
 template <int NC>
 __global__ void __launch_bounds__(256)
 k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
@@ -517,7 +526,7 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
       dev_load_windowed(Wd, W, lW, nW, pf, sx, tid, nt);
     }
     __syncthreads();
-    dev_mdct_forward<NC>(X, sx, sw, mdct + (size_t)row * n, tid, nt);
+    dev_mdct_forward<NC>(X, sx, sw, mdct + (size_t)row * n, tid, nt, getenv_free_pad(sf));
     const float *f = dev_drft_forward<NC>(X, sx, sf, tid, nt);
     // log spectrum + local maximum (lib/mapping0.c:310-345)
     float mx = -1e30f;

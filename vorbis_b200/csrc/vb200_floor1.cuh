@@ -210,15 +210,25 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
       }
 #pragma unroll
       for (int k = 0; k < F1_ACC; k++) s[k] = __reduce_add_sync(0xffffffffu, s[k]);
-      if (lane < 6) {                                    // what fit_line adds for this gap, chain = lane
-        int va = s[0], vb = s[6];
+      if (lane < F1_ACC) {                               // raw sums; turned into fit_line's terms below
+        int v = s[0];
 #pragma unroll
-        for (int k = 1; k < 6; k++) if (lane == k) { va = s[k]; vb = s[6 + k]; }
-        const int an = s[5], bn = s[11];
-        const double w = (double)((float)(bn + an) * F.twofitweight / (float)(an + 1)) + 1.0;
-        term[j * 6 + lane] = (double)vb + (double)va * w;
+        for (int k = 1; k < F1_ACC; k++) if (lane == k) v = s[k];
+        reinterpret_cast<int *>(term)[j * F1_ACC + lane] = v;
       }
       nonzero += s[5];
+    }
+    __syncwarp();
+    // what fit_line adds for a gap, chain f: (double)Xb + (double)Xa * weight (lib/floor1.c:465-474).  One
+    // lane per gap turns its 12 ints into the 6 doubles in place (same 48 bytes, private to the lane).
+    for (int g = lane; g < P - 1; g += 32) {
+      int a[F1_ACC];
+      const int *src = reinterpret_cast<const int *>(term) + g * F1_ACC;
+#pragma unroll
+      for (int k = 0; k < F1_ACC; k++) a[k] = src[k];
+      const double w = (double)((float)(a[11] + a[5]) * F.twofitweight / (float)(a[5] + 1)) + 1.0;
+#pragma unroll
+      for (int f = 0; f < 6; f++) term[g * 6 + f] = (double)a[6 + f] + (double)a[f] * w;
     }
     __syncwarp();
     if (!nonzero) {                                      // the reference returns NULL

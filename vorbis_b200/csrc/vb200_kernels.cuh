@@ -99,8 +99,14 @@ template <int NC> struct XLog2 { static constexpr int v = 1 + XLog2<NC / 2>::v; 
 template <> struct XLog2<1> { static constexpr int v = 0; };
 template <> struct XLog2<0> { static constexpr int v = 0; };
 
+// Padded index for the output of the last butterfly level when it goes to a separate buffer: the
+// bit-reverse stage gathers float2 at strides of 32 floats and more (16-way bank conflicts on the
+// plain layout); two extra floats per 32 and per 512 spread those gathers - and the level's own
+// stores - over all banks (checked for n2 = 1024: both gathers and the stores are conflict free).
+__device__ __forceinline__ int fly_pad(int a) { return a + 2 * (a >> 5) + 2 * (a >> 9); }
+
 template <int NC>
-__device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int tid, int nt) {
+__device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int tid, int nt, float *padbuf = nullptr) {
   const int N = NC ? NC : X.N;
   const int log2n = NC ? XLog2<NC>::v : X.log2n;
   const int nst = log2n - 6;
@@ -182,7 +188,13 @@ __device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int
     o0.x = d62 + d51;  o0.z = d62 - d51;
     o0.w = d73 + d40;  o0.y = d73 - d40;
     o1.w = s73 + s51;  o1.y = s73 - s51;
-    p[0] = o0; p[1] = o1;
+    if (padbuf) {
+      float2 *q = reinterpret_cast<float2 *>(padbuf + fly_pad(8 * u));
+      q[0] = make_float2(o0.x, o0.y); q[1] = make_float2(o0.z, o0.w);
+      q[2] = make_float2(o1.x, o1.y); q[3] = make_float2(o1.z, o1.w);
+    } else {
+      p[0] = o0; p[1] = o1;
+    }
   }
   __syncthreads();
 }
@@ -190,7 +202,7 @@ __device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int
 // mdct_bitreverse (lib/mdct.c:346-394): item m reads two complex values of the
 // upper half w[n2..N) through bitrev[] and writes four values of w[0..n2).
 template <int NC>
-__device__ __forceinline__ void dev_bitreverse(const XformDev &X, float *w, int tid, int nt) {
+__device__ __forceinline__ void dev_bitreverse(const XformDev &X, float *w, int tid, int nt, const float *padbuf = nullptr) {
   const int N = NC ? NC : X.N, n2 = N >> 1;
   const float2 *T = reinterpret_cast<const float2 *>(X.trig + N);
   const int2 *br = reinterpret_cast<const int2 *>(X.bitrev);
@@ -198,8 +210,8 @@ __device__ __forceinline__ void dev_bitreverse(const XformDev &X, float *w, int 
   for (int m = tid; m < (N >> 3); m += nt) {
     const int2 b = __ldg(br + m);
     const float2 t = __ldg(T + m);
-    const float2 x0 = *reinterpret_cast<const float2 *>(x + b.x);
-    const float2 x1 = *reinterpret_cast<const float2 *>(x + b.y);
+    const float2 x0 = padbuf ? *reinterpret_cast<const float2 *>(padbuf + fly_pad(b.x)) : *reinterpret_cast<const float2 *>(x + b.x);
+    const float2 x1 = padbuf ? *reinterpret_cast<const float2 *>(padbuf + fly_pad(b.y)) : *reinterpret_cast<const float2 *>(x + b.y);
     const float r0 = x0.y - x1.y;
     const float r1 = x0.x + x1.x;
     const float r2 = r1 * t.x + r0 * t.y;
@@ -215,9 +227,11 @@ __device__ __forceinline__ void dev_bitreverse(const XformDev &X, float *w, int 
 // Forward MDCT of the N samples at `in` (shared memory, read-only) using the N
 // floats of scratch at `w`; writes N/2 coefficients to `out` (global or shared).
 // mdct_forward, lib/mdct.c:492-562.
+// padbuf: optional n2 + n2/16 + n2/256 + 8 floats of scratch (16-byte aligned) for the padded hand-over
+// between the butterflies and the bit-reverse stage
 template <int NC>
 __device__ __forceinline__ void dev_mdct_forward(const XformDev &X, const float *in, float *w,
-                                                 float *out, int tid, int nt) {
+                                                 float *out, int tid, int nt, float *padbuf = nullptr) {
   const int N = NC ? NC : X.N, n2 = N >> 1, n4 = N >> 2, n16 = N >> 4;
   float *w2 = w + n2;
   const float2 *Tf = reinterpret_cast<const float2 *>(X.trig);
@@ -244,8 +258,8 @@ __device__ __forceinline__ void dev_mdct_forward(const XformDev &X, const float 
     *reinterpret_cast<float2 *>(w2 + 2 * p) = make_float2(r1 * t.y + r0 * t.x, r1 * t.x - r0 * t.y);
   }
   __syncthreads();
-  dev_butterflies<NC>(X, w2, tid, nt);
-  dev_bitreverse<NC>(X, w, tid, nt);
+  dev_butterflies<NC>(X, w2, tid, nt, padbuf);
+  dev_bitreverse<NC>(X, w, tid, nt, padbuf);
   const float2 *Tp = reinterpret_cast<const float2 *>(X.trig + n2);
   const float scale = X.scale;
   for (int i = tid; i < n4; i += nt) {
