@@ -483,7 +483,7 @@ struct PcmSrc {
 };
 
 // the FFT ping-pong buffer is idle during the MDCT: it takes the padded fly output
-__device__ __forceinline__ float *getenv_free_pad(float *sf) {
+__device__ __forceinline__ float *mdct_pad_buffer(float *sf) {
 #ifdef VB200_NO_FLY_PAD
   (void)sf; return nullptr;
 #else
@@ -526,7 +526,7 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
       dev_load_windowed(Wd, W, lW, nW, pf, sx, tid, nt);
     }
     __syncthreads();
-    dev_mdct_forward<NC>(X, sx, sw, mdct + (size_t)row * n, tid, nt, getenv_free_pad(sf));
+    dev_mdct_forward<NC>(X, sx, sw, mdct + (size_t)row * n, tid, nt, mdct_pad_buffer(sf));
     const float *f = dev_drft_forward<NC>(X, sx, sf, tid, nt);
     // log spectrum + local maximum (lib/mapping0.c:310-345)
     float mx = -1e30f;

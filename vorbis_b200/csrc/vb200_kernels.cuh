@@ -764,7 +764,7 @@ __device__ __forceinline__ void dev_tone_runs(const PsyDev &P, const float *logf
 // bit-identical to the reference's sequential scatter.  Requires L in {4,8,16,32} and
 // nt == 128 (G = 32,16,8,4 lanes); other L use dev_tone_slots_gather below.
 __device__ __forceinline__ void dev_tone_slots_scatter(const PsyDev &P, const ToneSmem &T, int tid, int nt) {
-  const int L = P.linesper, half = L >> 1, total = P.total;
+  const int L = P.linesper, total = P.total;
   for (int s = tid; s < total; s += nt) T.seed[s] = VB_NEGINF;
   __syncthreads();
   const int G = nt >> P.linesper_log2;               // lanes per class (<= 32)
@@ -824,7 +824,6 @@ __device__ __forceinline__ void dev_tone_slots_scatter(const PsyDev &P, const To
 
 // seed_curve, owner-computes (generic fallback): one item per seed slot
 __device__ __forceinline__ void dev_tone_slots_gather(const PsyDev &P, const ToneSmem &T, int tid, int nt) {
-  const int half = P.linesper >> 1;
   for (int s = tid; s < P.total; s += nt) {
     float m = VB_NEGINF;
     const int2 rg = __ldg(P.slot_rng + s);           // candidate range in cls_run (empty for s == 0)
