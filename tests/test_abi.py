@@ -44,3 +44,30 @@ def test_bad_arguments_return_error_codes_not_aborts():
     assert rc == -131, rc                                # OV_EINVAL
     assert b"power" in L.vb200_last_error()
     assert L.vb200_mdct_forward(None, 0, 1, None, None) == -131
+
+
+def test_envelope_apply_marks_is_plain_host_code():
+    """vb200_envelope_apply_marks (lib/envelope.c:254-264 replayed from trigger bits) needs no GPU:
+    against the oracle's restatement on random bits, and against the reference's marks on the fixtures"""
+    import numpy as np
+    from conftest import CONFIG_NAMES, load_npz, load_setup
+    from oracle import pyoracle
+    L = lib.load()
+    L.vb200_envelope_apply_marks.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.vb200_envelope_apply_marks.restype = None
+    rng = np.random.default_rng(2)
+    ret = rng.integers(0, 8, 300).astype(np.uint8) * (rng.random(300) < 0.2)
+    ret = np.ascontiguousarray(ret, np.uint8)
+    for first in (0, 7):
+        mark = np.zeros(first + len(ret) + 2, np.int32)
+        L.vb200_envelope_apply_marks(ret.ctypes.data, first, len(ret), mark.ctypes.data)
+        o = pyoracle.Oracle(load_setup(CONFIG_NAMES[0]))
+        assert np.array_equal(mark, o.envelope_marks(ret, first_step=first))
+    for name in CONFIG_NAMES:
+        env = load_npz("envelope", name)
+        o = pyoracle.Oracle(load_setup(name))
+        steps = int(env["steps"])
+        r, _ = o.envelope_search(env["stream"][None], 0, steps)
+        mark = np.zeros(steps + 2, np.int32)
+        L.vb200_envelope_apply_marks(np.ascontiguousarray(r[0]).ctypes.data, 0, steps, mark.ctypes.data)
+        assert np.array_equal(mark, env["marks"])
