@@ -129,36 +129,142 @@ def make_desc(nblocks):
     return d
 
 
-def cpu_reference_rate(setup_name, W, pcm_np, desc_np, threads):
-    """Reference CPU implementation of the same chain on `threads` host threads (the library is
-    single threaded; blocks are independent, one reference instance per thread).  Returns
-    (blocks/s, kind).  Uses oracle/_ref (the compiled reference) when present, else the oracle port."""
-    from concurrent.futures import ThreadPoolExecutor
+def usable_cpus():
+    """CPUs this process may really run on: the affinity mask, capped by the cgroup CPU quota
+    (a container can show 128 CPUs in its mask and own a fraction of them)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = list(range(os.cpu_count() or 1))
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            f = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if f[0] != "max":
+                    quota = float(f[0]) / float(f[1])
+            else:
+                q = float(f[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    n = len(cpus)
+    if quota is not None:
+        n = max(1, min(n, int(quota)))
+    return cpus[:n], {"affinity": len(cpus), "cgroup_quota": quota, "os_cpu_count": os.cpu_count()}
+
+
+def cpu_worker_main(argv):
+    """`bench.py --cpu-worker cpu blocks reps seed`: ONE process pinned to ONE cpu running the reference
+    chain (oracle/_ref when built, else the oracle port) on its own synthetic blocks.  Protocol on
+    stdin/stdout: prints "ready", waits for a line, runs `reps` passes, prints the elapsed seconds."""
+    cpu, nb, reps, seed = int(argv[0]), int(argv[1]), int(argv[2]), int(argv[3])
+    try:
+        os.sched_setaffinity(0, {cpu})
+    except Exception:
+        pass
     from vorbis_b200 import abi
-    nb = pcm_np.shape[0]
-    shards = [s for s in np.array_split(np.arange(nb), threads) if len(s)]
     from oracle import pyref
+    setup = abi.SetupHolder.load(os.path.join(GOLD, "setup_44k_stereo_q5.npz"))
+    N, ch = setup.blocksize(W_LONG), setup.channels
+    rng = np.random.default_rng(seed)
+    t = np.arange(N, dtype=np.float32)
+    pcm = (0.25 * rng.uniform(-1, 1, (nb, ch, N)) +
+           0.5 * np.sin(2 * np.pi * (440 + 110 * np.arange(ch)).reshape(1, ch, 1) * t / 44100.0
+                        + rng.uniform(0, 6.28, (nb, 1, 1)))).astype(np.float32)
+    desc = make_desc(nb)
     if pyref.available():
         kind = "reference"
-        ch = pcm_np.shape[1]
-        insts = [pyref.Ref(ch, 44100, 0.5) for _ in shards]
-
-        def run(i):
-            insts[i].encode_dsp_batch(W, pcm_np[shards[i]], desc_np[shards[i]])
+        inst = pyref.Ref(ch, 44100, 0.5)
+        run = lambda: inst.encode_dsp_batch(W_LONG, pcm, desc)
     else:
         kind = "port"
         from oracle import pyoracle
-        setup = abi.SetupHolder.load(os.path.join(GOLD, "setup_%s.npz" % setup_name))
-        insts = [pyoracle.Oracle(setup) for _ in shards]
-
-        def run(i):
-            insts[i].encode_dsp(W, pcm_np[shards[i]], desc_np[shards[i]])
-    with ThreadPoolExecutor(len(shards)) as ex:
-        list(ex.map(run, range(len(shards))))           # warm caches / page in
+        inst = pyoracle.Oracle(setup)
+        run = lambda: inst.encode_dsp(W_LONG, pcm, desc)
+    run()                                              # page in / warm caches
+    sys.stdout.write("ready %s\n" % kind); sys.stdout.flush()
+    while True:
+        line = sys.stdin.readline()
+        if not line or line.startswith("quit"):
+            return
         t0 = time.perf_counter()
-        list(ex.map(run, range(len(shards))))
-        dt = time.perf_counter() - t0
-    return nb / dt, kind, len(shards)
+        for _ in range(reps):
+            run()
+        sys.stdout.write("%.6f\n" % (time.perf_counter() - t0)); sys.stdout.flush()
+
+
+class CpuPool:
+    """One pinned worker PROCESS per cpu (the reference library is single threaded; blocks of different
+    streams are independent - BASELINE.md section 3).  step() releases all workers at once and returns the
+    wall time until the slowest one has finished."""
+
+    def __init__(self, cpus, blocks_per_core, reps=1):
+        self.cpus, self.nb, self.reps = list(cpus), blocks_per_core, reps
+        self.procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", str(c),
+                                        str(blocks_per_core), str(reps), str(7000 + i)],
+                                       stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, cwd=ROOT)
+                      for i, c in enumerate(self.cpus)]
+        self.kind = None
+        for p in self.procs:
+            ln = p.stdout.readline().split()
+            if not ln or ln[0] != "ready":
+                raise RuntimeError("cpu worker failed to start")
+            self.kind = ln[1]
+
+    def step(self):
+        t0 = time.perf_counter()
+        for p in self.procs:
+            p.stdin.write("go\n"); p.stdin.flush()
+        per = [float(p.stdout.readline()) for p in self.procs]
+        return time.perf_counter() - t0, per
+
+    def blocks_per_step(self):
+        return self.nb * self.reps * len(self.procs)
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.write("quit\n"); p.stdin.flush(); p.stdin.close()
+            except Exception:
+                pass
+        for p in self.procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:
+                p.kill()
+
+
+def cpu_reference_rates(blocks_per_core, steps, warmup, single_core=True):
+    """(all-core dict, 1-core dict or None).  Every step is a bounded sample: blocks_per_core long stereo
+    blocks on every usable cpu."""
+    cpus, info = usable_cpus()
+    pool = CpuPool(cpus, blocks_per_core)
+    try:
+        for _ in range(warmup):
+            pool.step()
+        walls = [pool.step()[0] for _ in range(steps)]
+    finally:
+        pool.close()
+    nb = pool.blocks_per_step()
+    rate = nb * len(walls) / sum(walls)
+    allc = {"value": rate, "unit": UNIT, "cores": len(cpus), "kind": pool.kind,
+            "blocks_per_s_per_core": rate / len(cpus), "cpu_info": info, "ms_per_step": 1e3 * sum(walls) / len(walls),
+            "sample": "%d long stereo blocks per step = %d on each of %d pinned single-threaded processes"
+                      % (nb, blocks_per_core, len(cpus))}
+    one = None
+    if single_core:
+        p1 = CpuPool(cpus[:1], blocks_per_core)
+        try:
+            p1.step()
+            w = [p1.step()[0] for _ in range(max(2, min(steps, 3)))]
+        finally:
+            p1.close()
+        one = {"value": blocks_per_core * len(w) / sum(w), "unit": UNIT, "cores": 1, "kind": p1.kind,
+               "sample": "%d long stereo blocks per step on one pinned process" % blocks_per_core}
+    return allc, one
 
 
 # ------------------------------------------------------------------------------------------
@@ -169,31 +275,16 @@ def run_reference_arm(args):
     from vorbis_b200 import abi
     setup = abi.SetupHolder.load(os.path.join(GOLD, "setup_44k_stereo_q5.npz"))
     N, ch = setup.blocksize(W_LONG), setup.channels
-    cores = os.cpu_count() or 1
-    per_core = args.ref_blocks_per_core
-    nb = per_core * cores
-    rng = np.random.default_rng(1)
-    t = np.arange(N, dtype=np.float32)
-    pcm = (0.25 * rng.uniform(-1, 1, (nb, ch, N)) +
-           0.5 * np.sin(2 * np.pi * (440 + 110 * np.arange(ch)).reshape(1, ch, 1) * t / 44100.0
-                        + rng.uniform(0, 6.28, (nb, 1, 1)))).astype(np.float32)
-    desc = make_desc(nb)
-    rates = []
-    kind = used = None
-    for i in range(args.warmup + args.steps):
-        r, kind, used = cpu_reference_rate("44k_stereo_q5", W_LONG, pcm, desc, cores)
-        if i >= args.warmup:
-            rates.append(r)
-    total_t = sum(nb / r for r in rates)
-    value = nb * len(rates) / total_t
+    allc, one = cpu_reference_rates(args.ref_blocks_per_core, args.steps, args.warmup)
+    value = allc["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / len(rates),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": allc["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(100000, N, ch), "l2": "n/a (CPU)",
-                   "note": "each step is a bounded sample of the workload: %d blocks" % nb},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind,
-                         "sample": "%d long stereo blocks (%d per thread) per step" % (nb, per_core)},
+        "config": {"workload": workload_name(args.blocks, N, ch), "blocks_per_gpu": args.blocks,
+                   "l2": "n/a (CPU)", "sharding": "independent blocks per rank, no collective",
+                   "note": "each step is a bounded sample of the workload: " + allc["sample"]},
+        "cpu_baseline": allc, "cpu_baseline_1core": one,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -471,14 +562,7 @@ def run_ours(args):
                 "phaseA_only_blocks_per_s": float(nb / (kms[:3].sum() * 1e-3))}
 
         # ---- CPU baseline on a bounded sample of the same workload (same chain, reference functions)
-        cores = os.cpu_count() or 1
-        nb_c = args.ref_blocks_per_core * cores
-        pcm_c = pcm[:min(nb, nb_c)].cpu().numpy()
-        if pcm_c.shape[0] < nb_c:
-            pcm_c = np.concatenate([pcm_c] * (nb_c // pcm_c.shape[0] + 1))[:nb_c]
-        rate_c, kind, used = cpu_reference_rate("44k_stereo_q5", W_LONG, pcm_c, make_desc(nb_c), cores)
-        cpu = {"value": rate_c, "unit": UNIT, "cores": used, "kind": kind,
-               "sample": "%d long stereo blocks (%d per thread)" % (nb_c, args.ref_blocks_per_core)}
+        cpu, cpu1 = cpu_reference_rates(args.ref_blocks_per_core, 2, 1)
 
         extra = None
         if not args.no_extra:
@@ -494,7 +578,7 @@ def run_ours(args):
             "config": {"workload": workload_name(nb, N, ch), "blocks_per_gpu": nb,
                        "l2": "inputs+intermediates+outputs per step (%.1f GB) exceed the 126 MB L2" % (30 * N * ch * nb / 1e9),
                        "sharding": "independent blocks per rank, no collective"},
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_1core": cpu1, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "extra": extra,
         }
         print(json.dumps(line))
@@ -513,7 +597,10 @@ def main():
     ap.add_argument("--e2e-blocks", type=int, default=50000, help="stereo blocks per GPU per e2e step")
     ap.add_argument("--e2e-blocks-per-stream", type=int, default=50)
     ap.add_argument("--no-extra", action="store_true", help="skip the informational configs 2/4")
-    ap.add_argument("--ref-blocks-per-core", type=int, default=512)
+    ap.add_argument("--ref-blocks-per-core", type=int, default=2048,
+                    help="CPU arms: long stereo blocks per pinned process per step (about 0.4 s of work)")
+    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-worker":
+        return cpu_worker_main(sys.argv[2:])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -19,6 +19,7 @@
 #include "vb200_kernels.cuh"
 #include "vb200_cqn.cuh"
 #include "vb200_psy2.cuh"
+#include "vb200_psy3.cuh"
 #include "vb200_floor1.cuh"
 #include "vb200_env.cuh"
 #include "vb200_res.cuh"
@@ -272,6 +273,8 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     if (p.eighth_octave_lines > 32) return fail(VB200_EIMPL, "eighth_octave_lines > 32");
     if (p.total_octave_lines >= 2048) return fail(VB200_EIMPL, "total_octave_lines >= 2048");
     { const int *dco = nullptr; if ((rc = upload(c, f.cls_off.data(), f.cls_off.size(), &dco))) return rc; d.cls_off = dco; }
+    d.max_cls_len = 0;
+    for (size_t k = 0; k + 1 < f.cls_off.size(); k++) d.max_cls_len = std::max(d.max_cls_len, f.cls_off[k + 1] - f.cls_off[k]);
   }
   // floor 1 lookups: what floor1_look (lib/floor1.c:205-253) derives from the post list
   for (int w = 0; w < 2; w++) {
@@ -1119,7 +1122,32 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
     const int n = N / 2;
     const char *ev = getenv("VB200_PSY_V1");
     const bool v2ok = !(ev && atoi(ev)) && (n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048);
-    if (v2ok) {
+    const char *ev2 = getenv("VB200_PSY_V2");
+    const bool v3ok = v2ok && !(ev2 && atoi(ev2)) && P0.linesper == P1.linesper &&
+                      psy3_supported(n, P0.total > P1.total ? P0.total : P1.total, P0.linesper);
+    if (v3ok) {
+      const int total = P0.total > P1.total ? P0.total : P1.total;
+      const int nruns = P0.nruns > P1.nruns ? P0.nruns : P1.nruns;
+      const int ngrp = P0.ngrp > P1.ngrp ? P0.ngrp : P1.ngrp;
+      const size_t smem3 = sizeof(float) * psy3_floats(n, total, nruns, ngrp);
+      int ctas = (int)((227 * 1024) / (smem3 + 1024));
+      if (ctas > PSY3_MINB) ctas = PSY3_MINB;
+      if (ctas < 1) ctas = 1;
+      { const char *e = getenv("VB200_PSY_CTAS"); if (e) ctas = atoi(e); }
+#define LAUNCH_PSY3(KK)                                                                            \
+      do {                                                                                         \
+        if ((rc = set_smem(k_phaseA_psy3<KK>, smem3))) return rc;                                  \
+        k_phaseA_psy3<KK><<<grid_for(c, rows, ctas), PSY3_THREADS, smem3, st>>>(P0, P1, ch, rows, A); \
+      } while (0)
+      switch (n / 128) {
+        case 1: LAUNCH_PSY3(1); break;
+        case 2: LAUNCH_PSY3(2); break;
+        case 4: LAUNCH_PSY3(4); break;
+        case 8: LAUNCH_PSY3(8); break;
+        default: LAUNCH_PSY3(16); break;
+      }
+#undef LAUNCH_PSY3
+    } else if (v2ok) {
       const int total = P0.total > P1.total ? P0.total : P1.total;
       const int nruns = P0.nruns > P1.nruns ? P0.nruns : P1.nruns;
       const int ngrp = P0.ngrp > P1.ngrp ? P0.ngrp : P1.ngrp;

@@ -16,7 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "../../include/vorbis_b200.h"
+#include "vorbis_b200.h"
 
 struct Floor1Dev {                     // vorbis_look_floor1 (lib/codec_internal.h:138-155) in 16-bit
   int posts, n, mult, pad;

@@ -61,6 +61,7 @@ struct PsyDev {
   const int   *long_grp;     // [nlong] groups folded cooperatively
   int nlong;
   const int *cls_off;        // [L+1] (device) class c owns cls_run[cls_off[c] .. cls_off[c+1])
+  int max_cls_len;           // longest class
 };
 
 // ------------------------------------------------------------------------
@@ -74,12 +75,27 @@ __device__ __forceinline__ float add345(float x) {             // "+ .345" is a 
 
 // 32-bit shared-window addressing: one cvta per array, then ld/st.shared with register offsets
 // (keeps the compiler from re-deriving the shared base inside predicated hot loops)
+#ifndef VB200_EMU
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_s16(unsigned a) { short v; asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(a)); return (int)v; }
+__device__ __forceinline__ int4 lds_v4(unsigned a) { int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_s16(unsigned a, int v) { asm volatile("st.shared.s16 [%0], %1;" :: "r"(a), "h"((short)v) : "memory"); }
 __device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int barid, int nt) { asm volatile("bar.sync %0, %1;" :: "r"(barid), "r"(nt) : "memory"); }
+#else   // host emulation build (tools/cuemu, development aid): "shared addresses" are offsets into the CTA's buffer
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)((const unsigned char *)p - cuemu::dyn_smem()); }
+__device__ __forceinline__ float lds_f32(unsigned a) { return *reinterpret_cast<const float *>(cuemu::dyn_smem() + a); }
+__device__ __forceinline__ int lds_s32(unsigned a) { return *reinterpret_cast<const int *>(cuemu::dyn_smem() + a); }
+__device__ __forceinline__ int lds_s16(unsigned a) { return (int)*reinterpret_cast<const short *>(cuemu::dyn_smem() + a); }
+__device__ __forceinline__ int4 lds_v4(unsigned a) { return *reinterpret_cast<const int4 *>(cuemu::dyn_smem() + a); }
+__device__ __forceinline__ void sts_s16(unsigned a, int v) { *reinterpret_cast<short *>(cuemu::dyn_smem() + a) = (short)v; }
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { *reinterpret_cast<float *>(cuemu::dyn_smem() + a) = v; }
+__device__ __forceinline__ void sts_s32(unsigned a, int v) { *reinterpret_cast<int *>(cuemu::dyn_smem() + a) = v; }
+__device__ __forceinline__ void named_bar_sync(int barid, int nt) { cuemu_named_barrier(barid, nt); }
+#endif
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -519,7 +535,7 @@ __device__ __forceinline__ void dev_load_windowed(const WinDev &Wd, int W, int l
 
 __device__ __forceinline__ void group_sync(int barid, int nt) {
   if (nt == 32) __syncwarp();
-  else asm volatile("bar.sync %0, %1;" :: "r"(barid), "r"(nt) : "memory");
+  else named_bar_sync(barid, nt);
 }
 
 struct Abd { float A, B, D; };
@@ -783,8 +799,7 @@ __device__ __forceinline__ void dev_tone_slots_scatter(const PsyDev &P, const To
   auto fetch = [&](int k, Run &r) {
     r.ext = 0;
     if (k < k1) {
-      int4 v;
-      asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a_rec + 16u * k));
+      const int4 v = lds_v4(a_rec + 16u * k);
       r.mx = __int_as_float(v.x);
       r.ci = v.y + g;
       r.sp = v.z + gL;
