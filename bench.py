@@ -398,6 +398,126 @@ def synth_stream_s16(torch, ns, stride, ch, rate, device, seed):
     return (x * 32767.0).round_().clamp_(-32768, 32767).to(torch.int16)
 
 
+def verify_against_oracle(setup, W, pcm_blocks, desc_np, got, streams=None, what=""):
+    """bit-exact check of a sample of what was just timed against the CPU oracle (outside any timed region);
+    raises on the first difference so that no throughput is ever printed for wrong output"""
+    from oracle import pyoracle
+    want = pyoracle.Oracle(setup).encode_dsp(W, pcm_blocks, desc_np, streams=streams)
+    for k in ("posts", "nonzero", "iwork"):
+        w = want[k]
+        if k == "iwork" and got[k].dtype == np.int16:
+            w = np.clip(w, -32768, 32767).astype(np.int16)
+        if not np.array_equal(got[k].reshape(w.shape), w):
+            bad = int((got[k].reshape(w.shape) != w).sum())
+            raise RuntimeError("%s: CUDA output differs from the oracle in `%s` (%d of %d values)" % (what, k, bad, w.size))
+    return int(pcm_blocks.shape[0])
+
+
+def synth_timelines_s16(torch, lo, hi, stride, ch, rate, device):
+    """int16 interleaved timelines [streams][stride][ch] of streams lo..hi-1 of the job: the config-3 noise+sine
+    mix with a few level drops followed by bursts per stream, so that the encoder really switches block sizes.
+    Seeded per STREAM (not per rank): the job is the same however it is sharded."""
+    ns = hi - lo
+    g = torch.Generator(device=device)
+    g.manual_seed(777000 + lo)
+    t = torch.arange(stride, device=device, dtype=torch.float32).view(1, stride, 1)
+    x = torch.rand((ns, stride, ch), generator=g, device=device, dtype=torch.float32).mul_(0.5).sub_(0.25)
+    sid = torch.arange(lo, hi, device=device, dtype=torch.float32).view(ns, 1, 1)
+    f = 440.0 + 110.0 * torch.arange(ch, device=device, dtype=torch.float32).view(1, 1, ch) + (sid % 97.0)
+    x.add_(0.5 * torch.sin(2 * np.pi * f * t / rate + sid))
+    # transients: every ~12000 samples a 300-sample drop to 1 % followed by a 100-sample burst (position by stream id)
+    pos = (torch.arange(stride, device=device).view(1, stride) + (torch.arange(lo, hi, device=device).view(ns, 1) * 1237) % 12000) % 12000
+    gain = torch.where(pos < 300, 0.01, 1.0).unsqueeze(-1)
+    x.mul_(gain)
+    burst = ((pos >= 300) & (pos < 400)).unsqueeze(-1)
+    x = torch.where(burst, torch.rand((ns, stride, ch), generator=g, device=device) * 1.8 - 0.9, x)
+    return (x * 32767.0).round_().clamp_(-32768, 32767).to(torch.int16)
+
+
+def streams_leg(torch, dist, ctx, abi, lib, setup, dev, world, rank, total_streams, blocks_per_stream, sptr):
+    """BASELINE configs[4]: `total_streams` independent streams as ONE job, split over the ranks with
+    shard.stream_slice (STRONG scaling: total work fixed), each rank running vb200_encode_streams_dev on its
+    slice: envelope search, block planning, both block sizes, ampmax chain across sizes.  Timed on the device
+    (CUDA events), max over ranks.  Two streams per rank are verified block by block against the oracle."""
+    from vorbis_b200 import shard
+    ch, rate = setup.channels, setup.rate
+    bs0, bs1 = setup.blocksize(0), setup.blocksize(1)
+    lo, hi = shard.stream_slice(total_streams, world, rank)
+    ns = hi - lo
+    stride = ((blocks_per_stream + 2) * (bs1 // 2) + 3) & ~3
+    pcm = synth_timelines_s16(torch, lo, hi, stride, ch, rate, dev)
+    max_blocks = stride // (bs0 // 2) + 8
+    cap = [ns * (stride // (bs0 // 2) + 8) // 4 + 64, ns * (stride // (bs1 // 2) + 8)]
+    plen = torch.full((ns,), stride, dtype=torch.int64, device=dev)
+    plan = torch.zeros((ns, max_blocks, 6), dtype=torch.int32, device=dev)
+    nblk = torch.zeros(ns, dtype=torch.int32, device=dev)
+    io = abi.StreamsIO()
+    io.pcm, io.pcm_fmt, io.max_blocks, io.stream_stride = pcm.data_ptr(), lib.PCM_S16_INTERLEAVED, max_blocks, stride
+    io.pcm_len, io.eof, io.plan, io.nblocks = plen.data_ptr(), None, plan.data_ptr(), nblk.data_ptr()
+    outs = []
+    for w, bsz in ((0, bs0), (1, bs1)):
+        io.cap[w] = cap[w]
+        o = {"posts": torch.empty((cap[w], ch, abi.FLOOR1_STRIDE), dtype=torch.int32, device=dev),
+             "nonzero": torch.empty((cap[w], ch), dtype=torch.int32, device=dev),
+             "iwork": torch.empty((cap[w], ch, bsz // 2), dtype=torch.int32, device=dev),
+             "ampmax_out": torch.empty(cap[w], dtype=torch.float32, device=dev)}
+        io.posts[w], io.nonzero[w], io.iwork[w], io.ampmax_out[w] = (o[k].data_ptr() for k in ("posts", "nonzero", "iwork", "ampmax_out"))
+        outs.append(o)
+
+    def step():
+        rc = ctx.L.vb200_encode_streams_dev(ctx.h, ns, 7, C.byref(io), sptr)
+        if rc:
+            raise RuntimeError("vb200_encode_streams_dev failed: %d %s" % (rc, ctx.L.vb200_last_error()))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    counts = [int(io.count[0]), int(io.count[1])]
+    # verify two streams of this rank's slice block by block (outside the timed region)
+    from oracle import pyoracle
+    orc = pyoracle.Oracle(setup)
+    hplan = plan.cpu().numpy().view(abi.STREAM_BLOCK_DTYPE).reshape(ns, max_blocks)
+    hn = nblk.cpu().numpy()
+    verified = 0
+    for s_ in sorted(set([0, ns - 1])):
+        tl = (pcm[s_].cpu().numpy().T.astype(np.float32) / np.float32(32768.0))
+        wplan, wouts = orc.encode_stream(tl, stride, 0)
+        if hn[s_] != len(wplan):
+            raise RuntimeError("streams leg: stream %d has %d blocks, oracle %d" % (lo + s_, hn[s_], len(wplan)))
+        for k, wb in enumerate(wplan):
+            gb = hplan[s_, k]
+            for nm in ("pos", "W", "lW", "nW", "blocktype"):
+                if gb[nm] != wb[nm]:
+                    raise RuntimeError("streams leg: plan differs from the oracle (stream %d block %d %s)" % (lo + s_, k, nm))
+            o = outs[int(gb["W"])]
+            sl = int(gb["slot"])
+            for nm in ("posts", "nonzero", "iwork"):
+                if not np.array_equal(o[nm][sl].cpu().numpy(), wouts[k][nm][0]):
+                    raise RuntimeError("streams leg: %s differs from the oracle (stream %d block %d)" % (nm, lo + s_, k))
+            verified += 1
+    t = torch.tensor([ms, float(counts[0]), float(counts[1]), float(verified)], device=dev, dtype=torch.float64)
+    tmax = t.clone()
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    blocks = float(t[1] + t[2])
+    return {"streams": total_streams, "blocks": int(blocks), "short_blocks": int(t[1]), "long_blocks": int(t[2]),
+            "ms_max_over_ranks": float(tmax[0]), "blocks_per_s": blocks / (float(tmax[0]) * 1e-3),
+            "streams_per_rank": ns, "scaling": "strong (fixed job, shard.stream_slice)",
+            "verified_blocks_vs_oracle": int(t[3]),
+            "call": "vb200_encode_streams_dev: int16 timelines resident, envelope search + block plan + both block sizes + "
+                    "ampmax chain across sizes; posts/nonzero/int32 residue out (device)"}
+
+
 KERNELS = ["k_phaseA_transform", "k_ampmax", "k_phaseA_psy", "k_floor1_fit", "k_floor1_render", "k_cqn"]
 
 
@@ -483,6 +603,13 @@ def run_ours(args):
     kms /= reps
     ctx.set_profiling(False)
 
+    # ---- the timed output must be the right output: 256 random blocks of the last step vs the oracle
+    vr = np.random.default_rng(4242 + rank)
+    sel = np.sort(vr.choice(nb, size=min(256, nb), replace=False))
+    tsel = torch.from_numpy(sel).to(dev)
+    got = {"posts": posts[tsel].cpu().numpy(), "nonzero": nonzero[tsel].cpu().numpy(), "iwork": iwork[tsel].cpu().numpy()}
+    verified = verify_against_oracle(setup, W_LONG, pcm[tsel].cpu().numpy(), desc_np[sel], got, what="resident step")
+
     # ---- end to end through the host-buffer C-ABI call: int16 stream PCM in (pinned), posts + residue out.
     # Every rank runs it on its own shard at the same time (streams are independent: no collective).
     bps = args.e2e_blocks_per_stream
@@ -529,12 +656,31 @@ def run_ours(args):
     d2h = int((h_posts.numel() + h_nz.numel() + h_amp.numel() + h_ovf.numel()) * 4 + h_iw.numel() * 2)
     if int(h_ovf.sum()) != 0:
         raise RuntimeError("int16 residue overflowed on the bench signal")
+    # verify whole streams (the ampmax chain runs along a stream): 6 random streams = 300 blocks
+    ssel = np.sort(vr.choice(ns_e, size=min(6, ns_e), replace=False))
+    hp_np = hp.numpy()
+    blk = np.stack([(hp_np[s_, k * hop:k * hop + N, :].T.astype(np.float32) / np.float32(32768.0))
+                    for s_ in ssel for k in range(bps)])
+    bsel = np.concatenate([np.arange(s_ * bps, (s_ + 1) * bps) for s_ in ssel])
+    got_e = {"posts": h_posts.numpy()[bsel], "nonzero": h_nz.numpy()[bsel], "iwork": h_iw.numpy()[bsel]}
+    verified_e2e = verify_against_oracle(setup, W_LONG, blk, hdesc[bsel], got_e, streams=(len(ssel), bps), what="e2e step")
     e2e = {"value": world * nb_e * args.steps / dt_max, "unit": UNIT,
            "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
            "blocks_per_step": nb_e * world, "gpu_launches": int(e2e_launches),
+           "verified_blocks_vs_oracle": verified_e2e,
            "call": "vb200_encode_dsp: %d streams x %d blocks per GPU, int16 interleaved stream PCM in (hop N/2, "
                    "blocks cut on the device), posts+nonzero+quantised residue (int16, overflow-counted) out; pinned host memory; "
                    "three-lane chunk pipeline; wall clock, max over ranks" % (ns_e, bps)}
+
+    # ---- BASELINE configs[4]: a fixed job of independent streams with real block switching, split over the ranks
+    streams_res = None
+    if args.streams > 0:
+        import torch.distributed as dist2
+        try:
+            streams_res = streams_leg(torch, dist2 if world > 1 else None, ctx, abi, lib, setup, dev, world, rank,
+                                      args.streams, args.stream_blocks, sptr)
+        except Exception as e:
+            streams_res = {"error": repr(e)}
 
     line = None
     if rank == 0:
@@ -570,6 +716,9 @@ def run_ours(args):
                 extra = extra_configs(torch, lib, abi, local, peak)
             except Exception as e:  # the headline line must still be printed
                 extra = {"error": repr(e)}
+        if streams_res is not None:
+            extra = dict(extra or {})
+            extra["streams_%d_mixed_blocks" % args.streams] = streams_res
 
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -578,7 +727,7 @@ def run_ours(args):
             "config": {"workload": workload_name(nb, N, ch), "blocks_per_gpu": nb,
                        "l2": "inputs+intermediates+outputs per step (%.1f GB) exceed the 126 MB L2" % (30 * N * ch * nb / 1e9),
                        "sharding": "independent blocks per rank, no collective"},
-            "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_1core": cpu1, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "verified_blocks_vs_oracle": verified, "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_1core": cpu1, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "extra": extra,
         }
         print(json.dumps(line))
@@ -594,9 +743,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blocks", type=int, default=100000, help="stereo blocks per GPU per step")
-    ap.add_argument("--e2e-blocks", type=int, default=50000, help="stereo blocks per GPU per e2e step")
+    ap.add_argument("--e2e-blocks", type=int, default=100000, help="stereo blocks per GPU per e2e step (same workload as the resident step)")
     ap.add_argument("--e2e-blocks-per-stream", type=int, default=50)
     ap.add_argument("--no-extra", action="store_true", help="skip the informational configs 2/4")
+    ap.add_argument("--streams", type=int, default=10000, help="configs[4]: streams of the fixed mixed-block job (0 = skip)")
+    ap.add_argument("--stream-blocks", type=int, default=50, help="long-block lengths per stream of that job")
     ap.add_argument("--ref-blocks-per-core", type=int, default=2048,
                     help="CPU arms: long stereo blocks per pinned process per step (about 0.4 s of work)")
     if len(sys.argv) > 1 and sys.argv[1] == "--cpu-worker":

@@ -19,7 +19,13 @@
  *     the others take HOST pointers, copy in/out and synchronise.
  *   - a context keeps grow-only device scratch: use one context per host thread
  *     (the reference is single threaded per vorbis_dsp_state as well);
- *     the host-pointer entry points serialise on a per-context mutex.
+ *     the host-pointer entry points serialise on a per-context mutex.  _dev calls
+ *     that use that scratch (Phase A, encode_dsp, encode_streams, envelope_search)
+ *     may be issued on different CUDA streams: each waits (on the device, via an
+ *     event) for the previous such call of the same context, so they never share
+ *     the scratch in time.  Growing the scratch re-allocates (cudaFree/cudaMalloc
+ *     synchronise the device): the first call at a new maximum size is not
+ *     asynchronous.
  */
 #ifndef VORBIS_B200_H
 #define VORBIS_B200_H
@@ -382,6 +388,58 @@ int vb200_envelope_search_dev(vb200_ctx*, int nstreams, const void *d_pcm, int p
 int vb200_envelope_search    (vb200_ctx*, int nstreams, const void *pcm, int pcm_fmt, int64_t stream_stride,
                               int first_step, int nsteps, int32_t *state, uint8_t *ret);
 void vb200_envelope_apply_marks(const uint8_t *ret, int first_step, int nsteps, int32_t *mark);
+
+/* ---- block planning: what vorbis_analysis_blockout decides per block ----------------
+ * lib/block.c:556-615 (nW from the envelope marks, blocktype) with the cursor / curmark walk of
+ * _ve_envelope_search (lib/envelope.c:269-327) and _ve_envelope_mark (:329-356), replayed per stream
+ * on the stream's timeline buffer: sample 0 is v->pcm[][0] of a fresh vorbis_dsp_state, i.e. the
+ * blocksizes[1]/2 samples of (pre-extrapolated) preamble, then the caller's PCM, then - after EOF -
+ * the extrapolated tail of vorbis_analysis_wrote(v,0).
+ *   mark   [nstreams][mark_stride] int32, mark[j] = envelope_lookup.mark of the 64-sample step j counted
+ *          from sample 0 (vb200_envelope_search + vb200_envelope_apply_marks over the whole timeline)
+ *   nsteps steps analysed (the reference's `last` = pcm_len/64 - 4 when the whole timeline was searched)
+ *   pcm_len[nstreams]  samples present per stream (v->pcm_current without any shift)
+ *   eof    [nstreams]  v->eofflag in timeline samples (preamble + samples written) or 0: no EOF yet
+ *   plan   [nstreams][max_blocks] blocks in stream order; nblocks[nstreams] how many (the stream stops
+ *          where vorbis_analysis_blockout would return 0)
+ * block sizes: blocksizes[0]/4 must be a multiple of 64 (the envelope search step).               */
+typedef struct vb200_stream_block {
+  int32_t pos;        /* first sample of the block on the timeline (centerW - blocksizes[W]/2) */
+  int32_t slot;       /* index of the block among the blocks of its size in the whole call */
+  int32_t W, lW, nW;  /* vb->W, vb->lW, vb->nW */
+  int32_t blocktype;  /* vorbis_block_internal.blocktype (psy look = blocktype + 2W) */
+} vb200_stream_block;
+int vb200_plan_blocks(vb200_ctx*, int nstreams, const int32_t *mark, int64_t mark_stride, int nsteps,
+                      const int64_t *pcm_len, const int64_t *eof, int max_blocks,
+                      vb200_stream_block *plan, int32_t *nblocks);
+
+/* ---- whole streams in ONE call (SURVEY §8 a12 + a15): envelope search, block planning, then the
+ * per-block encode DSP of both block sizes with the ampmax decay chain carried along each stream
+ * across sizes (lib/block.c:626-628).  The blocks of size W of all streams form one batch; block
+ * `slot` of that batch writes posts[W][slot], nonzero[W][slot], iwork[W][slot], ampmax_out[W][slot].
+ *   pcm       timeline buffers (see vb200_plan_blocks), VB200_PCM_F32_PLANAR [stream][ch][stream_stride]
+ *             or VB200_PCM_S16_INTERLEAVED [stream][stream_stride][ch]
+ *   cap[W]    capacity (blocks) of the size-W outputs; count[W] (host, out) blocks produced
+ *   plan / nblocks as vb200_plan_blocks (device pointers for the _dev form)
+ * Un-managed bitrate (blob `blobno`).  Streams start fresh (zero envelope state, ampmax -9999).   */
+typedef struct vb200_streams_io {
+  const void *pcm;
+  int32_t pcm_fmt;
+  int32_t max_blocks;
+  int64_t stream_stride;
+  const int64_t *pcm_len;      /* [nstreams] */
+  const int64_t *eof;          /* [nstreams] or NULL (no EOF anywhere) */
+  vb200_stream_block *plan;    /* [nstreams][max_blocks] out */
+  int32_t *nblocks;            /* [nstreams] out */
+  int32_t cap[2];
+  int32_t count[2];            /* out (host) */
+  int32_t *posts[2];           /* [cap][ch][VB200_FLOOR1_STRIDE] */
+  int32_t *nonzero[2];         /* [cap][ch] */
+  int32_t *iwork[2];           /* [cap][ch][blocksizes[W]/2] */
+  float   *ampmax_out[2];      /* [cap] */
+} vb200_streams_io;
+int vb200_encode_streams_dev(vb200_ctx*, int nstreams, int blobno, vb200_streams_io *d_io, void *stream);
+int vb200_encode_streams    (vb200_ctx*, int nstreams, int blobno, vb200_streams_io *io);
 
 /* ---- decode: mdct_backward (lib/mapping0.c:792-795) fused with the windowed
  *      overlap-add of vorbis_synthesis_blockin (lib/block.c:767-823).

@@ -63,6 +63,8 @@ def lib():
         L.vbo_residue_classify.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int]
         L.vbo_envelope_search.argtypes = [C.c_void_p, C.c_int, f32p, C.c_int64, C.c_int, C.c_int, i32p, u8p]
         L.vbo_envelope_apply_marks.argtypes = [u8p, C.c_int, C.c_int, i32p]
+        L.vbo_plan_blocks.argtypes = [C.c_void_p, C.c_int, i32p, C.c_int64, C.c_int, i64p, C.c_void_p, C.c_int,
+                                      C.c_void_p, i32p]
         _lib = L
     return _lib
 
@@ -271,6 +273,59 @@ class Oracle:
             mark = np.zeros(first_step + len(ret) + 2, np.int32)
         self.L.vbo_envelope_apply_marks(ret, first_step, len(ret), mark)
         return mark
+
+    def plan_blocks(self, mark, nsteps, pcm_len, eof=None, max_blocks=None):
+        """what vorbis_analysis_blockout decides per block (lib/block.c:534-689) from the timeline marks"""
+        mark = np.ascontiguousarray(mark, np.int32)
+        ns, stride = mark.shape
+        pcm_len = np.ascontiguousarray(pcm_len, np.int64)
+        eofp = None if eof is None else np.ascontiguousarray(eof, np.int64)
+        if max_blocks is None:
+            max_blocks = int(pcm_len.max()) // (self.bs[0] // 2) + 8
+        plan = np.zeros((ns, max_blocks), abi.STREAM_BLOCK_DTYPE)
+        nb = np.zeros(ns, np.int32)
+        self.L.vbo_plan_blocks(self.h, ns, mark.reshape(-1), stride, int(nsteps), pcm_len,
+                               None if eofp is None else eofp.ctypes.data, max_blocks, plan.ctypes.data, nb)
+        return plan, nb
+
+    def timeline_marks(self, timeline):
+        """envelope marks of whole timelines [streams][ch][len]: (mark [streams][nsteps+4], nsteps)"""
+        tl = np.ascontiguousarray(timeline, np.float32)
+        nsteps = tl.shape[2] // 64 - 4
+        ret, _ = self.envelope_search(tl, 0, nsteps)
+        mark = np.zeros((tl.shape[0], nsteps + 4), np.int32)
+        for s in range(tl.shape[0]):
+            mark[s, :nsteps + 2] = self.envelope_marks(ret[s])
+        return mark, nsteps
+
+    def encode_stream(self, tl, pcm_len, eof=0, blobno=7):
+        """The composition for ONE stream (what vorbis_analysis_blockout + mapping0_forward do per block):
+        marks -> block plan -> every block in order through encode_dsp with the ampmax decay chain carried
+        across block sizes (lib/block.c:626-628).  tl [ch][len] float32 timeline (see vb200_plan_blocks).
+        Returns (plan[nblocks], [encode_dsp result per block])."""
+        tl = np.ascontiguousarray(tl, np.float32)
+        pcm_len = int(pcm_len)
+        last = max(0, min(tl.shape[1] // 64 - 4, pcm_len // 64 - 4))   # steps the reference would have analysed
+        mark = np.zeros((1, last + 4), np.int32)
+        if last > 0:
+            ret, _ = self.envelope_search(tl[None], 0, last)
+            mark[0, :last + 2] = self.envelope_marks(ret[0])
+        plan, nb = self.plan_blocks(mark, last, [pcm_len], [int(eof)])
+        outs = []
+        g, prev = -9999.0, -9999.0
+        for k in range(int(nb[0])):
+            b = plan[0, k]
+            W = int(b["W"])
+            N = self.bs[W]
+            if prev > g:
+                g = prev
+            g = self.ampmax_decay(g, W)
+            d = np.zeros(1, abi.BLOCKDESC_DTYPE)
+            d["lW"], d["nW"], d["blocktype"], d["ampmax"] = b["lW"], b["nW"], b["blocktype"], g
+            r = self.encode_dsp(W, tl[None, :, b["pos"]:b["pos"] + N], d, blobno=blobno)
+            prev = float(r["ampmax_out"][0])
+            outs.append(r)
+        return plan[0, :int(nb[0])], outs
 
     def decouple(self, W, res):
         res = np.array(res, np.float32)

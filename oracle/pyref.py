@@ -103,6 +103,8 @@ def lib():
         L.ref_phaseA_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, f32p, f32p, f32p, f32p]
         L.ref_residue_classify.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i32p, i32p, C.c_int]
         L.ref_floor1_inverse2.argtypes = [C.c_void_p, C.c_int, C.c_int, i32p, i32p, f32p]
+        L.ref_set_timeline.argtypes = [C.c_void_p, C.c_long]
+        L.ref_get_timeline.argtypes = [C.POINTER(C.c_long), C.POINTER(C.c_long)]
         L.ref_envelope_marks.restype = C.c_long
         L.ref_envelope_marks.argtypes = [C.c_void_p, f32p, C.c_long, i32p, C.c_long, C.c_void_p, f32p]
         L.ref_encode_dsp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, i32p, i32p, i32p, f32p]
@@ -326,7 +328,7 @@ class Ref:
 
     def encode_capture(self, pcm, maxblocks=None,
                        fields=("pcm", "windowed", "fft", "mdct_raw", "logfft", "logmdct", "noise", "tone",
-                               "logmask", "mdct_m1", "ilogmask", "iwork_out")):
+                               "logmask", "mdct_m1", "ilogmask", "iwork_out"), timeline=False):
         """pcm: [ch][nsamples] float32.  One-shot: the handle is consumed."""
         pcm = np.ascontiguousarray(pcm, np.float32).reshape(self.channels, -1)
         ns = pcm.shape[1]
@@ -334,11 +336,21 @@ class Ref:
             maxblocks = ns // (self.bs[0] // 2) + 8
         cap, arr = self._mkcap(maxblocks, fields)
         nbytes = C.c_long(0)
+        tl = None
+        if timeline:
+            tl_cap = self.bs[1] // 2 + ns + 4 * self.bs[1]
+            tl = np.zeros((self.channels, tl_cap), np.float32)
+            self.L.ref_set_timeline(tl.ctypes.data, tl_cap)
         nb = self.L.ref_encode_capture(self.h, pcm, ns, C.byref(cap), C.byref(nbytes))
         k = min(nb, maxblocks)
         out = {name: a[:k] for name, a in arr.items()}
         out["nblocks"] = nb
         out["bytes"] = nbytes.value
+        if timeline:
+            ln, eof = C.c_long(0), C.c_long(0)
+            self.L.ref_get_timeline(C.byref(ln), C.byref(eof))
+            out["timeline"] = tl[:, :ln.value].copy()      # v->pcm in absolute samples (preamble, input, EOF tail)
+            out["eof"] = eof.value
         return out
 
     def decode_capture(self, maxblocks, pcm_cap, fields=("dec_coef", "dec_imdct")):

@@ -513,6 +513,26 @@ static void keep_packet(ref_handle *h, ogg_packet *op){
   h->npkt++;
 }
 
+/* Optional: record the stream's timeline as the encoder sees it - v->pcm[][] re-assembled in absolute
+ * samples (sample 0 = v->pcm[][0] of the fresh state): the (pre-extrapolated) preamble of
+ * blocksizes[1]/2 samples, the input, and the extrapolated tail that vorbis_analysis_wrote(v,0)
+ * appends.  The buffer is [ch][cap]; *len_out = samples recorded, *eof_out = v->eofflag in the
+ * same coordinates.  Call before ref_encode_capture; cleared by it.                                */
+static long g_chunk = 0;
+void ref_set_chunk(long n){ g_chunk = n; }   /* samples per vorbis_analysis_wrote of ref_encode_capture (default 1024) */
+static float *g_tl = NULL; static long g_tl_cap = 0, g_tl_len = 0, g_tl_shift = 0, g_tl_eof = 0;
+void ref_set_timeline(float *buf, long cap){ g_tl = buf; g_tl_cap = cap; g_tl_len = 0; g_tl_shift = 0; g_tl_eof = 0; }
+void ref_get_timeline(long *len_out, long *eof_out){ if(len_out) *len_out = g_tl_len; if(eof_out) *eof_out = g_tl_eof; }
+static void tl_record(ref_handle *h){
+  int c; long k;
+  if(!g_tl) return;
+  for(c=0;c<h->channels;c++)
+    for(k=0;k<h->vd.pcm_current;k++)
+      if(g_tl_shift+k<g_tl_cap) g_tl[(size_t)c*g_tl_cap+g_tl_shift+k] = h->vd.pcm[c][k];
+  if(g_tl_shift+h->vd.pcm_current>g_tl_len) g_tl_len = g_tl_shift+h->vd.pcm_current;
+  if(h->vd.eofflag>0 && !g_tl_eof) g_tl_eof = g_tl_shift+h->vd.eofflag;
+}
+
 /* Encode `nsamples` samples per channel (pcm = [ch][nsamples]) through the
  * reference API, capturing into *cap.  Returns number of blocks, and the
  * total packet bytes in *bytes_out.  The handle must be fresh (one use).   */
@@ -521,7 +541,7 @@ int ref_encode_capture(void *hv, const float *pcm, long nsamples, ref_capture *c
   long pos = 0, total = 0;
   int blocks = 0, i, eos = 0;
   ogg_packet op;
-  const long chunk = 1024;
+  const long chunk = g_chunk > 0 ? g_chunk : 1024;
 
   vorbis_analysis_headerout(&h->vd,&h->vc,&h->hdr[0],&h->hdr[1],&h->hdr[2]);
   for(i=0;i<3;i++){
@@ -542,8 +562,13 @@ int ref_encode_capture(void *hv, const float *pcm, long nsamples, ref_capture *c
     }else{
       vorbis_analysis_wrote(&h->vd,0);
     }
-    while(vorbis_analysis_blockout(&h->vd,&h->vb)==1){
+    tl_record(h);
+    while(1){
+      long cw_before = h->vd.centerW, pc_before = h->vd.pcm_current;
       vorbis_block_internal *vbi = (vorbis_block_internal*)h->vb.internal;
+      if(vorbis_analysis_blockout(&h->vd,&h->vb)!=1) break;
+      /* blockout moved the buffer by movementW = what pcm_current lost (lib/block.c:659) */
+      g_tl_shift += pc_before - h->vd.pcm_current; (void)cw_before;
       g_blk = blocks;
       g_cnt_window=g_cnt_mdct=g_cnt_fft=g_cnt_noise=g_cnt_tone=g_cnt_mix=g_cnt_fit=g_cnt_enc=0;
       if(cap_on()){
@@ -564,7 +589,7 @@ int ref_encode_capture(void *hv, const float *pcm, long nsamples, ref_capture *c
     if(todo<=0 && !eos) { /* blockout returned 0 after EOF without e_o_s: done */ eos = 1; }
   }
   if(cap) cap->nblocks = blocks < cap->maxblocks ? blocks : cap->maxblocks;
-  g_cap = NULL; g_blk = -1;
+  g_cap = NULL; g_blk = -1; g_tl = NULL;
   if(bytes_out) *bytes_out = total;
   return blocks;
 }

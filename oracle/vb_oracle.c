@@ -999,3 +999,4 @@ void vbo_phaseA_streams(vbo_ctx *c, int W, int nstreams, int bps, const vb200_ph
 #include "vb_oracle_floor.inc"
 #include "vb_oracle_env.inc"
 #include "vb_oracle_res.inc"
+#include "vb_oracle_plan.inc"

@@ -64,4 +64,7 @@ void vbo_residue_classify(vbo_ctx *c, int W, int nblocks, const int32_t *iwork, 
 void vbo_envelope_search(vbo_ctx *c, int nstreams, const float *pcm, int64_t stride, int first_step,
                          int nsteps, int32_t *state, uint8_t *ret);
 void vbo_envelope_apply_marks(const uint8_t *ret, int first_step, int nsteps, int32_t *mark);
+void vbo_plan_blocks(vbo_ctx *c, int nstreams, const int32_t *mark, int64_t mark_stride, int nsteps,
+                     const int64_t *pcm_len, const int64_t *eof, int max_blocks,
+                     vb200_stream_block *plan, int32_t *nblocks);
 #endif

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import CONFIG_NAMES, assert_bits_equal, load_npz, load_setup, make_desc
+from conftest import CONFIG_NAMES, REF_ARGS, assert_bits_equal, load_npz, load_setup, make_desc, probe_signal
 from vorbis_b200 import abi, lib as vlib
 
 pytestmark = pytest.mark.gpu
@@ -850,3 +850,87 @@ def test_encode_dsp_dev_split_half_batches(cfg, monkeypatch):
     got = {k: t[k].cpu().numpy() for k in ("posts", "nonzero", "iwork", "ampmax_out")}
     _enc_compare(got, want, "split halves")
     assert np.array_equal(t["classes"].cpu().numpy(), wcls)
+
+
+# ---- whole streams through the batch path -----------------------------------------------
+@pytest.mark.parametrize("fmt", ["f32", "s16"])
+def test_encode_streams_mixed_block_sizes(cfg, fmt):
+    """vb200_encode_streams: envelope search, block planning (lib/block.c:556-615), both block sizes and the
+    ampmax chain across sizes in ONE call.  f32: every block's W/lW/nW/blocktype/position, posts, nonzero and
+    quantised residue must equal what the UNMODIFIED reference produced for the same streams through its public
+    API (the timeline is the reference's own v->pcm: pre-extrapolated preamble, input, EOF tail).  s16: the same
+    call on int16 timelines against the oracle's composition."""
+    from oracle import pyref
+    from test_plan_vs_ref import burst_signal
+    name, setup, ctx, o, _, _ = cfg
+    ch, rate, q = REF_ARGS[name]
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built")
+    sigs = [probe_signal(ch, rate, 1.2, 11), burst_signal(ch, rate, 0.9, 5), burst_signal(ch, rate, 1.4, 9)]
+    caps = []
+    for s in sigs:
+        r = pyref.Ref(ch, rate, q)
+        caps.append(r.encode_capture(s, fields=("pcm", "iwork_out"), timeline=True))
+    stride = (max(c["timeline"].shape[1] for c in caps) + 3) & ~3
+    tl = np.zeros((len(caps), ch, stride), np.float32)
+    for i, c in enumerate(caps):
+        tl[i, :, :c["timeline"].shape[1]] = c["timeline"]
+    pcm_len = np.array([c["timeline"].shape[1] for c in caps], np.int64)
+    eof = np.array([c["eof"] for c in caps], np.int64)
+    if fmt == "f32":
+        got = ctx.encode_streams(tl, pcm_len, eof)
+    else:
+        s16 = np.clip(np.rint(tl * 32767.0), -32768, 32767).astype(np.int16)
+        tl = s16.astype(np.float32) / np.float32(32768.0)
+        got = ctx.encode_streams(np.ascontiguousarray(s16.transpose(0, 2, 1)), pcm_len, eof, fmt=vlib.PCM_S16_INTERLEAVED)
+    nshort = 0
+    for i, c in enumerate(caps):
+        if fmt == "f32":
+            k = c["nblocks"]
+            want_plan = {nm: c[nm][:k] for nm in ("W", "lW", "nW", "blocktype")}
+        else:
+            wplan, wouts = o.encode_stream(tl[i], int(pcm_len[i]), int(eof[i]))
+            k = len(wplan)
+            want_plan = {nm: wplan[nm] for nm in ("W", "lW", "nW", "blocktype")}
+        assert got["nblocks"][i] == k, "stream %d: %d blocks, want %d" % (i, got["nblocks"][i], k)
+        plan = got["plan"][i, :k]
+        for nm in ("W", "lW", "nW", "blocktype"):
+            assert np.array_equal(plan[nm], want_plan[nm]), "stream %d %s" % (i, nm)
+        for b in range(k):
+            W, slot = int(plan[b]["W"]), int(plan[b]["slot"])
+            n = setup.blocksize(W) // 2
+            nshort += W == 0
+            g = got[W]
+            if fmt == "f32":
+                P = setup.floor_posts(W, 0)
+                assert np.array_equal(tl[i][:, plan[b]["pos"]:plan[b]["pos"] + 2 * n], c["pcm"][b][:, :2 * n]), "block position"
+                assert np.array_equal(g["nonzero"][slot], c["nonzero_out"][b]), "stream %d block %d nonzero" % (i, b)
+                for cc in range(ch):
+                    if c["enc_posts"][b][cc][0] >= 0:
+                        Pc = setup.floor_posts(W, setup.floor_of(W, cc))
+                        assert np.array_equal(g["posts"][slot][cc][:Pc], c["enc_posts"][b][cc][:Pc]), "stream %d block %d posts" % (i, b)
+                assert np.array_equal(g["iwork"][slot], c["iwork_out"][b][:, :n]), "stream %d block %d residue" % (i, b)
+                assert g["ampmax_out"][slot] == c["ampmax_out"][b]
+            else:
+                w = wouts[b]
+                assert np.array_equal(g["posts"][slot], w["posts"][0]) and np.array_equal(g["nonzero"][slot], w["nonzero"][0])
+                assert np.array_equal(g["iwork"][slot], w["iwork"][0]), "stream %d block %d residue" % (i, b)
+    assert nshort >= 10                                       # the streams really mix the two sizes
+    assert got["count"][0] == nshort
+
+
+def test_plan_blocks_device_vs_oracle(cfg):
+    """vb200_plan_blocks (k_plan_blocks) against the oracle's restatement on random mark patterns with and without EOF"""
+    name, setup, ctx, o, _, _ = cfg
+    rng = np.random.default_rng(77)
+    ns, nsteps = 24, 900
+    mark = (rng.uniform(0, 1, (ns, nsteps + 4)) < rng.uniform(0.0, 0.08, (ns, 1))).astype(np.int32)
+    mark[:, nsteps:] = 0
+    pcm_len = np.full(ns, 64 * (nsteps + 4), np.int64) + rng.integers(0, 64, ns)
+    eof = np.where(np.arange(ns) % 3 == 0, 0, pcm_len - 3 * setup.blocksize(1) - rng.integers(0, 500, ns)).astype(np.int64)
+    want, wn = o.plan_blocks(mark, nsteps, pcm_len, eof, max_blocks=600)
+    got, gn = ctx.plan_blocks(mark, nsteps, pcm_len, eof, max_blocks=600)
+    assert np.array_equal(gn, wn) and wn.min() > 20
+    for s in range(ns):
+        for nm in ("pos", "W", "lW", "nW", "blocktype", "slot"):
+            assert np.array_equal(got[s, :wn[s]][nm], want[s, :wn[s]][nm]), "stream %d %s" % (s, nm)

@@ -123,6 +123,10 @@ BLOCKDESC_DTYPE = np.dtype(
 assert BLOCKDESC_DTYPE.itemsize == C.sizeof(BlockDesc)
 
 
+STREAM_BLOCK_DTYPE = np.dtype([("pos", "<i4"), ("slot", "<i4"), ("W", "<i4"), ("lW", "<i4"), ("nW", "<i4"),
+                               ("blocktype", "<i4")])      # vb200_stream_block
+
+
 class PhaseAIO(C.Structure):
     _fields_ = [
         ("pcm", C.c_void_p),
@@ -158,6 +162,26 @@ class EncodeIO(C.Structure):
         ("overflow", C.c_void_p),
         ("classes", C.c_void_p),
         ("class_stride", C.c_int64),
+    ]
+
+
+class StreamsIO(C.Structure):
+    """vb200_streams_io (include/vorbis_b200.h)"""
+    _fields_ = [
+        ("pcm", C.c_void_p),
+        ("pcm_fmt", C.c_int32),
+        ("max_blocks", C.c_int32),
+        ("stream_stride", C.c_int64),
+        ("pcm_len", C.c_void_p),
+        ("eof", C.c_void_p),
+        ("plan", C.c_void_p),
+        ("nblocks", C.c_void_p),
+        ("cap", C.c_int32 * 2),
+        ("count", C.c_int32 * 2),
+        ("posts", C.c_void_p * 2),
+        ("nonzero", C.c_void_p * 2),
+        ("iwork", C.c_void_p * 2),
+        ("ampmax_out", C.c_void_p * 2),
     ]
 
 

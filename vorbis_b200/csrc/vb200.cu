@@ -23,6 +23,7 @@
 #include "vb200_floor1.cuh"
 #include "vb200_env.cuh"
 #include "vb200_res.cuh"
+#include "vb200_streams.cuh"
 #include "floor1_db_table.h"
 
 using namespace vb200;
@@ -74,9 +75,15 @@ struct vb200_ctx {
   cudaStream_t s_split[2] = {nullptr, nullptr};       // vb200_encode_dsp_dev: two concurrent half-batches
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   DevBuf enc_buf[8];                 // scratch of vb200_encode_dsp_dev
+  DevBuf str_buf[40];                // scratch of vb200_plan_blocks / vb200_encode_streams[_dev]
   DevBuf enc_lane[3][17];            // per-lane device buffers of the pipelined vb200_encode_dsp
   cudaStream_t s_enc[3] = {nullptr, nullptr, nullptr};
   int psy_ctas_per_sm = 5;
+  int psy_carveout_ctas = -1;        // CTAs/SM the generic psy kernel's shared-memory carve-out was last set for (per device)
+  // The *_dev entry points keep their intermediates in per-context scratch: two calls in flight on different
+  // user streams would share it.  Every such call waits for the previous one's event and records its own.
+  cudaEvent_t ev_scratch = nullptr;
+  bool scratch_busy = false;
   const float *d_fromdB = nullptr;
   const int *d_mag[2] = {nullptr, nullptr}, *d_ang[2] = {nullptr, nullptr};
   const Floor1Dev *d_floor[2] = {nullptr, nullptr};   // [VB200_MAX_SUBMAPS] per block size
@@ -87,6 +94,16 @@ struct vb200_ctx {
   bool profiling = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+static int scratch_begin(vb200_ctx *c, cudaStream_t st) {
+  if (c->scratch_busy) CU(cudaStreamWaitEvent(st, c->ev_scratch, 0));
+  return 0;
+}
+static int scratch_end(vb200_ctx *c, cudaStream_t st) {
+  CU(cudaEventRecord(c->ev_scratch, st));
+  c->scratch_busy = true;
+  return 0;
+}
 
 template <class T>
 static int upload(vb200_ctx *c, const T *src, size_t count, const T **dst) {
@@ -119,21 +136,9 @@ extern "C" int vb200_device_count(void) {
 
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **out) {
-  if (!s || !out) return fail(VB200_EINVAL, "null argument");
-  for (int w = 0; w < 2; w++)
-    if (!pow2(s->blocksizes[w]) || s->blocksizes[w] < 64 || s->blocksizes[w] > 8192)
-      return fail(VB200_EINVAL, "block sizes must be powers of two in [64,8192] (lib/info.c:227-228)");
-  if (s->blocksizes[0] > s->blocksizes[1]) return fail(VB200_EINVAL, "blocksizes[0] > blocksizes[1]");
-  if (s->n_psy != 0 && s->n_psy != 4) return fail(VB200_EIMPL, "n_psy must be 0 or 4");
-  if (s->channels < 1 || s->channels > VB200_MAX_CHANNELS) return fail(VB200_EINVAL, "channels");
-  int ndev = 0;
-  CU(cudaGetDeviceCount(&ndev));
-  if (device < 0 || device >= ndev) return fail(VB200_EINVAL, "no such CUDA device");
-  CU(cudaSetDevice(device));
-  vb200_ctx *c = new vb200_ctx();
-  c->device = device;
-  c->setup = *s;
+extern "C" void vb200_ctx_destroy(vb200_ctx *c);
+// everything of vb200_ctx_create that can fail after the context exists; the caller destroys *c on failure
+static int ctx_build(vb200_ctx *c, const vb200_setup *s, int device) {
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -142,6 +147,7 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
   for (auto &st : c->s_enc) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto &st : c->s_split) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming));
   for (auto &e : c->ev_join) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
   for (int w = 0; w < 2; w++) {
@@ -327,6 +333,27 @@ extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **ou
     if ((rc = upload(c, hf, (size_t)VB200_MAX_SUBMAPS, &c->d_floor[w]))) return rc;
     if ((rc = upload(c, (const unsigned char *)s->chmux[w], (size_t)VB200_MAX_CHANNELS + 1, &c->d_chmux[w]))) return rc;
   }
+  return 0;
+}
+
+
+extern "C" int vb200_ctx_create(const vb200_setup *s, int device, vb200_ctx **out) {
+  if (!s || !out) return fail(VB200_EINVAL, "null argument");
+  for (int w = 0; w < 2; w++)
+    if (!pow2(s->blocksizes[w]) || s->blocksizes[w] < 64 || s->blocksizes[w] > 8192)
+      return fail(VB200_EINVAL, "block sizes must be powers of two in [64,8192] (lib/info.c:227-228)");
+  if (s->blocksizes[0] > s->blocksizes[1]) return fail(VB200_EINVAL, "blocksizes[0] > blocksizes[1]");
+  if (s->n_psy != 0 && s->n_psy != 4) return fail(VB200_EIMPL, "n_psy must be 0 or 4");
+  if (s->channels < 1 || s->channels > VB200_MAX_CHANNELS) return fail(VB200_EINVAL, "channels");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(VB200_EINVAL, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  vb200_ctx *c = new vb200_ctx();
+  c->device = device;
+  c->setup = *s;
+  const int rc = ctx_build(c, s, device);
+  if (rc) { vb200_ctx_destroy(c); return rc; }      // streams, events and every table uploaded so far are released
   *out = c;
   return 0;
 }
@@ -344,9 +371,11 @@ extern "C" void vb200_ctx_destroy(vb200_ctx *c) {
   for (auto &b : c->enc_buf) if (b.p) cudaFree(b.p);
   for (auto &b : c->env_buf) if (b.p) cudaFree(b.p);
   for (auto &l : c->enc_lane) for (auto &b : l) if (b.p) cudaFree(b.p);
+  for (auto &b : c->str_buf) if (b.p) cudaFree(b.p);
   for (auto &st : c->s_enc) if (st) cudaStreamDestroy(st);
   if (c->s_main) cudaStreamDestroy(c->s_main);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->ev_scratch) cudaEventDestroy(c->ev_scratch);
   delete c;
 }
 
@@ -460,14 +489,14 @@ __global__ void __launch_bounds__(256)
 k_drft_forward(XformDev X, int nvec, float *__restrict__ data) {
   extern __shared__ __align__(16) float sm[];
   const int N = X.N, tid = threadIdx.x, nt = blockDim.x;
-  float *sa = sm, *sb = sm + N + 4;
+  float *sa = sm, *sb = sm + fft_buf_floats(N);
   for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
     float4 *g = reinterpret_cast<float4 *>(data + (size_t)v * N);
     for (int i = tid; i < (N >> 2); i += nt) reinterpret_cast<float4 *>(sa)[i] = g[i];
     __syncthreads();
     const float *r = dev_drft_forward<0>(X, sa, sb, tid, nt);
     float *gs = data + (size_t)v * N;
-    for (int i = tid; i < N; i += nt) gs[i] = r[i];
+    for (int i = tid; i < N; i += nt) gs[i] = r[fft_idx(i)];
     __syncthreads();
   }
 }
@@ -483,7 +512,14 @@ struct PcmSrc {
   int fmt;                 // 0 blocks [row][N] f32, VB200_PCM_F32_PLANAR, VB200_PCM_S16_INTERLEAVED
   int bps, hop;
   long long stride;        // samples per channel per stream
+  const int2 *blk_src;     // optional [blocks]: (stream, first sample) of every block instead of (blk / bps, k * hop)
 };
+
+// stream and first sample of block `blk`: equal-size runs (k * hop) or the planner's table
+__device__ __forceinline__ void blk_origin(const PcmSrc &src, int blk, long long &st, long long &off) {
+  if (src.blk_src) { const int2 o = __ldg(src.blk_src + blk); st = o.x; off = o.y; }
+  else { const int s = blk / src.bps; st = s; off = (long long)(blk - s * src.bps) * src.hop; }
+}
 
 // the FFT ping-pong buffer is idle during the MDCT: it takes the padded fly output
 __device__ __forceinline__ float *mdct_pad_buffer(float *sf) {
@@ -502,16 +538,63 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
   extern __shared__ __align__(16) float sm[];
   __shared__ float s_red[8];
   const int N = NC ? NC : X.N, n = N >> 1, tid = threadIdx.x, nt = blockDim.x;
-  float *sx = sm, *sw = sm + N + 4, *sf = sm + 2 * N + 4;   // sx and sf hold N+2 (shifted FFT passes)
+  float *sx = sm, *sw = sm + fft_buf_floats(N), *sf = sw + N;   // sx and sf double as the padded FFT ping-pong buffers
   const float scale = 4.f / (float)N;
   const float scale_dB = add345(todB_dev(scale));
+  // The raw samples of the NEXT row travel global -> shared with cp.async (16-byte LDGSTS, no registers)
+  // while this row is transformed; the window is applied on the shared -> shared pass that follows.
+  // mode 0: nothing staged (unaligned source or channel layout without a vector path): direct loads
+  // mode 1: N floats staged;  mode 2: N stereo int16 frames staged (this row keeps its channel)
+  float *sraw = sf + fft_buf_floats(N);
+  auto stage = [&](int r) -> int {
+    const int b2 = r / ch, c = r - b2 * ch;
+    const char *g = nullptr;
+    int mode = 0;
+    if (src.fmt == VB200_PCM_S16_INTERLEAVED) {
+      long long st, off; blk_origin(src, b2, st, off);
+      g = reinterpret_cast<const char *>(reinterpret_cast<const short *>(src.base) + (st * src.stride + off) * ch);
+      mode = ch == 2 ? 2 : 0;
+    } else {
+      const float *pf = reinterpret_cast<const float *>(src.base);
+      if (src.fmt == VB200_PCM_F32_PLANAR) {
+        long long st, off; blk_origin(src, b2, st, off);
+        pf += (st * ch + c) * src.stride + off;
+      } else {
+        pf += (size_t)r * N;
+      }
+      g = reinterpret_cast<const char *>(pf);
+      mode = 1;
+    }
+    if (reinterpret_cast<uintptr_t>(g) & 15) mode = 0;
+    if (mode) {
+      const unsigned d = smem_u32(sraw);
+      for (int v = tid; v < (N >> 2); v += nt) cp_async16(d + 16u * v, g + 16 * (size_t)v);
+    }
+    cp_async_commit();
+    return mode;
+  };
+  int mode = blockIdx.x < nrows ? stage(blockIdx.x) : 0;
   for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
     const int blk = row / ch;
     const int lW = desc[blk].lW, nW = desc[blk].nW;
-    if (src.fmt == VB200_PCM_S16_INTERLEAVED) {
-      const int c = row - blk * ch, st = blk / src.bps, k = blk - st * src.bps;
-      const short *p16 = reinterpret_cast<const short *>(src.base) +
-                         ((long long)st * src.stride + (long long)k * src.hop) * ch + c;
+    cp_async_wait_all();
+    __syncthreads();
+    if (mode == 1) {
+      for (int v = tid; v < (N >> 2); v += nt)
+        *reinterpret_cast<float4 *>(sx + 4 * v) = dev_window4(Wd, W, lW, nW, 4 * v, *reinterpret_cast<const float4 *>(sraw + 4 * v));
+    } else if (mode == 2) {
+      // stereo: four frames = one 128-bit word, this row keeps its channel's four samples
+      const int sh = 16 * (row - blk * ch);
+      for (int v = tid; v < (N >> 2); v += nt) {
+        const int4 u = *reinterpret_cast<const int4 *>(sraw + 4 * v);
+        const float4 x = make_float4((float)(short)((unsigned)u.x >> sh) / 32768.f, (float)(short)((unsigned)u.y >> sh) / 32768.f,
+                                     (float)(short)((unsigned)u.z >> sh) / 32768.f, (float)(short)((unsigned)u.w >> sh) / 32768.f);
+        *reinterpret_cast<float4 *>(sx + 4 * v) = dev_window4(Wd, W, lW, nW, 4 * v, x);
+      }
+    } else if (src.fmt == VB200_PCM_S16_INTERLEAVED) {
+      const int c = row - blk * ch;
+      long long st, off; blk_origin(src, blk, st, off);
+      const short *p16 = reinterpret_cast<const short *>(src.base) + (st * src.stride + off) * ch + c;
       for (int i = tid; i < N; i += nt) {
         bool z;
         const float g = dev_window_gain(Wd, W, lW, nW, i, z);
@@ -521,14 +604,20 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
     } else {
       const float *pf = reinterpret_cast<const float *>(src.base);
       if (src.fmt == VB200_PCM_F32_PLANAR) {
-        const int c = row - blk * ch, st = blk / src.bps, k = blk - st * src.bps;
-        pf += ((long long)st * ch + c) * src.stride + (long long)k * src.hop;
+        const int c = row - blk * ch;
+        long long st, off; blk_origin(src, blk, st, off);
+        pf += (st * ch + c) * src.stride + off;
       } else {
         pf += (size_t)row * N;
       }
-      dev_load_windowed(Wd, W, lW, nW, pf, sx, tid, nt);
+      for (int i = tid; i < N; i += nt) {          // unaligned source: scalar loads
+        bool z;
+        const float g = dev_window_gain(Wd, W, lW, nW, i, z);
+        sx[i] = z ? 0.f : __ldg(pf + i) * g;
+      }
     }
     __syncthreads();
+    mode = row + gridDim.x < nrows ? stage(row + gridDim.x) : 0;
     dev_mdct_forward<NC>(X, sx, sw, mdct + (size_t)row * n, tid, nt, mdct_pad_buffer(sf));
     const float *f = dev_drft_forward<NC>(X, sx, sf, tid, nt);
     // log spectrum + local maximum (lib/mapping0.c:310-345)
@@ -537,9 +626,9 @@ k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
     for (int k = tid; k < n; k += nt) {
       float v;
       if (k == 0) {
-        v = add345(scale_dB + todB_dev(f[0]));
+        v = add345(scale_dB + todB_dev(f[fft_idx(0)]));
       } else {
-        const float2 c = *reinterpret_cast<const float2 *>(f + 2 * k - 1);   // aligned: f is shifted by one
+        const float2 c = *reinterpret_cast<const float2 *>(f + fft_idx(2 * k - 1));   // aligned: shifted by one, padded
         const float re = c.x, im = c.y;
         const float t = re * re + im * im;
         v = add345(scale_dB + .5f * todB_dev(t));
@@ -964,7 +1053,7 @@ extern "C" int vb200_drft_forward(vb200_ctx *c, int W, int nvec, float *data) {
   HostIO io{c};
   void *dd; int rc;
   if ((rc = io.h2d(data, sizeof(float) * (size_t)nvec * X.N, &dd))) return rc;
-  const size_t smem = sizeof(float) * (2 * X.N + 8);
+  const size_t smem = sizeof(float) * 2 * fft_buf_floats(X.N);
   if ((rc = set_smem(k_drft_forward, smem))) return rc;
   k_drft_forward<<<grid_for(c, nvec, 8), threads_for(X.N), smem, c->s_main>>>(X, nvec, (float *)dd);
   if ((rc = post_launch(c))) return rc;
@@ -1047,18 +1136,14 @@ extern "C" int vb200_offset_and_mix(vb200_ctx *c, int look, int nvec, int sel, c
 
 // ======================================================================== //
 // Phase A
-static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io,
-                         int nstreams, int bps, const float *d_amp0, cudaStream_t st,
-                         float *d_logfft, float *d_lmax, float *d_gmax, const PcmSrc *pcmsrc = nullptr) {
-  PcmSrc psrc;
-  if (pcmsrc) psrc = *pcmsrc;
-  else { psrc.base = io->pcm; psrc.fmt = 0; psrc.bps = 1; psrc.hop = 0; psrc.stride = 0; }
+// stage 1: window + MDCT + FFT + log spectrum of `nblocks` blocks of size W
+static int phaseA_transform_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io, const PcmSrc &psrc,
+                                   cudaStream_t st, float *d_logfft, float *d_lmax) {
   const XformDev &X = c->dx[W];
   const int ch = c->setup.channels, N = X.N;
   const int rows = nblocks * ch;
-  if (c->profiling) CU(cudaEventRecord(c->ev[0], st));
   {
-    const size_t smem = sizeof(float) * (3 * N + 8);
+    const size_t smem = sizeof(float) * (2 * N + 2 * fft_buf_floats(N));   // sx, sw, sf + the cp.async staging row
     int rc;
     float *mdct_raw = io->tap_mdct_raw ? io->tap_mdct_raw : io->mdct;
     const int grid = grid_for(c, rows, 8), nt = threads_for(N);
@@ -1078,18 +1163,16 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
 #undef LAUNCH_XF
     rc = post_launch(c); if (rc) return rc;
   }
-  if (c->profiling) CU(cudaEventRecord(c->ev[1], st));
-  {
-    const int n = N / 2;
-    const float secs = (float)n / (float)c->setup.rate;           // lib/psy.c:843
-    const float secs_att = secs * c->setup.ampmax_att_per_sec;
-    if (nstreams > 0)
-      k_ampmax<<<(nstreams + 127) / 128, 128, 0, st>>>(1, nstreams, bps, ch, io->desc, d_lmax, d_amp0, secs_att, d_gmax);
-    else
-      k_ampmax<<<(nblocks + 127) / 128, 128, 0, st>>>(0, nblocks, 0, ch, io->desc, d_lmax, nullptr, secs_att, d_gmax);
-    int rc = post_launch(c); if (rc) return rc;
-  }
-  if (c->profiling) CU(cudaEventRecord(c->ev[2], st));
+  return 0;
+}
+
+// stage 3: noise / tone masks + mix of `nblocks` blocks of size W, given every block's global ampmax
+static int phaseA_psy_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io, cudaStream_t st,
+                             float *d_logfft, float *d_lmax, float *d_gmax) {
+  const XformDev &X = c->dx[W];
+  const int ch = c->setup.channels, N = X.N;
+  const int rows = nblocks * ch;
+  int rc;
   {
     const PsyDev &P0 = c->dpsy[2 * W], &P1 = c->dpsy[2 * W + 1];
     const size_t smem = psy2_smem(P0, P1);
@@ -1097,7 +1180,7 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
     {
       // leave the rest of the 256 KB unified array to L1: the static psy tables (~60 KB per look)
       // are read through it on every row
-      static int tuned = -1;
+      int &tuned = c->psy_carveout_ctas;
       const char *e = getenv("VB200_PSY_CTAS");
       const int ctas = e ? atoi(e) : c->psy_ctas_per_sm;
       if (tuned != ctas) {
@@ -1129,16 +1212,20 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
       const int total = P0.total > P1.total ? P0.total : P1.total;
       const int nruns = P0.nruns > P1.nruns ? P0.nruns : P1.nruns;
       const int ngrp = P0.ngrp > P1.ngrp ? P0.ngrp : P1.ngrp;
-      const size_t smem3 = sizeof(float) * psy3_floats(n, total, nruns, ngrp);
+      int R = 1;                                     // rows per CTA sharing one scan warp (2: fewer instructions, same time)
+      { const char *e = getenv("VB200_PSY_ROWS"); if (e) R = atoi(e) == 1 ? 1 : 2; }
+      const size_t row_bytes = sizeof(float) * ((psy3_floats(n, total, nruns, ngrp) + 3) & ~(size_t)3);
+      const size_t smem3 = row_bytes * R;
       int ctas = (int)((227 * 1024) / (smem3 + 1024));
-      if (ctas > PSY3_MINB) ctas = PSY3_MINB;
+      if (ctas > PSY3_MINB / R) ctas = PSY3_MINB / R;
       if (ctas < 1) ctas = 1;
       { const char *e = getenv("VB200_PSY_CTAS"); if (e) ctas = atoi(e); }
-#define LAUNCH_PSY3(KK)                                                                            \
+#define LAUNCH_PSY3R(KK, RR)                                                                       \
       do {                                                                                         \
-        if ((rc = set_smem(k_phaseA_psy3<KK>, smem3))) return rc;                                  \
-        k_phaseA_psy3<KK><<<grid_for(c, rows, ctas), PSY3_THREADS, smem3, st>>>(P0, P1, ch, rows, A); \
+        if ((rc = set_smem(k_phaseA_psy3<KK, RR>, smem3))) return rc;                              \
+        k_phaseA_psy3<KK, RR><<<grid_for(c, (rows + RR - 1) / RR, ctas), PSY3_THREADS * RR, smem3, st>>>(P0, P1, ch, rows, A); \
       } while (0)
+#define LAUNCH_PSY3(KK) do { if (R == 1) LAUNCH_PSY3R(KK, 1); else LAUNCH_PSY3R(KK, 2); } while (0)
       switch (n / 128) {
         case 1: LAUNCH_PSY3(1); break;
         case 2: LAUNCH_PSY3(2); break;
@@ -1146,6 +1233,7 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
         case 8: LAUNCH_PSY3(8); break;
         default: LAUNCH_PSY3(16); break;
       }
+#undef LAUNCH_PSY3R
 #undef LAUNCH_PSY3
     } else if (v2ok) {
       const int total = P0.total > P1.total ? P0.total : P1.total;
@@ -1174,6 +1262,33 @@ static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io
     }
     rc = post_launch(c); if (rc) return rc;
   }
+  return 0;
+}
+
+static int phaseA_launch(vb200_ctx *c, int W, int nblocks, const vb200_phaseA_io *io,
+                         int nstreams, int bps, const float *d_amp0, cudaStream_t st,
+                         float *d_logfft, float *d_lmax, float *d_gmax, const PcmSrc *pcmsrc = nullptr) {
+  PcmSrc psrc;
+  if (pcmsrc) psrc = *pcmsrc;
+  else { psrc.base = io->pcm; psrc.fmt = 0; psrc.bps = 1; psrc.hop = 0; psrc.stride = 0; psrc.blk_src = nullptr; }
+  const XformDev &X = c->dx[W];
+  const int ch = c->setup.channels, N = X.N;
+  int rc;
+  if (c->profiling) CU(cudaEventRecord(c->ev[0], st));
+  if ((rc = phaseA_transform_launch(c, W, nblocks, io, psrc, st, d_logfft, d_lmax))) return rc;
+  if (c->profiling) CU(cudaEventRecord(c->ev[1], st));
+  {
+    const int n = N / 2;
+    const float secs = (float)n / (float)c->setup.rate;           // lib/psy.c:843
+    const float secs_att = secs * c->setup.ampmax_att_per_sec;
+    if (nstreams > 0)
+      k_ampmax<<<(nstreams + 127) / 128, 128, 0, st>>>(1, nstreams, bps, ch, io->desc, d_lmax, d_amp0, secs_att, d_gmax);
+    else
+      k_ampmax<<<(nblocks + 127) / 128, 128, 0, st>>>(0, nblocks, 0, ch, io->desc, d_lmax, nullptr, secs_att, d_gmax);
+    int rc = post_launch(c); if (rc) return rc;
+  }
+  if (c->profiling) CU(cudaEventRecord(c->ev[2], st));
+  if ((rc = phaseA_psy_launch(c, W, nblocks, io, st, d_logfft, d_lmax, d_gmax))) return rc;
   if (c->profiling) CU(cudaEventRecord(c->ev[3], st));
   return 0;
 }
@@ -1202,8 +1317,10 @@ static int phaseA_dev_common(vb200_ctx *c, int W, int nblocks, const vb200_phase
   if (!d_logfft && (rc = ensure(c, 13, sizeof(float) * (size_t)nblocks * ch * n, &d_logfft))) return rc;
   if ((rc = ensure(c, 14, sizeof(float) * (size_t)nblocks * ch, &d_lmax))) return rc;
   if ((rc = ensure(c, 15, sizeof(float) * (size_t)nblocks, &d_gmax))) return rc;
-  return phaseA_launch(c, W, nblocks, io, nstreams, bps, d_amp0, (cudaStream_t)stream,
-                       (float *)d_logfft, (float *)d_lmax, (float *)d_gmax, pcmsrc);
+  if ((rc = scratch_begin(c, (cudaStream_t)stream))) return rc;
+  if ((rc = phaseA_launch(c, W, nblocks, io, nstreams, bps, d_amp0, (cudaStream_t)stream,
+                          (float *)d_logfft, (float *)d_lmax, (float *)d_gmax, pcmsrc))) return rc;
+  return scratch_end(c, (cudaStream_t)stream);
 }
 
 extern "C" int vb200_analysis_phaseA_pcmstream_dev(vb200_ctx *c, int W, int nstreams, int bps,
@@ -1217,7 +1334,7 @@ extern "C" int vb200_analysis_phaseA_pcmstream_dev(vb200_ctx *c, int W, int nstr
     return fail(VB200_EINVAL, "hop and stream_stride must be multiples of 4 for float PCM");
   if (!c || W < 0 || W > 1) return fail(VB200_EINVAL, "ctx/W");
   if ((int64_t)(bps - 1) * hop + c->dx[W].N > stream_stride) return fail(VB200_EINVAL, "blocks exceed the stream buffer");
-  PcmSrc ps; ps.base = d_pcm; ps.fmt = fmt; ps.bps = bps; ps.hop = hop; ps.stride = stream_stride;
+  PcmSrc ps; ps.base = d_pcm; ps.fmt = fmt; ps.bps = bps; ps.hop = hop; ps.stride = stream_stride; ps.blk_src = nullptr;
   return phaseA_dev_common(c, W, nstreams * bps, io, nstreams, bps, d_amp0, stream, &ps);
 }
 
@@ -1611,7 +1728,7 @@ static int encode_launch(vb200_ctx *c, int W, int nstreams, int bps, int blobno,
   a.desc = d->desc; a.mdct = S.mdct; a.logmdct = S.logmdct; a.logmask = S.logmask; a.ampmax_out = d->ampmax_out;
   PcmSrc ps; const PcmSrc *pp = nullptr;
   if (d->pcm_fmt == VB200_PCM_F32_BLOCKS) a.pcm = (const float *)d->pcm;
-  else { ps.base = d->pcm; ps.fmt = d->pcm_fmt; ps.bps = bps; ps.hop = d->hop; ps.stride = d->stream_stride; pp = &ps; }
+  else { ps.base = d->pcm; ps.fmt = d->pcm_fmt; ps.bps = bps; ps.hop = d->hop; ps.stride = d->stream_stride; ps.blk_src = nullptr; pp = &ps; }
   int rc;
   if ((rc = phaseA_launch(c, W, nblocks, &a, d->independent ? 0 : nstreams, bps, d->ampmax0, st,
                           S.logfft, S.lmax, S.gmax, pp))) return rc;
@@ -1673,8 +1790,11 @@ extern "C" int vb200_encode_dsp_dev(vb200_ctx *c, int W, int nstreams, int bps, 
   { const char *e = getenv("VB200_SPLIT"); if (e) split = atoi(e); }
   size_t split_min = 2048;
   { const char *e = getenv("VB200_SPLIT_MIN"); if (e && atoi(e) > 0) split_min = (size_t)atoi(e); }
-  if (split < 2 || nstreams < 2 || c->profiling || nblocks < split_min)
-    return encode_launch(c, W, nstreams, bps, blobno, d, S, (cudaStream_t)stream);
+  if ((rc = scratch_begin(c, (cudaStream_t)stream))) return rc;
+  if (split < 2 || nstreams < 2 || c->profiling || nblocks < split_min) {
+    if ((rc = encode_launch(c, W, nstreams, bps, blobno, d, S, (cudaStream_t)stream))) return rc;
+    return scratch_end(c, (cudaStream_t)stream);
+  }
   cudaStream_t user = (cudaStream_t)stream;
   CU(cudaEventRecord(c->ev_fork, user));
   // pieces: (internal stream, share of the streams).  split 2: two halves.  split 4: four pieces on the
@@ -1714,7 +1834,7 @@ extern "C" int vb200_encode_dsp_dev(vb200_ctx *c, int W, int nstreams, int bps, 
     if (e != cudaSuccess) { c->grid_div = 1; return fail(VB200_EFAULT, "encode split join", e); }
   }
   c->grid_div = 1;
-  return 0;
+  return scratch_end(c, user);
 }
 
 extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int blobno, const vb200_encode_io *h) {
@@ -1769,6 +1889,196 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
     if (h->logmask) CU(cudaMemcpyAsync(h->logmask + r0 * n, S.logmask, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
   }
   for (auto &st : c->s_enc) CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ======================================================================== //
+// whole streams: block planning and the two size batches
+static int plan_check(vb200_ctx *c) {
+  if (c->n_psy != 4) return fail(VB200_EINVAL, "context has no psy setup");
+  if ((c->setup.blocksizes[0] / 4) % PLAN_STEP) return fail(VB200_EIMPL, "blocksizes[0]/4 must be a multiple of the 64-sample envelope step");
+  return 0;
+}
+
+// device: marks -> plan (slots final), gather tables and descriptors of both sizes; d_totals[2] on the device
+static int plan_launch(vb200_ctx *c, int nstreams, const int32_t *d_mark, int64_t mark_stride, int nsteps,
+                       const int64_t *d_len, const int64_t *d_eof, int max_blocks, vb200_stream_block *d_plan,
+                       int32_t *d_nblocks, const int cap[2], int2 *d_src[2], vb200_block_desc *d_desc[2],
+                       int32_t *d_totals, cudaStream_t st) {
+  void *p; int rc;
+  if ((rc = ensure_buf(c->str_buf[0], sizeof(int32_t) * 2 * (size_t)nstreams, &p))) return rc;
+  int32_t *d_counts = (int32_t *)p;
+  if ((rc = ensure_buf(c->str_buf[1], sizeof(int32_t) * 2 * (size_t)nstreams, &p))) return rc;
+  int32_t *d_offs = (int32_t *)p;
+  const int g = (nstreams + 127) / 128;
+  k_plan_blocks<<<g, 128, 0, st>>>(nstreams, c->setup.blocksizes[0], c->setup.blocksizes[1], d_mark, mark_stride, nsteps,
+                                   d_len, d_eof, max_blocks, d_plan, d_nblocks, d_counts);
+  k_plan_offsets<<<1, 32, 0, st>>>(nstreams, d_counts, d_offs, d_totals);
+  k_plan_fill<<<g, 128, 0, st>>>(nstreams, max_blocks, d_plan, d_nblocks, d_offs, cap[0], cap[1],
+                                 d_src[0], d_src[1], d_desc[0], d_desc[1]);
+  return post_launch(c, 3);
+}
+
+extern "C" int vb200_plan_blocks(vb200_ctx *c, int nstreams, const int32_t *mark, int64_t mark_stride, int nsteps,
+                                 const int64_t *pcm_len, const int64_t *eof, int max_blocks,
+                                 vb200_stream_block *plan, int32_t *nblocks) {
+  CHECK_CTX(c);
+  int rc;
+  if ((rc = plan_check(c))) return rc;
+  if (nstreams <= 0) return 0;
+  if (!mark || !pcm_len || !plan || !nblocks || max_blocks < 1 || nsteps < 0 || mark_stride < nsteps + 3)
+    return fail(VB200_EINVAL, "plan_blocks arguments");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaStream_t st = c->s_main;
+  void *p;
+  const size_t cap = (size_t)nstreams * max_blocks;
+  if ((rc = ensure_buf(c->str_buf[2], sizeof(int32_t) * (size_t)nstreams * mark_stride, &p))) return rc; int32_t *d_mark = (int32_t *)p;
+  if ((rc = ensure_buf(c->str_buf[3], sizeof(int64_t) * 2 * (size_t)nstreams, &p))) return rc; int64_t *d_len = (int64_t *)p, *d_eof = d_len + nstreams;
+  if ((rc = ensure_buf(c->str_buf[4], sizeof(vb200_stream_block) * cap, &p))) return rc; vb200_stream_block *d_plan = (vb200_stream_block *)p;
+  if ((rc = ensure_buf(c->str_buf[5], sizeof(int32_t) * ((size_t)nstreams + 2), &p))) return rc; int32_t *d_nb = (int32_t *)p, *d_tot = d_nb + nstreams;
+  int2 *d_src[2]; vb200_block_desc *d_desc[2];
+  for (int w = 0; w < 2; w++) {
+    if ((rc = ensure_buf(c->str_buf[6 + w], sizeof(int2) * cap, &p))) return rc; d_src[w] = (int2 *)p;
+    if ((rc = ensure_buf(c->str_buf[8 + w], sizeof(vb200_block_desc) * cap, &p))) return rc; d_desc[w] = (vb200_block_desc *)p;
+  }
+  CU(cudaMemcpyAsync(d_mark, mark, sizeof(int32_t) * (size_t)nstreams * mark_stride, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_len, pcm_len, sizeof(int64_t) * nstreams, cudaMemcpyHostToDevice, st));
+  if (eof) CU(cudaMemcpyAsync(d_eof, eof, sizeof(int64_t) * nstreams, cudaMemcpyHostToDevice, st));
+  const int caps[2] = {(int)cap, (int)cap};
+  if ((rc = plan_launch(c, nstreams, d_mark, mark_stride, nsteps, d_len, eof ? d_eof : nullptr, max_blocks, d_plan, d_nb,
+                        caps, d_src, d_desc, d_tot, st))) return rc;
+  CU(cudaMemcpyAsync(plan, d_plan, sizeof(vb200_stream_block) * cap, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(nblocks, d_nb, sizeof(int32_t) * nstreams, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int vb200_encode_streams_dev(vb200_ctx *c, int nstreams, int blobno, vb200_streams_io *d, void *stream) {
+  CHECK_CTX(c);
+  int rc;
+  if ((rc = plan_check(c))) return rc;
+  if (!d) return fail(VB200_EINVAL, "null io");
+  d->count[0] = d->count[1] = 0;
+  if (nstreams <= 0) return 0;
+  if (!d->pcm || !d->pcm_len || !d->plan || !d->nblocks || d->max_blocks < 1) return fail(VB200_EINVAL, "encode_streams: pcm, pcm_len, plan, nblocks");
+  if (d->pcm_fmt != VB200_PCM_F32_PLANAR && d->pcm_fmt != VB200_PCM_S16_INTERLEAVED) return fail(VB200_EINVAL, "pcm_fmt");
+  if (blobno < 0 || blobno >= VB200_PACKETBLOBS) return fail(VB200_EINVAL, "blobno");
+  for (int w = 0; w < 2; w++)
+    if (d->cap[w] < 0 || (d->cap[w] > 0 && (!d->posts[w] || !d->nonzero[w] || !d->iwork[w] || !d->ampmax_out[w])))
+      return fail(VB200_EINVAL, "encode_streams: outputs of a size with capacity > 0");
+  if (d->stream_stride < c->setup.blocksizes[1]) return fail(VB200_EINVAL, "stream_stride");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ch = c->setup.channels;
+  // 1. envelope search over the whole timeline (fresh detector state), 2. marks, 3. plan
+  const int nsteps = (int)(d->stream_stride / PLAN_STEP) - PLAN_VE_WIN;
+  if (nsteps < 1) return fail(VB200_EINVAL, "stream too short");
+  const int64_t mark_stride = nsteps + 4;
+  void *p;
+  const size_t sw = VB200_VE_STATE_WORDS(ch);
+  if ((rc = ensure_buf(c->str_buf[10], sizeof(int32_t) * sw * nstreams, &p))) return rc; int32_t *d_state = (int32_t *)p;
+  if ((rc = ensure_buf(c->str_buf[11], (size_t)nstreams * nsteps, &p))) return rc; uint8_t *d_ret = (uint8_t *)p;
+  if ((rc = ensure_buf(c->str_buf[2], sizeof(int32_t) * (size_t)nstreams * mark_stride, &p))) return rc; int32_t *d_mark = (int32_t *)p;
+  if ((rc = ensure_buf(c->str_buf[5], sizeof(int32_t) * 2, &p))) return rc; int32_t *d_tot = (int32_t *)p;
+  int2 *d_src[2]; vb200_block_desc *d_desc[2];
+  for (int w = 0; w < 2; w++) {
+    const size_t cw = d->cap[w] > 0 ? d->cap[w] : 1;
+    if ((rc = ensure_buf(c->str_buf[6 + w], sizeof(int2) * cw, &p))) return rc; d_src[w] = (int2 *)p;
+    if ((rc = ensure_buf(c->str_buf[8 + w], sizeof(vb200_block_desc) * cw, &p))) return rc; d_desc[w] = (vb200_block_desc *)p;
+  }
+  CU(cudaMemsetAsync(d_state, 0, sizeof(int32_t) * sw * nstreams, st));
+  if ((rc = vb200_envelope_search_dev(c, nstreams, d->pcm, d->pcm_fmt, d->stream_stride, 0, nsteps, d_state, d_ret, st))) return rc;
+  {
+    const long long total = (long long)nstreams * mark_stride;
+    k_env_marks<<<grid_for(c, (int)((total + 255) / 256), 8), 256, 0, st>>>(nstreams, nsteps, d_ret, d->pcm_len, d_mark, mark_stride);
+    if ((rc = post_launch(c))) return rc;
+  }
+  if ((rc = plan_launch(c, nstreams, d_mark, mark_stride, nsteps, d->pcm_len, d->eof, d->max_blocks, d->plan, d->nblocks,
+                        d->cap, d_src, d_desc, d_tot, st))) return rc;
+  int tot[2];
+  CU(cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));                       // the launches below are sized by the plan
+  d->count[0] = tot[0]; d->count[1] = tot[1];
+  if (tot[0] > d->cap[0] || tot[1] > d->cap[1]) return fail(VB200_EINVAL, "encode_streams: more blocks than cap[] (count[] holds the need)");
+  // 4. transforms of both sizes, 5. the ampmax chain along every stream, 6. the rest of the chain per size
+  EncScratch S[2];
+  vb200_phaseA_io a[2];
+  for (int w = 0; w < 2; w++) {
+    memset(&a[w], 0, sizeof(a[w]));
+    if (!tot[w]) continue;
+    const size_t n = c->dx[w].N / 2, nb = tot[w];
+    if ((rc = enc_scratch(c->str_buf + 12 + 8 * w, nb * ch, nb, n, nullptr, false, &S[w]))) return rc;
+    a[w].desc = d_desc[w]; a[w].mdct = S[w].mdct; a[w].logmdct = S[w].logmdct; a[w].logmask = S[w].logmask;
+    a[w].ampmax_out = d->ampmax_out[w];
+    PcmSrc ps; ps.base = d->pcm; ps.fmt = d->pcm_fmt; ps.bps = 1; ps.hop = 0; ps.stride = d->stream_stride; ps.blk_src = d_src[w];
+    if ((rc = phaseA_transform_launch(c, w, (int)nb, &a[w], ps, st, S[w].logfft, S[w].lmax))) return rc;
+  }
+  {
+    float sa[2];
+    for (int w = 0; w < 2; w++) sa[w] = ((float)(c->dx[w].N / 2) / (float)c->setup.rate) * c->setup.ampmax_att_per_sec;   // lib/psy.c:843
+    k_ampmax_plan<<<(nstreams + 127) / 128, 128, 0, st>>>(nstreams, d->max_blocks, ch, d->plan, d->nblocks,
+                                                          tot[0] ? S[0].lmax : nullptr, tot[1] ? S[1].lmax : nullptr,
+                                                          sa[0], sa[1], tot[0] ? S[0].gmax : nullptr, tot[1] ? S[1].gmax : nullptr);
+    if ((rc = post_launch(c))) return rc;
+  }
+  for (int w = 0; w < 2; w++) {
+    if (!tot[w]) continue;
+    const int nb = tot[w], rows = nb * ch;
+    if ((rc = phaseA_psy_launch(c, w, nb, &a[w], st, S[w].logfft, S[w].lmax, S[w].gmax))) return rc;
+    if ((rc = vb200_floor1_fit_dev(c, w, -1, rows, S[w].logmdct, S[w].logmask, d->posts[w], S[w].fitnz, st))) return rc;
+    if ((rc = vb200_floor1_render_dev(c, w, -1, rows, d->posts[w], S[w].fitnz, d->iwork[w], d->nonzero[w], st))) return rc;
+    CqnDev Q0, Q1;
+    if ((rc = cqn_setup(c, w, 0, blobno, &Q0))) return rc;
+    if ((rc = cqn_setup(c, w, 1, blobno, &Q1))) return rc;
+    if ((rc = cqn_launch(c, Q0, Q1, d_desc[w], nb, S[w].mdct, d->iwork[w], d->nonzero[w], st))) return rc;
+  }
+  return scratch_end(c, st);
+}
+
+extern "C" int vb200_encode_streams(vb200_ctx *c, int nstreams, int blobno, vb200_streams_io *h) {
+  CHECK_CTX(c);
+  int rc;
+  if ((rc = plan_check(c))) return rc;
+  if (!h) return fail(VB200_EINVAL, "null io");
+  h->count[0] = h->count[1] = 0;
+  if (nstreams <= 0) return 0;
+  if (!h->pcm || !h->pcm_len || !h->plan || !h->nblocks || h->max_blocks < 1) return fail(VB200_EINVAL, "encode_streams: pcm, pcm_len, plan, nblocks");
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaStream_t st = c->s_main;
+  const size_t ch = c->setup.channels;
+  const size_t pcm_bytes = (size_t)nstreams * ch * (size_t)h->stream_stride * (h->pcm_fmt == VB200_PCM_S16_INTERLEAVED ? 2 : 4);
+  const size_t pcap = (size_t)nstreams * h->max_blocks;
+  void *p;
+  vb200_streams_io d = *h;
+  if ((rc = ensure_buf(c->str_buf[28], pcm_bytes, &p))) return rc; d.pcm = p;
+  if ((rc = ensure_buf(c->str_buf[3], sizeof(int64_t) * 2 * (size_t)nstreams, &p))) return rc;
+  d.pcm_len = (int64_t *)p; d.eof = h->eof ? (int64_t *)p + nstreams : nullptr;
+  if ((rc = ensure_buf(c->str_buf[4], sizeof(vb200_stream_block) * pcap, &p))) return rc; d.plan = (vb200_stream_block *)p;
+  if ((rc = ensure_buf(c->str_buf[29], sizeof(int32_t) * nstreams, &p))) return rc; d.nblocks = (int32_t *)p;
+  for (int w = 0; w < 2; w++) {
+    const size_t cw = h->cap[w] > 0 ? h->cap[w] : 0, n = c->dx[w].N / 2;
+    if (!cw) continue;
+    if ((rc = ensure_buf(c->str_buf[30 + 4 * w], sizeof(int32_t) * cw * ch * VB200_FLOOR1_STRIDE, &p))) return rc; d.posts[w] = (int32_t *)p;
+    if ((rc = ensure_buf(c->str_buf[31 + 4 * w], sizeof(int32_t) * cw * ch, &p))) return rc; d.nonzero[w] = (int32_t *)p;
+    if ((rc = ensure_buf(c->str_buf[32 + 4 * w], sizeof(int32_t) * cw * ch * n, &p))) return rc; d.iwork[w] = (int32_t *)p;
+    if ((rc = ensure_buf(c->str_buf[33 + 4 * w], sizeof(float) * cw, &p))) return rc; d.ampmax_out[w] = (float *)p;
+  }
+  CU(cudaMemcpyAsync((void *)d.pcm, h->pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync((void *)d.pcm_len, h->pcm_len, sizeof(int64_t) * nstreams, cudaMemcpyHostToDevice, st));
+  if (h->eof) CU(cudaMemcpyAsync((void *)d.eof, h->eof, sizeof(int64_t) * nstreams, cudaMemcpyHostToDevice, st));
+  rc = vb200_encode_streams_dev(c, nstreams, blobno, &d, st);
+  h->count[0] = d.count[0]; h->count[1] = d.count[1];
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->plan, d.plan, sizeof(vb200_stream_block) * pcap, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->nblocks, d.nblocks, sizeof(int32_t) * nstreams, cudaMemcpyDeviceToHost, st));
+  for (int w = 0; w < 2; w++) {
+    const size_t nb = d.count[w], n = c->dx[w].N / 2;
+    if (!nb) continue;
+    CU(cudaMemcpyAsync(h->posts[w], d.posts[w], sizeof(int32_t) * nb * ch * VB200_FLOOR1_STRIDE, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->nonzero[w], d.nonzero[w], sizeof(int32_t) * nb * ch, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->iwork[w], d.iwork[w], sizeof(int32_t) * nb * ch * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h->ampmax_out[w], d.ampmax_out[w], sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -1938,6 +2248,7 @@ extern "C" int vb200_envelope_search_dev(vb200_ctx *c, int nstreams, const void 
   if ((rc = ensure_buf(c->env_buf[0], sizeof(float) * (size_t)per_step * chunk, &p_t))) return rc;
   if ((rc = ensure_buf(c->env_buf[1], sizeof(float) * (size_t)per_step * chunk * 32, &p_v))) return rc;
   EnvSrc src; src.base = d_pcm; src.fmt = fmt; src.stride = stride; src.ch = ch;
+  if ((rc = scratch_begin(c, st))) return rc;
   for (int j0 = 0; j0 < nsteps; j0 += chunk) {
     const int ns = nsteps - j0 < chunk ? nsteps - j0 : chunk;
     const long items = per_step * ns;
@@ -1948,7 +2259,7 @@ extern "C" int vb200_envelope_search_dev(vb200_ctx *c, int nstreams, const void 
         c->env, nstreams, ch, ns, nsteps, j0, (const float *)p_t, (const float *)p_v, d_state, d_ret);
     if ((rc = post_launch(c))) return rc;
   }
-  return 0;
+  return scratch_end(c, st);
 }
 
 extern "C" int vb200_envelope_search(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64_t stride,

@@ -85,6 +85,29 @@ __device__ __forceinline__ void sts_s16(unsigned a, int v) { asm volatile("st.sh
 __device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void named_bar_sync(int barid, int nt) { asm volatile("bar.sync %0, %1;" :: "r"(barid), "r"(nt) : "memory"); }
+// predicated forms (the access is skipped, and `old` is returned, when p is false): keep data-dependent
+// branches out of loops whose lanes would otherwise diverge on every iteration
+__device__ __forceinline__ float lds_f32_if(unsigned a, float old, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.f32 %0, [%1];\n\t}" : "+f"(old) : "r"(a), "r"((int)p));
+  return old;
+}
+__device__ __forceinline__ int lds_s16_if(unsigned a, int old, bool p) {
+  short v = (short)old;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.s16 %0, [%1];\n\t}" : "+h"(v) : "r"(a), "r"((int)p));
+  return (int)v;
+}
+__device__ __forceinline__ void sts_f32_if(unsigned a, float v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" :: "r"(a), "f"(v), "r"((int)p) : "memory");
+}
+__device__ __forceinline__ void sts_s16_if(unsigned a, int v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.s16 [%0], %1;\n\t}" :: "r"(a), "h"((short)v), "r"((int)p) : "memory");
+}
+// cp.async: 16 bytes global -> shared without passing through registers (SASS: LDGSTS)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 #else   // host emulation build (tools/cuemu, development aid): "shared addresses" are offsets into the CTA's buffer
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)((const unsigned char *)p - cuemu::dyn_smem()); }
 __device__ __forceinline__ float lds_f32(unsigned a) { return *reinterpret_cast<const float *>(cuemu::dyn_smem() + a); }
@@ -95,6 +118,13 @@ __device__ __forceinline__ void sts_s16(unsigned a, int v) { *reinterpret_cast<s
 __device__ __forceinline__ void sts_f32(unsigned a, float v) { *reinterpret_cast<float *>(cuemu::dyn_smem() + a) = v; }
 __device__ __forceinline__ void sts_s32(unsigned a, int v) { *reinterpret_cast<int *>(cuemu::dyn_smem() + a) = v; }
 __device__ __forceinline__ void named_bar_sync(int barid, int nt) { cuemu_named_barrier(barid, nt); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) { memcpy(cuemu::dyn_smem() + dst, src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ float lds_f32_if(unsigned a, float old, bool p) { return p ? lds_f32(a) : old; }
+__device__ __forceinline__ int lds_s16_if(unsigned a, int old, bool p) { return p ? lds_s16(a) : old; }
+__device__ __forceinline__ void sts_f32_if(unsigned a, float v, bool p) { if (p) sts_f32(a, v); }
+__device__ __forceinline__ void sts_s16_if(unsigned a, int v, bool p) { if (p) sts_s16(a, v); }
 #endif
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -342,8 +372,22 @@ __device__ __forceinline__ void dev_mdct_backward(const XformDev &X, const float
 // ------------------------------------------------------------------------
 // Real FFT forward (drftf1 + dradf4 + dradf2, lib/smallft.c:572-631, 168-268,
 // 113-166).  One pass per factor, last factor first; each pass reads cc and
-// writes ch (both N floats of shared memory).  Items: for every k<l1, the i=0
-// column, the twiddled interior pairs i=2,4,.., and the i=ido-1 column.
+// writes ch.  Items: for every k<l1, the i=0 column, the twiddled interior
+// pairs i=2,4,.., and the i=ido-1 column.
+//
+// Layout of the ping-pong buffers: logical element e of a pass output lives at float index
+// fft_idx(e) = pad(e + 1), pad(a) = a + 2*(a >> 5).  The shift by one float puts FFTPACK's (re,im)
+// pairs (2k-1,2k) on 8-byte boundaries (one 64-bit access per pair); the two spare floats per 32
+// spread the stride-4*ido stores of the small-ido passes over the banks (tools/fft_bank_sim.py:
+// 2344 -> 1315 wavefronts per N=2048 row).  Pairs never straddle a pad (they start on an even index).
+// The very first pass reads the caller's plain, unshifted input.
+__device__ __forceinline__ int fft_idx(int e) { const int a = e + 1; return a + 2 * (a >> 5); }
+__host__ __device__ constexpr int fft_buf_floats(int N) { return N + (N >> 4) + 16; }
+
+template <bool FIRST>
+__device__ __forceinline__ int fft_rd(int e) { return FIRST ? e : fft_idx(e); }
+
+template <bool FIRST>
 __device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, float *ch,
                                               const float *w1, const float *w2, const float *w3,
                                               int tid, int nt) {
@@ -351,13 +395,13 @@ __device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, 
   const int t0 = l1 * ido;
   if (ido == 1) {
     for (int k = tid; k < l1; k += nt) {
-      const float c0 = cc[k], c1 = cc[k + t0], c2 = cc[k + 2 * t0], c3 = cc[k + 3 * t0];
+      const float c0 = cc[fft_rd<FIRST>(k)], c1 = cc[fft_rd<FIRST>(k + t0)];
+      const float c2 = cc[fft_rd<FIRST>(k + 2 * t0)], c3 = cc[fft_rd<FIRST>(k + 3 * t0)];
       const float tr1 = c1 + c3, tr2 = c0 + c2;
-      // ch is shifted by one float (see dev_drft_forward): 4k+1,4k+2 form the aligned pair
-      float *o = ch + 4 * k;
-      o[0] = tr1 + tr2;                                                   // o[0]
-      *reinterpret_cast<float2 *>(o + 1) = make_float2(c0 - c2, c3 - c1); // o[2*ido-1], o[2*ido]
-      o[3] = tr2 - tr1;                                                   // o[4*ido-1]
+      const int o = 4 * k;
+      ch[fft_idx(o)] = tr1 + tr2;                                                      // o[0]
+      *reinterpret_cast<float2 *>(ch + fft_idx(o + 1)) = make_float2(c0 - c2, c3 - c1); // o[2*ido-1], o[2*ido]
+      ch[fft_idx(o + 3)] = tr2 - tr1;                                                  // o[4*ido-1]
     }
     return;
   }
@@ -367,26 +411,25 @@ __device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, 
   for (int v = tid; v < items + l1; v += nt) {
     if (v < items) {
       const int k = v >> hsh, ii = v & (half - 1);
-      const float *c0 = cc + k * ido, *c1 = c0 + t0, *c2 = c1 + t0, *c3 = c2 + t0;
-      float *o = ch + 4 * k * ido;
+      const int c0 = k * ido, c1 = c0 + t0, c2 = c1 + t0, c3 = c2 + t0;
+      const int o = 4 * k * ido;
       if (ii == 0) {
-        const float tr1 = c1[0] + c3[0];
-        const float tr2 = c0[0] + c2[0];
-        o[0]           = tr1 + tr2;
-        o[4 * ido - 1] = tr2 - tr1;
-        o[2 * ido - 1] = c0[0] - c2[0];
-        o[2 * ido]     = c3[0] - c1[0];
+        const float a0 = cc[fft_rd<FIRST>(c0)], a1 = cc[fft_rd<FIRST>(c1)];
+        const float a2 = cc[fft_rd<FIRST>(c2)], a3 = cc[fft_rd<FIRST>(c3)];
+        const float tr1 = a1 + a3;
+        const float tr2 = a0 + a2;
+        ch[fft_idx(o)]               = tr1 + tr2;
+        ch[fft_idx(o + 4 * ido - 1)] = tr2 - tr1;
+        *reinterpret_cast<float2 *>(ch + fft_idx(o + 2 * ido - 1)) = make_float2(a0 - a2, a3 - a1);
       } else {
         const int i = 2 * ii;
         const float wa1r = __ldg(w1 + i - 2), wa1i = __ldg(w1 + i - 1);
         const float wa2r = __ldg(w2 + i - 2), wa2i = __ldg(w2 + i - 1);
         const float wa3r = __ldg(w3 + i - 2), wa3i = __ldg(w3 + i - 1);
-        // (re,im) pairs sit at (i-1,i); the buffers are shifted by one float so that they are
-        // 8-byte aligned: one 64-bit access per pair, consecutive lanes on consecutive banks
-        const float2 a0 = *reinterpret_cast<const float2 *>(c0 + i - 1);
-        const float2 a1 = *reinterpret_cast<const float2 *>(c1 + i - 1);
-        const float2 a2 = *reinterpret_cast<const float2 *>(c2 + i - 1);
-        const float2 a3 = *reinterpret_cast<const float2 *>(c3 + i - 1);
+        const float2 a0 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c0 + i - 1));
+        const float2 a1 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c1 + i - 1));
+        const float2 a2 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c2 + i - 1));
+        const float2 a3 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c3 + i - 1));
         const float cr2 = wa1r * a1.x + wa1i * a1.y;
         const float ci2 = wa1r * a1.y - wa1i * a1.x;
         const float cr3 = wa2r * a2.x + wa2i * a2.y;
@@ -398,33 +441,34 @@ __device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, 
         const float ti2 = a0.y + ci3, ti3 = a0.y - ci3;
         const float tr2 = a0.x + cr3, tr3 = a0.x - cr3;
         const int ic = 2 * ido - i;
-        *reinterpret_cast<float2 *>(o + i - 1)            = make_float2(tr1 + tr2, ti1 + ti2);
-        *reinterpret_cast<float2 *>(o + ic - 1)           = make_float2(tr3 - ti4, tr4 - ti3);
-        *reinterpret_cast<float2 *>(o + 2 * ido + i - 1)  = make_float2(ti4 + tr3, tr4 + ti3);
-        *reinterpret_cast<float2 *>(o + 2 * ido + ic - 1) = make_float2(tr2 - tr1, ti1 - ti2);
+        *reinterpret_cast<float2 *>(ch + fft_idx(o + i - 1))            = make_float2(tr1 + tr2, ti1 + ti2);
+        *reinterpret_cast<float2 *>(ch + fft_idx(o + ic - 1))           = make_float2(tr3 - ti4, tr4 - ti3);
+        *reinterpret_cast<float2 *>(ch + fft_idx(o + 2 * ido + i - 1))  = make_float2(ti4 + tr3, tr4 + ti3);
+        *reinterpret_cast<float2 *>(ch + fft_idx(o + 2 * ido + ic - 1)) = make_float2(tr2 - tr1, ti1 - ti2);
       }
     } else {
       const int k = v - items;
-      const float *c0 = cc + k * ido, *c1 = c0 + t0, *c2 = c1 + t0, *c3 = c2 + t0;
-      float *o = ch + 4 * k * ido;
-      const float ti1 = -hsqt2 * (c1[ido - 1] + c3[ido - 1]);
-      const float tr1 =  hsqt2 * (c1[ido - 1] - c3[ido - 1]);
-      o[ido - 1]     = tr1 + c0[ido - 1];
-      o[3 * ido - 1] = c0[ido - 1] - tr1;
-      o[ido]         = ti1 - c2[ido - 1];
-      o[3 * ido]     = ti1 + c2[ido - 1];
+      const int c0 = k * ido + ido - 1, c1 = c0 + t0, c2 = c1 + t0, c3 = c2 + t0;
+      const int o = 4 * k * ido;
+      const float a0 = cc[fft_rd<FIRST>(c0)], a1 = cc[fft_rd<FIRST>(c1)];
+      const float a2 = cc[fft_rd<FIRST>(c2)], a3 = cc[fft_rd<FIRST>(c3)];
+      const float ti1 = -hsqt2 * (a1 + a3);
+      const float tr1 =  hsqt2 * (a1 - a3);
+      *reinterpret_cast<float2 *>(ch + fft_idx(o + ido - 1))     = make_float2(tr1 + a0, ti1 - a2);   // o[ido-1], o[ido]
+      *reinterpret_cast<float2 *>(ch + fft_idx(o + 3 * ido - 1)) = make_float2(a0 - tr1, ti1 + a2);   // o[3ido-1], o[3ido]
     }
   }
 }
 
+template <bool FIRST>
 __device__ __forceinline__ void dev_fft_pass2(int ido, int l1, const float *cc, float *ch,
                                               const float *w1, int tid, int nt) {
   const int t0 = l1 * ido;
   if (ido == 1) {
     for (int k = tid; k < l1; k += nt) {
-      const float a = cc[k], b = cc[k + t0];
-      ch[2 * k] = a + b;
-      ch[2 * k + 1] = a - b;
+      const float a = cc[fft_rd<FIRST>(k)], b = cc[fft_rd<FIRST>(k + t0)];
+      ch[fft_idx(2 * k)] = a + b;
+      ch[fft_idx(2 * k + 1)] = a - b;
     }
     return;
   }
@@ -434,36 +478,35 @@ __device__ __forceinline__ void dev_fft_pass2(int ido, int l1, const float *cc, 
   for (int v = tid; v < items + l1; v += nt) {
     if (v < items) {
       const int k = v >> hsh, ii = v & (half - 1);
-      const float *c0 = cc + k * ido, *c1 = c0 + t0;
-      float *o = ch + 2 * k * ido;
+      const int c0 = k * ido, c1 = c0 + t0;
+      const int o = 2 * k * ido;
       if (ii == 0) {
-        o[0]           = c0[0] + c1[0];
-        o[2 * ido - 1] = c0[0] - c1[0];
+        const float a0 = cc[fft_rd<FIRST>(c0)], a1 = cc[fft_rd<FIRST>(c1)];
+        ch[fft_idx(o)]               = a0 + a1;
+        ch[fft_idx(o + 2 * ido - 1)] = a0 - a1;
       } else {
         const int i = 2 * ii;
         const float wr = __ldg(w1 + i - 2), wi = __ldg(w1 + i - 1);
-        const float2 a0 = *reinterpret_cast<const float2 *>(c0 + i - 1);
-        const float2 a1 = *reinterpret_cast<const float2 *>(c1 + i - 1);
+        const float2 a0 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c0 + i - 1));
+        const float2 a1 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c1 + i - 1));
         const float tr2 = wr * a1.x + wi * a1.y;
         const float ti2 = wr * a1.y - wi * a1.x;
         const int ic = 2 * ido - i;
-        *reinterpret_cast<float2 *>(o + i - 1)  = make_float2(a0.x + tr2, a0.y + ti2);
-        *reinterpret_cast<float2 *>(o + ic - 1) = make_float2(a0.x - tr2, ti2 - a0.y);
+        *reinterpret_cast<float2 *>(ch + fft_idx(o + i - 1))  = make_float2(a0.x + tr2, a0.y + ti2);
+        *reinterpret_cast<float2 *>(ch + fft_idx(o + ic - 1)) = make_float2(a0.x - tr2, ti2 - a0.y);
       }
     } else {
       const int k = v - items;
-      const float *c0 = cc + k * ido, *c1 = c0 + t0;
-      float *o = ch + 2 * k * ido;
-      o[ido]     = -c1[ido - 1];
-      o[ido - 1] = c0[ido - 1];
+      const int c0 = k * ido + ido - 1, c1 = c0 + t0;
+      const int o = 2 * k * ido;
+      *reinterpret_cast<float2 *>(ch + fft_idx(o + ido - 1)) = make_float2(cc[fft_rd<FIRST>(c0)], -cc[fft_rd<FIRST>(c1)]);   // o[ido-1], o[ido]
     }
   }
 }
 
-// a: N input floats (16-byte aligned, unshifted).  a and b must each have room for N+2 floats.
-// Every pass writes its output shifted by ONE float (logical element e at address e+1) so that
-// FFTPACK's (re,im) pairs at (2k-1,2k) are 8-byte aligned; the first pass (ido == 1, no pairs)
-// reads the unshifted input.  Returns a pointer to logical element 0 of the result.
+// a: N plain input floats (16-byte aligned).  a and b must each have room for fft_buf_floats(N) floats:
+// after the first pass `a` is reused as a padded ping-pong buffer.  Returns the buffer that holds the
+// result; logical element e of it is at [fft_idx(e)].
 template <int NC>
 __device__ __forceinline__ float *dev_drft_forward(const XformDev &X, float *a, float *b,
                                                    int tid, int nt) {
@@ -473,19 +516,21 @@ __device__ __forceinline__ float *dev_drft_forward(const XformDev &X, float *a, 
   const int log2n = NC ? XLog2<NC>::v : X.log2n;
   const int nf = (log2n + 1) >> 1;
   int l2 = N, iw = N;
-  float *src = a, *dst = b + 1;
+  float *src = a, *dst = b;
 #pragma unroll
   for (int k1 = 0; k1 < nf; k1++) {
     const int ip = (k1 == nf - 1 && (log2n & 1)) ? 2 : 4;
     const int l1 = l2 / ip, ido = N / l2;
     iw -= (ip - 1) * ido;
-    if (ip == 4)
-      dev_fft_pass4(ido, l1, src, dst, X.wa + iw - 1, X.wa + iw + ido - 1, X.wa + iw + 2 * ido - 1, tid, nt);
-    else
-      dev_fft_pass2(ido, l1, src, dst, X.wa + iw - 1, tid, nt);
+    if (k1 == 0) {
+      if (ip == 4) dev_fft_pass4<true>(ido, l1, src, dst, X.wa + iw - 1, X.wa + iw + ido - 1, X.wa + iw + 2 * ido - 1, tid, nt);
+      else dev_fft_pass2<true>(ido, l1, src, dst, X.wa + iw - 1, tid, nt);
+    } else {
+      if (ip == 4) dev_fft_pass4<false>(ido, l1, src, dst, X.wa + iw - 1, X.wa + iw + ido - 1, X.wa + iw + 2 * ido - 1, tid, nt);
+      else dev_fft_pass2<false>(ido, l1, src, dst, X.wa + iw - 1, tid, nt);
+    }
     __syncthreads();
-    float *t = (k1 == 0) ? a + 1 : src;     // after the first pass `a` is reused shifted as well
-    src = dst; dst = t;
+    float *t = src; src = dst; dst = t;
     l2 = l1;
   }
   return src;
@@ -506,22 +551,32 @@ __device__ __forceinline__ float dev_window_gain(const WinDev &Wd, int W, int lW
   return 1.f;   // flat middle: sample is left untouched (x*1.0f is exact)
 }
 
+// The window regions all start on multiples of four samples (block sizes are powers of two >= 64), so a
+// float4 never straddles two regions: one decision and at most one 128-bit table load per four samples.
+__device__ __forceinline__ float4 dev_window4(const WinDev &Wd, int W, int lW, int nW, int i0, float4 x) {
+  if (!W) { lW = 0; nW = 0; }
+  const int n = Wd.N[W], ln = Wd.N[lW], rn = Wd.N[nW];
+  const int leftbegin = n / 4 - ln / 4, leftend = leftbegin + ln / 2;
+  const int rightbegin = n / 2 + n / 4 - rn / 4, rightend = rightbegin + rn / 2;
+  if (i0 < leftbegin || i0 >= rightend) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i0 < leftend) {
+    const float4 g = __ldg(reinterpret_cast<const float4 *>(Wd.win[lW] + (i0 - leftbegin)));
+    return make_float4(x.x * g.x, x.y * g.y, x.z * g.z, x.w * g.w);
+  }
+  if (i0 >= rightbegin) {                           // the falling half reads the table backwards
+    const float4 g = __ldg(reinterpret_cast<const float4 *>(Wd.win[nW] + (rn / 2 - 4 - (i0 - rightbegin))));
+    return make_float4(x.x * g.w, x.y * g.z, x.z * g.y, x.w * g.x);
+  }
+  return x;                                         // flat middle: untouched (x*1.0f is exact)
+}
+
 __device__ __forceinline__ void dev_load_windowed(const WinDev &Wd, int W, int lW, int nW,
                                                   const float *__restrict__ src, float *dst,
                                                   int tid, int nt) {
   const int N = Wd.N[W];
   const float4 *s4 = reinterpret_cast<const float4 *>(src);
-  for (int v = tid; v < (N >> 2); v += nt) {
-    const float4 x = __ldg(s4 + v);
-    float4 o;
-    bool z;
-    float g;
-    g = dev_window_gain(Wd, W, lW, nW, 4 * v + 0, z); o.x = z ? 0.f : x.x * g;
-    g = dev_window_gain(Wd, W, lW, nW, 4 * v + 1, z); o.y = z ? 0.f : x.y * g;
-    g = dev_window_gain(Wd, W, lW, nW, 4 * v + 2, z); o.z = z ? 0.f : x.z * g;
-    g = dev_window_gain(Wd, W, lW, nW, 4 * v + 3, z); o.w = z ? 0.f : x.w * g;
-    *reinterpret_cast<float4 *>(dst + 4 * v) = o;
-  }
+  for (int v = tid; v < (N >> 2); v += nt)
+    *reinterpret_cast<float4 *>(dst + 4 * v) = dev_window4(Wd, W, lW, nW, 4 * v, __ldg(s4 + v));
 }
 
 // ------------------------------------------------------------------------

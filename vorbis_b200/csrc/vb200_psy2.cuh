@@ -49,8 +49,8 @@ __host__ __device__ inline size_t psy2_floats(int n, int total, int nruns, int n
 // made the kernel ~93 KB of SASS and 11 % of the stall samples were instruction-cache misses.
 // They are real functions here (scalars only in the signature, so nothing spills to local).
 template <int NS>
-__device__ __noinline__ float regress_core(const int *__restrict__ bark, int bfe, int ffe, const float *S,
-                                           int i, float offset, int fixed) {
+__device__ __forceinline__ float dev_regress_bin(const int *__restrict__ bark, int bfe, int ffe, const float *S,
+                                                 int i, float offset, int fixed) {
   Abd cur; cur.A = 0.f; cur.B = 0.f; cur.D = 1.f;
   if (bfe > 0) {
     const int wb = i < bfe ? i : bfe - 1;
@@ -74,6 +74,12 @@ __device__ __noinline__ float regress_core(const int *__restrict__ bark, int bfe
     if (R2 - offset < v) v = R2 - offset;
   }
   return v;
+}
+
+template <int NS>
+__device__ __noinline__ float regress_core(const int *__restrict__ bark, int bfe, int ffe, const float *S,
+                                           int i, float offset, int fixed) {
+  return dev_regress_bin<NS>(bark, bfe, ffe, S, i, offset, fixed);
 }
 
 // final step of _vp_noisemask for one bin + tone lookup + _vp_offset_and_mix(select 1);

@@ -202,23 +202,28 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
     float a0 = 0.f, a1 = 0.f;
     int l0 = 0, l1 = 0, depth = 0, i = start;
     float s = lds_f32(as_ + 4u * (unsigned)i);
+    const unsigned tl = (unsigned)(total - 1);
     while (i <= last) {
       // lib/psy.c:465-484: pop while !(seeds[i] < amp[top]) and the two top entries both reach past i and
-      // amp[top] <= amp[top-1]
+      // amp[top] <= amp[top-1]; otherwise push.  Branch free: every lane does exactly one of the two per
+      // iteration, the memory operations are predicated.
       const bool pop = depth >= 2 && !(s < a0) && i < l0 && a0 <= a1 && i < l1;
-      if (pop) {
-        depth--;
-        a0 = a1; l0 = l1;
-        if (depth >= 2) { a1 = lds_f32(aa + 4u * (unsigned)(depth - 2)); l1 = lds_s16(ap + 2u * (unsigned)(depth - 2)) + L; }
-      } else {
-        if (i < end) {                               // i == end: only the pops belong to this segment
-          sts_f32(aa + 4u * (unsigned)depth, s); sts_s16(ap + 2u * (unsigned)depth, i);
-          a1 = a0; l1 = l0; a0 = s; l0 = i + L;
-          depth++;
-        }
-        i++;
-        s = lds_f32(as_ + 4u * (unsigned)(i < total ? i : total - 1));
-      }
+      const bool push = !pop && i < end;             // i == end: only the pops belong to this segment
+      const bool rel = pop && depth >= 3;            // the new second entry comes back from shared memory
+      const unsigned o = (unsigned)(pop ? depth - 3 : depth);
+      const float ra = lds_f32_if(aa + 4u * o, a1, rel);
+      const int rl = lds_s16_if(ap + 2u * o, l1 - L, rel) + L;
+      sts_f32_if(aa + 4u * o, s, push);
+      sts_s16_if(ap + 2u * o, i, push);
+      const float na0 = pop ? a1 : (push ? s : a0);
+      const int nl0 = pop ? l1 : (push ? i + L : l0);
+      a1 = pop ? ra : (push ? a0 : a1);
+      l1 = pop ? rl : (push ? l0 : l1);
+      a0 = na0; l0 = nl0;
+      depth += pop ? -1 : (push ? 1 : 0);
+      i += pop ? 0 : 1;
+      const unsigned in = (unsigned)i < tl ? (unsigned)i : tl;
+      s = lds_f32_if(as_ + 4u * in, s, !pop);
     }
     cnt = depth;
   }
@@ -263,9 +268,8 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
 // The running sums are strictly sequential fp32 (order matters): five lanes, one array each.
 // Two register sets alternate so that the next 16 values are in flight while 16 are accumulated and
 // nothing is copied between registers.
-__device__ __forceinline__ void dev_noise_scan3(int n, float *S, int ns, int lane) {
-  if (lane >= 5) return;
-  float4 *a = reinterpret_cast<float4 *>(S + lane * ns);
+__device__ __forceinline__ void dev_noise_scan3(int n, float *arr) {
+  float4 *a = reinterpret_cast<float4 *>(arr);
   const int q = n >> 2;                   // float4 count, a multiple of 8 (n is a multiple of 128)
   float t = 0.f;
   float4 v0 = a[0], v1 = a[1], v2 = a[2], v3 = a[3];
@@ -281,17 +285,64 @@ __device__ __forceinline__ void dev_noise_scan3(int n, float *S, int ns, int lan
 #undef SCAN4
 }
 
-template <int K>   // K = n / 128 bins per thread
-__global__ void __launch_bounds__(PSY3_THREADS, PSY3_MINB)
+// Two bins per call: halves the call overhead of the (deliberately not inlined, see vb200_psy2.cuh) per-bin
+// regression and gives the scheduler two independent dependency chains.
+template <int NS>
+__device__ __noinline__ float2 regress_pair(const int *__restrict__ bark, int bfe, int ffe, const float *S,
+                                            int i0, int i1, float offset, int fixed) {
+  float2 r;
+  r.x = dev_regress_bin<NS>(bark, bfe, ffe, S, i0, offset, fixed);
+  r.y = dev_regress_bin<NS>(bark, bfe, ffe, S, i1, offset, fixed);
+  return r;
+}
+
+// final step of _vp_noisemask + tone lookup + _vp_offset_and_mix(select 1) for one bin, everything by value
+struct MixOut { float logmask, m, nz, tn; };
+__device__ __noinline__ MixOut final_mix_val(float p2, float L, float p1, float noff, float ath, float gmin,
+                                             const float *__restrict__ compand, MixConst C, float m) {
+  MixOut o;
+  const float work = L - p1;                       // lib/psy.c:717
+  const float base = L - work;                     // lib/psy.c:722
+  int dB = (int)((double)p2 + .5);
+  if (dB >= VB200_COMPAND_LEVELS) dB = VB200_COMPAND_LEVELS - 1;
+  if (dB < 0) dB = 0;
+  const float nz = base + __ldg(compand + dB);
+  float tn = ath + C.att;                          // lib/psy.c:771, then max_seeds' flr update
+  if (tn < gmin) tn = gmin;
+  o.nz = nz; o.tn = tn;
+  float val = nz + noff;                           // lib/psy.c:789-791
+  if (val > C.noisemaxsupp) val = C.noisemaxsupp;
+  const float t = tn + C.toneatt;
+  o.logmask = val < t ? t : val;
+  const float coeffi = -17.2f;
+  float de;
+  val = val - L;
+  if (val > coeffi) {
+    de = (float)(1.0 - ((double)(val - coeffi) * 0.005 * (double)C.m_val));
+    if (de < 0.f) de = 0.0001f;
+  } else {
+    de = (float)(1.0 - ((double)(val - coeffi) * 0.0003 * (double)C.m_val));
+  }
+  o.m = m * de;
+  return o;
+}
+
+// K = n / 128 bins per thread; R = rows per CTA (128 threads each).  The R rows of a CTA run in lockstep and
+// share ONE scan warp: its lanes 5r..5r+4 carry the five running sums of row r, so the 1024 dependent
+// warp-level FADDs per scan are paid once per R rows.
+template <int K, int R>
+__global__ void __launch_bounds__(PSY3_THREADS * R, PSY3_MINB / R)
 k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
-  extern __shared__ __align__(16) float sm[];
+  extern __shared__ __align__(16) float sm_cta[];
   constexpr int nt = PSY3_THREADS;
-  const int n = K * nt, ns = n + 4, tid = threadIdx.x, lane = tid & 31;
+  const int n = K * nt, ns = n + 4, tid = threadIdx.x & (nt - 1), half = threadIdx.x >> 7, lane = tid & 31;
   const int total = P0.total > P1.total ? P0.total : P1.total;
   const int nruns = P0.nruns > P1.nruns ? P0.nruns : P1.nruns;
   const int ngrp = P0.ngrp > P1.ngrp ? P0.ngrp : P1.ngrp;
   const int tp = (total + 7) & ~7;
-  // carve: [ scan area | tone scratch (aliased) ] [ grp_min ] [ misc ]
+  const size_t row_floats = (psy3_floats(n, total, nruns, ngrp) + 3) & ~(size_t)3;
+  float *sm = sm_cta + half * row_floats;
+  // carve (per row): [ scan area | tone scratch (aliased) ] [ grp_min ] [ misc ]
   float *S = sm;
   float *s_fft = sm;                                 // dead once the run records exist
   float *copies = sm;                                // 4 x tp
@@ -300,7 +351,9 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
   const size_t area = psy3_floats(n, total, nruns, ngrp) - (size_t)((ngrp + 1 + 3) & ~3) - 16;
   float *grp_min = sm + area;
   int *s_misc = reinterpret_cast<int *>(grp_min + ((ngrp + 1 + 3) & ~3));
-  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+  for (int row0 = blockIdx.x * R; row0 < nrows; row0 += gridDim.x * R) {
+    // an odd tail: the spare half repeats the last row (identical values to identical addresses)
+    const int row = row0 + half < nrows ? row0 + half : nrows - 1;
     const int blk = row / ch;
     const PsyDev &P = A.desc[blk].blocktype ? P1 : P0;
     const float *gm = A.mdct_in + (size_t)row * n;
@@ -312,7 +365,7 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     int tph = 0;
 #define PHASE_MARK()                                                              \
     do {                                                                          \
-      if (A.dbg_cycles && tid == 0) {                                             \
+      if (A.dbg_cycles && threadIdx.x == 0) {                                     \
         const long long tnow = clock64();                                         \
         atomicAdd(A.dbg_cycles + tph, (unsigned long long)(tnow - tmark));        \
         tmark = tnow;                                                             \
@@ -338,7 +391,7 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     dev_tone_scatter3(P, copies, tp, run_rec, tid);
     __syncthreads();
     PHASE_MARK();   // 2 scatter
-    dev_chase3(P, copies, tp, s_misc, tid, A.dbg_cycles);
+    dev_chase3(P, copies, tp, s_misc, tid, half == 0 ? A.dbg_cycles : nullptr);
     PHASE_MARK();   // 3 chase
     // max_seeds gather, first half: one minimum per static group (lib/psy.c:522-533)
     const float *seed = copies;
@@ -390,12 +443,19 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k], 140.f, S, ns);
     __syncthreads();
     PHASE_MARK();   // 5 terms 1
-    if (tid < 32) dev_noise_scan3(n, S, ns, lane);
+    if (threadIdx.x < 5 * R) dev_noise_scan3(n, sm_cta + (threadIdx.x / 5) * row_floats + (threadIdx.x % 5) * ns);
     __syncthreads();
     PHASE_MARK();   // 6 scan 1
+    if (K >= 2) {
 #pragma unroll
-    for (int k = 0; k < K; k++)
-      p1[k] = regress_core<K * PSY3_THREADS + 4>(P.bark, P.bark_first_extra, P.fixed_first_extra, S, tid + k * nt, 140.f, -1);
+      for (int k = 0; k + 1 < K; k += 2) {
+        const float2 r = regress_pair<K * PSY3_THREADS + 4>(P.bark, P.bark_first_extra, P.fixed_first_extra, S,
+                                                            tid + k * nt, tid + (k + 1) * nt, 140.f, -1);
+        p1[k] = r.x; p1[k + 1] = r.y;
+      }
+    } else {
+      p1[0] = regress_core<K * PSY3_THREADS + 4>(P.bark, P.bark_first_extra, P.fixed_first_extra, S, tid, 140.f, -1);
+    }
     __syncthreads();
     PHASE_MARK();   // 7 regress 1
     // ---- pass 2 on logmdct - p1 (offset 0, bark + fixed windows)
@@ -403,7 +463,7 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k] - p1[k], 0.f, S, ns);
     __syncthreads();
     PHASE_MARK();   // 8 terms 2
-    if (tid < 32) dev_noise_scan3(n, S, ns, lane);
+    if (threadIdx.x < 5 * R) dev_noise_scan3(n, sm_cta + (threadIdx.x / 5) * row_floats + (threadIdx.x % 5) * ns);
     __syncthreads();
     PHASE_MARK();   // 9 scan 2
     MixConst MC;
@@ -413,17 +473,25 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     const int *bark = P.bark; const float *athp = P.ath, *compand = P.noisecompand;
     const short *bin_grp = P.bin_grp;
     const int bfe = P.bark_first_extra, ffe = P.fixed_first_extra, fixedw = P.noisewindowfixed;
+    float p2[K];
+    if (K >= 2) {
+#pragma unroll
+      for (int k = 0; k + 1 < K; k += 2) {
+        const float2 r = regress_pair<K * PSY3_THREADS + 4>(bark, bfe, ffe, S, tid + k * nt, tid + (k + 1) * nt, 0.f, fixedw);
+        p2[k] = r.x; p2[k + 1] = r.y;
+      }
+    } else {
+      p2[0] = regress_core<K * PSY3_THREADS + 4>(bark, bfe, ffe, S, tid, 0.f, fixedw);
+    }
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const int i = tid + k * nt;
-      const float p2 = regress_core<K * PSY3_THREADS + 4>(bark, bfe, ffe, S, i, 0.f, fixedw);
-      float m = M[k], nz, tn;
-      const float lm = final_mix_core(p2, L[k], p1[k], __ldg(noff + i), __ldg(athp + i),
-                                      grp_min[__ldg(bin_grp + i)], compand, MC, m, nz, tn);
-      __stcs(A.logmask + (size_t)row * n + i, lm);
-      __stcs(A.mdct_out + (size_t)row * n + i, m);
-      if (A.tap_noise) A.tap_noise[(size_t)row * n + i] = nz;
-      if (A.tap_tone) A.tap_tone[(size_t)row * n + i] = tn;
+      const MixOut o = final_mix_val(p2[k], L[k], p1[k], __ldg(noff + i), __ldg(athp + i),
+                                     grp_min[__ldg(bin_grp + i)], compand, MC, M[k]);
+      __stcs(A.logmask + (size_t)row * n + i, o.logmask);
+      __stcs(A.mdct_out + (size_t)row * n + i, o.m);
+      if (A.tap_noise) A.tap_noise[(size_t)row * n + i] = o.nz;
+      if (A.tap_tone) A.tap_tone[(size_t)row * n + i] = o.tn;
     }
     if (tid == 0 && (row % ch) == 0) A.ampmax_out[blk] = g;   // lib/mapping0.c:576
     __syncthreads();

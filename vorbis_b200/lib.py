@@ -35,6 +35,7 @@ EXPORTS = [
     "vb200_envelope_search_dev", "vb200_envelope_search", "vb200_envelope_apply_marks",
     "vb200_floor1_inverse2_dev", "vb200_floor1_inverse2", "vb200_decode_dsp_dev", "vb200_decode_dsp",
     "vb200_residue_partvals", "vb200_residue_classify_dev", "vb200_residue_classify",
+    "vb200_plan_blocks", "vb200_encode_streams_dev", "vb200_encode_streams",
     "vb200_malloc_device", "vb200_free_device", "vb200_memcpy_h2d", "vb200_memcpy_d2h", "vb200_synchronize",
 ]
 
@@ -108,6 +109,9 @@ def load():
     L.vb200_envelope_search.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int64, C.c_int, C.c_int, vp, vp]
     L.vb200_envelope_apply_marks.argtypes = [vp, C.c_int, C.c_int, vp]
     L.vb200_envelope_apply_marks.restype = None
+    L.vb200_plan_blocks.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int, vp, vp, C.c_int, vp, vp]
+    L.vb200_encode_streams.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.StreamsIO)]
+    L.vb200_encode_streams_dev.argtypes = [vp, C.c_int, C.c_int, C.POINTER(abi.StreamsIO), vp]
     L.vb200_malloc_device.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     L.vb200_free_device.argtypes = [vp, vp]
     L.vb200_memcpy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
@@ -320,6 +324,60 @@ class Context:
     def floor1_render_dev(self, W, nrows, d_posts, d_fit_nonzero, d_ilogmask, d_nonzero, floor_sel=-1, stream=None):
         self._chk(self.L.vb200_floor1_render_dev(self.h, W, floor_sel, nrows, _ptr(d_posts), _ptr(d_fit_nonzero),
                                                  _ptr(d_ilogmask), _ptr(d_nonzero), _ptr(stream)))
+
+    # ---- whole streams: envelope marks -> block plan -> both block sizes, ampmax chain across sizes ----
+    def plan_blocks(self, mark, nsteps, pcm_len, eof=None, max_blocks=None):
+        """mark [streams][stride] int32 (timeline steps), pcm_len/eof [streams] int64 -> (plan, nblocks)"""
+        mark = np.ascontiguousarray(mark, np.int32)
+        ns, stride = mark.shape
+        pcm_len = np.ascontiguousarray(pcm_len, np.int64)
+        eofp = None if eof is None else np.ascontiguousarray(eof, np.int64)
+        if max_blocks is None:
+            max_blocks = int(pcm_len.max()) // (self.bs[0] // 2) + 8
+        plan = np.zeros((ns, max_blocks), abi.STREAM_BLOCK_DTYPE)
+        nb = np.zeros(ns, np.int32)
+        self._chk(self.L.vb200_plan_blocks(self.h, ns, mark.ctypes.data, stride, int(nsteps), pcm_len.ctypes.data,
+                                        None if eofp is None else eofp.ctypes.data, max_blocks, plan.ctypes.data,
+                                        nb.ctypes.data))
+        return plan, nb
+
+    def encode_streams(self, pcm, pcm_len, eof=None, fmt=PCM_F32_PLANAR, max_blocks=None, cap=None, blobno=7):
+        """pcm: timeline buffers, PCM_F32_PLANAR [streams][ch][stride] float32 or PCM_S16_INTERLEAVED
+        [streams][stride][ch] int16.  Returns plan, nblocks and per block size W the batch outputs."""
+        ch = self.channels
+        if fmt == PCM_F32_PLANAR:
+            pcm = np.ascontiguousarray(pcm, np.float32)
+            ns, stride = pcm.shape[0], pcm.shape[2]
+            assert pcm.shape[1] == ch
+        else:
+            pcm = np.ascontiguousarray(pcm, np.int16)
+            ns, stride = pcm.shape[0], pcm.shape[1]
+            assert pcm.shape[2] == ch
+        pcm_len = np.ascontiguousarray(pcm_len, np.int64)
+        eofp = None if eof is None else np.ascontiguousarray(eof, np.int64)
+        if max_blocks is None:
+            max_blocks = stride // (self.bs[0] // 2) + 8
+        if cap is None:
+            cap = [ns * max_blocks, ns * (stride // (self.bs[1] // 2) + 8)]
+        io = abi.StreamsIO()
+        io.pcm, io.pcm_fmt, io.max_blocks, io.stream_stride = pcm.ctypes.data, fmt, max_blocks, stride
+        io.pcm_len = pcm_len.ctypes.data
+        io.eof = None if eofp is None else eofp.ctypes.data
+        plan = np.zeros((ns, max_blocks), abi.STREAM_BLOCK_DTYPE)
+        nb = np.zeros(ns, np.int32)
+        io.plan, io.nblocks = plan.ctypes.data, nb.ctypes.data
+        out = {}
+        for w in range(2):
+            n = self.bs[w] // 2
+            io.cap[w] = int(cap[w])
+            out[w] = {"posts": np.zeros((cap[w], ch, abi.FLOOR1_STRIDE), np.int32), "nonzero": np.zeros((cap[w], ch), np.int32),
+                      "iwork": np.zeros((cap[w], ch, n), np.int32), "ampmax_out": np.zeros(cap[w], np.float32)}
+            io.posts[w], io.nonzero[w] = out[w]["posts"].ctypes.data, out[w]["nonzero"].ctypes.data
+            io.iwork[w], io.ampmax_out[w] = out[w]["iwork"].ctypes.data, out[w]["ampmax_out"].ctypes.data
+        self._chk(self.L.vb200_encode_streams(self.h, ns, blobno, C.byref(io)))
+        for w in range(2):
+            out[w] = {k: v[:io.count[w]] for k, v in out[w].items()}
+        return {"plan": plan, "nblocks": nb, "count": [io.count[0], io.count[1]], 0: out[0], 1: out[1]}
 
     # ---- whole per-block encode DSP (Phase A -> floor1 -> Phase B) in one call ---------------
     def encode_dsp(self, W, pcm, desc, nstreams=None, fmt=0, hop=0, ampmax0=None, independent=None, blobno=7,
