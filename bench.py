@@ -156,6 +156,28 @@ def usable_cpus():
     return cpus[:n], {"affinity": len(cpus), "cgroup_quota": quota, "os_cpu_count": os.cpu_count()}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off: the H2D/D2H DMA of
+    the end-to-end path then stays on one socket.  Returns a short description for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return {"gpu": bdf, "numa_node": None}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0))
+        use = sorted(cpus & allowed)
+        if use:
+            os.sched_setaffinity(0, use)
+        return {"gpu": bdf, "numa_node": node, "cpus_bound": len(use)}
+    except Exception as e:  # binding is an optimisation, never a reason to fail
+        return {"error": repr(e)}
+
+
 def cpu_worker_main(argv):
     """`bench.py --cpu-worker cpu blocks reps seed`: ONE process pinned to ONE cpu running the reference
     chain (oracle/_ref when built, else the oracle port) on its own synthetic blocks.  Protocol on
@@ -237,10 +259,10 @@ class CpuPool:
                 p.kill()
 
 
-def cpu_reference_rates(blocks_per_core, steps, warmup, single_core=True):
+def cpu_reference_rates(blocks_per_core, steps, warmup, single_core=True, cpus_info=None):
     """(all-core dict, 1-core dict or None).  Every step is a bounded sample: blocks_per_core long stereo
     blocks on every usable cpu."""
-    cpus, info = usable_cpus()
+    cpus, info = cpus_info if cpus_info else usable_cpus()
     pool = CpuPool(cpus, blocks_per_core)
     try:
         for _ in range(warmup):
@@ -532,6 +554,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus_info = usable_cpus()                    # before the NUMA binding below narrows this process' affinity
+    numa = bind_to_gpu_numa_node(torch, local)
     setup = abi.SetupHolder.load(os.path.join(GOLD, "setup_44k_stereo_q5.npz"))
     ctx = lib.Context(setup, device=local)       # raises if the CUDA library is missing
     N, ch = setup.blocksize(W_LONG), setup.channels
@@ -666,7 +690,7 @@ def run_ours(args):
     verified_e2e = verify_against_oracle(setup, W_LONG, blk, hdesc[bsel], got_e, streams=(len(ssel), bps), what="e2e step")
     e2e = {"value": world * nb_e * args.steps / dt_max, "unit": UNIT,
            "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-           "blocks_per_step": nb_e * world, "gpu_launches": int(e2e_launches),
+           "blocks_per_step": nb_e * world, "gpu_launches": int(e2e_launches), "numa": numa,
            "verified_blocks_vs_oracle": verified_e2e,
            "call": "vb200_encode_dsp: %d streams x %d blocks per GPU, int16 interleaved stream PCM in (hop N/2, "
                    "blocks cut on the device), posts+nonzero+quantised residue (int16, overflow-counted) out; pinned host memory; "
@@ -708,7 +732,7 @@ def run_ours(args):
                 "phaseA_only_blocks_per_s": float(nb / (kms[:3].sum() * 1e-3))}
 
         # ---- CPU baseline on a bounded sample of the same workload (same chain, reference functions)
-        cpu, cpu1 = cpu_reference_rates(args.ref_blocks_per_core, 2, 1)
+        cpu, cpu1 = cpu_reference_rates(args.ref_blocks_per_core, 2, 1, cpus_info=cpus_info)
 
         extra = None
         if not args.no_extra:

@@ -15,6 +15,8 @@ from vorbis_b200 import abi
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "libvorbis_ref.so")
 DROPIN_PATH = os.path.join(HERE, "_ref", "libvorbis_dropin.so")
+if os.environ.get("VB200_DROPIN_EMU"):      # development aid (tools/cuemu): the drop-in linked against the host emulation
+    DROPIN_PATH = os.path.join(HERE, "_ref", "libvorbis_dropin_emu.so")
 
 f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
@@ -56,6 +58,7 @@ def dropin_lib():
         _declare(L)
         L.vb200shim_attach.argtypes = [C.c_void_p, C.c_int]
         L.vb200shim_launches.restype = C.c_ulonglong
+        L.ref_use_block_seam.argtypes = [C.c_int]
         _dropin = L
     return _dropin
 

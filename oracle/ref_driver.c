@@ -518,6 +518,11 @@ static void keep_packet(ref_handle *h, ogg_packet *op){
  * blocksizes[1]/2 samples, the input, and the extrapolated tail that vorbis_analysis_wrote(v,0)
  * appends.  The buffer is [ch][cap]; *len_out = samples recorded, *eof_out = v->eofflag in the
  * same coordinates.  Call before ref_encode_capture; cleared by it.                                */
+#ifdef VB200_DROPIN
+int vb200_vorbis_analysis(vorbis_block *vb, ogg_packet *op);   /* vorbis_b200/host/vb200_mapping0.c */
+static int g_seam1 = 0;
+void ref_use_block_seam(int on){ g_seam1 = on; }   /* ref_encode_capture: vorbis_analysis through vb200_mapping0_exportbundle */
+#endif
 static long g_chunk = 0;
 void ref_set_chunk(long n){ g_chunk = n; }   /* samples per vorbis_analysis_wrote of ref_encode_capture (default 1024) */
 static float *g_tl = NULL; static long g_tl_cap = 0, g_tl_len = 0, g_tl_shift = 0, g_tl_eof = 0;
@@ -576,6 +581,10 @@ int ref_encode_capture(void *hv, const float *pcm, long nsamples, ref_capture *c
         cap->blocktype[blocks]=vbi->blocktype;
         cap->ampmax_in[blocks]=vbi->ampmax;
       }
+#ifdef VB200_DROPIN
+      if(g_seam1){ if(vb200_vorbis_analysis(&h->vb,NULL)){ g_cap = NULL; g_blk = -1; g_tl = NULL; return -1; } }
+      else
+#endif
       vorbis_analysis(&h->vb,NULL);
       if(cap_on()) cap->ampmax_out[blocks]=vbi->ampmax;
       vorbis_bitrate_addblock(&h->vb);
@@ -895,3 +904,91 @@ void ref_residue_classify(void *hv, int W, int nblocks, const int32_t *iwork, co
   }
   free(bundle); free(zb); free(chan); free(copy);
 }
+
+
+
+/* packet summary: (count, bytes, FNV-1a over all packet bytes in order) of one encoder run */
+typedef struct { uint64_t *hash; long *bytes, *count; int *eos; } ms_sum;
+static void ms_sink(void *user, int stream, ogg_packet *op){
+  ms_sum *s = (ms_sum*)user;
+  long k;
+  uint64_t h = s->hash[stream];
+  for(k = 0; k < op->bytes; k++){ h ^= op->packet[k]; h *= 1099511628211ULL; }
+  h ^= (uint64_t)op->bytes; h *= 1099511628211ULL;
+  s->hash[stream] = h; s->bytes[stream] += op->bytes; s->count[stream]++;
+  if(op->e_o_s) s->eos[stream] = 1;
+}
+/* the same summary for ONE stock reference encoder (this library's vorbis_analysis: the unmodified CPU path in libvorbis_ref.so) */
+long ref_stock_encode_summary(int ch, long rate, float quality, const float *pcm, long nsamples,
+                              uint64_t *hash, long *bytes, long *count){
+  ref_handle *h = (ref_handle*)ref_open(ch, rate, quality);
+  ms_sum sum; int eos = 0, i; long pos = 0, blocks = 0;
+  ogg_packet op;
+  const long chunk = g_chunk > 0 ? g_chunk : 1024;
+  if(!h) return -1;
+  *hash = 1469598103934665603ULL; *bytes = 0; *count = 0;
+  sum.hash = hash; sum.bytes = bytes; sum.count = count; sum.eos = &eos;
+  while(!eos){
+    long todo = nsamples - pos < chunk ? nsamples - pos : chunk;
+    if(todo > 0){
+      float **buf = vorbis_analysis_buffer(&h->vd, (int)todo);
+      for(i = 0; i < ch; i++) memcpy(buf[i], pcm + (size_t)i*nsamples + pos, sizeof(float)*todo);
+      vorbis_analysis_wrote(&h->vd, (int)todo);
+      pos += todo;
+    }else vorbis_analysis_wrote(&h->vd, 0);
+    while(vorbis_analysis_blockout(&h->vd, &h->vb) == 1){
+      vorbis_analysis(&h->vb, NULL);
+      vorbis_bitrate_addblock(&h->vb);
+      while(vorbis_bitrate_flushpacket(&h->vd, &op)) ms_sink(&sum, 0, &op);
+      blocks++;
+    }
+    if(todo <= 0) eos = 1;
+  }
+  ref_close(h);
+  return blocks;
+}
+
+#ifdef VB200_DROPIN
+/* ---- multi-stream driver test hook (vorbis_b200/host/vb200_mapping0.c): N encoders of one configuration fed in
+ * lockstep with 1024-sample writes; every stream's packets are summarised as (count, bytes, FNV-1a hash of all
+ * packet bytes in order) so that they can be compared with N runs of the stock reference encoder.             */
+typedef struct vb200ms vb200ms;
+typedef void (*vb200ms_sink)(void *user, int stream, ogg_packet *op);
+vb200ms *vb200ms_open(int nstreams, int channels, long rate, float quality, int device);
+void vb200ms_close(vb200ms *m);
+vorbis_dsp_state *vb200ms_state(vb200ms *m, int stream);
+int vb200ms_round(vb200ms *m, vb200ms_sink sink, void *user);
+
+/* pcm [nstreams][ch][nsamples]; returns total blocks, or <0 */
+long ref_ms_encode(int nstreams, int ch, long rate, float quality, int device, const float *pcm, long nsamples,
+                   uint64_t *hash, long *bytes, long *count){
+  vb200ms *m = vb200ms_open(nstreams, ch, rate, quality, device);
+  ms_sum sum;
+  long pos = 0, blocks = 0;
+  int i, c, r, alldone = 0;
+  const long chunk = g_chunk > 0 ? g_chunk : 1024;
+  int *eos = (int*)calloc(nstreams, sizeof(int));
+  if(!m){ free(eos); return -1; }
+  for(i = 0; i < nstreams; i++){ hash[i] = 1469598103934665603ULL; bytes[i] = 0; count[i] = 0; }
+  sum.hash = hash; sum.bytes = bytes; sum.count = count; sum.eos = eos;
+  while(!alldone){
+    long todo = nsamples - pos < chunk ? nsamples - pos : chunk;
+    for(i = 0; i < nstreams; i++){
+      vorbis_dsp_state *vd = vb200ms_state(m, i);
+      if(todo > 0){
+        float **buf = vorbis_analysis_buffer(vd, (int)todo);
+        for(c = 0; c < ch; c++) memcpy(buf[c], pcm + ((size_t)i*ch + c)*nsamples + pos, sizeof(float)*todo);
+        vorbis_analysis_wrote(vd, (int)todo);
+      }else vorbis_analysis_wrote(vd, 0);
+    }
+    pos += todo > 0 ? todo : 0;
+    while((r = vb200ms_round(m, ms_sink, &sum)) > 0) blocks += r;
+    if(r < 0){ blocks = r; break; }
+    if(todo <= 0) alldone = 1;
+  }
+  vb200ms_close(m);
+  free(eos);
+  return blocks;
+}
+
+#endif

@@ -1,0 +1,291 @@
+/* vb200_mapping0.c — the block-level binding (SURVEY §8b seam 1): a `vorbis_func_mapping` whose
+ * forward() hands a whole block to the device in ONE call, and a multi-stream driver that hands the
+ * ready blocks of MANY vorbis_dsp_states to the device in one call per block size.
+ *
+ *   reference                                            this file
+ *   mapping0_exportbundle (lib/mapping0.c:802-808)   ->  vb200_mapping0_exportbundle: pack / unpack / free_info /
+ *                                                        inverse are the reference's own, forward is below
+ *   mapping0_forward (lib/mapping0.c:230-696)        ->  vb200_mapping0_forward: ONE vb200_encode_dsp call for
+ *                                                        everything between vb->pcm and the entropy coder
+ *                                                        (window, MDCT, FFT, masks, floor fit + render, couple /
+ *                                                        quantise / normalise), then on the host exactly what the
+ *                                                        reference does with bits: mode header (:603-610), the
+ *                                                        reference's own floor1_encode (lib/floor1.c:753) for the
+ *                                                        floor bits and _residue_P[]->class / ->forward
+ *                                                        (lib/mapping0.c:660-683) for the residue
+ *   a loop of vorbis_analysis over N encoders        ->  vb200ms_*: blockout for every stream, the blocks that are
+ *                                                        ready go to the device together, packets come back per stream
+ *
+ * floor1_encode is fed the device's posts re-expanded to the fit scale: its quantise step maps them back to
+ * the same integers and its predict/flag pass is idempotent on them, so it writes exactly the bits it would
+ * have written for the fit (its own render into a scratch curve is redundant host work of ~n integer ops per
+ * channel; the curve the residue was built from is the device's).  No reference source is restated here.
+ *
+ * Un-managed bitrate only (vorbis_encode_init_vbr): the managed mode's extra fits and blobs are not built,
+ * forward returns OV_EIMPL there.  A CUDA failure surfaces as OV_EFAULT from vorbis_analysis and latches in
+ * the binding (vb200shim_error).  Compiled like any libvorbis-internal backend against lib/codec_internal.h
+ * (oracle/Makefile target `dropin`); INTEGRATION.md shows the registry line a maintainer changes.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "vorbis/codec.h"
+#include "vorbis/vorbisenc.h"
+#include "codec_internal.h"
+#include "registry.h"
+#include "bitrate.h"
+
+#include "vorbis_b200.h"
+
+/* from vb200_ref_shim.c */
+typedef struct vb200_binding vb200_binding;
+int vb200shim_attach(vorbis_dsp_state *vd, int device);
+void vb200shim_detach(void);
+int vb200shim_select(vorbis_dsp_state *vd);
+vb200_binding *vb200shim_binding(vorbis_dsp_state *vd);
+vb200_ctx *vb200shim_ctx(vb200_binding *b);
+void vb200shim_set_error(vb200_binding *b, int rc);
+
+extern const vorbis_func_mapping mapping0_exportbundle;      /* the reference's own bundle (lib/mapping0.c:802) */
+extern int floor1_encode(oggpack_buffer *opb, vorbis_block *vb, vorbis_look_floor1 *look, int *post, int *ilogmask);
+
+/* ---- host half of one block: header bits, floor bits, residue bits -----------------------------------------
+ * posts [ch][VB200_FLOOR1_STRIDE], nonzero [ch] (after coupling), iwork [ch][n]: what vb200_encode_dsp returned */
+static int pack_block(vorbis_block *vb, const int32_t *posts, const int32_t *nonzero_dev, int32_t *iwork_dev){
+  vorbis_dsp_state *vd = vb->vd;
+  vorbis_info *vi = vd->vi;
+  codec_setup_info *ci = (codec_setup_info*)vi->codec_setup;
+  private_state *b = (private_state*)vd->backend_state;
+  vorbis_block_internal *vbi = (vorbis_block_internal*)vb->internal;
+  const int ch = vi->channels, n = vb->pcmend/2, k = PACKETBLOBS/2;
+  const int modenumber = (int)vb->W;
+  vorbis_info_mapping0 *info = (vorbis_info_mapping0*)ci->map_param[modenumber];
+  oggpack_buffer *opb = vbi->packetblob[k];
+  int **iwork = (int**)_vorbis_block_alloc(vb, ch*sizeof(*iwork));
+  int **couple_bundle = (int**)_vorbis_block_alloc(vb, ch*sizeof(*couple_bundle));
+  int *zerobundle = (int*)_vorbis_block_alloc(vb, ch*sizeof(*zerobundle));
+  int *scratch = (int*)_vorbis_block_alloc(vb, n*sizeof(*scratch));
+  int i, j;
+  vb->mode = modenumber;
+  for(i = 0; i < ch; i++){                                     /* the residue backend wants int** rows */
+    iwork[i] = (int*)_vorbis_block_alloc(vb, n*sizeof(**iwork));
+    memcpy(iwork[i], iwork_dev + (size_t)i*n, n*sizeof(int));
+  }
+  oggpack_write(opb, 0, 1);                                    /* packet type: audio */
+  oggpack_write(opb, modenumber, b->modebits);
+  if(vb->W){
+    oggpack_write(opb, vb->lW, 1);
+    oggpack_write(opb, vb->nW, 1);
+  }
+  for(i = 0; i < ch; i++){
+    const int submap = info->chmuxlist[i];
+    vorbis_look_floor1 *look = (vorbis_look_floor1*)b->flr[info->floorsubmap[submap]];
+    const int32_t *p = posts + (size_t)i*VB200_FLOOR1_STRIDE;
+    const int P = look->posts, mult = look->vi->mult;
+    int any = 0, fit[VIF_POSIT+2];
+    if(ci->floor_type[info->floorsubmap[submap]] != 1) return -1;
+    for(j = 0; j < P; j++) any |= p[j];
+    if(!any){                                                  /* floor1_fit returned NULL: an all-zero row (vorbis_b200.h) */
+      floor1_encode(opb, vb, look, NULL, scratch);
+      continue;
+    }
+    for(j = 0; j < P; j++){                                    /* back to the fit scale: the quantiser undoes it exactly */
+      const int v = p[j] & 0x7fff;
+      const int e = mult == 1 ? v << 2 : mult == 2 ? v << 3 : mult == 3 ? v*12 : v << 4;
+      fit[j] = e | (p[j] & 0x8000);
+    }
+    floor1_encode(opb, vb, look, fit, scratch);
+  }
+  for(i = 0; i < info->submaps; i++){                          /* classify and encode by submap */
+    int ch_in_bundle = 0;
+    long **classifications;
+    const int resnum = info->residuesubmap[i];
+    for(j = 0; j < ch; j++)
+      if(info->chmuxlist[j] == i){
+        zerobundle[ch_in_bundle] = nonzero_dev[j] ? 1 : 0;
+        couple_bundle[ch_in_bundle++] = iwork[j];
+      }
+    classifications = _residue_P[ci->residue_type[resnum]]->class(vb, b->residue[resnum], couple_bundle, zerobundle, ch_in_bundle);
+    ch_in_bundle = 0;
+    for(j = 0; j < ch; j++)
+      if(info->chmuxlist[j] == i) couple_bundle[ch_in_bundle++] = iwork[j];
+    _residue_P[ci->residue_type[resnum]]->forward(opb, vb, b->residue[resnum], couple_bundle, zerobundle, ch_in_bundle, classifications, i);
+  }
+  return 0;
+}
+
+/* ---- device half for a set of blocks of ONE size ------------------------------------------------------------ */
+typedef struct {
+  float *pcm; vb200_block_desc *desc; int32_t *posts, *nonzero, *iwork; float *ampmax;
+  size_t cap_blocks; int ch, N;
+} ms_batch;
+
+static int batch_reserve(ms_batch *B, size_t nb, int ch, int N){
+  if(B->cap_blocks >= nb && B->ch == ch && B->N == N) return 0;
+  free(B->pcm); free(B->desc); free(B->posts); free(B->nonzero); free(B->iwork); free(B->ampmax);
+  memset(B, 0, sizeof(*B));
+  B->pcm = (float*)malloc(sizeof(float)*nb*ch*N);
+  B->desc = (vb200_block_desc*)malloc(sizeof(vb200_block_desc)*nb);
+  B->posts = (int32_t*)malloc(sizeof(int32_t)*nb*ch*VB200_FLOOR1_STRIDE);
+  B->nonzero = (int32_t*)malloc(sizeof(int32_t)*nb*ch);
+  B->iwork = (int32_t*)malloc(sizeof(int32_t)*nb*ch*(N/2));
+  B->ampmax = (float*)malloc(sizeof(float)*nb);
+  if(!B->pcm || !B->desc || !B->posts || !B->nonzero || !B->iwork || !B->ampmax) return OV_EFAULT;
+  B->cap_blocks = nb; B->ch = ch; B->N = N;
+  return 0;
+}
+
+/* blocks[0..nb) all have vb->W == W and belong to states of ONE binding */
+static int forward_batch(vb200_binding *bind, ms_batch *B, vorbis_block **blocks, int nb, int W){
+  vorbis_info *vi = blocks[0]->vd->vi;
+  const int ch = vi->channels, N = (int)blocks[0]->pcmend;
+  vb200_encode_io io;
+  int i, c, rc;
+  if((rc = batch_reserve(B, (size_t)nb, ch, N))) return rc;
+  for(i = 0; i < nb; i++){
+    vorbis_block_internal *vbi = (vorbis_block_internal*)blocks[i]->internal;
+    for(c = 0; c < ch; c++) memcpy(B->pcm + ((size_t)i*ch + c)*N, blocks[i]->pcm[c], sizeof(float)*N);
+    B->desc[i].lW = (int32_t)blocks[i]->lW; B->desc[i].nW = (int32_t)blocks[i]->nW;
+    B->desc[i].blocktype = vbi->blocktype; B->desc[i].ampmax = vbi->ampmax;
+  }
+  memset(&io, 0, sizeof(io));
+  io.pcm = B->pcm; io.pcm_fmt = VB200_PCM_F32_BLOCKS; io.desc = B->desc; io.independent = 1;
+  io.posts = B->posts; io.nonzero = B->nonzero; io.iwork = B->iwork; io.ampmax_out = B->ampmax;
+  rc = vb200_encode_dsp(vb200shim_ctx(bind), W, nb, 1, PACKETBLOBS/2, &io);      /* one H2D, the six kernels, one D2H */
+  if(rc){
+    vb200shim_set_error(bind, rc);
+    fprintf(stderr, "vb200 mapping0: vb200_encode_dsp failed (%d): %s\n", rc, vb200_last_error());
+    return OV_EFAULT;
+  }
+  for(i = 0; i < nb; i++){
+    vorbis_block_internal *vbi = (vorbis_block_internal*)blocks[i]->internal;
+    vbi->ampmax = B->ampmax[i];                                /* lib/mapping0.c:576 */
+    if((rc = pack_block(blocks[i], B->posts + (size_t)i*ch*VB200_FLOOR1_STRIDE, B->nonzero + (size_t)i*ch,
+                        B->iwork + (size_t)i*ch*(N/2)))) return rc;
+  }
+  return 0;
+}
+
+/* ---- seam 1: vorbis_func_mapping ---------------------------------------------------------------------------- */
+static ms_batch g_single[2];                                   /* the single-block path's staging (one per block size) */
+
+static int vb200_mapping0_forward(vorbis_block *vb){
+  vb200_binding *bind = vb200shim_binding(vb->vd);
+  if(!bind){ fprintf(stderr, "vb200 mapping0: vorbis_dsp_state is not attached (vb200shim_attach)\n"); return OV_EFAULT; }
+  if(vorbis_bitrate_managed(vb)) return OV_EIMPL;              /* the managed-mode fits/blobs are not built on the device */
+  return forward_batch(bind, &g_single[vb->W ? 1 : 0], &vb, 1, (int)vb->W);
+}
+static void vb_pack(vorbis_info *vi, vorbis_info_mapping *vm, oggpack_buffer *opb){ mapping0_exportbundle.pack(vi, vm, opb); }
+static vorbis_info_mapping *vb_unpack(vorbis_info *vi, oggpack_buffer *opb){ return mapping0_exportbundle.unpack(vi, opb); }
+static void vb_free_info(vorbis_info_mapping *m){ mapping0_exportbundle.free_info(m); }
+static int vb_inverse(vorbis_block *vb, vorbis_info_mapping *m){ return mapping0_exportbundle.inverse(vb, m); }
+
+const vorbis_func_mapping vb200_mapping0_exportbundle = { &vb_pack, &vb_unpack, &vb_free_info, &vb200_mapping0_forward, &vb_inverse };
+
+/* vorbis_analysis (lib/analysis.c:29-63) with the mapping call bound to the bundle above: what a libvorbis built
+ * with `_mapping_P[0] = &vb200_mapping0_exportbundle` does.  Kept as a function so that the unmodified reference
+ * objects and this seam can live in one test library. */
+int vb200_vorbis_analysis(vorbis_block *vb, ogg_packet *op){
+  vorbis_block_internal *vbi = (vorbis_block_internal*)vb->internal;
+  int ret, i;
+  vb->glue_bits = 0; vb->time_bits = 0; vb->floor_bits = 0; vb->res_bits = 0;
+  for(i = 0; i < PACKETBLOBS; i++) oggpack_reset(vbi->packetblob[i]);
+  if((ret = vb200_mapping0_exportbundle.forward(vb))) return ret;
+  if(op){
+    if(vorbis_bitrate_managed(vb)) return OV_EINVAL;
+    op->packet = oggpack_get_buffer(&vb->opb);
+    op->bytes = oggpack_bytes(&vb->opb);
+    op->b_o_s = 0; op->e_o_s = vb->eofflag; op->granulepos = vb->granulepos; op->packetno = vb->sequence;
+  }
+  return 0;
+}
+
+/* ---- multi-stream driver: N independent encoders, the device sees their blocks together ---------------------- */
+typedef struct vb200ms {
+  int nstreams, channels, device;
+  vorbis_info *vi;               /* one vorbis_info per stream (each owns its codec setup -> one binding each... */
+  vorbis_comment vc;
+  vorbis_dsp_state *vd;
+  vorbis_block *vb;
+  vb200_binding *bind;           /* ...so all states are initialised from stream 0's vorbis_info: one shared binding */
+  ms_batch batch[2];
+  vorbis_block **ready[2];
+  int *ready_stream[2];
+} vb200ms;
+
+void vb200ms_close(vb200ms *m){
+  int i, w;
+  if(!m) return;
+  if(m->bind){ vb200shim_select(&m->vd[0]); vb200shim_detach(); }
+  for(i = 0; i < m->nstreams; i++){
+    if(m->vb) vorbis_block_clear(&m->vb[i]);
+    if(m->vd) vorbis_dsp_clear(&m->vd[i]);
+  }
+  if(m->vi){ vorbis_info_clear(&m->vi[0]); }
+  vorbis_comment_clear(&m->vc);
+  for(w = 0; w < 2; w++){
+    free(m->batch[w].pcm); free(m->batch[w].desc); free(m->batch[w].posts); free(m->batch[w].nonzero);
+    free(m->batch[w].iwork); free(m->batch[w].ampmax); free(m->ready[w]); free(m->ready_stream[w]);
+  }
+  free(m->vi); free(m->vd); free(m->vb); free(m);
+}
+
+/* N encoders of one configuration (vorbis_encode_init_vbr), all bound to one device context */
+vb200ms *vb200ms_open(int nstreams, int channels, long rate, float quality, int device){
+  vb200ms *m = (vb200ms*)calloc(1, sizeof(*m));
+  int i, w;
+  if(!m || nstreams < 1) { free(m); return NULL; }
+  m->nstreams = nstreams; m->channels = channels; m->device = device;
+  m->vi = (vorbis_info*)calloc(1, sizeof(*m->vi));
+  m->vd = (vorbis_dsp_state*)calloc(nstreams, sizeof(*m->vd));
+  m->vb = (vorbis_block*)calloc(nstreams, sizeof(*m->vb));
+  for(w = 0; w < 2; w++){
+    m->ready[w] = (vorbis_block**)calloc(nstreams, sizeof(vorbis_block*));
+    m->ready_stream[w] = (int*)calloc(nstreams, sizeof(int));
+  }
+  vorbis_comment_init(&m->vc);
+  vorbis_info_init(&m->vi[0]);
+  if(vorbis_encode_init_vbr(&m->vi[0], channels, rate, quality)){ vb200ms_close(m); return NULL; }
+  for(i = 0; i < nstreams; i++){                               /* every state reads the same (read-only) setup */
+    vorbis_analysis_init(&m->vd[i], &m->vi[0]);
+    vorbis_block_init(&m->vd[i], &m->vb[i]);
+  }
+  if(vb200shim_attach(&m->vd[0], device)){ vb200ms_close(m); return NULL; }
+  m->bind = vb200shim_binding(&m->vd[0]);
+  return m;
+}
+
+vorbis_dsp_state *vb200ms_state(vb200ms *m, int stream){ return &m->vd[stream]; }
+
+/* One round: every stream that has a block ready (vorbis_analysis_blockout) contributes it; the blocks go to the
+ * device in one call per block size; packets are handed to `sink` per stream in block order (the per-stream
+ * bitrate queue keeps packet order).  Returns the number of blocks processed (0: every stream needs more data),
+ * or a negative OV_* code. */
+typedef void (*vb200ms_sink)(void *user, int stream, ogg_packet *op);
+int vb200ms_round(vb200ms *m, vb200ms_sink sink, void *user){
+  int cnt[2] = {0, 0}, i, w, rc, total = 0;
+  ogg_packet op;
+  for(i = 0; i < m->nstreams; i++){
+    if(vorbis_analysis_blockout(&m->vd[i], &m->vb[i]) == 1){
+      vorbis_block_internal *vbi = (vorbis_block_internal*)m->vb[i].internal;
+      int k;
+      w = m->vb[i].W ? 1 : 0;
+      m->vb[i].glue_bits = 0; m->vb[i].time_bits = 0; m->vb[i].floor_bits = 0; m->vb[i].res_bits = 0;
+      for(k = 0; k < PACKETBLOBS; k++) oggpack_reset(vbi->packetblob[k]);      /* lib/analysis.c:37-41 */
+      m->ready[w][cnt[w]] = &m->vb[i];
+      m->ready_stream[w][cnt[w]++] = i;
+    }
+  }
+  for(w = 0; w < 2; w++){
+    if(!cnt[w]) continue;
+    if((rc = forward_batch(m->bind, &m->batch[w], m->ready[w], cnt[w], w))) return rc;
+    for(i = 0; i < cnt[w]; i++){
+      const int s = m->ready_stream[w][i];
+      vorbis_bitrate_addblock(&m->vb[s]);
+      while(vorbis_bitrate_flushpacket(&m->vd[s], &op)) if(sink) sink(user, s, &op);
+    }
+    total += cnt[w];
+  }
+  return total;
+}

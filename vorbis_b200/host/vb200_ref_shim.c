@@ -37,22 +37,76 @@
 
 #include "vorbis_b200.h"
 
-/* one attached encoder/decoder state at a time (the reference itself is single threaded
- * per vorbis_dsp_state); a production build would hang the context off
- * private_state instead of a global. */
-static struct {
+int vb200shim_attach_new(vorbis_dsp_state *vd, int device);
+/* Bindings: one device context per codec setup (vorbis_info.codec_setup), shared by every vorbis_dsp_state
+ * initialised from it - the device tables are read-only, so all streams of one configuration use the same
+ * context (SURVEY §8b "ownership").  vb200shim_attach() finds or creates the binding of a state and makes it
+ * the calling thread's current one; the stage-level shims below have the reference's own prototypes, which
+ * carry no state pointer, so they act on that current binding (the reference is single threaded per
+ * vorbis_dsp_state; concurrent states on different threads each attach in their own thread).  The block-level
+ * seam (vb200_mapping0.c) never uses the current binding: it looks the binding up from vb->vd.
+ * A CUDA failure latches binding->error (sticky) - vb200shim_error() - and vorbis_analysis reports
+ * OV_EFAULT through the block-level seam; the stage shims leave the data untouched as before.          */
+#define VB200_MAX_BINDINGS 64
+typedef struct vb200_binding {
   vb200_ctx *ctx;
-  vorbis_dsp_state *vd;
+  void *setup_key;                       /* vd->vi->codec_setup */
+  vorbis_dsp_state *vd;                  /* a state of this setup (for the lookups) */
+  int analysisp, refs, error;
   int32_t *octave[4], *bark[4];
   float *tonecurves[4], *noiseoffset[4];
-} g;
+  float *fscratch; size_t fscratch_cap;  /* grow-only host scratch of the stage shims (no malloc per call) */
+  int32_t *iscratch; size_t iscratch_cap;
+} vb200_binding;
+static vb200_binding g_bind[VB200_MAX_BINDINGS];
+static __thread vb200_binding *g_cur;
+#define g (*g_cur)
 
 static void shim_warn(const char *what, int rc){
+  if(g_cur && !g_cur->error) g_cur->error = rc;
   fprintf(stderr, "vb200 shim: %s failed (%d): %s\n", what, rc, vb200_last_error());
+}
+int vb200shim_error(void){ return g_cur ? g_cur->error : 0; }
+
+vb200_binding *vb200shim_binding(vorbis_dsp_state *vd){
+  int i;
+  for(i = 0; i < VB200_MAX_BINDINGS; i++)
+    if(g_bind[i].ctx && g_bind[i].setup_key == (void*)vd->vi->codec_setup && g_bind[i].analysisp == vd->analysisp) return &g_bind[i];
+  return NULL;
+}
+vb200_ctx *vb200shim_ctx(vb200_binding *b){ return b ? b->ctx : NULL; }
+void vb200shim_set_error(vb200_binding *b, int rc){ if(b && !b->error) b->error = rc; }
+static float *bind_fscratch(size_t n){
+  if(g.fscratch_cap < n){ free(g.fscratch); g.fscratch = (float*)malloc(sizeof(float)*n); g.fscratch_cap = g.fscratch ? n : 0; }
+  return g.fscratch;
+}
+static int32_t *bind_iscratch(size_t n){
+  if(g.iscratch_cap < n){ free(g.iscratch); g.iscratch = (int32_t*)malloc(sizeof(int32_t)*n); g.iscratch_cap = g.iscratch ? n : 0; }
+  return g.iscratch;
 }
 
 /* Build the device context from the lookups _vds_shared_init made (lib/block.c:170-294). */
 int vb200shim_attach(vorbis_dsp_state *vd, int device){
+  vorbis_info *vi = vd->vi;
+  vb200_binding *found = vb200shim_binding(vd);
+  if(found){ found->refs++; g_cur = found; return 0; }       /* another state of the same setup: share the context */
+  {
+    int slot;
+    for(slot = 0; slot < VB200_MAX_BINDINGS && g_bind[slot].ctx; slot++);
+    if(slot == VB200_MAX_BINDINGS){ fprintf(stderr, "vb200 shim: too many codec setups attached\n"); return VB200_EINVAL; }
+    memset(&g_bind[slot], 0, sizeof(g_bind[slot]));
+    g_cur = &g_bind[slot];
+  }
+  return vb200shim_attach_new(vd, device);
+}
+static void bind_release(vb200_binding *b){
+  int i;
+  if(b->ctx) vb200_ctx_destroy(b->ctx);
+  for(i = 0; i < 4; i++){ free(b->octave[i]); free(b->bark[i]); free(b->tonecurves[i]); free(b->noiseoffset[i]); }
+  free(b->fscratch); free(b->iscratch);
+  memset(b, 0, sizeof(*b));
+}
+int vb200shim_attach_new(vorbis_dsp_state *vd, int device){
   vorbis_info *vi = vd->vi;
   codec_setup_info *ci = (codec_setup_info*)vi->codec_setup;
   private_state *b = (private_state*)vd->backend_state;
@@ -143,19 +197,30 @@ int vb200shim_attach(vorbis_dsp_state *vd, int device){
     }
   }
   rc = vb200_ctx_create(&s, device, &g.ctx);
-  if(rc){ shim_warn("vb200_ctx_create", rc); return rc; }
-  g.vd = vd;
+  if(rc){
+    fprintf(stderr, "vb200 shim: vb200_ctx_create failed (%d): %s\n", rc, vb200_last_error());
+    bind_release(g_cur); g_cur = NULL;
+    return rc;
+  }
+  g.vd = vd; g.setup_key = (void*)vi->codec_setup; g.analysisp = vd->analysisp; g.refs = 1;
   return 0;
 }
 
+/* drop the calling thread's current binding (the context goes with its last user) */
 void vb200shim_detach(void){
-  int i;
-  if(g.ctx) vb200_ctx_destroy(g.ctx);
-  for(i = 0; i < 4; i++){ free(g.octave[i]); free(g.bark[i]); free(g.tonecurves[i]); free(g.noiseoffset[i]); }
-  memset(&g, 0, sizeof(g));
+  if(!g_cur) return;
+  if(--g_cur->refs <= 0) bind_release(g_cur);
+  g_cur = NULL;
+}
+/* make the binding of `vd` current for this thread (a thread that drives several attached states) */
+int vb200shim_select(vorbis_dsp_state *vd){
+  vb200_binding *b = vb200shim_binding(vd);
+  if(!b) return VB200_EINVAL;
+  g_cur = b;
+  return 0;
 }
 
-unsigned long long vb200shim_launches(void){ return g.ctx ? vb200_launch_count(g.ctx) : 0; }
+unsigned long long vb200shim_launches(void){ return (g_cur && g.ctx) ? vb200_launch_count(g.ctx) : 0; }
 
 static int W_of_n(int n){
   codec_setup_info *ci = (codec_setup_info*)g.vd->vi->codec_setup;
@@ -174,10 +239,9 @@ void vb200shim_mdct_forward(mdct_lookup *init, DATA_TYPE *in, DATA_TYPE *out){
 /* mdct_backward, lib/mdct.c:396 (in == out allowed, as at lib/mapping0.c:794) */
 void vb200shim_mdct_backward(mdct_lookup *init, DATA_TYPE *in, DATA_TYPE *out){
   int n = init->n;
-  float *tmp = (float*)malloc(sizeof(float)*n);
-  int rc = vb200_mdct_backward(g.ctx, W_of_n(n), 1, in, tmp);
+  float *tmp = bind_fscratch((size_t)n);
+  int rc = tmp ? vb200_mdct_backward(g.ctx, W_of_n(n), 1, in, tmp) : VB200_EFAULT;
   if(rc) shim_warn("mdct_backward", rc); else memcpy(out, tmp, sizeof(float)*n);
-  free(tmp);
 }
 /* _vorbis_apply_window, lib/window.c:2102 */
 void vb200shim_apply_window(float *d, int *winno, long *blocksizes, int lW, int W, int nW){
@@ -212,10 +276,11 @@ void vb200shim_couple_quantize_normalize(int blobno, vorbis_info_psy_global *gp,
                                          vorbis_info_mapping0 *vi, float **mdct, int **iwork, int *nonzero,
                                          int sliding_lowpass, int ch){
   int look = look_of(p), W = look >> 1, blocktype = look & 1, n = p->n, c, rc;
-  float *m = (float*)malloc(sizeof(float)*ch*n);
-  int32_t *iw = (int32_t*)malloc(sizeof(int32_t)*ch*n);
-  int32_t *nz = (int32_t*)malloc(sizeof(int32_t)*ch);
+  float *m = bind_fscratch((size_t)ch*n);
+  int32_t *iw = bind_iscratch((size_t)ch*n + ch);
+  int32_t *nz = iw ? iw + (size_t)ch*n : NULL;
   (void)gp; (void)vi; (void)sliding_lowpass;
+  if(!m || !iw){ shim_warn("couple_quantize_normalize (host scratch)", VB200_EFAULT); return; }
   for(c = 0; c < ch; c++){
     memcpy(m + (size_t)c*n, mdct[c], sizeof(float)*n);
     memcpy(iw + (size_t)c*n, iwork[c], sizeof(int32_t)*n);
@@ -224,11 +289,11 @@ void vb200shim_couple_quantize_normalize(int blobno, vorbis_info_psy_global *gp,
   rc = vb200_couple_quantize_normalize(g.ctx, W, blocktype, blobno, 1, m, iw, nz);
   if(rc) shim_warn("couple_quantize_normalize", rc);
   else for(c = 0; c < ch; c++){ memcpy(iwork[c], iw + (size_t)c*n, sizeof(int32_t)*n); nonzero[c] = nz[c]; }
-  free(m); free(iw); free(nz);
 }
 
 /* floor1_fit, lib/floor1.c:576: returns posts in vorbis_block storage, or NULL for a silent channel */
 int *vb200shim_floor1_fit(vorbis_block *vb, vorbis_look_floor1 *look, const float *logmdct, const float *logmask){
+  { vb200_binding *bb = vb200shim_binding(vb->vd); if(bb) g_cur = bb; }
   codec_setup_info *ci = (codec_setup_info*)g.vd->vi->codec_setup;
   private_state *b = (private_state*)g.vd->backend_state;
   vorbis_info_mapping0 *m = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[vb->W]->mapping];
@@ -251,6 +316,7 @@ int *vb200shim_floor1_fit(vorbis_block *vb, vorbis_look_floor1 *look, const floa
  * envelope_filter_state layout, so ve->filter / ve->stretch stay authoritative between calls.  */
 long vb200shim_envelope_search(vorbis_dsp_state *v){
   vorbis_info *vi = v->vi;
+  { vb200_binding *bb = vb200shim_binding(v); if(bb) g_cur = bb; }   /* every block starts here: the state's binding becomes current */
   codec_setup_info *ci = (codec_setup_info*)vi->codec_setup;
   envelope_lookup *ve = ((private_state*)(v->backend_state))->ve;
   long j;
