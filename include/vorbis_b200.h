@@ -388,6 +388,11 @@ int vb200_envelope_search_dev(vb200_ctx*, int nstreams, const void *d_pcm, int p
 int vb200_envelope_search    (vb200_ctx*, int nstreams, const void *pcm, int pcm_fmt, int64_t stream_stride,
                               int first_step, int nsteps, int32_t *state, uint8_t *ret);
 void vb200_envelope_apply_marks(const uint8_t *ret, int first_step, int nsteps, int32_t *mark);
+/* many streams with DIFFERENT amounts of new data in one call (the multi-stream driver of
+ * vorbis_b200/host/vb200_mapping0.c): stream s analyses steps 0 .. steps_per_stream[s]-1 (<= nsteps) of its
+ * buffer; ret [nstreams][nsteps], entries past a stream's own count are left untouched.  Host pointers.   */
+int vb200_envelope_search_var(vb200_ctx*, int nstreams, const void *pcm, int pcm_fmt, int64_t stream_stride,
+                              int nsteps, const int32_t *steps_per_stream, int32_t *state, uint8_t *ret);
 
 /* ---- block planning: what vorbis_analysis_blockout decides per block ----------------
  * lib/block.c:556-615 (nW from the envelope marks, blocktype) with the cursor / curmark walk of

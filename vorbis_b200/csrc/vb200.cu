@@ -1678,7 +1678,7 @@ struct EncScratch {
 // int32 residue -> saturated int16, counting per block what did not fit (VB200_IWORK_S16)
 __global__ void __launch_bounds__(256)
 k_pack_s16(const int4 *__restrict__ src, short4 *__restrict__ dst, long nvec, int vec_per_block_log2,
-           int32_t *__restrict__ overflow) {
+           int vec_per_block, int32_t *__restrict__ overflow) {
   for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
     const int4 a = __ldcs(src + v);
     int bad = 0;
@@ -1686,7 +1686,8 @@ k_pack_s16(const int4 *__restrict__ src, short4 *__restrict__ dst, long nvec, in
     short4 o;
     o.x = sat(a.x); o.y = sat(a.y); o.z = sat(a.z); o.w = sat(a.w);
     __stcs(dst + v, o);
-    if (bad) atomicAdd(overflow + (v >> vec_per_block_log2), bad);
+    // clipping is the rare case: the division for channel counts that are not a power of two only runs there
+    if (bad) atomicAdd(overflow + (vec_per_block_log2 >= 0 ? (v >> vec_per_block_log2) : (v / vec_per_block)), bad);
   }
 }
 
@@ -1749,11 +1750,9 @@ static int encode_launch(vb200_ctx *c, int W, int nstreams, int bps, int blobno,
     const long nvec = (long)rows * n / 4;
     int lg = 0;
     while ((1L << lg) < (long)ch * n / 4) lg++;
-    if ((1L << lg) != (long)ch * n / 4) {             // channels not a power of two: per-block counts need a division
-      return fail(VB200_EIMPL, "int16 residue needs a power-of-two channel count");
-    }
+    if ((1L << lg) != (long)ch * n / 4) lg = -1;      // channels not a power of two (5.1): per-block counts by division
     CU(cudaMemsetAsync(d->overflow, 0, sizeof(int32_t) * (size_t)nblocks, st));
-    k_pack_s16<<<grid_for(c, (int)((nvec + 255) / 256), 8), 256, 0, st>>>((const int4 *)iw, (short4 *)d->iwork, nvec, lg, d->overflow);
+    k_pack_s16<<<grid_for(c, (int)((nvec + 255) / 256), 8), 256, 0, st>>>((const int4 *)iw, (short4 *)d->iwork, nvec, lg, (int)((long)ch * n / 4), d->overflow);
     if ((rc = post_launch(c))) return rc;
   }
   if (c->profiling) CU(cudaEventRecord(c->ev[6], st));
@@ -2231,8 +2230,9 @@ static int env_check(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64
   return 0;
 }
 
-extern "C" int vb200_envelope_search_dev(vb200_ctx *c, int nstreams, const void *d_pcm, int fmt, int64_t stride,
-                                         int first_step, int nsteps, int32_t *d_state, uint8_t *d_ret, void *stream) {
+static int envelope_search_launch(vb200_ctx *c, int nstreams, const void *d_pcm, int fmt, int64_t stride,
+                                  int first_step, int nsteps, int32_t *d_state, uint8_t *d_ret, void *stream,
+                                  const int32_t *d_steps_per_stream) {
   CHECK_CTX(c);
   int rc;
   if ((rc = env_check(c, nstreams, d_pcm, fmt, stride, first_step, nsteps, d_state, d_ret))) return rc;
@@ -2256,14 +2256,19 @@ extern "C" int vb200_envelope_search_dev(vb200_ctx *c, int nstreams, const void 
     k_env_spectrum<<<grid, 32 * ENV_WARPS, 0, st>>>(c->env, src, nstreams, first_step + j0, ns, (float *)p_t, (float *)p_v);
     if ((rc = post_launch(c))) return rc;
     k_env_filter<<<(nstreams + ENV_WARPS - 1) / ENV_WARPS, 32 * ENV_WARPS, 0, st>>>(
-        c->env, nstreams, ch, ns, nsteps, j0, (const float *)p_t, (const float *)p_v, d_state, d_ret);
+        c->env, nstreams, ch, ns, nsteps, j0, (const float *)p_t, (const float *)p_v, d_state, d_ret, d_steps_per_stream);
     if ((rc = post_launch(c))) return rc;
   }
   return scratch_end(c, st);
 }
 
-extern "C" int vb200_envelope_search(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64_t stride,
-                                     int first_step, int nsteps, int32_t *state, uint8_t *ret) {
+extern "C" int vb200_envelope_search_dev(vb200_ctx *c, int nstreams, const void *d_pcm, int fmt, int64_t stride,
+                                         int first_step, int nsteps, int32_t *d_state, uint8_t *d_ret, void *stream) {
+  return envelope_search_launch(c, nstreams, d_pcm, fmt, stride, first_step, nsteps, d_state, d_ret, stream, nullptr);
+}
+
+static int envelope_search_host(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64_t stride,
+                                int first_step, int nsteps, int32_t *state, uint8_t *ret, const int32_t *steps_per_stream) {
   CHECK_CTX(c);
   int rc;
   if ((rc = env_check(c, nstreams, pcm, fmt, stride, first_step, nsteps, state, ret))) return rc;
@@ -2274,15 +2279,33 @@ extern "C" int vb200_envelope_search(vb200_ctx *c, int nstreams, const void *pcm
   const size_t st_bytes = sizeof(int32_t) * (size_t)nstreams * VB200_VE_STATE_WORDS(ch);
   void *dp, *ds, *dr;
   if ((rc = ensure_buf(c->env_buf[2], pcm_bytes, &dp))) return rc;
-  if ((rc = ensure_buf(c->env_buf[3], st_bytes + (size_t)nstreams * nsteps, &ds))) return rc;
+  if ((rc = ensure_buf(c->env_buf[3], st_bytes + (size_t)nstreams * nsteps + sizeof(int32_t) * (size_t)nstreams + 16, &ds))) return rc;
   dr = (char *)ds + st_bytes;
+  int32_t *dn = nullptr;
+  if (steps_per_stream) {
+    dn = (int32_t *)((char *)dr + (((size_t)nstreams * nsteps + 15) & ~(size_t)15));
+    CU(cudaMemcpyAsync(dn, steps_per_stream, sizeof(int32_t) * (size_t)nstreams, cudaMemcpyHostToDevice, c->s_main));
+  }
   CU(cudaMemcpyAsync(dp, pcm, pcm_bytes, cudaMemcpyHostToDevice, c->s_main));
   CU(cudaMemcpyAsync(ds, state, st_bytes, cudaMemcpyHostToDevice, c->s_main));
-  if ((rc = vb200_envelope_search_dev(c, nstreams, dp, fmt, stride, first_step, nsteps, (int32_t *)ds, (uint8_t *)dr, c->s_main))) return rc;
+  if ((rc = envelope_search_launch(c, nstreams, dp, fmt, stride, first_step, nsteps, (int32_t *)ds, (uint8_t *)dr, c->s_main, dn))) return rc;
   CU(cudaMemcpyAsync(state, ds, st_bytes, cudaMemcpyDeviceToHost, c->s_main));
   CU(cudaMemcpyAsync(ret, dr, (size_t)nstreams * nsteps, cudaMemcpyDeviceToHost, c->s_main));
   CU(cudaStreamSynchronize(c->s_main));
   return 0;
+}
+
+extern "C" int vb200_envelope_search(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64_t stride,
+                                     int first_step, int nsteps, int32_t *state, uint8_t *ret) {
+  return envelope_search_host(c, nstreams, pcm, fmt, stride, first_step, nsteps, state, ret, nullptr);
+}
+
+// streams with different amounts of new data in one call: stream s analyses its first steps_per_stream[s]
+// (<= nsteps) steps, its later ret entries are left untouched
+extern "C" int vb200_envelope_search_var(vb200_ctx *c, int nstreams, const void *pcm, int fmt, int64_t stride,
+                                         int nsteps, const int32_t *steps_per_stream, int32_t *state, uint8_t *ret) {
+  if (!steps_per_stream) return fail(VB200_EINVAL, "steps_per_stream");
+  return envelope_search_host(c, nstreams, pcm, fmt, stride, 0, nsteps, state, ret, steps_per_stream);
 }
 
 // lib/envelope.c:254-264, replayed on the host from the per-step trigger bits (plain C, no CUDA)

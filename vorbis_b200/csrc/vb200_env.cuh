@@ -75,7 +75,7 @@ k_env_spectrum(EnvDev E, EnvSrc src, int nstreams, int first_step, int nsteps,
 __global__ void __launch_bounds__(32 * ENV_WARPS)
 k_env_filter(EnvDev E, int nstreams, int ch, int nsteps, int ret_stride, int ret_off,
              const float *__restrict__ temps, const float *__restrict__ vals,
-             int *__restrict__ state, unsigned char *__restrict__ ret) {
+             int *__restrict__ state, unsigned char *__restrict__ ret, const int *__restrict__ steps_per_stream) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int st = blockIdx.x * ENV_WARPS + (threadIdx.x >> 5);
@@ -88,7 +88,10 @@ k_env_filter(EnvDev E, int nstreams, int ch, int nsteps, int ret_stride, int ret
   float bw[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) bw[i] = __ldg(E.bwin + band * 8 + i);
-  for (int j = 0; j < nsteps; j++) {
+  // streams may have different amounts of new data: stream st only runs its first steps_per_stream[st] steps
+  int lim = steps_per_stream ? steps_per_stream[st] - ret_off : nsteps;
+  if (lim > nsteps) lim = nsteps;
+  for (int j = 0; j < lim; j++) {
     stretch_state++;                                            // lib/envelope.c:242-244
     if (stretch_state > 24) stretch_state = 24;
     const int half = stretch_state / 2;

@@ -38,8 +38,15 @@
 
 #include "vorbis_b200.h"
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 /* from vb200_ref_shim.c */
 typedef struct vb200_binding vb200_binding;
+int vb200shim_envelope_prepare(vorbis_dsp_state *v, int *first_out);
+void vb200shim_envelope_state_get(vorbis_dsp_state *v, int32_t *state);
+void vb200shim_envelope_commit(vorbis_dsp_state *v, int first, int nsteps, const int32_t *state, const uint8_t *ret);
 int vb200shim_attach(vorbis_dsp_state *vd, int device);
 void vb200shim_detach(void);
 int vb200shim_select(vorbis_dsp_state *vd);
@@ -136,13 +143,18 @@ static int batch_reserve(ms_batch *B, size_t nb, int ch, int N){
   return 0;
 }
 
-/* blocks[0..nb) all have vb->W == W and belong to states of ONE binding */
-static int forward_batch(vb200_binding *bind, ms_batch *B, vorbis_block **blocks, int nb, int W){
+/* blocks[0..nb) all have vb->W == W and belong to states of ONE binding.  The staging copies and the host half
+ * (bits) of different blocks are independent - different vorbis_dsp_states share nothing that is written - so
+ * both loops run on all host threads; `after` (optional) is called by the thread that packed block i. */
+typedef void (*batch_after)(void *user, int i);
+static int forward_batch(vb200_binding *bind, ms_batch *B, vorbis_block **blocks, int nb, int W, batch_after after, void *user){
   vorbis_info *vi = blocks[0]->vd->vi;
   const int ch = vi->channels, N = (int)blocks[0]->pcmend;
   vb200_encode_io io;
   int i, c, rc;
+  int err = 0;
   if((rc = batch_reserve(B, (size_t)nb, ch, N))) return rc;
+#pragma omp parallel for private(c) schedule(static) if(nb > 8)
   for(i = 0; i < nb; i++){
     vorbis_block_internal *vbi = (vorbis_block_internal*)blocks[i]->internal;
     for(c = 0; c < ch; c++) memcpy(B->pcm + ((size_t)i*ch + c)*N, blocks[i]->pcm[c], sizeof(float)*N);
@@ -158,13 +170,19 @@ static int forward_batch(vb200_binding *bind, ms_batch *B, vorbis_block **blocks
     fprintf(stderr, "vb200 mapping0: vb200_encode_dsp failed (%d): %s\n", rc, vb200_last_error());
     return OV_EFAULT;
   }
+#pragma omp parallel for schedule(dynamic, 4) if(nb > 8)
   for(i = 0; i < nb; i++){
     vorbis_block_internal *vbi = (vorbis_block_internal*)blocks[i]->internal;
+    int r;
     vbi->ampmax = B->ampmax[i];                                /* lib/mapping0.c:576 */
-    if((rc = pack_block(blocks[i], B->posts + (size_t)i*ch*VB200_FLOOR1_STRIDE, B->nonzero + (size_t)i*ch,
-                        B->iwork + (size_t)i*ch*(N/2)))) return rc;
+    r = pack_block(blocks[i], B->posts + (size_t)i*ch*VB200_FLOOR1_STRIDE, B->nonzero + (size_t)i*ch,
+                   B->iwork + (size_t)i*ch*(N/2));
+    if(r){
+#pragma omp atomic write
+      err = r;
+    }else if(after) after(user, i);
   }
-  return 0;
+  return err;
 }
 
 /* ---- seam 1: vorbis_func_mapping ---------------------------------------------------------------------------- */
@@ -174,7 +192,7 @@ static int vb200_mapping0_forward(vorbis_block *vb){
   vb200_binding *bind = vb200shim_binding(vb->vd);
   if(!bind){ fprintf(stderr, "vb200 mapping0: vorbis_dsp_state is not attached (vb200shim_attach)\n"); return OV_EFAULT; }
   if(vorbis_bitrate_managed(vb)) return OV_EIMPL;              /* the managed-mode fits/blobs are not built on the device */
-  return forward_batch(bind, &g_single[vb->W ? 1 : 0], &vb, 1, (int)vb->W);
+  return forward_batch(bind, &g_single[vb->W ? 1 : 0], &vb, 1, (int)vb->W, NULL, NULL);
 }
 static void vb_pack(vorbis_info *vi, vorbis_info_mapping *vm, oggpack_buffer *opb){ mapping0_exportbundle.pack(vi, vm, opb); }
 static vorbis_info_mapping *vb_unpack(vorbis_info *vi, oggpack_buffer *opb){ return mapping0_exportbundle.unpack(vi, opb); }
@@ -202,6 +220,7 @@ int vb200_vorbis_analysis(vorbis_block *vb, ogg_packet *op){
 }
 
 /* ---- multi-stream driver: N independent encoders, the device sees their blocks together ---------------------- */
+typedef void (*vb200ms_sink_t)(void *user, int stream, ogg_packet *op);
 typedef struct vb200ms {
   int nstreams, channels, device;
   vorbis_info *vi;               /* one vorbis_info per stream (each owns its codec setup -> one binding each... */
@@ -212,6 +231,13 @@ typedef struct vb200ms {
   ms_batch batch[2];
   vorbis_block **ready[2];
   int *ready_stream[2];
+  /* the batched envelope search: staging of every stream's new 64-sample steps */
+  int *env_first, *env_steps, *env_list;
+  int32_t *env_nsteps;
+  float *env_pcm; size_t env_pcm_cap;
+  int32_t *env_state; uint8_t *env_ret; size_t env_ret_cap;
+  int threads;
+  vb200ms_sink_t sink; void *sink_user; int cur_w;
 } vb200ms;
 
 void vb200ms_close(vb200ms *m){
@@ -228,7 +254,28 @@ void vb200ms_close(vb200ms *m){
     free(m->batch[w].pcm); free(m->batch[w].desc); free(m->batch[w].posts); free(m->batch[w].nonzero);
     free(m->batch[w].iwork); free(m->batch[w].ampmax); free(m->ready[w]); free(m->ready_stream[w]);
   }
+  free(m->env_first); free(m->env_steps); free(m->env_list); free(m->env_nsteps); free(m->env_pcm); free(m->env_state); free(m->env_ret);
   free(m->vi); free(m->vd); free(m->vb); free(m);
+}
+
+static int host_threads(void){
+  const char *e = getenv("VB200MS_THREADS");
+  int n = e ? atoi(e) : 0;
+#ifdef _OPENMP
+  if(n < 1){
+    n = omp_get_num_procs();
+    { /* a container may own fewer CPUs than it sees (cgroup quota) */
+      FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+      long q = 0, per = 0;
+      if(f){ if(fscanf(f, "%ld %ld", &q, &per) == 2 && q > 0 && per > 0 && q/per < n) n = (int)(q/per); fclose(f); }
+    }
+    if(n > 32) n = 32;
+  }
+  if(n < 1) n = 1;
+  return n;
+#else
+  (void)n; return 1;
+#endif
 }
 
 /* N encoders of one configuration (vorbis_encode_init_vbr), all bound to one device context */
@@ -244,6 +291,13 @@ vb200ms *vb200ms_open(int nstreams, int channels, long rate, float quality, int 
     m->ready[w] = (vorbis_block**)calloc(nstreams, sizeof(vorbis_block*));
     m->ready_stream[w] = (int*)calloc(nstreams, sizeof(int));
   }
+  m->env_first = (int*)calloc(nstreams, sizeof(int)); m->env_steps = (int*)calloc(nstreams, sizeof(int));
+  m->env_list = (int*)calloc(nstreams, sizeof(int)); m->env_nsteps = (int32_t*)calloc(nstreams, sizeof(int32_t));
+  m->env_state = (int32_t*)calloc((size_t)nstreams*VB200_VE_STATE_WORDS(channels), sizeof(int32_t));
+  m->threads = host_threads();
+#ifdef _OPENMP
+  omp_set_num_threads(m->threads);
+#endif
   vorbis_comment_init(&m->vc);
   vorbis_info_init(&m->vi[0]);
   if(vorbis_encode_init_vbr(&m->vi[0], channels, rate, quality)){ vb200ms_close(m); return NULL; }
@@ -258,33 +312,92 @@ vb200ms *vb200ms_open(int nstreams, int channels, long rate, float quality, int 
 
 vorbis_dsp_state *vb200ms_state(vb200ms *m, int stream){ return &m->vd[stream]; }
 
-/* One round: every stream that has a block ready (vorbis_analysis_blockout) contributes it; the blocks go to the
- * device in one call per block size; packets are handed to `sink` per stream in block order (the per-stream
- * bitrate queue keeps packet order).  Returns the number of blocks processed (0: every stream needs more data),
- * or a negative OV_* code. */
+/* the analysis loop of _ve_envelope_search for ALL streams in one device call: the steps every stream has not
+ * analysed yet are staged side by side (their counts differ - vb200_envelope_search_var), the results go back into
+ * each state's envelope_lookup, and the blockout calls that follow find nothing left to analyse */
+static int env_round(vb200ms *m){
+  const int ch = m->channels;
+  int i, na = 0, maxsteps = 0, rc;
+#pragma omp parallel for schedule(static) if(m->nstreams > 8)
+  for(i = 0; i < m->nstreams; i++) m->env_steps[i] = vb200shim_envelope_prepare(&m->vd[i], &m->env_first[i]);
+  for(i = 0; i < m->nstreams; i++)
+    if(m->env_steps[i] > 0){ m->env_list[na++] = i; if(m->env_steps[i] > maxsteps) maxsteps = m->env_steps[i]; }
+  if(!na) return 0;
+  {
+    const long stride = ((64L*(maxsteps - 1) + 128) + 3) & ~3L;
+    const size_t need = (size_t)na*ch*stride, rneed = (size_t)na*maxsteps;
+    const size_t sw = VB200_VE_STATE_WORDS(ch);
+    if(m->env_pcm_cap < need){ free(m->env_pcm); m->env_pcm = (float*)malloc(sizeof(float)*need); m->env_pcm_cap = m->env_pcm ? need : 0; }
+    if(m->env_ret_cap < rneed){ free(m->env_ret); m->env_ret = (uint8_t*)malloc(rneed); m->env_ret_cap = m->env_ret ? rneed : 0; }
+    if(!m->env_pcm || !m->env_ret) return OV_EFAULT;
+#pragma omp parallel for schedule(static) if(na > 8)
+    for(i = 0; i < na; i++){
+      vorbis_dsp_state *v = &m->vd[m->env_list[i]];
+      const long len = 64L*(m->env_steps[m->env_list[i]] - 1) + 128;
+      int c;
+      for(c = 0; c < ch; c++){
+        float *dst = m->env_pcm + ((size_t)i*ch + c)*stride;
+        memcpy(dst, v->pcm[c] + 64L*m->env_first[m->env_list[i]], sizeof(float)*len);
+        if(len < stride) memset(dst + len, 0, sizeof(float)*(stride - len));
+      }
+      vb200shim_envelope_state_get(v, m->env_state + (size_t)i*sw);
+      m->env_nsteps[i] = m->env_steps[m->env_list[i]];
+    }
+    rc = vb200_envelope_search_var(vb200shim_ctx(m->bind), na, m->env_pcm, VB200_PCM_F32_PLANAR, stride, maxsteps,
+                                   m->env_nsteps, m->env_state, m->env_ret);
+    if(rc){ vb200shim_set_error(m->bind, rc); fprintf(stderr, "vb200 multistream: envelope search failed (%d): %s\n", rc, vb200_last_error()); return OV_EFAULT; }
+#pragma omp parallel for schedule(static) if(na > 8)
+    for(i = 0; i < na; i++){
+      const int s = m->env_list[i];
+      vb200shim_envelope_commit(&m->vd[s], m->env_first[s], m->env_steps[s], m->env_state + (size_t)i*sw, m->env_ret + (size_t)i*maxsteps);
+    }
+  }
+  return 0;
+}
+
+static void round_after(void *user, int i){                   /* run by the thread that packed block i of the current size */
+  vb200ms *m = (vb200ms*)user;
+  const int s = m->ready_stream[m->cur_w][i];
+  ogg_packet op;
+  vorbis_bitrate_addblock(&m->vb[s]);
+  while(vorbis_bitrate_flushpacket(&m->vd[s], &op)) if(m->sink) m->sink(m->sink_user, s, &op);
+}
+
+/* One round: the envelope search of every stream in one device call, then every stream that has a block ready
+ * (vorbis_analysis_blockout) contributes it; the blocks go to the device in one call per block size; the host half
+ * (the reference's floor1_encode and residue backend, the per-stream bitrate queue) runs on all host threads, one
+ * stream per thread at a time; packets are handed to `sink` (called from those threads, never concurrently for
+ * one stream) in block order.  Returns the number of blocks processed (0: every stream needs more data), or a
+ * negative OV_* code. */
 typedef void (*vb200ms_sink)(void *user, int stream, ogg_packet *op);
 int vb200ms_round(vb200ms *m, vb200ms_sink sink, void *user){
   int cnt[2] = {0, 0}, i, w, rc, total = 0;
-  ogg_packet op;
+  char *got;
+  if((rc = env_round(m))) return rc;
+  got = (char*)calloc(m->nstreams, 1);
+  if(!got) return OV_EFAULT;
+#pragma omp parallel for schedule(dynamic, 8) if(m->nstreams > 8)
   for(i = 0; i < m->nstreams; i++){
     if(vorbis_analysis_blockout(&m->vd[i], &m->vb[i]) == 1){
       vorbis_block_internal *vbi = (vorbis_block_internal*)m->vb[i].internal;
       int k;
-      w = m->vb[i].W ? 1 : 0;
       m->vb[i].glue_bits = 0; m->vb[i].time_bits = 0; m->vb[i].floor_bits = 0; m->vb[i].res_bits = 0;
       for(k = 0; k < PACKETBLOBS; k++) oggpack_reset(vbi->packetblob[k]);      /* lib/analysis.c:37-41 */
+      got[i] = 1;
+    }
+  }
+  for(i = 0; i < m->nstreams; i++)
+    if(got[i]){
+      w = m->vb[i].W ? 1 : 0;
       m->ready[w][cnt[w]] = &m->vb[i];
       m->ready_stream[w][cnt[w]++] = i;
     }
-  }
+  free(got);
+  m->sink = sink; m->sink_user = user;
   for(w = 0; w < 2; w++){
     if(!cnt[w]) continue;
-    if((rc = forward_batch(m->bind, &m->batch[w], m->ready[w], cnt[w], w))) return rc;
-    for(i = 0; i < cnt[w]; i++){
-      const int s = m->ready_stream[w][i];
-      vorbis_bitrate_addblock(&m->vb[s]);
-      while(vorbis_bitrate_flushpacket(&m->vd[s], &op)) if(sink) sink(user, s, &op);
-    }
+    m->cur_w = w;
+    if((rc = forward_batch(m->bind, &m->batch[w], m->ready[w], cnt[w], w, round_after, m))) return rc;
     total += cnt[w];
   }
   return total;

@@ -314,38 +314,57 @@ int *vb200shim_floor1_fit(vorbis_block *vb, vorbis_look_floor1 *look, const floa
  * the cursor over the marks that picks the next block size (:269-327) is host control flow over a
  * handful of ints and is restated here.  The filter state is handed over in the reference's own
  * envelope_filter_state layout, so ve->filter / ve->stretch stay authoritative between calls.  */
-long vb200shim_envelope_search(vorbis_dsp_state *v){
-  vorbis_info *vi = v->vi;
-  { vb200_binding *bb = vb200shim_binding(v); if(bb) g_cur = bb; }   /* every block starts here: the state's binding becomes current */
-  codec_setup_info *ci = (codec_setup_info*)vi->codec_setup;
+/* the analysis part of _ve_envelope_search split in two so that a driver of many states can run ONE device call
+ * for all of them (vb200_mapping0.c): prepare reports which steps are new, commit stores what the device found */
+int vb200shim_envelope_prepare(vorbis_dsp_state *v, int *first_out){
   envelope_lookup *ve = ((private_state*)(v->backend_state))->ve;
-  long j;
   int first = ve->current/ve->searchstep;
   int last = v->pcm_current/ve->searchstep - VE_WIN;
   if(first < 0) first = 0;
-  if(last + VE_WIN + VE_POST > ve->storage){                   /* :227-230 */
+  if(last + VE_WIN + VE_POST > ve->storage){                   /* lib/envelope.c:227-230 */
     ve->storage = last + VE_WIN + VE_POST;
     ve->mark = (int*)realloc(ve->mark, ve->storage*sizeof(*ve->mark));
   }
-  if(last > first){
-    const int nsteps = last - first, ch = ve->ch;
+  *first_out = first;
+  return last > first ? last - first : 0;
+}
+void vb200shim_envelope_state_get(vorbis_dsp_state *v, int32_t *state){
+  envelope_lookup *ve = ((private_state*)(v->backend_state))->ve;
+  state[0] = ve->stretch;
+  memcpy(state + 1, ve->filter, sizeof(envelope_filter_state)*VE_BANDS*ve->ch);
+}
+void vb200shim_envelope_commit(vorbis_dsp_state *v, int first, int nsteps, const int32_t *state, const uint8_t *ret){
+  envelope_lookup *ve = ((private_state*)(v->backend_state))->ve;
+  ve->stretch = state[0];
+  memcpy(ve->filter, state + 1, sizeof(envelope_filter_state)*VE_BANDS*ve->ch);
+  vb200_envelope_apply_marks(ret, first, nsteps, (int32_t*)ve->mark);   /* int == int32_t on every libvorbis target */
+  ve->current = (first + nsteps)*ve->searchstep;
+}
+
+long vb200shim_envelope_search(vorbis_dsp_state *v){
+  vorbis_info *vi = v->vi;
+  codec_setup_info *ci = (codec_setup_info*)vi->codec_setup;
+  envelope_lookup *ve = ((private_state*)(v->backend_state))->ve;
+  long j;
+  int first, nsteps, last;
+  { vb200_binding *bb = vb200shim_binding(v); if(bb) g_cur = bb; }   /* every block starts here: the state's binding becomes current */
+  nsteps = vb200shim_envelope_prepare(v, &first);
+  last = v->pcm_current/ve->searchstep - VE_WIN;
+  if(nsteps > 0){
+    const int ch = ve->ch;
     const long len = (long)ve->searchstep*(nsteps - 1) + ve->winlength;
-    float *tmp = (float*)malloc(sizeof(float)*(size_t)ch*len);
-    int32_t *state = (int32_t*)malloc(sizeof(int32_t)*VB200_VE_STATE_WORDS(ch));
-    uint8_t *ret = (uint8_t*)malloc((size_t)nsteps);
-    int32_t *mark = (int32_t*)ve->mark;                        /* int == int32_t on every libvorbis target */
+    float *tmp = bind_fscratch((size_t)ch*len);
+    int32_t *state = bind_iscratch((size_t)VB200_VE_STATE_WORDS(ch) + (size_t)(nsteps + 3)/4 + 1);
+    uint8_t *ret = state ? (uint8_t*)(state + VB200_VE_STATE_WORDS(ch)) : NULL;
     int c, rc;
-    for(c = 0; c < ch; c++) memcpy(tmp + (size_t)c*len, v->pcm[c] + (long)ve->searchstep*first, sizeof(float)*len);
-    state[0] = ve->stretch;
-    memcpy(state + 1, ve->filter, sizeof(envelope_filter_state)*VE_BANDS*ch);
-    rc = vb200_envelope_search(g.ctx, 1, tmp, VB200_PCM_F32_PLANAR, len, 0, nsteps, state, ret);
-    if(rc) shim_warn("envelope_search", rc);
+    if(!tmp || !state){ shim_warn("envelope_search (host scratch)", VB200_EFAULT); }
     else{
-      ve->stretch = state[0];
-      memcpy(ve->filter, state + 1, sizeof(envelope_filter_state)*VE_BANDS*ch);
-      vb200_envelope_apply_marks(ret, first, nsteps, mark);
+      for(c = 0; c < ch; c++) memcpy(tmp + (size_t)c*len, v->pcm[c] + (long)ve->searchstep*first, sizeof(float)*len);
+      vb200shim_envelope_state_get(v, state);
+      rc = vb200_envelope_search(g.ctx, 1, tmp, VB200_PCM_F32_PLANAR, len, 0, nsteps, state, ret);
+      if(rc) shim_warn("envelope_search", rc);
+      else vb200shim_envelope_commit(v, first, nsteps, state, ret);
     }
-    free(tmp); free(state); free(ret);
   }
   ve->current = last*ve->searchstep;
   {                                                            /* :269-327 */
