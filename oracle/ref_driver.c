@@ -973,6 +973,9 @@ long ref_ms_encode(int nstreams, int ch, long rate, float quality, int device, c
   sum.hash = hash; sum.bytes = bytes; sum.count = count; sum.eos = eos;
   while(!alldone){
     long todo = nsamples - pos < chunk ? nsamples - pos : chunk;
+    /* the application's side: N independent streams are fed by all host threads (the first and the last write of
+     * a stream run the reference's LPC pre-/post-extrapolation, ~1 ms each) */
+#pragma omp parallel for private(c) schedule(dynamic, 8) if(nstreams > 8)
     for(i = 0; i < nstreams; i++){
       vorbis_dsp_state *vd = vb200ms_state(m, i);
       if(todo > 0){

@@ -96,6 +96,13 @@ __device__ __forceinline__ int lds_s16_if(unsigned a, int old, bool p) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.s16 %0, [%1];\n\t}" : "+h"(v) : "r"(a), "r"((int)p));
   return (int)v;
 }
+__device__ __forceinline__ int lds_s32_if(unsigned a, int old, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.s32 %0, [%1];\n\t}" : "+r"(old) : "r"(a), "r"((int)p));
+  return old;
+}
+__device__ __forceinline__ void sts_s32_if(unsigned a, int v, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.s32 [%0], %1;\n\t}" :: "r"(a), "r"(v), "r"((int)p) : "memory");
+}
 __device__ __forceinline__ void sts_f32_if(unsigned a, float v, bool p) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" :: "r"(a), "f"(v), "r"((int)p) : "memory");
 }
@@ -124,6 +131,8 @@ __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ float lds_f32_if(unsigned a, float old, bool p) { return p ? lds_f32(a) : old; }
 __device__ __forceinline__ int lds_s16_if(unsigned a, int old, bool p) { return p ? lds_s16(a) : old; }
 __device__ __forceinline__ void sts_f32_if(unsigned a, float v, bool p) { if (p) sts_f32(a, v); }
+__device__ __forceinline__ int lds_s32_if(unsigned a, int old, bool p) { return p ? lds_s32(a) : old; }
+__device__ __forceinline__ void sts_s32_if(unsigned a, int v, bool p) { if (p) sts_s32(a, v); }
 __device__ __forceinline__ void sts_s16_if(unsigned a, int v, bool p) { if (p) sts_s16(a, v); }
 #endif
 

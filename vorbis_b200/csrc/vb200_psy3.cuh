@@ -131,7 +131,7 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
   const int lane = tid & 31, warp = tid >> 5;
   const unsigned full = 0xffffffffu;
   float *seed = copies, *astk = copies + tp;
-  short *pstk = reinterpret_cast<short *>(copies + 2 * tp);
+  int *lstk = reinterpret_cast<int *>(copies + 2 * tp);      // position + L of every stack entry (what the pop test compares)
   const float NINF = -3.0e38f;                       // below every seed (>= -9999)
   const int p0 = tid * RB;
   // 0. merge: this thread's RB positions
@@ -197,12 +197,13 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
   // pop the top entry, or push seeds[i] and advance.  Top two entries in registers (l = pos + L).
   int cnt = 0;
   if (start < BIG) {
-    const unsigned as_ = smem_u32(seed), aa = smem_u32(astk) + 4u * (unsigned)start, ap = smem_u32(pstk) + 2u * (unsigned)start;
+    const unsigned as_ = smem_u32(seed), aa = smem_u32(astk) + 4u * (unsigned)start, dl = smem_u32(lstk) - smem_u32(astk);
     const int last = end < total ? end : total - 1;
     float a0 = 0.f, a1 = 0.f;
     int l0 = 0, l1 = 0, depth = 0, i = start;
     float s = lds_f32(as_ + 4u * (unsigned)i);
     const unsigned tl = (unsigned)(total - 1);
+    unsigned top = aa;                               // address of the first free stack slot (amplitudes; positions at + dl)
     while (i <= last) {
       // lib/psy.c:465-484: pop while !(seeds[i] < amp[top]) and the two top entries both reach past i and
       // amp[top] <= amp[top-1]; otherwise push.  Branch free: every lane does exactly one of the two per
@@ -210,17 +211,18 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
       const bool pop = depth >= 2 && !(s < a0) && i < l0 && a0 <= a1 && i < l1;
       const bool push = !pop && i < end;             // i == end: only the pops belong to this segment
       const bool rel = pop && depth >= 3;            // the new second entry comes back from shared memory
-      const unsigned o = (unsigned)(pop ? depth - 3 : depth);
-      const float ra = lds_f32_if(aa + 4u * o, a1, rel);
-      const int rl = lds_s16_if(ap + 2u * o, l1 - L, rel) + L;
-      sts_f32_if(aa + 4u * o, s, push);
-      sts_s16_if(ap + 2u * o, i, push);
+      const unsigned o = pop ? top - 12u : top;
+      const float ra = lds_f32_if(o, a1, rel);
+      const int rl = lds_s32_if(o + dl, l1, rel);
+      sts_f32_if(o, s, push);
+      sts_s32_if(o + dl, i + L, push);
       const float na0 = pop ? a1 : (push ? s : a0);
       const int nl0 = pop ? l1 : (push ? i + L : l0);
       a1 = pop ? ra : (push ? a0 : a1);
       l1 = pop ? rl : (push ? l0 : l1);
       a0 = na0; l0 = nl0;
-      depth += pop ? -1 : (push ? 1 : 0);
+      const int dd = pop ? -1 : (push ? 1 : 0);
+      depth += dd; top += 4 * dd;
       i += pop ? 0 : 1;
       const unsigned in = (unsigned)i < tl ? (unsigned)i : tl;
       s = lds_f32_if(as_ + 4u * in, s, !pop);
@@ -235,12 +237,12 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
   for (int d = 0; d < cnt; d++) {
     const float a = astk[start + d];
     float an; int pn;
-    if (d + 1 < cnt) { an = astk[start + d + 1]; pn = pstk[start + d + 1]; }
+    if (d + 1 < cnt) { an = astk[start + d + 1]; pn = lstk[start + d + 1] - L; }
     else if (end < total) { an = astk[end]; pn = end; }          // first entry of the next segment
     else { an = NINF; pn = 0; }
-    int endpos = an > a ? pn : pstk[start + d] + L + 1;
+    int endpos = an > a ? pn : lstk[start + d] + 1;
     if (endpos > total) endpos = total;
-    pstk[start + d] = (short)endpos;
+    lstk[start + d] = endpos;
     if (endpos > Mx) Mx = endpos;
   }
   int incl = Mx;
@@ -256,7 +258,7 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
   for (int w2 = 0; w2 < warp; w2++) { const int t = s_misc[4 + w2]; if (t > cursor) cursor = t; }
   for (int d = 0; d < cnt; d++) {
     const float a = astk[start + d];
-    const int endpos = pstk[start + d];
+    const int endpos = lstk[start + d];
     for (int p = cursor; p < endpos; p++) seed[p] = a;
     if (endpos > cursor) cursor = endpos;
   }

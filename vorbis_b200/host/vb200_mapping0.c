@@ -41,6 +41,14 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <time.h>
+
+/* optional wall-clock breakdown of the multi-stream driver (VB200MS_PROFILE=1): seconds per phase, printed at close */
+static double g_prof[8];
+static int g_prof_on = -1;
+static double now_s(void){ struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9*t.tv_nsec; }
+#define PROF_T0() double prof_t0_ = (g_prof_on > 0) ? now_s() : 0.0
+#define PROF_ADD(k) do { if(g_prof_on > 0){ const double t_ = now_s(); g_prof[k] += t_ - prof_t0_; prof_t0_ = t_; } } while(0)
 
 /* from vb200_ref_shim.c */
 typedef struct vb200_binding vb200_binding;
@@ -153,6 +161,7 @@ static int forward_batch(vb200_binding *bind, ms_batch *B, vorbis_block **blocks
   vb200_encode_io io;
   int i, c, rc;
   int err = 0;
+  PROF_T0();
   if((rc = batch_reserve(B, (size_t)nb, ch, N))) return rc;
 #pragma omp parallel for private(c) schedule(static) if(nb > 8)
   for(i = 0; i < nb; i++){
@@ -164,7 +173,9 @@ static int forward_batch(vb200_binding *bind, ms_batch *B, vorbis_block **blocks
   memset(&io, 0, sizeof(io));
   io.pcm = B->pcm; io.pcm_fmt = VB200_PCM_F32_BLOCKS; io.desc = B->desc; io.independent = 1;
   io.posts = B->posts; io.nonzero = B->nonzero; io.iwork = B->iwork; io.ampmax_out = B->ampmax;
+  PROF_ADD(2);
   rc = vb200_encode_dsp(vb200shim_ctx(bind), W, nb, 1, PACKETBLOBS/2, &io);      /* one H2D, the six kernels, one D2H */
+  PROF_ADD(3);
   if(rc){
     vb200shim_set_error(bind, rc);
     fprintf(stderr, "vb200 mapping0: vb200_encode_dsp failed (%d): %s\n", rc, vb200_last_error());
@@ -182,6 +193,7 @@ static int forward_batch(vb200_binding *bind, ms_batch *B, vorbis_block **blocks
       err = r;
     }else if(after) after(user, i);
   }
+  PROF_ADD(4);
   return err;
 }
 
@@ -243,6 +255,11 @@ typedef struct vb200ms {
 void vb200ms_close(vb200ms *m){
   int i, w;
   if(!m) return;
+  if(g_prof_on > 0){
+    fprintf(stderr, "vb200ms profile (s): envelope %.3f  blockout %.3f  stage %.3f  device call %.3f  host half %.3f  threads %d\n",
+            g_prof[0], g_prof[1], g_prof[2], g_prof[3], g_prof[4], m->threads);
+    memset(g_prof, 0, sizeof(g_prof));
+  }
   if(m->bind){ vb200shim_select(&m->vd[0]); vb200shim_detach(); }
   for(i = 0; i < m->nstreams; i++){
     if(m->vb) vorbis_block_clear(&m->vb[i]);
@@ -373,7 +390,10 @@ typedef void (*vb200ms_sink)(void *user, int stream, ogg_packet *op);
 int vb200ms_round(vb200ms *m, vb200ms_sink sink, void *user){
   int cnt[2] = {0, 0}, i, w, rc, total = 0;
   char *got;
+  if(g_prof_on < 0){ const char *e = getenv("VB200MS_PROFILE"); g_prof_on = (e && atoi(e)) ? 1 : 0; }
+  PROF_T0();
   if((rc = env_round(m))) return rc;
+  PROF_ADD(0);
   got = (char*)calloc(m->nstreams, 1);
   if(!got) return OV_EFAULT;
 #pragma omp parallel for schedule(dynamic, 8) if(m->nstreams > 8)
@@ -393,6 +413,7 @@ int vb200ms_round(vb200ms *m, vb200ms_sink sink, void *user){
       m->ready_stream[w][cnt[w]++] = i;
     }
   free(got);
+  PROF_ADD(1);
   m->sink = sink; m->sink_user = user;
   for(w = 0; w < 2; w++){
     if(!cnt[w]) continue;
