@@ -726,7 +726,19 @@ def run_ours(args):
             traffic = per_row * ch * nb
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": KERNELS[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+        # the dominant kernel is issue bound (DRAM < 10 %): executed warp-instructions per row (ncu, profiles/summary.json)
+        # x rows of this launch / (live duration x SMs x SM clock) = IPC, against the 4 issue slots per cycle of an SM
+        issue = None
+        try:
+            ipr = summ["kernels"][KERNELS[dom]]["warp_instructions_per_row"]
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+            ipc = ipr * ch * nb / (kms[dom] * 1e-3 * sms * mhz * 1e6)
+            issue = {"warp_instructions_per_row": ipr, "ipc": ipc, "peak_ipc": 4.0, "frac": ipc / 4.0, "sms": sms, "sm_mhz": mhz,
+                     "source": "ncu instruction count (profiles/summary.json) x rows / (live CUDA-event duration x SMs x clock)"}
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": KERNELS[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "issue": issue,
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": {k: float(v) for k, v in zip(KERNELS, kms)},
                 "kernel_algorithmic_GBps": {k: (float(a * ch * nb / (v * 1e-3) / 1e9) if v > 0 else None)

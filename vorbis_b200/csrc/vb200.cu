@@ -1225,7 +1225,14 @@ static int phaseA_psy_launch(vb200_ctx *c, int W, int nblocks, const vb200_phase
         if ((rc = set_smem(k_phaseA_psy3<KK, RR>, smem3))) return rc;                              \
         k_phaseA_psy3<KK, RR><<<grid_for(c, (rows + RR - 1) / RR, ctas), PSY3_THREADS * RR, smem3, st>>>(P0, P1, ch, rows, A); \
       } while (0)
-#define LAUNCH_PSY3(KK) do { if (R == 1) LAUNCH_PSY3R(KK, 1); else LAUNCH_PSY3R(KK, 2); } while (0)
+#define LAUNCH_PSY4(KK)                                                                            \
+      do {                                                                                         \
+        if ((rc = set_smem(k_phaseA_psy4<KK>, row_bytes))) return rc;                              \
+        k_phaseA_psy4<KK><<<grid_for(c, rows, PSY3_MINB), PSY3_THREADS, row_bytes, st>>>(P0, P1, ch, rows, A); \
+      } while (0)
+      // k_phaseA_psy4 (regressions run behind the scans) is an experiment that measured slower than psy3: opt-in
+      static const bool psy_v4 = []() { const char *e = getenv("VB200_PSY_V4"); return e && atoi(e); }();
+#define LAUNCH_PSY3(KK) do { if (psy_v4) LAUNCH_PSY4(KK); else if (R == 1) LAUNCH_PSY3R(KK, 1); else LAUNCH_PSY3R(KK, 2); } while (0)
       switch (n / 128) {
         case 1: LAUNCH_PSY3(1); break;
         case 2: LAUNCH_PSY3(2); break;
@@ -1234,6 +1241,7 @@ static int phaseA_psy_launch(vb200_ctx *c, int W, int nblocks, const vb200_phase
         default: LAUNCH_PSY3(16); break;
       }
 #undef LAUNCH_PSY3R
+#undef LAUNCH_PSY4
 #undef LAUNCH_PSY3
     } else if (v2ok) {
       const int total = P0.total > P1.total ? P0.total : P1.total;

@@ -318,7 +318,13 @@ vb200ms *vb200ms_open(int nstreams, int channels, long rate, float quality, int 
   vorbis_comment_init(&m->vc);
   vorbis_info_init(&m->vi[0]);
   if(vorbis_encode_init_vbr(&m->vi[0], channels, rate, quality)){ vb200ms_close(m); return NULL; }
-  for(i = 0; i < nstreams; i++){                               /* every state reads the same (read-only) setup */
+  /* every state reads the same (read-only) setup; the first vorbis_analysis_init also builds the setup's shared
+   * encode codebooks (ci->fullbooks, lib/block.c:211-224), so it runs alone, the others on all host threads
+   * (each builds its own psy / floor / residue lookups, ~1.5 ms) */
+  vorbis_analysis_init(&m->vd[0], &m->vi[0]);
+  vorbis_block_init(&m->vd[0], &m->vb[0]);
+#pragma omp parallel for schedule(dynamic, 4) if(nstreams > 8)
+  for(i = 1; i < nstreams; i++){
     vorbis_analysis_init(&m->vd[i], &m->vi[0]);
     vorbis_block_init(&m->vd[i], &m->vb[i]);
   }
