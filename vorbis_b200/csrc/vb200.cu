@@ -1856,8 +1856,27 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
   if (cs < 1) cs = 1;
   if (cs > nstreams) cs = nstreams;
   const size_t pcm_per_stream = enc_pcm_bytes(h, ch, N, 1, bps);
-  for (int s0 = 0, it = 0; s0 < nstreams; s0 += cs, it++) {
-    const int L = it % 3, ns = nstreams - s0 < cs ? nstreams - s0 : cs;
+  // Chunk schedule: the pipeline's fill (first H2D + first kernels before anything overlaps) and drain (last kernels
+  // + last D2H) are exposed, so the first and the last chunks are small (cs/4, cs/2) and the middle ones full size.
+  int ramp = 1;
+  { const char *e = getenv("VB200_CHUNK_RAMP"); if (e) ramp = atoi(e); }
+  std::vector<int> sched;
+  {
+    int left = nstreams;
+    const int q = cs / 4 > 0 ? cs / 4 : 1, hlf = cs / 2 > 0 ? cs / 2 : 1;
+    if (ramp && nstreams >= 6 * cs) {
+      const int head[2] = {q, hlf};
+      for (int k = 0; k < 2; k++) { sched.push_back(head[k]); left -= head[k]; }
+      const int tail = q + hlf;
+      while (left - tail >= cs) { sched.push_back(cs); left -= cs; }
+      if (left - tail > 0) { sched.push_back(left - tail); left = tail; }
+      sched.push_back(hlf); sched.push_back(left - hlf);
+    } else {
+      while (left > 0) { const int t = left < cs ? left : cs; sched.push_back(t); left -= t; }
+    }
+  }
+  for (int s0 = 0, it = 0; it < (int)sched.size(); s0 += sched[it], it++) {
+    const int L = it % 3, ns = sched[it];
     const size_t nb = (size_t)ns * bps, b0 = (size_t)s0 * bps, rows = nb * ch, r0 = b0 * ch;
     cudaStream_t st = c->s_enc[L];
     DevBuf *B = c->enc_lane[L];
