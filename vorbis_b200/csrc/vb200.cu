@@ -76,8 +76,13 @@ struct vb200_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   DevBuf enc_buf[8];                 // scratch of vb200_encode_dsp_dev
   DevBuf str_buf[40];                // scratch of vb200_plan_blocks / vb200_encode_streams[_dev]
-  DevBuf enc_lane[3][17];            // per-lane device buffers of the pipelined vb200_encode_dsp
-  cudaStream_t s_enc[3] = {nullptr, nullptr, nullptr};
+  // vb200_encode_dsp (host buffers): chunks rotate over ENC_SETS buffer sets; one stream per copy direction and
+  // two compute streams, ordered by events (see there)
+  DevBuf enc_lane[4][17];
+  cudaStream_t s_enc[3] = {nullptr, nullptr, nullptr};   // compute 0, compute 1, host->device
+  cudaStream_t s_d2h = nullptr;
+  cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr}, ev_cmp[4] = {nullptr, nullptr, nullptr, nullptr},
+              ev_d2h[4] = {nullptr, nullptr, nullptr, nullptr};
   int psy_ctas_per_sm = 5;
   int psy_carveout_ctas = -1;        // CTAs/SM the generic psy kernel's shared-memory carve-out was last set for (per device)
   // The *_dev entry points keep their intermediates in per-context scratch: two calls in flight on different
@@ -145,6 +150,10 @@ static int ctx_build(vb200_ctx *c, const vb200_setup *s, int device) {
   CU(cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking));
   for (auto &st : c->s_lane) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto &st : c->s_enc) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  for (auto &e : c->ev_h2d) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : c->ev_cmp) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto &e : c->ev_d2h) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto &st : c->s_split) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming));
@@ -304,6 +313,10 @@ static int ctx_build(vb200_ctx *c, const vb200_setup *s, int device) {
       d.posts = P; d.n = f.n; d.mult = f.mult;
       d.maxover = f.maxover; d.maxunder = f.maxunder; d.maxerr = f.maxerr;
       d.twofitweight = f.twofitweight; d.twofitatten = f.twofitatten;
+      d.int_thresh = f.maxover == (float)(int)f.maxover && f.maxunder == (float)(int)f.maxunder &&
+                     fabsf(f.maxover) < 65536.f && fabsf(f.maxunder) < 65536.f;
+      d.maxover_i = d.int_thresh ? (int)f.maxover : 0;
+      d.maxunder_i = d.int_thresh ? (int)f.maxunder : 0;
       int order[VB200_VIF_POSIT + 2];
       for (int i = 0; i < P; i++) order[i] = i;
       std::sort(order, order + P, [&](int x, int y) { return f.postlist[x] < f.postlist[y]; });
@@ -323,6 +336,41 @@ static int ctx_build(vb200_ctx *c, const vb200_setup *s, int device) {
         }
         d.lo[i] = (short)lo; d.hi[i] = (short)hi;
         d.prcp[i] = 1.f / (float)(hx - lx);             // render_point's divisor for post i+2 is static
+      }
+      {                                                 // accumulate_fit schedule: narrow gaps share a step
+        int len[VB200_VIF_POSIT + 2], nbt = 0;
+        for (int j = 0; j + 1 < P; j++) {
+          int x1 = d.sorted[j + 1];
+          if (x1 >= f.n) x1 = f.n - 1;
+          len[j] = x1 - d.sorted[j] + 1;
+        }
+        for (int j = 0; j + 1 < P;) {
+          int c8 = 0, c16 = 0;
+          while (c8 < 4 && j + c8 + 1 < P && len[j + c8] <= 8) c8++;
+          while (c16 < 2 && j + c16 + 1 < P && len[j + c16] <= 16) c16++;
+          int sh = 5, cnt = 1;
+          if (c8 >= 3) { sh = 3; cnt = c8; }
+          else if (c16 == 2) { sh = 4; cnt = 2; }
+          d.acc_first[nbt] = (unsigned char)j; d.acc_shift[nbt] = (unsigned char)sh; d.acc_cnt[nbt] = (unsigned char)cnt;
+          nbt++;
+          j += cnt;
+        }
+        d.acc_nb = nbt;
+      }
+      {                                                 // dependency levels of the prediction passes
+        int level[VB200_VIF_POSIT + 2], nl = 0, w = 0;
+        level[0] = level[1] = -1;
+        for (int i = 2; i < P; i++) {
+          const int a = level[d.lo[i - 2]], b = level[d.hi[i - 2]];
+          level[i] = (a > b ? a : b) + 1;
+          if (level[i] + 1 > nl) nl = level[i] + 1;
+        }
+        d.nlevels = nl;
+        for (int lv = 0; lv < nl; lv++) {
+          d.lvl_start[lv] = (unsigned char)w;
+          for (int i = 2; i < P; i++) if (level[i] == lv) d.lvl_order[w++] = (unsigned char)i;
+        }
+        d.lvl_start[nl] = (unsigned char)w;
       }
     }
     for (int k = 0; k < s->channels; k++) {
@@ -373,6 +421,10 @@ extern "C" void vb200_ctx_destroy(vb200_ctx *c) {
   for (auto &l : c->enc_lane) for (auto &b : l) if (b.p) cudaFree(b.p);
   for (auto &b : c->str_buf) if (b.p) cudaFree(b.p);
   for (auto &st : c->s_enc) if (st) cudaStreamDestroy(st);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  for (auto &e : c->ev_h2d) if (e) cudaEventDestroy(e);
+  for (auto &e : c->ev_cmp) if (e) cudaEventDestroy(e);
+  for (auto &e : c->ev_d2h) if (e) cudaEventDestroy(e);
   if (c->s_main) cudaStreamDestroy(c->s_main);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   if (c->ev_scratch) cudaEventDestroy(c->ev_scratch);
@@ -1850,7 +1902,7 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
   if ((rc = enc_check(c, W, nstreams, bps, blobno, h))) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
   const int ch = c->setup.channels, N = c->dx[W].N, n = N / 2;
-  int chunk_blocks = 4096;                           // measured on B200: 2048 -> 4.68, 4096 -> 5.12, 8192 -> 4.55 M blocks/s end to end
+  int chunk_blocks = 8192;                           // measured on B200 (ramped schedule): 2048 -> 5.56, 4096 -> 6.11, 8192 -> 6.16 M blocks/s end to end
   { const char *e = getenv("VB200_CHUNK_BLOCKS"); if (e && atoi(e) > 0) chunk_blocks = atoi(e); }
   int cs = chunk_blocks / bps;                       // whole streams per chunk
   if (cs < 1) cs = 1;
@@ -1875,10 +1927,17 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
       while (left > 0) { const int t = left < cs ? left : cs; sched.push_back(t); left -= t; }
     }
   }
+  // Three-stage pipeline over ENC_SETS buffer sets: all host->device copies on one stream, all device->host
+  // copies on another (one DMA engine per direction anyway), the kernels of consecutive chunks alternately on two
+  // compute streams (a chunk's kernel tails overlap the next chunk's kernels).  Events carry the order
+  // H2D(k) -> kernels(k) -> D2H(k) -> H2D(k + ENC_SETS); nothing else is ordered, so the copy engines run ahead
+  // of / behind the kernels instead of every lane alternating copy and compute on its own stream.
+  constexpr int ENC_SETS = 4;
+  cudaStream_t s_h2d = c->s_enc[2], s_d2h = c->s_d2h;
   for (int s0 = 0, it = 0; it < (int)sched.size(); s0 += sched[it], it++) {
-    const int L = it % 3, ns = sched[it];
+    const int L = it % ENC_SETS, ns = sched[it];
     const size_t nb = (size_t)ns * bps, b0 = (size_t)s0 * bps, rows = nb * ch, r0 = b0 * ch;
-    cudaStream_t st = c->s_enc[L];
+    cudaStream_t st = c->s_enc[it & 1];
     DevBuf *B = c->enc_lane[L];
     void *p;
     vb200_encode_io d = *h;
@@ -1899,10 +1958,16 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
     if ((rc = ensure_buf(B[14], sizeof(float) * (size_t)cs * bps, &p))) return rc; d.ampmax_out = (float *)p;
     EncScratch S;
     if ((rc = enc_scratch(B, (size_t)cs * bps * ch, (size_t)cs * bps, n, nullptr, s16, &S))) return rc;
-    CU(cudaMemcpyAsync((void *)d.pcm, (const char *)h->pcm + pcm_per_stream * s0, pcm_per_stream * ns, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync((void *)d.desc, h->desc + b0, sizeof(vb200_block_desc) * nb, cudaMemcpyHostToDevice, st));
-    if (h->ampmax0) CU(cudaMemcpyAsync((void *)d.ampmax0, h->ampmax0 + s0, sizeof(float) * ns, cudaMemcpyHostToDevice, st));
+    if (it >= ENC_SETS) CU(cudaStreamWaitEvent(s_h2d, c->ev_d2h[L], 0));   // this set's previous chunk is back on the host
+    CU(cudaMemcpyAsync((void *)d.pcm, (const char *)h->pcm + pcm_per_stream * s0, pcm_per_stream * ns, cudaMemcpyHostToDevice, s_h2d));
+    CU(cudaMemcpyAsync((void *)d.desc, h->desc + b0, sizeof(vb200_block_desc) * nb, cudaMemcpyHostToDevice, s_h2d));
+    if (h->ampmax0) CU(cudaMemcpyAsync((void *)d.ampmax0, h->ampmax0 + s0, sizeof(float) * ns, cudaMemcpyHostToDevice, s_h2d));
+    CU(cudaEventRecord(c->ev_h2d[L], s_h2d));
+    CU(cudaStreamWaitEvent(st, c->ev_h2d[L], 0));
     if ((rc = encode_launch(c, W, ns, bps, blobno, &d, S, st))) return rc;
+    CU(cudaEventRecord(c->ev_cmp[L], st));
+    CU(cudaStreamWaitEvent(s_d2h, c->ev_cmp[L], 0));
+    st = s_d2h;
     CU(cudaMemcpyAsync(h->posts + r0 * VB200_FLOOR1_STRIDE, d.posts, sizeof(int32_t) * rows * VB200_FLOOR1_STRIDE, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h->nonzero + r0, d.nonzero, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync((char *)h->iwork + isz * r0 * n, d.iwork, isz * rows * n, cudaMemcpyDeviceToHost, st));
@@ -1913,8 +1978,10 @@ extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int 
     if (h->mdct) CU(cudaMemcpyAsync(h->mdct + r0 * n, S.mdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
     if (h->logmdct) CU(cudaMemcpyAsync(h->logmdct + r0 * n, S.logmdct, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
     if (h->logmask) CU(cudaMemcpyAsync(h->logmask + r0 * n, S.logmask, sizeof(float) * rows * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(c->ev_d2h[L], s_d2h));
   }
   for (auto &st : c->s_enc) CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(c->s_d2h));
   return 0;
 }
 

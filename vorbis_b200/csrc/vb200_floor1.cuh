@@ -25,6 +25,15 @@ struct Floor1Dev {                     // vorbis_look_floor1 (lib/codec_internal
   short fwd[VB200_VIF_POSIT + 3], rev[VB200_VIF_POSIT + 3];
   short lo[VB200_VIF_POSIT + 1], hi[VB200_VIF_POSIT + 1];
   float prcp[VB200_VIF_POSIT + 1];     // 1 / (postlist[hi[i]] - postlist[lo[i]])
+  // posts 2..P-1 ordered by dependency level (a post is predicted from its two neighbours lo[], hi[], which have
+  // smaller indices): level 0 needs only posts 0 and 1, level k only levels < k.  lvl_start[k]..lvl_start[k+1]
+  // index lvl_order[]; the prediction passes run one level per step, one lane per post
+  int nlevels;
+  // accumulate_fit batches: gaps acc_first[b] .. +acc_cnt[b]-1, each on a group of (1 << acc_shift[b]) lanes
+  int acc_nb;
+  unsigned char acc_first[VB200_VIF_POSIT + 1], acc_shift[VB200_VIF_POSIT + 1], acc_cnt[VB200_VIF_POSIT + 1];
+  int int_thresh, maxover_i, maxunder_i;   // maxover / maxunder as integers when they are whole numbers (inspect_error)
+  unsigned char lvl_order[VB200_VIF_POSIT + 1], lvl_start[VB200_VIF_POSIT + 5];
 };
 static_assert(sizeof(Floor1Dev) % 4 == 0, "Floor1Dev is copied as words");
 static_assert((sizeof(Floor1Dev) * VB200_MAX_SUBMAPS) % 8 == 0, "the per-warp fp64 terms follow the floor table in shared memory");
@@ -40,7 +49,7 @@ struct Floor1Args {
 #define F1_STATE (3 * (VB200_VIF_POSIT + 2) + 3 * ((VB200_VIF_POSIT + 2 + 1) / 2))   // A, B, out int; lon, hin, memo short
 
 __host__ __device__ inline size_t floor1_fit_smem_per_warp(int n) {
-  return sizeof(unsigned short) * (size_t)n + sizeof(int) * ((VB200_VIF_POSIT + 1) * F1_ACC + F1_STATE);
+  return ((sizeof(unsigned short) * (size_t)n + 7) & ~(size_t)7) + sizeof(int) * ((VB200_VIF_POSIT + 1) * F1_ACC + F1_STATE);
 }
 
 __device__ __forceinline__ int f1_dBquant(float x) {               // lib/floor1.c:278-283
@@ -99,14 +108,35 @@ __device__ __forceinline__ int f1_inspect(const Floor1Dev &F, const unsigned sho
                                           int y0, int y1, int lane) {
   const F1Line L(x0, x1, y0, y1);
   int mse = 0, viol = 0;
-  for (int x = x0 + lane; x < x1; x += 32) {
-    const int y = L.at(x);
-    const int v = q[x];
-    const int val = v & 0x7fff;
-    mse += (y - val) * (y - val);
-    if ((v & 0x8000) && (x == x0 || val)) {
-      if ((float)y + F.maxover < (float)val) viol = 1;
-      if ((float)y - F.maxunder > (float)val) viol = 1;
+  int x = x0 + lane;
+  if (x < x1) {
+    // the line at this lane's first x in closed form, then 32 abscissae per step: the error term advances by
+    // (32*ady) mod adx and wraps at most once more than floor(32*ady / adx) times
+    int y = L.at(x);
+    int r = (x - x0) * L.ady;
+    { int qq = __float2int_rz((float)r * L.rcp); int t = r - qq * L.adx; if (t < 0) t += L.adx; else if (t >= L.adx) t -= L.adx; r = t; }
+    const int n32 = 32 * L.ady;
+    int d32 = __float2int_rz((float)n32 * L.rcp);
+    int m32 = n32 - d32 * L.adx;
+    if (m32 < 0) { d32--; m32 += L.adx; } else if (m32 >= L.adx) { d32++; m32 -= L.adx; }
+    const int ystep = 32 * L.base + d32 * L.step;
+    const bool ith = F.int_thresh != 0;                // maxover / maxunder are whole numbers: integer compares are exact
+    for (; x < x1; x += 32) {
+      const int v = q[x];
+      const int val = v & 0x7fff;
+      mse += (y - val) * (y - val);
+      if ((v & 0x8000) && (x == x0 || val)) {
+        if (ith) {
+          if (y + F.maxover_i < val) viol = 1;
+          if (y - F.maxunder_i > val) viol = 1;
+        } else {
+          if ((float)y + F.maxover < (float)val) viol = 1;
+          if ((float)y - F.maxunder > (float)val) viol = 1;
+        }
+      }
+      r += m32;
+      y += ystep;
+      if (r >= L.adx) { r -= L.adx; y += L.step; }
     }
   }
   if (__any_sync(0xffffffffu, viol)) return 1;
@@ -192,16 +222,22 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
     }
     for (int i = lane; i < P; i += 32) { A[i] = -200; B[i] = -200; lon[i] = 0; hin[i] = 1; memo[i] = -1; }
     __syncwarp();
-    // accumulate_fit: one accumulator per gap, both ends inclusive
+    // accumulate_fit: one accumulator per gap, both ends inclusive.  The narrow low-frequency gaps (<= 8 or <= 16
+    // bins) are taken four or two at a time, one quarter / half warp each (static schedule acc_*): the twelve
+    // reductions of a step then serve up to four gaps.
     int nonzero = 0;
-    for (int j = 0; j < P - 1; j++) {
+    for (int bt = 0; bt < F.acc_nb; bt++) {
+      const int sh = F.acc_shift[bt], first = F.acc_first[bt], cnt = F.acc_cnt[bt];
+      const int w = 1 << sh, sub = lane >> sh, l = lane & (w - 1);
+      const int j = first + (sub < cnt ? sub : cnt - 1);       // spare sub-groups repeat the last gap, results unused
+      const unsigned gmask = sh == 5 ? 0xffffffffu : (((1u << w) - 1u) << (sub << sh));
       const int x0 = F.sorted[j];
       int x1 = F.sorted[j + 1];
       if (x1 >= n) x1 = n - 1;
       int s[F1_ACC];
 #pragma unroll
       for (int k = 0; k < F1_ACC; k++) s[k] = 0;
-      for (int x = x0 + lane; x <= x1; x += 32) {
+      for (int x = x0 + l; x <= x1; x += w) {
         const int v = q[x], val = v & 0x7fff;
         if (val) {
           if (v & 0x8000) { s[0] += x; s[1] += val; s[2] += x * x; s[3] += val * val; s[4] += x * val; s[5]++; }
@@ -209,15 +245,21 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
         }
       }
 #pragma unroll
-      for (int k = 0; k < F1_ACC; k++) s[k] = __reduce_add_sync(0xffffffffu, s[k]);
-      if (lane < F1_ACC) {                               // raw sums; turned into fit_line's terms below
-        int v = s[0];
+      for (int k = 0; k < F1_ACC; k++) s[k] = __reduce_add_sync(gmask, s[k]);
+      {                                                  // raw sums; turned into fit_line's terms below
+        int v = s[0], v2 = s[8];
 #pragma unroll
-        for (int k = 1; k < F1_ACC; k++) if (lane == k) v = s[k];
-        reinterpret_cast<int *>(term)[j * F1_ACC + lane] = v;
+        for (int k = 1; k < F1_ACC; k++) if (l == k) v = s[k];
+#pragma unroll
+        for (int k = 9; k < F1_ACC; k++) if (l + 8 == k) v2 = s[k];
+        if (sub < cnt) {
+          if (l < F1_ACC && l < w) reinterpret_cast<int *>(term)[j * F1_ACC + l] = v;
+          if (w == 8 && l < F1_ACC - 8) reinterpret_cast<int *>(term)[j * F1_ACC + 8 + l] = v2;
+          nonzero |= s[5];
+        }
       }
-      nonzero += s[5];
     }
+    nonzero = __any_sync(0xffffffffu, nonzero != 0);
     __syncwarp();
     // what fit_line adds for a gap, chain f: (double)Xb + (double)Xa * weight (lib/floor1.c:465-474).  One
     // lane per gap turns its 12 ints into the 6 doubles in place (same 48 bytes, private to the lane).
@@ -278,15 +320,19 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
     if (lane == 0) {
       out[0] = f1_postY(A, B, 0);
       out[1] = f1_postY(A, B, 1);
-      for (int i = 2; i < P; i++) {
+      fit_nonzero[row] = 1;
+    }
+    __syncwarp();
+    for (int lv = 0; lv < F.nlevels; lv++) {             // out[i] depends on out[lo], out[hi] only: level by level
+      for (int t = F.lvl_start[lv] + lane; t < F.lvl_start[lv + 1]; t += 32) {
+        const int i = F.lvl_order[t];
         const int ln = F.lo[i - 2], hn = F.hi[i - 2];
         const int predicted = f1_point(F.postlist[ln], F.postlist[hn], out[ln], out[hn], F.postlist[i], F.prcp[i - 2]);
         const int vx = f1_postY(A, B, i);
         out[i] = (vx >= 0 && predicted != vx) ? vx : (predicted | 0x8000);
       }
-      fit_nonzero[row] = 1;
+      __syncwarp();
     }
-    __syncwarp();
     for (int i = lane; i < VB200_FLOOR1_STRIDE; i += 32) po[i] = i < P ? out[i] : 0;
   }
 }
@@ -332,19 +378,23 @@ k_floor1_render(Floor1Args a, int32_t *__restrict__ posts, const int32_t *__rest
       post[i] = val | (p & 0x8000);
     }
     __syncwarp();
-    if (lane == 0) {                                     // prediction / flag pass, :788-832
-      for (int i = 2; i < P; i++) {
+    // prediction / flag pass, :788-832, one dependency level per step.  A post reads its neighbours' VALUES (final
+    // since their level) and its own flag (only posts of later levels clear it); several lanes may clear the same
+    // neighbour's flag (the "used" bit, read after the pass), hence the atomic AND.
+    for (int lv = 0; lv < F.nlevels; lv++) {
+      for (int t = F.lvl_start[lv] + lane; t < F.lvl_start[lv + 1]; t += 32) {
+        const int i = F.lvl_order[t];
         const int ln = F.lo[i - 2], hn = F.hi[i - 2];
         const int predicted = f1_point(F.postlist[ln], F.postlist[hn], post[ln], post[hn], F.postlist[i], F.prcp[i - 2]);
         if ((post[i] & 0x8000) || predicted == post[i]) {
           post[i] = predicted | 0x8000;
         } else {
-          post[ln] &= 0x7fff;
-          post[hn] &= 0x7fff;
+          atomicAnd(post + ln, 0x7fff);
+          atomicAnd(post + hn, 0x7fff);
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
     for (int i = lane; i < P; i += 32) pr[i] = post[i];
     // the posts that carry a value, in abscissa order
     int nseg = 0;

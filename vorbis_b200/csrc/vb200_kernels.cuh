@@ -81,6 +81,8 @@ __device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld
 __device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_s16(unsigned a) { short v; asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(a)); return (int)v; }
 __device__ __forceinline__ int4 lds_v4(unsigned a) { int4 v; asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f4(unsigned a) { float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f4(unsigned a, float4 v) { asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory"); }
 __device__ __forceinline__ void sts_s16(unsigned a, int v) { asm volatile("st.shared.s16 [%0], %1;" :: "r"(a), "h"((short)v) : "memory"); }
 __device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
@@ -122,6 +124,7 @@ __device__ __forceinline__ int lds_acquire(unsigned a) { int v; asm volatile("ld
 __device__ __forceinline__ int lds_volatile(unsigned a) { int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 __device__ __forceinline__ void spin_pause(unsigned ns) { __nanosleep(ns); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 // mbarrier with an arrival count of one: every arrive of the producer completes a phase; a consumer that finds the
 // data it needs not yet published parks on the current phase (try_wait suspends the warp in hardware instead of
 // spending issue slots on a poll loop; it is time limited, so the caller re-checks its condition in a loop)
@@ -141,6 +144,8 @@ __device__ __forceinline__ float lds_f32(unsigned a) { return *reinterpret_cast<
 __device__ __forceinline__ int lds_s32(unsigned a) { return *reinterpret_cast<const int *>(cuemu::dyn_smem() + a); }
 __device__ __forceinline__ int lds_s16(unsigned a) { return (int)*reinterpret_cast<const short *>(cuemu::dyn_smem() + a); }
 __device__ __forceinline__ int4 lds_v4(unsigned a) { return *reinterpret_cast<const int4 *>(cuemu::dyn_smem() + a); }
+__device__ __forceinline__ float4 lds_f4(unsigned a) { return *reinterpret_cast<const float4 *>(cuemu::dyn_smem() + a); }
+__device__ __forceinline__ void sts_f4(unsigned a, float4 v) { *reinterpret_cast<float4 *>(cuemu::dyn_smem() + a) = v; }
 __device__ __forceinline__ void sts_s16(unsigned a, int v) { *reinterpret_cast<short *>(cuemu::dyn_smem() + a) = (short)v; }
 __device__ __forceinline__ void sts_f32(unsigned a, float v) { *reinterpret_cast<float *>(cuemu::dyn_smem() + a) = v; }
 __device__ __forceinline__ void sts_s32(unsigned a, int v) { *reinterpret_cast<int *>(cuemu::dyn_smem() + a) = v; }
@@ -150,6 +155,7 @@ __device__ __forceinline__ int lds_acquire(unsigned a) { return __atomic_load_n(
 __device__ __forceinline__ int lds_volatile(unsigned a) { return __atomic_load_n(reinterpret_cast<int *>(cuemu::dyn_smem() + a), __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void fence_cta() { __atomic_thread_fence(__ATOMIC_ACQ_REL); }
 __device__ __forceinline__ void spin_pause(unsigned) { sched_yield(); }
+__device__ __forceinline__ void prefetch_l2(const void *) {}
 __device__ __forceinline__ void mbar_init1(unsigned) {}
 __device__ __forceinline__ void mbar_arrive_release(unsigned) { __atomic_thread_fence(__ATOMIC_RELEASE); }
 __device__ __forceinline__ void mbar_park(unsigned, unsigned) { sched_yield(); }
@@ -188,6 +194,18 @@ template <> struct XLog2<0> { static constexpr int v = 0; };
 // stores - over all banks (checked for n2 = 1024: both gathers and the stores are conflict free).
 __device__ __forceinline__ int fly_pad(int a) { return a + 2 * (a >> 5) + 2 * (a >> 9); }
 
+// mdct_butterfly_8 (lib/mdct.c:93-115) on registers: v0 = x0..x3, v1 = x4..x7
+__device__ __forceinline__ void dev_fly8(const float4 v0, const float4 v1, float4 &o0, float4 &o1) {
+  const float s62 = v1.z + v0.z, d62 = v1.z - v0.z;
+  const float s40 = v1.x + v0.x, d40 = v1.x - v0.x;
+  const float d51 = v1.y - v0.y, d73 = v1.w - v0.w;
+  const float s51 = v1.y + v0.y, s73 = v1.w + v0.w;
+  o1.z = s62 + s40;  o1.x = s62 - s40;
+  o0.x = d62 + d51;  o0.z = d62 - d51;
+  o0.w = d73 + d40;  o0.y = d73 - d40;
+  o1.w = s73 + s51;  o1.y = s73 - s51;
+}
+
 template <int NC>
 __device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int tid, int nt, float *padbuf = nullptr) {
   const int N = NC ? NC : X.N;
@@ -214,69 +232,77 @@ __device__ __forceinline__ void dev_butterflies(const XformDev &X, float *x, int
     }
     __syncthreads();
   }
-  // 32-point fly, first level (lib/mdct.c:152-209): item q pairs (30-2q) with (14-2q)
+  // 32-point fly, first level (lib/mdct.c:152-209): item q pairs (30-2q) with (14-2q).  The eight cases of
+  // the reference differ in which difference they take (a-b or b-a: both are computed, x-x is +0 either way,
+  // so one is not the negation of the other) and in the rotation: none (q=0,4), (r0 -/+ r1)*C2 (q=2,6), or
+  // r0*k + r1*k' with signed constants (q odd; a - b*c == a + b*(-c) exactly).  All lanes run the three
+  // forms and select: the eight-way switch on q cost eight serialised paths per warp.
   for (int u = tid; u < items; u += nt) {
     float *xc = x + 32 * (u >> 3);
     const int q = u & 7;
     const int a = 30 - 2 * q, b = 14 - 2 * q;
     const float2 hi = *reinterpret_cast<float2 *>(xc + a);
     const float2 lo = *reinterpret_cast<float2 *>(xc + b);
-    float r0, r1, o0, o1;
-    switch (q) {
-      case 0: r0 = hi.x - lo.x; r1 = hi.y - lo.y; o0 = r0;                       o1 = r1;                       break;
-      case 1: r0 = hi.x - lo.x; r1 = hi.y - lo.y; o0 = r0 * VB_C1 - r1 * VB_C3;  o1 = r0 * VB_C3 + r1 * VB_C1;  break;
-      case 2: r0 = hi.x - lo.x; r1 = hi.y - lo.y; o0 = (r0 - r1) * VB_C2;        o1 = (r0 + r1) * VB_C2;        break;
-      case 3: r0 = hi.x - lo.x; r1 = hi.y - lo.y; o0 = r0 * VB_C3 - r1 * VB_C1;  o1 = r1 * VB_C3 + r0 * VB_C1;  break;
-      case 4: r0 = hi.x - lo.x; r1 = lo.y - hi.y; o0 = r1;                       o1 = r0;                       break;
-      case 5: r0 = lo.x - hi.x; r1 = lo.y - hi.y; o0 = r1 * VB_C1 + r0 * VB_C3;  o1 = r1 * VB_C3 - r0 * VB_C1;  break;
-      case 6: r0 = lo.x - hi.x; r1 = lo.y - hi.y; o0 = (r1 + r0) * VB_C2;        o1 = (r1 - r0) * VB_C2;        break;
-      default: r0 = lo.x - hi.x; r1 = lo.y - hi.y; o0 = r1 * VB_C3 + r0 * VB_C1; o1 = r1 * VB_C1 - r0 * VB_C3;  break;
-    }
+    const float dxp = hi.x - lo.x, dxn = lo.x - hi.x, dyp = hi.y - lo.y, dyn = lo.y - hi.y;
+    const float r0 = q >= 5 ? dxn : dxp;
+    const float r1 = q >= 4 ? dyn : dyp;
+    // odd q: o0 = r0*k00 + r1*k01, o1 = r0*k10 + r1*k11
+    const bool q15 = (q == 1) | (q == 7);                // k00 = k11 = C1 there, C3 for q = 3, 5
+    const float k00 = q15 ? VB_C1 : VB_C3;
+    const float k3 = q15 ? VB_C3 : VB_C1;                // the other constant, sign by case
+    const float k01 = q < 4 ? -k3 : k3;
+    const float k10 = q < 4 ? k3 : -k3;
+    const float A0 = r0 * k00 + r1 * k01;
+    const float A1 = r0 * k10 + r1 * k00;
+    // q = 2: (r0 - r1)*C2, (r0 + r1)*C2;  q = 6: (r1 + r0)*C2, (r1 - r0)*C2
+    const float B0 = (q == 2 ? r0 - r1 : r1 + r0) * VB_C2;
+    const float B1 = (q == 2 ? r0 + r1 : r1 - r0) * VB_C2;
+    // q = 0: r0, r1;  q = 4: r1, r0
+    const float T0 = q == 0 ? r0 : r1, T1 = q == 0 ? r1 : r0;
+    const bool odd = q & 1, triv = (q & 3) == 0;
+    const float o0 = odd ? A0 : (triv ? T0 : B0);
+    const float o1 = odd ? A1 : (triv ? T1 : B1);
     *reinterpret_cast<float2 *>(xc + a) = make_float2(hi.x + lo.x, hi.y + lo.y);
     *reinterpret_cast<float2 *>(xc + b) = make_float2(o0, o1);
   }
   __syncthreads();
-  // 16-point fly, first level (lib/mdct.c:117-147): item j pairs (2j) with (2j+8)
-  for (int u = tid; u < items; u += nt) {
-    float *xc = x + 16 * (u >> 2);
-    const int j = u & 3;
-    const float2 lo = *reinterpret_cast<float2 *>(xc + 2 * j);
-    const float2 hi = *reinterpret_cast<float2 *>(xc + 2 * j + 8);
-    float o0, o1;
-    if (j == 0) {
-      const float a = lo.y - hi.y, b = lo.x - hi.x;
-      o0 = (a + b) * VB_C2; o1 = (a - b) * VB_C2;
-    } else if (j == 1) {
-      o0 = lo.y - hi.y; o1 = hi.x - lo.x;
-    } else if (j == 2) {
-      const float a = hi.x - lo.x, b = hi.y - lo.y;
-      o0 = (a - b) * VB_C2; o1 = (a + b) * VB_C2;
-    } else {
-      o0 = hi.x - lo.x; o1 = hi.y - lo.y;
+  // 16-point fly (lib/mdct.c:117-147) with its two 8-point flies (:93-115): one item per 16 values, all in
+  // registers - one shared-memory round trip and one barrier instead of two, and no per-lane case split
+  for (int u = tid; u < (n2 >> 4); u += nt) {
+    float4 *p = reinterpret_cast<float4 *>(x + 16 * u);
+    float4 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3];   // x0..x3, x4..x7, x8..x11, x12..x15
+    {
+      const float a = v0.y - v2.y, b = v0.x - v2.x;      // x1-x9, x0-x8
+      v2.x = v2.x + v0.x; v2.y = v2.y + v0.y;
+      v0.x = (a + b) * VB_C2; v0.y = (a - b) * VB_C2;
     }
-    *reinterpret_cast<float2 *>(xc + 2 * j + 8) = make_float2(hi.x + lo.x, hi.y + lo.y);
-    *reinterpret_cast<float2 *>(xc + 2 * j) = make_float2(o0, o1);
-  }
-  __syncthreads();
-  // 8-point fly (lib/mdct.c:93-115): one item per 8 values, in registers
-  for (int u = tid; u < (n2 >> 3); u += nt) {
-    float4 *p = reinterpret_cast<float4 *>(x + 8 * u);
-    const float4 v0 = p[0], v1 = p[1];           // x0..x3, x4..x7
-    const float s62 = v1.z + v0.z, d62 = v1.z - v0.z;
-    const float s40 = v1.x + v0.x, d40 = v1.x - v0.x;
-    const float d51 = v1.y - v0.y, d73 = v1.w - v0.w;
-    const float s51 = v1.y + v0.y, s73 = v1.w + v0.w;
-    float4 o0, o1;
-    o1.z = s62 + s40;  o1.x = s62 - s40;
-    o0.x = d62 + d51;  o0.z = d62 - d51;
-    o0.w = d73 + d40;  o0.y = d73 - d40;
-    o1.w = s73 + s51;  o1.y = s73 - s51;
+    {
+      const float o0 = v0.w - v2.w, o1 = v2.z - v0.z;    // x3-x11, x10-x2
+      v2.z = v2.z + v0.z; v2.w = v2.w + v0.w;
+      v0.z = o0; v0.w = o1;
+    }
+    {
+      const float a = v3.x - v1.x, b = v3.y - v1.y;      // x12-x4, x13-x5
+      v3.x = v3.x + v1.x; v3.y = v3.y + v1.y;
+      v1.x = (a - b) * VB_C2; v1.y = (a + b) * VB_C2;
+    }
+    {
+      const float o0 = v3.z - v1.z, o1 = v3.w - v1.w;    // x14-x6, x15-x7
+      v3.z = v3.z + v1.z; v3.w = v3.w + v1.w;
+      v1.z = o0; v1.w = o1;
+    }
+    float4 o0, o1, o2, o3;
+    dev_fly8(v0, v1, o0, o1);
+    dev_fly8(v2, v3, o2, o3);
     if (padbuf) {
-      float2 *q = reinterpret_cast<float2 *>(padbuf + fly_pad(8 * u));
+      float2 *q = reinterpret_cast<float2 *>(padbuf + fly_pad(16 * u));
       q[0] = make_float2(o0.x, o0.y); q[1] = make_float2(o0.z, o0.w);
       q[2] = make_float2(o1.x, o1.y); q[3] = make_float2(o1.z, o1.w);
+      float2 *r = reinterpret_cast<float2 *>(padbuf + fly_pad(16 * u + 8));
+      r[0] = make_float2(o2.x, o2.y); r[1] = make_float2(o2.z, o2.w);
+      r[2] = make_float2(o3.x, o3.y); r[3] = make_float2(o3.z, o3.w);
     } else {
-      p[0] = o0; p[1] = o1;
+      p[0] = o0; p[1] = o1; p[2] = o2; p[3] = o3;
     }
   }
   __syncthreads();
@@ -442,57 +468,76 @@ __device__ __forceinline__ void dev_fft_pass4(int ido, int l1, const float *cc, 
     }
     return;
   }
-  const int half = ido >> 1;                         // power of two
-  const int hsh = 31 - __clz(half);
-  const int items = l1 * half;
-  for (int v = tid; v < items + l1; v += nt) {
-    if (v < items) {
-      const int k = v >> hsh, ii = v & (half - 1);
-      const int c0 = k * ido, c1 = c0 + t0, c2 = c1 + t0, c3 = c2 + t0;
+  // ido >= 4 here (ido runs 1, 4, 16, ..).  l1*ido/2 work items of eight reals each: the first l1 are the two
+  // un-twiddled columns (i = 0 and i = ido-1) of one k, the others one twiddled pair (k, i).  With the
+  // special columns on the leading threads a warp runs ONE of the two code paths whenever l1 >= 32.
+  // Padded addresses: fft_idx(e + D) = fft_idx(e) + D + D/16 whenever 32 | D, so the four inputs of an item
+  // (t0 apart) and the output pairs 2*ido apart share one index computation each.
+  const int half = ido >> 1, hm1 = half - 1;
+  const int T = l1 * half;
+  const bool t0al = FIRST || (t0 & 31) == 0, idal = ((2 * ido) & 31) == 0;
+  const int pt0 = FIRST ? t0 : t0 + (t0 >> 4), p2 = 2 * ido + ((2 * ido) >> 4);
+  for (int v = tid; v < T; v += nt) {
+    if (v < l1) {
+      const int k = v;
+      const int c0 = k * ido;
       const int o = 4 * k * ido;
-      if (ii == 0) {
-        const float a0 = cc[fft_rd<FIRST>(c0)], a1 = cc[fft_rd<FIRST>(c1)];
-        const float a2 = cc[fft_rd<FIRST>(c2)], a3 = cc[fft_rd<FIRST>(c3)];
+      {
+        const int r0 = fft_rd<FIRST>(c0);
+        const int r1 = t0al ? r0 + pt0 : fft_idx(c0 + t0), r2 = t0al ? r1 + pt0 : fft_idx(c0 + 2 * t0);
+        const int r3 = t0al ? r2 + pt0 : fft_idx(c0 + 3 * t0);
+        const float a0 = cc[r0], a1 = cc[r1], a2 = cc[r2], a3 = cc[r3];
         const float tr1 = a1 + a3;
         const float tr2 = a0 + a2;
         ch[fft_idx(o)]               = tr1 + tr2;
         ch[fft_idx(o + 4 * ido - 1)] = tr2 - tr1;
         *reinterpret_cast<float2 *>(ch + fft_idx(o + 2 * ido - 1)) = make_float2(a0 - a2, a3 - a1);
-      } else {
-        const int i = 2 * ii;
-        const float wa1r = __ldg(w1 + i - 2), wa1i = __ldg(w1 + i - 1);
-        const float wa2r = __ldg(w2 + i - 2), wa2i = __ldg(w2 + i - 1);
-        const float wa3r = __ldg(w3 + i - 2), wa3i = __ldg(w3 + i - 1);
-        const float2 a0 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c0 + i - 1));
-        const float2 a1 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c1 + i - 1));
-        const float2 a2 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c2 + i - 1));
-        const float2 a3 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c3 + i - 1));
-        const float cr2 = wa1r * a1.x + wa1i * a1.y;
-        const float ci2 = wa1r * a1.y - wa1i * a1.x;
-        const float cr3 = wa2r * a2.x + wa2i * a2.y;
-        const float ci3 = wa2r * a2.y - wa2i * a2.x;
-        const float cr4 = wa3r * a3.x + wa3i * a3.y;
-        const float ci4 = wa3r * a3.y - wa3i * a3.x;
-        const float tr1 = cr2 + cr4, tr4 = cr4 - cr2;
-        const float ti1 = ci2 + ci4, ti4 = ci2 - ci4;
-        const float ti2 = a0.y + ci3, ti3 = a0.y - ci3;
-        const float tr2 = a0.x + cr3, tr3 = a0.x - cr3;
-        const int ic = 2 * ido - i;
-        *reinterpret_cast<float2 *>(ch + fft_idx(o + i - 1))            = make_float2(tr1 + tr2, ti1 + ti2);
-        *reinterpret_cast<float2 *>(ch + fft_idx(o + ic - 1))           = make_float2(tr3 - ti4, tr4 - ti3);
-        *reinterpret_cast<float2 *>(ch + fft_idx(o + 2 * ido + i - 1))  = make_float2(ti4 + tr3, tr4 + ti3);
-        *reinterpret_cast<float2 *>(ch + fft_idx(o + 2 * ido + ic - 1)) = make_float2(tr2 - tr1, ti1 - ti2);
+      }
+      {
+        const int e = c0 + ido - 1;
+        const int r0 = fft_rd<FIRST>(e);
+        const int r1 = t0al ? r0 + pt0 : fft_idx(e + t0), r2 = t0al ? r1 + pt0 : fft_idx(e + 2 * t0);
+        const int r3 = t0al ? r2 + pt0 : fft_idx(e + 3 * t0);
+        const float a0 = cc[r0], a1 = cc[r1], a2 = cc[r2], a3 = cc[r3];
+        const float ti1 = -hsqt2 * (a1 + a3);
+        const float tr1 =  hsqt2 * (a1 - a3);
+        const int s1 = fft_idx(o + ido - 1), s3 = idal ? s1 + p2 : fft_idx(o + 3 * ido - 1);
+        *reinterpret_cast<float2 *>(ch + s1) = make_float2(tr1 + a0, ti1 - a2);   // o[ido-1], o[ido]
+        *reinterpret_cast<float2 *>(ch + s3) = make_float2(a0 - tr1, ti1 + a2);   // o[3ido-1], o[3ido]
       }
     } else {
-      const int k = v - items;
-      const int c0 = k * ido + ido - 1, c1 = c0 + t0, c2 = c1 + t0, c3 = c2 + t0;
+      const int g = v - l1;
+      const int k = g / hm1, ii = 1 + g - k * hm1;     // hm1 is a compile-time constant in the templated kernels
+      const int c0 = k * ido;
       const int o = 4 * k * ido;
-      const float a0 = cc[fft_rd<FIRST>(c0)], a1 = cc[fft_rd<FIRST>(c1)];
-      const float a2 = cc[fft_rd<FIRST>(c2)], a3 = cc[fft_rd<FIRST>(c3)];
-      const float ti1 = -hsqt2 * (a1 + a3);
-      const float tr1 =  hsqt2 * (a1 - a3);
-      *reinterpret_cast<float2 *>(ch + fft_idx(o + ido - 1))     = make_float2(tr1 + a0, ti1 - a2);   // o[ido-1], o[ido]
-      *reinterpret_cast<float2 *>(ch + fft_idx(o + 3 * ido - 1)) = make_float2(a0 - tr1, ti1 + a2);   // o[3ido-1], o[3ido]
+      const int i = 2 * ii;
+      const float wa1r = __ldg(w1 + i - 2), wa1i = __ldg(w1 + i - 1);
+      const float wa2r = __ldg(w2 + i - 2), wa2i = __ldg(w2 + i - 1);
+      const float wa3r = __ldg(w3 + i - 2), wa3i = __ldg(w3 + i - 1);
+      const int r0 = fft_rd<FIRST>(c0 + i - 1);
+      const int r1 = t0al ? r0 + pt0 : fft_idx(c0 + t0 + i - 1), r2 = t0al ? r1 + pt0 : fft_idx(c0 + 2 * t0 + i - 1);
+      const int r3 = t0al ? r2 + pt0 : fft_idx(c0 + 3 * t0 + i - 1);
+      const float2 a0 = *reinterpret_cast<const float2 *>(cc + r0);
+      const float2 a1 = *reinterpret_cast<const float2 *>(cc + r1);
+      const float2 a2 = *reinterpret_cast<const float2 *>(cc + r2);
+      const float2 a3 = *reinterpret_cast<const float2 *>(cc + r3);
+      const float cr2 = wa1r * a1.x + wa1i * a1.y;
+      const float ci2 = wa1r * a1.y - wa1i * a1.x;
+      const float cr3 = wa2r * a2.x + wa2i * a2.y;
+      const float ci3 = wa2r * a2.y - wa2i * a2.x;
+      const float cr4 = wa3r * a3.x + wa3i * a3.y;
+      const float ci4 = wa3r * a3.y - wa3i * a3.x;
+      const float tr1 = cr2 + cr4, tr4 = cr4 - cr2;
+      const float ti1 = ci2 + ci4, ti4 = ci2 - ci4;
+      const float ti2 = a0.y + ci3, ti3 = a0.y - ci3;
+      const float tr2 = a0.x + cr3, tr3 = a0.x - cr3;
+      const int ic = 2 * ido - i;
+      const int o1 = fft_idx(o + i - 1), o2 = fft_idx(o + ic - 1);
+      const int o3 = idal ? o1 + p2 : fft_idx(o + 2 * ido + i - 1), o4 = idal ? o2 + p2 : fft_idx(o + 2 * ido + ic - 1);
+      *reinterpret_cast<float2 *>(ch + o1) = make_float2(tr1 + tr2, ti1 + ti2);
+      *reinterpret_cast<float2 *>(ch + o2) = make_float2(tr3 - ti4, tr4 - ti3);
+      *reinterpret_cast<float2 *>(ch + o3) = make_float2(ti4 + tr3, tr4 + ti3);
+      *reinterpret_cast<float2 *>(ch + o4) = make_float2(tr2 - tr1, ti1 - ti2);
     }
   }
 }
@@ -512,31 +557,28 @@ __device__ __forceinline__ void dev_fft_pass2(int ido, int l1, const float *cc, 
   const int half = ido >> 1;
   const int hsh = 31 - __clz(half);
   const int items = l1 * half;
-  for (int v = tid; v < items + l1; v += nt) {
-    if (v < items) {
-      const int k = v >> hsh, ii = v & (half - 1);
-      const int c0 = k * ido, c1 = c0 + t0;
-      const int o = 2 * k * ido;
-      if (ii == 0) {
-        const float a0 = cc[fft_rd<FIRST>(c0)], a1 = cc[fft_rd<FIRST>(c1)];
-        ch[fft_idx(o)]               = a0 + a1;
-        ch[fft_idx(o + 2 * ido - 1)] = a0 - a1;
-      } else {
-        const int i = 2 * ii;
-        const float wr = __ldg(w1 + i - 2), wi = __ldg(w1 + i - 1);
-        const float2 a0 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c0 + i - 1));
-        const float2 a1 = *reinterpret_cast<const float2 *>(cc + fft_rd<FIRST>(c1 + i - 1));
-        const float tr2 = wr * a1.x + wi * a1.y;
-        const float ti2 = wr * a1.y - wi * a1.x;
-        const int ic = 2 * ido - i;
-        *reinterpret_cast<float2 *>(ch + fft_idx(o + i - 1))  = make_float2(a0.x + tr2, a0.y + ti2);
-        *reinterpret_cast<float2 *>(ch + fft_idx(o + ic - 1)) = make_float2(a0.x - tr2, ti2 - a0.y);
-      }
+  for (int v = tid; v < items; v += nt) {
+    const int k = v >> hsh, ii = v & (half - 1);
+    const int c0 = k * ido, c1 = c0 + t0;
+    const int o = 2 * k * ido;
+    if (ii == 0) {                                     // the two un-twiddled columns of this k
+      const float a0 = cc[fft_rd<FIRST>(c0)], a1 = cc[fft_rd<FIRST>(c1)];
+      ch[fft_idx(o)]               = a0 + a1;
+      ch[fft_idx(o + 2 * ido - 1)] = a0 - a1;
+      *reinterpret_cast<float2 *>(ch + fft_idx(o + ido - 1)) =
+          make_float2(cc[fft_rd<FIRST>(c0 + ido - 1)], -cc[fft_rd<FIRST>(c1 + ido - 1)]);   // o[ido-1], o[ido]
     } else {
-      const int k = v - items;
-      const int c0 = k * ido + ido - 1, c1 = c0 + t0;
-      const int o = 2 * k * ido;
-      *reinterpret_cast<float2 *>(ch + fft_idx(o + ido - 1)) = make_float2(cc[fft_rd<FIRST>(c0)], -cc[fft_rd<FIRST>(c1)]);   // o[ido-1], o[ido]
+      const int i = 2 * ii;
+      const float wr = __ldg(w1 + i - 2), wi = __ldg(w1 + i - 1);
+      const int r0 = fft_rd<FIRST>(c0 + i - 1);
+      const int r1 = FIRST ? r0 + t0 : ((t0 & 31) == 0 ? r0 + t0 + (t0 >> 4) : fft_idx(c1 + i - 1));
+      const float2 a0 = *reinterpret_cast<const float2 *>(cc + r0);
+      const float2 a1 = *reinterpret_cast<const float2 *>(cc + r1);
+      const float tr2 = wr * a1.x + wi * a1.y;
+      const float ti2 = wr * a1.y - wi * a1.x;
+      const int ic = 2 * ido - i;
+      *reinterpret_cast<float2 *>(ch + fft_idx(o + i - 1))  = make_float2(a0.x + tr2, a0.y + ti2);
+      *reinterpret_cast<float2 *>(ch + fft_idx(o + ic - 1)) = make_float2(a0.x - tr2, ti2 - a0.y);
     }
   }
 }

@@ -271,19 +271,27 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
 // Two register sets alternate so that the next 16 values are in flight while 16 are accumulated and
 // nothing is copied between registers.
 __device__ __forceinline__ void dev_noise_scan3(int n, float *arr) {
-  float4 *a = reinterpret_cast<float4 *>(arr);
+  // explicit shared-window addresses: with generic pointers the compiler re-derived the base (S2R + IMAD, a
+  // ~25-cycle scoreboard wait) inside the loop, on the one warp everybody else is waiting for
+  unsigned a = smem_u32(arr);
   const int q = n >> 2;                   // float4 count, a multiple of 8 (n is a multiple of 128)
   float t = 0.f;
-  float4 v0 = a[0], v1 = a[1], v2 = a[2], v3 = a[3];
+  float4 v0 = lds_f4(a), v1 = lds_f4(a + 16), v2 = lds_f4(a + 32), v3 = lds_f4(a + 48);
+  float4 w0, w1, w2, w3;
 #define SCAN4(v) do { t += v.x; v.x = t; t += v.y; v.y = t; t += v.z; v.z = t; t += v.w; v.w = t; } while (0)
-  for (int i = 0; i < q; i += 8) {
-    float4 w0 = a[i + 4], w1 = a[i + 5], w2 = a[i + 6], w3 = a[i + 7];
+  for (int i = 8; i < q; i += 8, a += 128) {
+    w0 = lds_f4(a + 64); w1 = lds_f4(a + 80); w2 = lds_f4(a + 96); w3 = lds_f4(a + 112);
     SCAN4(v0); SCAN4(v1); SCAN4(v2); SCAN4(v3);
-    a[i] = v0; a[i + 1] = v1; a[i + 2] = v2; a[i + 3] = v3;
-    if (i + 8 < q) { v0 = a[i + 8]; v1 = a[i + 9]; v2 = a[i + 10]; v3 = a[i + 11]; }
+    sts_f4(a, v0); sts_f4(a + 16, v1); sts_f4(a + 32, v2); sts_f4(a + 48, v3);
+    v0 = lds_f4(a + 128); v1 = lds_f4(a + 144); v2 = lds_f4(a + 160); v3 = lds_f4(a + 176);
     SCAN4(w0); SCAN4(w1); SCAN4(w2); SCAN4(w3);
-    a[i + 4] = w0; a[i + 5] = w1; a[i + 6] = w2; a[i + 7] = w3;
+    sts_f4(a + 64, w0); sts_f4(a + 80, w1); sts_f4(a + 96, w2); sts_f4(a + 112, w3);
   }
+  w0 = lds_f4(a + 64); w1 = lds_f4(a + 80); w2 = lds_f4(a + 96); w3 = lds_f4(a + 112);
+  SCAN4(v0); SCAN4(v1); SCAN4(v2); SCAN4(v3);
+  sts_f4(a, v0); sts_f4(a + 16, v1); sts_f4(a + 32, v2); sts_f4(a + 48, v3);
+  SCAN4(w0); SCAN4(w1); SCAN4(w2); SCAN4(w3);
+  sts_f4(a + 64, w0); sts_f4(a + 80, w1); sts_f4(a + 96, w2); sts_f4(a + 112, w3);
 #undef SCAN4
 }
 
@@ -385,6 +393,15 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
       L[k] = add345(todB_dev(M[k]));                    // lib/mapping0.c:384-385
       __stcs(A.logmdct + (size_t)row * n + tid + k * nt, L[k]);
     }
+#ifndef VB200_NO_PREFETCH
+    {   // the next row of this CTA: HBM -> L2 while this one is worked on (128-byte lines)
+      const int nrow = row0 + gridDim.x * R + half;
+      if (nrow < nrows && tid < 2 * (n / 32)) {
+        const float *src = tid < n / 32 ? A.mdct_in : A.logfft;
+        prefetch_l2(src + (size_t)nrow * n + (tid & (n / 32 - 1)) * 32);
+      }
+    }
+#endif
     __syncthreads();
     PHASE_MARK();   // 0 load
     dev_tone_runs3(P, s_fft, g, att, run_rec, tid);
