@@ -1,13 +1,11 @@
 #!/bin/bash
 # A/B of library variants built under vorbis_b200/_variants (experiments only)
 cp vorbis_b200/libvorbis_b200.so /tmp/cur.so
-python -m pytest tests -m gpu -q -x 2>&1 | tail -2
-for v in cur fitredux; do
+for v in cur oldacc cur oldacc; do
   if [ $v = cur ]; then cp /tmp/cur.so vorbis_b200/libvorbis_b200.so; else cp vorbis_b200/_variants/$v.so vorbis_b200/libvorbis_b200.so; fi
   python bench.py --no-extra --streams 0 2>/dev/null | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read())
-print('$v', 'value %.0f' % d['value'], 'ms %.3f' % d['ms_per_step'], {k: round(v,3) for k,v in d['roofline']['kernel_ms'].items()})"
-  VB200_SPLIT=1 ncu --set full --clock-control none --import-source on -k regex:"k_phaseA_transform|k_floor1_fit" -s 6 -c 2 -o gpurun_out/x_$v python bench.py --steps 1 --warmup 3 --blocks 24000 --no-extra --streams 0 > gpurun_out/x_$v.log 2>&1
+print('$v', 'value %.0f' % d['value'], 'e2e %.0f' % d['e2e']['value'], 'ms %.3f' % d['ms_per_step'], {k: round(v,3) for k,v in d['roofline']['kernel_ms'].items()})"
 done
 cp /tmp/cur.so vorbis_b200/libvorbis_b200.so

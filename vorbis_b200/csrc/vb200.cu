@@ -337,26 +337,6 @@ static int ctx_build(vb200_ctx *c, const vb200_setup *s, int device) {
         d.lo[i] = (short)lo; d.hi[i] = (short)hi;
         d.prcp[i] = 1.f / (float)(hx - lx);             // render_point's divisor for post i+2 is static
       }
-      {                                                 // accumulate_fit schedule: narrow gaps share a step
-        int len[VB200_VIF_POSIT + 2], nbt = 0;
-        for (int j = 0; j + 1 < P; j++) {
-          int x1 = d.sorted[j + 1];
-          if (x1 >= f.n) x1 = f.n - 1;
-          len[j] = x1 - d.sorted[j] + 1;
-        }
-        for (int j = 0; j + 1 < P;) {
-          int c8 = 0, c16 = 0;
-          while (c8 < 4 && j + c8 + 1 < P && len[j + c8] <= 8) c8++;
-          while (c16 < 2 && j + c16 + 1 < P && len[j + c16] <= 16) c16++;
-          int sh = 5, cnt = 1;
-          if (c8 >= 3) { sh = 3; cnt = c8; }
-          else if (c16 == 2) { sh = 4; cnt = 2; }
-          d.acc_first[nbt] = (unsigned char)j; d.acc_shift[nbt] = (unsigned char)sh; d.acc_cnt[nbt] = (unsigned char)cnt;
-          nbt++;
-          j += cnt;
-        }
-        d.acc_nb = nbt;
-      }
       {                                                 // dependency levels of the prediction passes
         int level[VB200_VIF_POSIT + 2], nl = 0, w = 0;
         level[0] = level[1] = -1;
@@ -582,8 +562,11 @@ __device__ __forceinline__ float *mdct_pad_buffer(float *sf) {
 #endif
 }
 
+#ifndef XF_MINB
+#define XF_MINB 5
+#endif
 template <int NC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, XF_MINB)
 k_phaseA_transform(XformDev X, WinDev Wd, int W, int ch, int nrows,
                    PcmSrc src, const vb200_block_desc *__restrict__ desc,
                    float *__restrict__ mdct, float *__restrict__ logfft, float *__restrict__ lmax) {

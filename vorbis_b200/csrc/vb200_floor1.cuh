@@ -5,7 +5,10 @@
 //                    fit_line            :456-521   fp64 chains over per-gap terms computed once per row,
 //                                                   one lane per chain (12 lanes for the two fits of a
 //                                                   split, one fit per half-warp), summed in gap order
-//                    inspect_error       :523-566   lanes over x; the Bresenham line in closed form
+//                    inspect_error       :523-566   lanes over x; the Bresenham line in closed form at a lane's first x,
+//                                                   then 32 abscissae per step with an integer error term; integer
+//                                                   compares when maxover / maxunder are whole numbers
+//                    post prediction     :702-727   one dependency level per step (lvl_*), one lane per post
 //                    greedy splitting    :627-700   warp-uniform control flow, state in shared memory
 // k_floor1_render  floor1_encode minus the bit packing  :765-832 (quantise, predict/flag), :919-945
 //                    (render_line0 :376-403 into ilogmask)
@@ -29,9 +32,6 @@ struct Floor1Dev {                     // vorbis_look_floor1 (lib/codec_internal
   // smaller indices): level 0 needs only posts 0 and 1, level k only levels < k.  lvl_start[k]..lvl_start[k+1]
   // index lvl_order[]; the prediction passes run one level per step, one lane per post
   int nlevels;
-  // accumulate_fit batches: gaps acc_first[b] .. +acc_cnt[b]-1, each on a group of (1 << acc_shift[b]) lanes
-  int acc_nb;
-  unsigned char acc_first[VB200_VIF_POSIT + 1], acc_shift[VB200_VIF_POSIT + 1], acc_cnt[VB200_VIF_POSIT + 1];
   int int_thresh, maxover_i, maxunder_i;   // maxover / maxunder as integers when they are whole numbers (inspect_error)
   unsigned char lvl_order[VB200_VIF_POSIT + 1], lvl_start[VB200_VIF_POSIT + 5];
 };
@@ -222,22 +222,16 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
     }
     for (int i = lane; i < P; i += 32) { A[i] = -200; B[i] = -200; lon[i] = 0; hin[i] = 1; memo[i] = -1; }
     __syncwarp();
-    // accumulate_fit: one accumulator per gap, both ends inclusive.  The narrow low-frequency gaps (<= 8 or <= 16
-    // bins) are taken four or two at a time, one quarter / half warp each (static schedule acc_*): the twelve
-    // reductions of a step then serve up to four gaps.
+    // accumulate_fit: one accumulator per gap, both ends inclusive
     int nonzero = 0;
-    for (int bt = 0; bt < F.acc_nb; bt++) {
-      const int sh = F.acc_shift[bt], first = F.acc_first[bt], cnt = F.acc_cnt[bt];
-      const int w = 1 << sh, sub = lane >> sh, l = lane & (w - 1);
-      const int j = first + (sub < cnt ? sub : cnt - 1);       // spare sub-groups repeat the last gap, results unused
-      const unsigned gmask = sh == 5 ? 0xffffffffu : (((1u << w) - 1u) << (sub << sh));
+    for (int j = 0; j < P - 1; j++) {
       const int x0 = F.sorted[j];
       int x1 = F.sorted[j + 1];
       if (x1 >= n) x1 = n - 1;
       int s[F1_ACC];
 #pragma unroll
       for (int k = 0; k < F1_ACC; k++) s[k] = 0;
-      for (int x = x0 + l; x <= x1; x += w) {
+      for (int x = x0 + lane; x <= x1; x += 32) {
         const int v = q[x], val = v & 0x7fff;
         if (val) {
           if (v & 0x8000) { s[0] += x; s[1] += val; s[2] += x * x; s[3] += val * val; s[4] += x * val; s[5]++; }
@@ -245,21 +239,15 @@ k_floor1_fit(Floor1Args a, const float *__restrict__ logmdct, const float *__res
         }
       }
 #pragma unroll
-      for (int k = 0; k < F1_ACC; k++) s[k] = __reduce_add_sync(gmask, s[k]);
-      {                                                  // raw sums; turned into fit_line's terms below
-        int v = s[0], v2 = s[8];
+      for (int k = 0; k < F1_ACC; k++) s[k] = __reduce_add_sync(0xffffffffu, s[k]);
+      if (lane < F1_ACC) {                               // raw sums; turned into fit_line's terms below
+        int v = s[0];
 #pragma unroll
-        for (int k = 1; k < F1_ACC; k++) if (l == k) v = s[k];
-#pragma unroll
-        for (int k = 9; k < F1_ACC; k++) if (l + 8 == k) v2 = s[k];
-        if (sub < cnt) {
-          if (l < F1_ACC && l < w) reinterpret_cast<int *>(term)[j * F1_ACC + l] = v;
-          if (w == 8 && l < F1_ACC - 8) reinterpret_cast<int *>(term)[j * F1_ACC + 8 + l] = v2;
-          nonzero |= s[5];
-        }
+        for (int k = 1; k < F1_ACC; k++) if (lane == k) v = s[k];
+        reinterpret_cast<int *>(term)[j * F1_ACC + lane] = v;
       }
+      nonzero += s[5];
     }
-    nonzero = __any_sync(0xffffffffu, nonzero != 0);
     __syncwarp();
     // what fit_line adds for a gap, chain f: (double)Xb + (double)Xa * weight (lib/floor1.c:465-474).  One
     // lane per gap turns its 12 ints into the 6 doubles in place (same 48 bytes, private to the lane).
