@@ -696,7 +696,7 @@ def run_ours(args):
            "verified_blocks_vs_oracle": verified_e2e,
            "call": "vb200_encode_dsp: %d streams x %d blocks per GPU, int16 interleaved stream PCM in (hop N/2, "
                    "blocks cut on the device), posts+nonzero+quantised residue (int16, overflow-counted) out; pinned host memory; "
-                   "three-lane chunk pipeline; wall clock, max over ranks" % (ns_e, bps)}
+                   "chunks of 8192 blocks (ramped at both ends) over four buffer sets, one copy stream per direction + two compute streams; wall clock, max over ranks" % (ns_e, bps)}
 
     # ---- BASELINE configs[4]: a fixed job of independent streams with real block switching, split over the ranks
     streams_res = None

@@ -361,7 +361,8 @@ typedef struct vb200_encode_io {
 int vb200_encode_dsp_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream, int blobno,
                          const vb200_encode_io *d_io, void *stream);
 /* host buffers (pinned memory makes the copies asynchronous); whole streams are cut into chunks
- * that rotate over three lanes so H2D, the kernels and D2H of different chunks overlap         */
+ * that rotate over four device buffer sets: all H2D copies on one stream, all D2H copies on
+ * another, the kernels of consecutive chunks on two compute streams, ordered by events         */
 int vb200_encode_dsp    (vb200_ctx*, int W, int nstreams, int blocks_per_stream, int blobno,
                          const vb200_encode_io *io);
 

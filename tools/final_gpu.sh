@@ -10,5 +10,4 @@ VB200_SPLIT=1 ncu --metrics gpu__time_duration.sum --clock-control none -s 18 -c
 VB200_SPLIT=1 ncu --set full --clock-control none --import-source on -k regex:"k_phaseA_transform|k_phaseA_psy3|k_floor1_fit|k_floor1_render|k_cqn_fast" -s 15 -c 5 -o gpurun_out/r2_chain python bench.py --steps 1 --warmup 3 --blocks 24000 --no-extra --streams 0 > gpurun_out/r2_chain_ncu.log 2>&1
 python tools/phase_timing.py > gpurun_out/r2_phase_timing.txt 2>&1
 python tools/pcie_bw.py > gpurun_out/r2_pcie_bw.json 2>&1
-# end-to-end with and without the ramped chunk schedule
-for r in 1 0; do VB200_CHUNK_RAMP=$r python bench.py --no-extra --streams 0 --steps 5 --warmup 3 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ramp=$r e2e', d['e2e']['value'], 'value', d['value'])"; done > gpurun_out/r2_ramp.txt 2>&1
+
