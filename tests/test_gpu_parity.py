@@ -575,6 +575,32 @@ def test_encode_dsp_streams_vs_oracle(cfg, W, fmt, monkeypatch):
     assert not got["nonzero"][2 * bps:3 * bps].any(), "silent stream must come back all-zero"
 
 
+@pytest.mark.parametrize("ramp", ["1", "0"])
+def test_encode_dsp_many_chunks(cfg, ramp, monkeypatch):
+    """the host-buffer pipeline of vb200_encode_dsp with more chunks than buffer sets (the event chain
+    H2D(k) -> kernels(k) -> D2H(k) -> H2D(k+4) is exercised) and the ramped chunk schedule on and off"""
+    name, setup, ctx, o, _, _ = cfg
+    monkeypatch.setenv("VB200_CHUNK_BLOCKS", "12")
+    monkeypatch.setenv("VB200_CHUNK_RAMP", ramp)
+    W = 1
+    N, ch = setup.blocksize(W), setup.channels
+    hop, ns, bps = N // 2, 30, 3
+    stride = (bps - 1) * hop + N
+    rng = np.random.default_rng(4242)
+    s16 = np.clip(6000 * rng.standard_normal((ns, stride, ch)) * rng.uniform(0.05, 1.2, (ns, 1, 1)), -32768, 32767).astype(np.int16)
+    planar = np.ascontiguousarray((s16.astype(np.float32) / np.float32(32768.0)).transpose(0, 2, 1))
+    blocks = np.stack([planar[s, :, k * hop:k * hop + N] for s in range(ns) for k in range(bps)])
+    desc = np.zeros(ns * bps, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = W; desc["nW"] = W
+    desc["blocktype"] = rng.integers(0, 2, ns * bps)
+    amp0 = rng.uniform(-40, -3, ns).astype(np.float32)
+    want = o.encode_dsp(W, blocks, desc, streams=(ns, bps), ampmax0=amp0)
+    for rep in range(2):                                             # the second call reuses the buffer sets
+        got = ctx.encode_dsp(W, s16, desc, nstreams=ns, fmt=vlib.PCM_S16_INTERLEAVED, hop=hop, ampmax0=amp0,
+                             independent=False)
+        _enc_compare(got, want, "many chunks ramp=%s rep=%d" % (ramp, rep))
+
+
 def test_encode_dsp_device_pointers_and_errors(cfg):
     import torch
     name, setup, ctx, o, enc, _ = cfg
