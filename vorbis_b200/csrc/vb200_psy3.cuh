@@ -296,13 +296,6 @@ __device__ __forceinline__ void dev_noise_scan3(int n, float *arr) {
 #undef SCAN4
 }
 
-// The per-bin terms of the five running sums as a real function (two bins per call): inlined 8x per pass they were
-// 400 once-through instructions per row and warp; instruction fetch is 13 % of this kernel's stall samples.
-__device__ __noinline__ void noise_terms_pair(int i0, int i1, float f0, float f1, float offset, float *S, int ns) {
-  dev_noise_term1(i0, f0, offset, S, ns);
-  dev_noise_term1(i1, f1, offset, S, ns);
-}
-
 // Two bins per call: halves the call overhead of the (deliberately not inlined, see vb200_psy2.cuh) per-bin
 // regression and gives the scheduler two independent dependency chains.
 template <int NS>
@@ -466,12 +459,8 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     __syncthreads();                                   // tone scratch is dead from here on
     PHASE_MARK();   // 4 group minima
     // ---- noise mask, pass 1 (offset 140, bark windows)
-    if (K >= 2) {
 #pragma unroll
-      for (int k = 0; k + 1 < K; k += 2) noise_terms_pair(tid + k * nt, tid + (k + 1) * nt, L[k], L[k + 1], 140.f, S, ns);
-    } else {
-      dev_noise_term1(tid, L[0], 140.f, S, ns);
-    }
+    for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k], 140.f, S, ns);
     __syncthreads();
     PHASE_MARK();   // 5 terms 1
     if (threadIdx.x < 5 * R) dev_noise_scan3(n, sm_cta + (threadIdx.x / 5) * row_floats + (threadIdx.x % 5) * ns);
@@ -490,13 +479,8 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     __syncthreads();
     PHASE_MARK();   // 7 regress 1
     // ---- pass 2 on logmdct - p1 (offset 0, bark + fixed windows)
-    if (K >= 2) {
 #pragma unroll
-      for (int k = 0; k + 1 < K; k += 2)
-        noise_terms_pair(tid + k * nt, tid + (k + 1) * nt, L[k] - p1[k], L[k + 1] - p1[k + 1], 0.f, S, ns);
-    } else {
-      dev_noise_term1(tid, L[0] - p1[0], 0.f, S, ns);
-    }
+    for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k] - p1[k], 0.f, S, ns);
     __syncthreads();
     PHASE_MARK();   // 8 terms 2
     if (threadIdx.x < 5 * R) dev_noise_scan3(n, sm_cta + (threadIdx.x / 5) * row_floats + (threadIdx.x % 5) * ns);
