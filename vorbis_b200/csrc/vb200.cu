@@ -1255,11 +1255,13 @@ static int phaseA_psy_launch(vb200_ctx *c, int W, int nblocks, const vb200_phase
       if (ctas > PSY3_MINB / R) ctas = PSY3_MINB / R;
       if (ctas < 1) ctas = 1;
       { const char *e = getenv("VB200_PSY_CTAS"); if (e) ctas = atoi(e); }
-#define LAUNCH_PSY3R(KK, RR)                                                                       \
+      const bool dbg3 = A.dbg_cycles || A.tap_noise || A.tap_tone;   // clock marks / taps: the debug instance
+#define LAUNCH_PSY3D(KK, RR, DD)                                                                   \
       do {                                                                                         \
-        if ((rc = set_smem(k_phaseA_psy3<KK, RR>, smem3))) return rc;                              \
-        k_phaseA_psy3<KK, RR><<<grid_for(c, (rows + RR - 1) / RR, ctas), PSY3_THREADS * RR, smem3, st>>>(P0, P1, ch, rows, A); \
+        if ((rc = set_smem(k_phaseA_psy3<KK, RR, DD>, smem3))) return rc;                          \
+        k_phaseA_psy3<KK, RR, DD><<<grid_for(c, (rows + RR - 1) / RR, ctas), PSY3_THREADS * RR, smem3, st>>>(P0, P1, ch, rows, A); \
       } while (0)
+#define LAUNCH_PSY3R(KK, RR) do { if (dbg3) LAUNCH_PSY3D(KK, RR, true); else LAUNCH_PSY3D(KK, RR, false); } while (0)
 #define LAUNCH_PSY4(KK)                                                                            \
       do {                                                                                         \
         if ((rc = set_smem(k_phaseA_psy4<KK>, row_bytes))) return rc;                              \
@@ -1276,6 +1278,7 @@ static int phaseA_psy_launch(vb200_ctx *c, int W, int nblocks, const vb200_phase
         default: LAUNCH_PSY3(16); break;
       }
 #undef LAUNCH_PSY3R
+#undef LAUNCH_PSY3D
 #undef LAUNCH_PSY4
 #undef LAUNCH_PSY3
     } else if (v2ok) {

@@ -676,14 +676,15 @@ struct Abd { float A, B, D; };
 
 __device__ __forceinline__ Abd dev_window_abd(int lo, int hi, const float *S, int ns) {
   const float *N = S, *X = S + ns, *XX = S + 2 * ns, *Y = S + 3 * ns, *XY = S + 4 * ns;
-  float tN, tX, tXX, tY, tXY;
-  if (lo < 0) {
-    tN = N[hi] + N[-lo];   tX = X[hi] - X[-lo];   tXX = XX[hi] + XX[-lo];
-    tY = Y[hi] + Y[-lo];   tXY = XY[hi] - XY[-lo];
-  } else {
-    tN = N[hi] - N[lo];    tX = X[hi] - X[lo];    tXX = XX[hi] - XX[lo];
-    tY = Y[hi] - Y[lo];    tXY = XY[hi] - XY[lo];
-  }
+  // lo < 0 mirrors the window at 0 (lib/psy.c:608-624): N, XX, Y are ADDED there, X and XY subtracted as always.
+  // x + y == x - (-y) exactly, so the mirrored case only flips the sign bit of three operands: one code path.
+  const int a = lo < 0 ? -lo : lo;
+  const unsigned flip = lo < 0 ? 0x80000000u : 0u;
+  const float nN = __uint_as_float(__float_as_uint(N[a]) ^ flip);
+  const float nXX = __uint_as_float(__float_as_uint(XX[a]) ^ flip);
+  const float nY = __uint_as_float(__float_as_uint(Y[a]) ^ flip);
+  const float tN = N[hi] - nN, tX = X[hi] - X[a], tXX = XX[hi] - nXX;
+  const float tY = Y[hi] - nY, tXY = XY[hi] - XY[a];
   Abd r;
   r.A = tY * tXX - tX * tXY;
   r.B = tN * tXY - tX * tY;

@@ -28,6 +28,12 @@ namespace vb200 {
 constexpr int PSY3_THREADS = 128;
 constexpr int PSY3_L = 8;            // eighth_octave_lines
 constexpr int PSY3_RB = 7;           // chase positions per thread = linesper - 1
+#ifndef PSY3_ROLLED_PAIR
+#define PSY3_ROLLED_PAIR 0
+#endif
+#ifndef PSY3_SINGLE_REGRESS
+#define PSY3_SINGLE_REGRESS 0
+#endif
 #ifndef PSY3_MINB
 #define PSY3_MINB 8
 #endif
@@ -55,10 +61,12 @@ __device__ __forceinline__ void dev_tone_runs3(const PsyDev &P, const float *log
                                                int4 *run_rec, int tid) {
   const float dBoffset = P.max_curve_dB - gmax;
   const int total = P.total;
+#pragma unroll 1
   for (int k = tid; k < P.nruns; k += PSY3_THREADS) {
     const int4 rr = __ldg(P.runrec + k);             // lo|hi<<16, oc - firstoc, band, bits(ath[hi])
     const int lo = rr.x & 0xffff, hi = rr.x >> 16;
     float mx = logfft[lo];
+#pragma unroll 1
     for (int i = lo + 1; i <= hi; i++) { const float v = logfft[i]; if (v > mx) mx = v; }
     int4 rec = make_int4(__float_as_int(mx), 0, 0, 0);
     if (mx + 6.f > __int_as_float(rr.w) + att) {     // lib/psy.c:438
@@ -89,6 +97,7 @@ __device__ __forceinline__ void dev_tone_scatter3(const PsyDev &P, float *copies
   float *my = copies + w * tp;
   {
     const float4 ninf = make_float4(VB_NEGINF, VB_NEGINF, VB_NEGINF, VB_NEGINF);
+#pragma unroll 1
     for (int v = lane; v < (tp >> 2); v += 32) reinterpret_cast<float4 *>(my)[v] = ninf;
   }
   __syncwarp();
@@ -96,6 +105,7 @@ __device__ __forceinline__ void dev_tone_scatter3(const PsyDev &P, float *copies
   const int trips = (P.max_cls_len - w + 3) >> 2;    // warp-uniform
   const unsigned a_my = smem_u32(my), a_rec = smem_u32(run_rec);
   const float *__restrict__ curves = P.tonecurves;
+#pragma unroll 1
   for (int it = 0; it < trips; it++) {
     const int k = k0 + w + 4 * it;                   // this warp's it-th run of class c
     if (k < k1) {
@@ -105,6 +115,7 @@ __device__ __forceinline__ void dev_tone_scatter3(const PsyDev &P, float *copies
       int j = (q - (r.z >> 3)) & 3;                  // first point that lands on a slot this lane owns
       const float *cp = curves + r.y + j;
       unsigned a = a_my + 4u * (unsigned)(r.z + PSY3_L * j);
+#pragma unroll 1
       while (j < cnt) {
         const bool p1 = j + 4 < cnt, p2 = j + 8 < cnt, p3 = j + 12 < cnt;
         const float v0 = __ldg(cp);
@@ -122,11 +133,12 @@ __device__ __forceinline__ void dev_tone_scatter3(const PsyDev &P, float *copies
 }
 
 // ---- merge of the four copies + seed_chase, block wide.  On return copies[0..total) holds the chased seeds.
+template <bool DBG>
 __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int tp, int *s_misc, int tid,
                                            unsigned long long *dbg = nullptr) {
   constexpr int RB = PSY3_RB, L = PSY3_L;
-  long long tc = dbg ? clock64() : 0;
-#define CHASE_MARK(slot) do { if (dbg && tid == 0) { const long long tn_ = clock64(); atomicAdd(dbg + (slot), (unsigned long long)(tn_ - tc)); tc = tn_; } } while (0)
+  long long tc = (DBG && dbg) ? clock64() : 0;
+#define CHASE_MARK(slot) do { if (DBG && dbg && tid == 0) { const long long tn_ = clock64(); atomicAdd(dbg + (slot), (unsigned long long)(tn_ - tc)); tc = tn_; } } while (0)
   const int total = P.total;
   const int lane = tid & 31, warp = tid >> 5;
   const unsigned full = 0xffffffffu;
@@ -234,6 +246,7 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
   // 4. fill (lib/psy.c:489-503): entry k is written from the running cursor to endpos_k; the cursor is the
   // running maximum of the earlier endpos values = exclusive prefix maximum over the threads
   int Mx = 0;
+#pragma unroll 1
   for (int d = 0; d < cnt; d++) {
     const float a = astk[start + d];
     float an; int pn;
@@ -256,9 +269,11 @@ __device__ __forceinline__ void dev_chase3(const PsyDev &P, float *copies, int t
   if (lane == 0) cursor = 0;
   __syncthreads();
   for (int w2 = 0; w2 < warp; w2++) { const int t = s_misc[4 + w2]; if (t > cursor) cursor = t; }
+#pragma unroll 1
   for (int d = 0; d < cnt; d++) {
     const float a = astk[start + d];
     const int endpos = lstk[start + d];
+#pragma unroll 1
     for (int p = cursor; p < endpos; p++) seed[p] = a;
     if (endpos > cursor) cursor = endpos;
   }
@@ -302,8 +317,17 @@ template <int NS>
 __device__ __noinline__ float2 regress_pair(const int *__restrict__ bark, int bfe, int ffe, const float *S,
                                             int i0, int i1, float offset, int fixed) {
   float2 r;
+#if PSY3_ROLLED_PAIR
+  r.x = r.y = 0.f;
+#pragma unroll 1
+  for (int b = 0; b < 2; b++) {                        // one copy of the window code, two trips
+    const float v = dev_regress_bin<NS>(bark, bfe, ffe, S, b ? i1 : i0, offset, fixed);
+    if (b) r.y = v; else r.x = v;
+  }
+#else
   r.x = dev_regress_bin<NS>(bark, bfe, ffe, S, i0, offset, fixed);
   r.y = dev_regress_bin<NS>(bark, bfe, ffe, S, i1, offset, fixed);
+#endif
   return r;
 }
 
@@ -341,7 +365,9 @@ __device__ __noinline__ MixOut final_mix_val(float p2, float L, float p1, float 
 // K = n / 128 bins per thread; R = rows per CTA (128 threads each).  The R rows of a CTA run in lockstep and
 // share ONE scan warp: its lanes 5r..5r+4 carry the five running sums of row r, so the 1024 dependent
 // warp-level FADDs per scan are paid once per R rows.
-template <int K, int R>
+// DBG = true: the instance with the per-phase clock marks (tools/phase_timing.py) and the noise / tone taps of the
+// stage-level API; the production instance carries neither (code size: instruction fetch is a first-order cost here)
+template <int K, int R, bool DBG>
 __global__ void __launch_bounds__(PSY3_THREADS * R, PSY3_MINB / R)
 k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
   extern __shared__ __align__(16) float sm_cta[];
@@ -372,11 +398,11 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     const float g = A.gmax[blk], lmax = A.lmax[row];
     const float att = tone_att(P, lmax);
     float L[K], M[K], p1[K];
-    long long tmark = A.dbg_cycles ? clock64() : 0;
+    long long tmark = (DBG && A.dbg_cycles) ? clock64() : 0;
     int tph = 0;
 #define PHASE_MARK()                                                              \
     do {                                                                          \
-      if (A.dbg_cycles && threadIdx.x == 0) {                                     \
+      if (DBG && A.dbg_cycles && threadIdx.x == 0) {                                     \
         const long long tnow = clock64();                                         \
         atomicAdd(A.dbg_cycles + tph, (unsigned long long)(tnow - tmark));        \
         tmark = tnow;                                                             \
@@ -411,10 +437,11 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     dev_tone_scatter3(P, copies, tp, run_rec, tid);
     __syncthreads();
     PHASE_MARK();   // 2 scatter
-    dev_chase3(P, copies, tp, s_misc, tid, half == 0 ? A.dbg_cycles : nullptr);
+    dev_chase3<DBG>(P, copies, tp, s_misc, tid, half == 0 ? A.dbg_cycles : nullptr);
     PHASE_MARK();   // 3 chase
     // max_seeds gather, first half: one minimum per static group (lib/psy.c:522-533)
     const float *seed = copies;
+#pragma unroll 1
     for (int q = tid; q <= P.ngrp; q += nt) {
       float minV;
       if (q < P.ngrp) {
@@ -423,6 +450,7 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
         int pos = gg.x;
         minV = seed[pos];
         if (minV > P.tone_abs_limit) minV = P.tone_abs_limit;
+#pragma unroll 1
         while (pos < gg.y) {
           pos++;
           const float s = seed[pos];
@@ -436,11 +464,13 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     // long groups (the first few bins span tens of seed slots): the fold equals the minimum over
     // the non-NEGINF seeds of the range, joined by tone_abs_limit iff the first seed is not
     // NEGINF, and NEGINF if there is none - associative, so a warp reduces it with shuffles
+#pragma unroll 1
     for (int li = tid >> 5; li < P.nlong; li += nt >> 5) {
       const int q = __ldg(P.long_grp + li);
       const int4 gg = __ldg(P.grps + q);
       float mn = 3.0e38f;
       int any = 0;
+#pragma unroll 1
       for (int pos = gg.x + lane; pos <= gg.y; pos += 32) {
         const float s = seed[pos];
         if (s > VB_NEGINF) {
@@ -458,51 +488,49 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     }
     __syncthreads();                                   // tone scratch is dead from here on
     PHASE_MARK();   // 4 group minima
-    // ---- noise mask, pass 1 (offset 140, bark windows)
+    // ---- noise mask: two passes of the same three steps (terms, sequential sums, windowed regressions), ONE copy
+    // of the code (instruction fetch is a first-order cost in this kernel): pass 0 on logmdct with offset 140 and
+    // the bark windows only -> p1, pass 1 on logmdct - p1 with offset 0 and bark + fixed windows -> p2
+    // (lib/psy.c:706-726; logmdct - 0.f is logmdct exactly)
+    const int *bark = P.bark;
+    const int bfe = P.bark_first_extra, ffe = P.fixed_first_extra, fixedw = P.noisewindowfixed;
+    float p2[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k], 140.f, S, ns);
-    __syncthreads();
-    PHASE_MARK();   // 5 terms 1
-    if (threadIdx.x < 5 * R) dev_noise_scan3(n, sm_cta + (threadIdx.x / 5) * row_floats + (threadIdx.x % 5) * ns);
-    __syncthreads();
-    PHASE_MARK();   // 6 scan 1
-    if (K >= 2) {
+    for (int k = 0; k < K; k++) p1[k] = 0.f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+      const float off = pass ? 0.f : 140.f;
+      const int fx = pass ? fixedw : -1;
 #pragma unroll
-      for (int k = 0; k + 1 < K; k += 2) {
-        const float2 r = regress_pair<K * PSY3_THREADS + 4>(P.bark, P.bark_first_extra, P.fixed_first_extra, S,
-                                                            tid + k * nt, tid + (k + 1) * nt, 140.f, -1);
-        p1[k] = r.x; p1[k + 1] = r.y;
+      for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k] - p1[k], off, S, ns);
+      __syncthreads();
+      PHASE_MARK();   // 5 / 8 terms
+      if (threadIdx.x < 5 * R) dev_noise_scan3(n, sm_cta + (threadIdx.x / 5) * row_floats + (threadIdx.x % 5) * ns);
+      __syncthreads();
+      PHASE_MARK();   // 6 / 9 scan
+      if (K >= 2 && !PSY3_SINGLE_REGRESS) {
+#pragma unroll
+        for (int k = 0; k + 1 < K; k += 2) {
+          const float2 r = regress_pair<K * PSY3_THREADS + 4>(bark, bfe, ffe, S, tid + k * nt, tid + (k + 1) * nt, off, fx);
+          p2[k] = r.x; p2[k + 1] = r.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) p2[k] = regress_core<K * PSY3_THREADS + 4>(bark, bfe, ffe, S, tid + k * nt, off, fx);
       }
-    } else {
-      p1[0] = regress_core<K * PSY3_THREADS + 4>(P.bark, P.bark_first_extra, P.fixed_first_extra, S, tid, 140.f, -1);
-    }
-    __syncthreads();
-    PHASE_MARK();   // 7 regress 1
-    // ---- pass 2 on logmdct - p1 (offset 0, bark + fixed windows)
+      if (pass == 0) {
 #pragma unroll
-    for (int k = 0; k < K; k++) dev_noise_term1(tid + k * nt, L[k] - p1[k], 0.f, S, ns);
-    __syncthreads();
-    PHASE_MARK();   // 8 terms 2
-    if (threadIdx.x < 5 * R) dev_noise_scan3(n, sm_cta + (threadIdx.x / 5) * row_floats + (threadIdx.x % 5) * ns);
-    __syncthreads();
-    PHASE_MARK();   // 9 scan 2
+        for (int k = 0; k < K; k++) p1[k] = p2[k];
+        __syncthreads();                                 // the sums are overwritten by the second pass' terms
+        PHASE_MARK();   // 7 regress 1
+      }
+    }
     MixConst MC;
     MC.noisemaxsupp = P.noisemaxsupp; MC.toneatt = P.tone_masteratt[1]; MC.m_val = P.m_val;
     MC.att = att;
     const float *noff = P.noiseoffset + n;             // offset_select 1
-    const int *bark = P.bark; const float *athp = P.ath, *compand = P.noisecompand;
+    const float *athp = P.ath, *compand = P.noisecompand;
     const short *bin_grp = P.bin_grp;
-    const int bfe = P.bark_first_extra, ffe = P.fixed_first_extra, fixedw = P.noisewindowfixed;
-    float p2[K];
-    if (K >= 2) {
-#pragma unroll
-      for (int k = 0; k + 1 < K; k += 2) {
-        const float2 r = regress_pair<K * PSY3_THREADS + 4>(bark, bfe, ffe, S, tid + k * nt, tid + (k + 1) * nt, 0.f, fixedw);
-        p2[k] = r.x; p2[k + 1] = r.y;
-      }
-    } else {
-      p2[0] = regress_core<K * PSY3_THREADS + 4>(bark, bfe, ffe, S, tid, 0.f, fixedw);
-    }
 #pragma unroll
     for (int k = 0; k < K; k++) {
       const int i = tid + k * nt;
@@ -510,8 +538,8 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
                                      grp_min[__ldg(bin_grp + i)], compand, MC, M[k]);
       __stcs(A.logmask + (size_t)row * n + i, o.logmask);
       __stcs(A.mdct_out + (size_t)row * n + i, o.m);
-      if (A.tap_noise) A.tap_noise[(size_t)row * n + i] = o.nz;
-      if (A.tap_tone) A.tap_tone[(size_t)row * n + i] = o.tn;
+      if (DBG && A.tap_noise) A.tap_noise[(size_t)row * n + i] = o.nz;
+      if (DBG && A.tap_tone) A.tap_tone[(size_t)row * n + i] = o.tn;
     }
     if (tid == 0 && (row % ch) == 0) A.ampmax_out[blk] = g;   // lib/mapping0.c:576
     __syncthreads();
@@ -665,7 +693,7 @@ k_phaseA_psy4(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
     dev_tone_scatter3(P, copies, tp, run_rec, tid);
     __syncthreads();
     PHASE_MARK();   // 2 scatter
-    dev_chase3(P, copies, tp, s_misc, tid, A.dbg_cycles);
+    dev_chase3<true>(P, copies, tp, s_misc, tid, A.dbg_cycles);
     PHASE_MARK();   // 3 chase
     const float *seed = copies;
     for (int q = tid; q <= P.ngrp; q += nt) {           // max_seeds gather, one minimum per static group (lib/psy.c:522-533)
