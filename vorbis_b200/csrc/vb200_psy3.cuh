@@ -28,12 +28,6 @@ namespace vb200 {
 constexpr int PSY3_THREADS = 128;
 constexpr int PSY3_L = 8;            // eighth_octave_lines
 constexpr int PSY3_RB = 7;           // chase positions per thread = linesper - 1
-#ifndef PSY3_ROLLED_PAIR
-#define PSY3_ROLLED_PAIR 0
-#endif
-#ifndef PSY3_SINGLE_REGRESS
-#define PSY3_SINGLE_REGRESS 0
-#endif
 #ifndef PSY3_MINB
 #define PSY3_MINB 8
 #endif
@@ -317,17 +311,8 @@ template <int NS>
 __device__ __noinline__ float2 regress_pair(const int *__restrict__ bark, int bfe, int ffe, const float *S,
                                             int i0, int i1, float offset, int fixed) {
   float2 r;
-#if PSY3_ROLLED_PAIR
-  r.x = r.y = 0.f;
-#pragma unroll 1
-  for (int b = 0; b < 2; b++) {                        // one copy of the window code, two trips
-    const float v = dev_regress_bin<NS>(bark, bfe, ffe, S, b ? i1 : i0, offset, fixed);
-    if (b) r.y = v; else r.x = v;
-  }
-#else
   r.x = dev_regress_bin<NS>(bark, bfe, ffe, S, i0, offset, fixed);
   r.y = dev_regress_bin<NS>(bark, bfe, ffe, S, i1, offset, fixed);
-#endif
   return r;
 }
 
@@ -508,7 +493,7 @@ k_phaseA_psy3(PsyDev P0, PsyDev P1, int ch, int nrows, PhaseA2Args A) {
       if (threadIdx.x < 5 * R) dev_noise_scan3(n, sm_cta + (threadIdx.x / 5) * row_floats + (threadIdx.x % 5) * ns);
       __syncthreads();
       PHASE_MARK();   // 6 / 9 scan
-      if (K >= 2 && !PSY3_SINGLE_REGRESS) {
+      if (K >= 2) {
 #pragma unroll
         for (int k = 0; k + 1 < K; k += 2) {
           const float2 r = regress_pair<K * PSY3_THREADS + 4>(bark, bfe, ffe, S, tid + k * nt, tid + (k + 1) * nt, off, fx);
