@@ -1,7 +1,8 @@
 #!/bin/bash
 # A/B of library variants built under vorbis_b200/_variants (experiments only)
 cp vorbis_b200/libvorbis_b200.so /tmp/cur.so
-for v in cur fitnl cur fitnl; do
+python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+for v in cur prev cur prev; do
   if [ $v = cur ]; then cp /tmp/cur.so vorbis_b200/libvorbis_b200.so; else cp vorbis_b200/_variants/$v.so vorbis_b200/libvorbis_b200.so; fi
   python bench.py --no-extra --streams 0 2>/dev/null | tail -1 | python -c "
 import sys,json
