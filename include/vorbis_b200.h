@@ -366,6 +366,25 @@ int vb200_encode_dsp_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream,
 int vb200_encode_dsp    (vb200_ctx*, int W, int nstreams, int blocks_per_stream, int blobno,
                          const vb200_encode_io *io);
 
+/* ---- bitrate-managed mode ------------------------------------------------------
+ * What mapping0_forward does when vorbis_bitrate_managed(vb) (lib/mapping0.c:507-573, 596-646):
+ * Phase A as above, then besides the middle mask (offset_select 1) the low-noise and the
+ * high-noise masks (_vp_offset_and_mix selections 2 and 0, lib/psy.c:779-835), a floor1_fit on
+ * each (only where the middle fit exists), the twelve floor1_interpolate_fit curves in between
+ * (lib/floor1.c:731-757; a curve exists only where both of its ends do), and for EVERY one of the
+ * VB200_PACKETBLOBS curves k: the floor render (floor1_encode minus the bits, :765-945) and
+ * _vp_couple_quantize_normalize with blob k's coupling parameters and sliding low-pass.
+ * Same vb200_encode_io as vb200_encode_dsp with blob-major outputs:
+ *   posts   [VB200_PACKETBLOBS][nblocks*ch][VB200_FLOOR1_STRIDE]   (all zero where the curve is NULL)
+ *   nonzero [VB200_PACKETBLOBS][nblocks*ch]
+ *   iwork   [VB200_PACKETBLOBS][nblocks*ch][n]                     (iwork_fmt must be VB200_IWORK_S32)
+ * classes / overflow must be NULL.  The host keeps what it keeps in un-managed mode: the bits of
+ * floor1_encode, residue coding, and the bitrate manager's choice among the 15 packets.          */
+int vb200_encode_dsp_managed_dev(vb200_ctx*, int W, int nstreams, int blocks_per_stream,
+                                 const vb200_encode_io *d_io, void *stream);
+int vb200_encode_dsp_managed    (vb200_ctx*, int W, int nstreams, int blocks_per_stream,
+                                 const vb200_encode_io *io);
+
 /* ---- envelope / block-switch detector -----------------------------------------
  * The analysis loop of _ve_envelope_search (lib/envelope.c:232-267): for steps j = first_step ..
  * first_step+nsteps-1 of every stream and every channel, _ve_amp (:88-213) on the 128 samples that

@@ -222,6 +222,66 @@ class Oracle:
         a.update(posts=posts.reshape(nb, ch, -1), iwork=iwork, nonzero=nonzero)
         return a
 
+    def floor1_interpolate_fit(self, A, B, del_):
+        """floor1_interpolate_fit (lib/floor1.c:731-757) on rows of posts (padding entries are 0 and stay 0)"""
+        A = np.asarray(A, np.int64); B = np.asarray(B, np.int64)
+        out = ((65536 - del_) * (A & 0x7fff) + del_ * (B & 0x7fff) + 32768) >> 16
+        out |= np.where(((A & 0x8000) != 0) & ((B & 0x8000) != 0), 0x8000, 0)
+        return out.astype(np.int32)
+
+    def encode_dsp_managed(self, W, pcm, desc, streams=None, ampmax0=None):
+        """Bitrate-managed mapping0_forward (lib/mapping0.c:507-573, 596-646) composed from the stage oracles:
+        Phase A (mask select 1) -> middle fit; where it exists: masks 2 / 0 -> high / low fits; twelve interpolated
+        curves (NULL where an end is NULL); then per curve k the floor render and couple/quantise/normalise with
+        blob k's parameters.  Returns blob-major posts / nonzero / iwork like vb200_encode_dsp_managed."""
+        ch, n = self.channels, self.bs[W] // 2
+        NB, MID, S = abi.PACKETBLOBS, abi.PACKETBLOBS // 2, abi.FLOOR1_STRIDE
+        desc = np.ascontiguousarray(desc, abi.BLOCKDESC_DTYPE)
+        a = self.phaseA(W, pcm, desc, taps=True, streams=streams, ampmax0=ampmax0)
+        nb = desc.shape[0]
+        rows = nb * ch
+        logmask = {1: a["logmask"]}
+        for sel in (2, 0):
+            lm = np.empty((nb, ch, n), np.float32)
+            for bt in (0, 1):
+                idx = np.where(desc["blocktype"] == bt)[0]
+                if len(idx):
+                    m, _ = self.offset_and_mix(bt + (2 if W else 0), sel, a["noise"][idx], a["tone"][idx],
+                                               a["mdct"][idx], a["logmdct"][idx])
+                    lm[idx] = m.reshape(len(idx), ch, n)
+            logmask[sel] = lm
+        posts = np.zeros((NB, rows, S), np.int32)
+        present = np.zeros((NB, rows), np.int32)
+        pm, fm = self.floor1_fit(W, a["logmdct"], logmask[1])
+        ph, fh = self.floor1_fit(W, a["logmdct"], logmask[2])
+        pl, fl = self.floor1_fit(W, a["logmdct"], logmask[0])
+        mid = fm != 0
+        lo = mid & (fl != 0)
+        hi = mid & (fh != 0)
+        posts[MID][mid] = pm[mid]; present[MID] = mid
+        posts[0][lo] = pl[lo]; present[0] = lo
+        posts[NB - 1][hi] = ph[hi]; present[NB - 1] = hi
+        for k in range(1, MID):
+            posts[k][lo] = self.floor1_interpolate_fit(posts[0][lo], posts[MID][lo], k * 65536 // MID)
+            present[k] = lo
+        for k in range(MID + 1, NB - 1):
+            posts[k][hi] = self.floor1_interpolate_fit(posts[MID][hi], posts[NB - 1][hi], (k - MID) * 65536 // MID)
+            present[k] = hi
+        iwork = np.zeros((NB, nb, ch, n), np.int32)
+        nonzero = np.zeros((NB, nb, ch), np.int32)
+        out_posts = np.zeros((NB, nb, ch, S), np.int32)
+        for k in range(NB):
+            pk, ilog, nz = self.floor1_render(W, posts[k], present[k])
+            iw = ilog.reshape(nb, ch, n).copy()
+            z = nz.reshape(nb, ch).copy()
+            for bt in (0, 1):
+                idx = np.where(desc["blocktype"] == bt)[0]
+                if len(idx):
+                    iw2, z2 = self.couple_quantize_normalize(W, bt, k, a["mdct"][idx], iw[idx], z[idx])
+                    iw[idx], z[idx] = iw2, z2
+            iwork[k], nonzero[k], out_posts[k] = iw, z, pk.reshape(nb, ch, S)
+        return {"posts": out_posts, "nonzero": nonzero, "iwork": iwork, "ampmax_out": a["ampmax_out"]}
+
     def residue_partvals(self, W):
         return int(self.L.vbo_residue_partvals(self.h, W))
 

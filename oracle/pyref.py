@@ -66,6 +66,8 @@ def dropin_lib():
 def _declare(L):
     L.ref_open.restype = C.c_void_p
     L.ref_open.argtypes = [C.c_int, C.c_long, C.c_float]
+    L.ref_open_managed.restype = C.c_void_p
+    L.ref_open_managed.argtypes = [C.c_int, C.c_long, C.c_long]
     L.ref_close.argtypes = [C.c_void_p]
     L.ref_vd.restype = C.c_void_p
     L.ref_vd.argtypes = [C.c_void_p]
@@ -83,6 +85,8 @@ def lib():
         _declare(L)
         L.ref_open.restype = C.c_void_p
         L.ref_open.argtypes = [C.c_int, C.c_long, C.c_float]
+        L.ref_open_managed.restype = C.c_void_p
+        L.ref_open_managed.argtypes = [C.c_int, C.c_long, C.c_long]
         L.ref_close.argtypes = [C.c_void_p]
         L.ref_blocksize.argtypes = [C.c_void_p, C.c_int]
         L.ref_get_setup.argtypes = [C.c_void_p, C.POINTER(abi.Setup)]
@@ -111,6 +115,7 @@ def lib():
         L.ref_envelope_marks.restype = C.c_long
         L.ref_envelope_marks.argtypes = [C.c_void_p, f32p, C.c_long, i32p, C.c_long, C.c_void_p, f32p]
         L.ref_encode_dsp_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, i32p, i32p, i32p, f32p]
+        L.ref_encode_dsp_managed_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, C.c_void_p, i32p, i32p, i32p, f32p]
         _lib = L
     return _lib
 
@@ -124,9 +129,11 @@ class Ref:
     """One reference encoder instance: vorbis_encode_init_vbr(channels, rate, quality).
     dropin=True uses the CUDA-shimmed build and attaches the device context."""
 
-    def __init__(self, channels=2, rate=44100, quality=0.5, dropin=False, device=0):
+    def __init__(self, channels=2, rate=44100, quality=0.5, dropin=False, device=0, nominal_bitrate=None):
+        """nominal_bitrate (bits/s): a bitrate-managed encoder (vorbis_encode_init) instead of VBR quality"""
         self.L = dropin_lib() if dropin else lib()
-        self.h = self.L.ref_open(channels, rate, quality)
+        self.h = (self.L.ref_open(channels, rate, quality) if nominal_bitrate is None
+                  else self.L.ref_open_managed(channels, rate, int(nominal_bitrate)))
         if not self.h:
             raise RuntimeError("reference refused setup (ch=%d rate=%d q=%g)" % (channels, rate, quality))
         self.channels, self.rate, self.quality = channels, rate, quality
@@ -299,6 +306,20 @@ class Ref:
                "iwork": np.zeros((nb, ch, N // 2), np.int32), "ampmax_out": np.zeros(nb, np.float32)}
         self.L.ref_encode_dsp_batch(self.h, W, nb, pcm, desc.ctypes.data, out["posts"], out["nonzero"],
                                     out["iwork"], out["ampmax_out"])
+        return out
+
+    def encode_dsp_managed_batch(self, W, pcm, desc):
+        """bitrate-managed mapping0_forward with the reference's own functions (ref_encode_dsp_managed_batch):
+        blob-major posts [15][nb][ch][65], nonzero [15][nb][ch], iwork [15][nb][ch][n]"""
+        ch, N = self.channels, self.bs[W]
+        pcm = np.ascontiguousarray(pcm, np.float32).reshape(-1, ch, N)
+        nb = pcm.shape[0]
+        desc = np.ascontiguousarray(desc, abi.BLOCKDESC_DTYPE)
+        NB = abi.PACKETBLOBS
+        out = {"posts": np.zeros((NB, nb, ch, 65), np.int32), "nonzero": np.zeros((NB, nb, ch), np.int32),
+               "iwork": np.zeros((NB, nb, ch, N // 2), np.int32), "ampmax_out": np.zeros(nb, np.float32)}
+        self.L.ref_encode_dsp_managed_batch(self.h, W, nb, pcm, desc.ctypes.data, out["posts"], out["nonzero"],
+                                            out["iwork"], out["ampmax_out"])
         return out
 
     # ---- full API capture ----------------------------------------------------

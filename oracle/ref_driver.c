@@ -72,6 +72,24 @@ void *ref_open(int channels, long rate, float quality){
   return h;
 }
 
+/* a bitrate-managed encoder (vorbis_encode_init with a nominal bitrate: lib/vorbisenc.c:1199-1222): mapping0_forward
+ * then builds all PACKETBLOBS packets per block and lib/bitrate.c picks one */
+void *ref_open_managed(int channels, long rate, long nominal_bitrate){
+  ref_handle *h = (ref_handle*)calloc(1, sizeof(*h));
+  vorbis_info_init(&h->vi);
+  if(vorbis_encode_init(&h->vi, channels, rate, -1, nominal_bitrate, -1)){
+    vorbis_info_clear(&h->vi);
+    free(h);
+    return NULL;
+  }
+  vorbis_comment_init(&h->vc);
+  vorbis_analysis_init(&h->vd, &h->vi);
+  vorbis_block_init(&h->vd, &h->vb);
+  h->channels = channels;
+  h->rate = rate;
+  return h;
+}
+
 void ref_close(void *hv){
   ref_handle *h = (ref_handle*)hv;
   int i;
@@ -796,6 +814,105 @@ void ref_encode_dsp_batch(void *hv, int W, int nblocks, const float *pcm, const 
   }
   oggpack_writeclear(&opb);
   free(mdct); free(logmdct); free(logmask); free(m); free(iw); free(nz);
+}
+
+
+/* ---- bitrate-managed mode: what mapping0_forward does when vorbis_bitrate_managed(vb)
+ * (lib/mapping0.c:500-573 and the per-blob loop :596-646), with the reference's own functions in the
+ * reference's order: middle fit, then - where it exists - mask 2 + fit, mask 0 + fit, the twelve
+ * floor1_interpolate_fit curves; per blob k floor1_encode (its bits go to a scratch buffer) and
+ * _vp_couple_quantize_normalize(k).  Outputs blob-major: posts [15][rows][65] (0 where NULL),
+ * nonzero [15][rows], iwork [15][rows][n].  Pins oracle/pyoracle.py: encode_dsp_managed.          */
+extern int *floor1_interpolate_fit(vorbis_block *vb,vorbis_look_floor1 *look,int *A,int *B,int del);
+void ref_encode_dsp_managed_batch(void *hv, int W, int nblocks, const float *pcm, const vb200_block_desc *desc,
+                                  int32_t *posts_out, int32_t *nonzero_out, int32_t *iwork_out, float *ampmax_out){
+  ref_handle *h = (ref_handle*)hv;
+  codec_setup_info *ci = (codec_setup_info*)h->vi.codec_setup;
+  private_state *b = (private_state*)h->vd.backend_state;
+  vorbis_info_mapping0 *info = (vorbis_info_mapping0*)ci->map_param[ci->mode_param[W]->mapping];
+  int ch = h->vi.channels, N = (int)ci->blocksizes[W], n = N/2, blk, i, j, k;
+  size_t rows = (size_t)nblocks*ch;
+  float *work = (float*)malloc(sizeof(float)*N*ch);
+  float *gmdct = (float*)malloc(sizeof(float)*n*ch);
+  float *noise = (float*)malloc(sizeof(float)*n);
+  float *tone = (float*)malloc(sizeof(float)*n);
+  float *lmax = (float*)malloc(sizeof(float)*ch);
+  float **m = (float**)malloc(sizeof(*m)*ch);
+  int   **iw = (int**)malloc(sizeof(*iw)*ch);
+  int    *nz = (int*)malloc(sizeof(int)*ch);
+  int ***floor_posts = (int***)malloc(sizeof(*floor_posts)*ch);
+  oggpack_buffer opb;
+  oggpack_writeinit(&opb);
+  for(i=0;i<ch;i++) floor_posts[i] = (int**)malloc(sizeof(int*)*PACKETBLOBS);
+  h->vb.W = W;
+  h->vb.pcmend = N;
+  for(blk=0;blk<nblocks;blk++){
+    vorbis_look_psy *psy_look = b->psy+desc[blk].blocktype+(W?2:0);
+    float gmax = desc[blk].ampmax;
+    for(i=0;i<ch;i++){
+      float scale=4.f/N, scale_dB, *p = work+(size_t)i*N, *gm = gmdct+(size_t)i*n;
+      memcpy(p,pcm+((size_t)blk*ch+i)*N,sizeof(float)*N);
+      scale_dB=todB(&scale)+.345;
+      _vorbis_apply_window(p,b->window,ci->blocksizes,desc[blk].lW,W,desc[blk].nW);
+      mdct_forward((mdct_lookup*)b->transform[W][0],p,gm);
+      drft_forward(&b->fft_look[W],p);
+      p[0]=scale_dB+todB(p)+.345;
+      lmax[i]=p[0];
+      for(j=1;j<N-1;j+=2){
+        float t=p[j]*p[j]+p[j+1]*p[j+1];
+        t=p[(j+1)>>1]=scale_dB+.5f*todB(&t)+.345;
+        if(t>lmax[i])lmax[i]=t;
+      }
+      if(lmax[i]>0.f)lmax[i]=0.f;
+      if(lmax[i]>gmax)gmax=lmax[i];
+    }
+    for(i=0;i<ch;i++){
+      int submap = info->chmuxlist[i];
+      vorbis_look_floor1 *look = (vorbis_look_floor1*)b->flr[info->floorsubmap[submap]];
+      float *p = work+(size_t)i*N, *gm = gmdct+(size_t)i*n;
+      float *logmdct = p+n, *logmask = p;
+      for(k=0;k<PACKETBLOBS;k++) floor_posts[i][k]=NULL;
+      for(j=0;j<n;j++) logmdct[j]=todB(gm+j)+.345;
+      _vp_noisemask(psy_look,logmdct,noise);
+      _vp_tonemask(psy_look,p,tone,gmax,lmax[i]);
+      _vp_offset_and_mix(psy_look,noise,tone,1,logmask,gm,logmdct);
+      floor_posts[i][PACKETBLOBS/2]=floor1_fit(&h->vb,look,logmdct,logmask);
+      if(floor_posts[i][PACKETBLOBS/2]){
+        _vp_offset_and_mix(psy_look,noise,tone,2,logmask,gm,logmdct);
+        floor_posts[i][PACKETBLOBS-1]=floor1_fit(&h->vb,look,logmdct,logmask);
+        _vp_offset_and_mix(psy_look,noise,tone,0,logmask,gm,logmdct);
+        floor_posts[i][0]=floor1_fit(&h->vb,look,logmdct,logmask);
+        for(k=1;k<PACKETBLOBS/2;k++)
+          floor_posts[i][k]=floor1_interpolate_fit(&h->vb,look,floor_posts[i][0],floor_posts[i][PACKETBLOBS/2],
+                                                   k*65536/(PACKETBLOBS/2));
+        for(k=PACKETBLOBS/2+1;k<PACKETBLOBS-1;k++)
+          floor_posts[i][k]=floor1_interpolate_fit(&h->vb,look,floor_posts[i][PACKETBLOBS/2],floor_posts[i][PACKETBLOBS-1],
+                                                   (k-PACKETBLOBS/2)*65536/(PACKETBLOBS/2));
+      }
+    }
+    ampmax_out[blk]=gmax;
+    for(k=0;k<PACKETBLOBS;k++){
+      oggpack_reset(&opb);
+      for(i=0;i<ch;i++){
+        int submap = info->chmuxlist[i];
+        vorbis_look_floor1 *look = (vorbis_look_floor1*)b->flr[info->floorsubmap[submap]];
+        size_t row = (size_t)blk*ch+i;
+        int32_t *po = posts_out+((size_t)k*rows+row)*65;
+        m[i] = gmdct+(size_t)i*n;
+        iw[i] = (int*)(iwork_out+((size_t)k*rows+row)*n);
+        nz[i] = floor1_encode(&opb,&h->vb,look,floor_posts[i][k],iw[i]);
+        for(j=0;j<65;j++) po[j]=0;
+        if(floor_posts[i][k]) for(j=0;j<look->posts;j++) po[j]=floor_posts[i][k][j];
+      }
+      _vp_couple_quantize_normalize(k,&ci->psy_g_param,psy_look,info,m,iw,nz,
+                                    ci->psy_g_param.sliding_lowpass[W][k],ch);
+      for(i=0;i<ch;i++) nonzero_out[(size_t)k*rows+(size_t)blk*ch+i]=nz[i];
+    }
+    _vorbis_block_ripcord(&h->vb);
+  }
+  oggpack_writeclear(&opb);
+  for(i=0;i<ch;i++) free(floor_posts[i]);
+  free(floor_posts); free(work); free(gmdct); free(noise); free(tone); free(lmax); free(m); free(iw); free(nz);
 }
 
 

@@ -78,6 +78,35 @@ def test_block_seam_packets_identical(cuda_ok, ch, rate, q):
     ref.close()
 
 
+@pytest.mark.parametrize("ch,rate,nominal", [(2, 44100, 128000), (1, 44100, 64000)])
+def test_block_seam_managed_packets_identical(cuda_ok, ch, rate, nominal):
+    """bitrate-managed encoders (vorbis_encode_init with a nominal bitrate) through the same seam: ONE
+    vb200_encode_dsp_managed call per block returns all 15 curves (three masks and fits, twelve interpolated
+    curves, render + couple/quantise per curve), the host writes all 15 packet blobs with the reference's own
+    floor1_encode / residue forward, and lib/bitrate.c picks among them - the packets that come out must be
+    byte-identical to the stock encoder's."""
+    if not (pyref.available() and pyref.dropin_available()):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    pcm = probe_signal(ch, rate, 0.5, seed=6)
+    pcm[:, 6000:9000] = 0
+    ref = pyref.Ref(ch, rate, nominal_bitrate=nominal)
+    ref.encode_capture(pcm, fields=())
+    want = ref.packets()
+    enc = pyref.Ref(ch, rate, nominal_bitrate=nominal, dropin=True)
+    enc.L.ref_use_block_seam(1)
+    try:
+        nb = enc.L.ref_encode_capture(enc.h, np.ascontiguousarray(pcm, np.float32), pcm.shape[1], None, None)
+    finally:
+        enc.L.ref_use_block_seam(0)
+    got = enc.packets()
+    assert nb > 0 and len(got) == len(want) and len(want) > 10
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, "packet %d differs" % i
+    assert len(set(len(p) for p in want)) > 3
+    enc.close()
+    ref.close()
+
+
 @pytest.mark.parametrize("ch,rate,q", [(2, 44100, 0.5), (1, 22050, 0.3)])
 def test_multistream_driver_packets_identical(cuda_ok, ch, rate, q):
     """vb200ms_*: 7 concurrent encoders whose ready blocks go to the device together (one vb200_encode_dsp call per

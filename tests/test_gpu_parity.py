@@ -601,6 +601,42 @@ def test_encode_dsp_many_chunks(cfg, ramp, monkeypatch):
         _enc_compare(got, want, "many chunks ramp=%s rep=%d" % (ramp, rep))
 
 
+@pytest.mark.parametrize("W", [0, 1])
+def test_encode_dsp_managed_vs_oracle(cfg, W):
+    """bitrate-managed mode (vb200_encode_dsp_managed): the 15 curves of every block - posts, nonzero flags and
+    quantised residue of each - against the composed oracle (pinned on the reference's own functions in
+    tests/test_oracle_vs_ref.py::test_managed_chain_vs_reference); streams with an ampmax chain, mixed block
+    types, a silent stream (all 15 curves NULL) and a nearly silent one"""
+    name, setup, ctx, o, _, _ = cfg
+    N, ch = setup.blocksize(W), setup.channels
+    hop, ns, bps = N // 2, 5, 3
+    stride = (bps - 1) * hop + N
+    rng = np.random.default_rng(555 + W)
+    t = np.arange(stride)
+    s16 = np.clip(5000 * rng.standard_normal((ns, stride, ch)) * rng.uniform(0.02, 1.5, (ns, 1, 1)) +
+                  9000 * np.sin(2 * np.pi * 440.0 * t / setup.rate)[None, :, None], -32768, 32767).astype(np.int16)
+    s16[1] = 0
+    s16[3] = (s16[3] // 2000).astype(np.int16)
+    planar = np.ascontiguousarray((s16.astype(np.float32) / np.float32(32768.0)).transpose(0, 2, 1))
+    blocks = np.stack([planar[s, :, k * hop:k * hop + N] for s in range(ns) for k in range(bps)])
+    desc = np.zeros(ns * bps, abi.BLOCKDESC_DTYPE)
+    desc["lW"] = W; desc["nW"] = W
+    desc["blocktype"] = rng.integers(0, 2, ns * bps)
+    amp0 = rng.uniform(-40, -3, ns).astype(np.float32)
+    want = o.encode_dsp_managed(W, blocks, desc, streams=(ns, bps), ampmax0=amp0)
+    got = ctx.encode_dsp_managed(W, s16, desc, nstreams=ns, fmt=vlib.PCM_S16_INTERLEAVED, hop=hop, ampmax0=amp0,
+                                 independent=False)
+    for k in ("posts", "nonzero", "iwork"):
+        assert np.array_equal(got[k], want[k]), "%s: %d diffs" % (k, int((got[k] != want[k]).sum()))
+    assert_bits_equal(got["ampmax_out"], want["ampmax_out"], "ampmax_out")
+    assert not got["nonzero"][:, bps:2 * bps].any(), "the silent stream has no curve at any rate"
+    # the middle curve is what the un-managed call produces
+    one = ctx.encode_dsp(W, s16, desc, nstreams=ns, fmt=vlib.PCM_S16_INTERLEAVED, hop=hop, ampmax0=amp0, independent=False)
+    mid = abi.PACKETBLOBS // 2
+    for k in ("posts", "nonzero", "iwork"):
+        assert np.array_equal(got[k][mid], one[k]), "curve 7 vs vb200_encode_dsp: " + k
+
+
 def test_encode_dsp_device_pointers_and_errors(cfg):
     import torch
     name, setup, ctx, o, enc, _ = cfg

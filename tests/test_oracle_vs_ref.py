@@ -166,6 +166,42 @@ def test_encode_chain_vs_reference(args, oracle_lib):
     r.close()
 
 
+@pytest.mark.parametrize("args", [(2, 44100, 0.5), (1, 44100, 0.4), (6, 48000, 0.2)], ids=lambda g: "ch%d_%d_q%g" % g)
+def test_managed_chain_vs_reference(args, oracle_lib):
+    """bitrate-managed mode: the composed oracle (three masks, three fits, twelve interpolated curves, render +
+    couple/quantise per curve; what vb200_encode_dsp_managed is checked against) equals the reference's own
+    functions called in mapping0_forward's managed order (lib/mapping0.c:500-573, 596-646), incl. silent blocks
+    (NULL curves) and both block sizes"""
+    ch, rate, q = args
+    r = pyref.Ref(ch, rate, q)
+    o = oracle_lib.Oracle(r.setup())
+    pcm = probe_signal(ch, rate, 0.6, seed=21)
+    pcm[:, 5000:9000] = 0
+    cap = r.encode_capture(pcm)
+    nulls = 0
+    for W in (0, 1):
+        idx = np.where(cap["W"] == W)[0][:10]
+        if not len(idx):
+            continue
+        N = r.bs[W]
+        desc = np.zeros(len(idx), abi.BLOCKDESC_DTYPE)
+        for k in ("lW", "nW", "blocktype"):
+            desc[k] = cap[k][idx]
+        desc["ampmax"] = cap["ampmax_in"][idx]
+        blocks = np.ascontiguousarray(cap["pcm"][idx][:, :, :N])
+        a = o.encode_dsp_managed(W, blocks, desc)
+        b = r.encode_dsp_managed_batch(W, blocks, desc)
+        for k in ("posts", "nonzero", "iwork"):
+            assert np.array_equal(a[k], b[k]), (k, W)
+        assert_bits_equal(a["ampmax_out"], b["ampmax_out"], "ampmax_out")
+        mid = abi.PACKETBLOBS // 2
+        assert np.array_equal(a["iwork"][mid], o.encode_dsp(W, blocks, desc)["iwork"]), "curve 7 is the un-managed chain"
+        assert not np.array_equal(a["iwork"][0], a["iwork"][abi.PACKETBLOBS - 1]), "low and high rate curves differ"
+        nulls += int((a["posts"].reshape(abi.PACKETBLOBS, -1, abi.FLOOR1_STRIDE)[:, :, :2] == 0).all(axis=2).sum())
+    assert nulls > 0, "the probe holds silent blocks"
+    r.close()
+
+
 @pytest.mark.parametrize("args", [(2, 44100, 0.5), (1, 44100, 0.4), (6, 48000, 0.2), (1, 22050, 0.3), (2, 32000, 0.0),
                                   (2, 96000, 0.7)], ids=lambda g: "ch%d_%d_q%g" % g)
 def test_envelope_vs_reference(args, oracle_lib):

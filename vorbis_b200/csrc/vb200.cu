@@ -24,6 +24,7 @@
 #include "vb200_env.cuh"
 #include "vb200_res.cuh"
 #include "vb200_streams.cuh"
+#include "vb200_managed.cuh"
 #include "floor1_db_table.h"
 
 using namespace vb200;
@@ -76,6 +77,7 @@ struct vb200_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   DevBuf enc_buf[8];                 // scratch of vb200_encode_dsp_dev
   DevBuf str_buf[40];                // scratch of vb200_plan_blocks / vb200_encode_streams[_dev]
+  DevBuf mgd_buf[24];                // scratch + host-call staging of vb200_encode_dsp_managed[_dev]
   // vb200_encode_dsp (host buffers): chunks rotate over ENC_SETS buffer sets; one stream per copy direction and
   // two compute streams, ordered by events (see there)
   DevBuf enc_lane[4][17];
@@ -399,6 +401,7 @@ extern "C" void vb200_ctx_destroy(vb200_ctx *c) {
   for (auto &b : c->enc_buf) if (b.p) cudaFree(b.p);
   for (auto &b : c->env_buf) if (b.p) cudaFree(b.p);
   for (auto &l : c->enc_lane) for (auto &b : l) if (b.p) cudaFree(b.p);
+  for (auto &b : c->mgd_buf) if (b.p) cudaFree(b.p);
   for (auto &b : c->str_buf) if (b.p) cudaFree(b.p);
   for (auto &st : c->s_enc) if (st) cudaStreamDestroy(st);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -1880,6 +1883,113 @@ extern "C" int vb200_encode_dsp_dev(vb200_ctx *c, int W, int nstreams, int bps, 
   }
   c->grid_div = 1;
   return scratch_end(c, user);
+}
+
+// ---- bitrate-managed mode (lib/mapping0.c:507-573, 596-646): the chain above with three masks, three fits, the
+// twelve interpolated curves, and the floor render + couple/quantise/normalise of every one of the 15 curves
+static int managed_check(vb200_ctx *c, int W, int nstreams, int bps, const vb200_encode_io *io) {
+  int rc;
+  if ((rc = enc_check(c, W, nstreams, bps, VB200_PACKETBLOBS / 2, io))) return rc;
+  if (io->iwork_fmt != VB200_IWORK_S32) return fail(VB200_EINVAL, "managed mode writes int32 residue");
+  if (io->classes) return fail(VB200_EINVAL, "managed mode does not classify");
+  return 0;
+}
+
+extern "C" int vb200_encode_dsp_managed_dev(vb200_ctx *c, int W, int nstreams, int bps, const vb200_encode_io *d,
+                                            void *stream) {
+  CHECK_CTX(c); CHECK_W(W);
+  int rc;
+  if ((rc = managed_check(c, W, nstreams, bps, d))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ch = c->setup.channels, n = c->dx[W].N / 2, nblocks = nstreams * bps;
+  const size_t rows = (size_t)nblocks * ch, big = sizeof(float) * rows * n;
+  constexpr int NB = VB200_PACKETBLOBS, MID = VB200_PACKETBLOBS / 2;
+  DevBuf *B = c->mgd_buf;
+  void *p;
+  float *mdct, *logmdct, *logmask, *logfft, *lmax, *gmax, *noise, *tone, *alt;
+  int32_t *fz3, *present;
+  if ((rc = ensure_buf(B[0], big, &p))) return rc; mdct = (float *)p;
+  if ((rc = ensure_buf(B[1], big, &p))) return rc; logmdct = (float *)p;
+  if ((rc = ensure_buf(B[2], big, &p))) return rc; logmask = (float *)p;
+  if ((rc = ensure_buf(B[3], big, &p))) return rc; logfft = (float *)p;
+  if ((rc = ensure_buf(B[4], sizeof(float) * rows, &p))) return rc; lmax = (float *)p;
+  if ((rc = ensure_buf(B[5], sizeof(float) * nblocks, &p))) return rc; gmax = (float *)p;
+  if ((rc = ensure_buf(B[6], big, &p))) return rc; noise = (float *)p;
+  if ((rc = ensure_buf(B[7], big, &p))) return rc; tone = (float *)p;
+  if ((rc = ensure_buf(B[8], big, &p))) return rc; alt = (float *)p;
+  if ((rc = ensure_buf(B[9], sizeof(int32_t) * rows * 3, &p))) return rc; fz3 = (int32_t *)p;
+  if ((rc = ensure_buf(B[10], sizeof(int32_t) * rows * NB, &p))) return rc; present = (int32_t *)p;
+  if ((rc = scratch_begin(c, st))) return rc;
+  vb200_phaseA_io a;
+  memset(&a, 0, sizeof(a));
+  a.desc = d->desc; a.mdct = mdct; a.logmdct = logmdct; a.logmask = logmask; a.ampmax_out = d->ampmax_out;
+  a.tap_noise = noise; a.tap_tone = tone;
+  PcmSrc ps; const PcmSrc *pp = nullptr;
+  if (d->pcm_fmt == VB200_PCM_F32_BLOCKS) a.pcm = (const float *)d->pcm;
+  else { ps.base = d->pcm; ps.fmt = d->pcm_fmt; ps.bps = bps; ps.hop = d->hop; ps.stride = d->stream_stride; ps.blk_src = nullptr; pp = &ps; }
+  if ((rc = phaseA_launch(c, W, nblocks, &a, d->independent ? 0 : nstreams, bps, d->ampmax0, st, logfft, lmax, gmax, pp)))
+    return rc;
+  const size_t pblob = rows * VB200_FLOOR1_STRIDE;
+  int32_t *fz_lo = fz3, *fz_mid = fz3 + rows, *fz_hi = fz3 + 2 * rows;
+  // the middle curve (select 1, what un-managed mode codes), then the low-noise (2) and high-noise (0) masks
+  if ((rc = vb200_floor1_fit_dev(c, W, -1, (int)rows, logmdct, logmask, d->posts + MID * pblob, fz_mid, st))) return rc;
+  const PsyDev &P0 = c->dpsy[(W ? 2 : 0)], &P1 = c->dpsy[(W ? 2 : 0) + 1];
+  const long long total = (long long)rows * n;
+  for (int pass = 0; pass < 2; pass++) {
+    const int sel = pass ? 0 : 2;
+    k_mix_select<<<grid_for(c, (int)((total + 255) / 256), 8), 256, 0, st>>>(P0, P1, d->desc, ch, total, sel, noise, tone,
+                                                                            logmdct, alt);
+    if ((rc = post_launch(c))) return rc;
+    if ((rc = vb200_floor1_fit_dev(c, W, -1, (int)rows, logmdct, alt, d->posts + (sel ? NB - 1 : 0) * pblob,
+                                   sel ? fz_hi : fz_lo, st))) return rc;
+  }
+  k_floor1_interpolate<<<grid_for(c, (int)((rows * VB200_FLOOR1_STRIDE + 255) / 256), 8), 256, 0, st>>>(
+      (long long)rows, d->posts, fz_lo, fz_mid, fz_hi, present);
+  if ((rc = post_launch(c))) return rc;
+  for (int k = 0; k < NB; k++) {
+    int32_t *iw = (int32_t *)d->iwork + (size_t)k * rows * n, *nz = d->nonzero + (size_t)k * rows;
+    if ((rc = vb200_floor1_render_dev(c, W, -1, (int)rows, d->posts + k * pblob, present + (size_t)k * rows, iw, nz, st)))
+      return rc;
+    CqnDev Q0, Q1;
+    if ((rc = cqn_setup(c, W, 0, k, &Q0))) return rc;
+    if ((rc = cqn_setup(c, W, 1, k, &Q1))) return rc;
+    if ((rc = cqn_launch(c, Q0, Q1, d->desc, nblocks, mdct, iw, nz, st))) return rc;
+  }
+  return scratch_end(c, st);
+}
+
+// host buffers: one synchronous H2D - compute - D2H round trip (managed mode is not the throughput path)
+extern "C" int vb200_encode_dsp_managed(vb200_ctx *c, int W, int nstreams, int bps, const vb200_encode_io *h) {
+  CHECK_CTX(c); CHECK_W(W);
+  int rc;
+  if ((rc = managed_check(c, W, nstreams, bps, h))) return rc;
+  std::lock_guard<std::mutex> lk(c->mu);
+  const int ch = c->setup.channels, N = c->dx[W].N, n = N / 2;
+  const size_t nb = (size_t)nstreams * bps, rows = nb * ch;
+  constexpr int NB = VB200_PACKETBLOBS;
+  cudaStream_t st = c->s_main;
+  DevBuf *B = c->mgd_buf;
+  void *p;
+  vb200_encode_io d = *h;
+  d.mdct = d.logmdct = d.logmask = nullptr;
+  const size_t pcm_bytes = enc_pcm_bytes(h, ch, N, nstreams, bps);
+  if ((rc = ensure_buf(B[12], pcm_bytes, &p))) return rc; d.pcm = p;
+  if ((rc = ensure_buf(B[13], sizeof(vb200_block_desc) * nb, &p))) return rc; d.desc = (const vb200_block_desc *)p;
+  if ((rc = ensure_buf(B[14], sizeof(float) * nstreams, &p))) return rc; d.ampmax0 = h->ampmax0 ? (const float *)p : nullptr;
+  if ((rc = ensure_buf(B[15], sizeof(int32_t) * NB * rows * VB200_FLOOR1_STRIDE, &p))) return rc; d.posts = (int32_t *)p;
+  if ((rc = ensure_buf(B[16], sizeof(int32_t) * NB * rows, &p))) return rc; d.nonzero = (int32_t *)p;
+  if ((rc = ensure_buf(B[17], sizeof(int32_t) * NB * rows * n, &p))) return rc; d.iwork = p;
+  if ((rc = ensure_buf(B[18], sizeof(float) * nb, &p))) return rc; d.ampmax_out = (float *)p;
+  CU(cudaMemcpyAsync((void *)d.pcm, h->pcm, pcm_bytes, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync((void *)d.desc, h->desc, sizeof(vb200_block_desc) * nb, cudaMemcpyHostToDevice, st));
+  if (h->ampmax0) CU(cudaMemcpyAsync((void *)d.ampmax0, h->ampmax0, sizeof(float) * nstreams, cudaMemcpyHostToDevice, st));
+  if ((rc = vb200_encode_dsp_managed_dev(c, W, nstreams, bps, &d, st))) return rc;
+  CU(cudaMemcpyAsync(h->posts, d.posts, sizeof(int32_t) * NB * rows * VB200_FLOOR1_STRIDE, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->nonzero, d.nonzero, sizeof(int32_t) * NB * rows, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->iwork, d.iwork, sizeof(int32_t) * NB * rows * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h->ampmax_out, d.ampmax_out, sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
 }
 
 extern "C" int vb200_encode_dsp(vb200_ctx *c, int W, int nstreams, int bps, int blobno, const vb200_encode_io *h) {

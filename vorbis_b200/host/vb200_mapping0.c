@@ -21,8 +21,9 @@
  * have written for the fit (its own render into a scratch curve is redundant host work of ~n integer ops per
  * channel; the curve the residue was built from is the device's).  No reference source is restated here.
  *
- * Un-managed bitrate only (vorbis_encode_init_vbr): the managed mode's extra fits and blobs are not built,
- * forward returns OV_EIMPL there.  A CUDA failure surfaces as OV_EFAULT from vorbis_analysis and latches in
+ * Bitrate-managed encoders (vorbis_encode_init) take the same seam: one vb200_encode_dsp_managed call per block
+ * returns all PACKETBLOBS curves and the host writes all PACKETBLOBS packets (the multi-stream driver below is
+ * un-managed only).  A CUDA failure surfaces as OV_EFAULT from vorbis_analysis and latches in
  * the binding (vb200shim_error).  Compiled like any libvorbis-internal backend against lib/codec_internal.h
  * (oracle/Makefile target `dropin`); INTEGRATION.md shows the registry line a maintainer changes.
  */
@@ -67,13 +68,13 @@ extern int floor1_encode(oggpack_buffer *opb, vorbis_block *vb, vorbis_look_floo
 
 /* ---- host half of one block: header bits, floor bits, residue bits -----------------------------------------
  * posts [ch][VB200_FLOOR1_STRIDE], nonzero [ch] (after coupling), iwork [ch][n]: what vb200_encode_dsp returned */
-static int pack_block(vorbis_block *vb, const int32_t *posts, const int32_t *nonzero_dev, int32_t *iwork_dev){
+static int pack_block_blob(vorbis_block *vb, int k, const int32_t *posts, const int32_t *nonzero_dev, const int32_t *iwork_dev){
   vorbis_dsp_state *vd = vb->vd;
   vorbis_info *vi = vd->vi;
   codec_setup_info *ci = (codec_setup_info*)vi->codec_setup;
   private_state *b = (private_state*)vd->backend_state;
   vorbis_block_internal *vbi = (vorbis_block_internal*)vb->internal;
-  const int ch = vi->channels, n = vb->pcmend/2, k = PACKETBLOBS/2;
+  const int ch = vi->channels, n = vb->pcmend/2;
   const int modenumber = (int)vb->W;
   vorbis_info_mapping0 *info = (vorbis_info_mapping0*)ci->map_param[modenumber];
   oggpack_buffer *opb = vbi->packetblob[k];
@@ -128,6 +129,10 @@ static int pack_block(vorbis_block *vb, const int32_t *posts, const int32_t *non
     _residue_P[ci->residue_type[resnum]]->forward(opb, vb, b->residue[resnum], couple_bundle, zerobundle, ch_in_bundle, classifications, i);
   }
   return 0;
+}
+
+static int pack_block(vorbis_block *vb, const int32_t *posts, const int32_t *nonzero_dev, int32_t *iwork_dev){
+  return pack_block_blob(vb, PACKETBLOBS/2, posts, nonzero_dev, iwork_dev);    /* un-managed: the middle curve only */
 }
 
 /* ---- device half for a set of blocks of ONE size ------------------------------------------------------------ */
@@ -200,10 +205,50 @@ static int forward_batch(vb200_binding *bind, ms_batch *B, vorbis_block **blocks
 /* ---- seam 1: vorbis_func_mapping ---------------------------------------------------------------------------- */
 static ms_batch g_single[2];                                   /* the single-block path's staging (one per block size) */
 
+/* bitrate-managed mode (lib/mapping0.c:507-573, 596-687): ONE vb200_encode_dsp_managed call gives the posts, nonzero
+ * flags and quantised residue of all PACKETBLOBS curves of the block; the host then writes packetblob[k] for every k
+ * exactly as it writes the single packet of un-managed mode.  lib/bitrate.c picks among them afterwards. */
+static int forward_managed(vb200_binding *bind, vorbis_block *vb){
+  static __thread int32_t *posts, *nonzero, *iwork; static __thread float *pcm; static __thread size_t cap;
+  vorbis_info *vi = vb->vd->vi;
+  vorbis_block_internal *vbi = (vorbis_block_internal*)vb->internal;
+  const int ch = vi->channels, N = (int)vb->pcmend, n = N/2, W = (int)vb->W;
+  const size_t need = (size_t)ch*N;
+  vb200_encode_io io;
+  vb200_block_desc desc;
+  float ampmax;
+  int c, k, rc;
+  if(cap < need){
+    free(posts); free(nonzero); free(iwork); free(pcm);
+    pcm = (float*)malloc(sizeof(float)*need);
+    posts = (int32_t*)malloc(sizeof(int32_t)*PACKETBLOBS*ch*VB200_FLOOR1_STRIDE);
+    nonzero = (int32_t*)malloc(sizeof(int32_t)*PACKETBLOBS*ch);
+    iwork = (int32_t*)malloc(sizeof(int32_t)*PACKETBLOBS*ch*n);
+    cap = (pcm && posts && nonzero && iwork) ? need : 0;
+    if(!cap) return OV_EFAULT;
+  }
+  for(c = 0; c < ch; c++) memcpy(pcm + (size_t)c*N, vb->pcm[c], sizeof(float)*N);
+  desc.lW = (int32_t)vb->lW; desc.nW = (int32_t)vb->nW; desc.blocktype = vbi->blocktype; desc.ampmax = vbi->ampmax;
+  memset(&io, 0, sizeof(io));
+  io.pcm = pcm; io.pcm_fmt = VB200_PCM_F32_BLOCKS; io.desc = &desc; io.independent = 1;
+  io.posts = posts; io.nonzero = nonzero; io.iwork = iwork; io.ampmax_out = &ampmax;
+  rc = vb200_encode_dsp_managed(vb200shim_ctx(bind), W, 1, 1, &io);
+  if(rc){
+    vb200shim_set_error(bind, rc);
+    fprintf(stderr, "vb200 mapping0: vb200_encode_dsp_managed failed (%d): %s\n", rc, vb200_last_error());
+    return OV_EFAULT;
+  }
+  vbi->ampmax = ampmax;                                        /* lib/mapping0.c:576 */
+  for(k = 0; k < PACKETBLOBS; k++)
+    if((rc = pack_block_blob(vb, k, posts + (size_t)k*ch*VB200_FLOOR1_STRIDE, nonzero + (size_t)k*ch, iwork + (size_t)k*ch*n)))
+      return rc;
+  return 0;
+}
+
 static int vb200_mapping0_forward(vorbis_block *vb){
   vb200_binding *bind = vb200shim_binding(vb->vd);
   if(!bind){ fprintf(stderr, "vb200 mapping0: vorbis_dsp_state is not attached (vb200shim_attach)\n"); return OV_EFAULT; }
-  if(vorbis_bitrate_managed(vb)) return OV_EIMPL;              /* the managed-mode fits/blobs are not built on the device */
+  if(vorbis_bitrate_managed(vb)) return forward_managed(bind, vb);
   return forward_batch(bind, &g_single[vb->W ? 1 : 0], &vb, 1, (int)vb->W, NULL, NULL);
 }
 static void vb_pack(vorbis_info *vi, vorbis_info_mapping *vm, oggpack_buffer *opb){ mapping0_exportbundle.pack(vi, vm, opb); }

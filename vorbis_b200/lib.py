@@ -31,7 +31,7 @@ EXPORTS = [
     "vb200_couple_quantize_normalize_dev", "vb200_couple_quantize_normalize",
     "vb200_synthesis_dev", "vb200_synthesis", "vb200_decouple_dev", "vb200_decouple",
     "vb200_floor1_fit_dev", "vb200_floor1_fit", "vb200_floor1_render_dev", "vb200_floor1_render",
-    "vb200_encode_dsp_dev", "vb200_encode_dsp",
+    "vb200_encode_dsp_dev", "vb200_encode_dsp", "vb200_encode_dsp_managed_dev", "vb200_encode_dsp_managed",
     "vb200_envelope_search_dev", "vb200_envelope_search", "vb200_envelope_search_var", "vb200_envelope_apply_marks",
     "vb200_floor1_inverse2_dev", "vb200_floor1_inverse2", "vb200_decode_dsp_dev", "vb200_decode_dsp",
     "vb200_residue_partvals", "vb200_residue_classify_dev", "vb200_residue_classify",
@@ -98,6 +98,8 @@ def load():
     L.vb200_floor1_render.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     L.vb200_encode_dsp_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO), vp]
     L.vb200_encode_dsp.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO)]
+    L.vb200_encode_dsp_managed.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO)]
+    L.vb200_encode_dsp_managed_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(abi.EncodeIO), vp]
     L.vb200_residue_partvals.argtypes = [vp, C.c_int]
     L.vb200_residue_classify_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, vp]
     L.vb200_residue_classify.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, C.c_int]
@@ -427,6 +429,44 @@ class Context:
         for k, v in out.items():
             setattr(io, k, v.ctypes.data)
         self._chk(self.L.vb200_encode_dsp(self.h, W, nstreams, bps, blobno, C.byref(io)))
+        return out
+
+    def encode_dsp_managed(self, W, pcm, desc, nstreams=None, fmt=0, hop=0, ampmax0=None, independent=None):
+        """Bitrate-managed mode (vb200_encode_dsp_managed): the 15 curves of every block.  Inputs as encode_dsp;
+        returns posts [15][nb][ch][FLOOR1_STRIDE], nonzero [15][nb][ch], iwork [15][nb][ch][n], ampmax_out [nb]."""
+        ch, N = self.channels, self.bs[W]
+        n = N // 2
+        desc = np.ascontiguousarray(desc, abi.BLOCKDESC_DTYPE)
+        nb = desc.shape[0]
+        if nstreams is None:
+            nstreams = nb
+            if independent is None:
+                independent = True
+        bps = nb // nstreams
+        assert bps * nstreams == nb
+        io = abi.EncodeIO()
+        if fmt == 0:
+            pcm = np.ascontiguousarray(pcm, np.float32).reshape(nb, ch, N)
+        elif fmt == PCM_F32_PLANAR:
+            pcm = np.ascontiguousarray(pcm, np.float32)
+            assert pcm.shape[:2] == (nstreams, ch)
+            io.stream_stride = pcm.shape[2]
+        else:
+            pcm = np.ascontiguousarray(pcm, np.int16)
+            assert pcm.shape[0] == nstreams and pcm.shape[2] == ch
+            io.stream_stride = pcm.shape[1]
+        io.pcm, io.pcm_fmt, io.hop = pcm.ctypes.data, fmt, hop
+        io.desc = desc.ctypes.data
+        io.independent = 1 if independent else 0
+        if ampmax0 is not None:
+            ampmax0 = np.ascontiguousarray(ampmax0, np.float32)
+            io.ampmax0 = ampmax0.ctypes.data
+        NB = abi.PACKETBLOBS
+        out = {"posts": np.full((NB, nb, ch, abi.FLOOR1_STRIDE), -1, np.int32), "nonzero": np.full((NB, nb, ch), -1, np.int32),
+               "iwork": np.full((NB, nb, ch, n), -1, np.int32), "ampmax_out": np.zeros(nb, np.float32)}
+        for k, v in out.items():
+            setattr(io, k, v.ctypes.data)
+        self._chk(self.L.vb200_encode_dsp_managed(self.h, W, nstreams, bps, C.byref(io)))
         return out
 
     def encode_dsp_dev(self, W, nstreams, bps, io, blobno=7, stream=None):
