@@ -63,6 +63,10 @@ def test_transforms_vs_oracle_random(cfg, W):
     assert_bits_equal(ctx.apply_window(W, x, lW, nW), o.apply_window(W, x, lW, nW), "window")
     # empty batch is a no-op
     assert ctx.mdct_forward(W, np.zeros((0, N), np.float32)).shape == (0, N // 2)
+    # more vectors than resident CTAs (148 SMs x 8): every CTA walks several vectors, the next one staged by
+    # cp.async while the current one is transformed
+    big = rng.uniform(-1, 1, (4000, N)).astype(np.float32)
+    assert_bits_equal(ctx.mdct_forward(W, big), o.mdct_forward(W, big), "mdct_forward, 4000 vectors")
 
 
 @pytest.mark.parametrize("tag", ["L", "S"])

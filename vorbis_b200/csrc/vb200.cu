@@ -478,12 +478,23 @@ __global__ void __launch_bounds__(256)
 k_mdct_forward(XformDev X, int nvec, const float *__restrict__ in, float *__restrict__ out) {
   extern __shared__ __align__(16) float sm[];
   const int N = NC ? NC : X.N, tid = threadIdx.x, nt = blockDim.x;
-  float *sx = sm, *sw = sm + N;
-  for (int v = blockIdx.x; v < nvec; v += gridDim.x) {
-    const float4 *src = reinterpret_cast<const float4 *>(in + (size_t)v * N);
-    for (int i = tid; i < (N >> 2); i += nt) reinterpret_cast<float4 *>(sx)[i] = __ldg(src + i);
+  // two input buffers: the NEXT vector of this CTA travels global -> shared with cp.async (LDGSTS, no registers)
+  // while this one is transformed; the padded hand-over buffer keeps the bit-reverse gather conflict free
+  float *sx[2] = {sm, sm + N};
+  float *sw = sm + 2 * N, *pad = sm + 3 * N;
+  auto stage = [&](float *dst, int v) {
+    const float *src = in + (size_t)v * N;
+    const unsigned d = smem_u32(dst);
+    for (int i = tid; i < (N >> 2); i += nt) cp_async16(d + 16u * (unsigned)i, src + 4 * i);
+    cp_async_commit();
+  };
+  int v = blockIdx.x, buf = 0;
+  if (v < nvec) stage(sx[0], v);
+  for (; v < nvec; v += gridDim.x, buf ^= 1) {
+    cp_async_wait_all();
     __syncthreads();
-    dev_mdct_forward<NC>(X, sx, sw, out + (size_t)v * (N >> 1), tid, nt);
+    if (v + (int)gridDim.x < nvec) stage(sx[buf ^ 1], v + gridDim.x);
+    dev_mdct_forward<NC>(X, sx[buf], sw, out + (size_t)v * (N >> 1), tid, nt, pad);
     __syncthreads();
   }
 }
@@ -980,7 +991,7 @@ extern "C" int vb200_mdct_forward_dev(vb200_ctx *c, int W, int nvec, const float
   CHECK_CTX(c); CHECK_W(W);
   if (nvec <= 0) return 0;
   const XformDev &X = c->dx[W];
-  const size_t smem = sizeof(float) * 2 * X.N;
+  const size_t smem = sizeof(float) * (3 * (size_t)X.N + (X.N / 2 + X.N / 32 + X.N / 512 + 8));   // 2 x in, work, padded hand-over
   const int nt = threads_for(X.N);
   const int grid = grid_for(c, nvec, 8);
   int rc;
