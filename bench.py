@@ -382,6 +382,33 @@ def extra_configs(torch, lib, abi, device, peak):
     ms_e = timed(lambda: c44.envelope_search_dev(nse, pe.data_ptr(), lib.PCM_S16_INTERLEAVED, stride_e, 0, steps,
                                                  st_e.data_ptr(), ret_e.data_ptr(), stream=stream))
     out["envelope_search_1000streams_x800steps_s16"] = {"ms": ms_e, "long_block_equivalents_per_s": nse * steps / 16 / ms_e * 1e3}
+    # bitrate-managed mode: all 15 rate curves of every block, device resident
+    nbm, Nm, chm = 4000, bs[1], s44.channels
+    nm = Nm // 2
+    pm = synth_pcm_torch(torch, nbm, chm, Nm, 44100, dev, 77)
+    dm = torch.from_numpy(make_desc(nbm).view(np.uint8)).to(dev)
+    rows_m = nbm * chm
+    NBm = abi.PACKETBLOBS
+    posts_m = torch.empty((NBm, rows_m, abi.FLOOR1_STRIDE), dtype=torch.int32, device=dev)
+    nz_m = torch.empty((NBm, rows_m), dtype=torch.int32, device=dev)
+    iw_m = torch.empty((NBm, rows_m, nm), dtype=torch.int32, device=dev)
+    amp_m = torch.empty(nbm, dtype=torch.float32, device=dev)
+    iom = abi.EncodeIO()
+    iom.pcm, iom.pcm_fmt, iom.desc, iom.independent = pm.data_ptr(), 0, dm.data_ptr(), 1
+    iom.posts, iom.nonzero, iom.iwork, iom.ampmax_out = posts_m.data_ptr(), nz_m.data_ptr(), iw_m.data_ptr(), amp_m.data_ptr()
+    Lm = lib.load()
+
+    def run_managed():
+        rc = Lm.vb200_encode_dsp_managed_dev(c44.h, 1, nbm, 1, C.byref(iom), stream)
+        if rc:
+            raise RuntimeError("vb200_encode_dsp_managed_dev failed: %d" % rc)
+    try:
+        ms_m = timed(run_managed, reps=3)
+        out["managed_mode_4000_long_stereo_15curves"] = {"ms": ms_m, "stereo_blocks_per_s": nbm / ms_m * 1e3,
+                                                         "curves_per_s": nbm * NBm / ms_m * 1e3}
+    except Exception as e:                                   # informational leg: never take the headline down
+        out["managed_mode_4000_long_stereo_15curves"] = {"error": str(e)}
+    del posts_m, nz_m, iw_m, pm
     # Phase A alone through vb200_analysis_phaseA with float host buffers (the round-1 e2e figure, kept for
     # continuity: 16 KB in + 24.6 KB out per block instead of 4 KB + 8.4 KB for the one-call chain)
     nb, N, chn = 20000, bs[1], s44.channels
