@@ -605,8 +605,9 @@ def test_encode_dsp_many_chunks(cfg, ramp, monkeypatch):
         _enc_compare(got, want, "many chunks ramp=%s rep=%d" % (ramp, rep))
 
 
+@pytest.mark.parametrize("fmt", ["s16", "blocks"])
 @pytest.mark.parametrize("W", [0, 1])
-def test_encode_dsp_managed_vs_oracle(cfg, W):
+def test_encode_dsp_managed_vs_oracle(cfg, W, fmt):
     """bitrate-managed mode (vb200_encode_dsp_managed): the 15 curves of every block - posts, nonzero flags and
     quantised residue of each - against the composed oracle (pinned on the reference's own functions in
     tests/test_oracle_vs_ref.py::test_managed_chain_vs_reference); streams with an ampmax chain, mixed block
@@ -628,8 +629,11 @@ def test_encode_dsp_managed_vs_oracle(cfg, W):
     desc["blocktype"] = rng.integers(0, 2, ns * bps)
     amp0 = rng.uniform(-40, -3, ns).astype(np.float32)
     want = o.encode_dsp_managed(W, blocks, desc, streams=(ns, bps), ampmax0=amp0)
-    got = ctx.encode_dsp_managed(W, s16, desc, nstreams=ns, fmt=vlib.PCM_S16_INTERLEAVED, hop=hop, ampmax0=amp0,
-                                 independent=False)
+    if fmt == "s16":
+        got = ctx.encode_dsp_managed(W, s16, desc, nstreams=ns, fmt=vlib.PCM_S16_INTERLEAVED, hop=hop, ampmax0=amp0,
+                                     independent=False)
+    else:
+        got = ctx.encode_dsp_managed(W, blocks, desc, nstreams=ns, ampmax0=amp0, independent=False)
     for k in ("posts", "nonzero", "iwork"):
         assert np.array_equal(got[k], want[k]), "%s: %d diffs" % (k, int((got[k] != want[k]).sum()))
     assert_bits_equal(got["ampmax_out"], want["ampmax_out"], "ampmax_out")
